@@ -1,0 +1,495 @@
+// C-ABI of the B200-native FastDiff sampling path (see include/fastdiff_b200.h) and the per-step
+// kernel schedule.  No PyTorch types, no host synchronisation, no allocation after load_weights.
+#include "../../include/fastdiff_b200.h"
+#include "fd_blob.h"
+#include "fd_common.cuh"
+#include "fd_kernels_simt.cuh"
+#ifndef FD_EMU
+#include "fd_kernels_tc.cuh"
+#endif
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+using namespace fd;
+
+struct fd_handle {
+    int device = 0;
+    float* blob = nullptr;       // device copy of the packed weights
+    size_t blob_floats = 0;
+    uint64_t sec_off[FD_S_COUNT];
+    uint64_t sec_cnt[FD_S_COUNT];
+    float final_w[7 * C];        // host copies of tiny tensors passed by value
+    float final_b = 0.f;
+    int mode = FD_MODE_FP32_SIMT;
+    int stop_after = 99;
+    int attrs_set = 0;
+    uint64_t launches = 0;
+    std::string err;
+    void* tc_state = nullptr;    // tensor-core path resources (tensor maps etc.)
+};
+
+static std::string g_create_err;
+
+static int fail(fd_handle* h, int code, const char* fmt, ...) {
+    char buf[640];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define FD_CUDA(h, call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return fail(h, FD_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+static const float* sec(const fd_handle* h, int s) { return h->blob + h->sec_off[s]; }
+
+// ---- workspace layout (floats) ------------------------------------------------------------------
+struct WsLayout {
+    size_t emb, cnoise, hk, kern, d0, d1, d2, xa, xb, total;
+};
+static WsLayout ws_layout(int B, int Tm) {
+    WsLayout w;
+    auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };  // 256-byte granules
+    const size_t L = (size_t)Tm * HOP_TOTAL;
+    size_t o = 0;
+    w.emb = o;    o += al((size_t)B * EMB_OUT);
+    w.cnoise = o; o += al((size_t)NBLK * B * COND);
+    w.hk = o;     o += al((size_t)NBLK * B * (Tm + 2) * HID);
+    w.kern = o;   o += al((size_t)NBLK * B * Tm * KCN);
+    w.d0 = o;     o += al((size_t)B * (L / 4) * C);
+    w.d1 = o;     o += al((size_t)B * (L / 32) * C);
+    w.d2 = o;     o += al((size_t)B * Tm * C);
+    w.xa = o;     o += al((size_t)B * L * C);
+    w.xb = o;     o += al((size_t)B * L * C);
+    w.total = o;
+    return w;
+}
+
+// ---- API -----------------------------------------------------------------------------------------
+extern "C" const char* fd_version(void) { return "fastdiff_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* fd_last_error(fd_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int fd_create(const fd_config* cfg, int device, fd_handle** out) {
+    if (!cfg || !out) return fail(nullptr, FD_ERR_INVALID, "fd_create: null argument");
+    const bool ok = cfg->audio_channels == 1 && cfg->inner_channels == C && cfg->cond_channels == COND &&
+                    cfg->n_upsample == NBLK && cfg->upsample_ratios[0] == 8 && cfg->upsample_ratios[1] == 8 &&
+                    cfg->upsample_ratios[2] == 4 && cfg->lvc_layers_each_block == LAYERS && cfg->lvc_kernel_size == KS &&
+                    cfg->kpnet_hidden_channels == HID && cfg->kpnet_conv_size == 3 &&
+                    cfg->diffusion_step_embed_dim_in == EMB_IN && cfg->diffusion_step_embed_dim_mid == EMB_MID &&
+                    cfg->diffusion_step_embed_dim_out == EMB_OUT;
+    if (!ok)
+        return fail(nullptr, FD_ERR_UNSUPPORTED,
+                    "fd_create: only the architecture of modules/FastDiff/config/base.yaml:21-33 is built "
+                    "(C=32, cond=80, ratios 8/8/4, 4 LVC layers k=3, kpnet 64/3, embed 128/512/512)");
+#ifndef FD_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+        return fail(nullptr, FD_ERR_CUDA, "fd_create: no usable CUDA device (index %d of %d)", device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, FD_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, FD_ERR_UNSUPPORTED, "fd_create: kernels are built for sm_100a only (device is sm_%d%d)",
+                    prop.major, prop.minor);
+#endif
+    fd_handle* h = new fd_handle();
+    h->device = device;
+    *out = h;
+    return FD_OK;
+}
+
+extern "C" void fd_destroy(fd_handle* h) {
+    if (!h) return;
+#ifndef FD_EMU
+    cudaSetDevice(h->device);
+    tc_destroy(h->tc_state);
+#endif
+    if (h->blob) cudaFree(h->blob);
+    delete h;
+}
+
+static int parse_header(fd_handle* h, const uint64_t* hdr, size_t bytes) {
+    if (bytes < 24 || hdr[0] != FD_BLOB_MAGIC) return fail(h, FD_ERR_INVALID, "weight blob: bad magic");
+    if (hdr[1] != FD_BLOB_VERSION) return fail(h, FD_ERR_INVALID, "weight blob: version %ld, library expects %ld", (long)hdr[1], (long)FD_BLOB_VERSION);
+    if (hdr[2] != FD_S_COUNT) return fail(h, FD_ERR_INVALID, "weight blob: %ld sections, library expects %ld", (long)hdr[2], (long)FD_S_COUNT);
+    if (bytes < (3 + 2 * (size_t)FD_S_COUNT) * 8) return fail(h, FD_ERR_INVALID, "weight blob: truncated header");
+    for (int s = 0; s < FD_S_COUNT; ++s) {
+        h->sec_off[s] = hdr[3 + 2 * s];
+        h->sec_cnt[s] = hdr[4 + 2 * s];
+        if ((h->sec_off[s] + h->sec_cnt[s]) * 4 > bytes || (h->sec_off[s] & 63))
+            return fail(h, FD_ERR_INVALID, "weight blob: section %d out of range or misaligned", s);
+    }
+    // expected sizes of the sections whose shapes the kernels hard-code
+    struct { int s; size_t n; } chk[] = {
+        {FD_S_EMB_FREQ, 64}, {FD_S_FC1_WT, (size_t)EMB_IN * EMB_MID}, {FD_S_FC2_WT, (size_t)EMB_MID * EMB_OUT},
+        {FD_S_FIRST_W, 7 * C}, {FD_S_FINAL_W, 7 * C}, {FD_S_DB0_CONV_W, 3 * KK * C}, {FD_S_LB0_UP_W, 16 * C * C},
+        {FD_S_LB2_UP_W, 8 * C * C}, {FD_S_LB0_CONV_W, (size_t)LAYERS * KK * C}, {FD_S_LB0_KPIN_W, 5 * COND * HID},
+        {FD_S_LB0_KPRES_W, 6 * 3 * HID * HID}, {FD_S_LB0_KC_W, (size_t)KCK * KCN}, {FD_S_LB2_KC_B, KCN}};
+    for (auto& c : chk)
+        if (h->sec_cnt[c.s] != c.n) return fail(h, FD_ERR_INVALID, "weight blob: section %d has the wrong size (%ld)", c.s, (long)h->sec_cnt[c.s]);
+    return FD_OK;
+}
+
+static int finish_load(fd_handle* h, const uint64_t* hdr_host) {
+    (void)hdr_host;
+    return FD_OK;
+}
+
+extern "C" int fd_load_weights(fd_handle* h, const void* blob_host, size_t bytes) {
+    if (!h || !blob_host) return fail(h, FD_ERR_INVALID, "fd_load_weights: null argument");
+    int rc = parse_header(h, (const uint64_t*)blob_host, bytes);
+    if (rc) return rc;
+    FD_CUDA(h, cudaSetDevice(h->device));
+    if (h->blob) { cudaFree(h->blob); h->blob = nullptr; }
+    FD_CUDA(h, cudaMalloc((void**)&h->blob, bytes));
+    FD_CUDA(h, cudaMemcpy(h->blob, blob_host, bytes, cudaMemcpyHostToDevice));
+    h->blob_floats = bytes / 4;
+    const float* hb = (const float*)blob_host;
+    memcpy(h->final_w, hb + h->sec_off[FD_S_FINAL_W], sizeof h->final_w);
+    h->final_b = hb[h->sec_off[FD_S_FINAL_B]];
+#ifndef FD_EMU
+    rc = tc_init(&h->tc_state, h->device, h->blob, h->sec_off, h->err);
+    if (rc) return rc;
+#endif
+    return finish_load(h, (const uint64_t*)blob_host);
+}
+
+extern "C" int fd_load_weights_dev(fd_handle* h, const void* blob_dev, size_t bytes, void* stream) {
+    if (!h || !blob_dev) return fail(h, FD_ERR_INVALID, "fd_load_weights_dev: null argument");
+    FD_CUDA(h, cudaSetDevice(h->device));
+    const size_t hdr_bytes = (3 + 2 * (size_t)FD_S_COUNT) * 8;
+    if (bytes < hdr_bytes) return fail(h, FD_ERR_INVALID, "weight blob: truncated header");
+    uint64_t* hdr = (uint64_t*)malloc(hdr_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    FD_CUDA(h, cudaMemcpyAsync(hdr, blob_dev, hdr_bytes, cudaMemcpyDeviceToHost, st));
+    FD_CUDA(h, cudaStreamSynchronize(st));
+    int rc = parse_header(h, hdr, bytes);
+    free(hdr);
+    if (rc) return rc;
+    if (h->blob) { cudaFree(h->blob); h->blob = nullptr; }
+    FD_CUDA(h, cudaMalloc((void**)&h->blob, bytes));
+    FD_CUDA(h, cudaMemcpyAsync(h->blob, blob_dev, bytes, cudaMemcpyDeviceToDevice, st));
+    FD_CUDA(h, cudaMemcpyAsync(h->final_w, (const float*)blob_dev + h->sec_off[FD_S_FINAL_W], sizeof h->final_w, cudaMemcpyDeviceToHost, st));
+    FD_CUDA(h, cudaMemcpyAsync(&h->final_b, (const float*)blob_dev + h->sec_off[FD_S_FINAL_B], 4, cudaMemcpyDeviceToHost, st));
+    FD_CUDA(h, cudaStreamSynchronize(st));
+    h->blob_floats = bytes / 4;
+#ifndef FD_EMU
+    rc = tc_init(&h->tc_state, h->device, h->blob, h->sec_off, h->err);
+    if (rc) return rc;
+#endif
+    return FD_OK;
+}
+
+extern "C" int fd_workspace_bytes(fd_handle* h, int B, int Tm, size_t* out) {
+    if (!h || !out || B < 1 || Tm < 1) return fail(h, FD_ERR_INVALID, "fd_workspace_bytes: bad argument");
+    *out = ws_layout(B, Tm).total * 4;
+    return FD_OK;
+}
+
+extern "C" int fd_set_mode(fd_handle* h, int mode) {
+    if (!h) return FD_ERR_INVALID;
+    if (mode < FD_MODE_FP32_SIMT || mode > FD_MODE_TC_TF32) return fail(h, FD_ERR_INVALID, "fd_set_mode: unknown mode %d", mode);
+#ifdef FD_EMU
+    if (mode != FD_MODE_FP32_SIMT) return fail(h, FD_ERR_UNSUPPORTED, "fd_set_mode: the emulation build has no tensor-core path");
+#else
+    if (mode != FD_MODE_FP32_SIMT && !tc_available(h->tc_state))
+        return fail(h, FD_ERR_UNSUPPORTED, "fd_set_mode: tensor-core path unavailable (load weights first)");
+#endif
+    h->mode = mode;
+    return FD_OK;
+}
+extern "C" int fd_get_mode(fd_handle* h) { return h ? h->mode : FD_ERR_INVALID; }
+
+extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
+    if (!h || !key) return FD_ERR_INVALID;
+    if (!strcmp(key, "stop_after")) { h->stop_after = (int)value; return FD_OK; }
+    return fail(h, FD_ERR_INVALID, "fd_set_option: unknown key '%s'", key);
+}
+
+extern "C" uint64_t fd_launch_count(fd_handle* h) { return h ? h->launches : 0; }
+
+// ---- kernel attribute setup (dynamic smem opt-in), once per handle --------------------------------
+template <typename K>
+static cudaError_t set_smem(K kern, int bytes) {
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+static int setup_attrs(fd_handle* h) {
+    if (h->attrs_set) return FD_OK;
+    FD_CUDA(h, set_smem(k_kp_hidden, KP_SMEM_BYTES));
+    FD_CUDA(h, set_smem(k_dblock<4, true>, db_smem_bytes<4>()));
+    FD_CUDA(h, set_smem(k_dblock<8, false>, db_smem_bytes<8>()));
+    FD_CUDA(h, set_smem(k_lvc_layer<8, 64, false>, lvc_smem_bytes<8, 64>()));
+    FD_CUDA(h, set_smem(k_lvc_layer<64, 128, false>, lvc_smem_bytes<64, 128>()));
+    FD_CUDA(h, set_smem(k_lvc_layer<256, 256, true>, lvc_smem_bytes<256, 256>()));
+    h->attrs_set = 1;
+    return FD_OK;
+}
+
+#define FD_CHECK_LAUNCH(h, name)                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = cudaGetLastError();                                                  \
+        if (e_ != cudaSuccess) return fail(h, FD_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+        h->launches++;                                                                        \
+    } while (0)
+
+// One evaluation of the denoiser, leaving h_final (B,L,32) in ws.xa.  t_dev may be null (t_scalar used).
+static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, const float* t_dev, float t_scalar,
+                        int B, int Tm, float* ws, cudaStream_t st) {
+    const WsLayout w = ws_layout(B, Tm);
+    const int L = Tm * HOP_TOTAL;
+    float* emb = ws + w.emb; float* cnoise = ws + w.cnoise; float* hk = ws + w.hk; float* kern = ws + w.kern;
+    float* d0 = ws + w.d0; float* d1 = ws + w.d1; float* d2 = ws + w.d2; float* xa = ws + w.xa; float* xb = ws + w.xb;
+
+    // -- step embedding + per-block condition offsets
+    {
+        EmbedParams p;
+        p.freq = sec(h, FD_S_EMB_FREQ);
+        p.w1t = sec(h, FD_S_FC1_WT); p.b1 = sec(h, FD_S_FC1_B);
+        p.w2t = sec(h, FD_S_FC2_WT); p.b2 = sec(h, FD_S_FC2_B);
+        for (int n = 0; n < NBLK; ++n) {
+            p.fct_wt[n] = sec(h, FD_S_LB0_FCT_WT + n * FD_LB_STRIDE);
+            p.fct_b[n] = sec(h, FD_S_LB0_FCT_B + n * FD_LB_STRIDE);
+        }
+        FD_LAUNCH(k_embed, dim3(B), dim3(512), 0, st, p, t_dev, t_scalar, emb, cnoise, B);
+        FD_CHECK_LAUNCH(h, "k_embed");
+    }
+    // -- kernel predictor: hidden stack, then kernel_conv+bias_conv GEMM (all three blocks per launch)
+    {
+        KpParams p;
+        for (int n = 0; n < NBLK; ++n) {
+            p.in_w[n] = sec(h, FD_S_LB0_KPIN_W + n * FD_LB_STRIDE);   p.in_b[n] = sec(h, FD_S_LB0_KPIN_B + n * FD_LB_STRIDE);
+            p.res_w[n] = sec(h, FD_S_LB0_KPRES_W + n * FD_LB_STRIDE); p.res_b[n] = sec(h, FD_S_LB0_KPRES_B + n * FD_LB_STRIDE);
+        }
+        FD_LAUNCH(k_kp_hidden, dim3((Tm + KP_FT - 1) / KP_FT, B, NBLK), dim3(256), KP_SMEM_BYTES, st, p, mel_dev, cnoise, hk, B, Tm);
+        FD_CHECK_LAUNCH(h, "k_kp_hidden");
+    }
+    if (h->mode == FD_MODE_FP32_SIMT) {
+        KcParams p;
+        for (int n = 0; n < NBLK; ++n) { p.w[n] = sec(h, FD_S_LB0_KC_W + n * FD_LB_STRIDE); p.b[n] = sec(h, FD_S_LB0_KC_B + n * FD_LB_STRIDE); }
+        const int M = B * (Tm + 2) - 2;
+        FD_LAUNCH(k_kc_gemm_simt, dim3(KCN / 128, (M + 127) / 128, NBLK), dim3(256), 0, st, p, hk, kern, B, Tm);
+        FD_CHECK_LAUNCH(h, "k_kc_gemm_simt");
+    } else {
+#ifndef FD_EMU
+        int rc = tc_kc_gemm(h->tc_state, h->mode, hk, kern, B, Tm, st, h->err, &h->launches);
+        if (rc) return rc;
+#endif
+    }
+    if (h->stop_after <= 1) return FD_OK;
+
+    // -- first_audio_conv + the three DiffusionDBlocks
+    {
+        DbParams p;
+        p.first_w = sec(h, FD_S_FIRST_W); p.first_b = sec(h, FD_S_FIRST_B);
+        const float* ins[3] = {x_dev, d0, d1};
+        float* outs[3] = {d0, d1, d2};
+        const int tin[3] = {L, L / 4, L / 32}, tout[3] = {L / 4, L / 32, L / 256};
+        for (int n = 0; n < NBLK; ++n) {
+            p.res_w = sec(h, FD_S_DB0_RES_W + n * FD_DB_STRIDE);   p.res_b = sec(h, FD_S_DB0_RES_B + n * FD_DB_STRIDE);
+            p.conv_w = sec(h, FD_S_DB0_CONV_W + n * FD_DB_STRIDE); p.conv_b = sec(h, FD_S_DB0_CONV_B + n * FD_DB_STRIDE);
+            const dim3 grid((tout[n] + DB_TO - 1) / DB_TO, B);
+            if (n == 0) { auto k = k_dblock<4, true>;  FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<4>(), st, p, ins[n], outs[n], tin[n], tout[n]); }
+            else        { auto k = k_dblock<8, false>; FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<8>(), st, p, ins[n], outs[n], tin[n], tout[n]); }
+            FD_CHECK_LAUNCH(h, "k_dblock");
+        }
+    }
+    if (h->stop_after <= 2) return FD_OK;
+
+    // -- the three TimeAware_LVCBlocks
+    const float* blk_in = d2;
+    int Tin = Tm;
+    float* cur = xa; float* oth = xb;
+    for (int n = 0; n < NBLK; ++n) {
+        const int r = ratio_of(n), T = Tin * r;
+        const float* upw = sec(h, FD_S_LB0_UP_W + n * FD_LB_STRIDE);
+        const float* upb = sec(h, FD_S_LB0_UP_B + n * FD_LB_STRIDE);
+        {
+            const dim3 grid((Tin + 31) / 32, B);
+            if (r == 8) { auto k = k_upsample<8>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
+            else        { auto k = k_upsample<4>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
+            FD_CHECK_LAUNCH(h, "k_upsample");
+        }
+        const float* skip = (n == 0) ? d1 : (n == 1 ? d0 : x_dev);
+        const float* kern_n = kern + (size_t)n * B * Tm * KCN;
+        for (int i = 0; i < LAYERS; ++i) {
+            LvcParams p;
+            p.conv_w = sec(h, FD_S_LB0_CONV_W + n * FD_LB_STRIDE) + i * KK * C;
+            p.conv_b = sec(h, FD_S_LB0_CONV_B + n * FD_LB_STRIDE) + i * C;
+            p.first_w = sec(h, FD_S_FIRST_W); p.first_b = sec(h, FD_S_FIRST_B);
+            int dil = 1; for (int q = 0; q < i; ++q) dil *= 3;
+            const float* kl = kern_n + i * KPL;
+            bool done = false;
+#ifndef FD_EMU
+            if (h->mode != FD_MODE_FP32_SIMT) {
+                int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done);
+                if (rc) return rc;
+            }
+#endif
+            if (!done) {
+                if (n == 0)      { auto k = k_lvc_layer<8, 64, false>;    FD_LAUNCH(k, dim3((T + 63) / 64, B), dim3(256), (lvc_smem_bytes<8, 64>()), st, p, cur, skip, kl, oth, T, Tm, dil); }
+                else if (n == 1) { auto k = k_lvc_layer<64, 128, false>;  FD_LAUNCH(k, dim3((T + 127) / 128, B), dim3(256), (lvc_smem_bytes<64, 128>()), st, p, cur, skip, kl, oth, T, Tm, dil); }
+                else             { auto k = k_lvc_layer<256, 256, true>;  FD_LAUNCH(k, dim3((T + 255) / 256, B), dim3(256), (lvc_smem_bytes<256, 256>()), st, p, cur, skip, kl, oth, T, Tm, dil); }
+                FD_CHECK_LAUNCH(h, "k_lvc_layer");
+            }
+            float* tmp = cur; cur = oth; oth = tmp;
+        }
+        if (h->stop_after <= 3 + n) return FD_OK;
+        blk_in = cur;   // block output lives in `cur`; the next block upsamples it into the other buffer
+        Tin = T;
+        float* tmp = cur; cur = oth; oth = tmp;
+    }
+    return FD_OK;
+}
+
+// After run_denoiser the last block's output is in xa (up -> xa; 4 layers: xa->xb->xa->xb->xa ... per block the
+// parity of buffer swaps is fixed, see final_buffer()).
+static float* final_buffer(float* ws, int B, int Tm) {
+    // block 0: up->xa, layers end in xa; swap -> cur=xb. block 1: up->xb, ends in xb; swap -> cur=xa.
+    // block 2: up->xa, ends in xa.
+    return ws + ws_layout(B, Tm).xa;
+}
+static float* block_out_buffer(float* ws, int B, int Tm, int n) {
+    const WsLayout w = ws_layout(B, Tm);
+    return ws + (n == 1 ? w.xb : w.xa);
+}
+
+static int check_args(fd_handle* h, const void* a, const void* b, const void* c, int B, int Tm, void* ws, size_t ws_bytes) {
+    if (!h) return FD_ERR_INVALID;
+    if (!h->blob) return fail(h, FD_ERR_STATE, "weights not loaded (call fd_load_weights first)");
+    if (!a || !b || !c || !ws) return fail(h, FD_ERR_INVALID, "null device pointer");
+    if (B < 1 || Tm < 1) return fail(h, FD_ERR_INVALID, "bad shape: B=%d T'=%d", B, Tm);
+    if ((size_t)B * Tm * HOP_TOTAL > 0x7fffffffULL / 4) return fail(h, FD_ERR_INVALID, "B*L too large for 32-bit indexing of one call; split the batch");
+    if (ws_bytes < ws_layout(B, Tm).total * 4) return fail(h, FD_ERR_INVALID, "workspace too small: %ld bytes given, %ld needed", (long)ws_bytes, (long)(ws_layout(B, Tm).total * 4));
+    return FD_OK;
+}
+
+static void fill_final(const fd_handle* h, FinalParams& fp) {
+    memcpy(fp.w, h->final_w, sizeof fp.w);
+    fp.b = h->final_b;
+    fp.mode = 0; fp.coef = 0; fp.div = 1; fp.sigma = 0; fp.c1 = fp.c2 = fp.c3 = 0; fp.add_noise = 0; fp.draw = 0; fp.seed = 0;
+}
+
+extern "C" int fd_denoise(fd_handle* h, const float* x_dev, const float* mel_dev, const float* t_dev, float* eps_dev,
+                          int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    int rc = check_args(h, x_dev, mel_dev, t_dev, B, Tm, workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    if (!eps_dev) return fail(h, FD_ERR_INVALID, "null device pointer");
+    FD_CUDA(h, cudaSetDevice(h->device));
+    rc = setup_attrs(h);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)workspace_dev;
+    const WsLayout w = ws_layout(B, Tm);
+    FD_CUDA(h, cudaMemsetAsync(ws + w.hk, 0, (size_t)NBLK * B * (Tm + 2) * HID * 4, st));
+    rc = run_denoiser(h, x_dev, mel_dev, t_dev, 0.f, B, Tm, ws, st);
+    if (rc) return rc;
+    if (h->stop_after < 6) return FD_OK;
+    FinalParams fp;
+    fill_final(h, fp);
+    const int L = Tm * HOP_TOTAL;
+    FD_LAUNCH(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), x_dev, (const float*)nullptr, eps_dev, (float*)nullptr, L);
+    FD_CHECK_LAUNCH(h, "k_final");
+    return FD_OK;
+}
+
+extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const fd_step* steps, int n_steps,
+                         const float* noise_dev, int n_noise, uint64_t seed, int fill_xT, int ddim, float* seq_dev,
+                         int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    int rc = check_args(h, x_dev, mel_dev, steps, B, Tm, workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    if (n_steps < 0) return fail(h, FD_ERR_INVALID, "n_steps < 0");
+    int need = 0;
+    if (!ddim) for (int i = 0; i < n_steps; ++i) need += steps[i].add_noise ? 1 : 0;
+    if (noise_dev && n_noise < need) return fail(h, FD_ERR_INVALID, "noise_dev holds %d draws, the schedule needs %d", n_noise, need);
+    FD_CUDA(h, cudaSetDevice(h->device));
+    rc = setup_attrs(h);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)workspace_dev;
+    const WsLayout w = ws_layout(B, Tm);
+    const int L = Tm * HOP_TOTAL;
+    const size_t n = (size_t)B * L;
+    FD_CUDA(h, cudaMemsetAsync(ws + w.hk, 0, (size_t)NBLK * B * (Tm + 2) * HID * 4, st));
+    if (fill_xT) {
+        FD_LAUNCH(k_fill_normal, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x_dev, n, seed, 0u);
+        FD_CHECK_LAUNCH(h, "k_fill_normal");
+    }
+    if (seq_dev) FD_CUDA(h, cudaMemcpyAsync(seq_dev, x_dev, n * 4, cudaMemcpyDeviceToDevice, st));
+    int draw = 0;
+    for (int i = 0; i < n_steps; ++i) {
+        rc = run_denoiser(h, x_dev, mel_dev, nullptr, steps[i].t, B, Tm, ws, st);
+        if (rc) return rc;
+        FinalParams fp;
+        fill_final(h, fp);
+        const float* z = nullptr;
+        if (ddim) {
+            fp.mode = 2; fp.c1 = steps[i].c1; fp.c2 = steps[i].c2; fp.c3 = steps[i].c3;
+        } else {
+            fp.mode = 1; fp.coef = steps[i].coef_eps; fp.div = steps[i].div; fp.sigma = steps[i].sigma;
+            fp.add_noise = steps[i].add_noise ? 1 : 0;
+            if (fp.add_noise) {
+                if (noise_dev) z = noise_dev + (size_t)draw * n;
+                fp.draw = (uint32_t)(draw + 1); fp.seed = seed;
+                ++draw;
+            }
+        }
+        // in-place: every thread reads only its own x element
+        FD_LAUNCH(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), (const float*)x_dev, z, x_dev,
+                  seq_dev ? seq_dev + (size_t)(i + 1) * n : (float*)nullptr, L);
+        FD_CHECK_LAUNCH(h, "k_final");
+    }
+    return FD_OK;
+}
+
+extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, size_t* count, int B, int Tm,
+                             void* workspace_dev, void* stream) {
+    if (!h || !name || !count || !workspace_dev) return fail(h, FD_ERR_INVALID, "fd_debug_read: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)workspace_dev;
+    const WsLayout w = ws_layout(B, Tm);
+    const size_t L = (size_t)Tm * HOP_TOTAL;
+    const size_t len = strlen(name);
+    const int n = (len > 0 && name[len - 1] >= '0' && name[len - 1] <= '2') ? name[len - 1] - '0' : -1;
+    auto gather = [&](const float* src, int T, int Cn, int row_stride, size_t item_stride, int off) -> int {
+        *count = (size_t)B * Cn * T;
+        if (!out_dev) return FD_OK;
+        FD_LAUNCH(k_cl_to_ncl, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, src, out_dev, B, T, Cn, row_stride, (int)item_stride, off);
+        FD_CHECK_LAUNCH(h, "k_cl_to_ncl");
+        return FD_OK;
+    };
+    if (!strcmp(name, "embed")) {
+        *count = (size_t)B * EMB_OUT;
+        if (out_dev) FD_CUDA(h, cudaMemcpyAsync(out_dev, ws + w.emb, *count * 4, cudaMemcpyDeviceToDevice, st));
+        return FD_OK;
+    }
+    if (!strncmp(name, "down", 4) && n >= 0) {
+        const size_t T = n == 0 ? L / 4 : (n == 1 ? L / 32 : L / 256);
+        const float* src = ws + (n == 0 ? w.d0 : (n == 1 ? w.d1 : w.d2));
+        return gather(src, (int)T, C, C, T * C, 0);
+    }
+    if (!strncmp(name, "kp_hidden", 9) && n >= 0)
+        return gather(ws + w.hk + (size_t)n * B * (Tm + 2) * HID, Tm, HID, HID, (size_t)(Tm + 2) * HID, HID);
+    if (!strncmp(name, "lvc", 3) && n >= 0) {
+        const size_t T = (size_t)Tm * hop_of(n);
+        return gather(block_out_buffer(ws, B, Tm, n), (int)T, C, C, T * C, 0);
+    }
+    if ((!strncmp(name, "kernels", 7) || !strncmp(name, "kbias", 5)) && n >= 0) {
+        const int want_bias = name[1] == 'b';
+        *count = want_bias ? (size_t)B * LAYERS * LVC_OUT * Tm : (size_t)B * LAYERS * C * LVC_OUT * KS * Tm;
+        if (!out_dev) return FD_OK;
+        FD_LAUNCH(k_kern_to_ref, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, ws + w.kern + (size_t)n * B * Tm * KCN, out_dev, B, Tm, want_bias);
+        FD_CHECK_LAUNCH(h, "k_kern_to_ref");
+        return FD_OK;
+    }
+    return fail(h, FD_ERR_INVALID, "fd_debug_read: unknown tensor '%s'", name);
+}

@@ -1,0 +1,63 @@
+/* Packed-weight blob layout shared by the Python packer (fastdiff_b200/weights.py parses this file
+ * for the section order) and the CUDA library.
+ *
+ * blob := header | fp32 data
+ *   header: uint64 magic, uint64 version, uint64 n_sections, then n_sections x {uint64 offset, uint64 count}
+ *           (offset/count in fp32 elements from the start of the blob; every offset is a multiple of 64
+ *           elements = 256 B so any section can be the source of a 16-byte vector load / bulk copy).
+ *
+ * Section contents (folded weights: w = g*v/||v|| for every weight-normed Conv1d,
+ * /root/reference/modules/FastDiff/module/FastDiff_model.py:115-122):
+ *   EMB_FREQ  [64]            exp(-j ln(1e4)/63) built in fp32 exactly like util.py:425-427
+ *   FC1_WT    [128][512]      fc_t1.weight^T          FC1_B [512]
+ *   FC2_WT    [512][512]      fc_t2.weight^T          FC2_B [512]
+ *   FIRST_W   [7][32]         first_audio_conv [k][co]   FIRST_B [32]
+ *   FINAL_W   [7][32]         final_conv.0 [k][ci]       FINAL_B [1]
+ *   DBn_RES_W [32 ci][32 co]  downsample.n.residual_dense   DBn_RES_B [32]
+ *   DBn_CONV_W[3][3 k][32 ci][32 co]  downsample.n.conv.{0,1,2}   DBn_CONV_B [3][32]
+ *   LBn_FCT_WT[512][80]       lvc_blocks.n.fc_t.weight^T    LBn_FCT_B [80]
+ *   LBn_UP_W  [2r k][32 ci][32 co]  lvc_blocks.n.upsample.weight (ConvTranspose1d (ci,co,k))   LBn_UP_B [32]
+ *   LBn_CONV_W[4][3 k][32 ci][32 co] lvc_blocks.n.convs.{0..3}    LBn_CONV_B [4][32]
+ *   LBn_KPIN_W[5 j][80 ci][64 co]   kernel_predictor.input_conv.0   LBn_KPIN_B [64]
+ *   LBn_KPRES_W[6][3 j][64 ci][64 co] kernel_predictor.residual_conv.{1,3,6,8,11,13}   LBn_KPRES_B [6][64]
+ *   LBn_KC_W  [192 kk=(j*64+c)][24832 n]   kernel_conv + bias_conv fused along n, permuted so one GEMM row
+ *             is, per LVC layer l, the [96 (k*32+i)][64 o] operand of the location-variable conv followed
+ *             by its 64 biases:  n = l*6208 + (k*32+i)*64 + o   <- kernel_conv channel ((l*32+i)*64+o)*3+k
+ *                                n = l*6208 + 6144 + o          <- bias_conv channel l*64+o
+ *             (channel maps: modules.py:333-342)
+ *   LBn_KC_B  [24832]         same permutation of the two bias vectors
+ */
+#ifndef FD_BLOB_H
+#define FD_BLOB_H
+
+#define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
+#define FD_BLOB_VERSION 2ULL
+
+/* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
+/* FD_SECTIONS_BEGIN */
+#define FD_SECTIONS(X) \
+    X(EMB_FREQ) X(FC1_WT) X(FC1_B) X(FC2_WT) X(FC2_B) \
+    X(FIRST_W) X(FIRST_B) X(FINAL_W) X(FINAL_B) \
+    X(DB0_RES_W) X(DB0_RES_B) X(DB0_CONV_W) X(DB0_CONV_B) \
+    X(DB1_RES_W) X(DB1_RES_B) X(DB1_CONV_W) X(DB1_CONV_B) \
+    X(DB2_RES_W) X(DB2_RES_B) X(DB2_CONV_W) X(DB2_CONV_B) \
+    X(LB0_FCT_WT) X(LB0_FCT_B) X(LB0_UP_W) X(LB0_UP_B) X(LB0_CONV_W) X(LB0_CONV_B) \
+    X(LB0_KPIN_W) X(LB0_KPIN_B) X(LB0_KPRES_W) X(LB0_KPRES_B) X(LB0_KC_W) X(LB0_KC_B) \
+    X(LB1_FCT_WT) X(LB1_FCT_B) X(LB1_UP_W) X(LB1_UP_B) X(LB1_CONV_W) X(LB1_CONV_B) \
+    X(LB1_KPIN_W) X(LB1_KPIN_B) X(LB1_KPRES_W) X(LB1_KPRES_B) X(LB1_KC_W) X(LB1_KC_B) \
+    X(LB2_FCT_WT) X(LB2_FCT_B) X(LB2_UP_W) X(LB2_UP_B) X(LB2_CONV_W) X(LB2_CONV_B) \
+    X(LB2_KPIN_W) X(LB2_KPIN_B) X(LB2_KPRES_W) X(LB2_KPRES_B) X(LB2_KC_W) X(LB2_KC_B)
+/* FD_SECTIONS_END */
+
+enum fd_section {
+#define FD_X(name) FD_S_##name,
+    FD_SECTIONS(FD_X)
+#undef FD_X
+    FD_S_COUNT
+};
+
+/* stride between the per-block groups above */
+#define FD_DB_STRIDE 4
+#define FD_LB_STRIDE 12
+
+#endif

@@ -1,0 +1,141 @@
+"""Weight packer: reference-shaped state_dict -> the single blob the CUDA library loads.
+
+Accepts exactly the key set of the reference model's ``state_dict()``
+(/root/reference/modules/FastDiff/module/FastDiff_model.py:13-72; weight-normed convs arrive as
+``*.weight_g`` / ``*.weight_v``, ConvTranspose1d / Linear as plain ``*.weight``), folds weight-norm
+(w = g v/||v||, FastDiff_model.py:115-122 -- the reference re-materialises this on every forward),
+and lays every tensor out as the kernels read it (fastdiff_b200/csrc/fd_blob.h documents each section).
+One contiguous blob -> one H2D copy per process, or one NCCL broadcast in batch-shard mode.
+"""
+from __future__ import annotations
+
+import os
+import re
+from typing import Dict, List, Mapping
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BLOB_H = os.path.join(_HERE, "csrc", "fd_blob.h")
+
+C, COND, HID, LAYERS, KS = 32, 80, 64, 4, 3
+KK = C * KS
+LVC_OUT = 2 * C
+KPL = KK * LVC_OUT + LVC_OUT
+KCN = LAYERS * KPL
+RATIOS = (8, 8, 4)
+
+
+def _parse_blob_header():
+    txt = open(_BLOB_H).read()
+    body = txt[txt.index("/* FD_SECTIONS_BEGIN */"): txt.index("/* FD_SECTIONS_END */")]
+    names = re.findall(r"X\((\w+)\)", body)
+    magic = int(re.search(r"FD_BLOB_MAGIC\s+(0x[0-9A-Fa-f]+)ULL", txt).group(1), 16)
+    version = int(re.search(r"FD_BLOB_VERSION\s+(\d+)ULL", txt).group(1))
+    return names, magic, version
+
+
+SECTION_NAMES, BLOB_MAGIC, BLOB_VERSION = _parse_blob_header()
+
+
+def fold_weight_norm(sd: Mapping[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """``name.weight_g`` + ``name.weight_v`` -> ``name.weight`` (fp32); plain tensors pass through."""
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        v = v.detach().to("cpu", torch.float32)
+        if k.endswith(".weight_g"):
+            base = k[: -len(".weight_g")]
+            vv = sd[base + ".weight_v"].detach().to("cpu", torch.float32)
+            nrm = vv.reshape(vv.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (vv.dim() - 1)))
+            out[base + ".weight"] = v * vv / nrm
+        elif k.endswith(".weight_v"):
+            continue
+        else:
+            out[k] = v
+    return out
+
+
+def expected_keys(use_weight_norm: bool = True) -> List[str]:
+    from .synthetic import make_state_dict
+
+    return list(make_state_dict(0, use_weight_norm=use_weight_norm).keys())
+
+
+def _conv_kcico(w: torch.Tensor) -> torch.Tensor:
+    """Conv1d weight (co, ci, k) -> [k][ci][co]."""
+    return w.permute(2, 1, 0).contiguous()
+
+
+def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
+    W = fold_weight_norm(sd)
+    S: Dict[str, torch.Tensor] = {}
+    half = 64
+    c = np.log(10000) / (half - 1)
+    S["EMB_FREQ"] = torch.exp(torch.arange(half) * -c)  # fp32, same expression as util.py:425-427
+    S["FC1_WT"] = W["fc_t1.weight"].t().contiguous()
+    S["FC1_B"] = W["fc_t1.bias"]
+    S["FC2_WT"] = W["fc_t2.weight"].t().contiguous()
+    S["FC2_B"] = W["fc_t2.bias"]
+    S["FIRST_W"] = W["first_audio_conv.weight"][:, 0, :].t().contiguous()  # (32,1,7) -> [k][co]
+    S["FIRST_B"] = W["first_audio_conv.bias"]
+    S["FINAL_W"] = W["final_conv.0.weight"][0].t().contiguous()  # (1,32,7) -> [k][ci]
+    S["FINAL_B"] = W["final_conv.0.bias"]
+    for n in range(3):
+        p = f"downsample.{n}"
+        S[f"DB{n}_RES_W"] = W[f"{p}.residual_dense.weight"][:, :, 0].t().contiguous()  # [ci][co]
+        S[f"DB{n}_RES_B"] = W[f"{p}.residual_dense.bias"]
+        S[f"DB{n}_CONV_W"] = torch.stack([_conv_kcico(W[f"{p}.conv.{i}.weight"]) for i in range(3)])
+        S[f"DB{n}_CONV_B"] = torch.stack([W[f"{p}.conv.{i}.bias"] for i in range(3)])
+    for n in range(3):
+        p = f"lvc_blocks.{n}"
+        kp = f"{p}.kernel_predictor"
+        S[f"LB{n}_FCT_WT"] = W[f"{p}.fc_t.weight"].t().contiguous()
+        S[f"LB{n}_FCT_B"] = W[f"{p}.fc_t.bias"]
+        S[f"LB{n}_UP_W"] = W[f"{p}.upsample.weight"].permute(2, 0, 1).contiguous()  # (ci,co,k) -> [k][ci][co]
+        S[f"LB{n}_UP_B"] = W[f"{p}.upsample.bias"]
+        S[f"LB{n}_CONV_W"] = torch.stack([_conv_kcico(W[f"{p}.convs.{i}.weight"]) for i in range(LAYERS)])
+        S[f"LB{n}_CONV_B"] = torch.stack([W[f"{p}.convs.{i}.bias"] for i in range(LAYERS)])
+        S[f"LB{n}_KPIN_W"] = _conv_kcico(W[f"{kp}.input_conv.0.weight"])  # [5][80][64]
+        S[f"LB{n}_KPIN_B"] = W[f"{kp}.input_conv.0.bias"]
+        S[f"LB{n}_KPRES_W"] = torch.stack([_conv_kcico(W[f"{kp}.residual_conv.{i}.weight"]) for i in (1, 3, 6, 8, 11, 13)])
+        S[f"LB{n}_KPRES_B"] = torch.stack([W[f"{kp}.residual_conv.{i}.bias"] for i in (1, 3, 6, 8, 11, 13)])
+        # kernel_conv (24576,64,3): channel ((l*32+i)*64+o)*3+k ; bias_conv (256,64,3): channel l*64+o  (modules.py:333-342)
+        kc = W[f"{kp}.kernel_conv.weight"].reshape(LAYERS, C, LVC_OUT, KS, HID, 3)   # [l][i][o][k][c][j]
+        kc = kc.permute(5, 4, 0, 3, 1, 2).reshape(3 * HID, LAYERS, KK * LVC_OUT)      # [j*64+c][l][(k*32+i)*64+o]
+        bc = W[f"{kp}.bias_conv.weight"].reshape(LAYERS, LVC_OUT, HID, 3)            # [l][o][c][j]
+        bc = bc.permute(3, 2, 0, 1).reshape(3 * HID, LAYERS, LVC_OUT)                 # [j*64+c][l][o]
+        S[f"LB{n}_KC_W"] = torch.cat([kc, bc], dim=2).reshape(3 * HID, KCN).contiguous()
+        kcb = W[f"{kp}.kernel_conv.bias"].reshape(LAYERS, C, LVC_OUT, KS).permute(0, 3, 1, 2).reshape(LAYERS, KK * LVC_OUT)
+        bcb = W[f"{kp}.bias_conv.bias"].reshape(LAYERS, LVC_OUT)
+        S[f"LB{n}_KC_B"] = torch.cat([kcb, bcb], dim=1).reshape(KCN).contiguous()
+    assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
+    return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}
+
+
+def pack_state_dict(sd: Mapping[str, torch.Tensor]) -> np.ndarray:
+    """-> uint8 array holding the blob (header + 256-byte-aligned fp32 sections)."""
+    need = set(expected_keys(True))
+    need_plain = set(expected_keys(False))
+    have = set(sd.keys())
+    if have != need and have != need_plain:
+        missing = sorted((need - have))[:5]
+        extra = sorted((have - need))[:5]
+        raise KeyError(f"state_dict keys do not match the reference FastDiff model: missing {missing} unexpected {extra}")
+    secs = build_sections(sd)
+    n = len(SECTION_NAMES)
+    hdr_words = 3 + 2 * n
+    off = (hdr_words * 2 + 63) // 64 * 64  # in fp32 elements (a uint64 = 2 floats), 64-float granules
+    table = []
+    for name in SECTION_NAMES:
+        table.append((off, secs[name].size))
+        off += (secs[name].size + 63) // 64 * 64
+    blob = np.zeros(off, dtype=np.float32)
+    hdr = np.zeros(hdr_words, dtype=np.uint64)
+    hdr[0], hdr[1], hdr[2] = BLOB_MAGIC, BLOB_VERSION, n
+    for i, (o, c) in enumerate(table):
+        hdr[3 + 2 * i], hdr[4 + 2 * i] = o, c
+    blob.view(np.uint64)[:hdr_words] = hdr
+    for name, (o, c) in zip(SECTION_NAMES, table):
+        blob[o: o + c] = secs[name]
+    return blob.view(np.uint8)

@@ -1,0 +1,142 @@
+/*
+ * fastdiff_b200 -- C ABI of the B200-native FastDiff reverse-diffusion sampling path.
+ *
+ * The reference (Rongjiehuang/FastDiff) has no FFI layer: its boundary for this path is two Python
+ * call signatures.  Each entry point below names the reference interface it stands behind
+ * (file:line under /root/reference); fastdiff_b200/{model,sampler}.py bind them with ctypes and
+ * re-expose the reference's own Python signatures on top.
+ *
+ * Conventions
+ *   - return 0 on success, negative fd_status on failure; fd_last_error() gives the message.
+ *   - every pointer named *_dev is a DEVICE pointer owned by the caller (PyTorch); the library
+ *     borrows it for the duration of the call, launches on the caller's stream and never
+ *     synchronises the host.  Nothing is allocated after fd_load_weights(); scratch memory is the
+ *     caller-provided workspace (fd_workspace_bytes).
+ *   - layouts are the reference's: audio (B,1,L) fp32, mel (B,80,T') fp32 NCL, L = 256*T',
+ *     diffusion steps (B) fp32 (fractional steps).
+ *   - one handle per (device, stream); a handle is not thread-safe, distinct handles are independent.
+ *   - architecture: the one network the reference ships (modules/FastDiff/config/base.yaml:21-33);
+ *     fd_create() rejects any other fd_config with FD_ERR_UNSUPPORTED.
+ */
+#ifndef FASTDIFF_B200_H
+#define FASTDIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fd_handle fd_handle;
+
+typedef enum fd_status {
+    FD_OK = 0,
+    FD_ERR_INVALID = -1,      /* bad argument (shape, null pointer, blob mismatch) */
+    FD_ERR_UNSUPPORTED = -2,  /* architecture / device the kernels are not built for */
+    FD_ERR_CUDA = -3,         /* a CUDA runtime call or launch failed */
+    FD_ERR_STATE = -4         /* call order (e.g. denoise before load_weights) */
+} fd_status;
+
+/* Mirrors the ctor kwargs of FastDiff.__init__ (modules/FastDiff/module/FastDiff_model.py:13-26)
+ * = the hparams read by FastDiffTask.build_model (modules/FastDiff/task/FastDiff.py:17-29). */
+typedef struct fd_config {
+    int32_t audio_channels;               /* 1   */
+    int32_t inner_channels;               /* 32  */
+    int32_t cond_channels;                /* 80  */
+    int32_t n_upsample;                   /* 3   */
+    int32_t upsample_ratios[4];           /* 8,8,4 */
+    int32_t lvc_layers_each_block;        /* 4   */
+    int32_t lvc_kernel_size;              /* 3   */
+    int32_t kpnet_hidden_channels;        /* 64  */
+    int32_t kpnet_conv_size;              /* 3   */
+    int32_t diffusion_step_embed_dim_in;  /* 128 */
+    int32_t diffusion_step_embed_dim_mid; /* 512 */
+    int32_t diffusion_step_embed_dim_out; /* 512 */
+} fd_config;
+
+/* Per-reverse-step scalars, computed ON THE HOST exactly as the reference computes them
+ * (modules/FastDiff/module/util.py:187-204 for t; :219-229 for the update), one entry per executed
+ * step in execution order (n = N-1 ... 0).
+ *   ddim == 0:  x = (x - coef_eps*eps) / div;  if (add_noise) x = x + sigma*z      (util.py:226-229)
+ *   ddim != 0:  x = c1*x + c2*eps + c3*eps                                          (util.py:219-224)
+ */
+typedef struct fd_step {
+    float t;         /* steps_infer[n]: fractional diffusion step fed to the embedding */
+    float coef_eps;  /* beta_n / sqrt(1 - alpha_n^2) */
+    float div;       /* sqrt(1 - beta_n) */
+    float sigma;     /* sigma_n */
+    float c1, c2, c3;
+    int32_t add_noise; /* n > 0 */
+} fd_step;
+
+/* Arithmetic mode of the heavy contractions (kernel_conv GEMM, location-variable conv, dilated convs). */
+typedef enum fd_mode {
+    FD_MODE_FP32_SIMT = 0,   /* fp32 FFMA everywhere (strict; the on-device cross-check path) */
+    FD_MODE_TC_3XTF32 = 1,   /* tcgen05 kind::tf32 with hi/lo error compensation (fp32-level) */
+    FD_MODE_TC_TF32 = 2      /* tcgen05 kind::tf32 single pass (fast mode; error reported separately) */
+} fd_mode;
+
+/* Build a sampler/denoiser for `device`.  Stands behind FastDiff.__init__
+ * (modules/FastDiff/module/FastDiff_model.py:13-72). */
+int fd_create(const fd_config* cfg, int device, fd_handle** out);
+
+/* Copy the packed weight blob (host memory, produced by fastdiff_b200.weights.pack_state_dict from
+ * a reference state_dict: weight-norm folded, layouts permuted) to the device.  Stands behind
+ * nn.Module.load_state_dict / Trainer.restore_weights (utils/trainer.py:348-369).  The blob is
+ * borrowed during the call only. */
+int fd_load_weights(fd_handle* h, const void* blob_host, size_t bytes);
+
+/* Same, but the blob is already in device memory (e.g. received by one NCCL broadcast in
+ * batch-shard mode); the library keeps its own device copy. */
+int fd_load_weights_dev(fd_handle* h, const void* blob_dev, size_t bytes, void* stream);
+
+/* Scratch bytes needed for a (B, T') problem. */
+int fd_workspace_bytes(fd_handle* h, int B, int Tm, size_t* out);
+
+/* Select arithmetic mode (default: the best mode whose kernels are built in). */
+int fd_set_mode(fd_handle* h, int mode);
+int fd_get_mode(fd_handle* h);
+
+/* Integer options.  "stop_after": run fd_denoise only up to a stage (1 = kernel predictor, 2 = DBlocks,
+ * 3/4/5 = LVC block 0/1/2, >= 6 = everything; default) so fd_debug_read can inspect stage outputs. */
+int fd_set_option(fd_handle* h, const char* key, int64_t value);
+
+/* eps = FastDiff.forward((x_t, mel, t))   (modules/FastDiff/module/FastDiff_model.py:74-102).
+ * x_dev (B,1,256*Tm), mel_dev (B,80,Tm), t_dev (B), eps_dev (B,1,256*Tm). */
+int fd_denoise(fd_handle* h, const float* x_dev, const float* mel_dev, const float* t_dev,
+               float* eps_dev, int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* The reverse loop of sampling_given_noise_schedule (modules/FastDiff/module/util.py:216-234).
+ * x_dev: x_T on entry (unless fill_xT), x_0 on return.
+ * steps: HOST array of n_steps entries in execution order.
+ * noise_dev: parity mode -- device (n_noise,B,1,L) Gaussian draws in the reference's order
+ *            (one per step with add_noise); NULL -> on-device Philox4x32-10 keyed by `seed`.
+ * fill_xT: draw x_T on the device from the same Philox stream (perf mode).
+ * seq_dev: optional (n_steps+1,B,1,L) -- x after every step incl. x_T (return_sequence=True). */
+int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const fd_step* steps, int n_steps,
+              const float* noise_dev, int n_noise, uint64_t seed, int fill_xT, int ddim,
+              float* seq_dev, int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Stage helpers exposed for the parity tests (each is one stage of FastDiff.forward; same
+ * conventions).  fd_debug_read copies a named internal tensor of the LAST fd_denoise call out of
+ * the workspace, converted to the reference's NCL layout:
+ *   "embed" (B,512)  FastDiff_model.py:85-87     "down0|1|2" (B,32,L/4|L/32|L/256)  modules.py:127-138
+ *   "kp_hidden0|1|2" (B,64,T')  modules.py:328-329
+ *   "kernels0|1|2" (B,4,32,64,3,T') and "kbias0|1|2" (B,4,64,T')  modules.py:330-342
+ *   "lvc0|1|2" (B,32,8T'|64T'|256T')  modules.py:190-218
+ * out_dev must hold *count floats; if out_dev is NULL only *count is written. */
+int fd_debug_read(fd_handle* h, const char* name, float* out_dev, size_t* count, int B, int Tm,
+                  void* workspace_dev, void* stream);
+
+/* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+uint64_t fd_launch_count(fd_handle* h);
+
+const char* fd_last_error(fd_handle* h);   /* valid until the next call on h; h may be NULL for create errors */
+void fd_destroy(fd_handle* h);
+const char* fd_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTDIFF_B200_H */

@@ -1,0 +1,65 @@
+// Minimal CUDA execution-model shim for the CPU test-suite (TEST INFRASTRUCTURE, never shipped).
+// Runs every CTA of a launch on blockDim OS threads with a pthread barrier as __syncthreads, CTAs
+// one after another, "device" memory = host memory.  Enough for the SIMT kernels in
+// fastdiff_b200/csrc/fd_kernels_simt.cuh (no warp shuffles, no tensor-core / TMA instructions).
+#pragma once
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static
+
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+struct float4 { float x, y, z, w; } __attribute__((aligned(16)));
+static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
+
+namespace emu {
+extern thread_local dim3 t_threadIdx;
+extern dim3 g_blockIdx, g_blockDim, g_gridDim;
+extern pthread_barrier_t g_bar;
+extern unsigned char* g_dyn_smem;
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+}
+#define threadIdx (emu::t_threadIdx)
+#define blockIdx (emu::g_blockIdx)
+#define blockDim (emu::g_blockDim)
+#define gridDim (emu::g_gridDim)
+static inline void __syncthreads() { pthread_barrier_wait(&emu::g_bar); }
+
+#define FD_LAUNCH(kern, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+#define FD_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
+
+// arithmetic intrinsics (compile with -ffp-contract=off so the _rn forms are honoured)
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+
+// runtime subset
+typedef int cudaError_t;
+typedef void* cudaStream_t;
+enum { cudaSuccess = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaMalloc(void** p, size_t n) { return posix_memalign(p, 1024, n) ? 1 : cudaSuccess; }
+static inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
