@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the FastDiff reverse-diffusion sampling hot path (BASELINE.json metric:
+audio samples/sec (22.05 kHz) at N=4 reverse steps).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # CPU yardstick (oracle port of the reference)
+
+A "step" = one complete sampling call (all N=4 reverse steps incl. noise generation) over one batch of
+synthetic input.  Workload at every N: BASELINE.json configs[1] per GPU -- batch 8 x 10 s synthetic mel
+(T'=861, L=220,416), LJSpeech network, random-init weights -- i.e. weak scaling, utterances sharded over
+ranks, one NCCL broadcast of the packed weights at load, no per-step collective.
+Prints ONE JSON line on rank 0 (stdout); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N4_SCHEDULE = [3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]  # modules/FastDiff/task/FastDiff.py:88-89
+FLOP_PER_SAMPLE_STEP = 222601.0      # SURVEY.md section 8(d), torch FlopCounterMode on the reference
+KC_FLOP_PER_FRAME = 2.0 * 24832 * 192  # kernel_conv+bias_conv GEMM: 2*N*K per mel frame per LVC block
+METRIC = "audio samples/sec (22.05 kHz) at N=4 reverse steps"
+UNIT = "samples/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"tensor": float(p["bf16_tflops_sustained"]), "tensor_burst": float(p["bf16_tflops"]), "hbm": float(p["hbm_gbs"]),
+                "src": "MEASURED_PEAKS.json"}
+    except Exception:
+        return {"tensor": 1400.0, "tensor_burst": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def oracle_setup(seed=1234):
+    from fastdiff_b200.synthetic import make_state_dict
+    from oracle import fastdiff_oracle as O
+    sd = make_state_dict(seed)
+    return O, O.fold_weight_norm(sd)
+
+
+def cpu_sample_once(O, W, B, Tm, dh):
+    """One oracle sampling call (the reference algorithm on the host cores, fp32, all intra-op threads)."""
+    from fastdiff_b200.synthetic import make_inputs
+    _, mel = make_inputs(B, Tm, 0)
+    sched = torch.FloatTensor(N4_SCHEDULE)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        O.sample(W, (B, 1, Tm * 256), dh, sched, mel)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path.  The reference is pure PyTorch and
+    /root/reference does not exist on the GPU box, so this arm times oracle/fastdiff_oracle.py (kind "port": the same
+    ATen ops the reference issues, restated), on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O, W = oracle_setup()
+    dh = O.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
+    B, Tm = 1, 861  # bounded sample of the workload: 1 of the 8 utterances of a batch (10 s), all N=4 steps
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            cpu_sample_once(O, W, B, Tm, dh)
+        ts = [cpu_sample_once(O, W, B, Tm, dh) for _ in range(args.steps)]
+    per = sum(ts) / len(ts)
+    val = B * Tm * 256 / per
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "batch=8 x 10 s synthetic mel (T'=861), N=4, LJSpeech config, random-init weights",
+                   "sample": "1 utterance x 10 s (1/8 of a batch) per step", "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": "oracle port of the reference (torch CPU fp32), 1 x 10 s utterance, N=4, per step",
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import fastdiff_b200 as fb
+    from fastdiff_b200.sampler import build_steps
+    from fastdiff_b200.synthetic import make_inputs, make_state_dict
+    from fastdiff_b200.weights import pack_state_dict
+    from fastdiff_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, Tm = args.batch, args.frames
+    L = Tm * 256
+
+    # ---- weights: rank 0 packs, one broadcast of the blob, every rank loads from device memory -------------
+    if world > 1:
+        if rank == 0:
+            blob = torch.from_numpy(pack_state_dict(make_state_dict(1234))).to(dev)
+            n = torch.tensor([blob.numel()], device=dev, dtype=torch.int64)
+        else:
+            n = torch.zeros(1, device=dev, dtype=torch.int64)
+        dist.broadcast(n, 0)
+        if rank != 0:
+            blob = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
+        dist.broadcast(blob, 0)   # the only collective on the path
+        eng = Engine(device=dev)
+        eng.load_blob_device(blob)
+        net = None
+    else:
+        net = fb.FastDiff().to(dev).eval()
+        net.load_state_dict(make_state_dict(1234))
+        net.noise_mode = "device"
+        eng = net.engine(dev)
+    if args.mode:
+        eng.set_mode(args.mode)
+        if net is not None:
+            net.mode = args.mode
+    mode_name = {0: "fp32_simt", 1: "tc_3xtf32", 2: "tc_tf32"}[eng.get_mode()]
+
+    dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
+    sched = torch.FloatTensor(N4_SCHEDULE)
+    _, steps = build_steps(dh, sched)
+    _, mel_host = make_inputs(B, Tm, seed=rank)  # each rank owns its own utterances
+    mel = mel_host.to(dev)
+    x = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
+
+    def one_call(i):
+        eng.sample(x, mel, steps, noise=None, seed=1000 + i, fill_xT=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_call(i)
+    barrier()
+
+    # ---- timed region: device-resident inputs ------------------------------------------------------------
+    clocks = ClockSampler(local) if rank == 0 else None
+    eng.timing_enable(True)
+    eng.timing_report()  # drop warm-up records
+    l0 = eng.launch_count()
+    if clocks:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        one_call(args.warmup + i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if clocks else None
+    launches = eng.launch_count() - l0
+    per_kernel = eng.timing_report()
+    eng.timing_enable(False)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B * L / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API, host buffers, H2D/D2H inside the timed region ------------------------------------
+    e2e = None
+    try:
+        mel_pinned = mel_host.pin_memory()
+        out_host = torch.empty((B, 1, L), dtype=torch.float32).pin_memory()
+        if net is None:
+            # multi-rank: same call sequence as sampling_given_noise_schedule, on this rank's shard
+            def e2e_call(i):
+                m = mel_pinned.to(dev, non_blocking=True)
+                eng.sample(x, m, steps, noise=None, seed=5000 + i, fill_xT=True)
+                out_host.copy_(x, non_blocking=True)
+                torch.cuda.synchronize()
+        else:
+            def e2e_call(i):
+                net.seed = 5000 + i
+                with contextlib.redirect_stdout(sys.stderr):
+                    y = fb.sampling_given_noise_schedule(net, (B, 1, L), dh, sched, condition=mel_pinned.to(dev, non_blocking=True))
+                out_host.copy_(y, non_blocking=True)
+                torch.cuda.synchronize()
+        e2e_call(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_call(1 + i)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world * B * L * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": world * mel_host.numel() * 4,
+               "d2h_bytes_per_step": world * B * L * 4, "ms_per_step": dt / args.steps * 1e3,
+               "api": "fastdiff_b200.sampling_given_noise_schedule" if net is not None else "Engine.sample (batch shard)"}
+    except Exception as e:  # pragma: no cover
+        log("e2e leg failed:", repr(e))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (live CUDA-event time inside the timed region) -------------------
+    peaks = measured_peaks()
+    total_ms = sum(v["ms"] for v in per_kernel.values()) or 1.0
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
+    roofline = None
+    if dom:
+        n_dom = per_kernel[dom]["n"]
+        avg_ms = per_kernel[dom]["ms"] / n_dom
+        frames = B * Tm
+        samples = B * L
+        flop_per_launch = {
+            "kc_gemm": KC_FLOP_PER_FRAME * frames * 3,                    # one launch covers the 3 LVC blocks
+            "lvc_layer_b2": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples,     # dilated conv + LVC at full rate
+            "lvc_layer_b1": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 4,
+            "lvc_layer_b0": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 32,
+        }.get(dom)
+        if flop_per_launch:
+            ach = flop_per_launch / (avg_ms * 1e-3) / 1e12
+            roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tensor"], "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained (of measured)",
+                        "avg_launch_ms": avg_ms, "launches": n_dom, "share_of_step": per_kernel[dom]["ms"] / total_ms,
+                        "algorithmic_flop_per_launch": flop_per_launch, "mode": mode_name}
+    whole = {"achieved_tflops": FLOP_PER_SAMPLE_STEP * 4 * world * B * L / (ms_per_step * 1e-3) / 1e12,
+             "frac_of_bf16_sustained": FLOP_PER_SAMPLE_STEP * 4 * B * L / (ms_per_step * 1e-3) / 1e12 / peaks["tensor"]}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ---------------------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu:
+        try:
+            O, W = oracle_setup()
+            dho = O.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
+            cpu_sample_once(O, W, 1, 86, dho)  # warm-up (1 s)
+            tcpu = cpu_sample_once(O, W, 1, 861, dho)
+            cpu_baseline = {"value": 861 * 256 / tcpu, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": "oracle port of the reference (torch CPU fp32): 1 utterance x 10 s of the batch, all N=4 steps, 1 run",
+                            "seconds": tcpu, "host_cpus": os.cpu_count()}
+        except Exception as e:  # pragma: no cover
+            log("cpu baseline failed:", repr(e))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if mode_name != "tc_tf32" else "tf32", "data": "synthetic",
+        "config": {"workload": f"batch={B} x {Tm * 256 / 22050:.1f} s synthetic mel (T'={Tm}) per GPU, N=4, LJSpeech config, random-init weights",
+                   "global_batch": world * B, "parallelism": f"batch-shard x{world} (weights broadcast once, no per-step collective)",
+                   "arith_mode": mode_name, "noise": "on-device Philox4x32-10 (inside the timed region)",
+                   "l2": "inputs+activations per call (>=450 MB) exceed the 126 MB L2; no explicit flush"},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in per_kernel.items()}, "whole_step": whole,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=None, choices=[None, "fp32_simt", "tc_3xtf32", "tc_tf32"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--frames", type=int, default=861)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <vector>
 
 using namespace fd;
 
@@ -30,6 +31,40 @@ struct fd_handle {
     uint64_t launches = 0;
     std::string err;
     void* tc_state = nullptr;    // tensor-core path resources (tensor maps etc.)
+    // optional per-kernel-class device timing (bench.py's live roofline number)
+    int timing = 0;
+    struct TimedLaunch { int cls; cudaEvent_t a, b; };
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+enum fd_kernel_class { KC_EMBED, KC_KP_HIDDEN, KC_KC_GEMM, KC_DBLOCK, KC_UPSAMPLE, KC_LVC0, KC_LVC1, KC_LVC2, KC_FINAL, KC_FILL, KC_COUNT };
+static const char* const kKernelClassName[KC_COUNT] = {"embed", "kp_hidden", "kc_gemm", "dblock", "upsample", "lvc_layer_b0",
+                                                      "lvc_layer_b1", "lvc_layer_b2", "final_update", "fill_normal"};
+
+// Brackets the launches made in its scope with two events when timing is on (no-op otherwise).
+struct ScopedTimer {
+    fd_handle* h; cudaStream_t st; int idx = -1;
+    ScopedTimer(fd_handle* h_, int cls, cudaStream_t st_) : h(h_), st(st_) {
+#ifndef FD_EMU
+        if (!h->timing) return;
+        cudaEvent_t e[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!h->ev_pool.empty()) { e[i] = h->ev_pool.back(); h->ev_pool.pop_back(); }
+            else if (cudaEventCreate(&e[i]) != cudaSuccess) return;
+        }
+        h->timed.push_back({cls, e[0], e[1]});
+        idx = (int)h->timed.size() - 1;
+        cudaEventRecord(e[0], st);
+#else
+        (void)cls;
+#endif
+    }
+    ~ScopedTimer() {
+#ifndef FD_EMU
+        if (idx >= 0) cudaEventRecord(h->timed[idx].b, st);
+#endif
+    }
 };
 
 static std::string g_create_err;
@@ -112,6 +147,10 @@ extern "C" void fd_destroy(fd_handle* h) {
 #ifndef FD_EMU
     cudaSetDevice(h->device);
     tc_destroy(h->tc_state);
+#endif
+#ifndef FD_EMU
+    for (auto& t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
 #endif
     if (h->blob) cudaFree(h->blob);
     delete h;
@@ -217,6 +256,38 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
 
 extern "C" uint64_t fd_launch_count(fd_handle* h) { return h ? h->launches : 0; }
 
+extern "C" int fd_timing_enable(fd_handle* h, int on) {
+    if (!h) return FD_ERR_INVALID;
+    h->timing = on ? 1 : 0;
+    return FD_OK;
+}
+
+// Caller must have synchronised the stream.  Writes one JSON object {"class": {"ms": total, "n": launches}, ...}
+// for the launches recorded since the last report, then recycles the events.
+extern "C" int fd_timing_report(fd_handle* h, char* buf, size_t buf_bytes) {
+    if (!h || !buf || buf_bytes < 64) return FD_ERR_INVALID;
+    double ms[KC_COUNT] = {0};
+    long cnt[KC_COUNT] = {0};
+#ifndef FD_EMU
+    for (auto& t : h->timed) {
+        float e = 0.f;
+        if (cudaEventElapsedTime(&e, t.a, t.b) == cudaSuccess) { ms[t.cls] += e; cnt[t.cls]++; }
+        h->ev_pool.push_back(t.a); h->ev_pool.push_back(t.b);
+    }
+#endif
+    h->timed.clear();
+    size_t o = 0;
+    o += snprintf(buf + o, buf_bytes - o, "{");
+    bool first = true;
+    for (int c = 0; c < KC_COUNT && o + 96 < buf_bytes; ++c) {
+        if (!cnt[c]) continue;
+        o += snprintf(buf + o, buf_bytes - o, "%s\"%s\": {\"ms\": %.6f, \"n\": %ld}", first ? "" : ", ", kKernelClassName[c], ms[c], cnt[c]);
+        first = false;
+    }
+    snprintf(buf + o, buf_bytes - o, "}");
+    return FD_OK;
+}
+
 // ---- kernel attribute setup (dynamic smem opt-in), once per handle --------------------------------
 template <typename K>
 static cudaError_t set_smem(K kern, int bytes) {
@@ -260,6 +331,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             p.fct_wt[n] = sec(h, FD_S_LB0_FCT_WT + n * FD_LB_STRIDE);
             p.fct_b[n] = sec(h, FD_S_LB0_FCT_B + n * FD_LB_STRIDE);
         }
+        ScopedTimer tm(h, KC_EMBED, st);
         FD_LAUNCH(k_embed, dim3(B), dim3(512), 0, st, p, t_dev, t_scalar, emb, cnoise, B);
         FD_CHECK_LAUNCH(h, "k_embed");
     }
@@ -270,6 +342,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             p.in_w[n] = sec(h, FD_S_LB0_KPIN_W + n * FD_LB_STRIDE);   p.in_b[n] = sec(h, FD_S_LB0_KPIN_B + n * FD_LB_STRIDE);
             p.res_w[n] = sec(h, FD_S_LB0_KPRES_W + n * FD_LB_STRIDE); p.res_b[n] = sec(h, FD_S_LB0_KPRES_B + n * FD_LB_STRIDE);
         }
+        ScopedTimer tm(h, KC_KP_HIDDEN, st);
         FD_LAUNCH(k_kp_hidden, dim3((Tm + KP_FT - 1) / KP_FT, B, NBLK), dim3(256), KP_SMEM_BYTES, st, p, mel_dev, cnoise, hk, B, Tm);
         FD_CHECK_LAUNCH(h, "k_kp_hidden");
     }
@@ -277,10 +350,12 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         KcParams p;
         for (int n = 0; n < NBLK; ++n) { p.w[n] = sec(h, FD_S_LB0_KC_W + n * FD_LB_STRIDE); p.b[n] = sec(h, FD_S_LB0_KC_B + n * FD_LB_STRIDE); }
         const int M = B * (Tm + 2) - 2;
+        ScopedTimer tm(h, KC_KC_GEMM, st);
         FD_LAUNCH(k_kc_gemm_simt, dim3(KCN / 128, (M + 127) / 128, NBLK), dim3(256), 0, st, p, hk, kern, B, Tm);
         FD_CHECK_LAUNCH(h, "k_kc_gemm_simt");
     } else {
 #ifndef FD_EMU
+        ScopedTimer tm(h, KC_KC_GEMM, st);
         int rc = tc_kc_gemm(h->tc_state, h->mode, hk, kern, B, Tm, st, h->err, &h->launches);
         if (rc) return rc;
 #endif
@@ -298,6 +373,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             p.res_w = sec(h, FD_S_DB0_RES_W + n * FD_DB_STRIDE);   p.res_b = sec(h, FD_S_DB0_RES_B + n * FD_DB_STRIDE);
             p.conv_w = sec(h, FD_S_DB0_CONV_W + n * FD_DB_STRIDE); p.conv_b = sec(h, FD_S_DB0_CONV_B + n * FD_DB_STRIDE);
             const dim3 grid((tout[n] + DB_TO - 1) / DB_TO, B);
+            ScopedTimer tm(h, KC_DBLOCK, st);
             if (n == 0) { auto k = k_dblock<4, true>;  FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<4>(), st, p, ins[n], outs[n], tin[n], tout[n]); }
             else        { auto k = k_dblock<8, false>; FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<8>(), st, p, ins[n], outs[n], tin[n], tout[n]); }
             FD_CHECK_LAUNCH(h, "k_dblock");
@@ -315,6 +391,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         const float* upb = sec(h, FD_S_LB0_UP_B + n * FD_LB_STRIDE);
         {
             const dim3 grid((Tin + 31) / 32, B);
+            ScopedTimer tm(h, KC_UPSAMPLE, st);
             if (r == 8) { auto k = k_upsample<8>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
             else        { auto k = k_upsample<4>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
             FD_CHECK_LAUNCH(h, "k_upsample");
@@ -329,6 +406,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             int dil = 1; for (int q = 0; q < i; ++q) dil *= 3;
             const float* kl = kern_n + i * KPL;
             bool done = false;
+            ScopedTimer tm(h, KC_LVC0 + n, st);
 #ifndef FD_EMU
             if (h->mode != FD_MODE_FP32_SIMT) {
                 int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done);
@@ -397,8 +475,11 @@ extern "C" int fd_denoise(fd_handle* h, const float* x_dev, const float* mel_dev
     FinalParams fp;
     fill_final(h, fp);
     const int L = Tm * HOP_TOTAL;
-    FD_LAUNCH(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), x_dev, (const float*)nullptr, eps_dev, (float*)nullptr, L);
-    FD_CHECK_LAUNCH(h, "k_final");
+    {
+        ScopedTimer tm(h, KC_FINAL, st);
+        FD_LAUNCH(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), x_dev, (const float*)nullptr, eps_dev, (float*)nullptr, L);
+        FD_CHECK_LAUNCH(h, "k_final");
+    }
     return FD_OK;
 }
 
@@ -421,6 +502,7 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
     const size_t n = (size_t)B * L;
     FD_CUDA(h, cudaMemsetAsync(ws + w.hk, 0, (size_t)NBLK * B * (Tm + 2) * HID * 4, st));
     if (fill_xT) {
+        ScopedTimer tm(h, KC_FILL, st);
         FD_LAUNCH(k_fill_normal, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x_dev, n, seed, 0u);
         FD_CHECK_LAUNCH(h, "k_fill_normal");
     }
@@ -444,6 +526,7 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
             }
         }
         // in-place: every thread reads only its own x element
+        ScopedTimer tm(h, KC_FINAL, st);
         FD_LAUNCH(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), (const float*)x_dev, z, x_dev,
                   seq_dev ? seq_dev + (size_t)(i + 1) * n : (float*)nullptr, L);
         FD_CHECK_LAUNCH(h, "k_final");

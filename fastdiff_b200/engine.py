@@ -118,6 +118,18 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.fd_launch_count(self.h))
 
+    def timing_enable(self, on: bool = True):
+        self._check(self.lib.fd_timing_enable(self.h, int(on)), "fd_timing_enable")
+
+    def timing_report(self) -> dict:
+        """Per-kernel-class device time since the last report; synchronises the device first."""
+        import json
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        buf = C.create_string_buffer(4096)
+        self._check(self.lib.fd_timing_report(self.h, buf, 4096), "fd_timing_report")
+        return json.loads(buf.value.decode())
+
     def denoise(self, x: torch.Tensor, mel: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
         B, Tm = mel.shape[0], mel.shape[2]
         L = Tm * 256

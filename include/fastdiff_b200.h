@@ -132,6 +132,12 @@ int fd_debug_read(fd_handle* h, const char* name, float* out_dev, size_t* count,
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 uint64_t fd_launch_count(fd_handle* h);
 
+/* Optional device timing per kernel class (CUDA events around every launch on the caller's stream).
+ * After the caller has synchronised the stream, fd_timing_report writes one JSON object
+ * {"kc_gemm": {"ms": total, "n": launches}, ...} for the launches since the previous report. */
+int fd_timing_enable(fd_handle* h, int on);
+int fd_timing_report(fd_handle* h, char* buf, size_t buf_bytes);
+
 const char* fd_last_error(fd_handle* h);   /* valid until the next call on h; h may be NULL for create errors */
 void fd_destroy(fd_handle* h);
 const char* fd_version(void);

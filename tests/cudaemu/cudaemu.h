@@ -50,6 +50,7 @@ static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; retu
 // runtime subset
 typedef int cudaError_t;
 typedef void* cudaStream_t;
+typedef void* cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
