@@ -26,6 +26,7 @@ struct fd_handle {
     float final_w[7 * C];        // host copies of tiny tensors passed by value
     float final_b = 0.f;
     int mode = FD_MODE_FP32_SIMT;
+    int mode_set_by_user = 0;
     int stop_after = 99;
     int attrs_set = 0;
     uint64_t launches = 0;
@@ -89,7 +90,7 @@ static const float* sec(const fd_handle* h, int s) { return h->blob + h->sec_off
 
 // ---- workspace layout (floats) ------------------------------------------------------------------
 struct WsLayout {
-    size_t emb, cnoise, hk, kern, d0, d1, d2, xa, xb, total;
+    size_t emb, cnoise, hk, hk_hi, hk_lo, kern, d0, d1, d2, xa, xb, total;
 };
 static WsLayout ws_layout(int B, int Tm) {
     WsLayout w;
@@ -98,7 +99,9 @@ static WsLayout ws_layout(int B, int Tm) {
     size_t o = 0;
     w.emb = o;    o += al((size_t)B * EMB_OUT);
     w.cnoise = o; o += al((size_t)NBLK * B * COND);
-    w.hk = o;     o += al((size_t)NBLK * B * (Tm + 2) * HID);
+    w.hk = o;     o += al((size_t)NBLK * B * (Tm + 2) * HID);   // hk, hk_hi, hk_lo are contiguous (one memset)
+    w.hk_hi = o;  o += al((size_t)NBLK * B * (Tm + 2) * HID);
+    w.hk_lo = o;  o += al((size_t)NBLK * B * (Tm + 2) * HID);
     w.kern = o;   o += al((size_t)NBLK * B * Tm * KCN);
     w.d0 = o;     o += al((size_t)B * (L / 4) * C);
     w.d1 = o;     o += al((size_t)B * (L / 32) * C);
@@ -172,7 +175,8 @@ static int parse_header(fd_handle* h, const uint64_t* hdr, size_t bytes) {
         {FD_S_EMB_FREQ, 64}, {FD_S_FC1_WT, (size_t)EMB_IN * EMB_MID}, {FD_S_FC2_WT, (size_t)EMB_MID * EMB_OUT},
         {FD_S_FIRST_W, 7 * C}, {FD_S_FINAL_W, 7 * C}, {FD_S_DB0_CONV_W, 3 * KK * C}, {FD_S_LB0_UP_W, 16 * C * C},
         {FD_S_LB2_UP_W, 8 * C * C}, {FD_S_LB0_CONV_W, (size_t)LAYERS * KK * C}, {FD_S_LB0_KPIN_W, 5 * COND * HID},
-        {FD_S_LB0_KPRES_W, 6 * 3 * HID * HID}, {FD_S_LB0_KC_W, (size_t)KCK * KCN}, {FD_S_LB2_KC_B, KCN}};
+        {FD_S_LB0_KPRES_W, 6 * 3 * HID * HID}, {FD_S_LB0_KC_W, (size_t)KCK * KCN}, {FD_S_LB2_KC_B, KCN},
+        {FD_S_LB0_KCT_HI, (size_t)KCK * KCN}, {FD_S_LB2_KCT_LO, (size_t)KCK * KCN}};
     for (auto& c : chk)
         if (h->sec_cnt[c.s] != c.n) return fail(h, FD_ERR_INVALID, "weight blob: section %d has the wrong size (%ld)", c.s, (long)h->sec_cnt[c.s]);
     return FD_OK;
@@ -198,6 +202,7 @@ extern "C" int fd_load_weights(fd_handle* h, const void* blob_host, size_t bytes
 #ifndef FD_EMU
     rc = tc_init(&h->tc_state, h->device, h->blob, h->sec_off, h->err);
     if (rc) return rc;
+    if (!h->mode_set_by_user) h->mode = FD_MODE_TC_3XTF32;   // default: tensor cores at fp32-level accuracy
 #endif
     return finish_load(h, (const uint64_t*)blob_host);
 }
@@ -224,6 +229,7 @@ extern "C" int fd_load_weights_dev(fd_handle* h, const void* blob_dev, size_t by
 #ifndef FD_EMU
     rc = tc_init(&h->tc_state, h->device, h->blob, h->sec_off, h->err);
     if (rc) return rc;
+    if (!h->mode_set_by_user) h->mode = FD_MODE_TC_3XTF32;
 #endif
     return FD_OK;
 }
@@ -244,6 +250,7 @@ extern "C" int fd_set_mode(fd_handle* h, int mode) {
         return fail(h, FD_ERR_UNSUPPORTED, "fd_set_mode: tensor-core path unavailable (load weights first)");
 #endif
     h->mode = mode;
+    h->mode_set_by_user = 1;
     return FD_OK;
 }
 extern "C" int fd_get_mode(fd_handle* h) { return h ? h->mode : FD_ERR_INVALID; }
@@ -343,7 +350,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             p.res_w[n] = sec(h, FD_S_LB0_KPRES_W + n * FD_LB_STRIDE); p.res_b[n] = sec(h, FD_S_LB0_KPRES_B + n * FD_LB_STRIDE);
         }
         ScopedTimer tm(h, KC_KP_HIDDEN, st);
-        FD_LAUNCH(k_kp_hidden, dim3((Tm + KP_FT - 1) / KP_FT, B, NBLK), dim3(256), KP_SMEM_BYTES, st, p, mel_dev, cnoise, hk, B, Tm);
+        FD_LAUNCH(k_kp_hidden, dim3((Tm + KP_FT - 1) / KP_FT, B, NBLK), dim3(256), KP_SMEM_BYTES, st, p, mel_dev, cnoise, hk, ws + w.hk_hi, ws + w.hk_lo, B, Tm);
         FD_CHECK_LAUNCH(h, "k_kp_hidden");
     }
     if (h->mode == FD_MODE_FP32_SIMT) {
@@ -356,7 +363,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     } else {
 #ifndef FD_EMU
         ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = tc_kc_gemm(h->tc_state, h->mode, hk, kern, B, Tm, st, h->err, &h->launches);
+        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches);
         if (rc) return rc;
 #endif
     }
@@ -468,7 +475,7 @@ extern "C" int fd_denoise(fd_handle* h, const float* x_dev, const float* mel_dev
     cudaStream_t st = (cudaStream_t)stream;
     float* ws = (float*)workspace_dev;
     const WsLayout w = ws_layout(B, Tm);
-    FD_CUDA(h, cudaMemsetAsync(ws + w.hk, 0, (size_t)NBLK * B * (Tm + 2) * HID * 4, st));
+    FD_CUDA(h, cudaMemsetAsync(ws + w.hk, 0, (w.kern - w.hk) * 4, st));
     rc = run_denoiser(h, x_dev, mel_dev, t_dev, 0.f, B, Tm, ws, st);
     if (rc) return rc;
     if (h->stop_after < 6) return FD_OK;
@@ -500,7 +507,7 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
     const WsLayout w = ws_layout(B, Tm);
     const int L = Tm * HOP_TOTAL;
     const size_t n = (size_t)B * L;
-    FD_CUDA(h, cudaMemsetAsync(ws + w.hk, 0, (size_t)NBLK * B * (Tm + 2) * HID * 4, st));
+    FD_CUDA(h, cudaMemsetAsync(ws + w.hk, 0, (w.kern - w.hk) * 4, st));
     if (fill_xT) {
         ScopedTimer tm(h, KC_FILL, st);
         FD_LAUNCH(k_fill_normal, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x_dev, n, seed, 0u);

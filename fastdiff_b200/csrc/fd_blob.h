@@ -21,17 +21,22 @@
  *   LBn_KPIN_W[5 j][80 ci][64 co]   kernel_predictor.input_conv.0   LBn_KPIN_B [64]
  *   LBn_KPRES_W[6][3 j][64 ci][64 co] kernel_predictor.residual_conv.{1,3,6,8,11,13}   LBn_KPRES_B [6][64]
  *   LBn_KC_W  [192 kk=(j*64+c)][24832 n]   kernel_conv + bias_conv fused along n, permuted so one GEMM row
- *             is, per LVC layer l, the [96 (k*32+i)][64 o] operand of the location-variable conv followed
- *             by its 64 biases:  n = l*6208 + (k*32+i)*64 + o   <- kernel_conv channel ((l*32+i)*64+o)*3+k
- *                                n = l*6208 + 6144 + o          <- bias_conv channel l*64+o
+ *             is, per LVC layer l, the operand of the location-variable conv in K-major "panel" order
+ *             [k 3][i/4 8][o 64][i%4 4] (16-byte chunks of 4 input channels: directly a no-swizzle K-major UMMA
+ *             operand, and one conflict-free LDS.128 per lane for the SIMT kernel) followed by its 64 biases:
+ *                                n = l*6208 + ((k*8 + i/4)*64 + o)*4 + i%4   <- kernel_conv channel ((l*32+i)*64+o)*3+k
+ *                                n = l*6208 + 6144 + o                       <- bias_conv channel l*64+o
  *             (channel maps: modules.py:333-342)
  *   LBn_KC_B  [24832]         same permutation of the two bias vectors
+ *   LBn_KCT_HI / LBn_KCT_LO [24832 n][192 kk]   the same matrix transposed (K-major rows: the tcgen05 A operand),
+ *             split into tf32 pieces  w = hi + lo,  hi = RN_tf32(w), lo = RN_tf32(w - hi)  (low 13 mantissa bits zero)
+ *   LBn_CONVT_HI / LBn_CONVT_LO [4 layers][3 k][8 ci/4][32 co][4 ci%4]   lvc_blocks.n.convs.* as K-major UMMA panels, tf32 pieces
  */
 #ifndef FD_BLOB_H
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 2ULL
+#define FD_BLOB_VERSION 4ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */
@@ -42,11 +47,11 @@
     X(DB1_RES_W) X(DB1_RES_B) X(DB1_CONV_W) X(DB1_CONV_B) \
     X(DB2_RES_W) X(DB2_RES_B) X(DB2_CONV_W) X(DB2_CONV_B) \
     X(LB0_FCT_WT) X(LB0_FCT_B) X(LB0_UP_W) X(LB0_UP_B) X(LB0_CONV_W) X(LB0_CONV_B) \
-    X(LB0_KPIN_W) X(LB0_KPIN_B) X(LB0_KPRES_W) X(LB0_KPRES_B) X(LB0_KC_W) X(LB0_KC_B) \
+    X(LB0_KPIN_W) X(LB0_KPIN_B) X(LB0_KPRES_W) X(LB0_KPRES_B) X(LB0_KC_W) X(LB0_KC_B) X(LB0_KCT_HI) X(LB0_KCT_LO) X(LB0_CONVT_HI) X(LB0_CONVT_LO) \
     X(LB1_FCT_WT) X(LB1_FCT_B) X(LB1_UP_W) X(LB1_UP_B) X(LB1_CONV_W) X(LB1_CONV_B) \
-    X(LB1_KPIN_W) X(LB1_KPIN_B) X(LB1_KPRES_W) X(LB1_KPRES_B) X(LB1_KC_W) X(LB1_KC_B) \
+    X(LB1_KPIN_W) X(LB1_KPIN_B) X(LB1_KPRES_W) X(LB1_KPRES_B) X(LB1_KC_W) X(LB1_KC_B) X(LB1_KCT_HI) X(LB1_KCT_LO) X(LB1_CONVT_HI) X(LB1_CONVT_LO) \
     X(LB2_FCT_WT) X(LB2_FCT_B) X(LB2_UP_W) X(LB2_UP_B) X(LB2_CONV_W) X(LB2_CONV_B) \
-    X(LB2_KPIN_W) X(LB2_KPIN_B) X(LB2_KPRES_W) X(LB2_KPRES_B) X(LB2_KC_W) X(LB2_KC_B)
+    X(LB2_KPIN_W) X(LB2_KPIN_B) X(LB2_KPRES_W) X(LB2_KPRES_B) X(LB2_KC_W) X(LB2_KC_B) X(LB2_KCT_HI) X(LB2_KCT_LO) X(LB2_CONVT_HI) X(LB2_CONVT_LO)
 /* FD_SECTIONS_END */
 
 enum fd_section {
@@ -58,6 +63,6 @@ enum fd_section {
 
 /* stride between the per-block groups above */
 #define FD_DB_STRIDE 4
-#define FD_LB_STRIDE 12
+#define FD_LB_STRIDE 16
 
 #endif

@@ -43,6 +43,12 @@ __host__ __device__ inline int down_factor(int n) { return n == 0 ? 4 : 8; }    
 #define FD_SEL3(arr, i) ((i) == 0 ? (arr)[0] : ((i) == 1 ? (arr)[1] : (arr)[2]))
 
 __device__ __forceinline__ float lrelu(float v, float slope) { return v > 0.f ? v : v * slope; }
+// round-to-nearest-even to tf32, kept in an fp32 container with the low 13 mantissa bits zero (== weights.tf32_round)
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t u = __float_as_uint(x);
+    u = (u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
+    return __uint_as_float(u);
+}
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
 }  // namespace fd

@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __res
 //   cond = mel + fc_t(e);  h0 = lrelu_.1(conv5(cond));  h = h0 + R(h0), R = 6 x [conv3 + lrelu_.1]
 // One CTA = 32 output frames of one (block, batch item), halo (8 frames) recomputed.
 // Output hk: (3, B, T'+2, 64) channels-last with one zero frame either side of every item, so the
-// kernel_conv im2col row of frame f is the 192 contiguous floats starting at padded row f.
+// kernel_conv im2col row of frame f is the 192 contiguous floats starting at padded row f.  Written three
+// times: raw fp32 (SIMT GEMM) and as tf32 pieces hi/lo (tensor-core GEMM operands).
 // grid = (ceil(T'/32), B, 3), block = 256, dynamic smem = KP_SMEM_BYTES.
 // ------------------------------------------------------------------------------------------------
 struct KpParams {
@@ -76,7 +77,7 @@ constexpr int KP_SMEM_BYTES = (COND * KP_CS + 3 * HID * KP_HS) * 4;
 
 __global__ void __launch_bounds__(256) k_kp_hidden(KpParams p, const float* __restrict__ mel,
                                                    const float* __restrict__ cnoise, float* __restrict__ hk_all,
-                                                   int B, int Tm) {
+                                                   float* __restrict__ hk_hi_all, float* __restrict__ hk_lo_all, int B, int Tm) {
     FD_DYN_SMEM(float, sm);
     float* cond_s = sm;
     float* h0_s = cond_s + COND * KP_CS;
@@ -152,12 +153,18 @@ __global__ void __launch_bounds__(256) k_kp_hidden(KpParams p, const float* __re
             __syncthreads();
             src = dst;
         } else {
-            float* hk = hk_all + (size_t)(blk * B + b) * (Tm + 2) * HID;
+            const size_t item = (size_t)(blk * B + b) * (Tm + 2) * HID;
 #pragma unroll
             for (int r = 0; r < 11; ++r) {
                 const int row = r0 + r, f = f0 + row - 6;
-                if (row >= 6 && row < 6 + KP_FT && f < Tm)
-                    hk[(size_t)(1 + f) * HID + co] = h0_s[co * KP_HS + 1 + row] + lrelu(acc[r], 0.1f);
+                if (row >= 6 && row < 6 + KP_FT && f < Tm) {
+                    const float v = h0_s[co * KP_HS + 1 + row] + lrelu(acc[r], 0.1f);
+                    const size_t o = item + (size_t)(1 + f) * HID + co;
+                    hk_all[o] = v;
+                    const float hi = tf32_rn(v);       // tf32 pieces for the tensor-core GEMM (3xTF32)
+                    hk_hi_all[o] = hi;
+                    hk_lo_all[o] = tf32_rn(v - hi);
+                }
             }
         }
     }
@@ -554,12 +561,10 @@ __global__ void __launch_bounds__(256) k_lvc_layer(LvcParams p, const float* __r
             for (int k = 0; k < 3; ++k) {
 #pragma unroll 2
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    float w0[4], w1[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        w0[q] = W[(k * C + c4 * 4 + q) * LVC_OUT + lane];
-                        w1[q] = W[(k * C + c4 * 4 + q) * LVC_OUT + C + lane];
-                    }
+                    // panel order [k][i/4][o][i%4]: one 16-byte vector per lane holds the 4 input channels of chunk c4
+                    const float4 wa = *reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + lane) * 4);
+                    const float4 wb = *reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + C + lane) * 4);
+                    const float w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
                     for (int n = 0; n < 8; ++n) {
                         const float4 v = y4[(base + n + k) * 8 + c4];
@@ -695,7 +700,7 @@ __global__ void __launch_bounds__(256) k_kern_to_ref(const float* __restrict__ k
         const int ci = (int)(q % C); q /= C;
         const int l = (int)(q % LAYERS); q /= LAYERS;
         const int b = (int)q;
-        out[i] = kern[((size_t)b * Tm + f) * KCN + l * KPL + (k * C + ci) * LVC_OUT + o];
+        out[i] = kern[((size_t)b * Tm + f) * KCN + l * KPL + ((k * 8 + ci / 4) * LVC_OUT + o) * 4 + (ci & 3)];
     } else {  // (B,4,64,T')
         if (i >= (size_t)B * LAYERS * LVC_OUT * Tm) return;
         size_t q = i;

@@ -1,12 +1,706 @@
-// tcgen05 / TMA path (placeholder until the tensor-core kernels land).
+// tcgen05 / TMEM / TMA kernels (sm_100a) for the heavy contractions.
+//
+// Arithmetic: kind::tf32 MMAs with fp32 accumulation in TMEM.  FD_MODE_TC_3XTF32 splits BOTH operands into
+// explicit tf32 pieces  x = hi + lo  (hi = RN_tf32(x), lo = RN_tf32(x - hi); low 13 mantissa bits stored as zero, so
+// the tensor core's fp32->tf32 conversion is exact whatever its rounding) and accumulates hi*hi + hi*lo + lo*hi:
+// ~2^-21 relative per product, i.e. fp32-level.  FD_MODE_TC_TF32 issues only hi*hi.
+//
+// K8+K9  kernel_conv + bias_conv GEMM (modules.py:330-331), "swap-AB":
+//     D[n, p] = sum_k WT[n][k] * hkpad[p*64 + k]        n < 24832 (M side, 128 per tile), p = padded frame row (N side)
+//   A = weights, K-major rows of 192 floats (packer sections LBn_KCT_HI / _LO), TMA box {32 k, 128 n}
+//   B = kernel-predictor hidden rows; the im2col row of frame p is the 192 contiguous floats starting at
+//       hk[p*64], so k-atom a (32 floats) of row p is the plain 2-D box at (col (a&1)*32, row p + a/2)
+//   D in TMEM: lane = n, column = frame  ->  the epilogue thread of lane n holds consecutive frames in
+//   registers and a warp stores 32 consecutive n of one frame = one coalesced 128-byte line of
+//   kern[(b,f)][n]; no smem staging, bias added per lane.
+// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+// Persistent CTAs (grid = #SM), 2-stage smem ring (96 KB/stage), 2 x 256-column TMEM accumulators.
 #pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
 #include <string>
+#include "fd_blob.h"
 #include "fd_common.cuh"
+
 namespace fd {
-static inline int tc_init(void** state, int, const float*, const uint64_t*, std::string&) { *state = nullptr; return 0; }
-static inline void tc_destroy(void*) {}
-static inline bool tc_available(void*) { return false; }
-static inline int tc_kc_gemm(void*, int, const float*, float*, int, int, cudaStream_t, std::string&, uint64_t*) { return -2; }
-static inline int tc_lvc_layer(void*, int, int, int, const float*, const float*, const float*, float*, int, int, int, int,
-                               cudaStream_t, std::string&, uint64_t*, bool* done) { *done = false; return 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by one thread.
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor,
+// cute/arch/mma_sm100_desc.hpp: start>>4 [0,14), LBO [16,30), SBO [32,46), version=1 [46,48), layout [61,64) = 2).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;              // LBO (unused for swizzled K-major; canonical value 1)
+    d |= (uint64_t)(1024 >> 4) << 32;    // SBO: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel_conv GEMM
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KCG_BM = 128;                 // n rows per tile (MMA M)
+constexpr int KCG_BN = 256;                 // frames per tile (MMA N)
+constexpr int KCG_KATOM = 32;               // floats per 128-byte swizzle row
+constexpr int KCG_NATOM = KCK / KCG_KATOM;  // 6
+constexpr int KCG_STAGES = 2;
+constexpr int KCG_A_BYTES = KCG_BM * 128;   // 16 KB
+constexpr int KCG_B_BYTES = KCG_BN * 128;   // 32 KB
+constexpr int KCG_STAGE_BYTES = 2 * KCG_A_BYTES + 2 * KCG_B_BYTES;  // A_hi | A_lo | B_hi | B_lo = 96 KB
+constexpr int KCG_SMEM_BYTES = KCG_STAGES * KCG_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct KcgMaps {               // per LVC block: weights hi/lo, hidden hi/lo
+    CUtensorMap w_hi[NBLK], w_lo[NBLK], h_hi[NBLK], h_lo[NBLK];
+};
+
+__global__ void __launch_bounds__(256, 1)
+k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
+             const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + KCG_STAGES * KCG_STAGE_BYTES);
+    uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + KCG_STAGES;      // [STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * KCG_STAGES;  // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = tfull_bar + 2;         // [2]       epilogue -> MMA
+    uint32_t* tmem_base_s = (uint32_t*)(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int M = B * (Tm + 2) - 2;                       // padded frame rows
+    const int f_tiles = (M + KCG_BN - 1) / KCG_BN;
+    const int n_tiles = KCN / KCG_BM;                     // 194
+    const int tiles_per_blk = n_tiles * f_tiles;
+    const int total_tiles = NBLK * tiles_per_blk;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < KCG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int blk = tile / tiles_per_blk, r = tile % tiles_per_blk;
+                const int ft = r / n_tiles, nt = r % n_tiles;   // n fastest: consecutive CTAs share the frame tile
+                const CUtensorMap* wh = &maps.w_hi[blk]; const CUtensorMap* wl = &maps.w_lo[blk];
+                const CUtensorMap* hh = &maps.h_hi[blk]; const CUtensorMap* hl = &maps.h_lo[blk];
+                for (int a = 0; a < KCG_NATOM; ++a) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* st = smem + stage * KCG_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], three_pass ? KCG_STAGE_BYTES : (KCG_A_BYTES + KCG_B_BYTES));
+                    tma_load_2d(st, wh, a * KCG_KATOM, nt * KCG_BM, &full_bar[stage]);
+                    tma_load_2d(st + 2 * KCG_A_BYTES, hh, (a & 1) * KCG_KATOM, ft * KCG_BN + (a >> 1), &full_bar[stage]);
+                    if (three_pass) {
+                        tma_load_2d(st + KCG_A_BYTES, wl, a * KCG_KATOM, nt * KCG_BM, &full_bar[stage]);
+                        tma_load_2d(st + 2 * KCG_A_BYTES + KCG_B_BYTES, hl, (a & 1) * KCG_KATOM, ft * KCG_BN + (a >> 1), &full_bar[stage]);
+                    }
+                    if (++stage == KCG_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(KCG_BM, KCG_BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * KCG_BN;
+                for (int a = 0; a < KCG_NATOM; ++a) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * KCG_STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + KCG_A_BYTES);
+                    const uint64_t b_hi = umma_desc_sw128(st + 2 * KCG_A_BYTES), b_lo = umma_desc_sw128(st + 2 * KCG_A_BYTES + KCG_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < KCG_KATOM / 8; ++k) {   // UMMA_K = 8 tf32 = 32 bytes: advance start address by 2 (16-B units)
+                        const uint64_t adv = (uint64_t)(k * 2);
+                        umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
+                        if (three_pass) {
+                            umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&empty_bar[stage]);              // smem slot free once these MMAs have read it
+                    if (++stage == KCG_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);                    // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: TMEM -> registers -> (+bias) -> global =================
+        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        uint32_t acc = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int blk = tile / tiles_per_blk, r = tile % tiles_per_blk;
+            const int ft = r / n_tiles, nt = r % n_tiles;
+            const int n = nt * KCG_BM + q * 32 + lane;
+            const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
+            const float bv = bias[n];
+            float* kern = kern_all + (size_t)blk * B * Tm * KCN;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * KCG_BN;
+            int p = ft * KCG_BN;                       // padded row of column 0
+            int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
+            for (int c0 = 0; c0 < KCG_BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(taddr + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (p < M && fp >= 1 && fp <= Tm)
+                        kern[((size_t)bb * Tm + (fp - 1)) * KCN + n] = __uint_as_float(v[j]) + bv;
+                    ++p;
+                    if (++fp == Tm + 2) { fp = 0; ++bb; }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcState {
+    int device = 0, sm_count = 148;
+    PFN_encodeTiled encode = nullptr;
+    const float* blob = nullptr;
+    uint64_t sec_off[FD_S_COUNT];
+    CUtensorMap w_hi[NBLK], w_lo[NBLK];
+    bool ok = false;
+};
+
+static inline int tc_make_map_2d(TcState* s, CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+                                 uint32_t box_cols, uint32_t box_rows, std::string& err) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = s->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return -3; }
+    return 0;
+}
+
+static inline cudaError_t tc_set_lvc_attrs();
+static inline void tc_destroy(void* st) { delete (TcState*)st; }
+static inline bool tc_available(void* st) { return st && ((TcState*)st)->ok; }
+
+static inline int tc_init(void** state, int device, const float* blob, const uint64_t* sec_off, std::string& err) {
+    tc_destroy(*state);
+    TcState* s = new TcState();
+    *state = s;
+    s->device = device; s->blob = blob;
+    for (int i = 0; i < FD_S_COUNT; ++i) s->sec_off[i] = sec_off[i];
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+        err = "cuTensorMapEncodeTiled entry point unavailable"; return -3;
+    }
+    s->encode = (PFN_encodeTiled)fn;
+    for (int n = 0; n < NBLK; ++n) {
+        if (tc_make_map_2d(s, &s->w_hi[n], blob + sec_off[FD_S_LB0_KCT_HI + n * FD_LB_STRIDE], KCK, KCN, KCK * 4, KCG_KATOM, KCG_BM, err)) return -3;
+        if (tc_make_map_2d(s, &s->w_lo[n], blob + sec_off[FD_S_LB0_KCT_LO + n * FD_LB_STRIDE], KCK, KCN, KCK * 4, KCG_KATOM, KCG_BM, err)) return -3;
+    }
+    if (cudaFuncSetAttribute(k_kc_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KCG_SMEM_BYTES) != cudaSuccess ||
+        tc_set_lvc_attrs() != cudaSuccess) {
+        err = "cudaFuncSetAttribute(tensor-core kernels) failed"; return -3;
+    }
+    s->ok = true;
+    return 0;
+}
+
+// hk_hi / hk_lo: (3, B, T'+2, 64) each, written by k_kp_hidden.
+static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st,
+                             std::string& err, uint64_t* launches) {
+    TcState* s = (TcState*)state;
+    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    KcgMaps maps;
+    const uint64_t rows = (uint64_t)B * (Tm + 2);
+    for (int n = 0; n < NBLK; ++n) {
+        maps.w_hi[n] = s->w_hi[n]; maps.w_lo[n] = s->w_lo[n];
+        if (tc_make_map_2d(s, &maps.h_hi[n], hk_hi + (size_t)n * rows * HID, HID, rows, HID * 4, KCG_KATOM, KCG_BN, err)) return -3;
+        if (tc_make_map_2d(s, &maps.h_lo[n], hk_lo + (size_t)n * rows * HID, HID, rows, HID * 4, KCG_KATOM, KCG_BN, err)) return -3;
+    }
+    const int M = B * (Tm + 2) - 2;
+    const int total = NBLK * (KCN / KCG_BM) * ((M + KCG_BN - 1) / KCG_BN);
+    const int grid = total < s->sm_count ? total : s->sm_count;
+    k_kc_gemm_tc<<<grid, 256, KCG_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                    s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, mode == 1 ? 1 : 0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K11+K12+K13  one LVC layer on tensor cores (modules.py:208-217), blocks 1 (hop 64) and 2 (hop 256).
+//
+// Per tile of 128 time steps (one batch item), all operands K-major, NO swizzle, in "panel" order: a tile of R rows x 32
+// channels is stored as 8 panels (one per 16-byte chunk of 4 channels), panel c = R consecutive 16-byte rows.  In UMMA
+// terms ((8,m),(4,2)):((16B,SBO=128B),(4B,LBO=panel stride)); a dilated-conv tap is then just start address + shift*16 B,
+// for ANY shift (no swizzle-phase constraint), which is what makes the im2col free.
+//   conv :  D1[128 rows x 32]  = sum_{k<3} A[rows + (k-1)*dil][32 ci] * Wc[k][32 co x 32 ci]^T    rows t0-1 .. t0+126;
+//           the LVC also needs y at t0+127, t0+128: those 2 rows are computed with FFMA while the MMAs run
+//   y = lrelu(D1 + b) -> tf32 pieces -> panels (aliasing the A tile)
+//   lvc  :  D2[128 x 64] = sum_{k<3} Y[rows + k][32] * Wl[f][k][64 o x 32 i]^T   with the per-frame predicted kernels
+//           (hop 64: two frames per tile, each run over the whole M-tile into its own TMEM columns; rows pick their frame)
+//   out = xs + sigmoid(D2[:, :32] + b) * tanh(D2[:, 32:] + b),  xs = x + skip re-read from global
+// 3xTF32: every MMA is issued for (hi,hi), (hi,lo), (lo,hi).
+// One persistent CTA per SM with GROUPS independent 8-warp groups, each owning a tile slot (smem operands, TMEM columns,
+// mbarriers, a named barrier) and walking its own tile sequence, so one group's global loads / epilogues overlap the
+// other's MMAs.  Thread 0 of a group issues its MMAs.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LT_TT = 128;
+constexpr int LT_A_ROWS = 184;                      // conv input rows: t0-28 .. t0+155
+constexpr int LT_PANEL_A = LT_A_ROWS * 16 + 16;     // 2960 B (odd multiple of 16: conflict-free panel writes)
+constexpr int LT_Y_ROWS = 136;
+constexpr int LT_PANEL_Y = LT_Y_ROWS * 16 + 16;     // 2192 B
+constexpr int LT_A_BYTES = 8 * LT_PANEL_A;          // 23680
+constexpr int LT_CW_BYTES = 3 * 8 * C * 16;         // 12288
+constexpr int LT_LW_BYTES = KK * LVC_OUT * 4;       // 24576
+constexpr int LT_AU = 352;                          // audio samples staged per tile (SKIP_FIRST)
+template <int HOP>
+__host__ __device__ constexpr int lt_nf() { return LT_TT / HOP > 0 ? LT_TT / HOP : 1; }
+template <int HOP>
+__host__ __device__ constexpr int lt_slot_bytes() { return 2 * LT_A_BYTES + lt_nf<HOP>() * (2 * LT_LW_BYTES + 256) + LT_AU * 4; }
+constexpr int LT_SHARED_BYTES = 2 * LT_CW_BYTES + (7 * C + C + C) * 4 + 64;   // conv W pieces, first_w, first_b, conv_b, barriers+tmem ptr
+template <int HOP, int GROUPS>
+constexpr int lt_smem_bytes() { return GROUPS * lt_slot_bytes<HOP>() + LT_SHARED_BYTES + 1024; }
+
+__device__ __forceinline__ uint64_t umma_desc_ns(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;   // version; layout_type 0 = no swizzle
+    return d;
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// tf32 pieces with the conversion instruction (round-to-nearest; low 13 bits come back zero)
+__device__ __forceinline__ float cvt_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+    hi = make_float4(cvt_tf32(v.x), cvt_tf32(v.y), cvt_tf32(v.z), cvt_tf32(v.w));
+    lo = make_float4(cvt_tf32(v.x - hi.x), cvt_tf32(v.y - hi.y), cvt_tf32(v.z - hi.z), cvt_tf32(v.w - hi.w));
+}
+// gate non-linearities from ex2.approx/rcp.approx: abs error ~2e-7 (the precise tanhf/expf forms cost ~10x the instructions)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + exp2f(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + exp2f(2.8853900817779268f * x)); }
+
+struct LvcTcParams {
+    const float* cw_hi; const float* cw_lo;      // [3][8][32][4] tf32 pieces of this layer's dilated conv
+    const float* conv_b;                         // [32]
+    const float* first_w; const float* first_b;  // [7][32], [32]   (SKIP_FIRST)
+};
+
+template <int HOP, bool SKIP_FIRST, int GROUPS>
+__global__ void __launch_bounds__(256 * GROUPS, 1)
+k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
+               float* __restrict__ x_out, int B, int T, int Tm, int dil, int three_pass) {
+    constexpr int NF = lt_nf<HOP>();
+    constexpr int SLOT = lt_slot_bytes<HOP>();
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* cw_hi = smem + GROUPS * SLOT;
+    unsigned char* cw_lo = cw_hi + LT_CW_BYTES;
+    float* fw_s = (float*)(cw_lo + LT_CW_BYTES);         // [7][32] first_audio_conv weights
+    float* fb_s = fw_s + 7 * C;                          // [32]
+    float* cb_s = fb_s + C;                              // [32] dilated-conv bias
+    uint64_t* bars = (uint64_t*)(cb_s + C);              // [GROUPS][2]
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 4);
+
+    const int tid = threadIdx.x, g = tid >> 8, gt = tid & 255, gw = gt >> 5, lane = tid & 31;
+    unsigned char* slot = smem + g * SLOT;
+    unsigned char* a_hi = slot;                           // A panels (hi) | later: Y panels (hi)
+    unsigned char* a_lo = a_hi + LT_A_BYTES;
+    unsigned char* lw_hi = a_lo + LT_A_BYTES;             // [NF][24576]
+    unsigned char* lw_lo = lw_hi + NF * LT_LW_BYTES;
+    float* lbias = (float*)(lw_lo + NF * LT_LW_BYTES);    // [NF][64]
+    float* au_s = lbias + NF * 64;                        // [LT_AU]
+    uint64_t* bar = bars + 2 * g;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2 * GROUPS; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // per-layer constants: the global order of the conv weights is already the smem panel image
+        const float4* sh = reinterpret_cast<const float4*>(p.cw_hi); const float4* sl = reinterpret_cast<const float4*>(p.cw_lo);
+        for (int i = tid; i < LT_CW_BYTES / 16; i += 256 * GROUPS) {
+            reinterpret_cast<float4*>(cw_hi)[i] = sh[i];
+            reinterpret_cast<float4*>(cw_lo)[i] = sl[i];
+        }
+        if (tid < 7 * C) fw_s[tid] = SKIP_FIRST ? p.first_w[tid] : 0.f;
+        if (tid < C) { fb_s[tid] = SKIP_FIRST ? p.first_b[tid] : 0.f; cb_s[tid] = p.conv_b[tid]; }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s + g * 128;   // group columns: [0,32) conv, [32, 32+64*NF) lvc
+    constexpr uint32_t idesc_conv = umma_idesc_tf32(128, 32), idesc_lvc = umma_idesc_tf32(128, 64);
+
+    // phase-1 role of this thread is fixed: channel chunk c4 = gt & 7 -> keep its first-conv taps in registers
+    const int c4 = gt & 7;
+    float fwr[7][4], fbr[4];
+    if (SKIP_FIRST) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) fwr[k][q] = fw_s[k * C + c4 * 4 + q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) fbr[q] = fb_s[c4 * 4 + q];
+    }
+
+    const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt;
+    uint32_t parity = 0;
+    for (int tile = blockIdx.x * GROUPS + g; tile < total; tile += gridDim.x * GROUPS, parity ^= 1) {
+        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+        // ---------------- phase 1: operands -> smem panels ----------------
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) {   // predicted LVC kernels of the frame(s): split into tf32 pieces
+            const int f = t0 / HOP + fi;
+            if (f < Tm) {
+                const float4* src = reinterpret_cast<const float4*>(kern + ((size_t)b * Tm + f) * KCN);
+                float4 v[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) v[i] = src[gt + i * 256];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    float4 hi, lo;
+                    split4(v[i], hi, lo);
+                    reinterpret_cast<float4*>(lw_hi + fi * LT_LW_BYTES)[gt + i * 256] = hi;
+                    reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES)[gt + i * 256] = lo;
+                }
+                if (gt < 64) lbias[fi * 64 + gt] = kern[((size_t)b * Tm + f) * KCN + KK * LVC_OUT + gt];
+            }
+        }
+        if (SKIP_FIRST) {
+            for (int i = gt; i < LT_AU; i += 256) {   // au_s[i] <-> audio position t0 - 31 + i
+                const int pos = t0 - 31 + i;
+                au_s[i] = (pos >= 0 && pos < T) ? skip[(size_t)b * T + pos] : 0.f;
+            }
+            group_sync(1 + g, 256);
+        }
+        {   // A rows ar <-> t = t0 - 28 + ar; rows the 130 conv outputs touch: ar in [27-dil, 157+dil)
+            const int r_hi = 157 + dil;
+            for (int ar = 27 - dil + (gt >> 3); ar < r_hi; ar += 32) {
+                const int t = t0 - 28 + ar;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t >= 0 && t < T) {
+                    const float4 xv = reinterpret_cast<const float4*>(x_in)[((size_t)b * T + t) * 8 + c4];
+                    float4 sk;
+                    if (SKIP_FIRST) {
+                        sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) {
+                            const float a = au_s[ar + k];
+                            sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
+                            sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
+                        }
+                    } else {
+                        sk = reinterpret_cast<const float4*>(skip)[((size_t)b * T + t) * 8 + c4];
+                    }
+                    v.x = lrelu(xv.x + sk.x, 0.2f); v.y = lrelu(xv.y + sk.y, 0.2f);
+                    v.z = lrelu(xv.z + sk.z, 0.2f); v.w = lrelu(xv.w + sk.w, 0.2f);
+                }
+                float4 hi, lo;
+                split4(v, hi, lo);
+                *reinterpret_cast<float4*>(a_hi + c4 * LT_PANEL_A + ar * 16) = hi;
+                *reinterpret_cast<float4*>(a_lo + c4 * LT_PANEL_A + ar * 16) = lo;
+            }
+        }
+        fence_async_smem();
+        group_sync(1 + g, 256);
+        // ---------------- phase 2: dilated conv on tensor cores (+ 2 halo rows on FFMA meanwhile) ----------------
+        if (gt == 0) {
+            tc_fence_after();
+            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), wh = smem_u32(cw_hi), wl = smem_u32(cw_lo);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t arow = (uint32_t)((27 + (k - 1) * dil) * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t aoff = 2 * j * LT_PANEL_A + arow, boff = (uint32_t)((k * 8 + 2 * j) * C * 16);
+                    const uint64_t dah = umma_desc_ns(ah + aoff, LT_PANEL_A, 128), dal = umma_desc_ns(al + aoff, LT_PANEL_A, 128);
+                    const uint64_t dbh = umma_desc_ns(wh + boff, C * 16, 128), dbl = umma_desc_ns(wl + boff, C * 16, 128);
+                    umma_tf32(tmem_base, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
+                    if (three_pass) {
+                        umma_tf32(tmem_base, dah, dbl, idesc_conv, 1u);
+                        umma_tf32(tmem_base, dal, dbh, idesc_conv, 1u);
+                    }
+                }
+            }
+            tc_commit(&bar[0]);
+        }
+        __syncwarp();
+        float halo = 0.f;   // warps 6,7 of the group: conv outputs yr = 128 (warp 6), 129 (warp 7), lane = co
+        if (gw >= 6) {
+            const int yr = 128 + (gw - 6);
+            float acc = cb_s[lane];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int ar = yr + 27 + (k - 1) * dil;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 ah4 = *reinterpret_cast<const float4*>(a_hi + c * LT_PANEL_A + ar * 16);
+                    const float4 al4 = *reinterpret_cast<const float4*>(a_lo + c * LT_PANEL_A + ar * 16);
+                    const float4 wh4 = *reinterpret_cast<const float4*>(cw_hi + ((k * 8 + c) * C + lane) * 16);
+                    const float4 wl4 = *reinterpret_cast<const float4*>(cw_lo + ((k * 8 + c) * C + lane) * 16);
+                    acc = fmaf(ah4.x + al4.x, wh4.x + wl4.x, acc); acc = fmaf(ah4.y + al4.y, wh4.y + wl4.y, acc);
+                    acc = fmaf(ah4.z + al4.z, wh4.z + wl4.z, acc); acc = fmaf(ah4.w + al4.w, wh4.w + wl4.w, acc);
+                }
+            }
+            const int t = t0 - 1 + yr;
+            halo = (t >= 0 && t < T) ? lrelu(acc, 0.2f) : 0.f;
+        }
+        // ---------------- phase 3: y = lrelu(conv + b) -> tf32 panels (over the A tile) ----------------
+        mbar_wait(&bar[0], parity);
+        tc_fence_after();
+        group_sync(1 + g, 256);   // Y aliases A: the halo warps must have finished READING A before anyone writes Y
+        if (gw < 4) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16), v);
+            tmem_ld_wait();
+            const int yr = gw * 32 + lane, t = t0 - 1 + yr;
+            const bool in = (t >= 0 && t < T);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 y;
+                y.x = in ? lrelu(__uint_as_float(v[c * 4 + 0]) + cb_s[c * 4 + 0], 0.2f) : 0.f;
+                y.y = in ? lrelu(__uint_as_float(v[c * 4 + 1]) + cb_s[c * 4 + 1], 0.2f) : 0.f;
+                y.z = in ? lrelu(__uint_as_float(v[c * 4 + 2]) + cb_s[c * 4 + 2], 0.2f) : 0.f;
+                y.w = in ? lrelu(__uint_as_float(v[c * 4 + 3]) + cb_s[c * 4 + 3], 0.2f) : 0.f;
+                float4 hi, lo;
+                split4(y, hi, lo);
+                *reinterpret_cast<float4*>(a_hi + c * LT_PANEL_Y + yr * 16) = hi;
+                *reinterpret_cast<float4*>(a_lo + c * LT_PANEL_Y + yr * 16) = lo;
+            }
+        } else if (gw >= 6) {
+            const int yr = 128 + (gw - 6);
+            const float hi = cvt_tf32(halo), lo = cvt_tf32(halo - hi);
+            *reinterpret_cast<float*>(a_hi + (lane >> 2) * LT_PANEL_Y + yr * 16 + (lane & 3) * 4) = hi;
+            *reinterpret_cast<float*>(a_lo + (lane >> 2) * LT_PANEL_Y + yr * 16 + (lane & 3) * 4) = lo;
+        }
+        fence_async_smem();
+        tc_fence_before();
+        group_sync(1 + g, 256);
+        // ---------------- phase 4: location-variable conv on tensor cores ----------------
+        if (gt == 0) {
+            tc_fence_after();
+            const uint32_t yh = smem_u32(a_hi), yl = smem_u32(a_lo);
+#pragma unroll
+            for (int fi = 0; fi < NF; ++fi) {
+                const uint32_t d = tmem_base + 32 + fi * 64;
+                const uint32_t wh = smem_u32(lw_hi + fi * LT_LW_BYTES), wl = smem_u32(lw_lo + fi * LT_LW_BYTES);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t aoff = 2 * j * LT_PANEL_Y + k * 16, boff = (uint32_t)((k * 8 + 2 * j) * LVC_OUT * 16);
+                        const uint64_t dah = umma_desc_ns(yh + aoff, LT_PANEL_Y, 128), dal = umma_desc_ns(yl + aoff, LT_PANEL_Y, 128);
+                        const uint64_t dbh = umma_desc_ns(wh + boff, LVC_OUT * 16, 128), dbl = umma_desc_ns(wl + boff, LVC_OUT * 16, 128);
+                        umma_tf32(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
+                        if (three_pass) {
+                            umma_tf32(d, dah, dbl, idesc_lvc, 1u);
+                            umma_tf32(d, dal, dbh, idesc_lvc, 1u);
+                        }
+                    }
+                }
+            }
+            tc_commit(&bar[1]);
+        }
+        __syncwarp();
+        // ---------------- phase 5: gate + residual -> global ----------------
+        {
+            const int q = gw & 3, half = gw >> 2;              // lane quarter / which 16 of the 32 gate channels
+            const int r = q * 32 + lane, t = t0 + r;
+            const int fi = (HOP >= LT_TT) ? 0 : r / HOP;       // warp-uniform (HOP is a multiple of 32)
+            const size_t row = ((size_t)b * T + (t < T ? t : 0)) * C + half * 16;
+            float4 xs[4];                                      // residual base, fetched while the MMAs run
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                xs[c] = *reinterpret_cast<const float4*>(x_in + row + c * 4);
+                if (SKIP_FIRST) {
+                    const int o = half * 16 + c * 4;
+                    float4 sk = *reinterpret_cast<const float4*>(fb_s + o);
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const float a = au_s[28 + r + k];
+                        const float4 w = *reinterpret_cast<const float4*>(fw_s + k * C + o);
+                        sk.x = fmaf(w.x, a, sk.x); sk.y = fmaf(w.y, a, sk.y); sk.z = fmaf(w.z, a, sk.z); sk.w = fmaf(w.w, a, sk.w);
+                    }
+                    xs[c].x += sk.x; xs[c].y += sk.y; xs[c].z += sk.z; xs[c].w += sk.w;
+                } else {
+                    const float4 sk = *reinterpret_cast<const float4*>(skip + row + c * 4);
+                    xs[c].x += sk.x; xs[c].y += sk.y; xs[c].z += sk.z; xs[c].w += sk.w;
+                }
+            }
+            mbar_wait(&bar[1], parity);
+            tc_fence_after();
+            uint32_t zs[16], zt[16];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 32 + fi * 64 + half * 16;
+            tmem_ld_32x32b_x16(ta, zs);
+            tmem_ld_32x32b_x16(ta + 32, zt);
+            tmem_ld_wait();
+            if (t < T) {
+                const float* lb = lbias + fi * 64 + half * 16;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 o4;
+                    o4.x = xs[c].x + fast_sigmoid(__uint_as_float(zs[c * 4 + 0]) + lb[c * 4 + 0]) * fast_tanh(__uint_as_float(zt[c * 4 + 0]) + lb[32 + c * 4 + 0]);
+                    o4.y = xs[c].y + fast_sigmoid(__uint_as_float(zs[c * 4 + 1]) + lb[c * 4 + 1]) * fast_tanh(__uint_as_float(zt[c * 4 + 1]) + lb[32 + c * 4 + 1]);
+                    o4.z = xs[c].z + fast_sigmoid(__uint_as_float(zs[c * 4 + 2]) + lb[c * 4 + 2]) * fast_tanh(__uint_as_float(zt[c * 4 + 2]) + lb[32 + c * 4 + 2]);
+                    o4.w = xs[c].w + fast_sigmoid(__uint_as_float(zs[c * 4 + 3]) + lb[c * 4 + 3]) * fast_tanh(__uint_as_float(zt[c * 4 + 3]) + lb[32 + c * 4 + 3]);
+                    *reinterpret_cast<float4*>(x_out + row + c * 4) = o4;
+                }
+            }
+        }
+        tc_fence_before();
+        group_sync(1 + g, 256);   // the group's TMEM columns and smem slot are free for its next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(256u) : "memory");
+    }
+}
+
+// x_in/x_out: (B,T,32); skip: (B,T,32) buffer or (block 2) the audio (B,T); kern: this layer's slice of the predicted kernels.
+static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const float* x_in, const float* skip, const float* kern,
+                               float* x_out, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches,
+                               bool* done) {
+    *done = false;
+    TcState* s = (TcState*)state;
+    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    if (blk == 0) return 0;   // hop 8: stays on the SIMT kernel
+    LvcTcParams p;
+    p.cw_hi = s->blob + s->sec_off[FD_S_LB0_CONVT_HI + blk * FD_LB_STRIDE] + (size_t)layer * 3 * 8 * C * 4;
+    p.cw_lo = s->blob + s->sec_off[FD_S_LB0_CONVT_LO + blk * FD_LB_STRIDE] + (size_t)layer * 3 * 8 * C * 4;
+    p.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + blk * FD_LB_STRIDE] + layer * C;
+    p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
+    p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
+    const int total = B * ((T + LT_TT - 1) / LT_TT);
+    if (blk == 1) {
+        const int grid = total < s->sm_count ? total : s->sm_count;
+        k_lvc_layer_tc<64, false, 1><<<grid, 256, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, mode == 1 ? 1 : 0);
+    } else {
+        const int pairs = (total + 1) / 2, grid = pairs < s->sm_count ? pairs : s->sm_count;
+        k_lvc_layer_tc<256, true, 2><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, mode == 1 ? 1 : 0);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_tc failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    *done = true;
+    return 0;
+}
+
+static inline cudaError_t tc_set_lvc_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
+}
+
+}  // namespace fd

@@ -62,6 +62,20 @@ def expected_keys(use_weight_norm: bool = True) -> List[str]:
     return list(make_state_dict(0, use_weight_norm=use_weight_norm).keys())
 
 
+def tf32_round(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest-even to tf32 (10 explicit mantissa bits), result kept in fp32 with the low 13 bits zero.
+    Same bit arithmetic as fd::tf32_rn in csrc/fd_common.cuh."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0xFFF + ((u >> 13) & 1)) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def tf32_split(x: np.ndarray):
+    hi = tf32_round(x)
+    lo = tf32_round((x.astype(np.float32) - hi).astype(np.float32))
+    return hi, lo
+
+
 def _conv_kcico(w: torch.Tensor) -> torch.Tensor:
     """Conv1d weight (co, ci, k) -> [k][ci][co]."""
     return w.permute(2, 1, 0).contiguous()
@@ -101,14 +115,23 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         S[f"LB{n}_KPRES_W"] = torch.stack([_conv_kcico(W[f"{kp}.residual_conv.{i}.weight"]) for i in (1, 3, 6, 8, 11, 13)])
         S[f"LB{n}_KPRES_B"] = torch.stack([W[f"{kp}.residual_conv.{i}.bias"] for i in (1, 3, 6, 8, 11, 13)])
         # kernel_conv (24576,64,3): channel ((l*32+i)*64+o)*3+k ; bias_conv (256,64,3): channel l*64+o  (modules.py:333-342)
-        kc = W[f"{kp}.kernel_conv.weight"].reshape(LAYERS, C, LVC_OUT, KS, HID, 3)   # [l][i][o][k][c][j]
-        kc = kc.permute(5, 4, 0, 3, 1, 2).reshape(3 * HID, LAYERS, KK * LVC_OUT)      # [j*64+c][l][(k*32+i)*64+o]
-        bc = W[f"{kp}.bias_conv.weight"].reshape(LAYERS, LVC_OUT, HID, 3)            # [l][o][c][j]
-        bc = bc.permute(3, 2, 0, 1).reshape(3 * HID, LAYERS, LVC_OUT)                 # [j*64+c][l][o]
+        # target column order inside a layer: ((k*8 + i//4)*64 + o)*4 + i%4  -- the K-major UMMA operand "panel" layout
+        kc = W[f"{kp}.kernel_conv.weight"].reshape(LAYERS, 8, 4, LVC_OUT, KS, HID, 3)  # [l][i8][i4][o][k][c][j]
+        kc = kc.permute(6, 5, 0, 4, 1, 3, 2).reshape(3 * HID, LAYERS, KK * LVC_OUT)     # [j*64+c][l][k][i8][o][i4]
+        bc = W[f"{kp}.bias_conv.weight"].reshape(LAYERS, LVC_OUT, HID, 3)              # [l][o][c][j]
+        bc = bc.permute(3, 2, 0, 1).reshape(3 * HID, LAYERS, LVC_OUT)                   # [j*64+c][l][o]
         S[f"LB{n}_KC_W"] = torch.cat([kc, bc], dim=2).reshape(3 * HID, KCN).contiguous()
-        kcb = W[f"{kp}.kernel_conv.bias"].reshape(LAYERS, C, LVC_OUT, KS).permute(0, 3, 1, 2).reshape(LAYERS, KK * LVC_OUT)
+        kcb = W[f"{kp}.kernel_conv.bias"].reshape(LAYERS, 8, 4, LVC_OUT, KS).permute(0, 4, 1, 3, 2).reshape(LAYERS, KK * LVC_OUT)
         bcb = W[f"{kp}.bias_conv.bias"].reshape(LAYERS, LVC_OUT)
         S[f"LB{n}_KC_B"] = torch.cat([kcb, bcb], dim=1).reshape(KCN).contiguous()
+        hi, lo = tf32_split(S[f"LB{n}_KC_W"].t().contiguous().numpy())   # [24832][192], K-major rows
+        S[f"LB{n}_KCT_HI"] = torch.from_numpy(hi)
+        S[f"LB{n}_KCT_LO"] = torch.from_numpy(lo)
+        cw = torch.stack([W[f"{p}.convs.{i}.weight"] for i in range(LAYERS)])          # [l][co][ci][k]
+        cw = cw.reshape(LAYERS, C, 8, 4, KS).permute(0, 4, 2, 1, 3).contiguous()        # [l][k][ci8][co][ci4]
+        hi, lo = tf32_split(cw.numpy())
+        S[f"LB{n}_CONVT_HI"] = torch.from_numpy(hi)
+        S[f"LB{n}_CONVT_LO"] = torch.from_numpy(lo)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}
 

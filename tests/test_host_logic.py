@@ -73,7 +73,7 @@ def test_packer_layouts(synth):
     rng = np.random.default_rng(0)
     for _ in range(200):
         l, i, o, k, c, j = (int(rng.integers(n)) for n in (4, 32, 64, 3, 64, 3))
-        assert kc[j * 64 + c, l * 6208 + (k * 32 + i) * 64 + o] == kw[((l * 32 + i) * 64 + o) * 3 + k, c, j].item()
+        assert kc[j * 64 + c, l * 6208 + ((k * 8 + i // 4) * 64 + o) * 4 + i % 4] == kw[((l * 32 + i) * 64 + o) * 3 + k, c, j].item()
         assert kc[j * 64 + c, l * 6208 + 6144 + o] == bw[l * 64 + o, c, j].item()
     up = S["LB2_UP_W"].reshape(8, 32, 32)
     assert up[5, 3, 7] == W["lvc_blocks.2.upsample.weight"][3, 7, 5].item()
