@@ -13,7 +13,8 @@
 //   D in TMEM: lane = n, column = frame  ->  the epilogue thread of lane n holds consecutive frames in
 //   registers and a warp stores 32 consecutive n of one frame = one coalesced 128-byte line of
 //   kern[(b,f)][n]; no smem staging, bias added per lane.
-// Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer + TMEM allocator, warp 1 MMA issuer, warps 2-9 epilogue (two per TMEM lane
+// quarter, each taking 128 of the 256 columns).
 // Persistent CTAs (grid = #SM), 2-stage smem ring (96 KB/stage), 2 x 256-column TMEM accumulators.
 #pragma once
 #include <cuda.h>
@@ -114,11 +115,11 @@ struct KcgMaps {               // per LVC block: weights hi/lo, hidden hi/lo
     CUtensorMap w_hi[NBLK], w_lo[NBLK], h_hi[NBLK], h_lo[NBLK];
 };
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(320, 1)
 k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
              const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space
     uint64_t* bars = (uint64_t*)(smem + KCG_STAGES * KCG_STAGE_BYTES);
     uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
     uint64_t* empty_bar = bars + KCG_STAGES;      // [STAGES]  MMA -> TMA
@@ -135,10 +136,10 @@ k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bia
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < KCG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -201,9 +202,10 @@ k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bia
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 2) {
         // ================= epilogue: TMEM -> registers -> (+bias) -> global =================
-        const int q = warp & 3;   // TMEM lane quarter this warp may access
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int chalf = (warp - 2) >> 2;   // which 128 of the 256 frame columns
         uint32_t acc = 0, acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int blk = tile / tiles_per_blk, r = tile % tiles_per_blk;
@@ -212,21 +214,36 @@ k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bia
             const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
             const float bv = bias[n];
             float* kern = kern_all + (size_t)blk * B * Tm * KCN;
+            int p = ft * KCG_BN + chalf * 128;         // padded row of this warp's first column
+            int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
+            const bool fast = (fp >= 1) && (fp + 127 <= Tm) && (p + 127 < M);   // 128 valid frames of one item
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * KCG_BN;
-            int p = ft * KCG_BN;                       // padded row of column 0
-            int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
-            for (int c0 = 0; c0 < KCG_BN; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x32(taddr + c0, v);
-                tmem_ld_wait();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * KCG_BN + chalf * 128;
+            if (fast) {
+                float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN + n;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (p < M && fp >= 1 && fp <= Tm)
-                        kern[((size_t)bb * Tm + (fp - 1)) * KCN + n] = __uint_as_float(v[j]) + bv;
-                    ++p;
-                    if (++fp == Tm + 2) { fp = 0; ++bb; }
+                    for (int j = 0; j < 32; ++j) o[(size_t)j * KCN] = __uint_as_float(v[j]) + bv;   // immediate-offset stores
+                    o += (size_t)32 * KCN;
+                }
+            } else {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (p < M && fp >= 1 && fp <= Tm)
+                            kern[((size_t)bb * Tm + (fp - 1)) * KCN + n] = __uint_as_float(v[j]) + bv;
+                        ++p;
+                        if (++fp == Tm + 2) { fp = 0; ++bb; }
+                    }
                 }
             }
             tc_fence_before();
@@ -237,7 +254,7 @@ k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bia
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -315,7 +332,7 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
     const int M = B * (Tm + 2) - 2;
     const int total = NBLK * (KCN / KCG_BM) * ((M + KCG_BN - 1) / KCG_BN);
     const int grid = total < s->sm_count ? total : s->sm_count;
-    k_kc_gemm_tc<<<grid, 256, KCG_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
+    k_kc_gemm_tc<<<grid, 320, KCG_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
                                                     s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, mode == 1 ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc failed: ") + cudaGetErrorString(e); return -3; }
@@ -399,7 +416,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     constexpr int NF = lt_nf<HOP>();
     constexpr int SLOT = lt_slot_bytes<HOP>();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space
     unsigned char* cw_hi = smem + GROUPS * SLOT;
     unsigned char* cw_lo = cw_hi + LT_CW_BYTES;
     float* fw_s = (float*)(cw_lo + LT_CW_BYTES);         // [7][32] first_audio_conv weights
@@ -457,39 +474,55 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     uint32_t parity = 0;
     for (int tile = blockIdx.x * GROUPS + g; tile < total; tile += gridDim.x * GROUPS, parity ^= 1) {
         const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
-        // ---------------- phase 1: operands -> smem panels ----------------
+        // ---------------- phase 1: operands -> smem panels (all global loads of the tile issued up front) ----------------
+        const int r_lo = 27 - dil + (gt >> 3), r_hi = 157 + dil;   // A rows ar <-> t = t0 - 28 + ar, this thread: r_lo, r_lo+32, ...
+        float4 xv[6], kv[NF][6];
 #pragma unroll
-        for (int fi = 0; fi < NF; ++fi) {   // predicted LVC kernels of the frame(s): split into tf32 pieces
-            const int f = t0 / HOP + fi;
-            if (f < Tm) {
-                const float4* src = reinterpret_cast<const float4*>(kern + ((size_t)b * Tm + f) * KCN);
-                float4 v[6];
+        for (int i = 0; i < 6; ++i) {
+            const int ar = r_lo + i * 32, t = t0 - 28 + ar;
+            xv[i] = (ar < r_hi && t >= 0 && t < T) ? reinterpret_cast<const float4*>(x_in)[((size_t)b * T + t) * 8 + c4]
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float4 skv[6];
+        if (!SKIP_FIRST) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) v[i] = src[gt + i * 256];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    float4 hi, lo;
-                    split4(v[i], hi, lo);
-                    reinterpret_cast<float4*>(lw_hi + fi * LT_LW_BYTES)[gt + i * 256] = hi;
-                    reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES)[gt + i * 256] = lo;
-                }
-                if (gt < 64) lbias[fi * 64 + gt] = kern[((size_t)b * Tm + f) * KCN + KK * LVC_OUT + gt];
+            for (int i = 0; i < 6; ++i) {
+                const int ar = r_lo + i * 32, t = t0 - 28 + ar;
+                skv[i] = (ar < r_hi && t >= 0 && t < T) ? reinterpret_cast<const float4*>(skip)[((size_t)b * T + t) * 8 + c4]
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        }
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) {
+            const int f = t0 / HOP + fi;
+            const float4* src = reinterpret_cast<const float4*>(kern + ((size_t)b * Tm + (f < Tm ? f : 0)) * KCN);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) kv[fi][i] = src[gt + i * 256];
+            if (gt < 64) lbias[fi * 64 + gt] = kern[((size_t)b * Tm + (f < Tm ? f : 0)) * KCN + KK * LVC_OUT + gt];
         }
         if (SKIP_FIRST) {
             for (int i = gt; i < LT_AU; i += 256) {   // au_s[i] <-> audio position t0 - 31 + i
                 const int pos = t0 - 31 + i;
                 au_s[i] = (pos >= 0 && pos < T) ? skip[(size_t)b * T + pos] : 0.f;
             }
-            group_sync(1 + g, 256);
         }
-        {   // A rows ar <-> t = t0 - 28 + ar; rows the 130 conv outputs touch: ar in [27-dil, 157+dil)
-            const int r_hi = 157 + dil;
-            for (int ar = 27 - dil + (gt >> 3); ar < r_hi; ar += 32) {
-                const int t = t0 - 28 + ar;
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) {   // predicted LVC kernels of the frame(s): split into tf32 pieces
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                float4 hi, lo;
+                split4(kv[fi][i], hi, lo);
+                reinterpret_cast<float4*>(lw_hi + fi * LT_LW_BYTES)[gt + i * 256] = hi;
+                reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES)[gt + i * 256] = lo;
+            }
+        }
+        if (SKIP_FIRST) group_sync(1 + g, 256);   // audio tile visible
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int ar = r_lo + i * 32, t = t0 - 28 + ar;
+            if (ar < r_hi) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t >= 0 && t < T) {
-                    const float4 xv = reinterpret_cast<const float4*>(x_in)[((size_t)b * T + t) * 8 + c4];
                     float4 sk;
                     if (SKIP_FIRST) {
                         sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
@@ -500,10 +533,10 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                             sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
                         }
                     } else {
-                        sk = reinterpret_cast<const float4*>(skip)[((size_t)b * T + t) * 8 + c4];
+                        sk = skv[i];
                     }
-                    v.x = lrelu(xv.x + sk.x, 0.2f); v.y = lrelu(xv.y + sk.y, 0.2f);
-                    v.z = lrelu(xv.z + sk.z, 0.2f); v.w = lrelu(xv.w + sk.w, 0.2f);
+                    v.x = lrelu(xv[i].x + sk.x, 0.2f); v.y = lrelu(xv[i].y + sk.y, 0.2f);
+                    v.z = lrelu(xv[i].z + sk.z, 0.2f); v.w = lrelu(xv[i].w + sk.w, 0.2f);
                 }
                 float4 hi, lo;
                 split4(v, hi, lo);

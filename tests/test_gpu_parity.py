@@ -1,8 +1,11 @@
 """GPU parity tests proper: the CUDA path (through the C-ABI) against the oracle on the same seeded inputs.
 
-Stated tolerance (fp32 path): |eps_cuda - eps_oracle| <= 5e-5 absolute at eps rms ~1.3 (the reference's own
-fp32-vs-fp64 noise floor on eps is ~3e-6; the CUDA kernels sum in a different order and use CUDA's
-sinf/cosf/expf/tanhf instead of Sleef).  Per-stage tolerances are listed in STAGE_TOL.
+Stated fp32 tolerance: |eps_cuda - eps_oracle| <= 5e-5 absolute at eps rms ~1.3, for BOTH fp32-level modes:
+  fp32_simt  (FFMA everywhere; measured ~4e-6)          tc_3xtf32 (tcgen05, error-compensated tf32; measured ~1e-5, DEFAULT)
+(the reference's own fp32-vs-fp64 noise floor on eps is ~3e-6; the CUDA kernels sum in a different order and use CUDA's
+sinf/cosf/expf instead of Sleef).  Per-stage tolerances are listed in STAGE_TOL (fp32_simt) / STAGE_TOL_TC (tc_3xtf32).
+The single-pass tf32 mode (tc_tf32) is NOT an fp32-level mode: its measured error (~3e-3) is only bounded at 2e-2 here
+and it is never the default nor the benchmark headline.
 """
 import pytest
 import torch
@@ -11,6 +14,7 @@ gpu = pytest.mark.gpu
 
 EPS_TOL = 5e-5
 STAGE_TOL = {"embed": 2e-6, "down": 1e-5, "kernels": 2e-5, "kbias": 2e-5, "lvc": 1e-4}
+STAGE_TOL_TC = {"kernels": 4e-5, "kbias": 4e-5, "lvc": 2e-4}
 N4 = [3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]
 
 
@@ -69,6 +73,47 @@ def test_denoise_stages_vs_oracle(synth, cuda_lib, B, Tm):
 
 
 @gpu
+@pytest.mark.parametrize("B,Tm", [(1, 86), (2, 33), (3, 1), (2, 129)])
+def test_tensor_core_mode_vs_oracle(synth, cuda_lib, B, Tm):
+    """Default mode (tcgen05, 3xTF32): kernel-predictor GEMM output, every LVC block and eps against the oracle;
+    plus on-device agreement with the FFMA path and the bound on the fast single-pass mode."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    x, mel = make_inputs(B, Tm, 4)
+    t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
+    eps_ref, inter = O.denoise(W, x, mel, t, return_intermediates=True)
+    net = _net(sd, "tc_3xtf32")
+    eng = net.engine()
+    assert eng.get_mode() == 1
+    eps = net((x.cuda(), mel.cuda(), t.cuda())).cpu()
+    assert (eps - eps_ref).abs().max() < EPS_TOL
+    kp = _oracle_stage_refs(O, W, mel, inter)
+    for n in range(3):
+        k = eng.debug_read(f"kernels{n}", B, Tm).cpu().reshape(kp[n][0].shape)
+        b = eng.debug_read(f"kbias{n}", B, Tm).cpu().reshape(kp[n][1].shape)
+        assert (k - kp[n][0]).abs().max() < STAGE_TOL_TC["kernels"], f"kernels{n}"
+        assert (b - kp[n][1]).abs().max() < STAGE_TOL_TC["kbias"], f"kbias{n}"
+    assert (eng.debug_read("lvc2", B, Tm).cpu().reshape(B, 32, Tm * 256) - inter["lvc2"]).abs().max() < STAGE_TOL_TC["lvc"]
+    eng.set_option("stop_after", 4)
+    net((x.cuda(), mel.cuda(), t.cuda()))
+    assert (eng.debug_read("lvc1", B, Tm).cpu().reshape(B, 32, Tm * 64) - inter["lvc1"]).abs().max() < STAGE_TOL_TC["lvc"]
+    eng.set_option("stop_after", 99)
+    net.mode = "fp32_simt"
+    eps_simt = net((x.cuda(), mel.cuda(), t.cuda())).cpu()
+    assert (eps - eps_simt).abs().max() < EPS_TOL
+    net.mode = "tc_tf32"
+    eps_fast = net((x.cuda(), mel.cuda(), t.cuda())).cpu()
+    assert (eps_fast - eps_ref).abs().max() < 2e-2
+
+
+@gpu
+def test_default_mode_is_fp32_level_tensor_core(synth, cuda_lib):
+    sd, _ = synth
+    assert _net(sd).engine().get_mode() == 1  # FD_MODE_TC_3XTF32
+
+
+@gpu
 @pytest.mark.parametrize("ddim", [False, True])
 def test_sampler_vs_oracle_shared_noise(synth, cuda_lib, ddim):
     """End-to-end N=4 sampling with the reference's RNG stream (CPU generator, reference draw order)."""
@@ -76,7 +121,7 @@ def test_sampler_vs_oracle_shared_noise(synth, cuda_lib, ddim):
     from fastdiff_b200.synthetic import make_inputs
     from oracle import fastdiff_oracle as O
     sd, W = synth
-    net = _net(sd, "fp32_simt")
+    net = _net(sd, None)   # default mode (tc_3xtf32)
     B, Tm = 2, 20
     _, mel = make_inputs(B, Tm, 5)
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
