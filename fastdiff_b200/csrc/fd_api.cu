@@ -557,6 +557,20 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         FD_CHECK_LAUNCH(h, "k_cl_to_ncl");
         return FD_OK;
     };
+#ifndef FD_EMU
+    if (!strcmp(name, "lvc_timeline")) {   // 128 clock64 stamps as (hi,lo)-free doubles are overkill: deltas fit fp32
+        *count = 128;
+        if (!out_dev) return FD_OK;
+        unsigned long long host[128];
+        FD_CUDA(h, cudaStreamSynchronize(st));
+        FD_CUDA(h, cudaMemcpyFromSymbol(host, g_lvc_timeline, sizeof host));
+        float rel[128];
+        for (int i = 0; i < 128; ++i) rel[i] = (float)(double)(host[i] - host[0]);
+        FD_CUDA(h, cudaMemcpyAsync(out_dev, rel, sizeof rel, cudaMemcpyHostToDevice, st));
+        FD_CUDA(h, cudaStreamSynchronize(st));
+        return FD_OK;
+    }
+#endif
     if (!strcmp(name, "embed")) {
         *count = (size_t)B * EMB_OUT;
         if (out_dev) FD_CUDA(h, cudaMemcpyAsync(out_dev, ws + w.emb, *count * 4, cudaMemcpyDeviceToDevice, st));

@@ -353,13 +353,14 @@ __global__ void __launch_bounds__(256) k_dblock(DbParams p, const float* __restr
         const float* src = layer ? sb : sa;
         float* dst = layer ? sa : sb;
         const float bias = p.conv_b[layer * C + lane];
-        for (int base = warp * 5; base < 80; base += 8 * 5) {
-            float acc[5];
+        {   // 80 rows = 8 warps x 10: one pass, every weight fetched from smem once per warp
+            const int base = warp * 10;
+            float acc[10];
 #pragma unroll
-            for (int n = 0; n < 5; ++n) acc[n] = bias;
-            conv3_acc<5>(acc, src, base + DB_PAD, 1 << layer, cw + layer * KK * C, lane);
+            for (int n = 0; n < 10; ++n) acc[n] = bias;
+            conv3_acc<10>(acc, src, base + DB_PAD, 1 << layer, cw + layer * KK * C, lane);
 #pragma unroll
-            for (int n = 0; n < 5; ++n) {
+            for (int n = 0; n < 10; ++n) {
                 const int r = base + n, o = o0 - DB_HALO + r;
                 if (r < DB_R) dst[(r + DB_PAD) * C + lane] = (o >= 0 && o < To) ? lrelu(acc[n], 0.2f) : 0.f;
             }
@@ -370,24 +371,25 @@ __global__ void __launch_bounds__(256) k_dblock(DbParams p, const float* __restr
     {
         const float bias = p.conv_b[2 * C + lane] + p.res_b[lane];
         const float4* raw4 = reinterpret_cast<const float4*>(raw);
-        for (int base = warp * 4; base < DB_TO; base += 8 * 4) {
-            float acc[4];
+        {   // 64 rows = 8 warps x 8
+            const int base = warp * 8;
+            float acc[8];
 #pragma unroll
-            for (int n = 0; n < 4; ++n) acc[n] = bias;
-            conv3_acc<4>(acc, sa, base + DB_HALO + DB_PAD, 4, cw + 2 * KK * C, lane);
+            for (int n = 0; n < 8; ++n) acc[n] = bias;
+            conv3_acc<8>(acc, sa, base + DB_HALO + DB_PAD, 4, cw + 2 * KK * C, lane);
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
                 const float w0 = rw[(c4 * 4 + 0) * C + lane], w1 = rw[(c4 * 4 + 1) * C + lane];
                 const float w2 = rw[(c4 * 4 + 2) * C + lane], w3 = rw[(c4 * 4 + 3) * C + lane];
 #pragma unroll
-                for (int n = 0; n < 4; ++n) {
+                for (int n = 0; n < 8; ++n) {
                     const float4 v = raw4[(base + n) * 8 + c4];
                     acc[n] = fmaf(v.x, w0, acc[n]); acc[n] = fmaf(v.y, w1, acc[n]);
                     acc[n] = fmaf(v.z, w2, acc[n]); acc[n] = fmaf(v.w, w3, acc[n]);
                 }
             }
 #pragma unroll
-            for (int n = 0; n < 4; ++n) {
+            for (int n = 0; n < 8; ++n) {
                 const int o = o0 + base + n;
                 if (o < To) out[((size_t)b * To + o) * C + lane] = acc[n];
             }

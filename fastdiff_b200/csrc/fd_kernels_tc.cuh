@@ -56,6 +56,17 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
+// One lane of a converged warp (cute::elect_one_sync): the compiler recognises the elect.sync predicate as single-thread,
+// so uniform-datapath instructions (UTCHMMA, UTCBAR, UTMALDG) inside the branch are emitted straight-line.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -150,7 +161,7 @@ k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bia
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int blk = tile / tiles_per_blk, r = tile % tiles_per_blk;
@@ -173,7 +184,7 @@ k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bia
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_tf32(KCG_BM, KCG_BN);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -393,15 +404,27 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-// tf32 pieces with the conversion instruction (round-to-nearest; low 13 bits come back zero)
-__device__ __forceinline__ float cvt_tf32(float x) { uint32_t u; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x)); return __uint_as_float(u); }
+// tf32 pieces by Veltkamp splitting (3 FP ops): hi = x rounded to nearest at 11 significant bits (low 13 mantissa bits
+// zero -> exactly a tf32), lo = x - hi exactly.  lo is handed to the tensor core as is (its own tf32 conversion of lo costs
+// <= 2^-11 |lo| <= 2^-22 |x|).  `cvt.rna.tf32.f32` is emulated with ~8 integer instructions on sm_100a (ncu: it was the
+// majority of this kernel's instruction stream), and _rn intrinsics keep the compiler from contracting c - x into an FMA.
+__device__ __forceinline__ float split_hi(float x) {
+    const float c = __fmul_rn(x, 8193.0f);
+    return __fsub_rn(c, __fsub_rn(c, x));
+}
+__device__ __forceinline__ float cvt_tf32(float x) { return split_hi(x); }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
-    hi = make_float4(cvt_tf32(v.x), cvt_tf32(v.y), cvt_tf32(v.z), cvt_tf32(v.w));
-    lo = make_float4(cvt_tf32(v.x - hi.x), cvt_tf32(v.y - hi.y), cvt_tf32(v.z - hi.z), cvt_tf32(v.w - hi.w));
+    hi = make_float4(split_hi(v.x), split_hi(v.y), split_hi(v.z), split_hi(v.w));
+    lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
 // gate non-linearities from ex2.approx/rcp.approx: abs error ~2e-7 (the precise tanhf/expf forms cost ~10x the instructions)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + exp2f(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + exp2f(2.8853900817779268f * x)); }
+
+// phase timeline of CTA 0 / group 0 (clock64 at phase boundaries, 10 stamps per tile, first 12 tiles) -- read through
+// fd_debug_read("lvc_timeline"); costs one thread a handful of clock reads per tile.
+__device__ unsigned long long g_lvc_timeline[128];
+#define LT_STAMP(i) do { if (stamp && tile_no < 12) g_lvc_timeline[tile_no * 10 + (i)] = clock64(); } while (0)
 
 struct LvcTcParams {
     const float* cw_hi; const float* cw_lo;      // [3][8][32][4] tf32 pieces of this layer's dilated conv
@@ -440,7 +463,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(256u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     {   // per-layer constants: the global order of the conv weights is already the smem panel image
@@ -455,7 +478,11 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_base_s + g * 128;   // group columns: [0,32) conv, [32, 32+64*NF) lvc
+    // TMEM columns of a group (256 apart): three INDEPENDENT accumulators, one per tf32 pass (hi*hi, hi*lo, lo*hi), summed in
+    // the epilogues -- a single accumulator serialises the 36 small MMAs on the accumulate dependency (~100-140 cycles each,
+    // measured), three chains overlap.  conv: chain p at [32p, 32p+32); lvc (after the conv columns are dead): frame fi,
+    // chain p at [fi*192 + 64p, +64).
+    const uint32_t tmem_base = *tmem_base_s + g * 256;
     constexpr uint32_t idesc_conv = umma_idesc_tf32(128, 32), idesc_lvc = umma_idesc_tf32(128, 64);
 
     // phase-1 role of this thread is fixed: channel chunk c4 = gt & 7 -> keep its first-conv taps in registers
@@ -470,10 +497,24 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         for (int q = 0; q < 4; ++q) fbr[q] = fb_s[c4 * 4 + q];
     }
 
+    // Warp-uniform copies (shfl from lane 0) so the MMA issue path is provably uniform, and descriptor bases built once:
+    // every descriptor of the kernel is base + (byte offset >> 4) on the start-address field.
+    const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
+    const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * SLOT);
+    const uint64_t dA_hi = umma_desc_ns(slot_u, LT_PANEL_A, 128);                       // A panels (hi); lo = + LT_A_BYTES
+    const uint64_t dLW_hi = umma_desc_ns(slot_u + 2 * LT_A_BYTES, LVC_OUT * 16, 128);   // LVC kernels (hi); lo = + NF*LT_LW_BYTES
+    const uint64_t dCW_hi = umma_desc_ns(smem_u32(cw_hi), C * 16, 128);                 // conv weights (hi); lo = + LT_CW_BYTES
+    constexpr uint64_t kA_LO = LT_A_BYTES >> 4, kLW_LO = (uint64_t)(NF * LT_LW_BYTES) >> 4, kCW_LO = LT_CW_BYTES >> 4;
+    constexpr uint64_t kY_FROM_A = (uint64_t)((LT_PANEL_A - LT_PANEL_Y) >> 4) << 16;   // Y panels: same base, smaller LBO field
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+
     const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt;
     uint32_t parity = 0;
-    for (int tile = blockIdx.x * GROUPS + g; tile < total; tile += gridDim.x * GROUPS, parity ^= 1) {
+    const bool stamp = (blockIdx.x == 0 && tid == 0 && HOP == 256);
+    int tile_no = 0;
+    for (int tile = blockIdx.x * GROUPS + g; tile < total; tile += gridDim.x * GROUPS, parity ^= 1, ++tile_no) {
         const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+        LT_STAMP(0);
         // ---------------- phase 1: operands -> smem panels (all global loads of the tile issued up front) ----------------
         const int r_lo = 27 - dil + (gt >> 3), r_hi = 157 + dil;   // A rows ar <-> t = t0 - 28 + ar, this thread: r_lo, r_lo+32, ...
         float4 xv[6], kv[NF][6];
@@ -516,7 +557,9 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES)[gt + i * 256] = lo;
             }
         }
+        LT_STAMP(1);   // loads issued, kernels split+stored
         if (SKIP_FIRST) group_sync(1 + g, 256);   // audio tile visible
+        LT_STAMP(2);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const int ar = r_lo + i * 32, t = t0 - 28 + ar;
@@ -544,28 +587,31 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 *reinterpret_cast<float4*>(a_lo + c4 * LT_PANEL_A + ar * 16) = lo;
             }
         }
+        LT_STAMP(3);   // A built
         fence_async_smem();
         group_sync(1 + g, 256);
+        LT_STAMP(4);
         // ---------------- phase 2: dilated conv on tensor cores (+ 2 halo rows on FFMA meanwhile) ----------------
-        if (gt == 0) {
+        if (gw_u == 0) {   // whole warp, warp-uniform operands (descriptors stay in uniform registers); one elected lane issues
             tc_fence_after();
-            const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), wh = smem_u32(cw_hi), wl = smem_u32(cw_lo);
+            if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const uint32_t arow = (uint32_t)((27 + (k - 1) * dil) * 16);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t aoff = 2 * j * LT_PANEL_A + arow, boff = (uint32_t)((k * 8 + 2 * j) * C * 16);
-                    const uint64_t dah = umma_desc_ns(ah + aoff, LT_PANEL_A, 128), dal = umma_desc_ns(al + aoff, LT_PANEL_A, 128);
-                    const uint64_t dbh = umma_desc_ns(wh + boff, C * 16, 128), dbl = umma_desc_ns(wl + boff, C * 16, 128);
-                    umma_tf32(tmem_base, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
+                    const uint32_t aoff = (2 * j * LT_PANEL_A + arow) >> 4, boff = (uint32_t)((k * 8 + 2 * j) * C * 16) >> 4;
+                    const uint64_t dah = dA_hi + aoff, dal = dah + kA_LO, dbh = dCW_hi + boff, dbl = dbh + kCW_LO;
+                    umma_tf32(tmem_u, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
                     if (three_pass) {
-                        umma_tf32(tmem_base, dah, dbl, idesc_conv, 1u);
-                        umma_tf32(tmem_base, dal, dbh, idesc_conv, 1u);
+                        umma_tf32(tmem_u + 32, dah, dbl, idesc_conv, (k | j) ? 1u : 0u);
+                        umma_tf32(tmem_u + 64, dal, dbh, idesc_conv, (k | j) ? 1u : 0u);
                     }
                 }
             }
             tc_commit(&bar[0]);
+            }
+            __syncwarp();
         }
         __syncwarp();
         float halo = 0.f;   // warps 6,7 of the group: conv outputs yr = 128 (warp 6), 129 (warp 7), lane = co
@@ -589,12 +635,23 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             halo = (t >= 0 && t < T) ? lrelu(acc, 0.2f) : 0.f;
         }
         // ---------------- phase 3: y = lrelu(conv + b) -> tf32 panels (over the A tile) ----------------
+        LT_STAMP(5);   // conv MMAs issued (+ halo rows for warps 6,7)
         mbar_wait(&bar[0], parity);
         tc_fence_after();
+        LT_STAMP(6);   // conv MMAs complete
         group_sync(1 + g, 256);   // Y aliases A: the halo warps must have finished READING A before anyone writes Y
         if (gw < 4) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16), v);
+            if (three_pass) {   // total = hi*hi + (hi*lo + lo*hi)
+                uint32_t v1[32], v2[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16) + 32, v1);
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16) + 64, v2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    v[i] = __float_as_uint(__uint_as_float(v[i]) + (__uint_as_float(v1[i]) + __uint_as_float(v2[i])));
+            }
             tmem_ld_wait();
             const int yr = gw * 32 + lane, t = t0 - 1 + yr;
             const bool in = (t >= 0 && t < T);
@@ -612,37 +669,39 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             }
         } else if (gw >= 6) {
             const int yr = 128 + (gw - 6);
-            const float hi = cvt_tf32(halo), lo = cvt_tf32(halo - hi);
+            const float hi = split_hi(halo), lo = halo - hi;
             *reinterpret_cast<float*>(a_hi + (lane >> 2) * LT_PANEL_Y + yr * 16 + (lane & 3) * 4) = hi;
             *reinterpret_cast<float*>(a_lo + (lane >> 2) * LT_PANEL_Y + yr * 16 + (lane & 3) * 4) = lo;
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(1 + g, 256);
+        LT_STAMP(7);   // Y written
         // ---------------- phase 4: location-variable conv on tensor cores ----------------
-        if (gt == 0) {
+        if (gw_u == 0) {
             tc_fence_after();
-            const uint32_t yh = smem_u32(a_hi), yl = smem_u32(a_lo);
+            if (elect_one()) {
 #pragma unroll
             for (int fi = 0; fi < NF; ++fi) {
-                const uint32_t d = tmem_base + 32 + fi * 64;
-                const uint32_t wh = smem_u32(lw_hi + fi * LT_LW_BYTES), wl = smem_u32(lw_lo + fi * LT_LW_BYTES);
+                const uint32_t d = tmem_u + fi * 192;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t aoff = 2 * j * LT_PANEL_Y + k * 16, boff = (uint32_t)((k * 8 + 2 * j) * LVC_OUT * 16);
-                        const uint64_t dah = umma_desc_ns(yh + aoff, LT_PANEL_Y, 128), dal = umma_desc_ns(yl + aoff, LT_PANEL_Y, 128);
-                        const uint64_t dbh = umma_desc_ns(wh + boff, LVC_OUT * 16, 128), dbl = umma_desc_ns(wl + boff, LVC_OUT * 16, 128);
+                        const uint32_t aoff = (2 * j * LT_PANEL_Y + k * 16) >> 4;
+                        const uint32_t boff = (uint32_t)(fi * LT_LW_BYTES + (k * 8 + 2 * j) * LVC_OUT * 16) >> 4;
+                        const uint64_t dah = dA_hi - kY_FROM_A + aoff, dal = dah + kA_LO, dbh = dLW_hi + boff, dbl = dbh + kLW_LO;
                         umma_tf32(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
                         if (three_pass) {
-                            umma_tf32(d, dah, dbl, idesc_lvc, 1u);
-                            umma_tf32(d, dal, dbh, idesc_lvc, 1u);
+                            umma_tf32(d + 64, dah, dbl, idesc_lvc, (k | j) ? 1u : 0u);
+                            umma_tf32(d + 128, dal, dbh, idesc_lvc, (k | j) ? 1u : 0u);
                         }
                     }
                 }
             }
             tc_commit(&bar[1]);
+            }
+            __syncwarp();
         }
         __syncwarp();
         // ---------------- phase 5: gate + residual -> global ----------------
@@ -670,12 +729,27 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                     xs[c].x += sk.x; xs[c].y += sk.y; xs[c].z += sk.z; xs[c].w += sk.w;
                 }
             }
+            LT_STAMP(8);   // LVC MMAs issued, residual prefetched
             mbar_wait(&bar[1], parity);
             tc_fence_after();
+            LT_STAMP(9);   // LVC MMAs complete
             uint32_t zs[16], zt[16];
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 32 + fi * 64 + half * 16;
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + fi * 192 + half * 16;
             tmem_ld_32x32b_x16(ta, zs);
             tmem_ld_32x32b_x16(ta + 32, zt);
+            if (three_pass) {
+                uint32_t a1[16], a2[16];
+                tmem_ld_32x32b_x16(ta + 64, a1);
+                tmem_ld_32x32b_x16(ta + 128, a2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) zs[i] = __float_as_uint(__uint_as_float(zs[i]) + (__uint_as_float(a1[i]) + __uint_as_float(a2[i])));
+                tmem_ld_32x32b_x16(ta + 64 + 32, a1);
+                tmem_ld_32x32b_x16(ta + 128 + 32, a2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) zt[i] = __float_as_uint(__uint_as_float(zt[i]) + (__uint_as_float(a1[i]) + __uint_as_float(a2[i])));
+            }
             tmem_ld_wait();
             if (t < T) {
                 const float* lb = lbias + fi * 64 + half * 16;
@@ -697,7 +771,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     __syncthreads();
     if (tid < 32) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(512u) : "memory");
     }
 }
 

@@ -1,0 +1,57 @@
+"""Glue for the reference's own callers of the path.
+
+``patch_reference_task()`` is the whole integration: it swaps the three names the reference task module binds at import
+time (`FastDiff`, `sampling_given_noise_schedule`, `compute_hyperparams_given_schedule` --
+/root/reference/modules/FastDiff/task/FastDiff.py:5,9) for the B200 implementations, so the UNMODIFIED
+`FastDiffTask.build_model` / `test_step` (task/FastDiff.py:16-42, 60-119), `tasks/run.py` and the Trainer drive the
+CUDA path.  Nothing from the reference is copied; it must be importable (on `sys.path`) for this module's functions to work.
+"""
+from __future__ import annotations
+
+import importlib
+
+import numpy as np
+import torch
+
+from .model import FastDiff
+from .sampler import compute_hyperparams_given_schedule, sampling_given_noise_schedule
+
+N4_SCHEDULE = [3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]  # task/FastDiff.py:88-89
+
+
+def patch_reference_task(module_name: str = "modules.FastDiff.task.FastDiff"):
+    """Import the reference task module and rebind its model/sampler names; returns the (unmodified) task class."""
+    ref_task = importlib.import_module(module_name)
+    ref_task.FastDiff = FastDiff
+    ref_task.sampling_given_noise_schedule = sampling_given_noise_schedule
+    ref_task.compute_hyperparams_given_schedule = compute_hyperparams_given_schedule
+    return ref_task.FastDiffTask
+
+
+class FastDiffVocoder:
+    """`BaseVocoder`-shaped wrapper (vocoders/base_vocoder.py:23-40): spec2wav(mel [T,80]) -> wav [T*hop].
+    Register it in the reference with `register_vocoder(FastDiffVocoder)` (vocoders/base_vocoder.py:6-9)."""
+
+    def __init__(self, state_dict=None, ckpt_path=None, device="cuda", schedule=None, seed=None):
+        self.device = torch.device(device)
+        self.model = FastDiff().to(self.device).eval()
+        if ckpt_path is not None:
+            state_dict = torch.load(ckpt_path, map_location="cpu")["state_dict"]["model"]
+        if state_dict is not None:
+            self.model.load_state_dict(state_dict, strict=True)
+        self.dh = compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))  # base.yaml:38-40
+        self.schedule = torch.FloatTensor(N4_SCHEDULE if schedule is None else schedule)
+        if seed is not None:
+            self.model.noise_mode, self.model.seed = "device", int(seed)
+
+    def spec2wav(self, mel, **kwargs):
+        c = torch.as_tensor(np.asarray(mel), dtype=torch.float32).t().unsqueeze(0).to(self.device)
+        import contextlib
+        import io
+        with contextlib.redirect_stdout(io.StringIO()):
+            y = sampling_given_noise_schedule(self.model, (1, 1, c.shape[-1] * 256), self.dh, self.schedule.clone(), condition=c)
+        return y.view(-1).cpu().numpy()
+
+    @staticmethod
+    def wav2spec(wav_fn):
+        raise NotImplementedError("mel extraction is the reference's data_gen path (SURVEY.md 8f item 3: next)")
