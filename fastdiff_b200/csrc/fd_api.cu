@@ -258,6 +258,9 @@ extern "C" int fd_get_mode(fd_handle* h) { return h ? h->mode : FD_ERR_INVALID; 
 extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!h || !key) return FD_ERR_INVALID;
     if (!strcmp(key, "stop_after")) { h->stop_after = (int)value; return FD_OK; }
+#ifndef FD_EMU
+    if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
+#endif
     return fail(h, FD_ERR_INVALID, "fd_set_option: unknown key '%s'", key);
 }
 

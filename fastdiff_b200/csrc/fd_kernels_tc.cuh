@@ -284,6 +284,7 @@ struct TcState {
     const float* blob = nullptr;
     uint64_t sec_off[FD_S_COUNT];
     CUtensorMap w_hi[NBLK], w_lo[NBLK];
+    int lvc_swizzle = 0;   // LVC operand tiles: 0 = no-swizzle panels, 1 = SWIZZLE_128B + base_offset, 2 = SWIZZLE_128B, base_offset 0
     bool ok = false;
 };
 
@@ -302,6 +303,7 @@ static inline int tc_make_map_2d(TcState* s, CUtensorMap* m, const float* base, 
 static inline cudaError_t tc_set_lvc_attrs();
 static inline void tc_destroy(void* st) { delete (TcState*)st; }
 static inline bool tc_available(void* st) { return st && ((TcState*)st)->ok; }
+static inline void tc_set_lvc_swizzle(void* st, int v) { if (st) ((TcState*)st)->lvc_swizzle = v; }
 
 static inline int tc_init(void** state, int device, const float* blob, const uint64_t* sec_off, std::string& err) {
     tc_destroy(*state);
@@ -374,14 +376,28 @@ constexpr int LT_A_ROWS = 184;                      // conv input rows: t0-28 ..
 constexpr int LT_PANEL_A = LT_A_ROWS * 16 + 16;     // 2960 B (odd multiple of 16: conflict-free panel writes)
 constexpr int LT_Y_ROWS = 136;
 constexpr int LT_PANEL_Y = LT_Y_ROWS * 16 + 16;     // 2192 B
-constexpr int LT_A_BYTES = 8 * LT_PANEL_A;          // 23680
+constexpr int LT_A_BYTES = 24576;                   // >= 8*LT_PANEL_A (23680) and >= 184*128 (23552); 1 KB multiple
 constexpr int LT_CW_BYTES = 3 * 8 * C * 16;         // 12288
 constexpr int LT_LW_BYTES = KK * LVC_OUT * 4;       // 24576
 constexpr int LT_AU = 352;                          // audio samples staged per tile (SKIP_FIRST)
 template <int HOP>
 __host__ __device__ constexpr int lt_nf() { return LT_TT / HOP > 0 ? LT_TT / HOP : 1; }
+// slot = A hi | A lo | LW hi [NF] | LW lo [NF] | lbias | audio, padded to 1 KB so every operand tile can be SWIZZLE_128B
 template <int HOP>
-__host__ __device__ constexpr int lt_slot_bytes() { return 2 * LT_A_BYTES + lt_nf<HOP>() * (2 * LT_LW_BYTES + 256) + LT_AU * 4; }
+__host__ __device__ constexpr int lt_slot_bytes() { return ((2 * LT_A_BYTES + lt_nf<HOP>() * (2 * LT_LW_BYTES + 256) + LT_AU * 4) + 1023) / 1024 * 1024; }
+// Operand tile addressing.  SWZ = SWIZZLE_128B K-major (row r = 128 B at r*128, 16-byte chunk c stored at c ^ (r & 7));
+// !SWZ = no-swizzle panels (chunk c of row r at c*panel + r*16).  B-operand tiles hold NR rows per tap.
+template <bool SWZ>
+__device__ __forceinline__ uint32_t tile_off(int row, int c, int panel) {
+    return SWZ ? (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)) : (uint32_t)(c * panel + row * 16);
+}
+template <bool SWZ, int NR>
+__device__ __forceinline__ uint32_t btile_off(int k, int c, int n) {
+    return SWZ ? (uint32_t)(k * NR * 128 + n * 128 + ((c ^ (n & 7)) << 4)) : (uint32_t)(((k * 8 + c) * NR + n) * 16);
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t base_offset) {
+    return umma_desc_sw128(smem_addr) | ((uint64_t)(base_offset & 7u) << 49);
+}
 constexpr int LT_SHARED_BYTES = 2 * LT_CW_BYTES + (7 * C + C + C) * 4 + 64;   // conv W pieces, first_w, first_b, conv_b, barriers+tmem ptr
 template <int HOP, int GROUPS>
 constexpr int lt_smem_bytes() { return GROUPS * lt_slot_bytes<HOP>() + LT_SHARED_BYTES + 1024; }
@@ -432,10 +448,10 @@ struct LvcTcParams {
     const float* first_w; const float* first_b;  // [7][32], [32]   (SKIP_FIRST)
 };
 
-template <int HOP, bool SKIP_FIRST, int GROUPS>
+template <int HOP, bool SKIP_FIRST, int GROUPS, bool SWZ>
 __global__ void __launch_bounds__(256 * GROUPS, 1)
 k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
-               float* __restrict__ x_out, int B, int T, int Tm, int dil, int three_pass) {
+               float* __restrict__ x_out, int B, int T, int Tm, int dil, int three_pass, int bo_mode) {
     constexpr int NF = lt_nf<HOP>();
     constexpr int SLOT = lt_slot_bytes<HOP>();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -468,9 +484,10 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     }
     {   // per-layer constants: the global order of the conv weights is already the smem panel image
         const float4* sh = reinterpret_cast<const float4*>(p.cw_hi); const float4* sl = reinterpret_cast<const float4*>(p.cw_lo);
-        for (int i = tid; i < LT_CW_BYTES / 16; i += 256 * GROUPS) {
-            reinterpret_cast<float4*>(cw_hi)[i] = sh[i];
-            reinterpret_cast<float4*>(cw_lo)[i] = sl[i];
+        for (int i = tid; i < LT_CW_BYTES / 16; i += 256 * GROUPS) {   // global order [k][c8][co][4]
+            const uint32_t o = btile_off<SWZ, C>(i / (8 * C), (i / C) & 7, i % C);
+            *reinterpret_cast<float4*>(cw_hi + o) = sh[i];
+            *reinterpret_cast<float4*>(cw_lo + o) = sl[i];
         }
         if (tid < 7 * C) fw_s[tid] = SKIP_FIRST ? p.first_w[tid] : 0.f;
         if (tid < C) { fb_s[tid] = SKIP_FIRST ? p.first_b[tid] : 0.f; cb_s[tid] = p.conv_b[tid]; }
@@ -553,8 +570,10 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             for (int i = 0; i < 6; ++i) {
                 float4 hi, lo;
                 split4(kv[fi][i], hi, lo);
-                reinterpret_cast<float4*>(lw_hi + fi * LT_LW_BYTES)[gt + i * 256] = hi;
-                reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES)[gt + i * 256] = lo;
+                const int e = gt + i * 256;   // global order [k][c8][o][4]
+                const uint32_t o = btile_off<SWZ, LVC_OUT>(e / (8 * LVC_OUT), (e / LVC_OUT) & 7, e % LVC_OUT);
+                *reinterpret_cast<float4*>(lw_hi + fi * LT_LW_BYTES + o) = hi;
+                *reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES + o) = lo;
             }
         }
         LT_STAMP(1);   // loads issued, kernels split+stored
@@ -583,8 +602,8 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 }
                 float4 hi, lo;
                 split4(v, hi, lo);
-                *reinterpret_cast<float4*>(a_hi + c4 * LT_PANEL_A + ar * 16) = hi;
-                *reinterpret_cast<float4*>(a_lo + c4 * LT_PANEL_A + ar * 16) = lo;
+                *reinterpret_cast<float4*>(a_hi + tile_off<SWZ>(ar, c4, LT_PANEL_A)) = hi;
+                *reinterpret_cast<float4*>(a_lo + tile_off<SWZ>(ar, c4, LT_PANEL_A)) = lo;
             }
         }
         LT_STAMP(3);   // A built
@@ -600,8 +619,17 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 const uint32_t arow = (uint32_t)((27 + (k - 1) * dil) * 16);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t aoff = (2 * j * LT_PANEL_A + arow) >> 4, boff = (uint32_t)((k * 8 + 2 * j) * C * 16) >> 4;
-                    const uint64_t dah = dA_hi + aoff, dal = dah + kA_LO, dbh = dCW_hi + boff, dbl = dbh + kCW_LO;
+                    uint64_t dah, dal, dbh, dbl;
+                    if (SWZ) {   // row shift = start address + shift*128 B; swizzle phase of the first row goes in base_offset
+                        const uint32_t sh = (uint32_t)(27 + (k - 1) * dil), bo = bo_mode ? (sh & 7u) : 0u;
+                        dah = umma_desc_sw128_bo(slot_u + sh * 128 + j * 32, bo);
+                        dal = umma_desc_sw128_bo(slot_u + LT_A_BYTES + sh * 128 + j * 32, bo);
+                        dbh = umma_desc_sw128(smem_u32(cw_hi) + k * C * 128 + j * 32);
+                        dbl = umma_desc_sw128(smem_u32(cw_lo) + k * C * 128 + j * 32);
+                    } else {
+                        const uint32_t aoff = (2 * j * LT_PANEL_A + arow) >> 4, boff = (uint32_t)((k * 8 + 2 * j) * C * 16) >> 4;
+                        dah = dA_hi + aoff; dal = dah + kA_LO; dbh = dCW_hi + boff; dbl = dbh + kCW_LO;
+                    }
                     umma_tf32(tmem_u, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
                     if (three_pass) {
                         umma_tf32(tmem_u + 32, dah, dbl, idesc_conv, (k | j) ? 1u : 0u);
@@ -623,10 +651,10 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 const int ar = yr + 27 + (k - 1) * dil;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const float4 ah4 = *reinterpret_cast<const float4*>(a_hi + c * LT_PANEL_A + ar * 16);
-                    const float4 al4 = *reinterpret_cast<const float4*>(a_lo + c * LT_PANEL_A + ar * 16);
-                    const float4 wh4 = *reinterpret_cast<const float4*>(cw_hi + ((k * 8 + c) * C + lane) * 16);
-                    const float4 wl4 = *reinterpret_cast<const float4*>(cw_lo + ((k * 8 + c) * C + lane) * 16);
+                    const float4 ah4 = *reinterpret_cast<const float4*>(a_hi + tile_off<SWZ>(ar, c, LT_PANEL_A));
+                    const float4 al4 = *reinterpret_cast<const float4*>(a_lo + tile_off<SWZ>(ar, c, LT_PANEL_A));
+                    const float4 wh4 = *reinterpret_cast<const float4*>(cw_hi + btile_off<SWZ, C>(k, c, lane));
+                    const float4 wl4 = *reinterpret_cast<const float4*>(cw_lo + btile_off<SWZ, C>(k, c, lane));
                     acc = fmaf(ah4.x + al4.x, wh4.x + wl4.x, acc); acc = fmaf(ah4.y + al4.y, wh4.y + wl4.y, acc);
                     acc = fmaf(ah4.z + al4.z, wh4.z + wl4.z, acc); acc = fmaf(ah4.w + al4.w, wh4.w + wl4.w, acc);
                 }
@@ -664,14 +692,14 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 y.w = in ? lrelu(__uint_as_float(v[c * 4 + 3]) + cb_s[c * 4 + 3], 0.2f) : 0.f;
                 float4 hi, lo;
                 split4(y, hi, lo);
-                *reinterpret_cast<float4*>(a_hi + c * LT_PANEL_Y + yr * 16) = hi;
-                *reinterpret_cast<float4*>(a_lo + c * LT_PANEL_Y + yr * 16) = lo;
+                *reinterpret_cast<float4*>(a_hi + tile_off<SWZ>(yr, c, LT_PANEL_Y)) = hi;
+                *reinterpret_cast<float4*>(a_lo + tile_off<SWZ>(yr, c, LT_PANEL_Y)) = lo;
             }
         } else if (gw >= 6) {
             const int yr = 128 + (gw - 6);
             const float hi = split_hi(halo), lo = halo - hi;
-            *reinterpret_cast<float*>(a_hi + (lane >> 2) * LT_PANEL_Y + yr * 16 + (lane & 3) * 4) = hi;
-            *reinterpret_cast<float*>(a_lo + (lane >> 2) * LT_PANEL_Y + yr * 16 + (lane & 3) * 4) = lo;
+            *reinterpret_cast<float*>(a_hi + tile_off<SWZ>(yr, lane >> 2, LT_PANEL_Y) + (lane & 3) * 4) = hi;
+            *reinterpret_cast<float*>(a_lo + tile_off<SWZ>(yr, lane >> 2, LT_PANEL_Y) + (lane & 3) * 4) = lo;
         }
         fence_async_smem();
         tc_fence_before();
@@ -688,9 +716,19 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 for (int k = 0; k < 3; ++k) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint32_t aoff = (2 * j * LT_PANEL_Y + k * 16) >> 4;
-                        const uint32_t boff = (uint32_t)(fi * LT_LW_BYTES + (k * 8 + 2 * j) * LVC_OUT * 16) >> 4;
-                        const uint64_t dah = dA_hi - kY_FROM_A + aoff, dal = dah + kA_LO, dbh = dLW_hi + boff, dbl = dbh + kLW_LO;
+                        uint64_t dah, dal, dbh, dbl;
+                        if (SWZ) {
+                            const uint32_t bo = bo_mode ? (uint32_t)k : 0u;
+                            dah = umma_desc_sw128_bo(slot_u + k * 128 + j * 32, bo);
+                            dal = umma_desc_sw128_bo(slot_u + LT_A_BYTES + k * 128 + j * 32, bo);
+                            const uint32_t lwb = slot_u + 2 * LT_A_BYTES + fi * LT_LW_BYTES + k * LVC_OUT * 128 + j * 32;
+                            dbh = umma_desc_sw128(lwb);
+                            dbl = umma_desc_sw128(lwb + NF * LT_LW_BYTES);
+                        } else {
+                            const uint32_t aoff = (2 * j * LT_PANEL_Y + k * 16) >> 4;
+                            const uint32_t boff = (uint32_t)(fi * LT_LW_BYTES + (k * 8 + 2 * j) * LVC_OUT * 16) >> 4;
+                            dah = dA_hi - kY_FROM_A + aoff; dal = dah + kA_LO; dbh = dLW_hi + boff; dbl = dbh + kLW_LO;
+                        }
                         umma_tf32(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
                         if (three_pass) {
                             umma_tf32(d + 64, dah, dbl, idesc_lvc, (k | j) ? 1u : 0u);
@@ -790,12 +828,15 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
     p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
     const int total = B * ((T + LT_TT - 1) / LT_TT);
+    const int tp = mode == 1 ? 1 : 0, bo = s->lvc_swizzle == 2 ? 0 : 1;
     if (blk == 1) {
         const int grid = total < s->sm_count ? total : s->sm_count;
-        k_lvc_layer_tc<64, false, 1><<<grid, 256, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, mode == 1 ? 1 : 0);
+        if (s->lvc_swizzle) k_lvc_layer_tc<64, false, 1, true><<<grid, 256, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp, bo);
+        else                k_lvc_layer_tc<64, false, 1, false><<<grid, 256, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp, bo);
     } else {
         const int pairs = (total + 1) / 2, grid = pairs < s->sm_count ? pairs : s->sm_count;
-        k_lvc_layer_tc<256, true, 2><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, mode == 1 ? 1 : 0);
+        if (s->lvc_swizzle) k_lvc_layer_tc<256, true, 2, true><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp, bo);
+        else                k_lvc_layer_tc<256, true, 2, false><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp, bo);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_tc failed: ") + cudaGetErrorString(e); return -3; }
@@ -805,9 +846,11 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
 }
 
 static inline cudaError_t tc_set_lvc_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
+    cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
+    return e;
 }
 
 }  // namespace fd
