@@ -440,7 +440,11 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 // phase timeline of CTA 0 / group 0 (clock64 at phase boundaries, 10 stamps per tile, first 12 tiles) -- read through
 // fd_debug_read("lvc_timeline"); costs one thread a handful of clock reads per tile.
 __device__ unsigned long long g_lvc_timeline[128];
+#ifdef FD_LVC_TIMELINE
 #define LT_STAMP(i) do { if (stamp && tile_no < 12) g_lvc_timeline[tile_no * 10 + (i)] = clock64(); } while (0)
+#else
+#define LT_STAMP(i) do { } while (0)
+#endif
 
 struct LvcTcParams {
     const float* cw_hi; const float* cw_lo;      // [3][8][32][4] tf32 pieces of this layer's dilated conv
@@ -495,10 +499,8 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // TMEM columns of a group (256 apart): three INDEPENDENT accumulators, one per tf32 pass (hi*hi, hi*lo, lo*hi), summed in
-    // the epilogues -- a single accumulator serialises the 36 small MMAs on the accumulate dependency (~100-140 cycles each,
-    // measured), three chains overlap.  conv: chain p at [32p, 32p+32); lvc (after the conv columns are dead): frame fi,
-    // chain p at [fi*192 + 64p, +64).
+    // TMEM columns of a group (256 apart): [0,32) conv accumulator, [32 + 64 fi, +64) LVC accumulator of frame fi.  All three
+    // tf32 passes accumulate into the same tile: measured, there is no accumulate-chain penalty (profiles/r01_tcgen05_findings.md).
     const uint32_t tmem_base = *tmem_base_s + g * 256;
     constexpr uint32_t idesc_conv = umma_idesc_tf32(128, 32), idesc_lvc = umma_idesc_tf32(128, 64);
 
@@ -518,18 +520,21 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     // every descriptor of the kernel is base + (byte offset >> 4) on the start-address field.
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
     const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * SLOT);
-    const uint64_t dA_hi = umma_desc_ns(slot_u, LT_PANEL_A, 128);                       // A panels (hi); lo = + LT_A_BYTES
-    const uint64_t dLW_hi = umma_desc_ns(slot_u + 2 * LT_A_BYTES, LVC_OUT * 16, 128);   // LVC kernels (hi); lo = + NF*LT_LW_BYTES
-    const uint64_t dCW_hi = umma_desc_ns(smem_u32(cw_hi), C * 16, 128);                 // conv weights (hi); lo = + LT_CW_BYTES
-    constexpr uint64_t kA_LO = LT_A_BYTES >> 4, kLW_LO = (uint64_t)(NF * LT_LW_BYTES) >> 4, kCW_LO = LT_CW_BYTES >> 4;
-    constexpr uint64_t kY_FROM_A = (uint64_t)((LT_PANEL_A - LT_PANEL_Y) >> 4) << 16;   // Y panels: same base, smaller LBO field
+    const uint32_t cw_u = smem_u32(cw_hi);
+    // no-swizzle descriptors are rebuilt at the issue site from (slot_u, cw_u): a handful of uniform-datapath integer ops,
+    // cheaper than keeping 64-bit bases live across the whole tile loop (register pressure at 128 regs/thread)
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
 
     const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt;
     uint32_t parity = 0;
+#ifdef FD_LVC_TIMELINE
     const bool stamp = (blockIdx.x == 0 && tid == 0 && HOP == 256);
-    int tile_no = 0;
-    for (int tile = blockIdx.x * GROUPS + g; tile < total; tile += gridDim.x * GROUPS, parity ^= 1, ++tile_no) {
+    int tile_no = -1;
+#endif
+    for (int tile = blockIdx.x * GROUPS + g; tile < total; tile += gridDim.x * GROUPS, parity ^= 1) {
+#ifdef FD_LVC_TIMELINE
+        ++tile_no;
+#endif
         const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
         LT_STAMP(0);
         // ---------------- phase 1: operands -> smem panels (all global loads of the tile issued up front) ----------------
@@ -613,6 +618,8 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         // ---------------- phase 2: dilated conv on tensor cores (+ 2 halo rows on FFMA meanwhile) ----------------
         if (gw_u == 0) {   // whole warp, warp-uniform operands (descriptors stay in uniform registers); one elected lane issues
             tc_fence_after();
+            uint32_t slot_t = slot_u, cw_t = cw_u;
+            asm volatile("" : "+r"(slot_t), "+r"(cw_t));   // opaque per tile: keeps ptxas from hoisting ~150 descriptors out of the tile loop
             if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -622,18 +629,19 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                     uint64_t dah, dal, dbh, dbl;
                     if (SWZ) {   // row shift = start address + shift*128 B; swizzle phase of the first row goes in base_offset
                         const uint32_t sh = (uint32_t)(27 + (k - 1) * dil), bo = bo_mode ? (sh & 7u) : 0u;
-                        dah = umma_desc_sw128_bo(slot_u + sh * 128 + j * 32, bo);
-                        dal = umma_desc_sw128_bo(slot_u + LT_A_BYTES + sh * 128 + j * 32, bo);
-                        dbh = umma_desc_sw128(smem_u32(cw_hi) + k * C * 128 + j * 32);
-                        dbl = umma_desc_sw128(smem_u32(cw_lo) + k * C * 128 + j * 32);
+                        dah = umma_desc_sw128_bo(slot_t + sh * 128 + j * 32, bo);
+                        dal = umma_desc_sw128_bo(slot_t + LT_A_BYTES + sh * 128 + j * 32, bo);
+                        dbh = umma_desc_sw128(cw_t + k * C * 128 + j * 32);
+                        dbl = umma_desc_sw128(cw_t + LT_CW_BYTES + k * C * 128 + j * 32);
                     } else {
-                        const uint32_t aoff = (2 * j * LT_PANEL_A + arow) >> 4, boff = (uint32_t)((k * 8 + 2 * j) * C * 16) >> 4;
-                        dah = dA_hi + aoff; dal = dah + kA_LO; dbh = dCW_hi + boff; dbl = dbh + kCW_LO;
+                        const uint32_t aoff = 2 * j * LT_PANEL_A + arow, boff = (uint32_t)((k * 8 + 2 * j) * C * 16);
+                        dah = umma_desc_ns(slot_t + aoff, LT_PANEL_A, 128); dal = umma_desc_ns(slot_t + LT_A_BYTES + aoff, LT_PANEL_A, 128);
+                        dbh = umma_desc_ns(cw_t + boff, C * 16, 128); dbl = umma_desc_ns(cw_t + LT_CW_BYTES + boff, C * 16, 128);
                     }
                     umma_tf32(tmem_u, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
                     if (three_pass) {
-                        umma_tf32(tmem_u + 32, dah, dbl, idesc_conv, (k | j) ? 1u : 0u);
-                        umma_tf32(tmem_u + 64, dal, dbh, idesc_conv, (k | j) ? 1u : 0u);
+                        umma_tf32(tmem_u, dah, dbl, idesc_conv, 1u);
+                        umma_tf32(tmem_u, dal, dbh, idesc_conv, 1u);
                     }
                 }
             }
@@ -671,15 +679,6 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         if (gw < 4) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16), v);
-            if (three_pass) {   // total = hi*hi + (hi*lo + lo*hi)
-                uint32_t v1[32], v2[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16) + 32, v1);
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16) + 64, v2);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    v[i] = __float_as_uint(__uint_as_float(v[i]) + (__uint_as_float(v1[i]) + __uint_as_float(v2[i])));
-            }
             tmem_ld_wait();
             const int yr = gw * 32 + lane, t = t0 - 1 + yr;
             const bool in = (t >= 0 && t < T);
@@ -708,10 +707,12 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         // ---------------- phase 4: location-variable conv on tensor cores ----------------
         if (gw_u == 0) {
             tc_fence_after();
+            uint32_t slot_t = slot_u;
+            asm volatile("" : "+r"(slot_t));
             if (elect_one()) {
 #pragma unroll
             for (int fi = 0; fi < NF; ++fi) {
-                const uint32_t d = tmem_u + fi * 192;
+                const uint32_t d = tmem_u + 32 + fi * 64;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
 #pragma unroll
@@ -719,20 +720,21 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                         uint64_t dah, dal, dbh, dbl;
                         if (SWZ) {
                             const uint32_t bo = bo_mode ? (uint32_t)k : 0u;
-                            dah = umma_desc_sw128_bo(slot_u + k * 128 + j * 32, bo);
-                            dal = umma_desc_sw128_bo(slot_u + LT_A_BYTES + k * 128 + j * 32, bo);
-                            const uint32_t lwb = slot_u + 2 * LT_A_BYTES + fi * LT_LW_BYTES + k * LVC_OUT * 128 + j * 32;
+                            dah = umma_desc_sw128_bo(slot_t + k * 128 + j * 32, bo);
+                            dal = umma_desc_sw128_bo(slot_t + LT_A_BYTES + k * 128 + j * 32, bo);
+                            const uint32_t lwb = slot_t + 2 * LT_A_BYTES + fi * LT_LW_BYTES + k * LVC_OUT * 128 + j * 32;
                             dbh = umma_desc_sw128(lwb);
                             dbl = umma_desc_sw128(lwb + NF * LT_LW_BYTES);
                         } else {
-                            const uint32_t aoff = (2 * j * LT_PANEL_Y + k * 16) >> 4;
-                            const uint32_t boff = (uint32_t)(fi * LT_LW_BYTES + (k * 8 + 2 * j) * LVC_OUT * 16) >> 4;
-                            dah = dA_hi - kY_FROM_A + aoff; dal = dah + kA_LO; dbh = dLW_hi + boff; dbl = dbh + kLW_LO;
+                            const uint32_t aoff = 2 * j * LT_PANEL_Y + k * 16;
+                            const uint32_t boff = slot_t + 2 * LT_A_BYTES + (uint32_t)(fi * LT_LW_BYTES + (k * 8 + 2 * j) * LVC_OUT * 16);
+                            dah = umma_desc_ns(slot_t + aoff, LT_PANEL_Y, 128); dal = umma_desc_ns(slot_t + LT_A_BYTES + aoff, LT_PANEL_Y, 128);
+                            dbh = umma_desc_ns(boff, LVC_OUT * 16, 128); dbl = umma_desc_ns(boff + NF * LT_LW_BYTES, LVC_OUT * 16, 128);
                         }
                         umma_tf32(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
                         if (three_pass) {
-                            umma_tf32(d + 64, dah, dbl, idesc_lvc, (k | j) ? 1u : 0u);
-                            umma_tf32(d + 128, dal, dbh, idesc_lvc, (k | j) ? 1u : 0u);
+                            umma_tf32(d, dah, dbl, idesc_lvc, 1u);
+                            umma_tf32(d, dal, dbh, idesc_lvc, 1u);
                         }
                     }
                 }
@@ -772,22 +774,9 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             tc_fence_after();
             LT_STAMP(9);   // LVC MMAs complete
             uint32_t zs[16], zt[16];
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + fi * 192 + half * 16;
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 32 + fi * 64 + half * 16;
             tmem_ld_32x32b_x16(ta, zs);
             tmem_ld_32x32b_x16(ta + 32, zt);
-            if (three_pass) {
-                uint32_t a1[16], a2[16];
-                tmem_ld_32x32b_x16(ta + 64, a1);
-                tmem_ld_32x32b_x16(ta + 128, a2);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) zs[i] = __float_as_uint(__uint_as_float(zs[i]) + (__uint_as_float(a1[i]) + __uint_as_float(a2[i])));
-                tmem_ld_32x32b_x16(ta + 64 + 32, a1);
-                tmem_ld_32x32b_x16(ta + 128 + 32, a2);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) zt[i] = __float_as_uint(__uint_as_float(zt[i]) + (__uint_as_float(a1[i]) + __uint_as_float(a2[i])));
-            }
             tmem_ld_wait();
             if (t < T) {
                 const float* lb = lbias + fi * 64 + half * 16;
