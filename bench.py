@@ -39,6 +39,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout must carry exactly ONE JSON line.  Libraries (NCCL's version banner, the sampler's reference-compatible prints) write
+# to fd 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -60,7 +71,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
         except Exception as e:  # pragma: no cover
@@ -132,7 +143,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -282,10 +293,19 @@ def run_ours(args):
             "lvc_layer_b1": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 4,
             "lvc_layer_b0": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 32,
         }.get(dom)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tr = json.load(f).get(dom)
+            if tr and B == 8 and Tm == 861:
+                traffic = {"bytes_per_launch": tr["bytes_per_launch"], "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"],
+                           "source": "ncu --set full, " + tr["source"]}
+        except Exception:
+            pass
         if flop_per_launch:
             ach = flop_per_launch / (avg_ms * 1e-3) / 1e12
             roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tensor"], "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained (of measured)",
+                        "frac": ach / peaks["tensor"], "traffic": traffic, "peak_source": peaks["src"] + " bf16_tflops_sustained (of measured)",
                         "avg_launch_ms": avg_ms, "launches": n_dom, "share_of_step": per_kernel[dom]["ms"] / total_ms,
                         "algorithmic_flop_per_launch": flop_per_launch, "mode": mode_name}
     whole = {"achieved_tflops": FLOP_PER_SAMPLE_STEP * 4 * world * B * L / (ms_per_step * 1e-3) / 1e12,
@@ -316,7 +336,7 @@ def run_ours(args):
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in per_kernel.items()}, "whole_step": whole,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
