@@ -594,7 +594,7 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         const int want_bias = name[1] == 'b';
         *count = want_bias ? (size_t)B * LAYERS * LVC_OUT * Tm : (size_t)B * LAYERS * C * LVC_OUT * KS * Tm;
         if (!out_dev) return FD_OK;
-        FD_LAUNCH(k_kern_to_ref, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, ws + w.kern + (size_t)n * B * Tm * KCN, out_dev, B, Tm, want_bias);
+        FD_LAUNCH(k_kern_to_ref, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, ws + w.kern + (size_t)n * B * Tm * KCN, out_dev, B, Tm, want_bias, n == 0 ? 1 : 0);
         FD_CHECK_LAUNCH(h, "k_kern_to_ref");
         return FD_OK;
     }

@@ -21,22 +21,25 @@
  *   LBn_KPIN_W[5 j][80 ci][64 co]   kernel_predictor.input_conv.0   LBn_KPIN_B [64]
  *   LBn_KPRES_W[6][3 j][64 ci][64 co] kernel_predictor.residual_conv.{1,3,6,8,11,13}   LBn_KPRES_B [6][64]
  *   LBn_KC_W  [192 kk=(j*64+c)][24832 n]   kernel_conv + bias_conv fused along n, permuted so one GEMM row
- *             is, per LVC layer l, the operand of the location-variable conv in K-major "panel" order
- *             [k 3][i/4 8][o 64][i%4 4] (16-byte chunks of 4 input channels: directly a no-swizzle K-major UMMA
- *             operand, and one conflict-free LDS.128 per lane for the SIMT kernel) followed by its 64 biases:
- *                                n = l*6208 + ((k*8 + i/4)*64 + o)*4 + i%4   <- kernel_conv channel ((l*32+i)*64+o)*3+k
- *                                n = l*6208 + 6144 + o                       <- bias_conv channel l*64+o
+ *             is, per LVC layer l, the B operand of the location-variable conv as its SWIZZLE_128B K-major smem image:
+ *             per tap k a tile of 64 rows (o) x 128 B (32 input channels), the 16-byte chunk c = i/4 of row o stored at
+ *             chunk position c ^ (o & 7).  A bulk copy of the 24,576 B lands it in smem ready for tcgen05.mma, and the SIMT
+ *             kernel reads one conflict-free LDS.128 per lane.  Followed by the 64 biases:
+ *                                n = l*6208 + ((k*64 + o)*8 + ((i/4) ^ (o & 7)))*4 + i%4   <- kernel_conv channel ((l*32+i)*64+o)*3+k
+ *                                n = l*6208 + 6144 + o                                     <- bias_conv channel l*64+o
+ *             Block 0 (hop 8, SIMT consumer reading straight from HBM) uses PANEL order instead:
+ *                                n = l*6208 + ((k*8 + i/4)*64 + o)*4 + i%4   (consecutive lanes o -> consecutive 16-byte vectors)
  *             (channel maps: modules.py:333-342)
  *   LBn_KC_B  [24832]         same permutation of the two bias vectors
  *   LBn_KCT_HI / LBn_KCT_LO [24832 n][192 kk]   the same matrix transposed (K-major rows: the tcgen05 A operand),
  *             split into tf32 pieces  w = hi + lo,  hi = RN_tf32(w), lo = RN_tf32(w - hi)  (low 13 mantissa bits zero)
- *   LBn_CONVT_HI / LBn_CONVT_LO [4 layers][3 k][8 ci/4][32 co][4 ci%4]   lvc_blocks.n.convs.* as K-major UMMA panels, tf32 pieces
+ *   LBn_CONVT_HI / LBn_CONVT_LO [4 layers][3 k][32 co][8 chunks (ci/4) ^ (co&7)][4]   lvc_blocks.n.convs.* as SWIZZLE_128B K-major tiles, tf32 pieces
  */
 #ifndef FD_BLOB_H
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 4ULL
+#define FD_BLOB_VERSION 6ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */

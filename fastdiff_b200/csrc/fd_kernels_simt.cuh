@@ -559,21 +559,43 @@ __global__ void __launch_bounds__(256) k_lvc_layer(LvcParams p, const float* __r
             const float b0 = W[KK * LVC_OUT + lane], b1 = W[KK * LVC_OUT + C + lane];
 #pragma unroll
             for (int n = 0; n < 8; ++n) { a0[n] = b0; a1[n] = b1; }
+            if (WL_SMEM) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
+                for (int k = 0; k < 3; ++k) {
 #pragma unroll 2
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    // panel order [k][i/4][o][i%4]: one 16-byte vector per lane holds the 4 input channels of chunk c4
-                    const float4 wa = *reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + lane) * 4);
-                    const float4 wb = *reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + C + lane) * 4);
-                    const float w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w};
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        // SWIZZLE_128B tile order [k][o][(i/4) ^ (o&7)][i%4]: one 16-byte vector per lane = the 4 input channels
+                        // of chunk c4 for output channel o (lane, lane+32: same o&7, so the same swizzled position)
+                        const float4 wa = *reinterpret_cast<const float4*>(W + ((k * LVC_OUT + lane) * 8 + (c4 ^ (lane & 7))) * 4);
+                        const float4 wb = *reinterpret_cast<const float4*>(W + ((k * LVC_OUT + C + lane) * 8 + (c4 ^ (lane & 7))) * 4);
+                        const float w0[4] = {wa.x, wa.y, wa.z, wa.w}, w1[4] = {wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
-                    for (int n = 0; n < 8; ++n) {
-                        const float4 v = y4[(base + n + k) * 8 + c4];
-                        a0[n] = fmaf(v.x, w0[0], a0[n]); a0[n] = fmaf(v.y, w0[1], a0[n]);
-                        a0[n] = fmaf(v.z, w0[2], a0[n]); a0[n] = fmaf(v.w, w0[3], a0[n]);
-                        a1[n] = fmaf(v.x, w1[0], a1[n]); a1[n] = fmaf(v.y, w1[1], a1[n]);
-                        a1[n] = fmaf(v.z, w1[2], a1[n]); a1[n] = fmaf(v.w, w1[3], a1[n]);
+                        for (int n = 0; n < 8; ++n) {
+                            const float4 v = y4[(base + n + k) * 8 + c4];
+                            a0[n] = fmaf(v.x, w0[0], a0[n]); a0[n] = fmaf(v.y, w0[1], a0[n]);
+                            a0[n] = fmaf(v.z, w0[2], a0[n]); a0[n] = fmaf(v.w, w0[3], a0[n]);
+                            a1[n] = fmaf(v.x, w1[0], a1[n]); a1[n] = fmaf(v.y, w1[1], a1[n]);
+                            a1[n] = fmaf(v.z, w1[2], a1[n]); a1[n] = fmaf(v.w, w1[3], a1[n]);
+                        }
+                    }
+                }
+            } else {
+                // kernels straight from HBM (hop 8: each is used by 8 samples only).  Block 0's kernels are stored in PANEL order
+                // [k][i/4][o][i%4] (fd_blob.h): consecutive lanes read consecutive 16-byte vectors -> 512 B coalesced per request.
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+#pragma unroll 2
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 wa = *reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + lane) * 4);
+                        const float4 wb = *reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + C + lane) * 4);
+#pragma unroll
+                        for (int n = 0; n < 8; ++n) {
+                            const float4 v = y4[(base + n + k) * 8 + c4];
+                            a0[n] = fmaf(v.x, wa.x, a0[n]); a0[n] = fmaf(v.y, wa.y, a0[n]);
+                            a0[n] = fmaf(v.z, wa.z, a0[n]); a0[n] = fmaf(v.w, wa.w, a0[n]);
+                            a1[n] = fmaf(v.x, wb.x, a1[n]); a1[n] = fmaf(v.y, wb.y, a1[n]);
+                            a1[n] = fmaf(v.z, wb.z, a1[n]); a1[n] = fmaf(v.w, wb.w, a1[n]);
+                        }
                     }
                 }
             }
@@ -691,7 +713,7 @@ __global__ void __launch_bounds__(256) k_cl_to_ncl(const float* __restrict__ in,
 }
 
 __global__ void __launch_bounds__(256) k_kern_to_ref(const float* __restrict__ kern, float* __restrict__ out, int B, int Tm,
-                                                     int want_bias) {
+                                                     int want_bias, int panel) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (!want_bias) {  // (B,4,32,64,3,T')
         if (i >= (size_t)B * LAYERS * C * LVC_OUT * KS * Tm) return;
@@ -702,7 +724,9 @@ __global__ void __launch_bounds__(256) k_kern_to_ref(const float* __restrict__ k
         const int ci = (int)(q % C); q /= C;
         const int l = (int)(q % LAYERS); q /= LAYERS;
         const int b = (int)q;
-        out[i] = kern[((size_t)b * Tm + f) * KCN + l * KPL + ((k * 8 + ci / 4) * LVC_OUT + o) * 4 + (ci & 3)];
+        const int within = panel ? ((k * 8 + (ci >> 2)) * LVC_OUT + o) * 4 + (ci & 3)
+                                 : ((k * LVC_OUT + o) * 8 + ((ci >> 2) ^ (o & 7))) * 4 + (ci & 3);
+        out[i] = kern[((size_t)b * Tm + f) * KCN + l * KPL + within];
     } else {  // (B,4,64,T')
         if (i >= (size_t)B * LAYERS * LVC_OUT * Tm) return;
         size_t q = i;

@@ -104,6 +104,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;              // SWIZZLE_128B
     return d;
 }
+// K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices, LBO between K chunks, SBO between 8-row groups (microbenchmark only).
+__device__ __forceinline__ uint64_t umma_desc_ns(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -356,60 +365,45 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
 // ---------------------------------------------------------------------------------------------------------
 // K11+K12+K13  one LVC layer on tensor cores (modules.py:208-217), blocks 1 (hop 64) and 2 (hop 256).
 //
-// Per tile of 128 time steps (one batch item), all operands K-major, NO swizzle, in "panel" order: a tile of R rows x 32
-// channels is stored as 8 panels (one per 16-byte chunk of 4 channels), panel c = R consecutive 16-byte rows.  In UMMA
-// terms ((8,m),(4,2)):((16B,SBO=128B),(4B,LBO=panel stride)); a dilated-conv tap is then just start address + shift*16 B,
-// for ANY shift (no swizzle-phase constraint), which is what makes the im2col free.
+// Per tile of 128 time steps (one batch item).  Every operand is a K-major SWIZZLE_128B tile: row r = 128 B (32 channels)
+// at r*128, its 16-byte chunk c stored at chunk position c ^ (r & 7).  A dilated-conv tap is the SAME tile read from
+// `start + shift*128 B` -- measured on B200: shifts that are not multiples of 8 rows are handled correctly with descriptor
+// base_offset = 0 (the swizzle XOR uses absolute smem address bits), so the im2col over time costs nothing.
 //   conv :  D1[128 rows x 32]  = sum_{k<3} A[rows + (k-1)*dil][32 ci] * Wc[k][32 co x 32 ci]^T    rows t0-1 .. t0+126;
 //           the LVC also needs y at t0+127, t0+128: those 2 rows are computed with FFMA while the MMAs run
-//   y = lrelu(D1 + b) -> tf32 pieces -> panels (aliasing the A tile)
+//   y = lrelu(D1 + b) -> tf32 pieces -> rows of the Y tile (aliasing the A tile)
 //   lvc  :  D2[128 x 64] = sum_{k<3} Y[rows + k][32] * Wl[f][k][64 o x 32 i]^T   with the per-frame predicted kernels
 //           (hop 64: two frames per tile, each run over the whole M-tile into its own TMEM columns; rows pick their frame)
 //   out = xs + sigmoid(D2[:, :32] + b) * tanh(D2[:, 32:] + b),  xs = x + skip re-read from global
-// 3xTF32: every MMA is issued for (hi,hi), (hi,lo), (lo,hi).
-// One persistent CTA per SM with GROUPS independent 8-warp groups, each owning a tile slot (smem operands, TMEM columns,
-// mbarriers, a named barrier) and walking its own tile sequence, so one group's global loads / epilogues overlap the
-// other's MMAs.  Thread 0 of a group issues its MMAs.
+// 3xTF32: every MMA is issued for (hi,hi), (hi,lo), (lo,hi) into one accumulator.
+//
+// Data movement: the raw inputs of a tile -- x rows, skip rows (block 1) or the audio window (block 2), and the predicted
+// kernels, which the KC GEMM already wrote in this tile layout -- are fetched by cp.async.bulk (one elected thread, mbarrier
+// complete_tx) ONE TILE AHEAD, straight into the tile's own operand regions (x rows land row-major in the rows of the A_lo
+// tile, skip rows in A_hi, kernels in LW_hi), and are then transformed in place (x+skip, lrelu, Veltkamp tf32 split; the 8
+// lanes of a row read, __syncwarp, write the permuted chunks).  No register staging, no LDG queue pressure, no extra smem;
+// the copies for tile i+1 are issued the moment tile i's LVC MMAs have completed and overlap its gate epilogue.
+//
+// One persistent CTA per SM with GROUPS independent 8-warp groups, each owning a tile slot (operand tiles, TMEM columns,
+// mbarriers, a named barrier) and walking its own tile sequence, so one group's transforms / epilogues overlap the other's
+// MMAs.  One elected lane of a group's warp 0 issues its MMAs and bulk copies.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LT_TT = 128;
-constexpr int LT_A_ROWS = 184;                      // conv input rows: t0-28 .. t0+155
-constexpr int LT_PANEL_A = LT_A_ROWS * 16 + 16;     // 2960 B (odd multiple of 16: conflict-free panel writes)
-constexpr int LT_Y_ROWS = 136;
-constexpr int LT_PANEL_Y = LT_Y_ROWS * 16 + 16;     // 2192 B
-constexpr int LT_A_BYTES = 24576;                   // >= 8*LT_PANEL_A (23680) and >= 184*128 (23552); 1 KB multiple
-constexpr int LT_CW_BYTES = 3 * 8 * C * 16;         // 12288
-constexpr int LT_LW_BYTES = KK * LVC_OUT * 4;       // 24576
-constexpr int LT_AU = 352;                          // audio samples staged per tile (SKIP_FIRST)
+constexpr int LT_A_BYTES = 24576;                   // 192 rows x 128 B (rows 0..183 used: t0-28 .. t0+155)
+constexpr int LT_CW_BYTES = 3 * C * 128;            // 12288
+constexpr int LT_LW_BYTES = 3 * LVC_OUT * 128;      // 24576
+constexpr int LT_AU = 192;                          // audio window (SKIP_FIRST): positions t0-32 .. t0+159
 template <int HOP>
 __host__ __device__ constexpr int lt_nf() { return LT_TT / HOP > 0 ? LT_TT / HOP : 1; }
-// slot = A hi | A lo | LW hi [NF] | LW lo [NF] | lbias | audio, padded to 1 KB so every operand tile can be SWIZZLE_128B
 template <int HOP>
-__host__ __device__ constexpr int lt_slot_bytes() { return ((2 * LT_A_BYTES + lt_nf<HOP>() * (2 * LT_LW_BYTES + 256) + LT_AU * 4) + 1023) / 1024 * 1024; }
-// Operand tile addressing.  SWZ = SWIZZLE_128B K-major (row r = 128 B at r*128, 16-byte chunk c stored at c ^ (r & 7));
-// !SWZ = no-swizzle panels (chunk c of row r at c*panel + r*16).  B-operand tiles hold NR rows per tap.
-template <bool SWZ>
-__device__ __forceinline__ uint32_t tile_off(int row, int c, int panel) {
-    return SWZ ? (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)) : (uint32_t)(c * panel + row * 16);
-}
-template <bool SWZ, int NR>
-__device__ __forceinline__ uint32_t btile_off(int k, int c, int n) {
-    return SWZ ? (uint32_t)(k * NR * 128 + n * 128 + ((c ^ (n & 7)) << 4)) : (uint32_t)(((k * 8 + c) * NR + n) * 16);
-}
-__device__ __forceinline__ uint64_t umma_desc_sw128_bo(uint32_t smem_addr, uint32_t base_offset) {
-    return umma_desc_sw128(smem_addr) | ((uint64_t)(base_offset & 7u) << 49);
-}
-constexpr int LT_SHARED_BYTES = 2 * LT_CW_BYTES + (7 * C + C + C) * 4 + 64;   // conv W pieces, first_w, first_b, conv_b, barriers+tmem ptr
+__host__ __device__ constexpr int lt_slot_bytes() { return 2 * LT_A_BYTES + lt_nf<HOP>() * 2 * LT_LW_BYTES; }   // A hi | A lo | LW hi[NF] | LW lo[NF]
+template <int HOP>
+__host__ __device__ constexpr int lt_small_bytes() { return 2 * (lt_nf<HOP>() * 256 + LT_AU * 4); }            // double-buffered lbias | audio
+constexpr int LT_SHARED_BYTES = 2 * LT_CW_BYTES + (7 * C + C + C) * 4 + 128;   // conv W pieces, first_w, first_b, conv_b, barriers + tmem ptr
 template <int HOP, int GROUPS>
-constexpr int lt_smem_bytes() { return GROUPS * lt_slot_bytes<HOP>() + LT_SHARED_BYTES + 1024; }
+constexpr int lt_smem_bytes() { return GROUPS * (lt_slot_bytes<HOP>() + lt_small_bytes<HOP>()) + LT_SHARED_BYTES + 1024; }
 
-__device__ __forceinline__ uint64_t umma_desc_ns(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;
-    d |= (uint64_t)1 << 46;   // version; layout_type 0 = no swizzle
-    return d;
-}
+__device__ __forceinline__ uint32_t swz128(int row, int c) { return (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)); }
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -420,6 +414,10 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // tf32 pieces by Veltkamp splitting (3 FP ops): hi = x rounded to nearest at 11 significant bits (low 13 mantissa bits
 // zero -> exactly a tf32), lo = x - hi exactly.  lo is handed to the tensor core as is (its own tf32 conversion of lo costs
 // <= 2^-11 |lo| <= 2^-22 |x|).  `cvt.rna.tf32.f32` is emulated with ~8 integer instructions on sm_100a (ncu: it was the
@@ -428,7 +426,6 @@ __device__ __forceinline__ float split_hi(float x) {
     const float c = __fmul_rn(x, 8193.0f);
     return __fsub_rn(c, __fsub_rn(c, x));
 }
-__device__ __forceinline__ float cvt_tf32(float x) { return split_hi(x); }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
     hi = make_float4(split_hi(v.x), split_hi(v.y), split_hi(v.z), split_hi(v.w));
     lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
@@ -437,8 +434,8 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + exp2f(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + exp2f(2.8853900817779268f * x)); }
 
-// phase timeline of CTA 0 / group 0 (clock64 at phase boundaries, 10 stamps per tile, first 12 tiles) -- read through
-// fd_debug_read("lvc_timeline"); costs one thread a handful of clock reads per tile.
+// phase timeline of CTA 0 / group 0 (clock64 at phase boundaries) -- compiled in with -DFD_LVC_TIMELINE, read through
+// fd_debug_read("lvc_timeline").
 __device__ unsigned long long g_lvc_timeline[128];
 #ifdef FD_LVC_TIMELINE
 #define LT_STAMP(i) do { if (stamp && tile_no < 12) g_lvc_timeline[tile_no * 10 + (i)] = clock64(); } while (0)
@@ -447,55 +444,56 @@ __device__ unsigned long long g_lvc_timeline[128];
 #endif
 
 struct LvcTcParams {
-    const float* cw_hi; const float* cw_lo;      // [3][8][32][4] tf32 pieces of this layer's dilated conv
+    const float* cw_hi; const float* cw_lo;      // [3][32 co][8 chunks ^ (co&7)][4] tf32 pieces of this layer's dilated conv
     const float* conv_b;                         // [32]
     const float* first_w; const float* first_b;  // [7][32], [32]   (SKIP_FIRST)
 };
 
-template <int HOP, bool SKIP_FIRST, int GROUPS, bool SWZ>
+template <int HOP, bool SKIP_FIRST, int GROUPS>
 __global__ void __launch_bounds__(256 * GROUPS, 1)
 k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
-               float* __restrict__ x_out, int B, int T, int Tm, int dil, int three_pass, int bo_mode) {
+               float* __restrict__ x_out, int B, int T, int Tm, int dil, int three_pass) {
     constexpr int NF = lt_nf<HOP>();
     constexpr int SLOT = lt_slot_bytes<HOP>();
+    constexpr int SMALL = lt_small_bytes<HOP>();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space
     unsigned char* cw_hi = smem + GROUPS * SLOT;
     unsigned char* cw_lo = cw_hi + LT_CW_BYTES;
-    float* fw_s = (float*)(cw_lo + LT_CW_BYTES);         // [7][32] first_audio_conv weights
-    float* fb_s = fw_s + 7 * C;                          // [32]
-    float* cb_s = fb_s + C;                              // [32] dilated-conv bias
-    uint64_t* bars = (uint64_t*)(cb_s + C);              // [GROUPS][2]
-    uint32_t* tmem_base_s = (uint32_t*)(bars + 4);
+    unsigned char* small0 = cw_lo + LT_CW_BYTES;             // [GROUPS][2 buffers][lbias NF*64 | audio LT_AU]
+    float* fw_s = (float*)(small0 + GROUPS * SMALL);         // [7][32] first_audio_conv weights
+    float* fb_s = fw_s + 7 * C;                              // [32]
+    float* cb_s = fb_s + C;                                  // [32] dilated-conv bias
+    uint64_t* bars = (uint64_t*)(cb_s + C);                  // [GROUPS][4]: conv MMAs, LVC MMAs, loads, (pad)
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 8);
 
     const int tid = threadIdx.x, g = tid >> 8, gt = tid & 255, gw = gt >> 5, lane = tid & 31;
     unsigned char* slot = smem + g * SLOT;
-    unsigned char* a_hi = slot;                           // A panels (hi) | later: Y panels (hi)
-    unsigned char* a_lo = a_hi + LT_A_BYTES;
-    unsigned char* lw_hi = a_lo + LT_A_BYTES;             // [NF][24576]
+    unsigned char* a_hi = slot;                              // A tile (hi) | raw skip rows (block 1) | later: Y tile (hi)
+    unsigned char* a_lo = a_hi + LT_A_BYTES;                 // A tile (lo) | raw x rows            | later: Y tile (lo)
+    unsigned char* lw_hi = a_lo + LT_A_BYTES;                // [NF][24576]  raw predicted kernels -> hi
     unsigned char* lw_lo = lw_hi + NF * LT_LW_BYTES;
-    float* lbias = (float*)(lw_lo + NF * LT_LW_BYTES);    // [NF][64]
-    float* au_s = lbias + NF * 64;                        // [LT_AU]
-    uint64_t* bar = bars + 2 * g;
+    unsigned char* small = small0 + g * SMALL;
+    uint64_t* bar = bars + 4 * g;
 
     if (tid == 0) {
-        for (int i = 0; i < 2 * GROUPS; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 4 * GROUPS; ++i) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {   // per-layer constants: the global order of the conv weights is already the smem panel image
+    {   // per-layer constants: the global order of the conv weights is already the swizzled smem image
         const float4* sh = reinterpret_cast<const float4*>(p.cw_hi); const float4* sl = reinterpret_cast<const float4*>(p.cw_lo);
-        for (int i = tid; i < LT_CW_BYTES / 16; i += 256 * GROUPS) {   // global order [k][c8][co][4]
-            const uint32_t o = btile_off<SWZ, C>(i / (8 * C), (i / C) & 7, i % C);
-            *reinterpret_cast<float4*>(cw_hi + o) = sh[i];
-            *reinterpret_cast<float4*>(cw_lo + o) = sl[i];
+        for (int i = tid; i < LT_CW_BYTES / 16; i += 256 * GROUPS) {
+            reinterpret_cast<float4*>(cw_hi)[i] = sh[i];
+            reinterpret_cast<float4*>(cw_lo)[i] = sl[i];
         }
         if (tid < 7 * C) fw_s[tid] = SKIP_FIRST ? p.first_w[tid] : 0.f;
         if (tid < C) { fb_s[tid] = SKIP_FIRST ? p.first_b[tid] : 0.f; cb_s[tid] = p.conv_b[tid]; }
     }
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -504,7 +502,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     const uint32_t tmem_base = *tmem_base_s + g * 256;
     constexpr uint32_t idesc_conv = umma_idesc_tf32(128, 32), idesc_lvc = umma_idesc_tf32(128, 64);
 
-    // phase-1 role of this thread is fixed: channel chunk c4 = gt & 7 -> keep its first-conv taps in registers
+    // this thread's fixed role in the A transform: channel chunk c4 = gt & 7 -> keep its first-conv taps in registers
     const int c4 = gt & 7;
     float fwr[7][4], fbr[4];
     if (SKIP_FIRST) {
@@ -515,100 +513,109 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
 #pragma unroll
         for (int q = 0; q < 4; ++q) fbr[q] = fb_s[c4 * 4 + q];
     }
-
-    // Warp-uniform copies (shfl from lane 0) so the MMA issue path is provably uniform, and descriptor bases built once:
-    // every descriptor of the kernel is base + (byte offset >> 4) on the start-address field.
+    // warp-uniform copies (shfl from lane 0) so the issue paths are provably uniform
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
     const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * SLOT);
     const uint32_t cw_u = smem_u32(cw_hi);
-    // no-swizzle descriptors are rebuilt at the issue site from (slot_u, cw_u): a handful of uniform-datapath integer ops,
-    // cheaper than keeping 64-bit bases live across the whole tile loop (register pressure at 128 regs/thread)
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-    const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt;
-    uint32_t parity = 0;
+    const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt, tstride = gridDim.x * GROUPS;
+    const int r_lo = 27 - dil, r_hi = 157 + dil;   // A rows ar <-> t = t0 - 28 + ar that the 130 conv outputs touch
+
+    // Issue the bulk copies of one tile into this group's slot / small buffer `buf` (call from ONE thread).
+    auto issue_loads = [&](int tile, int buf) {
+        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+        float* lbias = (float*)(small + buf * (SMALL / 2));
+        float* au = lbias + NF * 64;
+        const int ar0 = max(r_lo, 28 - t0), ar1 = min(r_hi, T - t0 + 28);
+        const int i0 = max(0, 32 - t0), i1 = min(LT_AU, T - t0 + 32);
+        uint32_t bytes = 0;
+        if (ar1 > ar0) bytes += (uint32_t)(ar1 - ar0) * 128u * (SKIP_FIRST ? 1u : 2u);
+        if (SKIP_FIRST && i1 > i0) bytes += (uint32_t)(i1 - i0) * 4u;
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) bytes += LT_LW_BYTES + 256;
+        mbar_expect_tx(&bar[2], bytes);
+        if (ar1 > ar0) {
+            const size_t off = ((size_t)b * T + (t0 - 28 + ar0)) * C;
+            bulk_g2s(a_lo + ar0 * 128, x_in + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
+            if (!SKIP_FIRST) bulk_g2s(a_hi + ar0 * 128, skip + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
+        }
+        if (SKIP_FIRST && i1 > i0) bulk_g2s(au + i0, skip + (size_t)b * T + (t0 - 32 + i0), (uint32_t)(i1 - i0) * 4u, &bar[2]);
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) {
+            const int f = t0 / HOP + fi;
+            if (f < Tm) {
+                const float* src = kern + ((size_t)b * Tm + f) * KCN;
+                bulk_g2s(lw_hi + fi * LT_LW_BYTES, src, LT_LW_BYTES, &bar[2]);
+                bulk_g2s(lbias + fi * 64, src + KK * LVC_OUT, 256, &bar[2]);
+            }
+        }
+    };
+
+    int tile = blockIdx.x * GROUPS + g;
+    if (tile < total && gw_u == 0) { if (elect_one()) issue_loads(tile, 0); __syncwarp(); }
 #ifdef FD_LVC_TIMELINE
     const bool stamp = (blockIdx.x == 0 && tid == 0 && HOP == 256);
     int tile_no = -1;
 #endif
-    for (int tile = blockIdx.x * GROUPS + g; tile < total; tile += gridDim.x * GROUPS, parity ^= 1) {
+    uint32_t parity = 0;
+    for (; tile < total; tile += tstride, parity ^= 1) {
 #ifdef FD_LVC_TIMELINE
         ++tile_no;
 #endif
         const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+        const float* lbias = (const float*)(small + parity * (SMALL / 2));
+        float* au_s = (float*)lbias + NF * 64;
         LT_STAMP(0);
-        // ---------------- phase 1: operands -> smem panels (all global loads of the tile issued up front) ----------------
-        const int r_lo = 27 - dil + (gt >> 3), r_hi = 157 + dil;   // A rows ar <-> t = t0 - 28 + ar, this thread: r_lo, r_lo+32, ...
-        float4 xv[6], kv[NF][6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int ar = r_lo + i * 32, t = t0 - 28 + ar;
-            xv[i] = (ar < r_hi && t >= 0 && t < T) ? reinterpret_cast<const float4*>(x_in)[((size_t)b * T + t) * 8 + c4]
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---------------- phase 1: raw tile (bulk-copied one tile ago) -> tf32 operand tiles, in place ----------------
+        mbar_wait(&bar[2], parity);
+        LT_STAMP(1);
+        if (SKIP_FIRST) {   // audio positions outside [0,T) are zero (the first conv zero-pads)
+            if (gt < LT_AU) { const int pos = t0 - 32 + gt; if (pos < 0 || pos >= T) au_s[gt] = 0.f; }
+            group_sync(1 + g, 256);
         }
-        float4 skv[6];
-        if (!SKIP_FIRST) {
 #pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                const int ar = r_lo + i * 32, t = t0 - 28 + ar;
-                skv[i] = (ar < r_hi && t >= 0 && t < T) ? reinterpret_cast<const float4*>(skip)[((size_t)b * T + t) * 8 + c4]
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int fi = 0; fi < NF; ++fi) {   // predicted LVC kernels: hi in place, lo next to it (element-wise: the layout is already the tile's)
+            if (t0 / HOP + fi < Tm) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    float4* ph = reinterpret_cast<float4*>(lw_hi + fi * LT_LW_BYTES) + gt + i * 256;
+                    float4 hi, lo;
+                    split4(*ph, hi, lo);
+                    *ph = hi;
+                    reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES)[gt + i * 256] = lo;
+                }
             }
         }
-#pragma unroll
-        for (int fi = 0; fi < NF; ++fi) {
-            const int f = t0 / HOP + fi;
-            const float4* src = reinterpret_cast<const float4*>(kern + ((size_t)b * Tm + (f < Tm ? f : 0)) * KCN);
-#pragma unroll
-            for (int i = 0; i < 6; ++i) kv[fi][i] = src[gt + i * 256];
-            if (gt < 64) lbias[fi * 64 + gt] = kern[((size_t)b * Tm + (f < Tm ? f : 0)) * KCN + KK * LVC_OUT + gt];
-        }
-        if (SKIP_FIRST) {
-            for (int i = gt; i < LT_AU; i += 256) {   // au_s[i] <-> audio position t0 - 31 + i
-                const int pos = t0 - 31 + i;
-                au_s[i] = (pos >= 0 && pos < T) ? skip[(size_t)b * T + pos] : 0.f;
-            }
-        }
-#pragma unroll
-        for (int fi = 0; fi < NF; ++fi) {   // predicted LVC kernels of the frame(s): split into tf32 pieces
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-                float4 hi, lo;
-                split4(kv[fi][i], hi, lo);
-                const int e = gt + i * 256;   // global order [k][c8][o][4]
-                const uint32_t o = btile_off<SWZ, LVC_OUT>(e / (8 * LVC_OUT), (e / LVC_OUT) & 7, e % LVC_OUT);
-                *reinterpret_cast<float4*>(lw_hi + fi * LT_LW_BYTES + o) = hi;
-                *reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES + o) = lo;
-            }
-        }
-        LT_STAMP(1);   // loads issued, kernels split+stored
-        if (SKIP_FIRST) group_sync(1 + g, 256);   // audio tile visible
         LT_STAMP(2);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const int ar = r_lo + i * 32, t = t0 - 28 + ar;
-            if (ar < r_hi) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t >= 0 && t < T) {
-                    float4 sk;
-                    if (SKIP_FIRST) {
-                        sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
+        for (int i = 0; i < 6; ++i) {   // A rows: the 8 lanes of a row read its raw chunks, then write the swizzled tf32 pieces
+            const int ar = r_lo + (gt >> 3) + i * 32, t = t0 - 28 + ar;
+            const bool active = ar < r_hi;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active && t >= 0 && t < T) {
+                const float4 xv = *reinterpret_cast<const float4*>(a_lo + ar * 128 + c4 * 16);
+                float4 sk;
+                if (SKIP_FIRST) {
+                    sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
 #pragma unroll
-                        for (int k = 0; k < 7; ++k) {
-                            const float a = au_s[ar + k];
-                            sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
-                            sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
-                        }
-                    } else {
-                        sk = skv[i];
+                    for (int k = 0; k < 7; ++k) {
+                        const float a = au_s[ar + k + 1];
+                        sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
+                        sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
                     }
-                    v.x = lrelu(xv[i].x + sk.x, 0.2f); v.y = lrelu(xv[i].y + sk.y, 0.2f);
-                    v.z = lrelu(xv[i].z + sk.z, 0.2f); v.w = lrelu(xv[i].w + sk.w, 0.2f);
+                } else {
+                    sk = *reinterpret_cast<const float4*>(a_hi + ar * 128 + c4 * 16);
                 }
-                float4 hi, lo;
-                split4(v, hi, lo);
-                *reinterpret_cast<float4*>(a_hi + tile_off<SWZ>(ar, c4, LT_PANEL_A)) = hi;
-                *reinterpret_cast<float4*>(a_lo + tile_off<SWZ>(ar, c4, LT_PANEL_A)) = lo;
+                v.x = lrelu(xv.x + sk.x, 0.2f); v.y = lrelu(xv.y + sk.y, 0.2f);
+                v.z = lrelu(xv.z + sk.z, 0.2f); v.w = lrelu(xv.w + sk.w, 0.2f);
+            }
+            float4 hi, lo;
+            split4(v, hi, lo);
+            __syncwarp();   // every lane of the row has read its raw chunk before any lane overwrites the row
+            if (active) {
+                *reinterpret_cast<float4*>(a_hi + swz128(ar, c4)) = hi;
+                *reinterpret_cast<float4*>(a_lo + swz128(ar, c4)) = lo;
             }
         }
         LT_STAMP(3);   // A built
@@ -616,40 +623,29 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         group_sync(1 + g, 256);
         LT_STAMP(4);
         // ---------------- phase 2: dilated conv on tensor cores (+ 2 halo rows on FFMA meanwhile) ----------------
-        if (gw_u == 0) {   // whole warp, warp-uniform operands (descriptors stay in uniform registers); one elected lane issues
+        if (gw_u == 0) {
             tc_fence_after();
             uint32_t slot_t = slot_u, cw_t = cw_u;
-            asm volatile("" : "+r"(slot_t), "+r"(cw_t));   // opaque per tile: keeps ptxas from hoisting ~150 descriptors out of the tile loop
+            asm volatile("" : "+r"(slot_t), "+r"(cw_t));   // opaque per tile: keeps ptxas from hoisting ~100 descriptors out of the tile loop
             if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const uint32_t arow = (uint32_t)((27 + (k - 1) * dil) * 16);
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t sh = (uint32_t)(27 + (k - 1) * dil) * 128u;   // row shift: start address + shift*128 B, base_offset 0
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint64_t dah, dal, dbh, dbl;
-                    if (SWZ) {   // row shift = start address + shift*128 B; swizzle phase of the first row goes in base_offset
-                        const uint32_t sh = (uint32_t)(27 + (k - 1) * dil), bo = bo_mode ? (sh & 7u) : 0u;
-                        dah = umma_desc_sw128_bo(slot_t + sh * 128 + j * 32, bo);
-                        dal = umma_desc_sw128_bo(slot_t + LT_A_BYTES + sh * 128 + j * 32, bo);
-                        dbh = umma_desc_sw128(cw_t + k * C * 128 + j * 32);
-                        dbl = umma_desc_sw128(cw_t + LT_CW_BYTES + k * C * 128 + j * 32);
-                    } else {
-                        const uint32_t aoff = 2 * j * LT_PANEL_A + arow, boff = (uint32_t)((k * 8 + 2 * j) * C * 16);
-                        dah = umma_desc_ns(slot_t + aoff, LT_PANEL_A, 128); dal = umma_desc_ns(slot_t + LT_A_BYTES + aoff, LT_PANEL_A, 128);
-                        dbh = umma_desc_ns(cw_t + boff, C * 16, 128); dbl = umma_desc_ns(cw_t + LT_CW_BYTES + boff, C * 16, 128);
-                    }
-                    umma_tf32(tmem_u, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
-                    if (three_pass) {
-                        umma_tf32(tmem_u, dah, dbl, idesc_conv, 1u);
-                        umma_tf32(tmem_u, dal, dbh, idesc_conv, 1u);
+                    for (int j = 0; j < 4; ++j) {
+                        const uint64_t dah = umma_desc_sw128(slot_t + sh + j * 32), dal = umma_desc_sw128(slot_t + LT_A_BYTES + sh + j * 32);
+                        const uint64_t dbh = umma_desc_sw128(cw_t + k * C * 128 + j * 32), dbl = umma_desc_sw128(cw_t + LT_CW_BYTES + k * C * 128 + j * 32);
+                        umma_tf32(tmem_u, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
+                        if (three_pass) {
+                            umma_tf32(tmem_u, dah, dbl, idesc_conv, 1u);
+                            umma_tf32(tmem_u, dal, dbh, idesc_conv, 1u);
+                        }
                     }
                 }
-            }
-            tc_commit(&bar[0]);
+                tc_commit(&bar[0]);
             }
             __syncwarp();
         }
-        __syncwarp();
         float halo = 0.f;   // warps 6,7 of the group: conv outputs yr = 128 (warp 6), 129 (warp 7), lane = co
         if (gw >= 6) {
             const int yr = 128 + (gw - 6);
@@ -659,10 +655,10 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 const int ar = yr + 27 + (k - 1) * dil;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const float4 ah4 = *reinterpret_cast<const float4*>(a_hi + tile_off<SWZ>(ar, c, LT_PANEL_A));
-                    const float4 al4 = *reinterpret_cast<const float4*>(a_lo + tile_off<SWZ>(ar, c, LT_PANEL_A));
-                    const float4 wh4 = *reinterpret_cast<const float4*>(cw_hi + btile_off<SWZ, C>(k, c, lane));
-                    const float4 wl4 = *reinterpret_cast<const float4*>(cw_lo + btile_off<SWZ, C>(k, c, lane));
+                    const float4 ah4 = *reinterpret_cast<const float4*>(a_hi + swz128(ar, c));
+                    const float4 al4 = *reinterpret_cast<const float4*>(a_lo + swz128(ar, c));
+                    const float4 wh4 = *reinterpret_cast<const float4*>(cw_hi + k * C * 128 + swz128(lane, c));
+                    const float4 wl4 = *reinterpret_cast<const float4*>(cw_lo + k * C * 128 + swz128(lane, c));
                     acc = fmaf(ah4.x + al4.x, wh4.x + wl4.x, acc); acc = fmaf(ah4.y + al4.y, wh4.y + wl4.y, acc);
                     acc = fmaf(ah4.z + al4.z, wh4.z + wl4.z, acc); acc = fmaf(ah4.w + al4.w, wh4.w + wl4.w, acc);
                 }
@@ -670,8 +666,8 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             const int t = t0 - 1 + yr;
             halo = (t >= 0 && t < T) ? lrelu(acc, 0.2f) : 0.f;
         }
-        // ---------------- phase 3: y = lrelu(conv + b) -> tf32 panels (over the A tile) ----------------
-        LT_STAMP(5);   // conv MMAs issued (+ halo rows for warps 6,7)
+        // ---------------- phase 3: y = lrelu(conv + b) -> tf32 rows of the Y tile (over the A tile) ----------------
+        LT_STAMP(5);
         mbar_wait(&bar[0], parity);
         tc_fence_after();
         LT_STAMP(6);   // conv MMAs complete
@@ -691,14 +687,14 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 y.w = in ? lrelu(__uint_as_float(v[c * 4 + 3]) + cb_s[c * 4 + 3], 0.2f) : 0.f;
                 float4 hi, lo;
                 split4(y, hi, lo);
-                *reinterpret_cast<float4*>(a_hi + tile_off<SWZ>(yr, c, LT_PANEL_Y)) = hi;
-                *reinterpret_cast<float4*>(a_lo + tile_off<SWZ>(yr, c, LT_PANEL_Y)) = lo;
+                *reinterpret_cast<float4*>(a_hi + swz128(yr, c)) = hi;
+                *reinterpret_cast<float4*>(a_lo + swz128(yr, c)) = lo;
             }
         } else if (gw >= 6) {
             const int yr = 128 + (gw - 6);
             const float hi = split_hi(halo), lo = halo - hi;
-            *reinterpret_cast<float*>(a_hi + tile_off<SWZ>(yr, lane >> 2, LT_PANEL_Y) + (lane & 3) * 4) = hi;
-            *reinterpret_cast<float*>(a_lo + tile_off<SWZ>(yr, lane >> 2, LT_PANEL_Y) + (lane & 3) * 4) = lo;
+            *reinterpret_cast<float*>(a_hi + swz128(yr, lane >> 2) + (lane & 3) * 4) = hi;
+            *reinterpret_cast<float*>(a_lo + swz128(yr, lane >> 2) + (lane & 3) * 4) = lo;
         }
         fence_async_smem();
         tc_fence_before();
@@ -711,39 +707,28 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             asm volatile("" : "+r"(slot_t));
             if (elect_one()) {
 #pragma unroll
-            for (int fi = 0; fi < NF; ++fi) {
-                const uint32_t d = tmem_u + 32 + fi * 64;
+                for (int fi = 0; fi < NF; ++fi) {
+                    const uint32_t d = tmem_u + 32 + fi * 64;
+                    const uint32_t lwb = slot_t + 2 * LT_A_BYTES + fi * LT_LW_BYTES;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
+                    for (int k = 0; k < 3; ++k) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint64_t dah, dal, dbh, dbl;
-                        if (SWZ) {
-                            const uint32_t bo = bo_mode ? (uint32_t)k : 0u;
-                            dah = umma_desc_sw128_bo(slot_t + k * 128 + j * 32, bo);
-                            dal = umma_desc_sw128_bo(slot_t + LT_A_BYTES + k * 128 + j * 32, bo);
-                            const uint32_t lwb = slot_t + 2 * LT_A_BYTES + fi * LT_LW_BYTES + k * LVC_OUT * 128 + j * 32;
-                            dbh = umma_desc_sw128(lwb);
-                            dbl = umma_desc_sw128(lwb + NF * LT_LW_BYTES);
-                        } else {
-                            const uint32_t aoff = 2 * j * LT_PANEL_Y + k * 16;
-                            const uint32_t boff = slot_t + 2 * LT_A_BYTES + (uint32_t)(fi * LT_LW_BYTES + (k * 8 + 2 * j) * LVC_OUT * 16);
-                            dah = umma_desc_ns(slot_t + aoff, LT_PANEL_Y, 128); dal = umma_desc_ns(slot_t + LT_A_BYTES + aoff, LT_PANEL_Y, 128);
-                            dbh = umma_desc_ns(boff, LVC_OUT * 16, 128); dbl = umma_desc_ns(boff + NF * LT_LW_BYTES, LVC_OUT * 16, 128);
-                        }
-                        umma_tf32(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
-                        if (three_pass) {
-                            umma_tf32(d, dah, dbl, idesc_lvc, 1u);
-                            umma_tf32(d, dal, dbh, idesc_lvc, 1u);
+                        for (int j = 0; j < 4; ++j) {
+                            const uint64_t dah = umma_desc_sw128(slot_t + k * 128 + j * 32), dal = umma_desc_sw128(slot_t + LT_A_BYTES + k * 128 + j * 32);
+                            const uint64_t dbh = umma_desc_sw128(lwb + k * LVC_OUT * 128 + j * 32);
+                            const uint64_t dbl = umma_desc_sw128(lwb + NF * LT_LW_BYTES + k * LVC_OUT * 128 + j * 32);
+                            umma_tf32(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
+                            if (three_pass) {
+                                umma_tf32(d, dah, dbl, idesc_lvc, 1u);
+                                umma_tf32(d, dal, dbh, idesc_lvc, 1u);
+                            }
                         }
                     }
                 }
-            }
-            tc_commit(&bar[1]);
+                tc_commit(&bar[1]);
             }
             __syncwarp();
         }
-        __syncwarp();
         // ---------------- phase 5: gate + residual -> global ----------------
         {
             const int q = gw & 3, half = gw >> 2;              // lane quarter / which 16 of the 32 gate channels
@@ -759,7 +744,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                     float4 sk = *reinterpret_cast<const float4*>(fb_s + o);
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
-                        const float a = au_s[28 + r + k];
+                        const float a = au_s[29 + r + k];
                         const float4 w = *reinterpret_cast<const float4*>(fw_s + k * C + o);
                         sk.x = fmaf(w.x, a, sk.x); sk.y = fmaf(w.y, a, sk.y); sk.z = fmaf(w.z, a, sk.z); sk.w = fmaf(w.w, a, sk.w);
                     }
@@ -772,7 +757,8 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             LT_STAMP(8);   // LVC MMAs issued, residual prefetched
             mbar_wait(&bar[1], parity);
             tc_fence_after();
-            LT_STAMP(9);   // LVC MMAs complete
+            LT_STAMP(9);   // LVC MMAs complete: the slot's operand tiles are free -> fetch the next tile while this one is gated
+            if (gw_u == 0 && tile + tstride < total) { if (elect_one()) issue_loads(tile + tstride, (int)(parity ^ 1)); __syncwarp(); }
             uint32_t zs[16], zt[16];
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 32 + fi * 64 + half * 16;
             tmem_ld_32x32b_x16(ta, zs);
@@ -792,7 +778,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             }
         }
         tc_fence_before();
-        group_sync(1 + g, 256);   // the group's TMEM columns and smem slot are free for its next tile
+        group_sync(1 + g, 256);   // the group's TMEM columns are free for its next tile
     }
     tc_fence_before();
     __syncthreads();
@@ -817,15 +803,13 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
     p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
     const int total = B * ((T + LT_TT - 1) / LT_TT);
-    const int tp = mode == 1 ? 1 : 0, bo = s->lvc_swizzle == 2 ? 0 : 1;
+    const int tp = mode == 1 ? 1 : 0;
     if (blk == 1) {
         const int grid = total < s->sm_count ? total : s->sm_count;
-        if (s->lvc_swizzle) k_lvc_layer_tc<64, false, 1, true><<<grid, 256, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp, bo);
-        else                k_lvc_layer_tc<64, false, 1, false><<<grid, 256, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp, bo);
+        k_lvc_layer_tc<64, false, 1><<<grid, 256, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp);
     } else {
         const int pairs = (total + 1) / 2, grid = pairs < s->sm_count ? pairs : s->sm_count;
-        if (s->lvc_swizzle) k_lvc_layer_tc<256, true, 2, true><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp, bo);
-        else                k_lvc_layer_tc<256, true, 2, false><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp, bo);
+        k_lvc_layer_tc<256, true, 2><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_tc failed: ") + cudaGetErrorString(e); return -3; }
@@ -835,10 +819,8 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
 }
 
 static inline cudaError_t tc_set_lvc_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
+    cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
     return e;
 }
 

@@ -76,6 +76,11 @@ def tf32_split(x: np.ndarray):
     return hi, lo
 
 
+# swizzle gather indices: output[o, p] = input[o, p ^ (o & 7)]  (XOR is an involution, so the same table scatters and gathers)
+_SWZ_O = torch.arange(LVC_OUT).reshape(LVC_OUT, 1).expand(LVC_OUT, 8)
+_SWZ_SRC = torch.arange(8).reshape(1, 8) ^ (torch.arange(LVC_OUT).reshape(LVC_OUT, 1) & 7)
+
+
 def _conv_kcico(w: torch.Tensor) -> torch.Tensor:
     """Conv1d weight (co, ci, k) -> [k][ci][co]."""
     return w.permute(2, 1, 0).contiguous()
@@ -115,20 +120,31 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         S[f"LB{n}_KPRES_W"] = torch.stack([_conv_kcico(W[f"{kp}.residual_conv.{i}.weight"]) for i in (1, 3, 6, 8, 11, 13)])
         S[f"LB{n}_KPRES_B"] = torch.stack([W[f"{kp}.residual_conv.{i}.bias"] for i in (1, 3, 6, 8, 11, 13)])
         # kernel_conv (24576,64,3): channel ((l*32+i)*64+o)*3+k ; bias_conv (256,64,3): channel l*64+o  (modules.py:333-342)
-        # target column order inside a layer: ((k*8 + i//4)*64 + o)*4 + i%4  -- the K-major UMMA operand "panel" layout
+        # target column order inside a layer = the SWIZZLE_128B K-major smem image of the LVC B operand:
+        #   per tap k a [64 o rows][128 B] tile, 16-byte chunk c = i//4 of row o stored at chunk position c ^ (o & 7):
+        #   n = ((k*64 + o)*8 + ((i//4) ^ (o & 7)))*4 + i%4
         kc = W[f"{kp}.kernel_conv.weight"].reshape(LAYERS, 8, 4, LVC_OUT, KS, HID, 3)  # [l][i8][i4][o][k][c][j]
-        kc = kc.permute(6, 5, 0, 4, 1, 3, 2).reshape(3 * HID, LAYERS, KK * LVC_OUT)     # [j*64+c][l][k][i8][o][i4]
+        kc = kc.permute(6, 5, 0, 4, 3, 1, 2).reshape(3 * HID, LAYERS, KS, LVC_OUT, 8, 4)  # [j*64+c][l][k][o][i8][i4]
+        if n == 0:   # block 0 (hop 8) is consumed by the SIMT kernel straight from HBM: panel order [k][i8][o][i4], coalesced per lane
+            kc = kc.permute(0, 1, 2, 4, 3, 5).reshape(3 * HID, LAYERS, KK * LVC_OUT)
+        else:
+            kc = kc[:, :, :, _SWZ_O, _SWZ_SRC, :].reshape(3 * HID, LAYERS, KK * LVC_OUT)   # position p of row o <- chunk p ^ (o&7)
         bc = W[f"{kp}.bias_conv.weight"].reshape(LAYERS, LVC_OUT, HID, 3)              # [l][o][c][j]
         bc = bc.permute(3, 2, 0, 1).reshape(3 * HID, LAYERS, LVC_OUT)                   # [j*64+c][l][o]
         S[f"LB{n}_KC_W"] = torch.cat([kc, bc], dim=2).reshape(3 * HID, KCN).contiguous()
-        kcb = W[f"{kp}.kernel_conv.bias"].reshape(LAYERS, 8, 4, LVC_OUT, KS).permute(0, 4, 1, 3, 2).reshape(LAYERS, KK * LVC_OUT)
+        kcb = W[f"{kp}.kernel_conv.bias"].reshape(LAYERS, 8, 4, LVC_OUT, KS).permute(0, 4, 3, 1, 2)  # [l][k][o][i8][i4]
+        if n == 0:
+            kcb = kcb.permute(0, 1, 3, 2, 4).reshape(LAYERS, KK * LVC_OUT)
+        else:
+            kcb = kcb[:, :, _SWZ_O, _SWZ_SRC, :].reshape(LAYERS, KK * LVC_OUT)
         bcb = W[f"{kp}.bias_conv.bias"].reshape(LAYERS, LVC_OUT)
         S[f"LB{n}_KC_B"] = torch.cat([kcb, bcb], dim=1).reshape(KCN).contiguous()
         hi, lo = tf32_split(S[f"LB{n}_KC_W"].t().contiguous().numpy())   # [24832][192], K-major rows
         S[f"LB{n}_KCT_HI"] = torch.from_numpy(hi)
         S[f"LB{n}_KCT_LO"] = torch.from_numpy(lo)
         cw = torch.stack([W[f"{p}.convs.{i}.weight"] for i in range(LAYERS)])          # [l][co][ci][k]
-        cw = cw.reshape(LAYERS, C, 8, 4, KS).permute(0, 4, 2, 1, 3).contiguous()        # [l][k][ci8][co][ci4]
+        cw = cw.reshape(LAYERS, C, 8, 4, KS).permute(0, 4, 1, 2, 3)                      # [l][k][co][ci8][ci4]
+        cw = cw[:, :, _SWZ_O[:C], _SWZ_SRC[:C], :].contiguous()                          # SWIZZLE_128B image: chunk c at c ^ (co & 7)
         hi, lo = tf32_split(cw.numpy())
         S[f"LB{n}_CONVT_HI"] = torch.from_numpy(hi)
         S[f"LB{n}_CONVT_LO"] = torch.from_numpy(lo)

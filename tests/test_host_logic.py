@@ -73,8 +73,13 @@ def test_packer_layouts(synth):
     rng = np.random.default_rng(0)
     for _ in range(200):
         l, i, o, k, c, j = (int(rng.integers(n)) for n in (4, 32, 64, 3, 64, 3))
-        assert kc[j * 64 + c, l * 6208 + ((k * 8 + i // 4) * 64 + o) * 4 + i % 4] == kw[((l * 32 + i) * 64 + o) * 3 + k, c, j].item()
+        assert kc[j * 64 + c, l * 6208 + ((k * 64 + o) * 8 + ((i // 4) ^ (o & 7))) * 4 + i % 4] == kw[((l * 32 + i) * 64 + o) * 3 + k, c, j].item()
         assert kc[j * 64 + c, l * 6208 + 6144 + o] == bw[l * 64 + o, c, j].item()
+    kc0 = S["LB0_KC_W"].reshape(192, 24832)   # block 0: panel order
+    kw0 = W["lvc_blocks.0.kernel_predictor.kernel_conv.weight"]
+    for _ in range(100):
+        l, i, o, k, c, j = (int(rng.integers(n)) for n in (4, 32, 64, 3, 64, 3))
+        assert kc0[j * 64 + c, l * 6208 + ((k * 8 + i // 4) * 64 + o) * 4 + i % 4] == kw0[((l * 32 + i) * 64 + o) * 3 + k, c, j].item()
     up = S["LB2_UP_W"].reshape(8, 32, 32)
     assert up[5, 3, 7] == W["lvc_blocks.2.upsample.weight"][3, 7, 5].item()
     cw = S["LB0_CONV_W"].reshape(4, 3, 32, 32)
