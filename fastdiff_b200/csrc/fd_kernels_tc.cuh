@@ -454,13 +454,18 @@ __global__ void __launch_bounds__(256 * GROUPS, 1)
 k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
                float* __restrict__ x_out, int B, int T, int Tm, int dil, int three_pass) {
     constexpr int NF = lt_nf<HOP>();
+    // Merge the (hi,hi) and (hi,lo) passes into one MMA of twice the N (W_hi | W_lo as one operand): 88 vs 120 cycles per conv
+    // k-step, 112 vs 144 per LVC k-step (profiles/r01_tcgen05_findings.md) at the price of extra TMEM reads in the epilogues.
+    // Pays off for the single-group variant (nothing overlaps its MMAs); with two groups the MMAs are already hidden.
+    constexpr bool MERGE = (GROUPS == 1);
     constexpr int SLOT = lt_slot_bytes<HOP>();
     constexpr int SMALL = lt_small_bytes<HOP>();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset arithmetic keeps the shared address space
-    unsigned char* cw_hi = smem + GROUPS * SLOT;
-    unsigned char* cw_lo = cw_hi + LT_CW_BYTES;
-    unsigned char* small0 = cw_lo + LT_CW_BYTES;             // [GROUPS][2 buffers][lbias NF*64 | audio LT_AU]
+    // B-operand tiles are stored per tap as [hi rows | lo rows] so that (W_hi | W_lo) is ONE operand of twice the N:
+    //   conv: cw + k*8192 + {0: hi 32 rows, 4096: lo 32 rows};   lvc: lw + fi*49152 + k*16384 + {0: hi 64 rows, 8192: lo 64 rows}
+    unsigned char* cw = smem + GROUPS * SLOT;
+    unsigned char* small0 = cw + 2 * LT_CW_BYTES;            // [GROUPS][2 buffers][lbias NF*64 | audio LT_AU]
     float* fw_s = (float*)(small0 + GROUPS * SMALL);         // [7][32] first_audio_conv weights
     float* fb_s = fw_s + 7 * C;                              // [32]
     float* cb_s = fb_s + C;                                  // [32] dilated-conv bias
@@ -471,8 +476,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     unsigned char* slot = smem + g * SLOT;
     unsigned char* a_hi = slot;                              // A tile (hi) | raw skip rows (block 1) | later: Y tile (hi)
     unsigned char* a_lo = a_hi + LT_A_BYTES;                 // A tile (lo) | raw x rows            | later: Y tile (lo)
-    unsigned char* lw_hi = a_lo + LT_A_BYTES;                // [NF][24576]  raw predicted kernels -> hi
-    unsigned char* lw_lo = lw_hi + NF * LT_LW_BYTES;
+    unsigned char* lw = a_lo + LT_A_BYTES;                   // [NF][3 taps][hi 8 KB (raw on arrival) | lo 8 KB]
     unsigned char* small = small0 + g * SMALL;
     uint64_t* bar = bars + 4 * g;
 
@@ -486,9 +490,10 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     }
     {   // per-layer constants: the global order of the conv weights is already the swizzled smem image
         const float4* sh = reinterpret_cast<const float4*>(p.cw_hi); const float4* sl = reinterpret_cast<const float4*>(p.cw_lo);
-        for (int i = tid; i < LT_CW_BYTES / 16; i += 256 * GROUPS) {
-            reinterpret_cast<float4*>(cw_hi)[i] = sh[i];
-            reinterpret_cast<float4*>(cw_lo)[i] = sl[i];
+        for (int i = tid; i < LT_CW_BYTES / 16; i += 256 * GROUPS) {   // i = tap*256 + float4 within the 4 KB tap tile
+            const int k = i >> 8, w = i & 255;
+            reinterpret_cast<float4*>(cw + k * 8192)[w] = sh[i];
+            reinterpret_cast<float4*>(cw + k * 8192 + 4096)[w] = sl[i];
         }
         if (tid < 7 * C) fw_s[tid] = SKIP_FIRST ? p.first_w[tid] : 0.f;
         if (tid < C) { fb_s[tid] = SKIP_FIRST ? p.first_b[tid] : 0.f; cb_s[tid] = p.conv_b[tid]; }
@@ -497,10 +502,11 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // TMEM columns of a group (256 apart): [0,32) conv accumulator, [32 + 64 fi, +64) LVC accumulator of frame fi.  All three
-    // tf32 passes accumulate into the same tile: measured, there is no accumulate-chain penalty (profiles/r01_tcgen05_findings.md).
+    // TMEM columns of a group (256 apart): conv [0,64) = {[0,32): A_hi W_hi + A_lo W_hi, [32,64): A_hi W_lo};
+    // LVC frame fi at [64 + 128 fi, +128) = {[0,64): Y_hi W_hi + Y_lo W_hi, [64,128): Y_hi W_lo}; the epilogues add the halves.
     const uint32_t tmem_base = *tmem_base_s + g * 256;
-    constexpr uint32_t idesc_conv = umma_idesc_tf32(128, 32), idesc_lvc = umma_idesc_tf32(128, 64);
+    constexpr uint32_t idesc_conv = umma_idesc_tf32(128, 32), idesc_conv2 = umma_idesc_tf32(128, 64);
+    constexpr uint32_t idesc_lvc = umma_idesc_tf32(128, 64), idesc_lvc2 = umma_idesc_tf32(128, 128);
 
     // this thread's fixed role in the A transform: channel chunk c4 = gt & 7 -> keep its first-conv taps in registers
     const int c4 = gt & 7;
@@ -516,7 +522,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     // warp-uniform copies (shfl from lane 0) so the issue paths are provably uniform
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
     const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * SLOT);
-    const uint32_t cw_u = smem_u32(cw_hi);
+    const uint32_t cw_u = smem_u32(cw);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
 
     const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt, tstride = gridDim.x * GROUPS;
@@ -546,8 +552,29 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             const int f = t0 / HOP + fi;
             if (f < Tm) {
                 const float* src = kern + ((size_t)b * Tm + f) * KCN;
-                bulk_g2s(lw_hi + fi * LT_LW_BYTES, src, LT_LW_BYTES, &bar[2]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) bulk_g2s(lw + fi * 2 * LT_LW_BYTES + k * 16384, src + k * 2048, 8192, &bar[2]);
                 bulk_g2s(lbias + fi * 64, src + KK * LVC_OUT, 256, &bar[2]);
+            }
+        }
+    };
+
+    // predicted LVC kernels -> tf32 pieces (hi in place, lo in the half-tile next to it; element-wise: the KC GEMM already wrote
+    // them in this tile layout).  With two groups it runs in phase 1 (under the OTHER group's MMAs it would compete with their
+    // operand fetch for smem bandwidth -- measured slower); the single-group variant hides it under its own conv MMAs.
+    auto lw_split_tile = [&](int t0) {
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) {
+            if (t0 / HOP + fi < Tm) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const int e = gt + i * 256;   // float4 index inside the 24 KB of raw kernels: tap = e >> 9
+                    float4* ph = reinterpret_cast<float4*>(lw + fi * 2 * LT_LW_BYTES + (e >> 9) * 16384) + (e & 511);
+                    float4 hi, lo;
+                    split4(*ph, hi, lo);
+                    *ph = hi;
+                    ph[512] = lo;   // + 8 KB
+                }
             }
         }
     };
@@ -574,19 +601,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             if (gt < LT_AU) { const int pos = t0 - 32 + gt; if (pos < 0 || pos >= T) au_s[gt] = 0.f; }
             group_sync(1 + g, 256);
         }
-#pragma unroll
-        for (int fi = 0; fi < NF; ++fi) {   // predicted LVC kernels: hi in place, lo next to it (element-wise: the layout is already the tile's)
-            if (t0 / HOP + fi < Tm) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    float4* ph = reinterpret_cast<float4*>(lw_hi + fi * LT_LW_BYTES) + gt + i * 256;
-                    float4 hi, lo;
-                    split4(*ph, hi, lo);
-                    *ph = hi;
-                    reinterpret_cast<float4*>(lw_lo + fi * LT_LW_BYTES)[gt + i * 256] = lo;
-                }
-            }
-        }
+        if (!MERGE) lw_split_tile(t0);
         LT_STAMP(2);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {   // A rows: the 8 lanes of a row read its raw chunks, then write the swizzled tf32 pieces
@@ -634,11 +649,16 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint64_t dah = umma_desc_sw128(slot_t + sh + j * 32), dal = umma_desc_sw128(slot_t + LT_A_BYTES + sh + j * 32);
-                        const uint64_t dbh = umma_desc_sw128(cw_t + k * C * 128 + j * 32), dbl = umma_desc_sw128(cw_t + LT_CW_BYTES + k * C * 128 + j * 32);
-                        umma_tf32(tmem_u, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
-                        if (three_pass) {
-                            umma_tf32(tmem_u, dah, dbl, idesc_conv, 1u);
-                            umma_tf32(tmem_u, dal, dbh, idesc_conv, 1u);
+                        const uint64_t db = umma_desc_sw128(cw_t + k * 8192 + j * 32);   // rows 0-31 W_hi, rows 32-63 W_lo
+                        if (three_pass && MERGE) {
+                            umma_tf32(tmem_u, dah, db, idesc_conv2, (k | j) ? 1u : 0u);   // cols [0,32) += A_hi W_hi ; [32,64) += A_hi W_lo
+                            umma_tf32(tmem_u, dal, db, idesc_conv, 1u);                   // cols [0,32) += A_lo W_hi
+                        } else if (three_pass) {
+                            umma_tf32(tmem_u, dah, db, idesc_conv, (k | j) ? 1u : 0u);
+                            umma_tf32(tmem_u, dah, db + (4096 >> 4), idesc_conv, 1u);     // W_lo half-tile
+                            umma_tf32(tmem_u, dal, db, idesc_conv, 1u);
+                        } else {
+                            umma_tf32(tmem_u, dah, db, idesc_conv, (k | j) ? 1u : 0u);
                         }
                     }
                 }
@@ -646,6 +666,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             }
             __syncwarp();
         }
+        if (MERGE) lw_split_tile(t0);   // single group: nothing else overlaps the conv MMAs, so hide the split under them
         float halo = 0.f;   // warps 6,7 of the group: conv outputs yr = 128 (warp 6), 129 (warp 7), lane = co
         if (gw >= 6) {
             const int yr = 128 + (gw - 6);
@@ -657,8 +678,8 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
                 for (int c = 0; c < 8; ++c) {
                     const float4 ah4 = *reinterpret_cast<const float4*>(a_hi + swz128(ar, c));
                     const float4 al4 = *reinterpret_cast<const float4*>(a_lo + swz128(ar, c));
-                    const float4 wh4 = *reinterpret_cast<const float4*>(cw_hi + k * C * 128 + swz128(lane, c));
-                    const float4 wl4 = *reinterpret_cast<const float4*>(cw_lo + k * C * 128 + swz128(lane, c));
+                    const float4 wh4 = *reinterpret_cast<const float4*>(cw + k * 8192 + swz128(lane, c));
+                    const float4 wl4 = *reinterpret_cast<const float4*>(cw + k * 8192 + 4096 + swz128(lane, c));
                     acc = fmaf(ah4.x + al4.x, wh4.x + wl4.x, acc); acc = fmaf(ah4.y + al4.y, wh4.y + wl4.y, acc);
                     acc = fmaf(ah4.z + al4.z, wh4.z + wl4.z, acc); acc = fmaf(ah4.w + al4.w, wh4.w + wl4.w, acc);
                 }
@@ -675,6 +696,13 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         if (gw < 4) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16), v);
+            if (three_pass && MERGE) {
+                uint32_t v2[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16) + 32, v2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+            }
             tmem_ld_wait();
             const int yr = gw * 32 + lane, t = t0 - 1 + yr;
             const bool in = (t >= 0 && t < T);
@@ -708,19 +736,23 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             if (elect_one()) {
 #pragma unroll
                 for (int fi = 0; fi < NF; ++fi) {
-                    const uint32_t d = tmem_u + 32 + fi * 64;
-                    const uint32_t lwb = slot_t + 2 * LT_A_BYTES + fi * LT_LW_BYTES;
+                    const uint32_t d = tmem_u + 64 + fi * 128;
+                    const uint32_t lwb = slot_t + 2 * LT_A_BYTES + fi * 2 * LT_LW_BYTES;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const uint64_t dah = umma_desc_sw128(slot_t + k * 128 + j * 32), dal = umma_desc_sw128(slot_t + LT_A_BYTES + k * 128 + j * 32);
-                            const uint64_t dbh = umma_desc_sw128(lwb + k * LVC_OUT * 128 + j * 32);
-                            const uint64_t dbl = umma_desc_sw128(lwb + NF * LT_LW_BYTES + k * LVC_OUT * 128 + j * 32);
-                            umma_tf32(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
-                            if (three_pass) {
-                                umma_tf32(d, dah, dbl, idesc_lvc, 1u);
-                                umma_tf32(d, dal, dbh, idesc_lvc, 1u);
+                            const uint64_t db = umma_desc_sw128(lwb + k * 16384 + j * 32);   // rows 0-63 W_hi, rows 64-127 W_lo
+                            if (three_pass && MERGE) {
+                                umma_tf32(d, dah, db, idesc_lvc2, (k | j) ? 1u : 0u);   // cols [0,64) += Y_hi W_hi ; [64,128) += Y_hi W_lo
+                                umma_tf32(d, dal, db, idesc_lvc, 1u);                   // cols [0,64) += Y_lo W_hi
+                            } else if (three_pass) {
+                                umma_tf32(d, dah, db, idesc_lvc, (k | j) ? 1u : 0u);
+                                umma_tf32(d, dah, db + (8192 >> 4), idesc_lvc, 1u);     // W_lo half-tile
+                                umma_tf32(d, dal, db, idesc_lvc, 1u);
+                            } else {
+                                umma_tf32(d, dah, db, idesc_lvc, (k | j) ? 1u : 0u);
                             }
                         }
                     }
@@ -760,9 +792,20 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             LT_STAMP(9);   // LVC MMAs complete: the slot's operand tiles are free -> fetch the next tile while this one is gated
             if (gw_u == 0 && tile + tstride < total) { if (elect_one()) issue_loads(tile + tstride, (int)(parity ^ 1)); __syncwarp(); }
             uint32_t zs[16], zt[16];
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 32 + fi * 64 + half * 16;
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 64 + fi * 128 + half * 16;
             tmem_ld_32x32b_x16(ta, zs);
             tmem_ld_32x32b_x16(ta + 32, zt);
+            if (three_pass && MERGE) {   // + the (hi, lo) partial sums in the upper 64 columns
+                uint32_t a1[16], a2[16];
+                tmem_ld_32x32b_x16(ta + 64, a1);
+                tmem_ld_32x32b_x16(ta + 96, a2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    zs[i] = __float_as_uint(__uint_as_float(zs[i]) + __uint_as_float(a1[i]));
+                    zt[i] = __float_as_uint(__uint_as_float(zt[i]) + __uint_as_float(a2[i]));
+                }
+            }
             tmem_ld_wait();
             if (t < T) {
                 const float* lb = lbias + fi * 64 + half * 16;
