@@ -412,6 +412,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+template <int N> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]);
+template <> __device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld_32x32b_x8(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x32b_x16(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -449,11 +457,15 @@ struct LvcTcParams {
     const float* first_w; const float* first_b;  // [7][32], [32]   (SKIP_FIRST)
 };
 
-template <int HOP, bool SKIP_FIRST, int GROUPS>
-__global__ void __launch_bounds__(256 * GROUPS, 1)
+// GW = warps per group (8 or 16): the single-group variant runs 16 so that its transform / epilogue phases take half as long.
+template <int HOP, bool SKIP_FIRST, int GROUPS, int GW>
+__global__ void __launch_bounds__(32 * GW * GROUPS, 1)
 k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
                float* __restrict__ x_out, int B, int T, int Tm, int dil, int three_pass) {
     constexpr int NF = lt_nf<HOP>();
+    constexpr int GT = 32 * GW;              // threads per group
+    constexpr int NPART = GW / 4;            // warps per TMEM lane quarter
+    constexpr int CH = 32 / NPART;           // gate channels per warp in the LVC epilogue (16 or 8)
     // Merge the (hi,hi) and (hi,lo) passes into one MMA of twice the N (W_hi | W_lo as one operand): 88 vs 120 cycles per conv
     // k-step, 112 vs 144 per LVC k-step (profiles/r01_tcgen05_findings.md) at the price of extra TMEM reads in the epilogues.
     // Pays off for the single-group variant (nothing overlaps its MMAs); with two groups the MMAs are already hidden.
@@ -472,7 +484,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     uint64_t* bars = (uint64_t*)(cb_s + C);                  // [GROUPS][4]: conv MMAs, LVC MMAs, loads, (pad)
     uint32_t* tmem_base_s = (uint32_t*)(bars + 8);
 
-    const int tid = threadIdx.x, g = tid >> 8, gt = tid & 255, gw = gt >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, g = tid / GT, gt = tid % GT, gw = gt >> 5, lane = tid & 31;
     unsigned char* slot = smem + g * SLOT;
     unsigned char* a_hi = slot;                              // A tile (hi) | raw skip rows (block 1) | later: Y tile (hi)
     unsigned char* a_lo = a_hi + LT_A_BYTES;                 // A tile (lo) | raw x rows            | later: Y tile (lo)
@@ -490,7 +502,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     }
     {   // per-layer constants: the global order of the conv weights is already the swizzled smem image
         const float4* sh = reinterpret_cast<const float4*>(p.cw_hi); const float4* sl = reinterpret_cast<const float4*>(p.cw_lo);
-        for (int i = tid; i < LT_CW_BYTES / 16; i += 256 * GROUPS) {   // i = tap*256 + float4 within the 4 KB tap tile
+        for (int i = tid; i < LT_CW_BYTES / 16; i += GT * GROUPS) {   // i = tap*256 + float4 within the 4 KB tap tile
             const int k = i >> 8, w = i & 255;
             reinterpret_cast<float4*>(cw + k * 8192)[w] = sh[i];
             reinterpret_cast<float4*>(cw + k * 8192 + 4096)[w] = sl[i];
@@ -567,8 +579,8 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         for (int fi = 0; fi < NF; ++fi) {
             if (t0 / HOP + fi < Tm) {
 #pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    const int e = gt + i * 256;   // float4 index inside the 24 KB of raw kernels: tap = e >> 9
+                for (int i = 0; i < 1536 / GT; ++i) {
+                    const int e = gt + i * GT;   // float4 index inside the 24 KB of raw kernels: tap = e >> 9
                     float4* ph = reinterpret_cast<float4*>(lw + fi * 2 * LT_LW_BYTES + (e >> 9) * 16384) + (e & 511);
                     float4 hi, lo;
                     split4(*ph, hi, lo);
@@ -599,13 +611,13 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         LT_STAMP(1);
         if (SKIP_FIRST) {   // audio positions outside [0,T) are zero (the first conv zero-pads)
             if (gt < LT_AU) { const int pos = t0 - 32 + gt; if (pos < 0 || pos >= T) au_s[gt] = 0.f; }
-            group_sync(1 + g, 256);
+            group_sync(1 + g, GT);
         }
         if (!MERGE) lw_split_tile(t0);
         LT_STAMP(2);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {   // A rows: the 8 lanes of a row read its raw chunks, then write the swizzled tf32 pieces
-            const int ar = r_lo + (gt >> 3) + i * 32, t = t0 - 28 + ar;
+        for (int i = 0; i < 1536 / GT; ++i) {   // A rows: the 8 lanes of a row read its raw chunks, then write the swizzled tf32 pieces
+            const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
             const bool active = ar < r_hi;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (active && t >= 0 && t < T) {
@@ -635,7 +647,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         }
         LT_STAMP(3);   // A built
         fence_async_smem();
-        group_sync(1 + g, 256);
+        group_sync(1 + g, GT);
         LT_STAMP(4);
         // ---------------- phase 2: dilated conv on tensor cores (+ 2 halo rows on FFMA meanwhile) ----------------
         if (gw_u == 0) {
@@ -668,8 +680,8 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         }
         if (MERGE) lw_split_tile(t0);   // single group: nothing else overlaps the conv MMAs, so hide the split under them
         float halo = 0.f;   // warps 6,7 of the group: conv outputs yr = 128 (warp 6), 129 (warp 7), lane = co
-        if (gw >= 6) {
-            const int yr = 128 + (gw - 6);
+        if (gw >= GW - 2) {
+            const int yr = 128 + (gw - (GW - 2));
             float acc = cb_s[lane];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -692,41 +704,45 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         mbar_wait(&bar[0], parity);
         tc_fence_after();
         LT_STAMP(6);   // conv MMAs complete
-        group_sync(1 + g, 256);   // Y aliases A: the halo warps must have finished READING A before anyone writes Y
-        if (gw < 4) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16), v);
+        group_sync(1 + g, GT);   // Y aliases A: the halo warps must have finished READING A before anyone writes Y
+        if (gw < 4 * (GW / 8)) {   // GW/8 warps per lane quarter, each taking 32/(GW/8) of the 32 conv channels
+            constexpr int P3N = GW / 8, P3C = 32 / P3N;   // columns per warp: 32 or 16
+            const int q3 = gw & 3, part3 = gw >> 2;
+            uint32_t v[P3C];
+            const uint32_t ta3 = tmem_base + ((uint32_t)(q3 * 32) << 16) + part3 * P3C;
+            tmem_ld_cols<P3C>(ta3, v);
             if (three_pass && MERGE) {
-                uint32_t v2[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(gw * 32) << 16) + 32, v2);
+                uint32_t v2[P3C];
+                tmem_ld_cols<P3C>(ta3 + 32, v2);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                for (int i = 0; i < P3C; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
             }
             tmem_ld_wait();
-            const int yr = gw * 32 + lane, t = t0 - 1 + yr;
+            const int yr = q3 * 32 + lane, t = t0 - 1 + yr;
             const bool in = (t >= 0 && t < T);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int cc = 0; cc < P3C / 4; ++cc) {
+                const int c = part3 * (P3C / 4) + cc;
                 float4 y;
-                y.x = in ? lrelu(__uint_as_float(v[c * 4 + 0]) + cb_s[c * 4 + 0], 0.2f) : 0.f;
-                y.y = in ? lrelu(__uint_as_float(v[c * 4 + 1]) + cb_s[c * 4 + 1], 0.2f) : 0.f;
-                y.z = in ? lrelu(__uint_as_float(v[c * 4 + 2]) + cb_s[c * 4 + 2], 0.2f) : 0.f;
-                y.w = in ? lrelu(__uint_as_float(v[c * 4 + 3]) + cb_s[c * 4 + 3], 0.2f) : 0.f;
+                y.x = in ? lrelu(__uint_as_float(v[cc * 4 + 0]) + cb_s[c * 4 + 0], 0.2f) : 0.f;
+                y.y = in ? lrelu(__uint_as_float(v[cc * 4 + 1]) + cb_s[c * 4 + 1], 0.2f) : 0.f;
+                y.z = in ? lrelu(__uint_as_float(v[cc * 4 + 2]) + cb_s[c * 4 + 2], 0.2f) : 0.f;
+                y.w = in ? lrelu(__uint_as_float(v[cc * 4 + 3]) + cb_s[c * 4 + 3], 0.2f) : 0.f;
                 float4 hi, lo;
                 split4(y, hi, lo);
                 *reinterpret_cast<float4*>(a_hi + swz128(yr, c)) = hi;
                 *reinterpret_cast<float4*>(a_lo + swz128(yr, c)) = lo;
             }
-        } else if (gw >= 6) {
-            const int yr = 128 + (gw - 6);
+        } else if (gw >= GW - 2) {
+            const int yr = 128 + (gw - (GW - 2));
             const float hi = split_hi(halo), lo = halo - hi;
             *reinterpret_cast<float*>(a_hi + swz128(yr, lane >> 2) + (lane & 3) * 4) = hi;
             *reinterpret_cast<float*>(a_lo + swz128(yr, lane >> 2) + (lane & 3) * 4) = lo;
         }
         fence_async_smem();
         tc_fence_before();
-        group_sync(1 + g, 256);
+        group_sync(1 + g, GT);
         LT_STAMP(7);   // Y written
         // ---------------- phase 4: location-variable conv on tensor cores ----------------
         if (gw_u == 0) {
@@ -763,16 +779,16 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
         }
         // ---------------- phase 5: gate + residual -> global ----------------
         {
-            const int q = gw & 3, half = gw >> 2;              // lane quarter / which 16 of the 32 gate channels
+            const int q = gw & 3, part = gw >> 2;              // lane quarter / which CH of the 32 gate channels
             const int r = q * 32 + lane, t = t0 + r;
             const int fi = (HOP >= LT_TT) ? 0 : r / HOP;       // warp-uniform (HOP is a multiple of 32)
-            const size_t row = ((size_t)b * T + (t < T ? t : 0)) * C + half * 16;
-            float4 xs[4];                                      // residual base, fetched while the MMAs run
+            const size_t row = ((size_t)b * T + (t < T ? t : 0)) * C + part * CH;
+            float4 xs[CH / 4];                                 // residual base, fetched while the MMAs run
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < CH / 4; ++c) {
                 xs[c] = *reinterpret_cast<const float4*>(x_in + row + c * 4);
                 if (SKIP_FIRST) {
-                    const int o = half * 16 + c * 4;
+                    const int o = part * CH + c * 4;
                     float4 sk = *reinterpret_cast<const float4*>(fb_s + o);
 #pragma unroll
                     for (int k = 0; k < 7; ++k) {
@@ -791,26 +807,26 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             tc_fence_after();
             LT_STAMP(9);   // LVC MMAs complete: the slot's operand tiles are free -> fetch the next tile while this one is gated
             if (gw_u == 0 && tile + tstride < total) { if (elect_one()) issue_loads(tile + tstride, (int)(parity ^ 1)); __syncwarp(); }
-            uint32_t zs[16], zt[16];
-            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 64 + fi * 128 + half * 16;
-            tmem_ld_32x32b_x16(ta, zs);
-            tmem_ld_32x32b_x16(ta + 32, zt);
+            uint32_t zs[CH], zt[CH];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 64 + fi * 128 + part * CH;
+            tmem_ld_cols<CH>(ta, zs);
+            tmem_ld_cols<CH>(ta + 32, zt);
             if (three_pass && MERGE) {   // + the (hi, lo) partial sums in the upper 64 columns
-                uint32_t a1[16], a2[16];
-                tmem_ld_32x32b_x16(ta + 64, a1);
-                tmem_ld_32x32b_x16(ta + 96, a2);
+                uint32_t a1[CH], a2[CH];
+                tmem_ld_cols<CH>(ta + 64, a1);
+                tmem_ld_cols<CH>(ta + 96, a2);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < CH; ++i) {
                     zs[i] = __float_as_uint(__uint_as_float(zs[i]) + __uint_as_float(a1[i]));
                     zt[i] = __float_as_uint(__uint_as_float(zt[i]) + __uint_as_float(a2[i]));
                 }
             }
             tmem_ld_wait();
             if (t < T) {
-                const float* lb = lbias + fi * 64 + half * 16;
+                const float* lb = lbias + fi * 64 + part * CH;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < CH / 4; ++c) {
                     float4 o4;
                     o4.x = xs[c].x + fast_sigmoid(__uint_as_float(zs[c * 4 + 0]) + lb[c * 4 + 0]) * fast_tanh(__uint_as_float(zt[c * 4 + 0]) + lb[32 + c * 4 + 0]);
                     o4.y = xs[c].y + fast_sigmoid(__uint_as_float(zs[c * 4 + 1]) + lb[c * 4 + 1]) * fast_tanh(__uint_as_float(zt[c * 4 + 1]) + lb[32 + c * 4 + 1]);
@@ -821,7 +837,7 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
             }
         }
         tc_fence_before();
-        group_sync(1 + g, 256);   // the group's TMEM columns are free for its next tile
+        group_sync(1 + g, GT);   // the group's TMEM columns are free for its next tile
     }
     tc_fence_before();
     __syncthreads();
@@ -849,10 +865,10 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     const int tp = mode == 1 ? 1 : 0;
     if (blk == 1) {
         const int grid = total < s->sm_count ? total : s->sm_count;
-        k_lvc_layer_tc<64, false, 1><<<grid, 256, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp);
+        k_lvc_layer_tc<64, false, 1, 16><<<grid, 512, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp);
     } else {
         const int pairs = (total + 1) / 2, grid = pairs < s->sm_count ? pairs : s->sm_count;
-        k_lvc_layer_tc<256, true, 2><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp);
+        k_lvc_layer_tc<256, true, 2, 8><<<grid, 512, lt_smem_bytes<256, 2>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_tc failed: ") + cudaGetErrorString(e); return -3; }
@@ -862,8 +878,8 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
 }
 
 static inline cudaError_t tc_set_lvc_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
+    cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
     return e;
 }
 
