@@ -544,6 +544,20 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
     return FD_OK;
 }
 
+extern "C" int fd_wav_int16(fd_handle* h, const float* x_dev, int16_t* out_dev, int B, int L, void* workspace_dev, void* stream) {
+    if (!h || !x_dev || !out_dev || !workspace_dev || B < 1 || L < 1) return fail(h, FD_ERR_INVALID, "fd_wav_int16: bad argument");
+    FD_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* amax = (unsigned int*)workspace_dev;   // first B words of the workspace (free between sampling calls)
+    FD_CUDA(h, cudaMemsetAsync(amax, 0, (size_t)B * 4, st));
+    int nb = (L + 255) / 256; if (nb > 1024) nb = 1024;
+    FD_LAUNCH(k_absmax, dim3(nb, B), dim3(256), 0, st, x_dev, amax, L);
+    FD_CHECK_LAUNCH(h, "k_absmax");
+    FD_LAUNCH(k_wav_int16, dim3((L + 255) / 256, B), dim3(256), 0, st, x_dev, (const unsigned int*)amax, out_dev, L);
+    FD_CHECK_LAUNCH(h, "k_wav_int16");
+    return FD_OK;
+}
+
 extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, size_t* count, int B, int Tm,
                              void* workspace_dev, void* stream) {
     if (!h || !name || !count || !workspace_dev) return fail(h, FD_ERR_INVALID, "fd_debug_read: null argument");

@@ -702,6 +702,35 @@ __global__ void __launch_bounds__(256) k_final(FinalParams p, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// The step after the path: wav / |wav|.max() per utterance (task/FastDiff.py:110) then the int16 encode of
+// utils/audio.py:11-16 (wav *= 32767; astype(int16) = truncation toward zero), so only 2 bytes/sample leave the GPU.
+// Same fp32 operation sequence as the reference (divide, then multiply, both round-to-nearest) -> bit-identical int16.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, unsigned int* __restrict__ amax_bits, int L) {
+    __shared__ float red[256];
+    const int b = blockIdx.y;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < (size_t)L; i += (size_t)gridDim.x * 256) m = fmaxf(m, fabsf(x[(size_t)b * L + i]));
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + s2]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicMax(&amax_bits[b], __float_as_uint(red[0]));   // non-negative floats order like their bit patterns
+}
+
+__global__ void __launch_bounds__(256) k_wav_int16(const float* __restrict__ x, const unsigned int* __restrict__ amax_bits,
+                                                   int16_t* __restrict__ out, int L) {
+    const int b = blockIdx.y;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (size_t)L) return;
+    const float amax = __uint_as_float(amax_bits[b]);
+    const float v = __fmul_rn(__fdiv_rn(x[(size_t)b * L + i], amax), 32767.0f);
+    out[(size_t)b * L + i] = (int16_t)(int)v;   // float -> int truncates toward zero, like numpy's astype
+}
+
+// ------------------------------------------------------------------------------------------------
 // Debug/inspection gathers used by fd_debug_read (tests only): channels-last -> the reference's layouts.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cl_to_ncl(const float* __restrict__ in, float* __restrict__ out, int B, int T,

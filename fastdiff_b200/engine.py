@@ -168,6 +168,15 @@ class Engine:
         self._check(rc, "fd_sample")
         return x
 
+    def wav_int16(self, x: torch.Tensor) -> torch.Tensor:
+        """(B,1,L) fp32 waveform -> (B,L) int16: wav/|wav|.max() then *32767 and truncate (task/FastDiff.py:110, utils/audio.py:11-16)."""
+        B, L = x.shape[0], x.shape[-1]
+        x = self._dev(x.reshape(B, 1, L))
+        out = torch.empty((B, L), dtype=torch.int16, device=self.device)
+        ws = self.workspace(B, max(1, L // 256))
+        self._check(self.lib.fd_wav_int16(self.h, x.data_ptr(), out.data_ptr(), B, L, ws.data_ptr(), self._stream()), "fd_wav_int16")
+        return out
+
     def debug_read(self, name: str, B: int, Tm: int) -> torch.Tensor:
         ws = self.workspace(B, Tm)
         n = C.c_size_t()

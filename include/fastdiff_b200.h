@@ -118,6 +118,12 @@ int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const fd_step* s
               const float* noise_dev, int n_noise, uint64_t seed, int fill_xT, int ddim,
               float* seq_dev, int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* The step after the path: per-utterance peak normalisation and int16 encode on the device --
+ * wav_pred / wav_pred.abs().max() (modules/FastDiff/task/FastDiff.py:110) followed by utils/audio.py:11-16
+ * (wav *= 32767; astype(int16)).  x_dev (B,1,L) fp32 -> out_dev (B,L) int16, bit-identical to the reference's float ops.
+ * Uses the first B words of the workspace as scratch. */
+int fd_wav_int16(fd_handle* h, const float* x_dev, int16_t* out_dev, int B, int L, void* workspace_dev, void* stream);
+
 /* Stage helpers exposed for the parity tests (each is one stage of FastDiff.forward; same
  * conventions).  fd_debug_read copies a named internal tensor of the LAST fd_denoise call out of
  * the workspace, converted to the reference's NCL layout:

@@ -50,6 +50,12 @@ static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; retu
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
+static inline unsigned int atomicMax(unsigned int* a, unsigned int v) {
+    unsigned int old = __atomic_load_n(a, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(a, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+
 // runtime subset
 typedef int cudaError_t;
 typedef void* cudaStream_t;

@@ -203,3 +203,21 @@ def test_errors_are_loud(synth, cuda_lib):
         fb.sampling_given_noise_schedule(net, (1, 1, 1000), dh, torch.FloatTensor(N4), condition=torch.zeros(1, 80, 4).cuda())
     with pytest.raises(AssertionError):  # util.py:185
         fb.sampling_given_noise_schedule(net, (1, 1024), dh, torch.FloatTensor(N4), condition=torch.zeros(1, 80, 4).cuda())
+
+
+@gpu
+def test_wav_int16_encode_on_device_bitwise(synth, cuda_lib):
+    """peak-normalise + int16 encode after the path, bit-identical to the reference's float ops."""
+    import numpy as np
+    sd, _ = synth
+    net = _net(sd)
+    torch.manual_seed(1)
+    x = torch.randn(4, 1, 220416) * 1.7
+    got = net.engine().wav_int16(x.cuda()).cpu().numpy()
+    ref = []
+    for w in x:
+        w = w / w.abs().max()
+        a = w.view(-1).numpy().copy()
+        a *= 32767
+        ref.append(a.astype(np.int16))
+    assert np.array_equal(got, np.stack(ref))

@@ -140,3 +140,25 @@ def test_sampler_api_errors(emu_lib, synth):
                                          condition=torch.zeros(1, 80, 1))
     with pytest.raises(AssertionError, match="not matched"):
         fb.sampling_given_noise_schedule(net, (1, 1, 300), dh, torch.FloatTensor([0.5]), condition=torch.zeros(1, 80, 1))
+
+
+def _ref_int16(x):
+    """wav / |wav|.max() (modules/FastDiff/task/FastDiff.py:110) then utils/audio.py:11-16 (wav *= 32767; astype(int16))."""
+    out = []
+    for w in x:
+        w = w / w.abs().max()
+        a = w.view(-1).cpu().float().numpy().copy()
+        a *= 32767
+        out.append(a.astype(np.int16))
+    return np.stack(out)
+
+
+def test_wav_int16_encode_matches_reference_ops_bitwise(emu_lib, synth):
+    from fastdiff_b200.engine import Engine
+    from fastdiff_b200.weights import pack_state_dict
+    sd, _ = synth
+    eng = Engine(device="cpu", lib_path=emu_lib)
+    eng.load_blob(pack_state_dict(sd))
+    torch.manual_seed(0)
+    x = torch.randn(3, 1, 1300) * 2.5
+    assert np.array_equal(eng.wav_int16(x).numpy(), _ref_int16(x))
