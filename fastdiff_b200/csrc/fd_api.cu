@@ -28,6 +28,7 @@ struct fd_handle {
     int mode = FD_MODE_FP32_SIMT;
     int mode_set_by_user = 0;
     int stop_after = 99;
+    int tc_dblock = 1;           // DBlock 0 on tensor cores in the TC modes (option "tc_dblock")
     int attrs_set = 0;
     uint64_t launches = 0;
     std::string err;
@@ -258,6 +259,7 @@ extern "C" int fd_get_mode(fd_handle* h) { return h ? h->mode : FD_ERR_INVALID; 
 extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!h || !key) return FD_ERR_INVALID;
     if (!strcmp(key, "stop_after")) { h->stop_after = (int)value; return FD_OK; }
+    if (!strcmp(key, "tc_dblock")) { h->tc_dblock = (int)value; return FD_OK; }
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
 #endif
@@ -384,6 +386,15 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             p.conv_w = sec(h, FD_S_DB0_CONV_W + n * FD_DB_STRIDE); p.conv_b = sec(h, FD_S_DB0_CONV_B + n * FD_DB_STRIDE);
             const dim3 grid((tout[n] + DB_TO - 1) / DB_TO, B);
             ScopedTimer tm(h, KC_DBLOCK, st);
+            bool done_tc = false;
+#ifndef FD_EMU
+            if (n == 0 && h->mode != FD_MODE_FP32_SIMT && h->tc_dblock) {
+                int rc = tc_dblock0(h->tc_state, h->mode, x_dev, d0, B, L, st, h->err, &h->launches);
+                if (rc) return rc;
+                done_tc = true;
+            }
+#endif
+            if (done_tc) continue;
             if (n == 0) { auto k = k_dblock<4, true>;  FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<4>(), st, p, ins[n], outs[n], tin[n], tout[n]); }
             else        { auto k = k_dblock<8, false>; FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<8>(), st, p, ins[n], outs[n], tin[n], tout[n]); }
             FD_CHECK_LAUNCH(h, "k_dblock");

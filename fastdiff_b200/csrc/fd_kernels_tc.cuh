@@ -847,6 +847,229 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K3+K4  first_audio_conv + DiffusionDBlock 0 on tensor cores (FastDiff_model.py:89, modules.py:127-138):
+//   xs[o] = first_conv(audio)[4 o]  (evaluated only at the kept positions);
+//   out = conv_d4(lrelu(conv_d2(lrelu(conv_d1(lrelu(xs)))))) + W1x1 xs + b
+// One tile = 128 rows (positions o0-7 .. o0+120), 114 valid outputs (halo 7 recomputed).  Same building blocks as the LVC
+// kernel: SWIZZLE_128B K-major tiles, a dilated tap = start address + shift*128 B, 3xTF32 with the (hi,hi)/(hi,lo) passes
+// merged into one N=64 MMA (W_hi | W_lo as one operand), the 1x1 residual accumulated into the last conv's TMEM tile, the
+// audio window of the next tile fetched by cp.async.bulk one tile ahead.  One persistent CTA per SM, 16 warps.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DT_VALID = 114, DT_PAD = 8;
+constexpr int DT_ATILE = (128 + 2 * DT_PAD) * 128;     // 18432 B per piece (hi or lo)
+constexpr int DT_AU = 520;                             // audio window: positions 4*o0 - 32 .. + 519
+constexpr int DT_SMEM_BYTES = 4 * DT_ATILE + 2 * 16384 + 3 * 24576 + 8192 + 2 * (DT_AU * 4 + 32) + (7 * C + C + 4 * C) * 4 + 64 + 1024;
+
+struct DbTcParams {
+    const float* cw_hi; const float* cw_lo;     // [3][3][32][8][4]
+    const float* rw_hi; const float* rw_lo;     // [32][8][4]
+    const float* conv_b; const float* res_b;    // [3][32], [32]
+    const float* first_w; const float* first_b; // [7][32], [32]
+};
+
+__global__ void __launch_bounds__(512, 1)
+k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ out, int B, int L, int To, int three_pass) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* a_tile0 = smem;                                          // two ping-pong tiles, each hi | lo, rows 0..143 (row r at r + 8)
+    unsigned char* x_hi = smem + 4 * DT_ATILE;                             // xs (pre-activation) for the 1x1 residual, 128 rows
+    unsigned char* x_lo = x_hi + 16384;
+    unsigned char* wc = x_lo + 16384;                                      // [3 layers][3 taps][hi 4 KB | lo 4 KB]
+    unsigned char* wr = wc + 3 * 24576;                                    // residual: hi 4 KB | lo 4 KB
+    float* au0 = (float*)(wr + 8192);                                      // [2][DT_AU + 8]
+    float* fw_s = au0 + 2 * (DT_AU + 8);
+    float* fb_s = fw_s + 7 * C;
+    float* cb_s = fb_s + C;                                                // [3][32] conv biases, then [32] residual bias
+    uint64_t* bar = (uint64_t*)(cb_s + 4 * C);                             // [0] MMAs, [1] audio loads
+    uint32_t* tmem_base_s = (uint32_t*)(bar + 2);
+
+    const int tid = threadIdx.x, gw = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        const float4* sh = reinterpret_cast<const float4*>(p.cw_hi); const float4* sl = reinterpret_cast<const float4*>(p.cw_lo);
+        for (int i = tid; i < 3 * 3 * 256; i += 512) {   // i = (layer*3 + tap)*256 + float4 within the 4 KB tap tile
+            const int lt = i >> 8, w = i & 255;
+            reinterpret_cast<float4*>(wc + lt * 8192)[w] = sh[i];
+            reinterpret_cast<float4*>(wc + lt * 8192 + 4096)[w] = sl[i];
+        }
+        if (tid < 256) {
+            reinterpret_cast<float4*>(wr)[tid] = reinterpret_cast<const float4*>(p.rw_hi)[tid];
+            reinterpret_cast<float4*>(wr + 4096)[tid] = reinterpret_cast<const float4*>(p.rw_lo)[tid];
+        }
+        if (tid < 7 * C) fw_s[tid] = p.first_w[tid];
+        if (tid < C) { fb_s[tid] = p.first_b[tid]; cb_s[3 * C + tid] = p.res_b[tid]; }
+        if (tid < 3 * C) cb_s[tid] = p.conv_b[tid];
+        for (int i = tid; i < 4 * DT_ATILE / 16; i += 512) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // pad rows stay 0
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int gw_u = __shfl_sync(0xffffffffu, gw, 0);
+    const uint32_t smem_u = smem_u32(smem);
+    constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32), idesc64 = umma_idesc_tf32(128, 64);
+
+    const int c4 = tid & 7;
+    float fwr[7][4], fbr[4];
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) fwr[k][q] = fw_s[k * C + c4 * 4 + q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) fbr[q] = fb_s[c4 * 4 + q];
+
+    const int ntt = (To + DT_VALID - 1) / DT_VALID, total = B * ntt;
+    auto issue_audio = [&](int tile, int buf) {   // au[i] <-> audio position 4*o0 - 32 + i
+        const int b = tile / ntt, o0 = (tile % ntt) * DT_VALID;
+        const long p0 = 4L * o0 - 32;
+        const int i0 = (int)(p0 < 0 ? -p0 : 0), i1 = (int)((L - p0) < DT_AU ? (L - p0) : DT_AU);
+        const uint32_t bytes = i1 > i0 ? (uint32_t)(i1 - i0) * 4u : 0u;
+        mbar_expect_tx(&bar[1], bytes);
+        if (bytes) bulk_g2s(au0 + buf * (DT_AU + 8) + i0, audio + (size_t)b * L + (p0 + i0), bytes, &bar[1]);
+    };
+    int tile = blockIdx.x;
+    if (tile < total && gw_u == 0) { if (elect_one()) issue_audio(tile, 0); __syncwarp(); }
+    uint32_t par_ld = 0, par_mma = 0;
+    for (; tile < total; tile += gridDim.x, par_ld ^= 1) {
+        const int b = tile / ntt, o0 = (tile % ntt) * DT_VALID;
+        float* au = au0 + par_ld * (DT_AU + 8);
+        mbar_wait(&bar[1], par_ld);
+        {   // audio positions outside [0, L) are zero (first_audio_conv zero-pads)
+            const long p0 = 4L * o0 - 32;
+            for (int i = tid; i < DT_AU; i += 512) if (p0 + i < 0 || p0 + i >= L) au[i] = 0.f;
+        }
+        __syncthreads();
+        if (gw_u == 0 && tile + (int)gridDim.x < total) { if (elect_one()) issue_audio(tile + gridDim.x, (int)(par_ld ^ 1)); __syncwarp(); }
+        // ---- xs = first_conv(audio) at the kept positions; A0 = lrelu(xs), X = xs (tf32 pieces) ----
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int row = (tid >> 3) + i * 64, o = o0 - 7 + row;
+            float4 xs = make_float4(0.f, 0.f, 0.f, 0.f), a = xs;
+            if (o >= 0 && o < To) {
+                xs = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const float s1 = au[4 * row + k + 1];   // audio position 4 o + k - 3
+                    xs.x = fmaf(fwr[k][0], s1, xs.x); xs.y = fmaf(fwr[k][1], s1, xs.y);
+                    xs.z = fmaf(fwr[k][2], s1, xs.z); xs.w = fmaf(fwr[k][3], s1, xs.w);
+                }
+                a = make_float4(lrelu(xs.x, 0.2f), lrelu(xs.y, 0.2f), lrelu(xs.z, 0.2f), lrelu(xs.w, 0.2f));
+            }
+            float4 hi, lo;
+            split4(a, hi, lo);
+            *reinterpret_cast<float4*>(a_tile0 + swz128(row + DT_PAD, c4)) = hi;
+            *reinterpret_cast<float4*>(a_tile0 + DT_ATILE + swz128(row + DT_PAD, c4)) = lo;
+            split4(xs, hi, lo);
+            *reinterpret_cast<float4*>(x_hi + swz128(row, c4)) = hi;
+            *reinterpret_cast<float4*>(x_lo + swz128(row, c4)) = lo;
+        }
+        fence_async_smem();
+        __syncthreads();
+        // ---- three dilated convs, each: MMAs -> epilogue -> next tile ----
+#pragma unroll 1
+        for (int layer = 0; layer < 3; ++layer, par_mma ^= 1) {
+            const int src = layer & 1, dil = 1 << layer;
+            if (gw_u == 0) {
+                tc_fence_after();
+                uint32_t at = smem_u + (uint32_t)(src * 2 * DT_ATILE), wt = smem_u + 4 * DT_ATILE + 2 * 16384 + (uint32_t)(layer * 24576);
+                asm volatile("" : "+r"(at), "+r"(wt));
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t sh = (uint32_t)(DT_PAD + (k - 1) * dil) * 128u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint64_t dah = umma_desc_sw128(at + sh + j * 32), dal = umma_desc_sw128(at + DT_ATILE + sh + j * 32);
+                            const uint64_t db = umma_desc_sw128(wt + k * 8192 + j * 32);   // rows 0-31 W_hi, 32-63 W_lo
+                            if (three_pass) {
+                                umma_tf32(tmem_u, dah, db, idesc64, (k | j) ? 1u : 0u);
+                                umma_tf32(tmem_u, dal, db, idesc32, 1u);
+                            } else {
+                                umma_tf32(tmem_u, dah, db, idesc32, (k | j) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    if (layer == 2) {   // + W1x1 xs accumulated into the same tile
+                        const uint32_t xt = smem_u + 4 * DT_ATILE, rt = smem_u + 4 * DT_ATILE + 2 * 16384 + 3 * 24576;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint64_t dxh = umma_desc_sw128(xt + j * 32), dxl = umma_desc_sw128(xt + 16384 + j * 32);
+                            const uint64_t dr = umma_desc_sw128(rt + j * 32);
+                            if (three_pass) {
+                                umma_tf32(tmem_u, dxh, dr, idesc64, 1u);
+                                umma_tf32(tmem_u, dxl, dr, idesc32, 1u);
+                            } else {
+                                umma_tf32(tmem_u, dxh, dr, idesc32, 1u);
+                            }
+                        }
+                    }
+                    tc_commit(&bar[0]);
+                }
+                __syncwarp();
+            }
+            mbar_wait(&bar[0], par_mma);
+            tc_fence_after();
+            {   // epilogue: 4 warps per lane quarter, 8 channels each
+                const int q = gw & 3, part = gw >> 2, row = q * 32 + lane, o = o0 - 7 + row;
+                uint32_t v[8];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + part * 8;
+                tmem_ld_cols<8>(ta, v);
+                if (three_pass) {
+                    uint32_t v2[8];
+                    tmem_ld_cols<8>(ta + 32, v2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                }
+                tmem_ld_wait();
+                const float* bias = cb_s + layer * C + part * 8;
+                if (layer < 2) {
+                    const bool in = (o >= 0 && o < To);
+                    unsigned char* dst = a_tile0 + (src ^ 1) * 2 * DT_ATILE;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        float4 y;
+                        y.x = in ? lrelu(__uint_as_float(v[cc * 4 + 0]) + bias[cc * 4 + 0], 0.2f) : 0.f;
+                        y.y = in ? lrelu(__uint_as_float(v[cc * 4 + 1]) + bias[cc * 4 + 1], 0.2f) : 0.f;
+                        y.z = in ? lrelu(__uint_as_float(v[cc * 4 + 2]) + bias[cc * 4 + 2], 0.2f) : 0.f;
+                        y.w = in ? lrelu(__uint_as_float(v[cc * 4 + 3]) + bias[cc * 4 + 3], 0.2f) : 0.f;
+                        float4 hi, lo;
+                        split4(y, hi, lo);
+                        *reinterpret_cast<float4*>(dst + swz128(row + DT_PAD, part * 2 + cc)) = hi;
+                        *reinterpret_cast<float4*>(dst + DT_ATILE + swz128(row + DT_PAD, part * 2 + cc)) = lo;
+                    }
+                } else if (row >= 7 && row < 7 + DT_VALID && o < To) {
+                    const float* rb = cb_s + 3 * C + part * 8;
+                    float4 o0v, o1v;
+                    o0v.x = __uint_as_float(v[0]) + bias[0] + rb[0]; o0v.y = __uint_as_float(v[1]) + bias[1] + rb[1];
+                    o0v.z = __uint_as_float(v[2]) + bias[2] + rb[2]; o0v.w = __uint_as_float(v[3]) + bias[3] + rb[3];
+                    o1v.x = __uint_as_float(v[4]) + bias[4] + rb[4]; o1v.y = __uint_as_float(v[5]) + bias[5] + rb[5];
+                    o1v.z = __uint_as_float(v[6]) + bias[6] + rb[6]; o1v.w = __uint_as_float(v[7]) + bias[7] + rb[7];
+                    float* dstg = out + ((size_t)b * To + o) * C + part * 8;
+                    *reinterpret_cast<float4*>(dstg) = o0v;
+                    *reinterpret_cast<float4*>(dstg + 4) = o1v;
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(64u) : "memory");
+    }
+}
+
 // x_in/x_out: (B,T,32); skip: (B,T,32) buffer or (block 2) the audio (B,T); kern: this layer's slice of the predicted kernels.
 static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const float* x_in, const float* skip, const float* kern,
                                float* x_out, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches,
@@ -877,7 +1100,28 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     return 0;
 }
 
+// audio (B,L) -> d0 (B, L/4, 32)
+static inline int tc_dblock0(void* state, int mode, const float* audio, float* d0, int B, int L, cudaStream_t st, std::string& err,
+                             uint64_t* launches) {
+    TcState* s = (TcState*)state;
+    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    DbTcParams p;
+    p.cw_hi = s->blob + s->sec_off[FD_S_DB0_CONVT_HI]; p.cw_lo = s->blob + s->sec_off[FD_S_DB0_CONVT_LO];
+    p.rw_hi = s->blob + s->sec_off[FD_S_DB0_REST_HI];  p.rw_lo = s->blob + s->sec_off[FD_S_DB0_REST_LO];
+    p.conv_b = s->blob + s->sec_off[FD_S_DB0_CONV_B];  p.res_b = s->blob + s->sec_off[FD_S_DB0_RES_B];
+    p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];    p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
+    const int To = L / 4, total = B * ((To + DT_VALID - 1) / DT_VALID);
+    const int grid = total < s->sm_count ? total : s->sm_count;
+    k_dblock0_tc<<<grid, 512, DT_SMEM_BYTES, st>>>(p, audio, d0, B, L, To, mode == 1 ? 1 : 0);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_dblock0_tc failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    return 0;
+}
+
 static inline cudaError_t tc_set_lvc_attrs() {
+    cudaError_t e0 = cudaFuncSetAttribute(k_dblock0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
+    if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
     return e;

@@ -148,6 +148,14 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         hi, lo = tf32_split(cw.numpy())
         S[f"LB{n}_CONVT_HI"] = torch.from_numpy(hi)
         S[f"LB{n}_CONVT_LO"] = torch.from_numpy(lo)
+    # DBlock 0 on tensor cores: conv weights [l][k][co][chunk ^ (co&7)][4], residual 1x1 [co][chunk ^ (co&7)][4]
+    dw = torch.stack([W[f"downsample.0.conv.{i}.weight"] for i in range(3)])      # [l][co][ci][k]
+    dw = dw.reshape(3, C, 8, 4, 3).permute(0, 4, 1, 2, 3)[:, :, _SWZ_O[:C], _SWZ_SRC[:C], :].contiguous()
+    hi, lo = tf32_split(dw.numpy())
+    S["DB0_CONVT_HI"], S["DB0_CONVT_LO"] = torch.from_numpy(hi), torch.from_numpy(lo)
+    rw = W["downsample.0.residual_dense.weight"][:, :, 0].reshape(C, 8, 4)[_SWZ_O[:C], _SWZ_SRC[:C], :].contiguous()
+    hi, lo = tf32_split(rw.numpy())
+    S["DB0_REST_HI"], S["DB0_REST_LO"] = torch.from_numpy(hi), torch.from_numpy(lo)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}
 

@@ -41,3 +41,15 @@ for (B,Tm) in ((1,5),(2,33)):
             d = (got-inter[f'lvc{n}']).abs()
             print(f'B={B} Tm={Tm} {mode:10s} lvc{n} max|d| {d.max().item():.3e} mean|d| {d.mean().item():.3e} (rms {inter[f"lvc{n}"].pow(2).mean().sqrt():.3f})', flush=True)
         eng.set_option('stop_after', 99)
+
+print('--- DBlock 0 (tensor cores) ---', flush=True)
+for (B,Tm) in ((1,5),(2,33),(3,300)):
+    x, mel = make_inputs(B,Tm,3); t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B,1)
+    eps_o, inter = O.denoise(W, x, mel, t, return_intermediates=True)
+    for mode in ('fp32_simt','tc_3xtf32','tc_tf32'):
+        net.mode = mode; eng = net.engine(); eng.set_option('stop_after', 2)
+        net((x.cuda(), mel.cuda(), t.cuda()))
+        for n,T in enumerate((Tm*64, Tm*8, Tm)):
+            d = (eng.debug_read(f'down{n}',B,Tm).cpu().reshape(B,32,T) - inter[f'down{n}']).abs()
+            print(f'B={B} Tm={Tm} {mode:10s} down{n} max|d| {d.max().item():.3e} (rms {inter[f"down{n}"].pow(2).mean().sqrt():.3f})', flush=True)
+        eng.set_option('stop_after', 99)
