@@ -42,7 +42,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait: a protocol bug traps instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -281,6 +281,199 @@ k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bia
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// kernel_conv GEMM, CTA-pair version (cta_group::2).  The 1-CTA kernel above is shared-memory-bandwidth bound (per 128-cycle
+// N=256 MMA: 12 KB of operand reads + the TMA refill = 158 B/clk against 128 B/clk; profiles/r01_tcgen05_findings.md).  Here a
+// cluster of two CTAs computes a 256 (n) x 256 (frames) tile: each CTA stages its own 128 weight rows and HALF of the frame
+// rows (128), the leader issues one M=256 MMA per k-step that reads both halves, and each CTA ends up with its 128 n-rows x
+// 256 frames in its own TMEM.  Per SM: 8 KB operand reads per MMA + 64 KB TMA per stage = ~106 B/clk.
+//   * TMA loads of BOTH CTAs signal the LEADER's full barrier (cp.async.bulk.tensor...cta_group::2, barrier address with the
+//     peer bit cleared); the leader arms it with the byte count of the pair.
+//   * tcgen05.commit...multicast::cluster (mask 0b11) releases the smem slot / publishes the accumulator in both CTAs.
+//   * epilogue warps of both CTAs arrive (remotely for the peer) on the leader's tmem-empty barrier.
+// 3-stage ring of 64 KB per CTA, 2 x 256-column accumulators, 8 epilogue warps per CTA as in the 1-CTA kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KC2_STAGES = 3;
+constexpr int KC2_A_BYTES = 128 * 128;       // 16 KB: 128 weight rows x one 32-float k-atom
+constexpr int KC2_B_BYTES = 128 * 128;       // 16 KB: this CTA's 128 of the 256 frame rows
+constexpr int KC2_STAGE_BYTES = 2 * KC2_A_BYTES + 2 * KC2_B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 64 KB
+constexpr int KC2_SMEM_BYTES = KC2_STAGES * KC2_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;   // Sm100MmaPeerBitMask: the leader CTA's copy of the barrier
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on CTA 0's copy of `bar`
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0u));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
+              const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* bars = (uint64_t*)(smem + KC2_STAGES * KC2_STAGE_BYTES);
+    uint64_t* full_bar = bars;                     // [STAGES]  (leader's copy is used) TMA of both CTAs -> leader MMA
+    uint64_t* empty_bar = bars + KC2_STAGES;       // [STAGES]  leader MMA -> TMA producer of each CTA (multicast commit)
+    uint64_t* tfull_bar = bars + 2 * KC2_STAGES;   // [2]       leader MMA -> epilogue of each CTA (multicast commit)
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2]       (leader's copy) epilogue warps of both CTAs -> leader MMA
+    uint32_t* tmem_base_s = (uint32_t*)(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int M = B * (Tm + 2) - 2;
+    const int f_tiles = (M + 255) / 256;
+    const int n_pairs = KCN / 256;                 // 97
+    const int items_per_blk = n_pairs * f_tiles;
+    const int total_items = NBLK * items_per_blk;
+    const int pair_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < KC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {   // collective over the pair: the same warp of both CTAs
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();     // barriers of both CTAs initialised and TMEM allocated before any remote access
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 0) {
+        // ================= TMA producer (each CTA loads its own A rows and its half of the frames) =================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int item = pair_id; item < total_items; item += n_clusters) {
+                const int blk = item / items_per_blk, r = item % items_per_blk;
+                const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
+                const CUtensorMap* wh = &maps.w_hi[blk]; const CUtensorMap* wl = &maps.w_lo[blk];
+                const CUtensorMap* hh = &maps.h_hi[blk]; const CUtensorMap* hl = &maps.h_lo[blk];
+                for (int a = 0; a < 6; ++a) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    unsigned char* st = smem + stage * KC2_STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (three_pass ? KC2_STAGE_BYTES : (KC2_A_BYTES + KC2_B_BYTES)));
+                    const int frow = ft * 256 + (int)rank * 128 + (a >> 1);
+                    tma_load_2d_2sm(st, wh, a * 32, nt * 128, &full_bar[stage]);
+                    tma_load_2d_2sm(st + 2 * KC2_A_BYTES, hh, (a & 1) * 32, frow, &full_bar[stage]);
+                    if (three_pass) {
+                        tma_load_2d_2sm(st + KC2_A_BYTES, wl, a * 32, nt * 128, &full_bar[stage]);
+                        tma_load_2d_2sm(st + 2 * KC2_A_BYTES + KC2_B_BYTES, hl, (a & 1) * 32, frow, &full_bar[stage]);
+                    }
+                    if (++stage == KC2_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer: leader CTA only =================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_tf32(256, 256);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int item = pair_id; item < total_items; item += n_clusters) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int a = 0; a < 6; ++a) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * KC2_STAGE_BYTES);
+                    const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + KC2_A_BYTES);
+                    const uint64_t b_hi = umma_desc_sw128(st + 2 * KC2_A_BYTES), b_lo = umma_desc_sw128(st + 2 * KC2_A_BYTES + KC2_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 2);
+                        umma_tf32_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
+                        if (three_pass) {
+                            umma_tf32_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_tf32_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                        }
+                    }
+                    tc_commit_2sm(&empty_bar[stage]);
+                    if (++stage == KC2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2sm(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ================= epilogue (both CTAs): own TMEM (128 n rows x 256 frames) -> (+bias) -> global =================
+        const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int item = pair_id; item < total_items; item += n_clusters) {
+            const int blk = item / items_per_blk, r = item % items_per_blk;
+            const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
+            const int n = nt * 128 + q * 32 + lane;
+            const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
+            const float bv = bias[n];
+            float* kern = kern_all + (size_t)blk * B * Tm * KCN;
+            int p = ft * 256 + chalf * 128;
+            int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
+            const bool fast = (fp >= 1) && (fp + 127 <= Tm) && (p + 127 < M);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + chalf * 128;
+            if (fast) {
+                float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN + n;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o[(size_t)j * KCN] = __uint_as_float(v[j]) + bv;
+                    o += (size_t)32 * KCN;
+                }
+            } else {
+#pragma unroll 1
+                for (int c0 = 0; c0 < 128; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (p < M && fp >= 1 && fp <= Tm)
+                            kern[((size_t)bb * Tm + (fp - 1)) * KCN + n] = __uint_as_float(v[j]) + bv;
+                        ++p;
+                        if (++fp == Tm + 2) { fp = 0; ++bb; }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still touch its smem / barriers
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -293,6 +486,7 @@ struct TcState {
     const float* blob = nullptr;
     uint64_t sec_off[FD_S_COUNT];
     CUtensorMap w_hi[NBLK], w_lo[NBLK];
+    int kc_2cta = 1;       // kernel_conv GEMM on CTA pairs (cta_group::2, default); option "kc_2cta" = 0 selects the 1-CTA kernel
     int lvc_swizzle = 0;   // LVC operand tiles: 0 = no-swizzle panels, 1 = SWIZZLE_128B + base_offset, 2 = SWIZZLE_128B, base_offset 0
     bool ok = false;
 };
@@ -313,6 +507,7 @@ static inline cudaError_t tc_set_lvc_attrs();
 static inline void tc_destroy(void* st) { delete (TcState*)st; }
 static inline bool tc_available(void* st) { return st && ((TcState*)st)->ok; }
 static inline void tc_set_lvc_swizzle(void* st, int v) { if (st) ((TcState*)st)->lvc_swizzle = v; }
+static inline void tc_set_kc_2cta(void* st, int v) { if (st) ((TcState*)st)->kc_2cta = v; }
 
 static inline int tc_init(void** state, int device, const float* blob, const uint64_t* sec_off, std::string& err) {
     tc_destroy(*state);
@@ -352,6 +547,20 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         if (tc_make_map_2d(s, &maps.h_lo[n], hk_lo + (size_t)n * rows * HID, HID, rows, HID * 4, KCG_KATOM, KCG_BN, err)) return -3;
     }
     const int M = B * (Tm + 2) - 2;
+    if (s->kc_2cta) {
+        for (int n = 0; n < NBLK; ++n) {   // frame boxes of 128 rows: each CTA of a pair loads half of the 256-frame tile
+            if (tc_make_map_2d(s, &maps.h_hi[n], hk_hi + (size_t)n * rows * HID, HID, rows, HID * 4, KCG_KATOM, 128, err)) return -3;
+            if (tc_make_map_2d(s, &maps.h_lo[n], hk_lo + (size_t)n * rows * HID, HID, rows, HID * 4, KCG_KATOM, 128, err)) return -3;
+        }
+        const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
+        int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
+        k_kc_gemm_tc2<<<2 * clusters, 320, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                            s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, mode == 1 ? 1 : 0);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc2 failed: ") + cudaGetErrorString(e2); return -3; }
+        ++*launches;
+        return 0;
+    }
     const int total = NBLK * (KCN / KCG_BM) * ((M + KCG_BN - 1) / KCG_BN);
     const int grid = total < s->sm_count ? total : s->sm_count;
     k_kc_gemm_tc<<<grid, 320, KCG_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
@@ -1121,6 +1330,8 @@ static inline int tc_dblock0(void* state, int mode, const float* audio, float* d
 
 static inline cudaError_t tc_set_lvc_attrs() {
     cudaError_t e0 = cudaFuncSetAttribute(k_dblock0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_kc_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
     if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
