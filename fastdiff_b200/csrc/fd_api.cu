@@ -28,6 +28,7 @@ struct fd_handle {
     int mode = FD_MODE_FP32_SIMT;
     int mode_set_by_user = 0;
     int stop_after = 99;
+    int tc_upsample = 1;         // LVC-block upsample (blocks 1, 2) on tensor cores in the TC modes (option "tc_upsample")
     int tc_dblock = 1;           // DBlock 0 on tensor cores in the TC modes (option "tc_dblock")
     int attrs_set = 0;
     uint64_t launches = 0;
@@ -260,6 +261,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!h || !key) return FD_ERR_INVALID;
     if (!strcmp(key, "stop_after")) { h->stop_after = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_dblock")) { h->tc_dblock = (int)value; return FD_OK; }
+    if (!strcmp(key, "tc_upsample")) { h->tc_upsample = (int)value; return FD_OK; }
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "kc_2cta")) { tc_set_kc_2cta(h->tc_state, (int)value); return FD_OK; }
@@ -414,9 +416,19 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         {
             const dim3 grid((Tin + 31) / 32, B);
             ScopedTimer tm(h, KC_UPSAMPLE, st);
-            if (r == 8) { auto k = k_upsample<8>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
-            else        { auto k = k_upsample<4>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
-            FD_CHECK_LAUNCH(h, "k_upsample");
+            bool up_done = false;
+#ifndef FD_EMU
+            if (n >= 1 && h->mode != FD_MODE_FP32_SIMT && h->tc_upsample) {
+                int rc = tc_upsample(h->tc_state, h->mode, n, blk_in, cur, B, Tin, st, h->err, &h->launches);
+                if (rc) return rc;
+                up_done = true;
+            }
+#endif
+            if (!up_done) {
+                if (r == 8) { auto k = k_upsample<8>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
+                else        { auto k = k_upsample<4>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
+                FD_CHECK_LAUNCH(h, "k_upsample");
+            }
         }
         const float* skip = (n == 0) ? d1 : (n == 1 ? d0 : x_dev);
         const float* kern_n = kern + (size_t)n * B * Tm * KCN;

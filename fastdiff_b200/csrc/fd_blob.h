@@ -33,6 +33,8 @@
  *   LBn_KC_B  [24832]         same permutation of the two bias vectors
  *   LBn_KCT_HI / LBn_KCT_LO [24832 n][192 kk]   the same matrix transposed (K-major rows: the tcgen05 A operand),
  *             split into tf32 pieces  w = hi + lo,  hi = RN_tf32(w), lo = RN_tf32(w - hi)  (low 13 mantissa bits zero)
+ *   LBn_UPT_HI / _LO [2r taps][32 co][8 chunks (ci/4) ^ (co&7)][4] (n = 1, 2): lvc_blocks.n.upsample (ConvTranspose1d weight (ci,co,k))
+ *             as SWIZZLE_128B K-major tiles Wt[k][co][ci], tf32 pieces (tensor-core upsample)
  *   DB0_CONVT_HI / _LO [3 layers][3 k][32 co][8 chunks (ci/4) ^ (co&7)][4], DB0_REST_HI / _LO [32 co][8 chunks][4]:
  *             downsample.0 convs and its 1x1 residual as SWIZZLE_128B K-major tiles, tf32 pieces (tensor-core DBlock 0)
  *   LBn_CONVT_HI / LBn_CONVT_LO [4 layers][3 k][32 co][8 chunks (ci/4) ^ (co&7)][4]   lvc_blocks.n.convs.* as SWIZZLE_128B K-major tiles, tf32 pieces
@@ -41,7 +43,7 @@
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 7ULL
+#define FD_BLOB_VERSION 8ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */
@@ -57,7 +59,8 @@
     X(LB1_KPIN_W) X(LB1_KPIN_B) X(LB1_KPRES_W) X(LB1_KPRES_B) X(LB1_KC_W) X(LB1_KC_B) X(LB1_KCT_HI) X(LB1_KCT_LO) X(LB1_CONVT_HI) X(LB1_CONVT_LO) \
     X(LB2_FCT_WT) X(LB2_FCT_B) X(LB2_UP_W) X(LB2_UP_B) X(LB2_CONV_W) X(LB2_CONV_B) \
     X(LB2_KPIN_W) X(LB2_KPIN_B) X(LB2_KPRES_W) X(LB2_KPRES_B) X(LB2_KC_W) X(LB2_KC_B) X(LB2_KCT_HI) X(LB2_KCT_LO) X(LB2_CONVT_HI) X(LB2_CONVT_LO) \
-    X(DB0_CONVT_HI) X(DB0_CONVT_LO) X(DB0_REST_HI) X(DB0_REST_LO)
+    X(DB0_CONVT_HI) X(DB0_CONVT_LO) X(DB0_REST_HI) X(DB0_REST_LO) \
+    X(LB1_UPT_HI) X(LB1_UPT_LO) X(LB2_UPT_HI) X(LB2_UPT_LO)
 /* FD_SECTIONS_END */
 
 enum fd_section {

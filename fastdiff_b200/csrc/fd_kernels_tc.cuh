@@ -322,7 +322,8 @@ __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {   // arrives on t
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on CTA 0's copy of `bar`
     uint32_t remote;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0u));
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");   // cutlass ClusterBarrier::arrive(cta_id) form
+
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
@@ -1279,6 +1280,156 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// K10  LVC-block upsample on tensor cores: lrelu_.2 -> ConvTranspose1d(32,32,k=2r,stride=r,pad=r/2)  (modules.py:205-206)
+//   out[r m + ph] = b + lrelu(in[m + sh]) W[kk1] + lrelu(in[m + sh - 1]) W[kk1 + r],   sh = (ph + r/2)/r, kk1 = (ph + r/2) % r
+// One tile = 128 input rows (+1 halo row either side) -> 128 r output rows.  For every output phase ph the two taps are two
+// row-shifted reads of the SAME SWIZZLE_128B input tile; the r phase accumulators (64 TMEM columns each: merged tf32 passes)
+// are all live at once and one epilogue interleaves them into consecutive output rows.  Input rows of the next tile arrive by
+// cp.async.bulk while the current tile is written out.  16 warps; r = 4: 2 CTAs/SM (99 KB smem, 256 TMEM columns each).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int UT_AROWS = 136;                          // input rows m0-1 .. m0+128 (+pad)
+constexpr int UT_ATILE = UT_AROWS * 128;               // 17408 B per piece
+template <int R> constexpr int ut_smem_bytes() { return 2 * UT_ATILE + 2 * R * 8192 + 256 + 64 + 1024; }
+
+template <int R>
+__global__ void __launch_bounds__(512, (R == 4 ? 2 : 1))
+k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, const float* __restrict__ bias,
+              const float* __restrict__ in, float* __restrict__ out, int B, int Tin, int three_pass) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* a_hi = smem;                          // tile row ar <-> input row m0 - 1 + ar
+    unsigned char* a_lo = a_hi + UT_ATILE;               // raw rows land here
+    unsigned char* wt = a_lo + UT_ATILE;                 // [2R taps][hi 32 rows 4 KB | lo 32 rows 4 KB]
+    float* b_s = (float*)(wt + 2 * R * 8192);
+    uint64_t* bar = (uint64_t*)(b_s + 64);               // [0] MMAs, [1] loads
+    uint32_t* tmem_base_s = (uint32_t*)(bar + 2);
+    constexpr uint32_t NCOLS = R * 64;
+
+    const int tid = threadIdx.x, gw = tid >> 5, lane = tid & 31;
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(NCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * R * 256; i += 512) {   // i = tap*256 + float4 within the 4 KB tap tile
+        const int k = i >> 8, w = i & 255;
+        reinterpret_cast<float4*>(wt + k * 8192)[w] = reinterpret_cast<const float4*>(w_hi)[i];
+        reinterpret_cast<float4*>(wt + k * 8192 + 4096)[w] = reinterpret_cast<const float4*>(w_lo)[i];
+    }
+    if (tid < C) b_s[tid] = bias[tid];
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int gw_u = __shfl_sync(0xffffffffu, gw, 0);
+    const uint32_t smem_u = smem_u32(smem);
+    constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32), idesc64 = umma_idesc_tf32(128, 64);
+
+    const int ntt = (Tin + 127) / 128, total = B * ntt;
+    auto issue_rows = [&](int tile) {
+        const int b = tile / ntt, m0 = (tile % ntt) * 128;
+        const int ar0 = m0 == 0 ? 1 : 0, ar1 = min(130, Tin - m0 + 1);   // rows inside [0, Tin)
+        const uint32_t bytes = (uint32_t)(ar1 - ar0) * 128u;
+        mbar_expect_tx(&bar[1], bytes);
+        bulk_g2s(a_lo + ar0 * 128, in + ((size_t)b * Tin + (m0 - 1 + ar0)) * C, bytes, &bar[1]);
+    };
+    int tile = blockIdx.x;
+    if (tile < total && gw_u == 0) { if (elect_one()) issue_rows(tile); __syncwarp(); }
+    uint32_t parity = 0;
+    for (; tile < total; tile += gridDim.x, parity ^= 1) {
+        const int b = tile / ntt, m0 = (tile % ntt) * 128;
+        mbar_wait(&bar[1], parity);
+        // ---- lrelu + tf32 split, in place (8 lanes per row) ----
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int ar = (tid >> 3) + i * 64, c4 = tid & 7, m = m0 - 1 + ar;
+            const bool active = ar < 130;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active && m >= 0 && m < Tin) {
+                const float4 x = *reinterpret_cast<const float4*>(a_lo + ar * 128 + c4 * 16);
+                v = make_float4(lrelu(x.x, 0.2f), lrelu(x.y, 0.2f), lrelu(x.z, 0.2f), lrelu(x.w, 0.2f));
+            }
+            float4 hi, lo;
+            split4(v, hi, lo);
+            __syncwarp();
+            if (active) {
+                *reinterpret_cast<float4*>(a_hi + swz128(ar, c4)) = hi;
+                *reinterpret_cast<float4*>(a_lo + swz128(ar, c4)) = lo;
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (gw_u == 0) {
+            tc_fence_after();
+            uint32_t at = smem_u, wu = smem_u + 2 * UT_ATILE;
+            asm volatile("" : "+r"(at), "+r"(wu));
+            if (elect_one()) {
+#pragma unroll
+                for (int ph = 0; ph < R; ++ph) {
+                    const int sh = (ph + R / 2) / R, kk1 = (ph + R / 2) % R;
+                    const uint32_t d = tmem_u + ph * 64;
+#pragma unroll
+                    for (int tap = 0; tap < 2; ++tap) {   // tap 0: input m + sh (weights kk1); tap 1: input m + sh - 1 (weights kk1 + R)
+                        const uint32_t arow = (uint32_t)(1 + sh - tap) * 128u, kk = (uint32_t)(kk1 + tap * R);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint64_t dah = umma_desc_sw128(at + arow + j * 32), dal = umma_desc_sw128(at + UT_ATILE + arow + j * 32);
+                            const uint64_t db = umma_desc_sw128(wu + kk * 8192 + j * 32);
+                            if (three_pass) {
+                                umma_tf32(d, dah, db, idesc64, (tap | j) ? 1u : 0u);
+                                umma_tf32(d, dal, db, idesc32, 1u);
+                            } else {
+                                umma_tf32(d, dah, db, idesc32, (tap | j) ? 1u : 0u);
+                            }
+                        }
+                    }
+                }
+                tc_commit(&bar[0]);
+            }
+            __syncwarp();
+        }
+        mbar_wait(&bar[0], parity);
+        tc_fence_after();
+        if (gw_u == 0 && tile + (int)gridDim.x < total) { if (elect_one()) issue_rows(tile + gridDim.x); __syncwarp(); }   // tile is free
+        {   // epilogue: thread = (input row m, 8 channels); its r outputs are consecutive rows r m + ph
+            const int q = gw & 3, part = gw >> 2, m = m0 + q * 32 + lane;
+            const float* bb = b_s + part * 8;
+            float* dst = out + (((size_t)b * Tin + (m < Tin ? m : 0)) * R) * C + part * 8;
+#pragma unroll
+            for (int ph = 0; ph < R; ++ph) {
+                uint32_t v[8];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ph * 64 + part * 8;
+                tmem_ld_cols<8>(ta, v);
+                if (three_pass) {
+                    uint32_t v2[8];
+                    tmem_ld_cols<8>(ta + 32, v2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+                }
+                tmem_ld_wait();
+                if (m < Tin) {
+                    float4 o0 = make_float4(__uint_as_float(v[0]) + bb[0], __uint_as_float(v[1]) + bb[1], __uint_as_float(v[2]) + bb[2], __uint_as_float(v[3]) + bb[3]);
+                    float4 o1 = make_float4(__uint_as_float(v[4]) + bb[4], __uint_as_float(v[5]) + bb[5], __uint_as_float(v[6]) + bb[6], __uint_as_float(v[7]) + bb[7]);
+                    *reinterpret_cast<float4*>(dst + ph * C) = o0;
+                    *reinterpret_cast<float4*>(dst + ph * C + 4) = o1;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(NCOLS) : "memory");
+    }
+}
+
 // x_in/x_out: (B,T,32); skip: (B,T,32) buffer or (block 2) the audio (B,T); kern: this layer's slice of the predicted kernels.
 static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const float* x_in, const float* skip, const float* kern,
                                float* x_out, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches,
@@ -1309,6 +1460,28 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     return 0;
 }
 
+// in (B,Tin,32) -> out (B,Tin*r,32) for LVC blocks 1 (r = 8) and 2 (r = 4)
+static inline int tc_upsample(void* state, int mode, int blk, const float* in, float* out, int B, int Tin, cudaStream_t st, std::string& err,
+                              uint64_t* launches) {
+    TcState* s = (TcState*)state;
+    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    const float* wh = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_UPT_HI : FD_S_LB2_UPT_HI];
+    const float* wl = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_UPT_LO : FD_S_LB2_UPT_LO];
+    const float* bias = s->blob + s->sec_off[FD_S_LB0_UP_B + blk * FD_LB_STRIDE];
+    const int total = B * ((Tin + 127) / 128);
+    if (blk == 1) {
+        const int grid = total < s->sm_count ? total : s->sm_count;
+        k_upsample_tc<8><<<grid, 512, ut_smem_bytes<8>(), st>>>(wh, wl, bias, in, out, B, Tin, mode == 1 ? 1 : 0);
+    } else {
+        const int grid = total < 2 * s->sm_count ? total : 2 * s->sm_count;
+        k_upsample_tc<4><<<grid, 512, ut_smem_bytes<4>(), st>>>(wh, wl, bias, in, out, B, Tin, mode == 1 ? 1 : 0);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_upsample_tc failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    return 0;
+}
+
 // audio (B,L) -> d0 (B, L/4, 32)
 static inline int tc_dblock0(void* state, int mode, const float* audio, float* d0, int B, int L, cudaStream_t st, std::string& err,
                              uint64_t* launches) {
@@ -1332,6 +1505,10 @@ static inline cudaError_t tc_set_lvc_attrs() {
     cudaError_t e0 = cudaFuncSetAttribute(k_dblock0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_kc_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_upsample_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<4>());
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_upsample_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<8>());
     if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());

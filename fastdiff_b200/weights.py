@@ -156,6 +156,11 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
     rw = W["downsample.0.residual_dense.weight"][:, :, 0].reshape(C, 8, 4)[_SWZ_O[:C], _SWZ_SRC[:C], :].contiguous()
     hi, lo = tf32_split(rw.numpy())
     S["DB0_REST_HI"], S["DB0_REST_LO"] = torch.from_numpy(hi), torch.from_numpy(lo)
+    for n in (1, 2):   # ConvTranspose1d weight (ci, co, k) -> [k][co][chunk ^ (co&7)][4]
+        uw = W[f"lvc_blocks.{n}.upsample.weight"].permute(2, 1, 0)                       # [k][co][ci]
+        uw = uw.reshape(uw.shape[0], C, 8, 4)[:, _SWZ_O[:C], _SWZ_SRC[:C], :].contiguous()
+        hi, lo = tf32_split(uw.numpy())
+        S[f"LB{n}_UPT_HI"], S[f"LB{n}_UPT_LO"] = torch.from_numpy(hi), torch.from_numpy(lo)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}
 
