@@ -61,41 +61,93 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled DURING the timed regions: NVML polled every ~5 ms from a thread that is
+    started before the warm-up (so it is already running when the short timed region begins); only samples whose host
+    timestamp falls inside a [mark_begin, mark_end] window are reported.  Falls back to `nvidia-smi -lms` if NVML is missing."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.windows, self._t0 = index, [], [], None
+        self._stop = threading.Event()
+        self.thr = None
+        self.backend = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thr = threading.Thread(target=self._read, daemon=True)
-            self.thr.start()
-        except Exception as e:  # pragma: no cover
-            log("clock sampler unavailable:", e)
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    idx = self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            bits = [getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        t = time.perf_counter()
+                        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        pw = nv.nvmlDeviceGetPowerUsage(h) / 1e3
+                        rs = int(get_reasons(h))
+                        self.rows.append((t, sm, mx, pw, [n for n, b in zip(self.NAMES, bits) if rs & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.004)
+            self.backend = "nvml"
+        except Exception as e:
+            log("NVML unavailable (%r); falling back to nvidia-smi" % (e,))
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            try:
+                proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                        stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception as e2:  # pragma: no cover
+                log("clock sampler unavailable:", e2)
+                return
+            self.proc = proc
+
+            def poll():
+                for line in proc.stdout:
+                    c = [x.strip() for x in line.split(",")]
+                    try:
+                        self.rows.append((time.perf_counter(), float(c[0]), float(c[1]), float(c[2]),
+                                          [n for n, v in zip(self.NAMES, c[3:7]) if v.lower().startswith("active")]))
+                    except Exception:
+                        pass
+                    if self._stop.is_set():
+                        break
+            self.backend = "nvidia-smi"
+        self.thr = threading.Thread(target=poll, daemon=True)
+        self.thr.start()
+
+    def mark_begin(self):
+        self._t0 = time.perf_counter()
+
+    def mark_end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, time.perf_counter()))
+            self._t0 = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+        if self.thr is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        self._stop.set()
+        if getattr(self, "proc", None):
+            self.proc.terminate()
+        self.thr.join(timeout=2)
+        rows = [r for r in self.rows if any(a <= r[0] <= b for a, b in self.windows)]
+        sm = [r[1] for r in rows]
+        reasons = sorted({n for r in rows for n in r[4]}, key=self.NAMES.index)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(r[2] for r in rows) if rows else None,
+                "reasons": reasons, "samples": len(rows), "power_w_max": max(r[3] for r in rows) if rows else None,
+                "source": f"{self.backend}, polled during the timed regions (device-resident + e2e)"}
 
 
 def oracle_setup(seed=1234):
@@ -189,7 +241,7 @@ def run_ours(args):
         eng.set_mode(args.mode)
         if net is not None:
             net.mode = args.mode
-    mode_name = {0: "fp32_simt", 1: "tc_3xtf32", 2: "tc_tf32"}[eng.get_mode()]
+    mode_name = {0: "fp32_simt", 1: "tc_3xtf32", 2: "tc_tf32", 3: "tc_3xf16"}[eng.get_mode()]
 
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
     sched = torch.FloatTensor(N4_SCHEDULE)
@@ -206,26 +258,29 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks:
+        clocks.start()
     for i in range(args.warmup):
         one_call(i)
     barrier()
 
     # ---- timed region: device-resident inputs ------------------------------------------------------------
-    clocks = ClockSampler(local) if rank == 0 else None
     eng.timing_enable(True)
     eng.timing_report()  # drop warm-up records
     l0 = eng.launch_count()
-    if clocks:
-        clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if clocks:
+        clocks.mark_begin()
     ev0.record()
     for i in range(args.steps):
         one_call(args.warmup + i)
     ev1.record()
     barrier()
+    if clocks:
+        clocks.mark_end()
     ms = ev0.elapsed_time(ev1)
-    clk = clocks.stop() if clocks else None
     launches = eng.launch_count() - l0
     per_kernel = eng.timing_report()
     eng.timing_enable(False)
@@ -257,11 +312,15 @@ def run_ours(args):
                 torch.cuda.synchronize()
         e2e_call(0)
         barrier()
+        if clocks:
+            clocks.mark_begin()
         t0 = time.perf_counter()
         for i in range(args.steps):
             e2e_call(1 + i)
         barrier()
         dt = time.perf_counter() - t0
+        if clocks:
+            clocks.mark_end()
         tt = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -272,6 +331,7 @@ def run_ours(args):
     except Exception as e:  # pragma: no cover
         log("e2e leg failed:", repr(e))
 
+    clk = clocks.stop() if clocks else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -347,7 +407,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=None, choices=[None, "fp32_simt", "tc_3xtf32", "tc_tf32"])
+    ap.add_argument("--mode", default=None, choices=[None, "fp32_simt", "tc_3xtf32", "tc_tf32", "tc_3xf16"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--frames", type=int, default=861)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -7,8 +7,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "csrc", "libfastdiff_b200.so")
 
-FD_MODE_FP32_SIMT, FD_MODE_TC_3XTF32, FD_MODE_TC_TF32 = 0, 1, 2
-MODE_NAMES = {"fp32_simt": 0, "tc_3xtf32": 1, "tc_tf32": 2}
+FD_MODE_FP32_SIMT, FD_MODE_TC_3XTF32, FD_MODE_TC_TF32, FD_MODE_TC_3XF16 = 0, 1, 2, 3
+MODE_NAMES = {"fp32_simt": 0, "tc_3xtf32": 1, "tc_tf32": 2, "tc_3xf16": 3}
 
 
 class fd_config(C.Structure):

@@ -204,7 +204,7 @@ extern "C" int fd_load_weights(fd_handle* h, const void* blob_host, size_t bytes
 #ifndef FD_EMU
     rc = tc_init(&h->tc_state, h->device, h->blob, h->sec_off, h->err);
     if (rc) return rc;
-    if (!h->mode_set_by_user) h->mode = FD_MODE_TC_3XTF32;   // default: tensor cores at fp32-level accuracy
+    if (!h->mode_set_by_user) h->mode = FD_MODE_TC_3XF16;   // default: tensor cores at fp32-level accuracy
 #endif
     return finish_load(h, (const uint64_t*)blob_host);
 }
@@ -231,7 +231,7 @@ extern "C" int fd_load_weights_dev(fd_handle* h, const void* blob_dev, size_t by
 #ifndef FD_EMU
     rc = tc_init(&h->tc_state, h->device, h->blob, h->sec_off, h->err);
     if (rc) return rc;
-    if (!h->mode_set_by_user) h->mode = FD_MODE_TC_3XTF32;
+    if (!h->mode_set_by_user) h->mode = FD_MODE_TC_3XF16;
 #endif
     return FD_OK;
 }
@@ -244,7 +244,7 @@ extern "C" int fd_workspace_bytes(fd_handle* h, int B, int Tm, size_t* out) {
 
 extern "C" int fd_set_mode(fd_handle* h, int mode) {
     if (!h) return FD_ERR_INVALID;
-    if (mode < FD_MODE_FP32_SIMT || mode > FD_MODE_TC_TF32) return fail(h, FD_ERR_INVALID, "fd_set_mode: unknown mode %d", mode);
+    if (mode < FD_MODE_FP32_SIMT || mode > FD_MODE_TC_3XF16) return fail(h, FD_ERR_INVALID, "fd_set_mode: unknown mode %d", mode);
 #ifdef FD_EMU
     if (mode != FD_MODE_FP32_SIMT) return fail(h, FD_ERR_UNSUPPORTED, "fd_set_mode: the emulation build has no tensor-core path");
 #else
@@ -358,7 +358,8 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             p.res_w[n] = sec(h, FD_S_LB0_KPRES_W + n * FD_LB_STRIDE); p.res_b[n] = sec(h, FD_S_LB0_KPRES_B + n * FD_LB_STRIDE);
         }
         ScopedTimer tm(h, KC_KP_HIDDEN, st);
-        FD_LAUNCH(k_kp_hidden, dim3((Tm + KP_FT - 1) / KP_FT, B, NBLK), dim3(256), KP_SMEM_BYTES, st, p, mel_dev, cnoise, hk, ws + w.hk_hi, ws + w.hk_lo, B, Tm);
+        FD_LAUNCH(k_kp_hidden, dim3((Tm + KP_FT - 1) / KP_FT, B, NBLK), dim3(256), KP_SMEM_BYTES, st, p, mel_dev, cnoise, hk, ws + w.hk_hi, ws + w.hk_lo, B, Tm,
+                  h->mode == FD_MODE_TC_3XF16 ? 1 : 0);
         FD_CHECK_LAUNCH(h, "k_kp_hidden");
     }
     if (h->mode == FD_MODE_FP32_SIMT) {
@@ -632,7 +633,8 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         const int want_bias = name[1] == 'b';
         *count = want_bias ? (size_t)B * LAYERS * LVC_OUT * Tm : (size_t)B * LAYERS * C * LVC_OUT * KS * Tm;
         if (!out_dev) return FD_OK;
-        FD_LAUNCH(k_kern_to_ref, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, ws + w.kern + (size_t)n * B * Tm * KCN, out_dev, B, Tm, want_bias, n == 0 ? 1 : 0);
+        FD_LAUNCH(k_kern_to_ref, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, ws + w.kern + (size_t)n * B * Tm * KCN, out_dev, B, Tm, want_bias,
+                  n == 0 ? 1 : (h->mode == FD_MODE_TC_3XF16 ? 2 : 0));
         FD_CHECK_LAUNCH(h, "k_kern_to_ref");
         return FD_OK;
     }

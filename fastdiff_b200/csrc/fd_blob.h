@@ -38,12 +38,19 @@
  *   DB0_CONVT_HI / _LO [3 layers][3 k][32 co][8 chunks (ci/4) ^ (co&7)][4], DB0_REST_HI / _LO [32 co][8 chunks][4]:
  *             downsample.0 convs and its 1x1 residual as SWIZZLE_128B K-major tiles, tf32 pieces (tensor-core DBlock 0)
  *   LBn_CONVT_HI / LBn_CONVT_LO [4 layers][3 k][32 co][8 chunks (ci/4) ^ (co&7)][4]   lvc_blocks.n.convs.* as SWIZZLE_128B K-major tiles, tf32 pieces
+ *
+ * fp16-piece operands (mode tc_3xf16; two fp16 values per fp32 blob element, little endian).  w*S = hi + lo with
+ * hi = RN_f16(w*S), lo = RN_f16(w*S - hi); S = the per-tensor power of two that puts max|w|*S in (8192, 16384] (SCALES16):
+ *   LBn_KCT_F16 [2 planes: hi, lo][24832 n][192 kk] fp16   the LBn_KCT matrix (K-major rows of 384 B: the tcgen05 A operand)
+ *   LBn_CONV_F16 (n = 1, 2) [4 layers][3 k][32 co] rows of 128 B = [32 ci hi | 32 ci lo] fp16, the 16-byte chunk c (8 values) of
+ *             row co stored at chunk position c ^ (co & 7): SWIZZLE_128B K-major B-operand tiles of the dilated convs
+ *   SCALES16  [64]  S of: kernel_conv block n at [n]; lvc_blocks.n.convs.l at [4 + 4 n + l]
  */
 #ifndef FD_BLOB_H
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 8ULL
+#define FD_BLOB_VERSION 9ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */
@@ -60,7 +67,8 @@
     X(LB2_FCT_WT) X(LB2_FCT_B) X(LB2_UP_W) X(LB2_UP_B) X(LB2_CONV_W) X(LB2_CONV_B) \
     X(LB2_KPIN_W) X(LB2_KPIN_B) X(LB2_KPRES_W) X(LB2_KPRES_B) X(LB2_KC_W) X(LB2_KC_B) X(LB2_KCT_HI) X(LB2_KCT_LO) X(LB2_CONVT_HI) X(LB2_CONVT_LO) \
     X(DB0_CONVT_HI) X(DB0_CONVT_LO) X(DB0_REST_HI) X(DB0_REST_LO) \
-    X(LB1_UPT_HI) X(LB1_UPT_LO) X(LB2_UPT_HI) X(LB2_UPT_LO)
+    X(LB1_UPT_HI) X(LB1_UPT_LO) X(LB2_UPT_HI) X(LB2_UPT_LO) \
+    X(LB0_KCT_F16) X(LB1_KCT_F16) X(LB2_KCT_F16) X(LB1_CONV_F16) X(LB2_CONV_F16) X(SCALES16)
 /* FD_SECTIONS_END */
 
 enum fd_section {

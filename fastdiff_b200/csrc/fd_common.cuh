@@ -17,6 +17,7 @@
 
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 namespace fd {
 
@@ -49,6 +50,55 @@ __device__ __forceinline__ float tf32_rn(float x) {
     u = (u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u;
     return __uint_as_float(u);
 }
+// ---- fp16 pieces (mode tc_3xf16): v*S = hi + lo, hi = RN_f16(v*S), lo = RN_f16(v*S - hi).  hi and lo carry 11 significant
+// bits each (the same as a tf32 pair), S is a power of two that keeps lo out of the fp16 subnormals for the magnitudes the
+// network produces (full 22-bit precision for |v*S| >= 2^-3, absolute error <= 2^-25 below); |v*S| saturates at 65504.
+// Software conversion = the bit-exact definition (round to nearest even, gradual underflow); the device build uses cvt.rn.f16.f32.
+__host__ __device__ inline uint16_t f16_bits_rn_soft(float f) {
+    uint32_t x; memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x7F800000u) return (uint16_t)(sign | (x > 0x7F800000u ? 0x7E00u : 0x7C00u));
+    if (x >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                      // rounds to >= 65520 -> inf
+    if (x < 0x33000001u) return (uint16_t)sign;                                   // <= 2^-25 -> 0 (ties to even)
+    uint32_t e = x >> 23, m = (x & 0x7FFFFFu) | 0x800000u, shift, half;
+    if (e >= 113) { shift = 13; half = (uint32_t)(e - 112) << 10; m &= 0x7FFFFFu; }   // normal: drop the implicit bit
+    else { shift = 126 - e; half = 0; }                                            // subnormal: keep it and shift further
+    const uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), mid = 1u << (shift - 1);
+    uint32_t h = half + q;
+    if (rem > mid || (rem == mid && (h & 1u))) ++h;                                // carries into the exponent correctly
+    return (uint16_t)(sign | h);
+}
+__host__ __device__ inline float f16_bits_to_float_soft(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 31u, m = h & 0x3FFu;
+    uint32_t x;
+    if (e == 0) {
+        if (m == 0) x = sign;
+        else { int k = 0; uint32_t mm = m; while (!(mm & 0x400u)) { mm <<= 1; ++k; } x = sign | ((uint32_t)(113 - k) << 23) | ((mm & 0x3FFu) << 13); }
+    } else if (e == 31) x = sign | 0x7F800000u | (m << 13);
+    else x = sign | ((e + 112u) << 23) | (m << 13);
+    float f; memcpy(&f, &x, 4);
+    return f;
+}
+#ifdef FD_EMU
+__device__ __forceinline__ uint16_t f16_bits_rn(float f) { return f16_bits_rn_soft(f); }
+__device__ __forceinline__ float f16_bits_to_float(uint16_t h) { return f16_bits_to_float_soft(h); }
+#else
+__device__ __forceinline__ uint16_t f16_bits_rn(float f) { uint16_t h; asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(f)); return h; }
+__device__ __forceinline__ float f16_bits_to_float(uint16_t h) { float f; asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h)); return f; }
+#endif
+constexpr float F16_MAX = 65504.f;
+// (hi, lo) fp16 pieces of v*scale, saturated
+__device__ __forceinline__ void f16_split(float v, float scale, uint16_t& hi, uint16_t& lo) {
+    const float s = fminf(fmaxf(v * scale, -F16_MAX), F16_MAX);
+    hi = f16_bits_rn(s);
+    lo = f16_bits_rn(s - f16_bits_to_float(hi));
+}
+// fixed power-of-two prescales of the dynamic operands (weights carry per-tensor scales chosen by the packer, section SCALES16)
+constexpr float S16_HK = 16.f;       // kernel-predictor hidden state (B operand of the kernel_conv GEMM)
+constexpr float S16_ACT = 16.f;      // LVC-block activations (A operands of the dilated conv and of the location-variable conv)
+constexpr float S16_KERN = 64.f;     // predicted LVC kernels (B operand of the location-variable conv), written by the kernel_conv GEMM
+
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
 }  // namespace fd

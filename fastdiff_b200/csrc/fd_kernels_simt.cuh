@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __res
 // One CTA = 32 output frames of one (block, batch item), halo (8 frames) recomputed.
 // Output hk: (3, B, T'+2, 64) channels-last with one zero frame either side of every item, so the
 // kernel_conv im2col row of frame f is the 192 contiguous floats starting at padded row f.  Written three
-// times: raw fp32 (SIMT GEMM) and as tf32 pieces hi/lo (tensor-core GEMM operands).
+// times: raw fp32 (SIMT GEMM) and as tf32 pieces hi/lo -- or, with f16 != 0, as fp16 pieces of v*S16_HK in rows of 128 B
+// (tensor-core GEMM operands).
 // grid = (ceil(T'/32), B, 3), block = 256, dynamic smem = KP_SMEM_BYTES.
 // ------------------------------------------------------------------------------------------------
 struct KpParams {
@@ -77,7 +78,7 @@ constexpr int KP_SMEM_BYTES = (COND * KP_CS + 3 * HID * KP_HS) * 4;
 
 __global__ void __launch_bounds__(256) k_kp_hidden(KpParams p, const float* __restrict__ mel,
                                                    const float* __restrict__ cnoise, float* __restrict__ hk_all,
-                                                   float* __restrict__ hk_hi_all, float* __restrict__ hk_lo_all, int B, int Tm) {
+                                                   float* __restrict__ hk_hi_all, float* __restrict__ hk_lo_all, int B, int Tm, int f16) {
     FD_DYN_SMEM(float, sm);
     float* cond_s = sm;
     float* h0_s = cond_s + COND * KP_CS;
@@ -152,19 +153,26 @@ __global__ void __launch_bounds__(256) k_kp_hidden(KpParams p, const float* __re
             }
             __syncthreads();
             src = dst;
-        } else {
-            const size_t item = (size_t)(blk * B + b) * (Tm + 2) * HID;
+        }
+    }
+    // acc now holds the last residual conv: h = h0 + lrelu(acc)
+    const size_t item = (size_t)(blk * B + b) * (Tm + 2) * HID;
 #pragma unroll
-            for (int r = 0; r < 11; ++r) {
-                const int row = r0 + r, f = f0 + row - 6;
-                if (row >= 6 && row < 6 + KP_FT && f < Tm) {
-                    const float v = h0_s[co * KP_HS + 1 + row] + lrelu(acc[r], 0.1f);
-                    const size_t o = item + (size_t)(1 + f) * HID + co;
-                    hk_all[o] = v;
-                    const float hi = tf32_rn(v);       // tf32 pieces for the tensor-core GEMM (3xTF32)
-                    hk_hi_all[o] = hi;
-                    hk_lo_all[o] = tf32_rn(v - hi);
-                }
+    for (int r = 0; r < 11; ++r) {
+        const int row = r0 + r, f = f0 + row - 6;
+        if (row >= 6 && row < 6 + KP_FT && f < Tm) {
+            const float v = h0_s[co * KP_HS + 1 + row] + lrelu(acc[r], 0.1f);
+            const size_t o = item + (size_t)(1 + f) * HID + co;
+            hk_all[o] = v;
+            if (f16) {                         // fp16 pieces of v*S16_HK (3xFP16): rows of 64 values = 128 B
+                uint16_t h16, l16;
+                f16_split(v, S16_HK, h16, l16);
+                reinterpret_cast<uint16_t*>(hk_hi_all)[o] = h16;
+                reinterpret_cast<uint16_t*>(hk_lo_all)[o] = l16;
+            } else {
+                const float hi = tf32_rn(v);   // tf32 pieces for the tensor-core GEMM (3xTF32)
+                hk_hi_all[o] = hi;
+                hk_lo_all[o] = tf32_rn(v - hi);
             }
         }
     }
@@ -753,6 +761,13 @@ __global__ void __launch_bounds__(256) k_kern_to_ref(const float* __restrict__ k
         const int ci = (int)(q % C); q /= C;
         const int l = (int)(q % LAYERS); q /= LAYERS;
         const int b = (int)q;
+        if (panel == 2) {   // fp16 pieces of w*S16_KERN: row (k,o) = [32 i hi | 32 i lo], chunk c (8 values) at position c ^ (o & 7)
+            const uint16_t* rowp = reinterpret_cast<const uint16_t*>(kern + ((size_t)b * Tm + f) * KCN + l * KPL) + (k * LVC_OUT + o) * 64;
+            const float hi = f16_bits_to_float(rowp[(((ci >> 3) ^ (o & 7)) << 3) + (ci & 7)]);
+            const float lo = f16_bits_to_float(rowp[(((4 + (ci >> 3)) ^ (o & 7)) << 3) + (ci & 7)]);
+            out[i] = (hi + lo) * (1.f / S16_KERN);
+            return;
+        }
         const int within = panel ? ((k * 8 + (ci >> 2)) * LVC_OUT + o) * 4 + (ci & 3)
                                  : ((k * LVC_OUT + o) * 8 + ((ci >> 2) ^ (o & 7))) * 4 + (ci & 3);
         out[i] = kern[((size_t)b * Tm + f) * KCN + l * KPL + within];

@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <string>
 #include "fd_blob.h"
 #include "fd_common.cuh"
@@ -116,6 +117,17 @@ __device__ __forceinline__ uint64_t umma_desc_ns(uint32_t smem_addr, uint32_t lb
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at 17, M>>4 at 24.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// kind::f16 with A = B = fp16 (format code 0), D = f32; one instruction covers K = 16 (32 bytes of a K-major row).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -315,6 +327,13 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, 
         "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
@@ -326,9 +345,18 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+// F16 = true (mode tc_3xf16): the operands are fp16 pieces (weights LBn_KCT_F16 prescaled per tensor, hidden rows of 64 fp16
+// = 128 B prescaled by S16_HK), a k-atom is 64 values = one tap of the im2col (box at row p + a), every MMA is kind::f16 with
+// K = 16, and the epilogue undoes the scales: kern = acc * inv[blk] + bias.  Half the MMAs and half the operand bytes of the
+// tf32 variant for the same 22 significant bits per operand.
+// EPW = epilogue warps per CTA (8 or 16: EPW/4 per TMEM lane quarter, each taking 256/(EPW/4) of the 256 frame columns).
+template <bool F16, int EPW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
-              const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass) {
+              const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass,
+              float inv0, float inv1, float inv2) {
+    constexpr int NATOM = F16 ? 3 : 6;
+    constexpr int CPW = 256 / (EPW / 4);   // frame columns per epilogue warp
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = (uint64_t*)(smem + KC2_STAGES * KC2_STAGE_BYTES);
@@ -349,7 +377,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < KC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 16); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * EPW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {   // collective over the pair: the same warp of both CTAs
@@ -370,16 +398,17 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                 const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
                 const CUtensorMap* wh = &maps.w_hi[blk]; const CUtensorMap* wl = &maps.w_lo[blk];
                 const CUtensorMap* hh = &maps.h_hi[blk]; const CUtensorMap* hl = &maps.h_lo[blk];
-                for (int a = 0; a < 6; ++a) {
+                for (int a = 0; a < NATOM; ++a) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* st = smem + stage * KC2_STAGE_BYTES;
                     if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (three_pass ? KC2_STAGE_BYTES : (KC2_A_BYTES + KC2_B_BYTES)));
-                    const int frow = ft * 256 + (int)rank * 128 + (a >> 1);
+                    const int frow = ft * 256 + (int)rank * 128 + (F16 ? a : (a >> 1));
+                    const int fcol = F16 ? 0 : (a & 1) * 32;
                     tma_load_2d_2sm(st, wh, a * 32, nt * 128, &full_bar[stage]);
-                    tma_load_2d_2sm(st + 2 * KC2_A_BYTES, hh, (a & 1) * 32, frow, &full_bar[stage]);
+                    tma_load_2d_2sm(st + 2 * KC2_A_BYTES, hh, fcol, frow, &full_bar[stage]);
                     if (three_pass) {
                         tma_load_2d_2sm(st + KC2_A_BYTES, wl, a * 32, nt * 128, &full_bar[stage]);
-                        tma_load_2d_2sm(st + 2 * KC2_A_BYTES + KC2_B_BYTES, hl, (a & 1) * 32, frow, &full_bar[stage]);
+                        tma_load_2d_2sm(st + 2 * KC2_A_BYTES + KC2_B_BYTES, hl, fcol, frow, &full_bar[stage]);
                     }
                     if (++stage == KC2_STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -388,13 +417,13 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
     } else if (warp == 1) {
         // ================= MMA issuer: leader CTA only =================
         if (rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_tf32(256, 256);
+            constexpr uint32_t idesc = F16 ? umma_idesc_f16(256, 256) : umma_idesc_tf32(256, 256);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (int item = pair_id; item < total_items; item += n_clusters) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
-                for (int a = 0; a < 6; ++a) {
+                for (int a = 0; a < NATOM; ++a) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * KC2_STAGE_BYTES);
@@ -403,10 +432,18 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
-                        umma_tf32_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
-                        if (three_pass) {
-                            umma_tf32_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                            umma_tf32_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                        if (F16) {
+                            umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
+                            if (three_pass) {
+                                umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                                umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                            }
+                        } else {
+                            umma_tf32_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
+                            if (three_pass) {
+                                umma_tf32_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                                umma_tf32_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                            }
                         }
                     }
                     tc_commit_2sm(&empty_bar[stage]);
@@ -419,7 +456,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
     } else {
         // ================= epilogue (both CTAs): own TMEM (128 n rows x 256 frames) -> (+bias) -> global =================
         const int q = warp & 3;
-        const int chalf = (warp - 2) >> 2;
+        const int cpart = (warp - 2) >> 2;
         uint32_t acc = 0, acc_phase = 0;
         for (int item = pair_id; item < total_items; item += n_clusters) {
             const int blk = item / items_per_blk, r = item % items_per_blk;
@@ -427,34 +464,63 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             const int n = nt * 128 + q * 32 + lane;
             const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
             const float bv = bias[n];
+            const float inv = F16 ? (blk == 0 ? inv0 : (blk == 1 ? inv1 : inv2)) : 1.f;
             float* kern = kern_all + (size_t)blk * B * Tm * KCN;
-            int p = ft * 256 + chalf * 128;
+            // F16, blocks 1 and 2 (tensor-core LVC consumers): the predicted kernel w is written as fp16 pieces of w*S16_KERN straight
+            // into the SWIZZLE_128B smem image of the LVC B operand -- per (layer, tap) 64 rows (o) of 128 B = [32 i hi | 32 i lo],
+            // 16-byte chunk c at position c ^ (o & 7) -- in the SAME 24,576 bytes the fp32 image occupies.  Lane n holds element
+            // (l, k, o, i) and the 32 lanes of a warp the 32 i of one row.  The 64 biases per layer stay fp32.
+            const bool pieces = F16 && blk >= 1;
+            const int rem = n % KPL;
+            const bool is_w = rem < KK * LVC_OUT;          // warp-uniform: 6144 and KPL are multiples of 32
+            // two 16-bit stores per value (a warp covers the 64 contiguous bytes of the hi half and of the lo half of one row: full sectors)
+            int word = n, hw_hi = 0, hw_lo = 0;             // 32-bit word / 16-bit halfword indices inside the frame record
+            if (pieces && is_w) {
+                const int ko = rem >> 5, oo = ko & 63, ci = ((((rem >> 2) & 7) ^ (oo & 7)) << 2) + (rem & 3);
+                const int base = 2 * ((n - rem) + ko * 32) + (ci & 7);
+                hw_hi = base + (((ci >> 3) ^ (oo & 7)) << 3);
+                hw_lo = base + (((4 + (ci >> 3)) ^ (oo & 7)) << 3);
+            }
+            const float inv_s = inv * S16_KERN, bv_s = bv * S16_KERN;
+            auto put = [&](float* rec, float accv) {        // rec = this frame's record (KCN words)
+                if (pieces && is_w) {
+                    const float sv = fmaf(accv, inv_s, bv_s);
+                    uint16_t h16, l16;
+                    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h16) : "f"(sv));
+                    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l16) : "f"(sv - f16_bits_to_float(h16)));
+                    reinterpret_cast<uint16_t*>(rec)[hw_hi] = h16;
+                    reinterpret_cast<uint16_t*>(rec)[hw_lo] = l16;
+                } else {
+                    rec[word] = F16 ? fmaf(accv, inv, bv) : accv + bv;
+                }
+            };
+            int p = ft * 256 + cpart * CPW;
             int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
-            const bool fast = (fp >= 1) && (fp + 127 <= Tm) && (p + 127 < M);
+            const bool fast = (fp >= 1) && (fp + CPW - 1 <= Tm) && (p + CPW - 1 < M);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + chalf * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * CPW;
             if (fast) {
-                float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN + n;
+                float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN;
 #pragma unroll 1
-                for (int c0 = 0; c0 < 128; c0 += 32) {
+                for (int c0 = 0; c0 < CPW; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c0, v);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) o[(size_t)j * KCN] = __uint_as_float(v[j]) + bv;
+                    for (int j = 0; j < 32; ++j) put(o + (size_t)j * KCN, __uint_as_float(v[j]));
                     o += (size_t)32 * KCN;
                 }
             } else {
 #pragma unroll 1
-                for (int c0 = 0; c0 < 128; c0 += 32) {
+                for (int c0 = 0; c0 < CPW; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c0, v);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (p < M && fp >= 1 && fp <= Tm)
-                            kern[((size_t)bb * Tm + (fp - 1)) * KCN + n] = __uint_as_float(v[j]) + bv;
+                        if (p < M && fp >= 1 && fp <= Tm)    // uniform across the warp (depends on the column only)
+                            put(kern + ((size_t)bb * Tm + (fp - 1)) * KCN, __uint_as_float(v[j]));
                         ++p;
                         if (++fp == Tm + 2) { fp = 0; ++bb; }
                     }
@@ -487,6 +553,8 @@ struct TcState {
     const float* blob = nullptr;
     uint64_t sec_off[FD_S_COUNT];
     CUtensorMap w_hi[NBLK], w_lo[NBLK];
+    CUtensorMap w16_hi[NBLK], w16_lo[NBLK];   // fp16 pieces (LBn_KCT_F16): rows of 96 fp32-sized elements = 192 fp16
+    float scales16[64];                       // host copy of section SCALES16
     int kc_2cta = 1;       // kernel_conv GEMM on CTA pairs (cta_group::2, default); option "kc_2cta" = 0 selects the 1-CTA kernel
     int lvc_swizzle = 0;   // LVC operand tiles: 0 = no-swizzle panels, 1 = SWIZZLE_128B + base_offset, 2 = SWIZZLE_128B, base_offset 0
     bool ok = false;
@@ -527,6 +595,14 @@ static inline int tc_init(void** state, int device, const float* blob, const uin
         if (tc_make_map_2d(s, &s->w_hi[n], blob + sec_off[FD_S_LB0_KCT_HI + n * FD_LB_STRIDE], KCK, KCN, KCK * 4, KCG_KATOM, KCG_BM, err)) return -3;
         if (tc_make_map_2d(s, &s->w_lo[n], blob + sec_off[FD_S_LB0_KCT_LO + n * FD_LB_STRIDE], KCK, KCN, KCK * 4, KCG_KATOM, KCG_BM, err)) return -3;
     }
+    for (int n = 0; n < NBLK; ++n) {
+        const float* w16 = blob + sec_off[FD_S_LB0_KCT_F16 + n];
+        if (tc_make_map_2d(s, &s->w16_hi[n], w16, KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
+        if (tc_make_map_2d(s, &s->w16_lo[n], w16 + (size_t)KCN * (KCK / 2), KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
+    }
+    if (cudaMemcpy(s->scales16, blob + sec_off[FD_S_SCALES16], sizeof s->scales16, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        err = "reading SCALES16 failed"; return -3;
+    }
     if (cudaFuncSetAttribute(k_kc_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KCG_SMEM_BYTES) != cudaSuccess ||
         tc_set_lvc_attrs() != cudaSuccess) {
         err = "cudaFuncSetAttribute(tensor-core kernels) failed"; return -3;
@@ -548,6 +624,23 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         if (tc_make_map_2d(s, &maps.h_lo[n], hk_lo + (size_t)n * rows * HID, HID, rows, HID * 4, KCG_KATOM, KCG_BN, err)) return -3;
     }
     const int M = B * (Tm + 2) - 2;
+    if (mode == FD_MODE_TC_3XF16) {   // fp16 pieces: hk rows are 64 fp16 = 32 fp32-sized elements = one 128-byte k-atom
+        for (int n = 0; n < NBLK; ++n) {
+            maps.w_hi[n] = s->w16_hi[n]; maps.w_lo[n] = s->w16_lo[n];
+            if (tc_make_map_2d(s, &maps.h_hi[n], hk_hi + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128, err)) return -3;
+            if (tc_make_map_2d(s, &maps.h_lo[n], hk_lo + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128, err)) return -3;
+        }
+        const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
+        int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
+        float inv[NBLK];
+        for (int n = 0; n < NBLK; ++n) inv[n] = 1.f / (s->scales16[n] * S16_HK);
+        k_kc_gemm_tc2<true, 16><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                                  s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2]);
+        cudaError_t e2 = cudaGetLastError();
+        if (e2 != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc2<f16> failed: ") + cudaGetErrorString(e2); return -3; }
+        ++*launches;
+        return 0;
+    }
     if (s->kc_2cta) {
         for (int n = 0; n < NBLK; ++n) {   // frame boxes of 128 rows: each CTA of a pair loads half of the 256-frame tile
             if (tc_make_map_2d(s, &maps.h_hi[n], hk_hi + (size_t)n * rows * HID, HID, rows, HID * 4, KCG_KATOM, 128, err)) return -3;
@@ -555,8 +648,8 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         }
         const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
         int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
-        k_kc_gemm_tc2<<<2 * clusters, 320, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
-                                                            s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, mode == 1 ? 1 : 0);
+        k_kc_gemm_tc2<false, 8><<<2 * clusters, 320, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                                   s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, mode == 1 ? 1 : 0, 1.f, 1.f, 1.f);
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc2 failed: ") + cudaGetErrorString(e2); return -3; }
         ++*launches;
@@ -1058,6 +1151,366 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K11+K12+K13, mode tc_3xf16: the same LVC layer on kind::f16 MMAs over fp16 PIECES (hi | lo) of power-of-two prescaled
+// operands.  Same tile walk, tap-as-shifted-start trick, one-tile-ahead bulk prefetch and two independent 8-warp groups per CTA
+// as k_lvc_layer_tc above; what changes:
+//   * one operand row = 128 B = [32 channels hi | 32 channels lo] (fp16; 16-byte chunk c at position c ^ (row & 7)), so an
+//     operand tile is HALF the bytes of the tf32 hi + lo pair and the three passes of a tap are the K-slices
+//       (hi,hi): A + {0,32} x B + {0,32}     (hi,lo): A + {0,32} x B + {64,96}     (lo,hi): A + {64,96} x B + {0,32}
+//     -> 6 MMAs of K = 16 per tap instead of 12 of K = 8;
+//   * the predicted kernels arrive from the kernel_conv GEMM already as pieces in this layout: no split phase, no lo half-tile;
+//   * the raw x rows are transformed in place to pieces (8 lanes per row: LDS.128 -> STS.64 hi + STS.64 lo);
+//   * block 2 keeps xs = x + first_conv(audio) (fp32) of the 128 output rows in smem for the gate epilogue instead of recomputing
+//     it (7 FMA per channel) and re-reading x from global;
+//   * all 8 warps of a group take part in the conv epilogue (2 per TMEM lane quarter, 16 channels each) and the two extra conv
+//     rows are split over 192 threads (one tap each) while the MMAs run;
+//   * sigmoid(a) * tanh(b) = (1 - E) / ((1 + e^-a)(1 + E)), E = e^-2b: two ex2 and ONE rcp per gate.
+// Scales: A pieces hold v*S16_ACT, conv weights w*S (per tensor, SCALES16), predicted kernels w*S16_KERN; the epilogues multiply
+// the accumulators by inv_c = 1/(S16_ACT*S) and inv_l = 1/(S16_ACT*S16_KERN).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LH_A_BYTES = 24576;                    // 192 rows x 128 B
+constexpr int LH_XS_BYTES = 16384;                   // 128 rows x 128 B fp32 (SKIP_FIRST)
+constexpr int LH_LW_BYTES = 24576;                   // per frame: 3 taps x 64 rows x 128 B
+constexpr int LH_CW_BYTES = 3 * C * 128;             // 12288
+template <int HOP, bool SKIP_FIRST>
+__host__ __device__ constexpr int lh_slot_bytes() { return LH_A_BYTES + (SKIP_FIRST ? LH_XS_BYTES : LH_A_BYTES) + lt_nf<HOP>() * LH_LW_BYTES; }
+constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C) * 4 + 2 * 3 * 64 * 4 + 128;   // conv W, first_w, first_b, conv_b, halo partials, barriers + tmem ptr
+template <int HOP, bool SKIP_FIRST, int GROUPS>
+constexpr int lh_smem_bytes() { return GROUPS * (lh_slot_bytes<HOP, SKIP_FIRST>() + lt_small_bytes<HOP>()) + LH_SHARED_BYTES + 1024; }
+
+struct LvcHParams {
+    const float* cw16;                           // [3 taps][32 co][128 B] SWIZZLE_128B image of this layer's dilated conv (LBn_CONV_F16)
+    const float* conv_b;                         // [32]
+    const float* first_w; const float* first_b;  // [7][32], [32]   (SKIP_FIRST)
+};
+
+// 4 floats -> fp16 pieces of v*S16_ACT: hi (4 halves in a uint2), lo likewise
+__device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo) {
+    const float sx = v.x * S16_ACT, sy = v.y * S16_ACT, sz = v.z * S16_ACT, sw = v.w * S16_ACT;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(sy), "f"(sx));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(sw), "f"(sz));
+    const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo.x) : "f"(sy - h01.y), "f"(sx - h01.x));
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo.y) : "f"(sw - h23.y), "f"(sz - h23.x));
+}
+// sigmoid(a) * tanh(b) with two ex2 and one rcp; b clamped to +-15 (tanh is +-1 to fp32 precision beyond 9.01) so E stays finite
+__device__ __forceinline__ float gate_st(float a, float b) {
+    const float bc = fminf(fmaxf(b, -15.f), 15.f);
+    const float E = exp2f(-2.8853900817779268f * bc), A = exp2f(-1.4426950408889634f * a);
+    return __fdividef(1.f - E, (1.f + A) * (1.f + E));
+}
+
+template <int HOP, bool SKIP_FIRST, int GROUPS>
+__global__ void __launch_bounds__(256 * GROUPS, 1)
+k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
+              float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l) {
+    constexpr int NF = lt_nf<HOP>();
+    constexpr int GT = 256;                   // threads per group (8 warps)
+    constexpr int SLOT = lh_slot_bytes<HOP, SKIP_FIRST>();
+    constexpr int SMALL = lt_small_bytes<HOP>();
+    constexpr int S_OFF = LH_A_BYTES;                                              // raw skip rows (block 1) | xs rows (block 2)
+    constexpr int LW_OFF = LH_A_BYTES + (SKIP_FIRST ? LH_XS_BYTES : LH_A_BYTES);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* cw = smem + GROUPS * SLOT;                 // [3 taps][32 rows][128 B]
+    unsigned char* small0 = cw + LH_CW_BYTES;                 // [GROUPS][2 buffers][lbias NF*64 | audio LT_AU]
+    float* fw_s = (float*)(small0 + GROUPS * SMALL);          // [7][32]
+    float* fb_s = fw_s + 7 * C;                               // [32]
+    float* cb_s = fb_s + C;                                   // [32]
+    float* hp_s = cb_s + C;                                   // [GROUPS][3 taps][64]: partial sums of the two extra conv rows
+    uint64_t* bars = (uint64_t*)(hp_s + 2 * 3 * 64);          // [GROUPS][4]: conv MMAs, LVC MMAs, loads, (pad)
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 8);
+
+    const int tid = threadIdx.x, g = tid / GT, gt = tid % GT, gw = gt >> 5, lane = tid & 31;
+    unsigned char* slot = smem + g * SLOT;
+    unsigned char* a_t = slot;                                // A tile (raw x rows on arrival) | later: Y tile
+    unsigned char* s_t = slot + S_OFF;
+    unsigned char* lw = slot + LW_OFF;
+    unsigned char* small = small0 + g * SMALL;
+    float* hp = hp_s + g * 3 * 64;
+    uint64_t* bar = bars + 4 * g;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4 * GROUPS; ++i) mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.cw16);
+        for (int i = tid; i < LH_CW_BYTES / 16; i += GT * GROUPS) reinterpret_cast<float4*>(cw)[i] = src[i];
+        if (tid < 7 * C) fw_s[tid] = SKIP_FIRST ? p.first_w[tid] : 0.f;
+        if (tid < C) { fb_s[tid] = SKIP_FIRST ? p.first_b[tid] : 0.f; cb_s[tid] = p.conv_b[tid]; }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // TMEM columns of a group (256 apart): conv [0,32); LVC frame fi at [32 + 64 fi, +64)
+    const uint32_t tmem_base = *tmem_base_s + g * 256;
+    constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 64);
+
+    const int c4 = gt & 7;   // this thread's channel quad in the A transform
+    float fwr[7][4], fbr[4];
+    if (SKIP_FIRST) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) fwr[k][q] = fw_s[k * C + c4 * 4 + q];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) fbr[q] = fb_s[c4 * 4 + q];
+    }
+    const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
+    const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * SLOT);
+    const uint32_t cw_u = smem_u32(cw);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+
+    const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt, tstride = gridDim.x * GROUPS;
+    const int r_lo = 27 - dil, r_hi = 157 + dil;   // A rows ar <-> t = t0 - 28 + ar that the 130 conv outputs touch
+
+    auto issue_loads = [&](int tile, int buf) {
+        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+        float* lbias = (float*)(small + buf * (SMALL / 2));
+        float* au = lbias + NF * 64;
+        const int ar0 = max(r_lo, 28 - t0), ar1 = min(r_hi, T - t0 + 28);
+        const int i0 = max(0, 32 - t0), i1 = min(LT_AU, T - t0 + 32);
+        uint32_t bytes = 0;
+        if (ar1 > ar0) bytes += (uint32_t)(ar1 - ar0) * 128u * (SKIP_FIRST ? 1u : 2u);
+        if (SKIP_FIRST && i1 > i0) bytes += (uint32_t)(i1 - i0) * 4u;
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) bytes += LH_LW_BYTES + 256;
+        mbar_expect_tx(&bar[2], bytes);
+        if (ar1 > ar0) {
+            const size_t off = ((size_t)b * T + (t0 - 28 + ar0)) * C;
+            bulk_g2s(a_t + ar0 * 128, x_in + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
+            if (!SKIP_FIRST) bulk_g2s(s_t + ar0 * 128, skip + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
+        }
+        if (SKIP_FIRST && i1 > i0) bulk_g2s(au + i0, skip + (size_t)b * T + (t0 - 32 + i0), (uint32_t)(i1 - i0) * 4u, &bar[2]);
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) {
+            const int f = t0 / HOP + fi;
+            if (f < Tm) {
+                const float* src = kern + ((size_t)b * Tm + f) * KCN;
+                bulk_g2s(lw + fi * LH_LW_BYTES, src, LH_LW_BYTES, &bar[2]);       // 3 taps x 64 rows x 128 B of pieces, ready to use
+                bulk_g2s(lbias + fi * 64, src + KK * LVC_OUT, 256, &bar[2]);
+            }
+        }
+    };
+
+    int tile = blockIdx.x * GROUPS + g;
+    if (tile < total && gw_u == 0) { if (elect_one()) issue_loads(tile, 0); __syncwarp(); }
+    uint32_t parity = 0;
+    for (; tile < total; tile += tstride, parity ^= 1) {
+        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+        const float* lbias = (const float*)(small + parity * (SMALL / 2));
+        float* au_s = (float*)lbias + NF * 64;
+        // ---------------- phase 1: raw rows (bulk-copied one tile ago) -> fp16 pieces, in place ----------------
+        mbar_wait(&bar[2], parity);
+        if (SKIP_FIRST) {   // audio positions outside [0,T) are zero (the first conv zero-pads)
+            if (gt < LT_AU) { const int pos = t0 - 32 + gt; if (pos < 0 || pos >= T) au_s[gt] = 0.f; }
+            group_sync(1 + g, GT);
+        }
+#pragma unroll
+        for (int i = 0; i < 1536 / GT; ++i) {
+            const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
+            const bool active = ar < r_hi;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), pre = v;
+            if (active && t >= 0 && t < T) {
+                const float4 xv = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
+                float4 sk;
+                if (SKIP_FIRST) {
+                    sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const float a = au_s[ar + k + 1];
+                        sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
+                        sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
+                    }
+                } else {
+                    sk = *reinterpret_cast<const float4*>(s_t + ar * 128 + c4 * 16);
+                }
+                pre = make_float4(xv.x + sk.x, xv.y + sk.y, xv.z + sk.z, xv.w + sk.w);
+                v.x = lrelu(pre.x, 0.2f); v.y = lrelu(pre.y, 0.2f); v.z = lrelu(pre.z, 0.2f); v.w = lrelu(pre.w, 0.2f);
+            }
+            uint2 hi, lo;
+            split4_f16(v, hi, lo);
+            __syncwarp();   // every lane of the row has read its raw chunk before any lane overwrites the row
+            if (active) {
+                const int sw = ar & 7;
+                *reinterpret_cast<uint2*>(a_t + ar * 128 + (((c4 >> 1) ^ sw) << 4) + (c4 & 1) * 8) = hi;
+                *reinterpret_cast<uint2*>(a_t + ar * 128 + (((4 + (c4 >> 1)) ^ sw) << 4) + (c4 & 1) * 8) = lo;
+                if (SKIP_FIRST && ar >= 28 && ar < 28 + LT_TT)   // xs of output row r = ar - 28, chunk c4 at position c4 ^ (r & 7)
+                    *reinterpret_cast<float4*>(s_t + (ar - 28) * 128 + ((c4 ^ ((ar - 28) & 7)) << 4)) = pre;
+            }
+        }
+        fence_async_smem();
+        group_sync(1 + g, GT);
+        // ---------------- phase 2: dilated conv on tensor cores (+ the 2 extra rows on FFMA meanwhile) ----------------
+        if (gw_u == 0) {
+            tc_fence_after();
+            uint32_t slot_t = slot_u, cw_t = cw_u;
+            asm volatile("" : "+r"(slot_t), "+r"(cw_t));   // opaque per tile: keeps ptxas from hoisting the descriptors out of the tile loop
+            if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t sh = (uint32_t)(27 + (k - 1) * dil) * 128u;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t dah = umma_desc_sw128(slot_t + sh + j * 32), dal = umma_desc_sw128(slot_t + sh + 64 + j * 32);
+                        const uint64_t dbh = umma_desc_sw128(cw_t + k * 4096 + j * 32), dbl = umma_desc_sw128(cw_t + k * 4096 + 64 + j * 32);
+                        umma_f16(tmem_u, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
+                        umma_f16(tmem_u, dah, dbl, idesc_conv, 1u);
+                        umma_f16(tmem_u, dal, dbh, idesc_conv, 1u);
+                    }
+                }
+                tc_commit(&bar[0]);
+            }
+            __syncwarp();
+        }
+        if (gt < 192) {   // conv outputs yr = 128, 129 (LVC taps of the last rows): thread = (tap k, row, co), partial sum over 32 ci
+            const int o64 = gt & 63, k = gt >> 6, yr = 128 + (o64 >> 5), co = o64 & 31;
+            const int ar = yr + 27 + (k - 1) * dil;
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint4 ah = *reinterpret_cast<const uint4*>(a_t + ar * 128 + ((c ^ (ar & 7)) << 4));
+                const uint4 al = *reinterpret_cast<const uint4*>(a_t + ar * 128 + (((4 + c) ^ (ar & 7)) << 4));
+                const uint4 wh = *reinterpret_cast<const uint4*>(cw + k * 4096 + co * 128 + ((c ^ (co & 7)) << 4));
+                const uint4 wl = *reinterpret_cast<const uint4*>(cw + k * 4096 + co * 128 + (((4 + c) ^ (co & 7)) << 4));
+                const uint32_t ahv[4] = {ah.x, ah.y, ah.z, ah.w}, alv[4] = {al.x, al.y, al.z, al.w};
+                const uint32_t whv[4] = {wh.x, wh.y, wh.z, wh.w}, wlv[4] = {wl.x, wl.y, wl.z, wl.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&ahv[e])), a2 = __half22float2(*reinterpret_cast<const __half2*>(&alv[e]));
+                    const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&whv[e])), w2 = __half22float2(*reinterpret_cast<const __half2*>(&wlv[e]));
+                    acc = fmaf(a1.x + a2.x, w1.x + w2.x, acc);
+                    acc = fmaf(a1.y + a2.y, w1.y + w2.y, acc);
+                }
+            }
+            hp[k * 64 + o64] = acc;
+        }
+        // ---------------- phase 3: y = lrelu(conv + b) -> fp16 pieces, rows of the Y tile (over the A tile) ----------------
+        mbar_wait(&bar[0], parity);
+        tc_fence_after();
+        group_sync(1 + g, GT);   // Y aliases A: the partial-sum threads have finished READING A; hp is visible
+        {
+            const int q3 = gw & 3, part3 = gw >> 2;   // lane quarter / which 16 of the 32 conv channels
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q3 * 32) << 16) + part3 * 16, v);
+            tmem_ld_wait();
+            const int yr = q3 * 32 + lane, t = t0 - 1 + yr;
+            const bool in = (t >= 0 && t < T);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                float4 y0, y1;
+                const int cb0 = part3 * 16 + cc * 8;
+                y0.x = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 0]), inv_c, cb_s[cb0 + 0]), 0.2f) : 0.f;
+                y0.y = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 1]), inv_c, cb_s[cb0 + 1]), 0.2f) : 0.f;
+                y0.z = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 2]), inv_c, cb_s[cb0 + 2]), 0.2f) : 0.f;
+                y0.w = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 3]), inv_c, cb_s[cb0 + 3]), 0.2f) : 0.f;
+                y1.x = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 4]), inv_c, cb_s[cb0 + 4]), 0.2f) : 0.f;
+                y1.y = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 5]), inv_c, cb_s[cb0 + 5]), 0.2f) : 0.f;
+                y1.z = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 6]), inv_c, cb_s[cb0 + 6]), 0.2f) : 0.f;
+                y1.w = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 7]), inv_c, cb_s[cb0 + 7]), 0.2f) : 0.f;
+                uint2 h0, l0, h1, l1;
+                split4_f16(y0, h0, l0);
+                split4_f16(y1, h1, l1);
+                const int chunk = part3 * 2 + cc, sw = yr & 7;
+                *reinterpret_cast<uint4*>(a_t + yr * 128 + ((chunk ^ sw) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<uint4*>(a_t + yr * 128 + (((4 + chunk) ^ sw) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
+            if (gt < 64) {   // rows 128, 129
+                const int yr2 = 128 + (gt >> 5), co = gt & 31, t2 = t0 - 1 + yr2;
+                const float accv = hp[gt] + hp[64 + gt] + hp[128 + gt];
+                const float y = (t2 >= 0 && t2 < T) ? lrelu(fmaf(accv, inv_c, cb_s[co]), 0.2f) : 0.f;
+                uint16_t h16, l16;
+                f16_split(y, S16_ACT, h16, l16);
+                *reinterpret_cast<uint16_t*>(a_t + yr2 * 128 + (((co >> 3) ^ (yr2 & 7)) << 4) + (co & 7) * 2) = h16;
+                *reinterpret_cast<uint16_t*>(a_t + yr2 * 128 + (((4 + (co >> 3)) ^ (yr2 & 7)) << 4) + (co & 7) * 2) = l16;
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        group_sync(1 + g, GT);
+        // ---------------- phase 4: location-variable conv on tensor cores ----------------
+        if (gw_u == 0) {
+            tc_fence_after();
+            uint32_t slot_t = slot_u;
+            asm volatile("" : "+r"(slot_t));
+            if (elect_one()) {
+#pragma unroll
+                for (int fi = 0; fi < NF; ++fi) {
+                    const uint32_t d = tmem_u + 32 + fi * 64;
+                    const uint32_t lwb = slot_t + LW_OFF + fi * LH_LW_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint64_t dah = umma_desc_sw128(slot_t + k * 128 + j * 32), dal = umma_desc_sw128(slot_t + k * 128 + 64 + j * 32);
+                            const uint64_t dbh = umma_desc_sw128(lwb + k * 8192 + j * 32), dbl = umma_desc_sw128(lwb + k * 8192 + 64 + j * 32);
+                            umma_f16(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
+                            umma_f16(d, dah, dbl, idesc_lvc, 1u);
+                            umma_f16(d, dal, dbh, idesc_lvc, 1u);
+                        }
+                    }
+                }
+                tc_commit(&bar[1]);
+            }
+            __syncwarp();
+        }
+        // ---------------- phase 5: gate + residual -> global ----------------
+        {
+            const int q = gw & 3, part = gw >> 2;              // lane quarter / which 16 of the 32 gate channels
+            const int r = q * 32 + lane, t = t0 + r;
+            const int fi = (HOP >= LT_TT) ? 0 : r / HOP;       // warp-uniform (HOP is a multiple of 32)
+            const size_t row = ((size_t)b * T + (t < T ? t : 0)) * C + part * 16;
+            float4 xs[4];                                      // residual base
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (SKIP_FIRST) {
+                    xs[c] = *reinterpret_cast<const float4*>(s_t + r * 128 + (((part * 4 + c) ^ (r & 7)) << 4));
+                } else {
+                    xs[c] = *reinterpret_cast<const float4*>(x_in + row + c * 4);
+                    const float4 sk = *reinterpret_cast<const float4*>(skip + row + c * 4);
+                    xs[c].x += sk.x; xs[c].y += sk.y; xs[c].z += sk.z; xs[c].w += sk.w;
+                }
+            }
+            mbar_wait(&bar[1], parity);
+            tc_fence_after();
+            // LVC MMAs complete: the A/Y tile and the kernels are free -> fetch the next tile while this one is gated
+            if (gw_u == 0 && tile + tstride < total) { if (elect_one()) issue_loads(tile + tstride, (int)(parity ^ 1)); __syncwarp(); }
+            uint32_t zs[16], zt[16];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 32 + fi * 64 + part * 16;
+            tmem_ld_32x32b_x16(ta, zs);
+            tmem_ld_32x32b_x16(ta + 32, zt);
+            tmem_ld_wait();
+            if (t < T) {
+                const float* lb = lbias + fi * 64 + part * 16;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 o4;
+                    o4.x = xs[c].x + gate_st(fmaf(__uint_as_float(zs[c * 4 + 0]), inv_l, lb[c * 4 + 0]), fmaf(__uint_as_float(zt[c * 4 + 0]), inv_l, lb[32 + c * 4 + 0]));
+                    o4.y = xs[c].y + gate_st(fmaf(__uint_as_float(zs[c * 4 + 1]), inv_l, lb[c * 4 + 1]), fmaf(__uint_as_float(zt[c * 4 + 1]), inv_l, lb[32 + c * 4 + 1]));
+                    o4.z = xs[c].z + gate_st(fmaf(__uint_as_float(zs[c * 4 + 2]), inv_l, lb[c * 4 + 2]), fmaf(__uint_as_float(zt[c * 4 + 2]), inv_l, lb[32 + c * 4 + 2]));
+                    o4.w = xs[c].w + gate_st(fmaf(__uint_as_float(zs[c * 4 + 3]), inv_l, lb[c * 4 + 3]), fmaf(__uint_as_float(zt[c * 4 + 3]), inv_l, lb[32 + c * 4 + 3]));
+                    *reinterpret_cast<float4*>(x_out + row + c * 4) = o4;
+                }
+            }
+        }
+        tc_fence_before();
+        group_sync(1 + g, GT);   // the group's TMEM columns, xs rows and partial sums are free for its next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K3+K4  first_audio_conv + DiffusionDBlock 0 on tensor cores (FastDiff_model.py:89, modules.py:127-138):
 //   xs[o] = first_conv(audio)[4 o]  (evaluated only at the kept positions);
 //   out = conv_d4(lrelu(conv_d2(lrelu(conv_d1(lrelu(xs)))))) + W1x1 xs + b
@@ -1438,6 +1891,22 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (blk == 0) return 0;   // hop 8: stays on the SIMT kernel
+    if (mode == FD_MODE_TC_3XF16) {
+        LvcHParams hp;
+        hp.cw16 = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16] + (size_t)layer * (LH_CW_BYTES / 4);
+        hp.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + blk * FD_LB_STRIDE] + layer * C;
+        hp.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
+        hp.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
+        const float inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * blk + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
+        const int tiles = B * ((T + LT_TT - 1) / LT_TT), pairs = (tiles + 1) / 2, grid = pairs < s->sm_count ? pairs : s->sm_count;
+        if (blk == 1) k_lvc_layer_h<64, false, 2><<<grid, 512, lh_smem_bytes<64, false, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l);
+        else          k_lvc_layer_h<256, true, 2><<<grid, 512, lh_smem_bytes<256, true, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_h failed: ") + cudaGetErrorString(e); return -3; }
+        ++*launches;
+        *done = true;
+        return 0;
+    }
     LvcTcParams p;
     p.cw_hi = s->blob + s->sec_off[FD_S_LB0_CONVT_HI + blk * FD_LB_STRIDE] + (size_t)layer * 3 * 8 * C * 4;
     p.cw_lo = s->blob + s->sec_off[FD_S_LB0_CONVT_LO + blk * FD_LB_STRIDE] + (size_t)layer * 3 * 8 * C * 4;
@@ -1445,7 +1914,7 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
     p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
     const int total = B * ((T + LT_TT - 1) / LT_TT);
-    const int tp = mode == 1 ? 1 : 0;
+    const int tp = mode != FD_MODE_TC_TF32 ? 1 : 0;
     if (blk == 1) {
         const int grid = total < s->sm_count ? total : s->sm_count;
         k_lvc_layer_tc<64, false, 1, 16><<<grid, 512, lt_smem_bytes<64, 1>(), st>>>(p, x_in, skip, kern, x_out, B, T, Tm, dil, tp);
@@ -1471,10 +1940,10 @@ static inline int tc_upsample(void* state, int mode, int blk, const float* in, f
     const int total = B * ((Tin + 127) / 128);
     if (blk == 1) {
         const int grid = total < s->sm_count ? total : s->sm_count;
-        k_upsample_tc<8><<<grid, 512, ut_smem_bytes<8>(), st>>>(wh, wl, bias, in, out, B, Tin, mode == 1 ? 1 : 0);
+        k_upsample_tc<8><<<grid, 512, ut_smem_bytes<8>(), st>>>(wh, wl, bias, in, out, B, Tin, mode != FD_MODE_TC_TF32 ? 1 : 0);
     } else {
         const int grid = total < 2 * s->sm_count ? total : 2 * s->sm_count;
-        k_upsample_tc<4><<<grid, 512, ut_smem_bytes<4>(), st>>>(wh, wl, bias, in, out, B, Tin, mode == 1 ? 1 : 0);
+        k_upsample_tc<4><<<grid, 512, ut_smem_bytes<4>(), st>>>(wh, wl, bias, in, out, B, Tin, mode != FD_MODE_TC_TF32 ? 1 : 0);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_upsample_tc failed: ") + cudaGetErrorString(e); return -3; }
@@ -1494,7 +1963,7 @@ static inline int tc_dblock0(void* state, int mode, const float* audio, float* d
     p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];    p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
     const int To = L / 4, total = B * ((To + DT_VALID - 1) / DT_VALID);
     const int grid = total < s->sm_count ? total : s->sm_count;
-    k_dblock0_tc<<<grid, 512, DT_SMEM_BYTES, st>>>(p, audio, d0, B, L, To, mode == 1 ? 1 : 0);
+    k_dblock0_tc<<<grid, 512, DT_SMEM_BYTES, st>>>(p, audio, d0, B, L, To, mode != FD_MODE_TC_TF32 ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_dblock0_tc failed: ") + cudaGetErrorString(e); return -3; }
     ++*launches;
@@ -1504,11 +1973,17 @@ static inline int tc_dblock0(void* state, int mode, const float* audio, float* d
 static inline cudaError_t tc_set_lvc_attrs() {
     cudaError_t e0 = cudaFuncSetAttribute(k_dblock0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
     if (e0 != cudaSuccess) return e0;
-    e0 = cudaFuncSetAttribute(k_kc_gemm_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
+    e0 = cudaFuncSetAttribute(k_kc_gemm_tc2<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_upsample_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<4>());
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_upsample_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<8>());
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_lvc_layer_h<64, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lh_smem_bytes<64, false, 2>());
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_lvc_layer_h<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lh_smem_bytes<256, true, 2>());
     if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());

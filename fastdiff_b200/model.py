@@ -104,7 +104,7 @@ class FastDiff(nn.Module):
         # device-side state
         self._engine: Optional[Engine] = None
         self._packed_version = None
-        self.mode = None          # None -> library default; or "fp32_simt" | "tc_3xtf32" | "tc_tf32"
+        self.mode = None          # None -> library default (tc_3xf16); or "fp32_simt" | "tc_3xtf32" | "tc_tf32" | "tc_3xf16"
         self.noise_mode = "reference"  # sampler: "reference" (CPU generator, reference order) | "device" (Philox)
         self.seed = 0
         self._lib_path = None     # tests point this at the CPU emulation build

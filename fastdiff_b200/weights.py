@@ -76,6 +76,30 @@ def tf32_split(x: np.ndarray):
     return hi, lo
 
 
+def f16_scale(x: np.ndarray) -> float:
+    """Per-tensor power-of-two prescale S with max|x|*S in (8192, 16384] (fd_blob.h, SCALES16)."""
+    m = float(np.max(np.abs(x)))
+    if not np.isfinite(m) or m == 0.0:
+        return 1.0
+    return float(2.0 ** np.floor(np.log2(16384.0 / m)))
+
+
+def f16_split(x: np.ndarray, scale: float):
+    """x*scale = hi + lo as fp16 pieces (round to nearest even, saturating) -> two uint16 arrays.
+    Same arithmetic as fd::f16_split in csrc/fd_common.cuh."""
+    s = np.clip(np.ascontiguousarray(x, dtype=np.float32) * np.float32(scale), -65504.0, 65504.0).astype(np.float32)
+    hi = s.astype(np.float16)
+    lo = (s - hi.astype(np.float32)).astype(np.float16)
+    return hi.view(np.uint16), lo.view(np.uint16)
+
+
+def _u16_as_f32(u: np.ndarray) -> torch.Tensor:
+    """uint16 array (even element count) -> fp32 tensor holding the same bytes (two fp16 per blob element)."""
+    u = np.ascontiguousarray(u, dtype=np.uint16).reshape(-1)
+    assert u.size % 2 == 0
+    return torch.from_numpy(u.view(np.float32).copy())
+
+
 # swizzle gather indices: output[o, p] = input[o, p ^ (o & 7)]  (XOR is an involution, so the same table scatters and gathers)
 _SWZ_O = torch.arange(LVC_OUT).reshape(LVC_OUT, 1).expand(LVC_OUT, 8)
 _SWZ_SRC = torch.arange(8).reshape(1, 8) ^ (torch.arange(LVC_OUT).reshape(LVC_OUT, 1) & 7)
@@ -161,6 +185,29 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         uw = uw.reshape(uw.shape[0], C, 8, 4)[:, _SWZ_O[:C], _SWZ_SRC[:C], :].contiguous()
         hi, lo = tf32_split(uw.numpy())
         S[f"LB{n}_UPT_HI"], S[f"LB{n}_UPT_LO"] = torch.from_numpy(hi), torch.from_numpy(lo)
+    # ---- fp16-piece operands (mode tc_3xf16) ----
+    scales = np.zeros(64, dtype=np.float32)
+    conv16 = {}
+    for n in range(3):
+        kct = S[f"LB{n}_KC_W"].t().contiguous().numpy()                                 # [24832][192], K-major rows
+        sc = f16_scale(kct)
+        scales[n] = sc
+        hi, lo = f16_split(kct, sc)
+        S[f"LB{n}_KCT_F16"] = _u16_as_f32(np.stack([hi, lo]))
+    for n in (1, 2):
+        cw = torch.stack([W[f"lvc_blocks.{n}.convs.{i}.weight"] for i in range(LAYERS)]).numpy()   # [l][co][ci][k]
+        rows = np.zeros((LAYERS, KS, C, 8, 8), dtype=np.uint16)                          # [l][k][co][chunk position][8 fp16]
+        for l in range(LAYERS):
+            sc = f16_scale(cw[l])
+            scales[4 + 4 * n + l] = sc
+            hi, lo = f16_split(cw[l], sc)                                                # [co][ci][k]
+            both = np.concatenate([hi, lo], axis=1).transpose(2, 0, 1).reshape(KS, C, 8, 8)   # [k][co][chunk c][8]: chunks 0-3 hi, 4-7 lo
+            for co in range(C):
+                for c in range(8):
+                    rows[l, :, co, c ^ (co & 7), :] = both[:, co, c, :]
+        conv16[n] = _u16_as_f32(rows)
+    S["LB1_CONV_F16"], S["LB2_CONV_F16"] = conv16[1], conv16[2]
+    S["SCALES16"] = torch.from_numpy(scales)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}
 

@@ -74,7 +74,10 @@ typedef struct fd_step {
 typedef enum fd_mode {
     FD_MODE_FP32_SIMT = 0,   /* fp32 FFMA everywhere (strict; the on-device cross-check path) */
     FD_MODE_TC_3XTF32 = 1,   /* tcgen05 kind::tf32 with hi/lo error compensation (fp32-level) */
-    FD_MODE_TC_TF32 = 2      /* tcgen05 kind::tf32 single pass (fast mode; error reported separately) */
+    FD_MODE_TC_TF32 = 2,     /* tcgen05 kind::tf32 single pass (fast mode; error reported separately) */
+    FD_MODE_TC_3XF16 = 3     /* tcgen05 kind::f16 on fp16 hi/lo pieces of power-of-two prescaled operands, 3 passes, fp32
+                                accumulation: the same 22 significant bits per operand as 3xTF32 at twice the MMA rate
+                                (fp32-level; operands saturate at |v*S| = 65504).  Default after load. */
 } fd_mode;
 
 /* Build a sampler/denoiser for `device`.  Stands behind FastDiff.__init__

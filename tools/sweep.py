@@ -84,7 +84,7 @@ def main():
         assert torch.isfinite(x).all()
         return ms, n_exec, sps, tf
 
-    mode = {0: "fp32_simt", 1: "tc_3xtf32", 2: "tc_tf32"}[eng.get_mode()]
+    mode = {0: "fp32_simt", 1: "tc_3xtf32", 2: "tc_tf32", 3: "tc_3xf16"}[eng.get_mode()]
     print(f"# sweep on {torch.cuda.get_device_name(0)}, arithmetic mode {mode}, peak = {peak} TFLOP/s (MEASURED_PEAKS bf16 sustained)\n")
     print("| config | B | T' (s) | N (executed) | ms / call | ms / reverse step | audio samples/s | algorithmic TFLOP/s | frac of bf16 peak |")
     print("|---|---|---|---|---|---|---|---|---|")
