@@ -241,6 +241,9 @@ def run_ours(args):
         eng.set_mode(args.mode)
         if net is not None:
             net.mode = args.mode
+    for kv in args.opt:
+        key, val = kv.split("=")
+        eng.set_option(key, int(val))
     mode_name = {0: "fp32_simt", 1: "tc_3xtf32", 2: "tc_tf32", 3: "tc_3xf16"}[eng.get_mode()]
 
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
@@ -411,6 +414,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--frames", type=int, default=861)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--opt", action="append", default=[], help="library tuning option key=value (fd_set_option), repeatable")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -265,6 +265,8 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "kc_2cta")) { tc_set_kc_2cta(h->tc_state, (int)value); return FD_OK; }
+    if (!strcmp(key, "lvc_groups")) { tc_set_lvc_groups(h->tc_state, (int)value); return FD_OK; }
+    if (!strcmp(key, "lvc_exp")) { tc_set_lvc_exp(h->tc_state, (int)value); return FD_OK; }
 #endif
     return fail(h, FD_ERR_INVALID, "fd_set_option: unknown key '%s'", key);
 }

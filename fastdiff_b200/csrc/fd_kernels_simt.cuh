@@ -35,13 +35,15 @@ __global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __res
     __syncthreads();
     {
         float acc = p.b1[j];
-        for (int i = 0; i < EMB_IN; ++i) acc = fmaf(s_in[i], p.w1t[i * EMB_MID + j], acc);
+#pragma unroll 16
+        for (int i = 0; i < EMB_IN; ++i) acc = fmaf(s_in[i], __ldg(p.w1t + i * EMB_MID + j), acc);   // 16 independent loads in flight, same summation order
         s_mid[j] = acc * sigmoidf_(acc);
     }
     __syncthreads();
     {
         float acc = p.b2[j];
-        for (int i = 0; i < EMB_MID; ++i) acc = fmaf(s_mid[i], p.w2t[i * EMB_OUT + j], acc);
+#pragma unroll 16
+        for (int i = 0; i < EMB_MID; ++i) acc = fmaf(s_mid[i], __ldg(p.w2t + i * EMB_OUT + j), acc);
         acc = acc * sigmoidf_(acc);
         s_out[j] = acc;
         emb[b * EMB_OUT + j] = acc;
@@ -51,7 +53,8 @@ __global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __res
         const int blk = j / COND, c = j % COND;
         const float* w = FD_SEL3(p.fct_wt, blk);
         float acc = FD_SEL3(p.fct_b, blk)[c];
-        for (int i = 0; i < EMB_OUT; ++i) acc = fmaf(s_out[i], w[i * COND + c], acc);
+#pragma unroll 16
+        for (int i = 0; i < EMB_OUT; ++i) acc = fmaf(s_out[i], __ldg(w + i * COND + c), acc);
         cnoise[(blk * B + b) * COND + c] = acc;
     }
 }

@@ -366,7 +366,8 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
     uint64_t* tempty_bar = tfull_bar + 2;          // [2]       (leader's copy) epilogue warps of both CTAs -> leader MMA
     uint32_t* tmem_base_s = (uint32_t*)(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index broadcast from lane 0: the role branches below are then provably warp-uniform for ptxas (uniform registers stay usable)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int M = B * (Tm + 2) - 2;
     const int f_tiles = (M + 255) / 256;
@@ -482,34 +483,48 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                 hw_lo = base + (((4 + (ci >> 3)) ^ (oo & 7)) << 3);
             }
             const float inv_s = inv * S16_KERN, bv_s = bv * S16_KERN;
-            auto put = [&](float* rec, float accv) {        // rec = this frame's record (KCN words)
-                if (pieces && is_w) {
-                    const float sv = fmaf(accv, inv_s, bv_s);
-                    uint16_t h16, l16;
-                    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h16) : "f"(sv));
-                    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l16) : "f"(sv - f16_bits_to_float(h16)));
-                    reinterpret_cast<uint16_t*>(rec)[hw_hi] = h16;
-                    reinterpret_cast<uint16_t*>(rec)[hw_lo] = l16;
-                } else {
-                    rec[word] = F16 ? fmaf(accv, inv, bv) : accv + bv;
-                }
+            // warp-uniform; broadcast from lane 0 so that ptxas KNOWS it (otherwise every store below re-materialises its uniform
+            // memory descriptor with two R2UR: 40% of the epilogue's instructions)
+            const bool as_pieces = __shfl_sync(0xffffffffu, (int)(pieces && is_w), 0) != 0;
+            auto put_pieces = [&](uint16_t* ph, uint16_t* pl, float accv) {
+                const float sv = fmaf(accv, inv_s, bv_s);
+                uint16_t h16, l16;
+                asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h16) : "f"(sv));
+                asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l16) : "f"(sv - f16_bits_to_float(h16)));
+                *ph = h16;
+                *pl = l16;
             };
             int p = ft * 256 + cpart * CPW;
             int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
-            const bool fast = (fp >= 1) && (fp + CPW - 1 <= Tm) && (p + CPW - 1 < M);
+            const bool fast = __shfl_sync(0xffffffffu, (int)((fp >= 1) && (fp + CPW - 1 <= Tm) && (p + CPW - 1 < M)), 0) != 0;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * CPW;
             if (fast) {
-                float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN;
+                float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN;   // record of this warp's first frame; frames are KCN words apart
+                if (as_pieces) {
+                    uint16_t* ph = reinterpret_cast<uint16_t*>(o) + hw_hi;
+                    uint16_t* pl = reinterpret_cast<uint16_t*>(o) + hw_lo;
 #pragma unroll 1
-                for (int c0 = 0; c0 < CPW; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + c0, v);
-                    tmem_ld_wait();
+                    for (int c0 = 0; c0 < CPW; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + c0, v);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) put(o + (size_t)j * KCN, __uint_as_float(v[j]));
-                    o += (size_t)32 * KCN;
+                        for (int j = 0; j < 32; ++j) put_pieces(ph + (size_t)j * (2 * KCN), pl + (size_t)j * (2 * KCN), __uint_as_float(v[j]));
+                        ph += (size_t)64 * KCN; pl += (size_t)64 * KCN;
+                    }
+                } else {
+                    o += word;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < CPW; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + c0, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[(size_t)j * KCN] = F16 ? fmaf(__uint_as_float(v[j]), inv, bv) : __uint_as_float(v[j]) + bv;
+                        o += (size_t)32 * KCN;
+                    }
                 }
             } else {
 #pragma unroll 1
@@ -519,8 +534,11 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        if (p < M && fp >= 1 && fp <= Tm)    // uniform across the warp (depends on the column only)
-                            put(kern + ((size_t)bb * Tm + (fp - 1)) * KCN, __uint_as_float(v[j]));
+                        if (p < M && fp >= 1 && fp <= Tm) {   // uniform across the warp (depends on the column only)
+                            float* rec = kern + ((size_t)bb * Tm + (fp - 1)) * KCN;
+                            if (as_pieces) put_pieces(reinterpret_cast<uint16_t*>(rec) + hw_hi, reinterpret_cast<uint16_t*>(rec) + hw_lo, __uint_as_float(v[j]));
+                            else rec[word] = F16 ? fmaf(__uint_as_float(v[j]), inv, bv) : __uint_as_float(v[j]) + bv;
+                        }
                         ++p;
                         if (++fp == Tm + 2) { fp = 0; ++bb; }
                     }
@@ -556,6 +574,8 @@ struct TcState {
     CUtensorMap w16_hi[NBLK], w16_lo[NBLK];   // fp16 pieces (LBn_KCT_F16): rows of 96 fp32-sized elements = 192 fp16
     float scales16[64];                       // host copy of section SCALES16
     int kc_2cta = 1;       // kernel_conv GEMM on CTA pairs (cta_group::2, default); option "kc_2cta" = 0 selects the 1-CTA kernel
+    int lvc_exp = 0;       // timing experiments only (option "lvc_exp"): 1 = no second conv pass, 2 / 4 = hi*hi only in the LVC / conv (WRONG results)
+    int lvc_groups = 2;    // tc_3xf16, block 2: independent 8-warp groups per CTA (2 or 3; option "lvc_groups")
     int lvc_swizzle = 0;   // LVC operand tiles: 0 = no-swizzle panels, 1 = SWIZZLE_128B + base_offset, 2 = SWIZZLE_128B, base_offset 0
     bool ok = false;
 };
@@ -577,6 +597,8 @@ static inline void tc_destroy(void* st) { delete (TcState*)st; }
 static inline bool tc_available(void* st) { return st && ((TcState*)st)->ok; }
 static inline void tc_set_lvc_swizzle(void* st, int v) { if (st) ((TcState*)st)->lvc_swizzle = v; }
 static inline void tc_set_kc_2cta(void* st, int v) { if (st) ((TcState*)st)->kc_2cta = v; }
+static inline void tc_set_lvc_groups(void* st, int v) { if (st) ((TcState*)st)->lvc_groups = v; }
+static inline void tc_set_lvc_exp(void* st, int v) { if (st) ((TcState*)st)->lvc_exp = v; }
 
 static inline int tc_init(void** state, int device, const float* blob, const uint64_t* sec_off, std::string& err) {
     tc_destroy(*state);
@@ -1162,8 +1184,9 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
 //   * the raw x rows are transformed in place to pieces (8 lanes per row: LDS.128 -> STS.64 hi + STS.64 lo);
 //   * block 2 keeps xs = x + first_conv(audio) (fp32) of the 128 output rows in smem for the gate epilogue instead of recomputing
 //     it (7 FMA per channel) and re-reading x from global;
-//   * all 8 warps of a group take part in the conv epilogue (2 per TMEM lane quarter, 16 channels each) and the two extra conv
-//     rows are split over 192 threads (one tap each) while the MMAs run;
+//   * all 8 warps of a group take part in the conv epilogue (2 per TMEM lane quarter, 16 channels each); the two extra conv rows
+//     (yr = 128, 129) come from a second MMA pass over A rows +128 whose rows 0, 1 are read back -- no FFMA side path, and every
+//     conv output is produced by the same instruction sequence whatever the tiling (batch-composition independent bits);
 //   * sigmoid(a) * tanh(b) = (1 - E) / ((1 + e^-a)(1 + E)), E = e^-2b: two ex2 and ONE rcp per gate.
 // Scales: A pieces hold v*S16_ACT, conv weights w*S (per tensor, SCALES16), predicted kernels w*S16_KERN; the epilogues multiply
 // the accumulators by inv_c = 1/(S16_ACT*S) and inv_l = 1/(S16_ACT*S16_KERN).
@@ -1174,7 +1197,7 @@ constexpr int LH_LW_BYTES = 24576;                   // per frame: 3 taps x 64 r
 constexpr int LH_CW_BYTES = 3 * C * 128;             // 12288
 template <int HOP, bool SKIP_FIRST>
 __host__ __device__ constexpr int lh_slot_bytes() { return LH_A_BYTES + (SKIP_FIRST ? LH_XS_BYTES : LH_A_BYTES) + lt_nf<HOP>() * LH_LW_BYTES; }
-constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C) * 4 + 2 * 3 * 64 * 4 + 128;   // conv W, first_w, first_b, conv_b, halo partials, barriers + tmem ptr
+constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C) * 4 + 3 * 3 * 64 * 4 + 192;   // conv W, first_w, first_b, conv_b, barriers + tmem ptr
 template <int HOP, bool SKIP_FIRST, int GROUPS>
 constexpr int lh_smem_bytes() { return GROUPS * (lh_slot_bytes<HOP, SKIP_FIRST>() + lt_small_bytes<HOP>()) + LH_SHARED_BYTES + 1024; }
 
@@ -1194,16 +1217,33 @@ __device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo)
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo.y) : "f"(sw - h23.y), "f"(sz - h23.x));
 }
 // sigmoid(a) * tanh(b) with two ex2 and one rcp; b clamped to +-15 (tanh is +-1 to fp32 precision beyond 9.01) so E stays finite
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#ifndef LH_TWOPASS
+#define LH_TWOPASS 1
+#endif
+#ifndef LH_GATE_ASM
+#define LH_GATE_ASM 1
+#endif
+#ifndef LH_HALO_MMA
+#define LH_HALO_MMA 0   // 1: the two extra conv rows from a second MMA pass; 0: FFMA partial sums on warps 2-7 while the MMAs run (faster: measured)
+#endif
 __device__ __forceinline__ float gate_st(float a, float b) {
     const float bc = fminf(fmaxf(b, -15.f), 15.f);
-    const float E = exp2f(-2.8853900817779268f * bc), A = exp2f(-1.4426950408889634f * a);
-    return __fdividef(1.f - E, (1.f + A) * (1.f + E));
+#if !LH_GATE_ASM
+    const float E2 = exp2f(-2.8853900817779268f * bc), A2 = exp2f(-1.4426950408889634f * a);
+    return __fdividef(1.f - E2, (1.f + A2) * (1.f + E2));
+#endif
+    const float E = ex2_approx(-2.8853900817779268f * bc), A = ex2_approx(-1.4426950408889634f * a);   // A = +inf for a << 0 -> result 0
+    return (1.f - E) * rcp_approx((1.f + A) * (1.f + E));
 }
+// leaky ReLU with slope 0.2 as max(v, 0.2 v): two instructions instead of compare + multiply + select
+__device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }
 
 template <int HOP, bool SKIP_FIRST, int GROUPS>
 __global__ void __launch_bounds__(256 * GROUPS, 1)
 k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
-              float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l) {
+              float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l, int exp_mask) {
     constexpr int NF = lt_nf<HOP>();
     constexpr int GT = 256;                   // threads per group (8 warps)
     constexpr int SLOT = lh_slot_bytes<HOP, SKIP_FIRST>();
@@ -1217,9 +1257,9 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     float* fw_s = (float*)(small0 + GROUPS * SMALL);          // [7][32]
     float* fb_s = fw_s + 7 * C;                               // [32]
     float* cb_s = fb_s + C;                                   // [32]
-    float* hp_s = cb_s + C;                                   // [GROUPS][3 taps][64]: partial sums of the two extra conv rows
-    uint64_t* bars = (uint64_t*)(hp_s + 2 * 3 * 64);          // [GROUPS][4]: conv MMAs, LVC MMAs, loads, (pad)
-    uint32_t* tmem_base_s = (uint32_t*)(bars + 8);
+    float* hp_s = cb_s + C;                                   // [GROUPS][3 taps][64]: partial sums of the two extra conv rows (LH_HALO_MMA == 0)
+    uint64_t* bars = (uint64_t*)(hp_s + GROUPS * 3 * 64);     // [GROUPS][4]: conv MMAs, LVC MMAs, loads, (pad)
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 4 * GROUPS);
 
     const int tid = threadIdx.x, g = tid / GT, gt = tid % GT, gw = gt >> 5, lane = tid & 31;
     unsigned char* slot = smem + g * SLOT;
@@ -1227,8 +1267,8 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     unsigned char* s_t = slot + S_OFF;
     unsigned char* lw = slot + LW_OFF;
     unsigned char* small = small0 + g * SMALL;
-    float* hp = hp_s + g * 3 * 64;
     uint64_t* bar = bars + 4 * g;
+    float* hp = hp_s + g * 3 * 64;
 
     if (tid == 0) {
         for (int i = 0; i < 4 * GROUPS; ++i) mbar_init(&bars[i], 1);
@@ -1248,20 +1288,14 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // TMEM columns of a group (256 apart): conv [0,32); LVC frame fi at [32 + 64 fi, +64)
-    const uint32_t tmem_base = *tmem_base_s + g * 256;
+    // TMEM columns of a group (256 apart): conv [0,32); LVC frame fi at [32 + 64 fi, +64); second conv pass (rows +128) after them
+    constexpr uint32_t D2_COL = 32 + NF * 64;
+    constexpr uint32_t TSTRIDE = (D2_COL + 32 <= 128) ? 128 : 256;
+    static_assert(GROUPS * TSTRIDE <= 512, "TMEM columns");
+    const uint32_t tmem_base = *tmem_base_s + g * TSTRIDE;
     constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 64);
 
     const int c4 = gt & 7;   // this thread's channel quad in the A transform
-    float fwr[7][4], fbr[4];
-    if (SKIP_FIRST) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k)
-#pragma unroll
-            for (int q = 0; q < 4; ++q) fwr[k][q] = fw_s[k * C + c4 * 4 + q];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) fbr[q] = fb_s[c4 * 4 + q];
-    }
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
     const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * SLOT);
     const uint32_t cw_u = smem_u32(cw);
@@ -1301,52 +1335,135 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
 
     int tile = blockIdx.x * GROUPS + g;
     if (tile < total && gw_u == 0) { if (elect_one()) issue_loads(tile, 0); __syncwarp(); }
+#ifdef FD_LVC_TIMELINE
+    const bool stamp = (blockIdx.x == 0 && tid == 0 && HOP == 256);
+    int tile_no = -1;
+#endif
     uint32_t parity = 0;
+    int b = tile / ntt, tt = tile % ntt;                       // maintained incrementally (no per-tile division)
+    const int bstep = tstride / ntt, ttstep = tstride % ntt;
     for (; tile < total; tile += tstride, parity ^= 1) {
-        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+#ifdef FD_LVC_TIMELINE
+        ++tile_no;
+#endif
+        LT_STAMP(0);
+        const int t0 = tt * LT_TT;
         const float* lbias = (const float*)(small + parity * (SMALL / 2));
         float* au_s = (float*)lbias + NF * 64;
         // ---------------- phase 1: raw rows (bulk-copied one tile ago) -> fp16 pieces, in place ----------------
         mbar_wait(&bar[2], parity);
+        LT_STAMP(1);
         if (SKIP_FIRST) {   // audio positions outside [0,T) are zero (the first conv zero-pads)
             if (gt < LT_AU) { const int pos = t0 - 32 + gt; if (pos < 0 || pos >= T) au_s[gt] = 0.f; }
             group_sync(1 + g, GT);
         }
+        LT_STAMP(2);
+#if !LH_TWOPASS
+        {
+            float fwr[7][4], fbr[4];
+            if (SKIP_FIRST) {
 #pragma unroll
-        for (int i = 0; i < 1536 / GT; ++i) {
-            const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
-            const bool active = ar < r_hi;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), pre = v;
-            if (active && t >= 0 && t < T) {
-                const float4 xv = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
-                float4 sk;
-                if (SKIP_FIRST) {
-                    sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) {
-                        const float a = au_s[ar + k + 1];
-                        sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
-                        sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
-                    }
-                } else {
-                    sk = *reinterpret_cast<const float4*>(s_t + ar * 128 + c4 * 16);
+                for (int k = 0; k < 7; ++k) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(fw_s + k * C + c4 * 4);
+                    fwr[k][0] = w4.x; fwr[k][1] = w4.y; fwr[k][2] = w4.z; fwr[k][3] = w4.w;
                 }
-                pre = make_float4(xv.x + sk.x, xv.y + sk.y, xv.z + sk.z, xv.w + sk.w);
-                v.x = lrelu(pre.x, 0.2f); v.y = lrelu(pre.y, 0.2f); v.z = lrelu(pre.z, 0.2f); v.w = lrelu(pre.w, 0.2f);
+                const float4 b4 = *reinterpret_cast<const float4*>(fb_s + c4 * 4);
+                fbr[0] = b4.x; fbr[1] = b4.y; fbr[2] = b4.z; fbr[3] = b4.w;
             }
-            uint2 hi, lo;
-            split4_f16(v, hi, lo);
-            __syncwarp();   // every lane of the row has read its raw chunk before any lane overwrites the row
-            if (active) {
-                const int sw = ar & 7;
-                *reinterpret_cast<uint2*>(a_t + ar * 128 + (((c4 >> 1) ^ sw) << 4) + (c4 & 1) * 8) = hi;
-                *reinterpret_cast<uint2*>(a_t + ar * 128 + (((4 + (c4 >> 1)) ^ sw) << 4) + (c4 & 1) * 8) = lo;
-                if (SKIP_FIRST && ar >= 28 && ar < 28 + LT_TT)   // xs of output row r = ar - 28, chunk c4 at position c4 ^ (r & 7)
-                    *reinterpret_cast<float4*>(s_t + (ar - 28) * 128 + ((c4 ^ ((ar - 28) & 7)) << 4)) = pre;
+#pragma unroll
+            for (int i = 0; i < 1536 / GT; ++i) {
+                const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
+                const bool active = ar < r_hi;
+                float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active && t >= 0 && t < T) {
+                    const float4 xv = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
+                    float4 sk;
+                    if (SKIP_FIRST) {
+                        sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) {
+                            const float a = au_s[ar + k + 1];
+                            sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
+                            sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
+                        }
+                    } else {
+                        sk = *reinterpret_cast<const float4*>(s_t + ar * 128 + c4 * 16);
+                    }
+                    pre = make_float4(xv.x + sk.x, xv.y + sk.y, xv.z + sk.z, xv.w + sk.w);
+                }
+                const float4 v = make_float4(lrelu02(pre.x), lrelu02(pre.y), lrelu02(pre.z), lrelu02(pre.w));
+                uint2 hi, lo;
+                split4_f16(v, hi, lo);
+                __syncwarp();   // every lane of the row has read its raw chunk before any lane overwrites the row
+                if (active) {
+                    const int sw = ar & 7;
+                    *reinterpret_cast<uint2*>(a_t + ar * 128 + (((c4 >> 1) ^ sw) << 4) + (c4 & 1) * 8) = hi;
+                    *reinterpret_cast<uint2*>(a_t + ar * 128 + (((4 + (c4 >> 1)) ^ sw) << 4) + (c4 & 1) * 8) = lo;
+                    if (SKIP_FIRST && ar >= 28 && ar < 28 + LT_TT)
+                        *reinterpret_cast<float4*>(s_t + (ar - 28) * 128 + ((c4 ^ ((ar - 28) & 7)) << 4)) = pre;
+                }
             }
         }
+#else
+        {   // pass 1: every thread pulls its 6 (row, channel quad) items into registers; one __syncwarp; pass 2: transform + store
+            float fwr[7][4], fbr[4];   // first-conv taps of this thread's channel quad: live in this phase only (reloaded per tile)
+            if (SKIP_FIRST) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(fw_s + k * C + c4 * 4);
+                    fwr[k][0] = w4.x; fwr[k][1] = w4.y; fwr[k][2] = w4.z; fwr[k][3] = w4.w;
+                }
+                const float4 b4 = *reinterpret_cast<const float4*>(fb_s + c4 * 4);
+                fbr[0] = b4.x; fbr[1] = b4.y; fbr[2] = b4.z; fbr[3] = b4.w;
+            }
+            float4 xv[1536 / GT], sv[1536 / GT];
+#pragma unroll
+            for (int i = 0; i < 1536 / GT; ++i) {
+                const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
+                xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); sv[i] = xv[i];
+                if (ar < r_hi && t >= 0 && t < T) {
+                    xv[i] = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
+                    if (!SKIP_FIRST) sv[i] = *reinterpret_cast<const float4*>(s_t + ar * 128 + c4 * 16);
+                }
+            }
+            __syncwarp();   // the 8 lanes of a row sit in one warp: every raw chunk has been read before any row is overwritten
+#pragma unroll
+            for (int i = 0; i < 1536 / GT; ++i) {
+                const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
+                const bool active = ar < r_hi;
+                float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active && t >= 0 && t < T) {
+                    float4 sk;
+                    if (SKIP_FIRST) {
+                        sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) {
+                            const float a = au_s[ar + k + 1];
+                            sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
+                            sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
+                        }
+                    } else {
+                        sk = sv[i];
+                    }
+                    pre = make_float4(xv[i].x + sk.x, xv[i].y + sk.y, xv[i].z + sk.z, xv[i].w + sk.w);
+                }
+                const float4 v = make_float4(lrelu02(pre.x), lrelu02(pre.y), lrelu02(pre.z), lrelu02(pre.w));
+                uint2 hi, lo;
+                split4_f16(v, hi, lo);
+                if (active) {
+                    const int sw = ar & 7;
+                    *reinterpret_cast<uint2*>(a_t + ar * 128 + (((c4 >> 1) ^ sw) << 4) + (c4 & 1) * 8) = hi;
+                    *reinterpret_cast<uint2*>(a_t + ar * 128 + (((4 + (c4 >> 1)) ^ sw) << 4) + (c4 & 1) * 8) = lo;
+                    if (SKIP_FIRST && ar >= 28 && ar < 28 + LT_TT)   // xs of output row r = ar - 28, chunk c4 at position c4 ^ (r & 7)
+                        *reinterpret_cast<float4*>(s_t + (ar - 28) * 128 + ((c4 ^ ((ar - 28) & 7)) << 4)) = pre;
+                }
+            }
+        }
+#endif
+        LT_STAMP(3);
         fence_async_smem();
         group_sync(1 + g, GT);
+        LT_STAMP(4);
         // ---------------- phase 2: dilated conv on tensor cores (+ the 2 extra rows on FFMA meanwhile) ----------------
         if (gw_u == 0) {
             tc_fence_after();
@@ -1361,16 +1478,34 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                         const uint64_t dah = umma_desc_sw128(slot_t + sh + j * 32), dal = umma_desc_sw128(slot_t + sh + 64 + j * 32);
                         const uint64_t dbh = umma_desc_sw128(cw_t + k * 4096 + j * 32), dbl = umma_desc_sw128(cw_t + k * 4096 + 64 + j * 32);
                         umma_f16(tmem_u, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
-                        umma_f16(tmem_u, dah, dbl, idesc_conv, 1u);
-                        umma_f16(tmem_u, dal, dbh, idesc_conv, 1u);
+                        if (!(exp_mask & 4)) {
+                            umma_f16(tmem_u, dah, dbl, idesc_conv, 1u);
+                            umma_f16(tmem_u, dal, dbh, idesc_conv, 1u);
+                        }
+                    }
+                }
+                // second pass over A rows +128: its output rows 0 and 1 are the conv rows yr = 128, 129 that the LVC taps of the last
+                // output rows need.  The other 126 rows read past the A tile (whatever bytes follow it in this slot) and are never used.
+                if (LH_HALO_MMA && !(exp_mask & 1))
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t sh = (uint32_t)(128 + 27 + (k - 1) * dil) * 128u;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t dah = umma_desc_sw128(slot_t + sh + j * 32), dal = umma_desc_sw128(slot_t + sh + 64 + j * 32);
+                        const uint64_t dbh = umma_desc_sw128(cw_t + k * 4096 + j * 32), dbl = umma_desc_sw128(cw_t + k * 4096 + 64 + j * 32);
+                        umma_f16(tmem_u + D2_COL, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
+                        umma_f16(tmem_u + D2_COL, dah, dbl, idesc_conv, 1u);
+                        umma_f16(tmem_u + D2_COL, dal, dbh, idesc_conv, 1u);
                     }
                 }
                 tc_commit(&bar[0]);
             }
             __syncwarp();
         }
-        if (gt < 192) {   // conv outputs yr = 128, 129 (LVC taps of the last rows): thread = (tap k, row, co), partial sum over 32 ci
-            const int o64 = gt & 63, k = gt >> 6, yr = 128 + (o64 >> 5), co = o64 & 31;
+#if !LH_HALO_MMA
+        if (gt >= 64) {   // conv outputs yr = 128, 129 on FFMA while the MMAs run (warps 2-7: not the issuing warp): thread = (tap, row, co)
+            const int h = gt - 64, o64 = h & 63, k = h >> 6, yr = 128 + (o64 >> 5), co = o64 & 31;
             const int ar = yr + 27 + (k - 1) * dil;
             float acc = 0.f;
 #pragma unroll
@@ -1391,49 +1526,67 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             }
             hp[k * 64 + o64] = acc;
         }
+#endif
         // ---------------- phase 3: y = lrelu(conv + b) -> fp16 pieces, rows of the Y tile (over the A tile) ----------------
+        LT_STAMP(5);
         mbar_wait(&bar[0], parity);
         tc_fence_after();
+        LT_STAMP(6);
+#if !LH_HALO_MMA
         group_sync(1 + g, GT);   // Y aliases A: the partial-sum threads have finished READING A; hp is visible
+#endif
         {
             const int q3 = gw & 3, part3 = gw >> 2;   // lane quarter / which 16 of the 32 conv channels
+            // 16 accumulator columns of row yr -> y = lrelu(acc*inv_c + b) -> fp16 pieces -> the row's hi and lo chunks
+            auto emit_row = [&](const uint32_t (&v)[16], int yr) {
+                const int t = t0 - 1 + yr;
+                const bool in = (t >= 0 && t < T);
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    float4 y0, y1;
+                    const int cb0 = part3 * 16 + cc * 8;
+                    y0.x = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 0]), inv_c, cb_s[cb0 + 0])) : 0.f;
+                    y0.y = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 1]), inv_c, cb_s[cb0 + 1])) : 0.f;
+                    y0.z = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 2]), inv_c, cb_s[cb0 + 2])) : 0.f;
+                    y0.w = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 3]), inv_c, cb_s[cb0 + 3])) : 0.f;
+                    y1.x = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 4]), inv_c, cb_s[cb0 + 4])) : 0.f;
+                    y1.y = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 5]), inv_c, cb_s[cb0 + 5])) : 0.f;
+                    y1.z = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 6]), inv_c, cb_s[cb0 + 6])) : 0.f;
+                    y1.w = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 7]), inv_c, cb_s[cb0 + 7])) : 0.f;
+                    uint2 h0, l0, h1, l1;
+                    split4_f16(y0, h0, l0);
+                    split4_f16(y1, h1, l1);
+                    const int chunk = part3 * 2 + cc, sw = yr & 7;
+                    *reinterpret_cast<uint4*>(a_t + yr * 128 + ((chunk ^ sw) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                    *reinterpret_cast<uint4*>(a_t + yr * 128 + (((4 + chunk) ^ sw) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                }
+            };
             uint32_t v[16];
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q3 * 32) << 16) + part3 * 16, v);
             tmem_ld_wait();
-            const int yr = q3 * 32 + lane, t = t0 - 1 + yr;
-            const bool in = (t >= 0 && t < T);
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                float4 y0, y1;
-                const int cb0 = part3 * 16 + cc * 8;
-                y0.x = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 0]), inv_c, cb_s[cb0 + 0]), 0.2f) : 0.f;
-                y0.y = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 1]), inv_c, cb_s[cb0 + 1]), 0.2f) : 0.f;
-                y0.z = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 2]), inv_c, cb_s[cb0 + 2]), 0.2f) : 0.f;
-                y0.w = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 3]), inv_c, cb_s[cb0 + 3]), 0.2f) : 0.f;
-                y1.x = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 4]), inv_c, cb_s[cb0 + 4]), 0.2f) : 0.f;
-                y1.y = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 5]), inv_c, cb_s[cb0 + 5]), 0.2f) : 0.f;
-                y1.z = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 6]), inv_c, cb_s[cb0 + 6]), 0.2f) : 0.f;
-                y1.w = in ? lrelu(fmaf(__uint_as_float(v[cc * 8 + 7]), inv_c, cb_s[cb0 + 7]), 0.2f) : 0.f;
-                uint2 h0, l0, h1, l1;
-                split4_f16(y0, h0, l0);
-                split4_f16(y1, h1, l1);
-                const int chunk = part3 * 2 + cc, sw = yr & 7;
-                *reinterpret_cast<uint4*>(a_t + yr * 128 + ((chunk ^ sw) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-                *reinterpret_cast<uint4*>(a_t + yr * 128 + (((4 + chunk) ^ sw) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            emit_row(v, q3 * 32 + lane);
+#if LH_HALO_MMA
+            if (q3 == 0) {   // rows 128, 129 = rows 0, 1 of the second pass (TMEM lanes 0, 1)
+                tmem_ld_32x32b_x16(tmem_base + D2_COL + part3 * 16, v);
+                tmem_ld_wait();
+                if (lane < 2) emit_row(v, 128 + lane);
             }
-            if (gt < 64) {   // rows 128, 129
+#else
+            if (gt < 64) {   // rows 128, 129 from the FFMA partial sums
                 const int yr2 = 128 + (gt >> 5), co = gt & 31, t2 = t0 - 1 + yr2;
                 const float accv = hp[gt] + hp[64 + gt] + hp[128 + gt];
-                const float y = (t2 >= 0 && t2 < T) ? lrelu(fmaf(accv, inv_c, cb_s[co]), 0.2f) : 0.f;
+                const float y = (t2 >= 0 && t2 < T) ? lrelu02(fmaf(accv, inv_c, cb_s[co])) : 0.f;
                 uint16_t h16, l16;
                 f16_split(y, S16_ACT, h16, l16);
                 *reinterpret_cast<uint16_t*>(a_t + yr2 * 128 + (((co >> 3) ^ (yr2 & 7)) << 4) + (co & 7) * 2) = h16;
                 *reinterpret_cast<uint16_t*>(a_t + yr2 * 128 + (((4 + (co >> 3)) ^ (yr2 & 7)) << 4) + (co & 7) * 2) = l16;
             }
+#endif
         }
         fence_async_smem();
         tc_fence_before();
         group_sync(1 + g, GT);
+        LT_STAMP(7);
         // ---------------- phase 4: location-variable conv on tensor cores ----------------
         if (gw_u == 0) {
             tc_fence_after();
@@ -1451,8 +1604,10 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                             const uint64_t dah = umma_desc_sw128(slot_t + k * 128 + j * 32), dal = umma_desc_sw128(slot_t + k * 128 + 64 + j * 32);
                             const uint64_t dbh = umma_desc_sw128(lwb + k * 8192 + j * 32), dbl = umma_desc_sw128(lwb + k * 8192 + 64 + j * 32);
                             umma_f16(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
-                            umma_f16(d, dah, dbl, idesc_lvc, 1u);
-                            umma_f16(d, dal, dbh, idesc_lvc, 1u);
+                            if (!(exp_mask & 2)) {
+                                umma_f16(d, dah, dbl, idesc_lvc, 1u);
+                                umma_f16(d, dal, dbh, idesc_lvc, 1u);
+                            }
                         }
                     }
                 }
@@ -1477,8 +1632,10 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                     xs[c].x += sk.x; xs[c].y += sk.y; xs[c].z += sk.z; xs[c].w += sk.w;
                 }
             }
+            LT_STAMP(8);
             mbar_wait(&bar[1], parity);
             tc_fence_after();
+            LT_STAMP(9);
             // LVC MMAs complete: the A/Y tile and the kernels are free -> fetch the next tile while this one is gated
             if (gw_u == 0 && tile + tstride < total) { if (elect_one()) issue_loads(tile + tstride, (int)(parity ^ 1)); __syncwarp(); }
             uint32_t zs[16], zt[16];
@@ -1500,7 +1657,9 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             }
         }
         tc_fence_before();
-        group_sync(1 + g, GT);   // the group's TMEM columns, xs rows and partial sums are free for its next tile
+        group_sync(1 + g, GT);   // the group's TMEM columns and xs rows are free for its next tile
+        b += bstep; tt += ttstep;
+        if (tt >= ntt) { tt -= ntt; ++b; }
     }
     tc_fence_before();
     __syncthreads();
@@ -1898,9 +2057,12 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
         hp.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
         hp.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
         const float inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * blk + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
-        const int tiles = B * ((T + LT_TT - 1) / LT_TT), pairs = (tiles + 1) / 2, grid = pairs < s->sm_count ? pairs : s->sm_count;
-        if (blk == 1) k_lvc_layer_h<64, false, 2><<<grid, 512, lh_smem_bytes<64, false, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l);
-        else          k_lvc_layer_h<256, true, 2><<<grid, 512, lh_smem_bytes<256, true, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l);
+        const int tiles = B * ((T + LT_TT - 1) / LT_TT);
+        const int ng = (blk == 2 && s->lvc_groups == 3) ? 3 : 2;
+        const int per = (tiles + ng - 1) / ng, grid = per < s->sm_count ? per : s->sm_count;
+        if (blk == 1)     k_lvc_layer_h<64, false, 2><<<grid, 512, lh_smem_bytes<64, false, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp);
+        else if (ng == 3) k_lvc_layer_h<256, true, 3><<<grid, 768, lh_smem_bytes<256, true, 3>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp);
+        else              k_lvc_layer_h<256, true, 2><<<grid, 512, lh_smem_bytes<256, true, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_h failed: ") + cudaGetErrorString(e); return -3; }
         ++*launches;
@@ -1984,6 +2146,8 @@ static inline cudaError_t tc_set_lvc_attrs() {
     e0 = cudaFuncSetAttribute(k_lvc_layer_h<64, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lh_smem_bytes<64, false, 2>());
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_lvc_layer_h<256, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lh_smem_bytes<256, true, 2>());
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_lvc_layer_h<256, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lh_smem_bytes<256, true, 3>());
     if (e0 != cudaSuccess) return e0;
     cudaError_t e = cudaFuncSetAttribute(k_lvc_layer_tc<64, false, 1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<64, 1>());
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());

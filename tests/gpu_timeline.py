@@ -8,7 +8,7 @@ x, mel = make_inputs(B,Tm,3); t = torch.full((B,1), 74.99)
 for _ in range(2): net((x.cuda(), mel.cuda(), t.cuda()))
 torch.cuda.synchronize()
 tl = net.engine().debug_read('lvc_timeline', B, Tm).cpu().reshape(-1)[:120].reshape(12,10)
-names = ['start','ld+lwsplit','ausync','Abuilt','sync','convIssued','convDone','Ywritten','lvcIssued','lvcDone']
+names = ['start','loadwait','ausync','Abuilt','sync','convIssued+halo','convDone','Ywritten','lvcIssued+xs','lvcDone']
 print('per-tile phase durations (cycles), group 0 of CTA 0, last LVC layer (dil 27) of block 2:')
 for i in range(12):
     d = [int(tl[i,j]-tl[i,j-1]) for j in range(1,10)]
