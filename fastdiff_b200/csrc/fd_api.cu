@@ -30,6 +30,7 @@ struct fd_handle {
     int stop_after = 99;
     int tc_upsample = 1;         // LVC-block upsample (blocks 1, 2) on tensor cores in the TC modes (option "tc_upsample")
     int tc_dblock = 1;           // DBlock 0 on tensor cores in the TC modes (option "tc_dblock")
+    int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
     int attrs_set = 0;
     uint64_t launches = 0;
     std::string err;
@@ -261,12 +262,14 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!h || !key) return FD_ERR_INVALID;
     if (!strcmp(key, "stop_after")) { h->stop_after = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_dblock")) { h->tc_dblock = (int)value; return FD_OK; }
+    if (!strcmp(key, "tc_kp")) { h->tc_kp = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_upsample")) { h->tc_upsample = (int)value; return FD_OK; }
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "kc_2cta")) { tc_set_kc_2cta(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "lvc_groups")) { tc_set_lvc_groups(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "lvc_exp")) { tc_set_lvc_exp(h->tc_state, (int)value); return FD_OK; }
+    if (!strcmp(key, "kc_exp")) { tc_set_kc_exp(h->tc_state, (int)value); return FD_OK; }
 #endif
     return fail(h, FD_ERR_INVALID, "fd_set_option: unknown key '%s'", key);
 }
@@ -360,9 +363,19 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             p.res_w[n] = sec(h, FD_S_LB0_KPRES_W + n * FD_LB_STRIDE); p.res_b[n] = sec(h, FD_S_LB0_KPRES_B + n * FD_LB_STRIDE);
         }
         ScopedTimer tm(h, KC_KP_HIDDEN, st);
+        bool kp_done = false;
+#ifndef FD_EMU
+        if (h->mode == FD_MODE_TC_3XF16 && h->tc_kp) {
+            int rc = tc_kp_hidden(h->tc_state, mel_dev, cnoise, hk, ws + w.hk_hi, ws + w.hk_lo, B, Tm, st, h->err, &h->launches);
+            if (rc) return rc;
+            kp_done = true;
+        }
+#endif
+        if (!kp_done) {
         FD_LAUNCH(k_kp_hidden, dim3((Tm + KP_FT - 1) / KP_FT, B, NBLK), dim3(256), KP_SMEM_BYTES, st, p, mel_dev, cnoise, hk, ws + w.hk_hi, ws + w.hk_lo, B, Tm,
                   h->mode == FD_MODE_TC_3XF16 ? 1 : 0);
         FD_CHECK_LAUNCH(h, "k_kp_hidden");
+        }
     }
     if (h->mode == FD_MODE_FP32_SIMT) {
         KcParams p;

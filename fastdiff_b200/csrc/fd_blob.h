@@ -44,13 +44,19 @@
  *   LBn_KCT_F16 [2 planes: hi, lo][24832 n][192 kk] fp16   the LBn_KCT matrix (K-major rows of 384 B: the tcgen05 A operand)
  *   LBn_CONV_F16 (n = 1, 2) [4 layers][3 k][32 co] rows of 128 B = [32 ci hi | 32 ci lo] fp16, the 16-byte chunk c (8 values) of
  *             row co stored at chunk position c ^ (co & 7): SWIZZLE_128B K-major B-operand tiles of the dilated convs
- *   SCALES16  [64]  S of: kernel_conv block n at [n]; lvc_blocks.n.convs.l at [4 + 4 n + l]
+ *   LBn_KPW_F16 [28 slots][16 KB]  kernel-predictor hidden stack as B-operand tiles in consumption order (tensor-core k_kp_hidden_tc):
+ *             a tile = 64 rows (co) x 128 B, 16-byte chunk c at position c ^ (co & 7).
+ *             slots 0..9  : input_conv taps j = 0..4, two slots per tap: {ci 0..63: hi tile 8 KB | lo tile 8 KB},
+ *                           {ci 64..79: one tile with rows [16 ci hi (32 B) | 16 ci lo (32 B) | 64 B zero], then 8 KB unused}
+ *             slots 10..27: residual convs l = 0..5, taps j = 0..2: {hi tile 8 KB | lo tile 8 KB} over the 64 input channels
+ *   SCALES16  [64]  S of: kernel_conv block n at [n]; lvc_blocks.n.convs.l at [4 + 4 n + l];
+ *                   kernel predictor of block n: input_conv at [16 + 8 n], residual conv l at [17 + 8 n + l]
  */
 #ifndef FD_BLOB_H
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 9ULL
+#define FD_BLOB_VERSION 10ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */
@@ -68,7 +74,8 @@
     X(LB2_KPIN_W) X(LB2_KPIN_B) X(LB2_KPRES_W) X(LB2_KPRES_B) X(LB2_KC_W) X(LB2_KC_B) X(LB2_KCT_HI) X(LB2_KCT_LO) X(LB2_CONVT_HI) X(LB2_CONVT_LO) \
     X(DB0_CONVT_HI) X(DB0_CONVT_LO) X(DB0_REST_HI) X(DB0_REST_LO) \
     X(LB1_UPT_HI) X(LB1_UPT_LO) X(LB2_UPT_HI) X(LB2_UPT_LO) \
-    X(LB0_KCT_F16) X(LB1_KCT_F16) X(LB2_KCT_F16) X(LB1_CONV_F16) X(LB2_CONV_F16) X(SCALES16)
+    X(LB0_KCT_F16) X(LB1_KCT_F16) X(LB2_KCT_F16) X(LB1_CONV_F16) X(LB2_CONV_F16) \
+    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(SCALES16)
 /* FD_SECTIONS_END */
 
 enum fd_section {

@@ -354,7 +354,7 @@ template <bool F16, int EPW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
               const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass,
-              float inv0, float inv1, float inv2) {
+              float inv0, float inv1, float inv2, int exp_mask) {
     constexpr int NATOM = F16 ? 3 : 6;
     constexpr int CPW = 256 / (EPW / 4);   // frame columns per epilogue warp
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -435,7 +435,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                         const uint64_t adv = (uint64_t)(k * 2);
                         if (F16) {
                             umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
-                            if (three_pass) {
+                            if (three_pass && !(exp_mask & 2)) {
                                 umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                                 umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
                             }
@@ -500,7 +500,9 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * CPW;
-            if (fast) {
+            if (exp_mask & 1) {
+                // timing experiment: no epilogue work at all
+            } else if (fast) {
                 float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN;   // record of this warp's first frame; frames are KCN words apart
                 if (as_pieces) {
                     uint16_t* ph = reinterpret_cast<uint16_t*>(o) + hw_hi;
@@ -574,6 +576,7 @@ struct TcState {
     CUtensorMap w16_hi[NBLK], w16_lo[NBLK];   // fp16 pieces (LBn_KCT_F16): rows of 96 fp32-sized elements = 192 fp16
     float scales16[64];                       // host copy of section SCALES16
     int kc_2cta = 1;       // kernel_conv GEMM on CTA pairs (cta_group::2, default); option "kc_2cta" = 0 selects the 1-CTA kernel
+    int kc_exp = 0;        // timing experiments only (option "kc_exp"): 1 = epilogue does nothing, 2 = hi*hi MMAs only (WRONG results)
     int lvc_exp = 0;       // timing experiments only (option "lvc_exp"): 1 = no second conv pass, 2 / 4 = hi*hi only in the LVC / conv (WRONG results)
     int lvc_groups = 2;    // tc_3xf16, block 2: independent 8-warp groups per CTA (2 or 3; option "lvc_groups")
     int lvc_swizzle = 0;   // LVC operand tiles: 0 = no-swizzle panels, 1 = SWIZZLE_128B + base_offset, 2 = SWIZZLE_128B, base_offset 0
@@ -599,6 +602,7 @@ static inline void tc_set_lvc_swizzle(void* st, int v) { if (st) ((TcState*)st)-
 static inline void tc_set_kc_2cta(void* st, int v) { if (st) ((TcState*)st)->kc_2cta = v; }
 static inline void tc_set_lvc_groups(void* st, int v) { if (st) ((TcState*)st)->lvc_groups = v; }
 static inline void tc_set_lvc_exp(void* st, int v) { if (st) ((TcState*)st)->lvc_exp = v; }
+static inline void tc_set_kc_exp(void* st, int v) { if (st) ((TcState*)st)->kc_exp = v; }
 
 static inline int tc_init(void** state, int device, const float* blob, const uint64_t* sec_off, std::string& err) {
     tc_destroy(*state);
@@ -657,7 +661,7 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         float inv[NBLK];
         for (int n = 0; n < NBLK; ++n) inv[n] = 1.f / (s->scales16[n] * S16_HK);
         k_kc_gemm_tc2<true, 16><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
-                                                                  s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2]);
+                                                                  s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp);
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc2<f16> failed: ") + cudaGetErrorString(e2); return -3; }
         ++*launches;
@@ -671,7 +675,7 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
         int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
         k_kc_gemm_tc2<false, 8><<<2 * clusters, 320, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
-                                                                   s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, mode == 1 ? 1 : 0, 1.f, 1.f, 1.f);
+                                                                   s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, mode == 1 ? 1 : 0, 1.f, 1.f, 1.f, 0);
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc2 failed: ") + cudaGetErrorString(e2); return -3; }
         ++*launches;
@@ -1670,6 +1674,222 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K5+K6+K7 on tensor cores (mode tc_3xf16): KernelPredictor hidden stack (modules.py:202-203, 328-329)
+//   cond = mel + fc_t(e);  h0 = lrelu_.1(conv5(cond));  h = h0 + R(h0),  R = 6 x [conv3 + lrelu_.1]
+// One tile = 128 frame rows (frames f0-8 .. f0+119) of one (LVC block, item); the 112 rows 8..119 are exact after the 7 layers
+// (each conv eats one row -- two for the k = 5 input conv -- from either edge; rows outside [0, T') are forced to zero after
+// every layer, which is the zero padding the reference's convs see).  All seven convs are kind::f16 MMAs on fp16 pieces:
+//   A = activation tiles, rows = frames, 128 B = 64 channels (hi tile, lo tile; pieces of v*S16_HK); a tap = start + shift*128 B
+//       (cond has 80 channels: channels 64..79 live in a third tile whose rows are [16 hi | 16 lo | unused])
+//   B = weight tiles streamed from the blob (LBn_KPW_F16, 28 slots of 16 KB in consumption order) through a 6-slot smem ring by
+//       one elected thread (cp.async.bulk + mbarrier), released by tcgen05.commit
+//   D = 64 fp32 columns in TMEM; epilogue (16 warps: 4 per lane quarter, 16 channels each): acc*inv + bias -> lrelu -> zero outside
+//       [0,T') -> pieces -> the other A tile pair.  h0 stays in registers (the thread <-> (row, channels) mapping is fixed), and
+//       the last epilogue writes h = h0 + lrelu(.) as fp32 and as pieces (the kernel_conv GEMM's B operand).
+// Persistent, grid = min(#tiles, #SM), 512 threads.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int KT_VALID = 112, KT_PAD = 8;
+constexpr int KT_TILE = (128 + 2 * KT_PAD) * 128;      // 18432 B
+constexpr int KT_SLOT = 16384, KT_NSLOT = 6, KT_NLOAD = 28;
+constexpr int KT_SMEM_BYTES = 5 * KT_TILE + KT_NSLOT * KT_SLOT + 7 * HID * 4 + COND * 4 + (2 * KT_NSLOT + 1) * 8 + 16 + 1024;
+
+struct KpTcParams {
+    const float* w16[NBLK];       // LBn_KPW_F16
+    const float* in_b[NBLK];      // [64]
+    const float* res_b[NBLK];     // [6][64]
+    float inv[NBLK][8];           // 1 / (S16_HK * S_w) per layer (0: input conv, 1..6: residual convs)
+};
+
+__global__ void __launch_bounds__(512, 1)
+k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ mel, const float* __restrict__ cnoise,
+               float* __restrict__ hk_all, float* __restrict__ hk_hi_all, float* __restrict__ hk_lo_all, int B, int Tm) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    // tiles: 0 = P_hi, 1 = P_lo (cond ch 0..63, then odd layers' output), 2 = Q_hi, 3 = Q_lo (even layers' output), 4 = cond ch 64..79
+    unsigned char* ring = smem + 5 * KT_TILE;
+    float* bias_s = (float*)(ring + KT_NSLOT * KT_SLOT);   // [7][64]
+    float* cn_s = bias_s + 7 * HID;                         // [80] fc_t(e) of this (block, item)
+    uint64_t* full_bar = (uint64_t*)(cn_s + COND);          // [6]
+    uint64_t* empty_bar = full_bar + KT_NSLOT;              // [6]
+    uint64_t* mma_bar = empty_bar + KT_NSLOT;               // [1]
+    uint32_t* tmem_base_s = (uint32_t*)(mma_bar + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int gw = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        for (int i = 0; i < KT_NSLOT; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(mma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (gw == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(64u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 5 * KT_TILE / 16; i += 512) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // pad rows stay 0
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_u = smem_u32(smem);
+    constexpr uint32_t idesc = umma_idesc_f16(128, 64);
+
+    const int ntf = (Tm + KT_VALID - 1) / KT_VALID, per_blk = B * ntf, total = NBLK * per_blk;
+    // ring counters, kept identical in every lane of warp 0 (the elected lane works on copies; the deterministic update is applied by
+    // all lanes afterwards, so it does not matter which lane elect.sync picks next time).  Both advance KT_NLOAD per tile.
+    uint32_t ld_issued = 0, ld_used = 0;
+    uint32_t par_mma = 0;
+    int cur_blk = -1;
+
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int blk = tile / per_blk, rem = tile % per_blk, b = rem / ntf, f0 = (rem % ntf) * KT_VALID;
+        const float* wsrc = FD_SEL3(p.w16, blk);
+        if (blk != cur_blk) {   // biases of this block (the previous tile's last __syncthreads ordered its reads before these writes)
+            if (tid < HID) bias_s[tid] = FD_SEL3(p.in_b, blk)[tid];
+            if (tid < 6 * HID) bias_s[HID + tid] = FD_SEL3(p.res_b, blk)[tid];
+            cur_blk = blk;
+        }
+        if (tid < COND) cn_s[tid] = cnoise[(blk * B + b) * COND + tid];
+        __syncthreads();
+        // ---- cond rows r = -2 .. 129 (frames f0-10 .. f0+121) -> pieces in tiles 0,1 (ch 0..63) and 4 (ch 64..79) ----
+        for (int idx = tid; idx < COND * 132; idx += 512) {
+            const int ci = idx / 132, rr = idx % 132, f = f0 - 10 + rr, row = KT_PAD - 2 + rr;
+            float v = 0.f;   // the conv zero-pads cond (= mel + noise): outside [0,T') it is 0, not the noise
+            if (f >= 0 && f < Tm) v = mel[((size_t)b * COND + ci) * Tm + f] + cn_s[ci];
+            uint16_t h16, l16;
+            f16_split(v, S16_HK, h16, l16);
+            if (ci < 64) {
+                const uint32_t off = (uint32_t)row * 128u + ((((uint32_t)ci >> 3) ^ ((uint32_t)row & 7u)) << 4) + ((uint32_t)ci & 7u) * 2u;
+                *reinterpret_cast<uint16_t*>(smem + off) = h16;
+                *reinterpret_cast<uint16_t*>(smem + KT_TILE + off) = l16;
+            } else {
+                const uint32_t c2 = (uint32_t)ci - 64u;   // hi chunk c2>>3 (0..1), lo chunk 2 + (c2>>3)
+                unsigned char* t4 = smem + 4 * KT_TILE + (uint32_t)row * 128u;
+                *reinterpret_cast<uint16_t*>(t4 + (((c2 >> 3) ^ ((uint32_t)row & 7u)) << 4) + (c2 & 7u) * 2u) = h16;
+                *reinterpret_cast<uint16_t*>(t4 + (((2u + (c2 >> 3)) ^ ((uint32_t)row & 7u)) << 4) + (c2 & 7u) * 2u) = l16;
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+
+        float h0[16];   // this thread's 16 channels of h0 (row = TMEM lane), kept for the final residual
+#pragma unroll 1
+        for (int layer = 0; layer < 7; ++layer, par_mma ^= 1) {
+            const int src = (layer & 1) ? 2 : 0;   // layer 0 reads tiles 0,1(+4) -> writes 2,3; layer 1 reads 2,3 -> writes 0,1; ...
+            if (gw == 0) {
+                tc_fence_after();
+                const int nslots = layer == 0 ? 10 : 3;
+                const uint32_t tile_base_ld = ld_used - (ld_used % KT_NLOAD);
+                const uint32_t ld_used_start = ld_used;
+                if (elect_one()) {
+                    const uint32_t at = smem_u + (uint32_t)(src * KT_TILE), x1t = smem_u + 4u * KT_TILE, ringu = smem_u + 5u * KT_TILE;
+                    for (int sidx = 0; sidx < nslots; ++sidx) {
+                        // keep the ring full: loads of this tile up to 6 ahead of the slot about to be consumed; load i goes to ring slot
+                        // i % 6 once the MMAs that read its previous content have completed (empty barrier)
+                        while (ld_issued < ld_used + KT_NSLOT && ld_issued < tile_base_ld + KT_NLOAD) {
+                            const uint32_t rs = ld_issued % KT_NSLOT, li = ld_issued % KT_NLOAD;
+                            if (ld_issued >= KT_NSLOT) mbar_wait(&empty_bar[rs], ((ld_issued / KT_NSLOT) - 1) & 1);
+                            const bool half = (li < 10) && (li & 1);     // the ci 64..79 slots carry one 8 KB tile
+                            const uint32_t bytes = half ? 8192u : 16384u;
+                            mbar_expect_tx(&full_bar[rs], bytes);
+                            bulk_g2s(ring + rs * KT_SLOT, wsrc + (size_t)li * (KT_SLOT / 4), bytes, &full_bar[rs]);
+                            ++ld_issued;
+                        }
+                        const uint32_t rs = ld_used % KT_NSLOT;
+                        mbar_wait(&full_bar[rs], (ld_used / KT_NSLOT) & 1);
+                        tc_fence_after();
+                        const uint32_t wt = ringu + rs * KT_SLOT;
+                        if (layer == 0 && (sidx & 1)) {   // cond channels 64..79 of tap j: one K = 16 step, pieces at byte 0 (hi) and 32 (lo)
+                            const int j = sidx >> 1;
+                            const uint32_t sh = (uint32_t)(KT_PAD + j - 2) * 128u;
+                            const uint64_t da = umma_desc_sw128(x1t + sh), db = umma_desc_sw128(wt);
+                            umma_f16(tmem_u, da, db, idesc, 1u);
+                            umma_f16(tmem_u, da, db + 2, idesc, 1u);        // A_hi x W_lo (+32 B)
+                            umma_f16(tmem_u, da + 2, db, idesc, 1u);        // A_lo x W_hi
+                        } else {
+                            const int j = layer == 0 ? (sidx >> 1) : sidx;
+                            const uint32_t sh = (uint32_t)(KT_PAD + j - (layer == 0 ? 2 : 1)) * 128u;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t dah = umma_desc_sw128(at + sh + ks * 32), dal = umma_desc_sw128(at + KT_TILE + sh + ks * 32);
+                                const uint64_t dbh = umma_desc_sw128(wt + ks * 32), dbl = umma_desc_sw128(wt + 8192 + ks * 32);
+                                umma_f16(tmem_u, dah, dbh, idesc, (sidx | ks) ? 1u : 0u);
+                                umma_f16(tmem_u, dah, dbl, idesc, 1u);
+                                umma_f16(tmem_u, dal, dbh, idesc, 1u);
+                            }
+                        }
+                        tc_commit(&empty_bar[rs]);   // slot free once these MMAs have read it
+                        ++ld_used;
+                    }
+                    tc_commit(mma_bar);
+                }
+                __syncwarp();
+                ld_used = ld_used_start + nslots;   // what the elected lane did, applied in every lane
+                ld_issued = min(ld_used + KT_NSLOT - 1, tile_base_ld + (uint32_t)KT_NLOAD);
+            }
+            mbar_wait(mma_bar, par_mma);
+            tc_fence_after();
+            {   // epilogue
+                const int q = gw & 3, part = gw >> 2, row = q * 32 + lane, f = f0 - 8 + row;
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + part * 16, v);
+                tmem_ld_wait();
+                const float inv = FD_SEL3(p.inv, blk)[layer];
+                const float* bias = bias_s + layer * HID + part * 16;
+                const bool in = (f >= 0 && f < Tm);
+                float y[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) y[i] = in ? lrelu(fmaf(__uint_as_float(v[i]), inv, bias[i]), 0.1f) : 0.f;
+                if (layer == 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) h0[i] = y[i];
+                }
+                if (layer < 6) {
+                    unsigned char* dst = smem + (src ^ 2) * KT_TILE + (uint32_t)(row + KT_PAD) * 128u;
+                    const uint32_t sw = (uint32_t)(row + KT_PAD) & 7u;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint2 ha, la, hb, lb;
+                        const float s = S16_HK / S16_ACT;   // split4_f16 prescales by S16_ACT
+                        split4_f16(make_float4(y[cc * 8 + 0] * s, y[cc * 8 + 1] * s, y[cc * 8 + 2] * s, y[cc * 8 + 3] * s), ha, la);
+                        split4_f16(make_float4(y[cc * 8 + 4] * s, y[cc * 8 + 5] * s, y[cc * 8 + 6] * s, y[cc * 8 + 7] * s), hb, lb);
+                        const uint32_t pos = (((uint32_t)(part * 2 + cc)) ^ sw) << 4;
+                        *reinterpret_cast<uint4*>(dst + pos) = make_uint4(ha.x, ha.y, hb.x, hb.y);
+                        *reinterpret_cast<uint4*>(dst + KT_TILE + pos) = make_uint4(la.x, la.y, lb.x, lb.y);
+                    }
+                } else if (row >= 8 && row < 8 + KT_VALID && f < Tm) {
+                    const size_t o = ((size_t)(blk * B + b) * (Tm + 2) + (size_t)(1 + f)) * HID + part * 16;
+                    float hv[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) hv[i] = h0[i] + y[i];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(hk_all + o + c * 4) = make_float4(hv[c * 4], hv[c * 4 + 1], hv[c * 4 + 2], hv[c * 4 + 3]);
+                    const float s = S16_HK / S16_ACT;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint2 ha, la, hb, lb;
+                        split4_f16(make_float4(hv[cc * 8 + 0] * s, hv[cc * 8 + 1] * s, hv[cc * 8 + 2] * s, hv[cc * 8 + 3] * s), ha, la);
+                        split4_f16(make_float4(hv[cc * 8 + 4] * s, hv[cc * 8 + 5] * s, hv[cc * 8 + 6] * s, hv[cc * 8 + 7] * s), hb, lb);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(hk_hi_all) + o + cc * 8) = make_uint4(ha.x, ha.y, hb.x, hb.y);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(hk_lo_all) + o + cc * 8) = make_uint4(la.x, la.y, lb.x, lb.y);
+                    }
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (gw == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K3+K4  first_audio_conv + DiffusionDBlock 0 on tensor cores (FastDiff_model.py:89, modules.py:127-138):
 //   xs[o] = first_conv(audio)[4 o]  (evaluated only at the kept positions);
 //   out = conv_d4(lrelu(conv_d2(lrelu(conv_d1(lrelu(xs)))))) + W1x1 xs + b
@@ -2132,7 +2352,32 @@ static inline int tc_dblock0(void* state, int mode, const float* audio, float* d
     return 0;
 }
 
+static inline int tc_kp_hidden(void* state, const float* mel, const float* cnoise, float* hk, float* hk_hi, float* hk_lo, int B, int Tm,
+                               cudaStream_t st, std::string& err, uint64_t* launches) {
+    TcState* s = (TcState*)state;
+    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    KpTcParams p;
+    for (int n = 0; n < NBLK; ++n) {
+        p.w16[n] = s->blob + s->sec_off[FD_S_LB0_KPW_F16 + n];
+        p.in_b[n] = s->blob + s->sec_off[FD_S_LB0_KPIN_B + n * FD_LB_STRIDE];
+        p.res_b[n] = s->blob + s->sec_off[FD_S_LB0_KPRES_B + n * FD_LB_STRIDE];
+        for (int l = 0; l < 7; ++l) p.inv[n][l] = 1.f / (S16_HK * s->scales16[16 + 8 * n + l]);
+        p.inv[n][7] = 0.f;
+    }
+    const int total = NBLK * B * ((Tm + KT_VALID - 1) / KT_VALID);
+    const int grid = total < s->sm_count ? total : s->sm_count;
+    k_kp_hidden_tc<<<grid, 512, KT_SMEM_BYTES, st>>>(p, mel, cnoise, hk, hk_hi, hk_lo, B, Tm);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_kp_hidden_tc failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    return 0;
+}
+
 static inline cudaError_t tc_set_lvc_attrs() {
+    {
+        cudaError_t ek = cudaFuncSetAttribute(k_kp_hidden_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM_BYTES);
+        if (ek != cudaSuccess) return ek;
+    }
     cudaError_t e0 = cudaFuncSetAttribute(k_dblock0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES);
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_kc_gemm_tc2<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);

@@ -207,6 +207,39 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
                     rows[l, :, co, c ^ (co & 7), :] = both[:, co, c, :]
         conv16[n] = _u16_as_f32(rows)
     S["LB1_CONV_F16"], S["LB2_CONV_F16"] = conv16[1], conv16[2]
+    # kernel-predictor hidden stack: B-operand tiles (64 co rows x 128 B, chunk c at c ^ (co & 7)) in consumption order
+    swz = (np.arange(8)[None, :] ^ (np.arange(HID)[:, None] & 7))                          # [co][chunk] -> position
+
+    def _tile(rows_u16):   # [64 co][64 fp16] -> swizzled 8 KB image (uint16 [64][64])
+        t = np.zeros((HID, 8, 8), dtype=np.uint16)
+        src = rows_u16.reshape(HID, 8, 8)
+        for co in range(HID):
+            t[co, swz[co], :] = src[co]
+        return t.reshape(HID, 64)
+
+    for n in range(3):
+        kp = f"lvc_blocks.{n}.kernel_predictor"
+        slots = np.zeros((28, 2, HID, 64), dtype=np.uint16)                                  # 28 x 16 KB
+        win = W[f"{kp}.input_conv.0.weight"].numpy()                                        # (64 co, 80 ci, 5)
+        sc = f16_scale(win)
+        scales[16 + 8 * n] = sc
+        hi, lo = f16_split(win, sc)
+        for j in range(5):
+            slots[2 * j, 0] = _tile(np.ascontiguousarray(hi[:, :64, j]))
+            slots[2 * j, 1] = _tile(np.ascontiguousarray(lo[:, :64, j]))
+            x1 = np.zeros((HID, 64), dtype=np.uint16)
+            x1[:, 0:16] = hi[:, 64:80, j]
+            x1[:, 16:32] = lo[:, 64:80, j]
+            slots[2 * j + 1, 0] = _tile(x1)
+        for l, idx in enumerate((1, 3, 6, 8, 11, 13)):
+            wr = W[f"{kp}.residual_conv.{idx}.weight"].numpy()                              # (64 co, 64 ci, 3)
+            sc = f16_scale(wr)
+            scales[17 + 8 * n + l] = sc
+            hi, lo = f16_split(wr, sc)
+            for j in range(3):
+                slots[10 + 3 * l + j, 0] = _tile(np.ascontiguousarray(hi[:, :, j]))
+                slots[10 + 3 * l + j, 1] = _tile(np.ascontiguousarray(lo[:, :, j]))
+        S[f"LB{n}_KPW_F16"] = _u16_as_f32(slots)
     S["SCALES16"] = torch.from_numpy(scales)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}

@@ -7,7 +7,7 @@ from oracle import fastdiff_oracle as O
 import torch.nn.functional as F
 sd = make_state_dict(1234, g_jitter=0.1); W = O.fold_weight_norm(sd)
 net = fb.FastDiff().cuda().eval(); net.load_state_dict(sd)
-MODES = ('tc_3xf16', 'tc_3xf16:lvc_groups=3')
+MODES = ('tc_3xf16', 'tc_3xf16:tc_kp=0')
 for (B, Tm) in ((1, 5), (2, 33), (3, 300)):
     x, mel = make_inputs(B, Tm, 3); t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
     eps_o, inter = O.denoise(W, x, mel, t, return_intermediates=True)
@@ -15,7 +15,7 @@ for (B, Tm) in ((1, 5), (2, 33), (3, 300)):
     for mode in MODES:
         net.mode = mode.split(':')[0]
         eng = net.engine(); eng.set_option('stop_after', 1)
-        eng.set_option('lvc_groups', 3 if 'lvc_groups=3' in mode else 2)
+        eng.set_option('tc_kp', 0 if 'tc_kp=0' in mode else 1)
         try:
             net((x.cuda(), mel.cuda(), t.cuda())); torch.cuda.synchronize()
         except Exception as ex:
