@@ -593,12 +593,17 @@ __global__ void __launch_bounds__(256) k_lvc_layer(LvcParams p, const float* __r
             } else {
                 // kernels straight from HBM (hop 8: each is used by 8 samples only).  Block 0's kernels are stored in PANEL order
                 // [k][i/4][o][i%4] (fd_blob.h): consecutive lanes read consecutive 16-byte vectors -> 512 B coalesced per request.
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < 3; ++k) {
-#pragma unroll 2
+                    float4 wreg[16];   // the whole tap (16 x 512 B per warp) in flight before the first FMA: latency-bound otherwise
+#pragma unroll
                     for (int c4 = 0; c4 < 8; ++c4) {
-                        const float4 wa = *reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + lane) * 4);
-                        const float4 wb = *reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + C + lane) * 4);
+                        wreg[2 * c4] = __ldg(reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + lane) * 4));
+                        wreg[2 * c4 + 1] = __ldg(reinterpret_cast<const float4*>(W + ((k * 8 + c4) * LVC_OUT + C + lane) * 4));
+                    }
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const float4 wa = wreg[2 * c4], wb = wreg[2 * c4 + 1];
 #pragma unroll
                         for (int n = 0; n < 8; ++n) {
                             const float4 v = y4[(base + n + k) * 8 + c4];
@@ -683,18 +688,46 @@ struct FinalParams {
 __global__ void __launch_bounds__(256) k_final(FinalParams p, const float* __restrict__ h, const float* __restrict__ x_t,
                                                const float* __restrict__ z, float* __restrict__ out,
                                                float* __restrict__ seq_out, int L) {
-    __shared__ float s[(256 + 6) * 33];
+    // h rows t0-3 .. t0+258 staged as float4 chunks, chunk c4 of row r at position c4 ^ (r & 7) (conflict-free both ways).
+    // Thread (q = tid/4, cg = tid%4) accumulates the 4 outputs 4q..4q+3 over channels 8cg..8cg+7 from 10 rows (2 LDS.128 per row:
+    // 2.8x less shared-memory traffic than one output per thread), the 4 channel-group partials are summed in a fixed order.
+    __shared__ float4 s4[(256 + 6) * 8];
+    __shared__ float part[4][256];
     const int tid = threadIdx.x, t0 = blockIdx.x * 256, b = blockIdx.y;
-    for (int idx = tid; idx < (256 + 6) * C; idx += 256) {
-        const int r = idx >> 5, c = idx & 31, t = t0 - 3 + r;
-        s[r * 33 + c] = (t >= 0 && t < L) ? h[((size_t)b * L + t) * C + c] : 0.f;
+    for (int idx = tid; idx < (256 + 6) * 8; idx += 256) {
+        const int r = idx >> 3, c4 = idx & 7, t = t0 - 3 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < L) v = *reinterpret_cast<const float4*>(h + ((size_t)b * L + t) * C + c4 * 4);
+        s4[r * 8 + (c4 ^ (r & 7))] = v;
     }
     __syncthreads();
-    float eps = p.b;
+    {
+        const int q = tid >> 2, cg = tid & 3;
+        float wr[7][8];   // this channel group's taps in registers (p.w[...cg...] would be a lane-divergent constant-bank access per FMA)
 #pragma unroll
-    for (int k = 0; k < 7; ++k)
+        for (int k = 0; k < 7; ++k)
 #pragma unroll
-        for (int c = 0; c < C; ++c) eps = fmaf(s[(tid + k) * 33 + c], p.w[k * C + c], eps);
+            for (int c = 0; c < 8; ++c) wr[k][c] = p.w[k * C + cg * 8 + c];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int rr = 0; rr < 10; ++rr) {
+            const int r = 4 * q + rr;
+            const float4 va = s4[r * 8 + ((2 * cg) ^ (r & 7))], vb = s4[r * 8 + ((2 * cg + 1) ^ (r & 7))];
+            const float v[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int k = rr - i;   // row r feeds output 4q+i through tap k
+                if (k >= 0 && k < 7) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc[i] = fmaf(v[c], wr[k][c], acc[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) part[cg][4 * q + i] = acc[i];
+    }
+    __syncthreads();
+    const float eps = (((p.b + part[0][tid]) + part[1][tid]) + part[2][tid]) + part[3][tid];
     const size_t e = (size_t)b * L + t0 + tid;
     float r;
     if (p.mode == 0) {

@@ -349,6 +349,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 // = 128 B prescaled by S16_HK), a k-atom is 64 values = one tap of the im2col (box at row p + a), every MMA is kind::f16 with
 // K = 16, and the epilogue undoes the scales: kern = acc * inv[blk] + bias.  Half the MMAs and half the operand bytes of the
 // tf32 variant for the same 22 significant bits per operand.
+#ifndef KC_STORE_CS
+#define KC_STORE_CS 0     // 1: streaming (evict-first) cache hint on the predicted-kernel stores
+#endif
+#ifndef KC_STORE_SHFL
+#define KC_STORE_SHFL 0   // 1: adjacent lanes swap one piece and store 32-bit words (one 128-byte line per warp store) instead of two 16-bit stores
+#endif
 // EPW = epilogue warps per CTA (8 or 16: EPW/4 per TMEM lane quarter, each taking 256/(EPW/4) of the 256 frame columns).
 template <bool F16, int EPW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
@@ -402,13 +408,15 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                 for (int a = 0; a < NATOM; ++a) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     unsigned char* st = smem + stage * KC2_STAGE_BYTES;
-                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (three_pass ? KC2_STAGE_BYTES : (KC2_A_BYTES + KC2_B_BYTES)));
+                    // timing experiment (exp_mask & 16, WRONG results): weights loaded for the first tile only -> half the operand feed
+                    const bool skip_a = (exp_mask & 16) && item != pair_id;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (skip_a ? 2u * KC2_B_BYTES : (three_pass ? KC2_STAGE_BYTES : (KC2_A_BYTES + KC2_B_BYTES))));
                     const int frow = ft * 256 + (int)rank * 128 + (F16 ? a : (a >> 1));
                     const int fcol = F16 ? 0 : (a & 1) * 32;
-                    tma_load_2d_2sm(st, wh, a * 32, nt * 128, &full_bar[stage]);
+                    if (!skip_a) tma_load_2d_2sm(st, wh, a * 32, nt * 128, &full_bar[stage]);
                     tma_load_2d_2sm(st + 2 * KC2_A_BYTES, hh, fcol, frow, &full_bar[stage]);
                     if (three_pass) {
-                        tma_load_2d_2sm(st + KC2_A_BYTES, wl, a * 32, nt * 128, &full_bar[stage]);
+                        if (!skip_a) tma_load_2d_2sm(st + KC2_A_BYTES, wl, a * 32, nt * 128, &full_bar[stage]);
                         tma_load_2d_2sm(st + 2 * KC2_A_BYTES + KC2_B_BYTES, hl, fcol, frow, &full_bar[stage]);
                     }
                     if (++stage == KC2_STAGES) { stage = 0; phase ^= 1; }
@@ -478,7 +486,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             int word = n, hw_hi = 0, hw_lo = 0;             // 32-bit word / 16-bit halfword indices inside the frame record
             if (pieces && is_w) {
                 const int ko = rem >> 5, oo = ko & 63, ci = ((((rem >> 2) & 7) ^ (oo & 7)) << 2) + (rem & 3);
-                const int base = 2 * ((n - rem) + ko * 32) + (ci & 7);
+                const int base = 2 * ((n - rem) + ko * 32) + (KC_STORE_SHFL ? (ci & 6) : (ci & 7));
                 hw_hi = base + (((ci >> 3) ^ (oo & 7)) << 3);
                 hw_lo = base + (((4 + (ci >> 3)) ^ (oo & 7)) << 3);
             }
@@ -486,13 +494,29 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             // warp-uniform; broadcast from lane 0 so that ptxas KNOWS it (otherwise every store below re-materialises its uniform
             // memory descriptor with two R2UR: 40% of the epilogue's instructions)
             const bool as_pieces = __shfl_sync(0xffffffffu, (int)(pieces && is_w), 0) != 0;
+            const int odd = lane & 1;
             auto put_pieces = [&](uint16_t* ph, uint16_t* pl, float accv) {
                 const float sv = fmaf(accv, inv_s, bv_s);
                 uint16_t h16, l16;
                 asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h16) : "f"(sv));
+#if KC_STORE_SHFL
+                // even lane (element i) keeps the hi halves of (i, i+1), odd lane the lo halves; ph/pl point at the even element's halfword
+                const float hi_f = f16_bits_to_float(h16), lo_f = sv - hi_f;
+                const float recv = __shfl_xor_sync(0xffffffffu, odd ? hi_f : lo_f, 1);
+                uint32_t packed;
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(odd ? lo_f : recv), "f"(odd ? recv : hi_f));
+                *reinterpret_cast<uint32_t*>(odd ? pl : ph) = packed;
+                (void)l16;
+#else
                 asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l16) : "f"(sv - f16_bits_to_float(h16)));
+#if KC_STORE_CS
+                asm volatile("st.global.cs.b16 [%0], %1;" ::"l"(ph), "h"(h16) : "memory");
+                asm volatile("st.global.cs.b16 [%0], %1;" ::"l"(pl), "h"(l16) : "memory");
+#else
                 *ph = h16;
                 *pl = l16;
+#endif
+#endif
             };
             int p = ft * 256 + cpart * CPW;
             int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
@@ -502,6 +526,35 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * CPW;
             if (exp_mask & 1) {
                 // timing experiment: no epilogue work at all
+            } else if (exp_mask & 4) {
+                // timing experiment: TMEM loads + arithmetic, no global stores (the store is predicated on a value that never occurs)
+#pragma unroll 1
+                for (int c0 = 0; c0 < CPW; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+                    float acc2 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc2 += fmaf(__uint_as_float(v[j]), inv_s, bv_s);
+                    if (acc2 == 1.2345e-33f) kern[n] = acc2;
+                }
+            } else if ((exp_mask & 8) && fast) {
+                // timing experiment (WRONG data layout): the same bytes and records, but written as 16-byte stores -- lane l writes one
+                // 16-B chunk of the record of frame j0 + (l & 7): 1/8 of the store instructions of the real path
+                float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN + (n & ~31) + ((lane >> 3) << 2);
+#pragma unroll 1
+                for (int c0 = 0; c0 < CPW; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float* r = o + (size_t)(j + (lane & 7)) * KCN;
+                        *reinterpret_cast<uint4*>(r) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        *reinterpret_cast<uint4*>(r + 16) = make_uint4(v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+                    }
+                    o += (size_t)32 * KCN;
+                }
             } else if (fast) {
                 float* o = kern + ((size_t)bb * Tm + (fp - 1)) * KCN;   // record of this warp's first frame; frames are KCN words apart
                 if (as_pieces) {
