@@ -31,6 +31,12 @@ struct fd_handle {
     int tc_upsample = 1;         // LVC-block upsample (blocks 1, 2) on tensor cores in the TC modes (option "tc_upsample")
     int tc_dblock = 1;           // DBlock 0 on tensor cores in the TC modes (option "tc_dblock")
     int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
+    int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
+                                 // (option "overlap"; forked from / joined into the caller's stream with events inside every call)
+#ifndef FD_EMU
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+#endif
     int attrs_set = 0;
     uint64_t launches = 0;
     std::string err;
@@ -144,6 +150,14 @@ extern "C" int fd_create(const fd_config* cfg, int device, fd_handle** out) {
 #endif
     fd_handle* h = new fd_handle();
     h->device = device;
+#ifndef FD_EMU
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, FD_ERR_CUDA, "fd_create: creating the side stream / events failed");
+    }
+#endif
     *out = h;
     return FD_OK;
 }
@@ -157,6 +171,9 @@ extern "C" void fd_destroy(fd_handle* h) {
 #ifndef FD_EMU
     for (auto& t : h->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
 #endif
     if (h->blob) cudaFree(h->blob);
     delete h;
@@ -263,6 +280,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "stop_after")) { h->stop_after = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_dblock")) { h->tc_dblock = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_kp")) { h->tc_kp = (int)value; return FD_OK; }
+    if (!strcmp(key, "overlap")) { h->overlap = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_upsample")) { h->tc_upsample = (int)value; return FD_OK; }
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
@@ -341,6 +359,44 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     float* emb = ws + w.emb; float* cnoise = ws + w.cnoise; float* hk = ws + w.hk; float* kern = ws + w.kern;
     float* d0 = ws + w.d0; float* d1 = ws + w.d1; float* d2 = ws + w.d2; float* xa = ws + w.xa; float* xb = ws + w.xb;
 
+    // -- first_audio_conv + the three DiffusionDBlocks: independent of the kernel-predictor path, so they run on the side stream
+    //    (forked here, joined before the first LVC block) unless a debugging stop or the option "overlap" = 0 asks for serial order
+    auto run_dblocks = [&](cudaStream_t sd) -> int {
+        DbParams p;
+        p.first_w = sec(h, FD_S_FIRST_W); p.first_b = sec(h, FD_S_FIRST_B);
+        const float* ins[3] = {x_dev, d0, d1};
+        float* outs[3] = {d0, d1, d2};
+        const int tin[3] = {L, L / 4, L / 32}, tout[3] = {L / 4, L / 32, L / 256};
+        for (int n = 0; n < NBLK; ++n) {
+            p.res_w = sec(h, FD_S_DB0_RES_W + n * FD_DB_STRIDE);   p.res_b = sec(h, FD_S_DB0_RES_B + n * FD_DB_STRIDE);
+            p.conv_w = sec(h, FD_S_DB0_CONV_W + n * FD_DB_STRIDE); p.conv_b = sec(h, FD_S_DB0_CONV_B + n * FD_DB_STRIDE);
+            const dim3 grid((tout[n] + DB_TO - 1) / DB_TO, B);
+            ScopedTimer tm(h, KC_DBLOCK, sd);
+            bool done_tc = false;
+#ifndef FD_EMU
+            if (n == 0 && h->mode != FD_MODE_FP32_SIMT && h->tc_dblock) {
+                int rc = tc_dblock0(h->tc_state, h->mode, x_dev, d0, B, L, sd, h->err, &h->launches);
+                if (rc) return rc;
+                done_tc = true;
+            }
+#endif
+            if (done_tc) continue;
+            if (n == 0) { auto k = k_dblock<4, true>;  FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<4>(), sd, p, ins[n], outs[n], tin[n], tout[n]); }
+            else        { auto k = k_dblock<8, false>; FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<8>(), sd, p, ins[n], outs[n], tin[n], tout[n]); }
+            FD_CHECK_LAUNCH(h, "k_dblock");
+        }
+            return FD_OK;
+    };
+    bool forked = false;
+#ifndef FD_EMU
+    if (h->overlap && h->side && h->stop_after > 2) {
+        FD_CUDA(h, cudaEventRecord(h->ev_fork, st));
+        FD_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        int rc = run_dblocks(h->side);
+        if (rc) return rc;
+        forked = true;
+    }
+#endif
     // -- step embedding + per-block condition offsets
     {
         EmbedParams p;
@@ -393,32 +449,13 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     }
     if (h->stop_after <= 1) return FD_OK;
 
-    // -- first_audio_conv + the three DiffusionDBlocks
-    {
-        DbParams p;
-        p.first_w = sec(h, FD_S_FIRST_W); p.first_b = sec(h, FD_S_FIRST_B);
-        const float* ins[3] = {x_dev, d0, d1};
-        float* outs[3] = {d0, d1, d2};
-        const int tin[3] = {L, L / 4, L / 32}, tout[3] = {L / 4, L / 32, L / 256};
-        for (int n = 0; n < NBLK; ++n) {
-            p.res_w = sec(h, FD_S_DB0_RES_W + n * FD_DB_STRIDE);   p.res_b = sec(h, FD_S_DB0_RES_B + n * FD_DB_STRIDE);
-            p.conv_w = sec(h, FD_S_DB0_CONV_W + n * FD_DB_STRIDE); p.conv_b = sec(h, FD_S_DB0_CONV_B + n * FD_DB_STRIDE);
-            const dim3 grid((tout[n] + DB_TO - 1) / DB_TO, B);
-            ScopedTimer tm(h, KC_DBLOCK, st);
-            bool done_tc = false;
+    if (!forked) { int rc = run_dblocks(st); if (rc) return rc; }
 #ifndef FD_EMU
-            if (n == 0 && h->mode != FD_MODE_FP32_SIMT && h->tc_dblock) {
-                int rc = tc_dblock0(h->tc_state, h->mode, x_dev, d0, B, L, st, h->err, &h->launches);
-                if (rc) return rc;
-                done_tc = true;
-            }
-#endif
-            if (done_tc) continue;
-            if (n == 0) { auto k = k_dblock<4, true>;  FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<4>(), st, p, ins[n], outs[n], tin[n], tout[n]); }
-            else        { auto k = k_dblock<8, false>; FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<8>(), st, p, ins[n], outs[n], tin[n], tout[n]); }
-            FD_CHECK_LAUNCH(h, "k_dblock");
-        }
+    if (forked) {
+        FD_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+        FD_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
     }
+#endif
     if (h->stop_after <= 2) return FD_OK;
 
     // -- the three TimeAware_LVCBlocks
