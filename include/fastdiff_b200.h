@@ -9,7 +9,9 @@
  * Conventions
  *   - return 0 on success, negative fd_status on failure; fd_last_error() gives the message.
  *   - every pointer named *_dev is a DEVICE pointer owned by the caller (PyTorch); the library
- *     borrows it for the duration of the call, launches on the caller's stream and never
+ *     borrows it for the duration of the call, launches on the caller's stream (plus one internal
+ *     side stream for the DiffusionDBlock chain, forked from and joined back into the caller's
+ *     stream with events inside the same call, so the caller sees ordinary stream semantics) and never
  *     synchronises the host.  Nothing is allocated after fd_load_weights(); scratch memory is the
  *     caller-provided workspace (fd_workspace_bytes).
  *   - layouts are the reference's: audio (B,1,L) fp32, mel (B,80,T') fp32 NCL, L = 256*T',
@@ -102,7 +104,10 @@ int fd_set_mode(fd_handle* h, int mode);
 int fd_get_mode(fd_handle* h);
 
 /* Integer options.  "stop_after": run fd_denoise only up to a stage (1 = kernel predictor, 2 = DBlocks,
- * 3/4/5 = LVC block 0/1/2, >= 6 = everything; default) so fd_debug_read can inspect stage outputs. */
+ * 3/4/5 = LVC block 0/1/2, >= 6 = everything; default) so fd_debug_read can inspect stage outputs.
+ * Tuning / cross-check switches (defaults in brackets): "overlap" [1] DBlock chain on the internal side stream; "tc_kp" [1],
+ * "tc_dblock" [1], "tc_upsample" [1] tensor-core versions of the kernel-predictor stack / DBlock 0 / upsampling; "kc_2cta" [1];
+ * "lvc_groups" [2]; "lvc_swizzle"; "kc_exp", "lvc_exp" [0] timing experiments that produce WRONG results. */
 int fd_set_option(fd_handle* h, const char* key, int64_t value);
 
 /* eps = FastDiff.forward((x_t, mel, t))   (modules/FastDiff/module/FastDiff_model.py:74-102).

@@ -110,6 +110,40 @@ def test_tensor_core_mode_vs_oracle(synth, cuda_lib, B, Tm, mode):
 
 
 @gpu
+def test_f16_mode_options_and_guards(synth, cuda_lib):
+    """tc_3xf16 building blocks: the tensor-core kernel-predictor stack against the FFMA one, the side-stream overlap against the
+    serial order (bitwise), the cross_check guard, and saturation (finite output, flagged by cross_check) beyond the fp16 range."""
+    from fastdiff_b200.synthetic import make_inputs
+    sd, _ = synth
+    net = _net(sd, "tc_3xf16")
+    B, Tm = 2, 150
+    x, mel = make_inputs(B, Tm, 6)
+    t = torch.tensor([[23.46759], [498.0537]])
+    data = (x.cuda(), mel.cuda(), t.cuda())
+    eng = net.engine()
+    eps = net(data)
+    hk_tc = [eng.debug_read(f"kp_hidden{n}", B, Tm).clone() for n in range(3)]
+    eng.set_option("tc_kp", 0)
+    eps_simt_kp = net(data)
+    hk_simt = [eng.debug_read(f"kp_hidden{n}", B, Tm) for n in range(3)]
+    eng.set_option("tc_kp", 1)
+    for a, b in zip(hk_tc, hk_simt):
+        assert (a - b).abs().max() < 2e-5 * max(1.0, b.abs().max().item())
+    assert (eps - eps_simt_kp).abs().max() < EPS_TOL
+    eng.set_option("overlap", 0)
+    eps_serial = net(data)
+    eng.set_option("overlap", 1)
+    assert torch.equal(eps, eps_serial)
+    chk = net.cross_check(data, modes=("fp32_simt", "tc_3xtf32"))
+    assert chk["fp32_simt"] < EPS_TOL and chk["tc_3xtf32"] < EPS_TOL
+    assert eng.get_mode() == 3 and net.mode == "tc_3xf16"
+    big = (x.cuda() * 3e4, mel.cuda(), t.cuda())        # |activation| * 16 >> 65504: operands saturate
+    out = net(big)
+    assert torch.isfinite(out).all()
+    assert net.cross_check(big)["fp32_simt"] > 1.0       # ... and the guard shows it
+
+
+@gpu
 def test_default_mode_is_fp32_level_tensor_core(synth, cuda_lib):
     sd, _ = synth
     assert _net(sd).engine().get_mode() == 3  # FD_MODE_TC_3XF16

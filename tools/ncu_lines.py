@@ -36,7 +36,12 @@ def main():
     hi = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hi]
     ix = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[hi + 1:] if len(r) == len(hdr)]
+    data = []
+    for r in rows[hi + 1:]:
+        if r and r[0] == "Kernel Name":   # a second block (ncu repeats the listing): keep the first
+            break
+        if len(r) == len(hdr):
+            data.append(r)
     assert len(data) == len(sl), (len(data), len(sl))
     agg = {}
     tot_i = tot_s = 0
