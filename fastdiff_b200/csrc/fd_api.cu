@@ -31,6 +31,7 @@ struct fd_handle {
     int tc_upsample = 1;         // LVC-block upsample (blocks 1, 2) on tensor cores in the TC modes (option "tc_upsample")
     int tc_dblock = 1;           // DBlock 0 on tensor cores in the TC modes (option "tc_dblock")
     int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
+    int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
                                  // (option "overlap"; forked from / joined into the caller's stream with events inside every call)
 #ifndef FD_EMU
@@ -281,6 +282,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_dblock")) { h->tc_dblock = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_kp")) { h->tc_kp = (int)value; return FD_OK; }
     if (!strcmp(key, "overlap")) { h->overlap = (int)value; return FD_OK; }
+    if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_upsample")) { h->tc_upsample = (int)value; return FD_OK; }
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
@@ -501,9 +503,9 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             }
 #endif
             if (!done) {
-                if (n == 0)      { auto k = k_lvc_layer<8, 64, false>;    FD_LAUNCH(k, dim3((T + 63) / 64, B), dim3(256), (lvc_smem_bytes<8, 64>()), st, p, cur, skip, kl, oth, T, Tm, dil); }
-                else if (n == 1) { auto k = k_lvc_layer<64, 128, false>;  FD_LAUNCH(k, dim3((T + 127) / 128, B), dim3(256), (lvc_smem_bytes<64, 128>()), st, p, cur, skip, kl, oth, T, Tm, dil); }
-                else             { auto k = k_lvc_layer<256, 256, true>;  FD_LAUNCH(k, dim3((T + 255) / 256, B), dim3(256), (lvc_smem_bytes<256, 256>()), st, p, cur, skip, kl, oth, T, Tm, dil); }
+                if (n == 0)      { auto k = k_lvc_layer<8, 64, false>;    FD_LAUNCH(k, dim3((T + 63) / 64, B), dim3(256), (lvc_smem_bytes<8, 64>()), st, p, cur, skip, kl, oth, T, Tm, dil, h->b0_prefetch); }
+                else if (n == 1) { auto k = k_lvc_layer<64, 128, false>;  FD_LAUNCH(k, dim3((T + 127) / 128, B), dim3(256), (lvc_smem_bytes<64, 128>()), st, p, cur, skip, kl, oth, T, Tm, dil, h->b0_prefetch); }
+                else             { auto k = k_lvc_layer<256, 256, true>;  FD_LAUNCH(k, dim3((T + 255) / 256, B), dim3(256), (lvc_smem_bytes<256, 256>()), st, p, cur, skip, kl, oth, T, Tm, dil, h->b0_prefetch); }
                 FD_CHECK_LAUNCH(h, "k_lvc_layer");
             }
             float* tmp = cur; cur = oth; oth = tmp;

@@ -481,7 +481,7 @@ constexpr int lvc_smem_bytes() {
 template <int HOP, int TT, bool SKIP_FIRST>
 __global__ void __launch_bounds__(256) k_lvc_layer(LvcParams p, const float* __restrict__ x_in,
                                                    const float* __restrict__ skip, const float* __restrict__ kern,
-                                                   float* __restrict__ x_out, int T, int Tm, int dil) {
+                                                   float* __restrict__ x_out, int T, int Tm, int dil, int flags) {
     constexpr bool WL_SMEM = HOP >= 64;
     constexpr int NF = TT / HOP > 0 ? TT / HOP : 1;
     FD_DYN_SMEM(float, sm);
@@ -493,6 +493,17 @@ __global__ void __launch_bounds__(256) k_lvc_layer(LvcParams p, const float* __r
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = blockIdx.x * TT, b = blockIdx.y;
 
+#ifndef FD_EMU
+    if (!WL_SMEM && lane == 0 && (flags & 1)) {
+        // hop 8: every warp reads its frame's 24.8 KB of predicted kernels straight from global in phase 3, a few loads at a time
+        // (latency-bound).  Pull them into L2 now, all at once, so that phases 1-2 hide the HBM latency.
+        const int f = (t0 + warp * 8) / HOP;
+        if (f < Tm) {
+            const float* src = kern + ((size_t)b * Tm + f) * KCN;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(KPL * 4)) : "memory");
+        }
+    }
+#endif
     for (int i = tid; i < KK * C; i += 256) cw_s[i] = p.conv_w[i];
     if (WL_SMEM) {
         for (int fi = 0; fi < NF; ++fi) {

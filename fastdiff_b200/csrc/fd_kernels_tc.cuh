@@ -1390,8 +1390,28 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         }
     };
 
+    // L2 prefetch of the tile after the next one (x rows, skip rows, predicted kernels: all come from HBM), so that the bulk copies
+    // issued one tile ahead are L2 hits (call from ONE thread)
+    auto prefetch_l2 = [&](int tile) {
+        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+        const int ar0 = max(r_lo, 28 - t0), ar1 = min(r_hi, T - t0 + 28);
+        if (ar1 > ar0) {
+            const size_t off = ((size_t)b * T + (t0 - 28 + ar0)) * C;
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x_in + off), "r"((uint32_t)(ar1 - ar0) * 128u) : "memory");
+            if (!SKIP_FIRST) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(skip + off), "r"((uint32_t)(ar1 - ar0) * 128u) : "memory");
+        }
+#pragma unroll
+        for (int fi = 0; fi < NF; ++fi) {
+            const int f = t0 / HOP + fi;
+            if (f < Tm) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kern + ((size_t)b * Tm + f) * KCN), "r"((uint32_t)(KPL * 4)) : "memory");
+        }
+    };
+
     int tile = blockIdx.x * GROUPS + g;
-    if (tile < total && gw_u == 0) { if (elect_one()) issue_loads(tile, 0); __syncwarp(); }
+    if (tile < total && gw_u == 0) {
+        if (elect_one()) { issue_loads(tile, 0); if ((exp_mask & 8) && tile + tstride < total) prefetch_l2(tile + tstride); }
+        __syncwarp();
+    }
 #ifdef FD_LVC_TIMELINE
     const bool stamp = (blockIdx.x == 0 && tid == 0 && HOP == 256);
     int tile_no = -1;
@@ -1694,7 +1714,10 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             tc_fence_after();
             LT_STAMP(9);
             // LVC MMAs complete: the A/Y tile and the kernels are free -> fetch the next tile while this one is gated
-            if (gw_u == 0 && tile + tstride < total) { if (elect_one()) issue_loads(tile + tstride, (int)(parity ^ 1)); __syncwarp(); }
+            if (gw_u == 0 && tile + tstride < total) {
+                if (elect_one()) { issue_loads(tile + tstride, (int)(parity ^ 1)); if ((exp_mask & 8) && tile + 2 * tstride < total) prefetch_l2(tile + 2 * tstride); }
+                __syncwarp();
+            }
             uint32_t zs[16], zt[16];
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + 32 + fi * 64 + part * 16;
             tmem_ld_32x32b_x16(ta, zs);
