@@ -1254,7 +1254,7 @@ constexpr int LH_LW_BYTES = 24576;                   // per frame: 3 taps x 64 r
 constexpr int LH_CW_BYTES = 3 * C * 128;             // 12288
 template <int HOP, bool SKIP_FIRST>
 __host__ __device__ constexpr int lh_slot_bytes() { return LH_A_BYTES + (SKIP_FIRST ? LH_XS_BYTES : LH_A_BYTES) + lt_nf<HOP>() * LH_LW_BYTES; }
-constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C) * 4 + 3 * 3 * 64 * 4 + 192;   // conv W, first_w, first_b, conv_b, barriers + tmem ptr
+constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C + C) * 4 + 3 * 3 * 64 * 4 + 192;   // conv W, first_w, first_b, conv_b, barriers + tmem ptr
 template <int HOP, bool SKIP_FIRST, int GROUPS>
 constexpr int lh_smem_bytes() { return GROUPS * (lh_slot_bytes<HOP, SKIP_FIRST>() + lt_small_bytes<HOP>()) + LH_SHARED_BYTES + 1024; }
 
@@ -1265,20 +1265,21 @@ struct LvcHParams {
 };
 
 // 4 floats -> fp16 pieces of v*S16_ACT: hi (4 halves in a uint2), lo likewise
+__device__ __forceinline__ void split4_f16_pre(const float sx, const float sy, const float sz, const float sw, uint2& hi, uint2& lo);
 __device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo) {
-    const float sx = v.x * S16_ACT, sy = v.y * S16_ACT, sz = v.z * S16_ACT, sw = v.w * S16_ACT;
+    split4_f16_pre(v.x * S16_ACT, v.y * S16_ACT, v.z * S16_ACT, v.w * S16_ACT, hi, lo);
+}
+// same, for values that already carry the prescale
+__device__ __forceinline__ void split4_f16_pre(const float sx, const float sy, const float sz, const float sw, uint2& hi, uint2& lo) {
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(sy), "f"(sx));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(sw), "f"(sz));
     const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo.x) : "f"(sy - h01.y), "f"(sx - h01.x));
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo.y) : "f"(sw - h23.y), "f"(sz - h23.x));
 }
-// sigmoid(a) * tanh(b) with two ex2 and one rcp; b clamped to +-15 (tanh is +-1 to fp32 precision beyond 9.01) so E stays finite
+// sigmoid(a) * tanh(b) with two ex2 and one rcp; b clamped from below at -15 (tanh is -1 to fp32 precision below -9.01) so E stays finite
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-#ifndef LH_TWOPASS
-#define LH_TWOPASS 1
-#endif
 #ifndef LH_GATE_ASM
 #define LH_GATE_ASM 1
 #endif
@@ -1286,7 +1287,7 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 #define LH_HALO_MMA 0   // 1: the two extra conv rows from a second MMA pass; 0: FFMA partial sums on warps 2-7 while the MMAs run (faster: measured)
 #endif
 __device__ __forceinline__ float gate_st(float a, float b) {
-    const float bc = fminf(fmaxf(b, -15.f), 15.f);
+    const float bc = fmaxf(b, -15.f);   // E = e^-2b must stay finite (E -> 0 for large b is harmless); tanh(-15) = -1 to fp32 precision
 #if !LH_GATE_ASM
     const float E2 = exp2f(-2.8853900817779268f * bc), A2 = exp2f(-1.4426950408889634f * a);
     return __fdividef(1.f - E2, (1.f + A2) * (1.f + E2));
@@ -1296,11 +1297,15 @@ __device__ __forceinline__ float gate_st(float a, float b) {
 }
 // leaky ReLU with slope 0.2 as max(v, 0.2 v): two instructions instead of compare + multiply + select
 __device__ __forceinline__ float lrelu02(float v) { return fmaxf(v, 0.2f * v); }
+// S16_ACT * lrelu_0.2(v) in the same three instructions (the prescale of the fp16 pieces folded into the two products; exact: power of two)
+__device__ __forceinline__ float lrelu02_s(float v) { return fmaxf(v * S16_ACT, v * (0.2f * S16_ACT)); }
 
 template <int HOP, bool SKIP_FIRST, int GROUPS>
 __global__ void __launch_bounds__(256 * GROUPS, 1)
 k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
-              float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l, int exp_mask) {
+              float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l, int exp_mask, int skip_in_rt, int skip_out_rt) {
+    // where the skip is added is a run-time choice for block 1 only; block 2 (SKIP_FIRST) always adds it on the way in (compile-time)
+    const bool skip_in = SKIP_FIRST ? true : (skip_in_rt != 0), skip_out = SKIP_FIRST ? false : (skip_out_rt != 0);
     constexpr int NF = lt_nf<HOP>();
     constexpr int GT = 256;                   // threads per group (8 warps)
     constexpr int SLOT = lh_slot_bytes<HOP, SKIP_FIRST>();
@@ -1314,7 +1319,8 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     float* fw_s = (float*)(small0 + GROUPS * SMALL);          // [7][32]
     float* fb_s = fw_s + 7 * C;                               // [32]
     float* cb_s = fb_s + C;                                   // [32]
-    float* hp_s = cb_s + C;                                   // [GROUPS][3 taps][64]: partial sums of the two extra conv rows (LH_HALO_MMA == 0)
+    float* cbs_s = cb_s + C;                                  // [32] conv bias * S16_ACT
+    float* hp_s = cbs_s + C;                                  // [GROUPS][3 taps][64]: partial sums of the two extra conv rows (LH_HALO_MMA == 0)
     uint64_t* bars = (uint64_t*)(hp_s + GROUPS * 3 * 64);     // [GROUPS][4]: conv MMAs, LVC MMAs, loads, (pad)
     uint32_t* tmem_base_s = (uint32_t*)(bars + 4 * GROUPS);
 
@@ -1339,7 +1345,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         const float4* src = reinterpret_cast<const float4*>(p.cw16);
         for (int i = tid; i < LH_CW_BYTES / 16; i += GT * GROUPS) reinterpret_cast<float4*>(cw)[i] = src[i];
         if (tid < 7 * C) fw_s[tid] = SKIP_FIRST ? p.first_w[tid] : 0.f;
-        if (tid < C) { fb_s[tid] = SKIP_FIRST ? p.first_b[tid] : 0.f; cb_s[tid] = p.conv_b[tid]; }
+        if (tid < C) { fb_s[tid] = SKIP_FIRST ? p.first_b[tid] : 0.f; cb_s[tid] = p.conv_b[tid]; cbs_s[tid] = p.conv_b[tid] * S16_ACT; }
     }
     fence_async_smem();
     tc_fence_before();
@@ -1368,7 +1374,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         const int ar0 = max(r_lo, 28 - t0), ar1 = min(r_hi, T - t0 + 28);
         const int i0 = max(0, 32 - t0), i1 = min(LT_AU, T - t0 + 32);
         uint32_t bytes = 0;
-        if (ar1 > ar0) bytes += (uint32_t)(ar1 - ar0) * 128u * (SKIP_FIRST ? 1u : 2u);
+        if (ar1 > ar0) bytes += (uint32_t)(ar1 - ar0) * 128u * ((SKIP_FIRST || !skip_in) ? 1u : 2u);
         if (SKIP_FIRST && i1 > i0) bytes += (uint32_t)(i1 - i0) * 4u;
 #pragma unroll
         for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) bytes += LH_LW_BYTES + 256;
@@ -1376,7 +1382,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         if (ar1 > ar0) {
             const size_t off = ((size_t)b * T + (t0 - 28 + ar0)) * C;
             bulk_g2s(a_t + ar0 * 128, x_in + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
-            if (!SKIP_FIRST) bulk_g2s(s_t + ar0 * 128, skip + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
+            if (!SKIP_FIRST && skip_in) bulk_g2s(s_t + ar0 * 128, skip + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
         }
         if (SKIP_FIRST && i1 > i0) bulk_g2s(au + i0, skip + (size_t)b * T + (t0 - 32 + i0), (uint32_t)(i1 - i0) * 4u, &bar[2]);
 #pragma unroll
@@ -1398,7 +1404,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         if (ar1 > ar0) {
             const size_t off = ((size_t)b * T + (t0 - 28 + ar0)) * C;
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x_in + off), "r"((uint32_t)(ar1 - ar0) * 128u) : "memory");
-            if (!SKIP_FIRST) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(skip + off), "r"((uint32_t)(ar1 - ar0) * 128u) : "memory");
+            if (!SKIP_FIRST && skip_in) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(skip + off), "r"((uint32_t)(ar1 - ar0) * 128u) : "memory");
         }
 #pragma unroll
         for (int fi = 0; fi < NF; ++fi) {
@@ -1435,56 +1441,12 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             group_sync(1 + g, GT);
         }
         LT_STAMP(2);
-#if !LH_TWOPASS
-        {
-            float fwr[7][4], fbr[4];
-            if (SKIP_FIRST) {
-#pragma unroll
-                for (int k = 0; k < 7; ++k) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(fw_s + k * C + c4 * 4);
-                    fwr[k][0] = w4.x; fwr[k][1] = w4.y; fwr[k][2] = w4.z; fwr[k][3] = w4.w;
-                }
-                const float4 b4 = *reinterpret_cast<const float4*>(fb_s + c4 * 4);
-                fbr[0] = b4.x; fbr[1] = b4.y; fbr[2] = b4.z; fbr[3] = b4.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 1536 / GT; ++i) {
-                const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
-                const bool active = ar < r_hi;
-                float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (active && t >= 0 && t < T) {
-                    const float4 xv = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
-                    float4 sk;
-                    if (SKIP_FIRST) {
-                        sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
-#pragma unroll
-                        for (int k = 0; k < 7; ++k) {
-                            const float a = au_s[ar + k + 1];
-                            sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
-                            sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
-                        }
-                    } else {
-                        sk = *reinterpret_cast<const float4*>(s_t + ar * 128 + c4 * 16);
-                    }
-                    pre = make_float4(xv.x + sk.x, xv.y + sk.y, xv.z + sk.z, xv.w + sk.w);
-                }
-                const float4 v = make_float4(lrelu02(pre.x), lrelu02(pre.y), lrelu02(pre.z), lrelu02(pre.w));
-                uint2 hi, lo;
-                split4_f16(v, hi, lo);
-                __syncwarp();   // every lane of the row has read its raw chunk before any lane overwrites the row
-                if (active) {
-                    const int sw = ar & 7;
-                    *reinterpret_cast<uint2*>(a_t + ar * 128 + (((c4 >> 1) ^ sw) << 4) + (c4 & 1) * 8) = hi;
-                    *reinterpret_cast<uint2*>(a_t + ar * 128 + (((4 + (c4 >> 1)) ^ sw) << 4) + (c4 & 1) * 8) = lo;
-                    if (SKIP_FIRST && ar >= 28 && ar < 28 + LT_TT)
-                        *reinterpret_cast<float4*>(s_t + (ar - 28) * 128 + ((c4 ^ ((ar - 28) & 7)) << 4)) = pre;
-                }
-            }
-        }
-#else
-        {   // pass 1: every thread pulls its 6 (row, channel quad) items into registers; one __syncwarp; pass 2: transform + store
+        {   // pass 1: every thread pulls its 6 (row, channel quad) items into registers; one __syncwarp; pass 2: transform + store.
+            // skip_in (first layer of a block): the rows are x and the skip is added here; later layers read z = x + skip, written so by
+            // the previous layer's epilogue (skip_out) -- the reference's "x += audio_down" of the next layer, moved to where the row is
+            // produced: 128 rows instead of the 130 + 2 dil rows this phase touches, same rounding sequence.
             float fwr[7][4], fbr[4];   // first-conv taps of this thread's channel quad: live in this phase only (reloaded per tile)
-            if (SKIP_FIRST) {
+            if (SKIP_FIRST && skip_in) {
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
                     const float4 w4 = *reinterpret_cast<const float4*>(fw_s + k * C + c4 * 4);
@@ -1500,7 +1462,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                 xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); sv[i] = xv[i];
                 if (ar < r_hi && t >= 0 && t < T) {
                     xv[i] = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
-                    if (!SKIP_FIRST) sv[i] = *reinterpret_cast<const float4*>(s_t + ar * 128 + c4 * 16);
+                    if (!SKIP_FIRST && skip_in) sv[i] = *reinterpret_cast<const float4*>(s_t + ar * 128 + c4 * 16);
                 }
             }
             __syncwarp();   // the 8 lanes of a row sit in one warp: every raw chunk has been read before any row is overwritten
@@ -1508,8 +1470,8 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             for (int i = 0; i < 1536 / GT; ++i) {
                 const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
                 const bool active = ar < r_hi;
-                float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (active && t >= 0 && t < T) {
+                float4 pre = xv[i];   // zero outside [0,T)
+                if (skip_in && active && t >= 0 && t < T) {
                     float4 sk;
                     if (SKIP_FIRST) {
                         sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
@@ -1524,9 +1486,8 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                     }
                     pre = make_float4(xv[i].x + sk.x, xv[i].y + sk.y, xv[i].z + sk.z, xv[i].w + sk.w);
                 }
-                const float4 v = make_float4(lrelu02(pre.x), lrelu02(pre.y), lrelu02(pre.z), lrelu02(pre.w));
                 uint2 hi, lo;
-                split4_f16(v, hi, lo);
+                split4_f16_pre(lrelu02_s(pre.x), lrelu02_s(pre.y), lrelu02_s(pre.z), lrelu02_s(pre.w), hi, lo);
                 if (active) {
                     const int sw = ar & 7;
                     *reinterpret_cast<uint2*>(a_t + ar * 128 + (((c4 >> 1) ^ sw) << 4) + (c4 & 1) * 8) = hi;
@@ -1536,7 +1497,6 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                 }
             }
         }
-#endif
         LT_STAMP(3);
         fence_async_smem();
         group_sync(1 + g, GT);
@@ -1614,25 +1574,23 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
 #endif
         {
             const int q3 = gw & 3, part3 = gw >> 2;   // lane quarter / which 16 of the 32 conv channels
-            // 16 accumulator columns of row yr -> y = lrelu(acc*inv_c + b) -> fp16 pieces -> the row's hi and lo chunks
+            // 16 accumulator columns of row yr -> S16_ACT * lrelu(acc*inv_c + b) (the pieces' prescale folded into the FFMA) -> pieces
+            const float inv_cs = inv_c * S16_ACT;
             auto emit_row = [&](const uint32_t (&v)[16], int yr) {
                 const int t = t0 - 1 + yr;
                 const bool in = (t >= 0 && t < T);
 #pragma unroll
                 for (int cc = 0; cc < 2; ++cc) {
-                    float4 y0, y1;
+                    float y[8];
                     const int cb0 = part3 * 16 + cc * 8;
-                    y0.x = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 0]), inv_c, cb_s[cb0 + 0])) : 0.f;
-                    y0.y = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 1]), inv_c, cb_s[cb0 + 1])) : 0.f;
-                    y0.z = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 2]), inv_c, cb_s[cb0 + 2])) : 0.f;
-                    y0.w = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 3]), inv_c, cb_s[cb0 + 3])) : 0.f;
-                    y1.x = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 4]), inv_c, cb_s[cb0 + 4])) : 0.f;
-                    y1.y = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 5]), inv_c, cb_s[cb0 + 5])) : 0.f;
-                    y1.z = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 6]), inv_c, cb_s[cb0 + 6])) : 0.f;
-                    y1.w = in ? lrelu02(fmaf(__uint_as_float(v[cc * 8 + 7]), inv_c, cb_s[cb0 + 7])) : 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float tt2 = fmaf(__uint_as_float(v[cc * 8 + e]), inv_cs, cbs_s[cb0 + e]);
+                        y[e] = in ? fmaxf(tt2, 0.2f * tt2) : 0.f;
+                    }
                     uint2 h0, l0, h1, l1;
-                    split4_f16(y0, h0, l0);
-                    split4_f16(y1, h1, l1);
+                    split4_f16_pre(y[0], y[1], y[2], y[3], h0, l0);
+                    split4_f16_pre(y[4], y[5], y[6], y[7], h1, l1);
                     const int chunk = part3 * 2 + cc, sw = yr & 7;
                     *reinterpret_cast<uint4*>(a_t + yr * 128 + ((chunk ^ sw) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
                     *reinterpret_cast<uint4*>(a_t + yr * 128 + (((4 + chunk) ^ sw) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
@@ -1698,15 +1656,30 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             const int r = q * 32 + lane, t = t0 + r;
             const int fi = (HOP >= LT_TT) ? 0 : r / HOP;       // warp-uniform (HOP is a multiple of 32)
             const size_t row = ((size_t)b * T + (t < T ? t : 0)) * C + part * 16;
-            float4 xs[4];                                      // residual base
+            float4 xs[4], so[4];                               // residual base x + skip; skip to add to the output (skip_out)
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                so[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (SKIP_FIRST) {
                     xs[c] = *reinterpret_cast<const float4*>(s_t + r * 128 + (((part * 4 + c) ^ (r & 7)) << 4));
+                    if (skip_out) {   // first_conv(audio) at this row, 4 channels at a time (audio position t + k - 3 = au_s[29 + r + k])
+                        const int o = part * 16 + c * 4;
+                        float4 sk = *reinterpret_cast<const float4*>(fb_s + o);
+#pragma unroll
+                        for (int k = 0; k < 7; ++k) {
+                            const float a = au_s[29 + r + k];
+                            const float4 w = *reinterpret_cast<const float4*>(fw_s + k * C + o);
+                            sk.x = fmaf(w.x, a, sk.x); sk.y = fmaf(w.y, a, sk.y); sk.z = fmaf(w.z, a, sk.z); sk.w = fmaf(w.w, a, sk.w);
+                        }
+                        so[c] = sk;
+                    }
                 } else {
                     xs[c] = *reinterpret_cast<const float4*>(x_in + row + c * 4);
-                    const float4 sk = *reinterpret_cast<const float4*>(skip + row + c * 4);
-                    xs[c].x += sk.x; xs[c].y += sk.y; xs[c].z += sk.z; xs[c].w += sk.w;
+                    if (skip_in || skip_out) {
+                        const float4 sk = *reinterpret_cast<const float4*>(skip + row + c * 4);
+                        if (skip_in) { xs[c].x += sk.x; xs[c].y += sk.y; xs[c].z += sk.z; xs[c].w += sk.w; }
+                        if (skip_out) so[c] = sk;
+                    }
                 }
             }
             LT_STAMP(8);
@@ -1732,6 +1705,9 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                     o4.y = xs[c].y + gate_st(fmaf(__uint_as_float(zs[c * 4 + 1]), inv_l, lb[c * 4 + 1]), fmaf(__uint_as_float(zt[c * 4 + 1]), inv_l, lb[32 + c * 4 + 1]));
                     o4.z = xs[c].z + gate_st(fmaf(__uint_as_float(zs[c * 4 + 2]), inv_l, lb[c * 4 + 2]), fmaf(__uint_as_float(zt[c * 4 + 2]), inv_l, lb[32 + c * 4 + 2]));
                     o4.w = xs[c].w + gate_st(fmaf(__uint_as_float(zs[c * 4 + 3]), inv_l, lb[c * 4 + 3]), fmaf(__uint_as_float(zt[c * 4 + 3]), inv_l, lb[32 + c * 4 + 3]));
+                    if (skip_out) {   // the next layer's "x += audio_down": (x + gate) + skip, the reference's rounding sequence
+                        o4.x = __fadd_rn(o4.x, so[c].x); o4.y = __fadd_rn(o4.y, so[c].y); o4.z = __fadd_rn(o4.z, so[c].z); o4.w = __fadd_rn(o4.w, so[c].w);
+                    }
                     *reinterpret_cast<float4*>(x_out + row + c * 4) = o4;
                 }
             }
@@ -2354,11 +2330,15 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
         hp.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
         const float inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * blk + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
         const int tiles = B * ((T + LT_TT - 1) / LT_TT);
+        // where the skip is added: block 1 adds it to the rows it produces (skip_out; only the first layer adds it on the way in), which
+        // drops the skip tile from the loads (-7 %); block 2 recomputes first_conv(audio) on the way in for every layer (in its gate
+        // epilogue the same work sits on the critical path: +7 %)
+        const int skip_in = (blk == 2 || layer == 0) ? 1 : 0, skip_out = (blk == 1 && layer < LAYERS - 1) ? 1 : 0;
         const int ng = (blk == 2 && s->lvc_groups == 3) ? 3 : 2;
         const int per = (tiles + ng - 1) / ng, grid = per < s->sm_count ? per : s->sm_count;
-        if (blk == 1)     k_lvc_layer_h<64, false, 2><<<grid, 512, lh_smem_bytes<64, false, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp);
-        else if (ng == 3) k_lvc_layer_h<256, true, 3><<<grid, 768, lh_smem_bytes<256, true, 3>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp);
-        else              k_lvc_layer_h<256, true, 2><<<grid, 512, lh_smem_bytes<256, true, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp);
+        if (blk == 1)     k_lvc_layer_h<64, false, 2><<<grid, 512, lh_smem_bytes<64, false, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp, skip_in, skip_out);
+        else if (ng == 3) k_lvc_layer_h<256, true, 3><<<grid, 768, lh_smem_bytes<256, true, 3>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp, skip_in, skip_out);
+        else              k_lvc_layer_h<256, true, 2><<<grid, 512, lh_smem_bytes<256, true, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp, skip_in, skip_out);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_h failed: ") + cudaGetErrorString(e); return -3; }
         ++*launches;
