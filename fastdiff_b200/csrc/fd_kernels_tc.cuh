@@ -1254,7 +1254,7 @@ constexpr int LH_LW_BYTES = 24576;                   // per frame: 3 taps x 64 r
 constexpr int LH_CW_BYTES = 3 * C * 128;             // 12288
 template <int HOP, bool SKIP_FIRST>
 __host__ __device__ constexpr int lh_slot_bytes() { return LH_A_BYTES + (SKIP_FIRST ? LH_XS_BYTES : LH_A_BYTES) + lt_nf<HOP>() * LH_LW_BYTES; }
-constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C + C) * 4 + 3 * 3 * 64 * 4 + 192;   // conv W, first_w, first_b, conv_b, barriers + tmem ptr
+constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C + C) * 4 + 3 * 3 * 64 * 4 + 3 * 512 + 192;   // conv W, first_w, first_b, conv_b, barriers + tmem ptr
 template <int HOP, bool SKIP_FIRST, int GROUPS>
 constexpr int lh_smem_bytes() { return GROUPS * (lh_slot_bytes<HOP, SKIP_FIRST>() + lt_small_bytes<HOP>()) + LH_SHARED_BYTES + 1024; }
 
@@ -1282,9 +1282,6 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #ifndef LH_GATE_ASM
 #define LH_GATE_ASM 1
-#endif
-#ifndef LH_HALO_MMA
-#define LH_HALO_MMA 0   // 1: the two extra conv rows from a second MMA pass; 0: FFMA partial sums on warps 2-7 while the MMAs run (faster: measured)
 #endif
 __device__ __forceinline__ float gate_st(float a, float b) {
     const float bc = fmaxf(b, -15.f);   // E = e^-2b must stay finite (E -> 0 for large b is harmless); tanh(-15) = -1 to fp32 precision
@@ -1320,8 +1317,9 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     float* fb_s = fw_s + 7 * C;                               // [32]
     float* cb_s = fb_s + C;                                   // [32]
     float* cbs_s = cb_s + C;                                  // [32] conv bias * S16_ACT
-    float* hp_s = cbs_s + C;                                  // [GROUPS][3 taps][64]: partial sums of the two extra conv rows (LH_HALO_MMA == 0)
-    uint64_t* bars = (uint64_t*)(hp_s + GROUPS * 3 * 64);     // [GROUPS][4]: conv MMAs, LVC MMAs, loads, (pad)
+    float* hp_s = cbs_s + C;                                  // [GROUPS][3][64] (unused since the halo rows are carried / come from the second MMA pass)
+    unsigned char* carry_s = (unsigned char*)(hp_s + GROUPS * 3 * 64);   // [GROUPS][2][256 B]: Y rows 0, 1 of the previous tile (pieces)
+    uint64_t* bars = (uint64_t*)(carry_s + GROUPS * 512);     // [GROUPS][4]: conv MMAs, LVC MMAs, loads, (pad)
     uint32_t* tmem_base_s = (uint32_t*)(bars + 4 * GROUPS);
 
     const int tid = threadIdx.x, g = tid / GT, gt = tid % GT, gw = gt >> 5, lane = tid & 31;
@@ -1331,7 +1329,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     unsigned char* lw = slot + LW_OFF;
     unsigned char* small = small0 + g * SMALL;
     uint64_t* bar = bars + 4 * g;
-    float* hp = hp_s + g * 3 * 64;
+    unsigned char* carry = carry_s + g * 512;
 
     if (tid == 0) {
         for (int i = 0; i < 4 * GROUPS; ++i) mbar_init(&bars[i], 1);
@@ -1364,7 +1362,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     const uint32_t cw_u = smem_u32(cw);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
 
-    const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt, tstride = gridDim.x * GROUPS;
+    const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt;
     const int r_lo = 27 - dil, r_hi = 157 + dil;   // A rows ar <-> t = t0 - 28 + ar that the 130 conv outputs touch
 
     auto issue_loads = [&](int tile, int buf) {
@@ -1413,9 +1411,16 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         }
     };
 
-    int tile = blockIdx.x * GROUPS + g;
-    if (tile < total && gw_u == 0) {
-        if (elect_one()) { issue_loads(tile, 0); if ((exp_mask & 8) && tile + tstride < total) prefetch_l2(tile + tstride); }
+    // Tile walk: every group owns one contiguous chunk of tiles and walks it in DESCENDING time order.  The two conv rows past the
+    // M = 128 tile that the LVC taps of the last output rows need (yr = 128, 129) are then exactly Y rows 0, 1 of the tile processed
+    // just before (t0 + 128): they are carried over in shared memory (256 B) instead of being recomputed.  Only the first tile of a
+    // chunk and the last tile of an utterance have no predecessor: they get the rows from a second MMA pass over A rows +128 (same
+    // instruction sequence as the carried rows -> the same bits, whatever the chunking or the batch composition).
+    const int ngroups = gridDim.x * GROUPS, chunk = (total + ngroups - 1) / ngroups;
+    const int tile_lo = (blockIdx.x * GROUPS + g) * chunk, tile_hi = min(total, tile_lo + chunk) - 1;
+    int tile = tile_hi;
+    if (tile >= tile_lo && gw_u == 0) {
+        if (elect_one()) { issue_loads(tile, 0); if ((exp_mask & 8) && tile - 1 >= tile_lo) prefetch_l2(tile - 1); }
         __syncwarp();
     }
 #ifdef FD_LVC_TIMELINE
@@ -1423,12 +1428,12 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     int tile_no = -1;
 #endif
     uint32_t parity = 0;
-    int b = tile / ntt, tt = tile % ntt;                       // maintained incrementally (no per-tile division)
-    const int bstep = tstride / ntt, ttstep = tstride % ntt;
-    for (; tile < total; tile += tstride, parity ^= 1) {
+    int b = tile >= 0 ? tile / ntt : 0, tt = tile >= 0 ? tile % ntt : 0;   // maintained incrementally (no per-tile division)
+    for (; tile >= tile_lo; --tile, parity ^= 1) {
 #ifdef FD_LVC_TIMELINE
         ++tile_no;
 #endif
+        const bool have_carry = (tile != tile_hi) && (tt != ntt - 1);   // the previous tile of this group was (b, tt + 1)
         LT_STAMP(0);
         const int t0 = tt * LT_TT;
         const float* lbias = (const float*)(small + parity * (SMALL / 2));
@@ -1523,7 +1528,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                 }
                 // second pass over A rows +128: its output rows 0 and 1 are the conv rows yr = 128, 129 that the LVC taps of the last
                 // output rows need.  The other 126 rows read past the A tile (whatever bytes follow it in this slot) and are never used.
-                if (LH_HALO_MMA && !(exp_mask & 1))
+                if (!have_carry)
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const uint32_t sh = (uint32_t)(128 + 27 + (k - 1) * dil) * 128u;
@@ -1540,43 +1545,16 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             }
             __syncwarp();
         }
-#if !LH_HALO_MMA
-        if (gt >= 64) {   // conv outputs yr = 128, 129 on FFMA while the MMAs run (warps 2-7: not the issuing warp): thread = (tap, row, co)
-            const int h = gt - 64, o64 = h & 63, k = h >> 6, yr = 128 + (o64 >> 5), co = o64 & 31;
-            const int ar = yr + 27 + (k - 1) * dil;
-            float acc = 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint4 ah = *reinterpret_cast<const uint4*>(a_t + ar * 128 + ((c ^ (ar & 7)) << 4));
-                const uint4 al = *reinterpret_cast<const uint4*>(a_t + ar * 128 + (((4 + c) ^ (ar & 7)) << 4));
-                const uint4 wh = *reinterpret_cast<const uint4*>(cw + k * 4096 + co * 128 + ((c ^ (co & 7)) << 4));
-                const uint4 wl = *reinterpret_cast<const uint4*>(cw + k * 4096 + co * 128 + (((4 + c) ^ (co & 7)) << 4));
-                const uint32_t ahv[4] = {ah.x, ah.y, ah.z, ah.w}, alv[4] = {al.x, al.y, al.z, al.w};
-                const uint32_t whv[4] = {wh.x, wh.y, wh.z, wh.w}, wlv[4] = {wl.x, wl.y, wl.z, wl.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 a1 = __half22float2(*reinterpret_cast<const __half2*>(&ahv[e])), a2 = __half22float2(*reinterpret_cast<const __half2*>(&alv[e]));
-                    const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&whv[e])), w2 = __half22float2(*reinterpret_cast<const __half2*>(&wlv[e]));
-                    acc = fmaf(a1.x + a2.x, w1.x + w2.x, acc);
-                    acc = fmaf(a1.y + a2.y, w1.y + w2.y, acc);
-                }
-            }
-            hp[k * 64 + o64] = acc;
-        }
-#endif
         // ---------------- phase 3: y = lrelu(conv + b) -> fp16 pieces, rows of the Y tile (over the A tile) ----------------
         LT_STAMP(5);
         mbar_wait(&bar[0], parity);
         tc_fence_after();
         LT_STAMP(6);
-#if !LH_HALO_MMA
-        group_sync(1 + g, GT);   // Y aliases A: the partial-sum threads have finished READING A; hp is visible
-#endif
         {
             const int q3 = gw & 3, part3 = gw >> 2;   // lane quarter / which 16 of the 32 conv channels
             // 16 accumulator columns of row yr -> S16_ACT * lrelu(acc*inv_c + b) (the pieces' prescale folded into the FFMA) -> pieces
             const float inv_cs = inv_c * S16_ACT;
-            auto emit_row = [&](const uint32_t (&v)[16], int yr) {
+            auto emit_row = [&](const uint32_t (&v)[16], int yr, unsigned char* copy_to) {
                 const int t = t0 - 1 + yr;
                 const bool in = (t >= 0 && t < T);
 #pragma unroll
@@ -1594,29 +1572,24 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                     const int chunk = part3 * 2 + cc, sw = yr & 7;
                     *reinterpret_cast<uint4*>(a_t + yr * 128 + ((chunk ^ sw) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
                     *reinterpret_cast<uint4*>(a_t + yr * 128 + (((4 + chunk) ^ sw) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                    if (copy_to) {   // rows 0, 1 again, for the next tile of this group (row yr of a 2-row image; 128 & 7 == 0, 129 & 7 == 1)
+                        *reinterpret_cast<uint4*>(copy_to + yr * 128 + ((chunk ^ sw) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                        *reinterpret_cast<uint4*>(copy_to + yr * 128 + (((4 + chunk) ^ sw) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                    }
                 }
             };
             uint32_t v[16];
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q3 * 32) << 16) + part3 * 16, v);
             tmem_ld_wait();
-            emit_row(v, q3 * 32 + lane);
-#if LH_HALO_MMA
-            if (q3 == 0) {   // rows 128, 129 = rows 0, 1 of the second pass (TMEM lanes 0, 1)
+            emit_row(v, q3 * 32 + lane, (q3 == 0 && lane < 2) ? carry + parity * 256 : nullptr);
+            if (have_carry) {
+                if (gt < 16)   // rows 128, 129 = rows 0, 1 of the previous tile, already pieces in exactly this 256-byte layout
+                    reinterpret_cast<uint4*>(a_t + 128 * 128)[gt] = reinterpret_cast<const uint4*>(carry + (parity ^ 1) * 256)[gt];
+            } else if (q3 == 0) {   // rows 128, 129 = rows 0, 1 of the second pass (TMEM lanes 0, 1)
                 tmem_ld_32x32b_x16(tmem_base + D2_COL + part3 * 16, v);
                 tmem_ld_wait();
-                if (lane < 2) emit_row(v, 128 + lane);
+                if (lane < 2) emit_row(v, 128 + lane, nullptr);
             }
-#else
-            if (gt < 64) {   // rows 128, 129 from the FFMA partial sums
-                const int yr2 = 128 + (gt >> 5), co = gt & 31, t2 = t0 - 1 + yr2;
-                const float accv = hp[gt] + hp[64 + gt] + hp[128 + gt];
-                const float y = (t2 >= 0 && t2 < T) ? lrelu02(fmaf(accv, inv_c, cb_s[co])) : 0.f;
-                uint16_t h16, l16;
-                f16_split(y, S16_ACT, h16, l16);
-                *reinterpret_cast<uint16_t*>(a_t + yr2 * 128 + (((co >> 3) ^ (yr2 & 7)) << 4) + (co & 7) * 2) = h16;
-                *reinterpret_cast<uint16_t*>(a_t + yr2 * 128 + (((4 + (co >> 3)) ^ (yr2 & 7)) << 4) + (co & 7) * 2) = l16;
-            }
-#endif
         }
         fence_async_smem();
         tc_fence_before();
@@ -1687,8 +1660,8 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             tc_fence_after();
             LT_STAMP(9);
             // LVC MMAs complete: the A/Y tile and the kernels are free -> fetch the next tile while this one is gated
-            if (gw_u == 0 && tile + tstride < total) {
-                if (elect_one()) { issue_loads(tile + tstride, (int)(parity ^ 1)); if ((exp_mask & 8) && tile + 2 * tstride < total) prefetch_l2(tile + 2 * tstride); }
+            if (gw_u == 0 && tile - 1 >= tile_lo) {
+                if (elect_one()) { issue_loads(tile - 1, (int)(parity ^ 1)); if ((exp_mask & 8) && tile - 2 >= tile_lo) prefetch_l2(tile - 2); }
                 __syncwarp();
             }
             uint32_t zs[16], zt[16];
@@ -1714,8 +1687,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         }
         tc_fence_before();
         group_sync(1 + g, GT);   // the group's TMEM columns and xs rows are free for its next tile
-        b += bstep; tt += ttstep;
-        if (tt >= ntt) { tt -= ntt; ++b; }
+        if (--tt < 0) { tt = ntt - 1; --b; }
     }
     tc_fence_before();
     __syncthreads();
