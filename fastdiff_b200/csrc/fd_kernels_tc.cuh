@@ -479,7 +479,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             // into the SWIZZLE_128B smem image of the LVC B operand -- per (layer, tap) 64 rows (o) of 128 B = [32 i hi | 32 i lo],
             // 16-byte chunk c at position c ^ (o & 7) -- in the SAME 24,576 bytes the fp32 image occupies.  Lane n holds element
             // (l, k, o, i) and the 32 lanes of a warp the 32 i of one row.  The 64 biases per layer stay fp32.
-            const bool pieces = F16 && blk >= 1;
+            const bool pieces = F16 && blk >= 1 && !(exp_mask & 32);   // exp 32: timing experiment, fp32 full-line stores for every block (WRONG for the LVC consumer)
             const int rem = n % KPL;
             const bool is_w = rem < KK * LVC_OUT;          // warp-uniform: 6144 and KPL are multiples of 32
             // two 16-bit stores per value (a warp covers the 64 contiguous bytes of the hi half and of the lo half of one row: full sectors)
@@ -1365,7 +1365,9 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt;
     const int r_lo = 27 - dil, r_hi = 157 + dil;   // A rows ar <-> t = t0 - 28 + ar that the 130 conv outputs touch
 
-    auto issue_loads = [&](int tile, int buf) {
+    // keep_lw: the tile uses the same frame as the one just processed (hop 256: two tiles per frame, walked back to back): its
+    // predicted kernels are already in place, only the 64 biases (double-buffered with the audio window) are fetched again
+    auto issue_loads = [&](int tile, int buf, bool keep_lw) {
         const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
         float* lbias = (float*)(small + buf * (SMALL / 2));
         float* au = lbias + NF * 64;
@@ -1375,7 +1377,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         if (ar1 > ar0) bytes += (uint32_t)(ar1 - ar0) * 128u * ((SKIP_FIRST || !skip_in) ? 1u : 2u);
         if (SKIP_FIRST && i1 > i0) bytes += (uint32_t)(i1 - i0) * 4u;
 #pragma unroll
-        for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) bytes += LH_LW_BYTES + 256;
+        for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) bytes += (keep_lw ? 0 : LH_LW_BYTES) + 256;
         mbar_expect_tx(&bar[2], bytes);
         if (ar1 > ar0) {
             const size_t off = ((size_t)b * T + (t0 - 28 + ar0)) * C;
@@ -1388,7 +1390,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             const int f = t0 / HOP + fi;
             if (f < Tm) {
                 const float* src = kern + ((size_t)b * Tm + f) * KCN;
-                bulk_g2s(lw + fi * LH_LW_BYTES, src, LH_LW_BYTES, &bar[2]);       // 3 taps x 64 rows x 128 B of pieces, ready to use
+                if (!keep_lw) bulk_g2s(lw + fi * LH_LW_BYTES, src, LH_LW_BYTES, &bar[2]);   // 3 taps x 64 rows x 128 B of pieces, ready to use
                 bulk_g2s(lbias + fi * 64, src + KK * LVC_OUT, 256, &bar[2]);
             }
         }
@@ -1420,7 +1422,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     const int tile_lo = (blockIdx.x * GROUPS + g) * chunk, tile_hi = min(total, tile_lo + chunk) - 1;
     int tile = tile_hi;
     if (tile >= tile_lo && gw_u == 0) {
-        if (elect_one()) { issue_loads(tile, 0); if ((exp_mask & 8) && tile - 1 >= tile_lo) prefetch_l2(tile - 1); }
+        if (elect_one()) { issue_loads(tile, 0, false); if ((exp_mask & 8) && tile - 1 >= tile_lo) prefetch_l2(tile - 1); }
         __syncwarp();
     }
 #ifdef FD_LVC_TIMELINE
@@ -1661,7 +1663,10 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             LT_STAMP(9);
             // LVC MMAs complete: the A/Y tile and the kernels are free -> fetch the next tile while this one is gated
             if (gw_u == 0 && tile - 1 >= tile_lo) {
-                if (elect_one()) { issue_loads(tile - 1, (int)(parity ^ 1)); if ((exp_mask & 8) && tile - 2 >= tile_lo) prefetch_l2(tile - 2); }
+                if (elect_one()) {   // tile - 1 = (b, tt - 1) shares this tile's frame iff hop 256 and tt is odd
+                    issue_loads(tile - 1, (int)(parity ^ 1), HOP == 2 * LT_TT && (tt & 1) && !(exp_mask & 16));
+                    if ((exp_mask & 8) && tile - 2 >= tile_lo) prefetch_l2(tile - 2);
+                }
                 __syncwarp();
             }
             uint32_t zs[16], zt[16];
