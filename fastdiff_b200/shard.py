@@ -31,7 +31,7 @@ class ShardedFastDiff:
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.engine = Engine(device=self.device, lib_path=lib_path)
         if self.rank == 0:
             from .weights import pack_state_dict

@@ -223,6 +223,26 @@ def test_full_size_properties(synth, cuda_lib):
 
 
 @gpu
+def test_time_shard_sampler_world1_equals_sampler(synth, cuda_lib):
+    """SURVEY.md 8f.4 plumbing on one GPU (world 1: no halo, no exchange): per-step fd_sample calls with sliced reference-order
+    noise == the single-call sampler bitwise.  The 2-rank halo exchange is covered by tests/test_timeshard_gloo.py (CPU, emulated
+    source) and tests/gpu_timeshard_check.py (2 GPUs, NCCL)."""
+    import fastdiff_b200 as fb
+    from fastdiff_b200.synthetic import make_inputs
+    from fastdiff_b200.timeshard import TimeShardedSampler
+    sd, _ = synth
+    net = _net(sd)
+    B, Tm = 2, 40
+    _, mel = make_inputs(B, Tm, 12)
+    dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
+    torch.manual_seed(3)
+    ref = fb.sampling_given_noise_schedule(net, (B, 1, Tm * 256), dh, torch.FloatTensor(N4), condition=mel.cuda())
+    torch.manual_seed(3)
+    got = TimeShardedSampler(net.engine()).sample((B, 1, Tm * 256), dh, torch.FloatTensor(N4), mel)
+    assert torch.equal(got, ref)
+
+
+@gpu
 def test_errors_are_loud(synth, cuda_lib):
     import fastdiff_b200 as fb
     from fastdiff_b200._lib import FdError
