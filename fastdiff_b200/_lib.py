@@ -43,6 +43,7 @@ SYMBOLS = {
     "fd_sample": (C.c_int, [_P, _P, _P, C.POINTER(fd_step), C.c_int, _P, C.c_int, C.c_uint64, C.c_int, C.c_int, _P,
                             C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "fd_wav_int16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "fd_mel_frontend": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fd_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_size_t), C.c_int, C.c_int, _P, _P]),
     "fd_launch_count": (C.c_uint64, [_P]),
     "fd_timing_enable": (C.c_int, [_P, C.c_int]),

@@ -623,6 +623,20 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
     return FD_OK;
 }
 
+// The step before the path: wav (B, n) -> log10-mel (B, 80, 1 + n/256), the reference's process_utterance
+// (data_gen/tts/data_gen_utils.py:93-147).  fb_dev (80, 513) / range_dev (80, 2): librosa.filters.mel table and its non-zero
+// bin ranges, built by the host layer (fastdiff_b200/mel.py).  Needs no weights.
+extern "C" int fd_mel_frontend(fd_handle* h, const float* wav_dev, int B, int n_samples, const float* fb_dev, const int32_t* range_dev,
+                               float* mel_dev, void* stream) {
+    if (!h || !wav_dev || !fb_dev || !range_dev || !mel_dev || B < 1 || n_samples < 1) return fail(h, FD_ERR_INVALID, "fd_mel_frontend: bad argument");
+    FD_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Tm = 1 + n_samples / MEL_HOP;
+    FD_LAUNCH(k_mel_frontend, dim3(Tm, B), dim3(256), 0, st, wav_dev, n_samples, fb_dev, (const int*)range_dev, mel_dev, Tm);
+    FD_CHECK_LAUNCH(h, "k_mel_frontend");
+    return FD_OK;
+}
+
 extern "C" int fd_wav_int16(fd_handle* h, const float* x_dev, int16_t* out_dev, int B, int L, void* workspace_dev, void* stream) {
     if (!h || !x_dev || !out_dev || !workspace_dev || B < 1 || L < 1) return fail(h, FD_ERR_INVALID, "fd_wav_int16: bad argument");
     FD_CUDA(h, cudaSetDevice(h->device));

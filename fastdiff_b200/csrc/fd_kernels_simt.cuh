@@ -786,6 +786,63 @@ __global__ void __launch_bounds__(256) k_wav_int16(const float* __restrict__ x, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// The step before the path: wav -> log10-mel, the reference's `process_utterance`
+// (data_gen/tts/data_gen_utils.py:93-147): librosa 0.8.0 stft(n_fft 1024, hop 256, periodic Hann, centre padding with zeros),
+// |.|, librosa.filters.mel(22050, 1024, 80, 80, 7600) (table + non-zero ranges built on the host), log10(max(1e-6, .)).
+// One CTA = one frame: 1024 samples centred at f*256, window, radix-2 decimation-in-time FFT in shared memory (bit-reversed
+// load, 10 stages of 512 butterflies), magnitudes of bins 0..512, 80 triangular filters.  grid = (T', B), block = 256.
+// ------------------------------------------------------------------------------------------------
+constexpr int MEL_NFFT = 1024, MEL_HOP = 256, MEL_BINS = 513, MEL_N = 80;
+
+__device__ __forceinline__ int mel_bitrev10(int j) {
+    int r = 0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) r |= ((j >> i) & 1) << (9 - i);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_mel_frontend(const float* __restrict__ wav, int n, const float* __restrict__ fb,
+                                                      const int* __restrict__ fb_range, float* __restrict__ mel, int Tm) {
+    __shared__ float re[MEL_NFFT], im[MEL_NFFT];
+    __shared__ float twc[MEL_NFFT / 2], tws[MEL_NFFT / 2];
+    __shared__ float mag[MEL_BINS + 3];
+    const int tid = threadIdx.x, f = blockIdx.x, b = blockIdx.y;
+    for (int i = tid; i < MEL_NFFT / 2; i += 256) {   // e^{-2 pi i k / 1024}
+        float sn, cs;
+        sincospif(-2.0f * (float)i / (float)MEL_NFFT, &sn, &cs);
+        twc[i] = cs; tws[i] = sn;
+    }
+    for (int j = tid; j < MEL_NFFT; j += 256) {
+        const long pos = (long)f * MEL_HOP - MEL_NFFT / 2 + j;
+        const float v = (pos >= 0 && pos < n) ? wav[(size_t)b * n + pos] : 0.f;
+        const float w = 0.5f - 0.5f * cospif(2.0f * (float)j / (float)MEL_NFFT);   // periodic Hann
+        const int r = mel_bitrev10(j);
+        re[r] = v * w; im[r] = 0.f;
+    }
+    __syncthreads();
+    for (int half = 1; half < MEL_NFFT; half <<= 1) {
+        for (int t = tid; t < MEL_NFFT / 2; t += 256) {
+            const int k = t & (half - 1), i0 = ((t - k) << 1) + k, i1 = i0 + half;
+            const int tw = k * (MEL_NFFT / 2 / half);
+            const float c = twc[tw], s2 = tws[tw];
+            const float tr = re[i1] * c - im[i1] * s2, ti = re[i1] * s2 + im[i1] * c;
+            const float ur = re[i0], ui = im[i0];
+            re[i1] = ur - tr; im[i1] = ui - ti;
+            re[i0] = ur + tr; im[i0] = ui + ti;
+        }
+        __syncthreads();
+    }
+    for (int k = tid; k < MEL_BINS; k += 256) mag[k] = sqrtf(re[k] * re[k] + im[k] * im[k]);
+    __syncthreads();
+    if (tid < MEL_N) {
+        const int lo = fb_range[2 * tid], hi = fb_range[2 * tid + 1];
+        float acc = 0.f;
+        for (int k = lo; k < hi; ++k) acc = fmaf(fb[tid * MEL_BINS + k], mag[k], acc);
+        mel[((size_t)b * MEL_N + tid) * Tm + f] = log10f(fmaxf(1e-6f, acc));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Debug/inspection gathers used by fd_debug_read (tests only): channels-last -> the reference's layouts.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cl_to_ncl(const float* __restrict__ in, float* __restrict__ out, int B, int T,

@@ -126,6 +126,14 @@ int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const fd_step* s
               const float* noise_dev, int n_noise, uint64_t seed, int fill_xT, int ddim,
               float* seq_dev, int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* The step before the path: waveform -> log10-mel on the device, the reference's process_utterance
+ * (data_gen/tts/data_gen_utils.py:93-147: librosa 0.8.0 stft(1024, hop 256, periodic Hann, zero centre padding), magnitude,
+ * librosa.filters.mel(22050, 1024, 80, 80, 7600), log10(max(1e-6, .))).  wav_dev (B, n_samples) fp32 -> mel_dev
+ * (B, 80, 1 + n_samples/256) fp32.  fb_dev (80, 513) fp32 / range_dev (80, 2) int32: the mel filter table and the [lo, hi)
+ * range of non-zero FFT bins of every filter (built by fastdiff_b200/mel.py).  Needs no weights. */
+int fd_mel_frontend(fd_handle* h, const float* wav_dev, int B, int n_samples, const float* fb_dev, const int32_t* range_dev,
+                    float* mel_dev, void* stream);
+
 /* The step after the path: per-utterance peak normalisation and int16 encode on the device --
  * wav_pred / wav_pred.abs().max() (modules/FastDiff/task/FastDiff.py:110) followed by utils/audio.py:11-16
  * (wav *= 32767; astype(int16)).  x_dev (B,1,L) fp32 -> out_dev (B,L) int16, bit-identical to the reference's float ops.

@@ -48,6 +48,8 @@ static inline float __fsub_rn(float a, float b) { volatile float r = a - b; retu
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline void sincospif(float x, float* s, float* c) { *s = (float)sin(3.14159265358979323846 * (double)x); *c = (float)cos(3.14159265358979323846 * (double)x); }
+static inline float cospif(float x) { return (float)cos(3.14159265358979323846 * (double)x); }
 static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
