@@ -1,5 +1,10 @@
 // tcgen05 / TMEM / TMA kernels (sm_100a) for the heavy contractions.
 //
+// Two families share this file.  The DEFAULT mode FD_MODE_TC_3XF16 runs kind::f16 MMAs on fp16 hi/lo pieces of power-of-two
+// prescaled operands (fd_common.cuh: f16_split, S16_*): k_kc_gemm_tc2<true, 16>, k_lvc_layer_h,
+// k_kp_hidden_tc.  The older kind::tf32 family (k_kc_gemm_tc, k_kc_gemm_tc2<false, 8>, k_lvc_layer_tc, and still the only
+// version of k_dblock0_tc / k_upsample_tc) is described first:
+//
 // Arithmetic: kind::tf32 MMAs with fp32 accumulation in TMEM.  FD_MODE_TC_3XTF32 splits BOTH operands into
 // explicit tf32 pieces  x = hi + lo  (hi = RN_tf32(x), lo = RN_tf32(x - hi); low 13 mantissa bits stored as zero, so
 // the tensor core's fp32->tf32 conversion is exact whatever its rounding) and accumulates hi*hi + hi*lo + lo*hi:
@@ -494,7 +499,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             // warp-uniform; broadcast from lane 0 so that ptxas KNOWS it (otherwise every store below re-materialises its uniform
             // memory descriptor with two R2UR: 40% of the epilogue's instructions)
             const bool as_pieces = __shfl_sync(0xffffffffu, (int)(pieces && is_w), 0) != 0;
-            const int odd = lane & 1;
+            [[maybe_unused]] const int odd = lane & 1;
             auto put_pieces = [&](uint16_t* ph, uint16_t* pl, float accv) {
                 const float sv = fmaf(accv, inv_s, bv_s);
                 uint16_t h16, l16;
@@ -1241,9 +1246,13 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
 //   * the raw x rows are transformed in place to pieces (8 lanes per row: LDS.128 -> STS.64 hi + STS.64 lo);
 //   * block 2 keeps xs = x + first_conv(audio) (fp32) of the 128 output rows in smem for the gate epilogue instead of recomputing
 //     it (7 FMA per channel) and re-reading x from global;
-//   * all 8 warps of a group take part in the conv epilogue (2 per TMEM lane quarter, 16 channels each); the two extra conv rows
-//     (yr = 128, 129) come from a second MMA pass over A rows +128 whose rows 0, 1 are read back -- no FFMA side path, and every
-//     conv output is produced by the same instruction sequence whatever the tiling (batch-composition independent bits);
+//   * all 8 warps of a group take part in the conv epilogue (2 per TMEM lane quarter, 16 channels each);
+//   * tile walk: every group owns a contiguous chunk of tiles and walks it in DESCENDING time order, so the two extra conv rows
+//     (yr = 128, 129) are Y rows 0, 1 of the tile processed just before and are carried over in 256 B of smem; only chunk starts
+//     and utterance ends take them from a second MMA pass over A rows +128 -- the same instruction sequence, hence the same bits:
+//     every conv output is independent of the tiling and of the batch composition;
+//   * block 1 adds the skip to the rows it PRODUCES (skip_out: the next layer's x += audio_down, same rounding order), so only the
+//     first layer of the block loads the skip tile; block 2 recomputes first_conv(audio) on the way in (compile-time);
 //   * sigmoid(a) * tanh(b) = (1 - E) / ((1 + e^-a)(1 + E)), E = e^-2b: two ex2 and ONE rcp per gate.
 // Scales: A pieces hold v*S16_ACT, conv weights w*S (per tensor, SCALES16), predicted kernels w*S16_KERN; the epilogues multiply
 // the accumulators by inv_c = 1/(S16_ACT*S) and inv_l = 1/(S16_ACT*S16_KERN).
@@ -1254,7 +1263,7 @@ constexpr int LH_LW_BYTES = 24576;                   // per frame: 3 taps x 64 r
 constexpr int LH_CW_BYTES = 3 * C * 128;             // 12288
 template <int HOP, bool SKIP_FIRST>
 __host__ __device__ constexpr int lh_slot_bytes() { return LH_A_BYTES + (SKIP_FIRST ? LH_XS_BYTES : LH_A_BYTES) + lt_nf<HOP>() * LH_LW_BYTES; }
-constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C + C) * 4 + 3 * 3 * 64 * 4 + 3 * 512 + 192;   // conv W, first_w, first_b, conv_b, barriers + tmem ptr
+constexpr int LH_SHARED_BYTES = LH_CW_BYTES + (7 * C + C + C + C) * 4 + 3 * 3 * 64 * 4 + 3 * 512 + 192;   // conv W, first_w, first_b, conv_b (x1, x16), spare, carried rows, barriers + tmem ptr
 template <int HOP, bool SKIP_FIRST, int GROUPS>
 constexpr int lh_smem_bytes() { return GROUPS * (lh_slot_bytes<HOP, SKIP_FIRST>() + lt_small_bytes<HOP>()) + LH_SHARED_BYTES + 1024; }
 
