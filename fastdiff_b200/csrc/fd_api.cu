@@ -31,6 +31,7 @@ struct fd_handle {
     int tc_upsample = 1;         // LVC-block upsample (blocks 1, 2) on tensor cores in the TC modes (option "tc_upsample")
     int tc_dblock = 1;           // DBlock 0 on tensor cores in the TC modes (option "tc_dblock")
     int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
+    int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
                                  // (option "overlap"; forked from / joined into the caller's stream with events inside every call)
@@ -107,8 +108,8 @@ static WsLayout ws_layout(int B, int Tm) {
     auto al = [](size_t v) { return (v + 63) & ~(size_t)63; };  // 256-byte granules
     const size_t L = (size_t)Tm * HOP_TOTAL;
     size_t o = 0;
-    w.emb = o;    o += al((size_t)B * EMB_OUT);
-    w.cnoise = o; o += al((size_t)NBLK * B * COND);
+    w.emb = o;    o += al((size_t)EMB_SLOTS * B * EMB_OUT);          // one slot per reverse step of a chunk of the schedule
+    w.cnoise = o; o += al((size_t)EMB_SLOTS * NBLK * B * COND);
     w.hk = o;     o += al((size_t)NBLK * B * (Tm + 2) * HID);   // hk, hk_hi, hk_lo are contiguous (one memset)
     w.hk_hi = o;  o += al((size_t)NBLK * B * (Tm + 2) * HID);
     w.hk_lo = o;  o += al((size_t)NBLK * B * (Tm + 2) * HID);
@@ -283,6 +284,10 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_kp")) { h->tc_kp = (int)value; return FD_OK; }
     if (!strcmp(key, "overlap")) { h->overlap = (int)value; return FD_OK; }
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
+    if (!strcmp(key, "emb_slots")) {
+        if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
+        h->emb_slots = (int)value; return FD_OK;
+    }
     if (!strcmp(key, "tc_upsample")) { h->tc_upsample = (int)value; return FD_OK; }
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
@@ -354,11 +359,30 @@ static int setup_attrs(fd_handle* h) {
     } while (0)
 
 // One evaluation of the denoiser, leaving h_final (B,L,32) in ws.xa.  t_dev may be null (t_scalar used).
+static int launch_embed(fd_handle* h, const float* t_dev, const EmbedSteps& ts, int nslots, int B, float* ws, cudaStream_t st) {
+    const WsLayout w = ws_layout(B, 1);   // emb / cnoise sit at the front of the workspace: their offsets do not depend on T'
+    EmbedParams p;
+    p.freq = sec(h, FD_S_EMB_FREQ);
+    p.w1t = sec(h, FD_S_FC1_WT); p.b1 = sec(h, FD_S_FC1_B);
+    p.w2t = sec(h, FD_S_FC2_WT); p.b2 = sec(h, FD_S_FC2_B);
+    for (int n = 0; n < NBLK; ++n) {
+        p.fct_wt[n] = sec(h, FD_S_LB0_FCT_WT + n * FD_LB_STRIDE);
+        p.fct_b[n] = sec(h, FD_S_LB0_FCT_B + n * FD_LB_STRIDE);
+    }
+    ScopedTimer tm(h, KC_EMBED, st);
+    FD_LAUNCH(k_embed, dim3(B, nslots), dim3(512), 0, st, p, t_dev, ts, ws + w.emb, ws + w.cnoise, B);
+    FD_CHECK_LAUNCH(h, "k_embed");
+    return FD_OK;
+}
+
+// emb_slot >= 0: the step embedding of this evaluation is already in that slot (fd_sample computes a chunk of steps per launch);
+// emb_slot < 0: compute it here into slot 0 from t_dev / t_scalar.
 static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, const float* t_dev, float t_scalar,
-                        int B, int Tm, float* ws, cudaStream_t st) {
+                        int B, int Tm, float* ws, cudaStream_t st, int emb_slot = -1) {
     const WsLayout w = ws_layout(B, Tm);
     const int L = Tm * HOP_TOTAL;
-    float* emb = ws + w.emb; float* cnoise = ws + w.cnoise; float* hk = ws + w.hk; float* kern = ws + w.kern;
+    const int slot = emb_slot < 0 ? 0 : emb_slot;
+    float* cnoise = ws + w.cnoise + (size_t)slot * NBLK * B * COND; float* hk = ws + w.hk; float* kern = ws + w.kern;
     float* d0 = ws + w.d0; float* d1 = ws + w.d1; float* d2 = ws + w.d2; float* xa = ws + w.xa; float* xb = ws + w.xb;
 
     // -- first_audio_conv + the three DiffusionDBlocks: independent of the kernel-predictor path, so they run on the side stream
@@ -400,18 +424,11 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     }
 #endif
     // -- step embedding + per-block condition offsets
-    {
-        EmbedParams p;
-        p.freq = sec(h, FD_S_EMB_FREQ);
-        p.w1t = sec(h, FD_S_FC1_WT); p.b1 = sec(h, FD_S_FC1_B);
-        p.w2t = sec(h, FD_S_FC2_WT); p.b2 = sec(h, FD_S_FC2_B);
-        for (int n = 0; n < NBLK; ++n) {
-            p.fct_wt[n] = sec(h, FD_S_LB0_FCT_WT + n * FD_LB_STRIDE);
-            p.fct_b[n] = sec(h, FD_S_LB0_FCT_B + n * FD_LB_STRIDE);
-        }
-        ScopedTimer tm(h, KC_EMBED, st);
-        FD_LAUNCH(k_embed, dim3(B), dim3(512), 0, st, p, t_dev, t_scalar, emb, cnoise, B);
-        FD_CHECK_LAUNCH(h, "k_embed");
+    if (emb_slot < 0) {
+        EmbedSteps ts;
+        ts.t[0] = t_scalar;
+        int rc = launch_embed(h, t_dev, ts, 1, B, ws, st);
+        if (rc) return rc;
     }
     // -- kernel predictor: hidden stack, then kernel_conv+bias_conv GEMM (all three blocks per launch)
     {
@@ -598,7 +615,14 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
     if (seq_dev) FD_CUDA(h, cudaMemcpyAsync(seq_dev, x_dev, n * 4, cudaMemcpyDeviceToDevice, st));
     int draw = 0;
     for (int i = 0; i < n_steps; ++i) {
-        rc = run_denoiser(h, x_dev, mel_dev, nullptr, steps[i].t, B, Tm, ws, st);
+        if (i % h->emb_slots == 0) {   // step embeddings of the next (up to) 64 reverse steps in one launch
+            EmbedSteps ts;
+            const int ns = n_steps - i < h->emb_slots ? n_steps - i : h->emb_slots;
+            for (int s2 = 0; s2 < ns; ++s2) ts.t[s2] = steps[i + s2].t;
+            rc = launch_embed(h, nullptr, ts, ns, B, ws, st);
+            if (rc) return rc;
+        }
+        rc = run_denoiser(h, x_dev, mel_dev, nullptr, steps[i].t, B, Tm, ws, st, i % h->emb_slots);
         if (rc) return rc;
         FinalParams fp;
         fill_final(h, fp);

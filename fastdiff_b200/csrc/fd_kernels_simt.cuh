@@ -20,13 +20,21 @@ struct EmbedParams {
     const float* fct_b[NBLK];          // [80]
 };
 
-__global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __restrict__ t_dev, float t_scalar,
-                                               float* __restrict__ emb, float* __restrict__ cnoise, int B) {
+// grid = (B, S): S = 1 with t_dev (fd_denoise: one diffusion step per item) or S reverse steps of a schedule at once (fd_sample: the
+// steps' scalars are known before the loop, so the embedding MLP leaves the per-step critical path); slot s writes emb[s][B][512]
+// and cnoise[s][3][B][80].
+constexpr int EMB_SLOTS = 64;
+struct EmbedSteps { float t[EMB_SLOTS]; };
+
+__global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __restrict__ t_dev, EmbedSteps ts,
+                                               float* __restrict__ emb_all, float* __restrict__ cnoise_all, int B) {
     __shared__ float s_in[EMB_IN];
     __shared__ float s_mid[EMB_MID];
     __shared__ float s_out[EMB_OUT];
-    const int b = blockIdx.x, j = threadIdx.x;
-    const float tv = t_dev ? t_dev[b] : t_scalar;
+    const int b = blockIdx.x, slot = blockIdx.y, j = threadIdx.x;
+    const float tv = t_dev ? t_dev[b] : ts.t[slot];
+    float* emb = emb_all + (size_t)slot * B * EMB_OUT;
+    float* cnoise = cnoise_all + (size_t)slot * NBLK * B * COND;
     if (j < EMB_IN / 2) {
         const float a = tv * p.freq[j];
         s_in[j] = sinf(a);

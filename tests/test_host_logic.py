@@ -162,3 +162,30 @@ def test_wav_int16_encode_matches_reference_ops_bitwise(emu_lib, synth):
     torch.manual_seed(0)
     x = torch.randn(3, 1, 1300) * 2.5
     assert np.array_equal(eng.wav_int16(x).numpy(), _ref_int16(x))
+
+
+def test_embedding_chunks_equal_single_chunk(emu_lib, synth):
+    """fd_sample computes the step embeddings of up to 64 reverse steps per launch (csrc/fd_api.cu: launch_embed).  With the chunk
+    size forced to 1 (option "emb_slots": every step recomputes slot 0) a 2-step sampler must give the same bits as with one chunk
+    (slots 0 and 1), through the emulated CUDA source.  (Two steps only: an emulated evaluation costs ~20 s.)"""
+    import fastdiff_b200 as fb
+    from fastdiff_b200.engine import Engine
+    from fastdiff_b200.sampler import build_steps
+    from fastdiff_b200.synthetic import make_inputs
+    from fastdiff_b200.weights import pack_state_dict
+    sd, _ = synth
+    eng = Engine(device="cpu", lib_path=emu_lib)
+    eng.load_blob(pack_state_dict(sd))
+    dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
+    _, steps = build_steps(dh, torch.FloatTensor([2.5376e-02, 7.0414e-01]))
+    B, Tm = 1, 1
+    _, mel = make_inputs(B, Tm, 4)
+    torch.manual_seed(0)
+    x0 = torch.randn(B, 1, 256)
+    noise = torch.randn(1, B, 1, 256)
+    ref = eng.sample(x0.clone(), mel, steps, noise=noise)
+    assert torch.isfinite(ref).all()
+    for slots in (1,):
+        eng.set_option("emb_slots", slots)
+        assert torch.equal(eng.sample(x0.clone(), mel, steps, noise=noise), ref)
+    eng.set_option("emb_slots", 64)
