@@ -1,6 +1,7 @@
 // Minimal CUDA execution-model shim for the CPU test-suite (TEST INFRASTRUCTURE, never shipped).
-// Runs every CTA of a launch on blockDim OS threads with a pthread barrier as __syncthreads, CTAs
-// one after another, "device" memory = host memory.  Enough for the SIMT kernels in
+// Every CTA of a launch runs on ONE OS thread as blockDim cooperative fibers (ucontext): __syncthreads() switches to the next
+// fiber of the CTA and the barrier opens when every live fiber has arrived; CTAs are handed out to a small pool of OS threads.
+// "Device" memory = host memory, __shared__ = static thread_local (one CTA per OS thread at a time).  Enough for the SIMT kernels in
 // fastdiff_b200/csrc/fd_kernels_simt.cuh (no warp shuffles, no tensor-core / TMA instructions).
 #pragma once
 #include <pthread.h>
@@ -19,27 +20,27 @@
 #define __restrict__
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
-#define __shared__ static
+#define __shared__ static thread_local
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct float4 { float x, y, z, w; } __attribute__((aligned(16)));
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 
 namespace emu {
-extern thread_local dim3 t_threadIdx;
-extern dim3 g_blockIdx, g_blockDim, g_gridDim;
-extern pthread_barrier_t g_bar;
-extern unsigned char* g_dyn_smem;
+extern thread_local dim3 t_threadIdx, t_blockIdx;
+extern dim3 g_blockDim, g_gridDim;
+extern thread_local unsigned char* t_dyn_smem;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+void syncthreads();
 }
 #define threadIdx (emu::t_threadIdx)
-#define blockIdx (emu::g_blockIdx)
+#define blockIdx (emu::t_blockIdx)
 #define blockDim (emu::g_blockDim)
 #define gridDim (emu::g_gridDim)
-static inline void __syncthreads() { pthread_barrier_wait(&emu::g_bar); }
+static inline void __syncthreads() { emu::syncthreads(); }
 
 #define FD_LAUNCH(kern, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
-#define FD_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::g_dyn_smem)
+#define FD_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::t_dyn_smem)
 
 // arithmetic intrinsics (compile with -ffp-contract=off so the _rn forms are honoured)
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }

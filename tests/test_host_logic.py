@@ -166,8 +166,8 @@ def test_wav_int16_encode_matches_reference_ops_bitwise(emu_lib, synth):
 
 def test_embedding_chunks_equal_single_chunk(emu_lib, synth):
     """fd_sample computes the step embeddings of up to 64 reverse steps per launch (csrc/fd_api.cu: launch_embed).  With the chunk
-    size forced to 1 (option "emb_slots": every step recomputes slot 0) a 2-step sampler must give the same bits as with one chunk
-    (slots 0 and 1), through the emulated CUDA source.  (Two steps only: an emulated evaluation costs ~20 s.)"""
+    size forced to 1, 2, 3 (option "emb_slots") the N = 4 sampler must give the same bits as with one chunk, through the emulated
+    CUDA source: slot indexing across chunk boundaries."""
     import fastdiff_b200 as fb
     from fastdiff_b200.engine import Engine
     from fastdiff_b200.sampler import build_steps
@@ -177,15 +177,15 @@ def test_embedding_chunks_equal_single_chunk(emu_lib, synth):
     eng = Engine(device="cpu", lib_path=emu_lib)
     eng.load_blob(pack_state_dict(sd))
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
-    _, steps = build_steps(dh, torch.FloatTensor([2.5376e-02, 7.0414e-01]))
-    B, Tm = 1, 1
+    _, steps = build_steps(dh, torch.FloatTensor([3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]))
+    B, Tm = 2, 3
     _, mel = make_inputs(B, Tm, 4)
     torch.manual_seed(0)
-    x0 = torch.randn(B, 1, 256)
-    noise = torch.randn(1, B, 1, 256)
+    x0 = torch.randn(B, 1, Tm * 256)
+    noise = torch.randn(3, B, 1, Tm * 256)
     ref = eng.sample(x0.clone(), mel, steps, noise=noise)
     assert torch.isfinite(ref).all()
-    for slots in (1,):
+    for slots in (1, 2, 3):
         eng.set_option("emb_slots", slots)
         assert torch.equal(eng.sample(x0.clone(), mel, steps, noise=noise), ref)
     eng.set_option("emb_slots", 64)

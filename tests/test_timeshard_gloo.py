@@ -1,6 +1,6 @@
 """Time-axis shard mode on 2 CPU ranks (gloo, emulated CUDA source): one utterance split along time with a
-17-frame halo exchanged after every reverse step == the unsharded sampler under the same RNG stream (N = 2 reverse steps with an
-explicit schedule, 18 + 17 frames: sized for the CPU emulation)."""
+17-frame halo exchanged after every reverse step == the unsharded sampler under the same RNG stream, for the N = 4 schedule and a
+batch of 2 (23 + 22 frames)."""
 import os
 import sys
 
@@ -8,8 +8,8 @@ import torch
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-N4 = [2.5376e-02, 7.0414e-01]
-B, TM = 1, 35
+N4 = [3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]
+B, TM = 2, 45
 
 
 def _worker(rank, world, port, emu_lib, q):
@@ -68,7 +68,7 @@ def test_two_rank_time_shard_matches_unsharded(emu_lib, synth):
     torch.manual_seed(21)
     size = (B, 1, TM * 256)
     x = torch.normal(0, 1, size=size)
-    zs = torch.stack([torch.normal(0, 1, size=size) for _ in range(1)])
+    zs = torch.stack([torch.normal(0, 1, size=size) for _ in range(3)])
     eng.sample(x, mel, steps, noise=zs)
     assert got.shape == x.shape
     err = (got - x).abs().max().item()
