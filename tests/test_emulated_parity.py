@@ -1,0 +1,55 @@
+"""The shipped CUDA source (SIMT kernels + host orchestration, compiled for the CPU fibre emulator in tests/cudaemu) against the
+oracle at BASELINE.json configs[0] -- single 1 s mel (T' = 86), N = 4 -- and at ragged shapes; no GPU needed.  The tensor-core
+kernels cannot be emulated: they are covered by tests/test_gpu_parity.py against the same oracle and against this FFMA path."""
+import pytest
+import torch
+
+N4 = [3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]
+
+
+def _net(sd, emu_lib):
+    import fastdiff_b200 as fb
+    net = fb.FastDiff().eval()
+    net._lib_path = emu_lib
+    net.load_state_dict(sd)
+    return net
+
+
+@pytest.mark.parametrize("B,Tm", [(1, 86), (2, 33), (3, 1), (1, 7)])
+def test_emulated_denoiser_vs_oracle(synth, emu_lib, B, Tm):
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    net = _net(sd, emu_lib)
+    x, mel = make_inputs(B, Tm, 3)
+    t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
+    ref, inter = O.denoise(W, x, mel, t, return_intermediates=True)
+    eps = net((x, mel, t))
+    assert (eps - ref).abs().max() < 5e-5          # the stated fp32 tolerance (eps rms ~1.3)
+    eng = net.engine()
+    L = Tm * 256
+    for n, T in enumerate((L // 4, L // 32, L // 256)):
+        assert (eng.debug_read(f"down{n}", B, Tm).reshape(B, 32, T) - inter[f"down{n}"]).abs().max() < 1e-5
+    assert (eng.debug_read("lvc2", B, Tm).reshape(B, 32, L) - inter["lvc2"]).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("ddim", [False, True])
+def test_emulated_sampler_config0_vs_oracle(synth, emu_lib, ddim):
+    """configs[0]: 1 s, N = 4, the reference's RNG stream; every intermediate x_t of the reverse loop (return_sequence)."""
+    import fastdiff_b200 as fb
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    net = _net(sd, emu_lib)
+    B, Tm = 1, 86
+    _, mel = make_inputs(B, Tm, 5)
+    dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
+    torch.manual_seed(11)
+    ref = O.sample(W, (B, 1, Tm * 256), dh, torch.FloatTensor(N4), mel, ddim=ddim, return_sequence=True)
+    torch.manual_seed(11)
+    got = fb.sampling_given_noise_schedule(net, (B, 1, Tm * 256), dh, torch.FloatTensor(N4), condition=mel, ddim=ddim,
+                                           return_sequence=True)
+    assert len(got) == len(ref) == 5
+    assert torch.equal(got[0], ref[0])
+    for i in range(1, 5):
+        assert (got[i] - ref[i]).abs().max() < 5e-4, i      # end-to-end tolerance at x rms ~3.4
