@@ -53,5 +53,25 @@ class FastDiffVocoder:
         return y.view(-1).cpu().numpy()
 
     @staticmethod
-    def wav2spec(wav_fn):
-        raise NotImplementedError("mel extraction is the reference's data_gen path (SURVEY.md 8f item 3: next)")
+    def wav2spec(wav_fn, engine=None):
+        """(wav [T*256], mel [T,80]) of a 22.05 kHz wav file or float array -- `process_utterance`
+        (data_gen/tts/data_gen_utils.py:93-147 via vocoders/base_vocoder.py:32-40) on the device (fastdiff_b200/mel.py).
+        The reference loads with librosa.core.load(sr=22050), i.e. PCM scaled to [-1, 1) and resampled if needed; only the
+        native-rate case is handled here (no resampler on the path)."""
+        from .engine import Engine
+        from .mel import SAMPLE_RATE, wav2mel
+        if isinstance(wav_fn, (str, bytes)) or hasattr(wav_fn, "__fspath__"):
+            from scipy.io import wavfile
+            sr, data = wavfile.read(wav_fn)
+            if sr != SAMPLE_RATE:
+                raise ValueError(f"{wav_fn}: {sr} Hz; resample to {SAMPLE_RATE} Hz first")
+            if data.ndim > 1:
+                data = data.mean(axis=1)
+            if np.issubdtype(data.dtype, np.integer):
+                data = data.astype(np.float32) / float(np.iinfo(data.dtype).max + 1)
+            wav = np.ascontiguousarray(data, dtype=np.float32)
+        else:
+            wav = np.ascontiguousarray(wav_fn, dtype=np.float32)
+        eng = engine if engine is not None else Engine(device="cuda")
+        w, mel = wav2mel(eng, torch.from_numpy(wav))
+        return w[0].cpu().numpy(), mel[0].t().contiguous().cpu().numpy()

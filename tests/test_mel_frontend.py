@@ -77,3 +77,33 @@ def test_gpu_mel_frontend_matches_oracle(cuda_lib):
     _, m2 = wav2mel(eng, w)
     _, m0 = wav2mel(eng, w[0])
     assert torch.equal(m2[0], m0[0])
+
+
+def test_vocoder_wav2spec_matches_oracle(emu_lib, tmp_path):
+    """`BaseVocoder.wav2spec` shape: (wav, mel [T,80]) from a wav FILE, through the emulated CUDA source; plus the reference's own
+    example audio when the reference tree is mounted (build container only)."""
+    import os
+    from scipy.io import wavfile
+    from fastdiff_b200.engine import Engine
+    from fastdiff_b200.plugin import FastDiffVocoder
+    from oracle import mel_oracle as M
+    eng = Engine(device="cpu", lib_path=emu_lib)
+    pcm = (np.clip(_signals()[1], -1, 1) * 32767).astype(np.int16)
+    fn = tmp_path / "a.wav"
+    wavfile.write(fn, 22050, pcm)
+    files = [str(fn)]
+    ref_audio = "/root/reference/egs/audios/LJ001-0001_gt.wav"
+    if os.path.exists(ref_audio) and wavfile.read(ref_audio)[0] == 22050:
+        files.append(ref_audio)
+    for f in files:
+        wav, mel = FastDiffVocoder.wav2spec(f, engine=eng)
+        sr, data = wavfile.read(f)
+        x = data.astype(np.float32) / 32768.0
+        w_ref, mel_ref = M.wav2mel(x)
+        assert mel.shape == (1 + len(x) // 256, 80) and wav.shape == (mel.shape[0] * 256,)
+        assert np.array_equal(wav, w_ref)
+        loud = 10.0 ** mel_ref > 1e-3 * (10.0 ** mel_ref).max(axis=0, keepdims=True)
+        assert np.abs(mel.T - mel_ref)[loud].max() < 1e-3
+    with pytest.raises(ValueError):
+        wavfile.write(tmp_path / "b.wav", 16000, pcm)
+        FastDiffVocoder.wav2spec(str(tmp_path / "b.wav"), engine=eng)
