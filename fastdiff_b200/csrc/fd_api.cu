@@ -4,9 +4,7 @@
 #include "fd_blob.h"
 #include "fd_common.cuh"
 #include "fd_kernels_simt.cuh"
-#ifndef FD_EMU
-#include "fd_kernels_tc.cuh"
-#endif
+#include "fd_kernels_tc.cuh"   // under FD_EMU only the fp16-piece kernels (k_lvc_layer_h, k_kp_hidden_tc) compile, on the tcemu.h model
 
 #include <stdarg.h>
 #include <stdio.h>
@@ -266,7 +264,8 @@ extern "C" int fd_set_mode(fd_handle* h, int mode) {
     if (!h) return FD_ERR_INVALID;
     if (mode < FD_MODE_FP32_SIMT || mode > FD_MODE_TC_3XF16) return fail(h, FD_ERR_INVALID, "fd_set_mode: unknown mode %d", mode);
 #ifdef FD_EMU
-    if (mode != FD_MODE_FP32_SIMT) return fail(h, FD_ERR_UNSUPPORTED, "fd_set_mode: the emulation build has no tensor-core path");
+    if (mode != FD_MODE_FP32_SIMT && mode != FD_MODE_TC_3XF16)
+        return fail(h, FD_ERR_UNSUPPORTED, "fd_set_mode: the emulation build models only the fp16-piece tensor-core kernels (tc_3xf16)");
 #else
     if (mode != FD_MODE_FP32_SIMT && !tc_available(h->tc_state))
         return fail(h, FD_ERR_UNSUPPORTED, "fd_set_mode: tensor-core path unavailable (load weights first)");
@@ -359,6 +358,67 @@ static int setup_attrs(fd_handle* h) {
     } while (0)
 
 // One evaluation of the denoiser, leaving h_final (B,L,32) in ws.xa.  t_dev may be null (t_scalar used).
+#ifdef FD_EMU
+// ---- emulation of mode tc_3xf16 (TEST INFRASTRUCTURE path of the emulation build only) -------------------------------------
+// k_kp_hidden_tc and k_lvc_layer_h run on the tcemu.h model.  The CTA-pair kernel_conv GEMM is not modelled: the FFMA GEMM runs
+// instead and this converter rewrites its fp32 output for blocks 1/2 into the fp16-piece image the LVC kernel expects -- an
+// independent statement of the layout the GPU epilogue writes (k_kc_gemm_tc2<true>): per (frame, layer, tap) 64 rows (o) of 128 B =
+// [32 i hi | 32 i lo] of w*S16_KERN, 16-byte chunk c at position c ^ (o & 7), in place of the fp32 row
+// [(i/4) ^ (o & 7)][i % 4] of the same 128 bytes.
+__global__ void __launch_bounds__(256) k_emu_kern_to_pieces(float* __restrict__ kern, size_t n_rows) {
+    const size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;   // row = ((frame * LAYERS + l) * 3 + k) * 64 + o
+    if (r >= n_rows) return;
+    const size_t per_frame = (size_t)LAYERS * 3 * 64;
+    const size_t frame = r / per_frame, rem = r % per_frame;
+    const int l = (int)(rem / 192), ko = (int)(rem % 192), o = ko & 63;
+    float* row = kern + frame * KCN + (size_t)l * KPL + (size_t)ko * 32;
+    float w[32];
+    for (int i = 0; i < 32; ++i) w[i] = row[(((i >> 2) ^ (o & 7)) << 2) + (i & 3)];
+    uint16_t* out = reinterpret_cast<uint16_t*>(row);
+    for (int i = 0; i < 32; ++i) {
+        uint16_t hi, lo;
+        f16_split(w[i], S16_KERN, hi, lo);
+        out[(((i >> 3) ^ (o & 7)) << 3) + (i & 7)] = hi;
+        out[(((4 + (i >> 3)) ^ (o & 7)) << 3) + (i & 7)] = lo;
+    }
+}
+
+static float emu_scale16(const fd_handle* h, int idx) { return h->blob[h->sec_off[FD_S_SCALES16] + idx]; }
+
+static int emu_kp_hidden_tc(fd_handle* h, const float* mel, const float* cnoise, float* hk, float* hk_hi, float* hk_lo, int B, int Tm, cudaStream_t st) {
+    KpTcParams p;
+    for (int n = 0; n < NBLK; ++n) {
+        p.w16[n] = sec(h, FD_S_LB0_KPW_F16 + n);
+        p.in_b[n] = sec(h, FD_S_LB0_KPIN_B + n * FD_LB_STRIDE);
+        p.res_b[n] = sec(h, FD_S_LB0_KPRES_B + n * FD_LB_STRIDE);
+        for (int l = 0; l < 7; ++l) p.inv[n][l] = 1.f / (S16_HK * emu_scale16(h, 16 + 8 * n + l));
+        p.inv[n][7] = 0.f;
+    }
+    const int total = NBLK * B * ((Tm + KT_VALID - 1) / KT_VALID);
+    FD_LAUNCH(k_kp_hidden_tc, dim3(total < 8 ? total : 8), dim3(512), KT_SMEM_BYTES, st, p, mel, cnoise, hk, hk_hi, hk_lo, B, Tm);
+    FD_CHECK_LAUNCH(h, "k_kp_hidden_tc");
+    return FD_OK;
+}
+
+static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, const float* skip, const float* kern, float* x_out,
+                           int B, int T, int Tm, int dil, cudaStream_t st) {
+    LvcHParams hp;
+    hp.cw16 = sec(h, blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16) + (size_t)layer * (LH_CW_BYTES / 4);
+    hp.conv_b = sec(h, FD_S_LB0_CONV_B + blk * FD_LB_STRIDE) + layer * C;
+    hp.first_w = sec(h, FD_S_FIRST_W);
+    hp.first_b = sec(h, FD_S_FIRST_B);
+    const float inv_c = 1.f / (S16_ACT * emu_scale16(h, 4 + 4 * blk + layer)), inv_l = 1.f / (S16_ACT * S16_KERN);
+    const int tiles = B * ((T + LT_TT - 1) / LT_TT);
+    const int skip_in = (blk == 2 || layer == 0) ? 1 : 0, skip_out = (blk == 1 && layer < LAYERS - 1) ? 1 : 0;
+    // a small grid on purpose: every group then walks a chunk of several tiles (carried halo rows, kernel reuse, prefetch one tile ahead)
+    int grid = (tiles + 5) / 6; if (grid < 1) grid = 1; if (grid > 8) grid = 8;
+    if (blk == 1) { auto k = k_lvc_layer_h<64, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<64, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
+    else          { auto k = k_lvc_layer_h<256, true, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<256, true, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
+    FD_CHECK_LAUNCH(h, "k_lvc_layer_h");
+    return FD_OK;
+}
+#endif  // FD_EMU
+
 static int launch_embed(fd_handle* h, const float* t_dev, const EmbedSteps& ts, int nslots, int B, float* ws, cudaStream_t st) {
     const WsLayout w = ws_layout(B, 1);   // emb / cnoise sit at the front of the workspace: their offsets do not depend on T'
     EmbedParams p;
@@ -439,7 +499,13 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         }
         ScopedTimer tm(h, KC_KP_HIDDEN, st);
         bool kp_done = false;
-#ifndef FD_EMU
+#ifdef FD_EMU
+        if (h->mode == FD_MODE_TC_3XF16 && h->tc_kp) {
+            int rc = emu_kp_hidden_tc(h, mel_dev, cnoise, hk, ws + w.hk_hi, ws + w.hk_lo, B, Tm, st);
+            if (rc) return rc;
+            kp_done = true;
+        }
+#else
         if (h->mode == FD_MODE_TC_3XF16 && h->tc_kp) {
             int rc = tc_kp_hidden(h->tc_state, mel_dev, cnoise, hk, ws + w.hk_hi, ws + w.hk_lo, B, Tm, st, h->err, &h->launches);
             if (rc) return rc;
@@ -452,13 +518,25 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         FD_CHECK_LAUNCH(h, "k_kp_hidden");
         }
     }
-    if (h->mode == FD_MODE_FP32_SIMT) {
+#ifdef FD_EMU
+    const bool simt_gemm = true;
+#else
+    const bool simt_gemm = h->mode == FD_MODE_FP32_SIMT;
+#endif
+    if (simt_gemm) {
         KcParams p;
         for (int n = 0; n < NBLK; ++n) { p.w[n] = sec(h, FD_S_LB0_KC_W + n * FD_LB_STRIDE); p.b[n] = sec(h, FD_S_LB0_KC_B + n * FD_LB_STRIDE); }
         const int M = B * (Tm + 2) - 2;
         ScopedTimer tm(h, KC_KC_GEMM, st);
         FD_LAUNCH(k_kc_gemm_simt, dim3(KCN / 128, (M + 127) / 128, NBLK), dim3(256), 0, st, p, hk, kern, B, Tm);
         FD_CHECK_LAUNCH(h, "k_kc_gemm_simt");
+#ifdef FD_EMU
+        if (h->mode == FD_MODE_TC_3XF16) {   // blocks 1, 2: fp32 image -> fp16-piece image (see k_emu_kern_to_pieces)
+            const size_t n_rows = (size_t)2 * B * Tm * LAYERS * 3 * 64;
+            FD_LAUNCH(k_emu_kern_to_pieces, dim3((unsigned)((n_rows + 255) / 256)), dim3(256), 0, st, kern + (size_t)B * Tm * KCN, n_rows);
+            FD_CHECK_LAUNCH(h, "k_emu_kern_to_pieces");
+        }
+#endif
     } else {
 #ifndef FD_EMU
         ScopedTimer tm(h, KC_KC_GEMM, st);
@@ -513,7 +591,13 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             const float* kl = kern_n + i * KPL;
             bool done = false;
             ScopedTimer tm(h, KC_LVC0 + n, st);
-#ifndef FD_EMU
+#ifdef FD_EMU
+            if (h->mode == FD_MODE_TC_3XF16 && n >= 1) {
+                int rc = emu_lvc_layer_h(h, n, i, cur, skip, kl, oth, B, T, Tm, dil, st);
+                if (rc) return rc;
+                done = true;
+            }
+#else
             if (h->mode != FD_MODE_FP32_SIMT) {
                 int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done);
                 if (rc) return rc;

@@ -22,15 +22,23 @@
 // quarter, each taking 128 of the 256 columns).
 // Persistent CTAs (grid = #SM), 2-stage smem ring (96 KB/stage), 2 x 256-column TMEM accumulators.
 #pragma once
+// The fp16-piece kernels (k_lvc_layer_h, k_kp_hidden_tc) also compile for the CPU fibre emulator (FD_EMU: tests/cudaemu/tcemu.h
+// supplies functional models of the PTX wrappers); everything else in this file is GPU-only.
+#ifndef FD_EMU
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#endif
 #include <string>
 #include "fd_blob.h"
 #include "fd_common.cuh"
+#ifdef FD_EMU
+#include "tcemu.h"
+#endif
 
 namespace fd {
 
+#ifndef FD_EMU
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------------------------------------
@@ -134,6 +142,31 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+
+// --- wrappers the fp16-piece kernels use in both builds (the emulator has models of the same names) ---
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t ncols) {       // whole warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+// two floats -> packed fp16 pair, round to nearest even, saturating at +-65504: `upper` lands in bits [16,32)
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float upper, float lower) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+    return d;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// opaque to the optimiser: keeps ptxas from hoisting ~100 descriptors out of a tile loop
+#define FD_OPAQUE(x) asm volatile("" : "+r"(x))
+#define FD_OPAQUE2(x, y) asm volatile("" : "+r"(x), "+r"(y))
 
 // ---------------------------------------------------------------------------------------------------------
 // kernel_conv GEMM
@@ -775,6 +808,7 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
 // mbarriers, a named barrier) and walking its own tile sequence, so one group's transforms / epilogues overlap the other's
 // MMAs.  One elected lane of a group's warp 0 issues its MMAs and bulk copies.
 // ---------------------------------------------------------------------------------------------------------
+#endif  // !FD_EMU
 constexpr int LT_TT = 128;
 constexpr int LT_A_BYTES = 24576;                   // 192 rows x 128 B (rows 0..183 used: t0-28 .. t0+155)
 constexpr int LT_CW_BYTES = 3 * C * 128;            // 12288
@@ -791,6 +825,7 @@ template <int HOP, int GROUPS>
 constexpr int lt_smem_bytes() { return GROUPS * (lt_slot_bytes<HOP>() + lt_small_bytes<HOP>()) + LT_SHARED_BYTES + 1024; }
 
 __device__ __forceinline__ uint32_t swz128(int row, int c) { return (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)); }
+#ifndef FD_EMU
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -1234,6 +1269,11 @@ k_lvc_layer_tc(LvcTcParams p, const float* __restrict__ x_in, const float* __res
     }
 }
 
+#endif  // !FD_EMU
+#ifndef LT_STAMP
+#define LT_STAMP(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // K11+K12+K13, mode tc_3xf16: the same LVC layer on kind::f16 MMAs over fp16 PIECES (hi | lo) of power-of-two prescaled
 // operands.  Same tile walk, tap-as-shifted-start trick, one-tile-ahead bulk prefetch and two independent 8-warp groups per CTA
@@ -1280,15 +1320,13 @@ __device__ __forceinline__ void split4_f16(const float4 v, uint2& hi, uint2& lo)
 }
 // same, for values that already carry the prescale
 __device__ __forceinline__ void split4_f16_pre(const float sx, const float sy, const float sz, const float sw, uint2& hi, uint2& lo) {
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi.x) : "f"(sy), "f"(sx));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi.y) : "f"(sw), "f"(sz));
-    const float2 h01 = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), h23 = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo.x) : "f"(sy - h01.y), "f"(sx - h01.x));
-    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo.y) : "f"(sw - h23.y), "f"(sz - h23.x));
+    hi.x = pack_f16x2_sat(sy, sx);
+    hi.y = pack_f16x2_sat(sw, sz);
+    const float2 h01 = unpack_f16x2(hi.x), h23 = unpack_f16x2(hi.y);
+    lo.x = pack_f16x2_sat(sy - h01.y, sx - h01.x);
+    lo.y = pack_f16x2_sat(sw - h23.y, sz - h23.x);
 }
 // sigmoid(a) * tanh(b) with two ex2 and one rcp; b clamped from below at -15 (tanh is -1 to fp32 precision below -9.01) so E stays finite
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #ifndef LH_GATE_ASM
 #define LH_GATE_ASM 1
 #endif
@@ -1296,7 +1334,7 @@ __device__ __forceinline__ float gate_st(float a, float b) {
     const float bc = fmaxf(b, -15.f);   // E = e^-2b must stay finite (E -> 0 for large b is harmless); tanh(-15) = -1 to fp32 precision
 #if !LH_GATE_ASM
     const float E2 = exp2f(-2.8853900817779268f * bc), A2 = exp2f(-1.4426950408889634f * a);
-    return __fdividef(1.f - E2, (1.f + A2) * (1.f + E2));
+    return (1.f - E2) / ((1.f + A2) * (1.f + E2));
 #endif
     const float E = ex2_approx(-2.8853900817779268f * bc), A = ex2_approx(-1.4426950408889634f * a);   // A = +inf for a << 0 -> result 0
     return (1.f - E) * rcp_approx((1.f + A) * (1.f + E));
@@ -1318,7 +1356,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     constexpr int SMALL = lt_small_bytes<HOP>();
     constexpr int S_OFF = LH_A_BYTES;                                              // raw skip rows (block 1) | xs rows (block 2)
     constexpr int LW_OFF = LH_A_BYTES + (SKIP_FIRST ? LH_XS_BYTES : LH_A_BYTES);
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* cw = smem + GROUPS * SLOT;                 // [3 taps][32 rows][128 B]
     unsigned char* small0 = cw + LH_CW_BYTES;                 // [GROUPS][2 buffers][lbias NF*64 | audio LT_AU]
@@ -1342,12 +1380,9 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
 
     if (tid == 0) {
         for (int i = 0; i < 4 * GROUPS; ++i) mbar_init(&bars[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
-    if (tid < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (tid < 32) tmem_alloc(tmem_base_s, 512u);
     {
         const float4* src = reinterpret_cast<const float4*>(p.cw16);
         for (int i = tid; i < LH_CW_BYTES / 16; i += GT * GROUPS) reinterpret_cast<float4*>(cw)[i] = src[i];
@@ -1412,13 +1447,13 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         const int ar0 = max(r_lo, 28 - t0), ar1 = min(r_hi, T - t0 + 28);
         if (ar1 > ar0) {
             const size_t off = ((size_t)b * T + (t0 - 28 + ar0)) * C;
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(x_in + off), "r"((uint32_t)(ar1 - ar0) * 128u) : "memory");
-            if (!SKIP_FIRST && skip_in) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(skip + off), "r"((uint32_t)(ar1 - ar0) * 128u) : "memory");
+            bulk_prefetch_l2(x_in + off, (uint32_t)(ar1 - ar0) * 128u);
+            if (!SKIP_FIRST && skip_in) bulk_prefetch_l2(skip + off, (uint32_t)(ar1 - ar0) * 128u);
         }
 #pragma unroll
         for (int fi = 0; fi < NF; ++fi) {
             const int f = t0 / HOP + fi;
-            if (f < Tm) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kern + ((size_t)b * Tm + f) * KCN), "r"((uint32_t)(KPL * 4)) : "memory");
+            if (f < Tm) bulk_prefetch_l2(kern + ((size_t)b * Tm + f) * KCN, (uint32_t)(KPL * 4));
         }
     };
 
@@ -1521,7 +1556,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         if (gw_u == 0) {
             tc_fence_after();
             uint32_t slot_t = slot_u, cw_t = cw_u;
-            asm volatile("" : "+r"(slot_t), "+r"(cw_t));   // opaque per tile: keeps ptxas from hoisting the descriptors out of the tile loop
+            FD_OPAQUE2(slot_t, cw_t);   // opaque per tile: keeps ptxas from hoisting the descriptors out of the tile loop
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
@@ -1610,7 +1645,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         if (gw_u == 0) {
             tc_fence_after();
             uint32_t slot_t = slot_u;
-            asm volatile("" : "+r"(slot_t));
+            FD_OPAQUE(slot_t);
             if (elect_one()) {
 #pragma unroll
                 for (int fi = 0; fi < NF; ++fi) {
@@ -1707,7 +1742,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     __syncthreads();
     if (tid < 32) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(512u) : "memory");
+        tmem_dealloc(*tmem_base_s, 512u);
     }
 }
 
@@ -1741,7 +1776,7 @@ struct KpTcParams {
 __global__ void __launch_bounds__(512, 1)
 k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ mel, const float* __restrict__ cnoise,
                float* __restrict__ hk_all, float* __restrict__ hk_hi_all, float* __restrict__ hk_lo_all, int B, int Tm) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     // tiles: 0 = P_hi, 1 = P_lo (cond ch 0..63, then odd layers' output), 2 = Q_hi, 3 = Q_lo (even layers' output), 4 = cond ch 64..79
     unsigned char* ring = smem + 5 * KT_TILE;
@@ -1757,12 +1792,9 @@ k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ m
     if (tid == 0) {
         for (int i = 0; i < KT_NSLOT; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(mma_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
-    if (gw == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(64u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (gw == 0) tmem_alloc(tmem_base_s, 64u);
     for (int i = tid; i < 5 * KT_TILE / 16; i += 512) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // pad rows stay 0
     fence_async_smem();
     tc_fence_before();
@@ -1923,10 +1955,11 @@ k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ m
     __syncthreads();
     if (gw == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+        tmem_dealloc(tmem_base, 64u);
     }
 }
 
+#ifndef FD_EMU
 // ---------------------------------------------------------------------------------------------------------
 // K3+K4  first_audio_conv + DiffusionDBlock 0 on tensor cores (FastDiff_model.py:89, modules.py:127-138):
 //   xs[o] = first_conv(audio)[4 o]  (evaluated only at the kept positions);
@@ -2440,5 +2473,7 @@ static inline cudaError_t tc_set_lvc_attrs() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lvc_layer_tc<256, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lt_smem_bytes<256, 2>());
     return e;
 }
+
+#endif  // !FD_EMU
 
 }  // namespace fd

@@ -1,6 +1,7 @@
 // Minimal CUDA execution-model shim for the CPU test-suite (TEST INFRASTRUCTURE, never shipped).
-// Every CTA of a launch runs on ONE OS thread as blockDim cooperative fibers (ucontext): __syncthreads() switches to the next
-// fiber of the CTA and the barrier opens when every live fiber has arrived; CTAs are handed out to a small pool of OS threads.
+// Every CTA of a launch runs on ONE OS thread as blockDim cooperative fibres (ucontext).  A fibre runs until it blocks at a barrier
+// (__syncthreads, bar.sync id/n, __syncwarp), yields in a spin-wait, or ends; barriers open when the expected number of fibres has
+// arrived (all live ones for __syncthreads).  CTAs are handed out to a small pool of OS threads.
 // "Device" memory = host memory, __shared__ = static thread_local (one CTA per OS thread at a time).  Enough for the SIMT kernels in
 // fastdiff_b200/csrc/fd_kernels_simt.cuh (no warp shuffles, no tensor-core / TMA instructions).
 #pragma once
@@ -25,13 +26,29 @@
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct float4 { float x, y, z, w; } __attribute__((aligned(16)));
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
+struct float2 { float x, y; };
+struct uint2 { unsigned x, y; } __attribute__((aligned(8)));
+struct uint4 { unsigned x, y, z, w; } __attribute__((aligned(16)));
+static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r; r.x = a; r.y = b; return r; }
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
+#define __grid_constant__
+template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
+static inline unsigned min(unsigned a, int b) { return a < (unsigned)b ? a : (unsigned)b; }
 
 namespace emu {
 extern thread_local dim3 t_threadIdx, t_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
 extern thread_local unsigned char* t_dyn_smem;
+extern thread_local size_t t_dyn_smem_bytes;
+extern thread_local unsigned t_linear_tid;
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 void syncthreads();
+void syncwarp();
+void barrier(int key, int expected);   // key 1..15: named barrier (bar.sync key, expected)
+void yield();                          // for spin-waits (mbarrier polling)
+void cta_begin();                      // per-CTA state of the tensor-core model (tcemu.cpp): TMEM, mbarriers
+void cta_end();
 }
 #define threadIdx (emu::t_threadIdx)
 #define blockIdx (emu::t_blockIdx)

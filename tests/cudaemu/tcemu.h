@@ -1,0 +1,122 @@
+// Functional model of the tcgen05 / mbarrier / bulk-copy PTX subset used by the fp16-piece tensor-core kernels
+// (fastdiff_b200/csrc/fd_kernels_f16.cuh), for the CPU fibre emulator.  TEST INFRASTRUCTURE, never shipped.
+//   * shared-memory "addresses" are byte offsets into the CTA's dynamic shared memory (1024-byte aligned like the real window);
+//   * an mbarrier keeps its state in its own 64-bit word {pending arrivals, arrival count, outstanding tx bytes, phase};
+//   * cp.async.bulk copies synchronously and completes its bytes at once; tcgen05.mma executes synchronously at issue (so
+//     tcgen05.commit is a plain arrive); polling loops yield to the other fibres of the CTA;
+//   * tcgen05.mma kind::f16, cta_group::1, K = 16, both operands K-major SWIZZLE_128B from shared-memory descriptors: the swizzle
+//     XORs ABSOLUTE address bits [7,10) into [4,7) (descriptor base_offset 0, as measured on B200), D = 128 lanes x N fp32 columns;
+//   * TMEM = 128 lanes x 512 fp32 columns per CTA.
+#pragma once
+#include <stdio.h>
+
+namespace fd {
+
+struct EmuMbar { int16_t pending; int16_t count; int32_t tx; uint32_t phase; };   // overlays the kernel's uint64_t (+ 4 bytes of it)
+static_assert(sizeof(EmuMbar) <= 12, "mbarrier state");
+// the kernels lay their mbarriers out as consecutive uint64_t: keep the model inside 8 bytes
+struct EmuMbar8 { int16_t pending; int16_t count; int32_t tx_phase; };            // tx in the upper 31 bits (signed), phase in bit 0
+static_assert(sizeof(EmuMbar8) == 8, "mbarrier state");
+
+inline thread_local float emu_tmem[128][512];
+
+inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - emu::t_dyn_smem); }
+inline unsigned char* emu_smem_ptr(uint32_t a) { return emu::t_dyn_smem + a; }
+
+inline void emu_mbar_settle(EmuMbar8* b) {
+    if (b->pending == 0 && (b->tx_phase >> 1) == 0) { b->tx_phase ^= 1; b->pending = b->count; }
+}
+inline void mbar_init(uint64_t* bar, uint32_t count) { EmuMbar8* b = (EmuMbar8*)bar; b->pending = b->count = (int16_t)count; b->tx_phase = 0; }
+inline void mbar_init_fence() {}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {   // mbarrier.arrive.expect_tx
+    EmuMbar8* b = (EmuMbar8*)bar;
+    b->tx_phase += (int32_t)(bytes << 1);
+    --b->pending;
+    emu_mbar_settle(b);
+}
+inline void mbar_arrive(uint64_t* bar) { EmuMbar8* b = (EmuMbar8*)bar; --b->pending; emu_mbar_settle(b); }
+inline void emu_mbar_complete_tx(uint64_t* bar, uint32_t bytes) { EmuMbar8* b = (EmuMbar8*)bar; b->tx_phase -= (int32_t)(bytes << 1); emu_mbar_settle(b); }
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const EmuMbar8* b = (const EmuMbar8*)bar;
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
+        if ((uint32_t)(b->tx_phase & 1) != (parity & 1)) return;
+        emu::yield();
+    }
+    fprintf(stderr, "tcemu: mbarrier wait timed out (protocol bug)\n");
+    abort();
+}
+inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { memcpy(smem_dst, gsrc, bytes); emu_mbar_complete_tx(bar, bytes); }
+inline void bulk_prefetch_l2(const void*, uint32_t) {}
+inline bool elect_one() { return (emu::t_linear_tid & 31) == 0; }
+inline void tc_fence_before() {}
+inline void tc_fence_after() {}
+inline void fence_async_smem() {}
+inline void tc_commit(uint64_t* bar) { mbar_arrive(bar); }
+inline void tmem_alloc(uint32_t* dst_smem, uint32_t) { *dst_smem = 0; }
+inline void tmem_dealloc(uint32_t, uint32_t) {}
+inline void group_sync(int id, int nthreads) { emu::barrier(id, nthreads); }
+inline void tmem_ld_wait() {}
+
+inline uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+constexpr uint32_t umma_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+
+inline float emu_f16_at(uint32_t desc_start, uint32_t sbo, int row, int k) {   // element (row, k) of a K-major SWIZZLE_128B operand slice
+    const uint32_t lin = desc_start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 128u + (uint32_t)k * 2u;
+    const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
+    uint16_t h;
+    memcpy(&h, emu_smem_ptr(phys), 2);
+    return f16_bits_to_float_soft(h);
+}
+inline void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+    const uint32_t a0 = (uint32_t)(a_desc & 0x3FFF) << 4, b0 = (uint32_t)(b_desc & 0x3FFF) << 4;
+    const uint32_t sa = (uint32_t)((a_desc >> 32) & 0x3FFF) << 4, sb = (uint32_t)((b_desc >> 32) & 0x3FFF) << 4;
+    if (M != 128 || ((a_desc >> 61) & 7) != 2 || ((b_desc >> 61) & 7) != 2) { fprintf(stderr, "tcemu: unsupported MMA shape/layout\n"); abort(); }
+    const int lane0 = (int)(d_tmem >> 16), col0 = (int)(d_tmem & 0xFFFF);
+    float bt[256][16];
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < 16; ++k) bt[n][k] = emu_f16_at(b0, sb, n, k);
+    for (int m = 0; m < M; ++m) {
+        float a[16];
+        for (int k = 0; k < 16; ++k) a[k] = emu_f16_at(a0, sa, m, k);
+        for (int n = 0; n < N; ++n) {
+            float acc = accumulate ? emu_tmem[lane0 + m][col0 + n] : 0.f;
+            for (int k = 0; k < 16; ++k) acc += a[k] * bt[n][k];
+            emu_tmem[lane0 + m][col0 + n] = acc;
+        }
+    }
+}
+template <int N> inline void emu_tmem_ld(uint32_t taddr, uint32_t (&v)[N]) {
+    const int lane = (int)(taddr >> 16) + (int)(emu::t_linear_tid & 31), col = (int)(taddr & 0xFFFF);
+    for (int i = 0; i < N; ++i) memcpy(&v[i], &emu_tmem[lane][col + i], 4);
+}
+inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) { emu_tmem_ld<32>(taddr, v); }
+inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) { emu_tmem_ld<16>(taddr, v); }
+inline void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) { emu_tmem_ld<8>(taddr, v); }
+
+// packed fp16 helpers (cvt.rn.satfinite.f16x2.f32 d, a, b: a -> upper half, b -> lower half)
+inline uint16_t emu_f16_sat(float f) {
+    if (f > F16_MAX) f = F16_MAX;
+    if (f < -F16_MAX) f = -F16_MAX;
+    return f16_bits_rn_soft(f);
+}
+inline uint32_t pack_f16x2_sat(float upper, float lower) { return ((uint32_t)emu_f16_sat(upper) << 16) | emu_f16_sat(lower); }
+inline float2 unpack_f16x2(uint32_t u) { float2 r; r.x = f16_bits_to_float_soft((uint16_t)(u & 0xFFFF)); r.y = f16_bits_to_float_soft((uint16_t)(u >> 16)); return r; }
+inline float ex2_approx(float x) { return exp2f(x); }
+inline float rcp_approx(float x) { return 1.f / x; }
+#define FD_OPAQUE(x) ((void)0)
+#define FD_OPAQUE2(x, y) ((void)0)
+
+}  // namespace fd
+
+// warp primitives as the kernels use them: lane-0 broadcasts of warp-uniform values, and __syncwarp as a real barrier
+template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline void __syncwarp() { emu::syncwarp(); }

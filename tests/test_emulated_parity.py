@@ -53,3 +53,54 @@ def test_emulated_sampler_config0_vs_oracle(synth, emu_lib, ddim):
     assert torch.equal(got[0], ref[0])
     for i in range(1, 5):
         assert (got[i] - ref[i]).abs().max() < 5e-4, i      # end-to-end tolerance at x rms ~3.4
+
+
+@pytest.mark.parametrize("B,Tm", [(1, 5), (2, 33), (3, 1), (2, 129)])
+def test_emulated_tensor_core_mode_vs_oracle(synth, emu_lib, B, Tm):
+    """Mode tc_3xf16 on the CPU: k_kp_hidden_tc and k_lvc_layer_h run on a functional model of tcgen05.mma / TMEM / mbarrier /
+    cp.async.bulk (tests/cudaemu/tcemu.h: descriptors, SWIZZLE_128B with absolute-address XOR, kind::f16 K = 16, fp32 accumulation);
+    the kernel_conv GEMM is the FFMA one followed by an independent statement of the piece layout (k_emu_kern_to_pieces).  Checks
+    every LVC block and eps against the oracle -- the same assertions the GPU test makes."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    import torch.nn.functional as F
+    sd, W = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    x, mel = make_inputs(B, Tm, 4)
+    t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
+    ref, inter = O.denoise(W, x, mel, t, return_intermediates=True)
+    eps = net((x, mel, t))
+    eng = net.engine()
+    assert eng.get_mode() == 3
+    assert (eps - ref).abs().max() < 5e-5
+    e = inter["embed"]
+    for n in range(3):
+        p = f"lvc_blocks.{n}"
+        noise = F.linear(e, W[f"{p}.fc_t.weight"], W[f"{p}.fc_t.bias"]).unsqueeze(-1)
+        k, bb = O.kernel_predictor(W, f"{p}.kernel_predictor", mel + noise)
+        gk = eng.debug_read(f"kernels{n}", B, Tm).reshape(k.shape)      # blocks 1, 2: decoded from the fp16 pieces
+        gb = eng.debug_read(f"kbias{n}", B, Tm).reshape(bb.shape)
+        assert (gk - k).abs().max() < 4e-5 and (gb - bb).abs().max() < 4e-5
+    assert (eng.debug_read("lvc2", B, Tm).reshape(B, 32, Tm * 256) - inter["lvc2"]).abs().max() < 2e-4
+    eng.set_option("stop_after", 4)
+    net((x, mel, t))
+    assert (eng.debug_read("lvc1", B, Tm).reshape(B, 32, Tm * 64) - inter["lvc1"]).abs().max() < 2e-4
+    eng.set_option("stop_after", 99)
+    net.mode = "fp32_simt"
+    assert (net((x, mel, t)) - eps).abs().max() < 5e-5
+
+
+def test_emulated_tensor_core_mode_is_batch_and_tiling_independent(synth, emu_lib):
+    """The carried halo rows (descending tile walk) and the second-MMA-pass fallback give the same bits: an item evaluated alone
+    (different chunking of the tile walk) equals the same item inside a batch, bitwise -- on the tensor-core model."""
+    from fastdiff_b200.synthetic import make_inputs
+    sd, _ = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    B, Tm = 3, 40
+    x, mel = make_inputs(B, Tm, 9)
+    t = torch.full((B, 1), 74.99228)
+    full = net((x, mel, t))
+    for lo, hi in ((0, 1), (1, 3)):
+        assert torch.equal(net((x[lo:hi], mel[lo:hi], t[lo:hi])), full[lo:hi])
