@@ -417,6 +417,31 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
     FD_CHECK_LAUNCH(h, "k_lvc_layer_h");
     return FD_OK;
 }
+
+// DBlock 0 and the upsampling of blocks 1/2 still run the 3xTF32 kernels in mode tc_3xf16: modelled as well
+static int emu_dblock0_tc(fd_handle* h, const float* audio, float* d0, int B, int L, cudaStream_t st) {
+    DbTcParams p;
+    p.cw_hi = sec(h, FD_S_DB0_CONVT_HI); p.cw_lo = sec(h, FD_S_DB0_CONVT_LO);
+    p.rw_hi = sec(h, FD_S_DB0_REST_HI);  p.rw_lo = sec(h, FD_S_DB0_REST_LO);
+    p.conv_b = sec(h, FD_S_DB0_CONV_B);  p.res_b = sec(h, FD_S_DB0_RES_B);
+    p.first_w = sec(h, FD_S_FIRST_W);    p.first_b = sec(h, FD_S_FIRST_B);
+    const int To = L / 4, total = B * ((To + DT_VALID - 1) / DT_VALID);
+    FD_LAUNCH(k_dblock0_tc, dim3(total < 6 ? total : 6), dim3(512), DT_SMEM_BYTES, st, p, audio, d0, B, L, To, 1);
+    FD_CHECK_LAUNCH(h, "k_dblock0_tc");
+    return FD_OK;
+}
+
+static int emu_upsample_tc(fd_handle* h, int blk, const float* in, float* out, int B, int Tin, cudaStream_t st) {
+    const float* wh = sec(h, blk == 1 ? FD_S_LB1_UPT_HI : FD_S_LB2_UPT_HI);
+    const float* wl = sec(h, blk == 1 ? FD_S_LB1_UPT_LO : FD_S_LB2_UPT_LO);
+    const float* bias = sec(h, FD_S_LB0_UP_B + blk * FD_LB_STRIDE);
+    const int total = B * ((Tin + 127) / 128);
+    const int grid = total < 6 ? total : 6;
+    if (blk == 1) { auto k = k_upsample_tc<8>; FD_LAUNCH(k, dim3(grid), dim3(512), (ut_smem_bytes<8>()), st, wh, wl, bias, in, out, B, Tin, 1); }
+    else          { auto k = k_upsample_tc<4>; FD_LAUNCH(k, dim3(grid), dim3(512), (ut_smem_bytes<4>()), st, wh, wl, bias, in, out, B, Tin, 1); }
+    FD_CHECK_LAUNCH(h, "k_upsample_tc");
+    return FD_OK;
+}
 #endif  // FD_EMU
 
 static int launch_embed(fd_handle* h, const float* t_dev, const EmbedSteps& ts, int nslots, int B, float* ws, cudaStream_t st) {
@@ -459,7 +484,13 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             const dim3 grid((tout[n] + DB_TO - 1) / DB_TO, B);
             ScopedTimer tm(h, KC_DBLOCK, sd);
             bool done_tc = false;
-#ifndef FD_EMU
+#ifdef FD_EMU
+            if (n == 0 && h->mode == FD_MODE_TC_3XF16 && h->tc_dblock) {
+                int rc = emu_dblock0_tc(h, x_dev, d0, B, L, sd);
+                if (rc) return rc;
+                done_tc = true;
+            }
+#else
             if (n == 0 && h->mode != FD_MODE_FP32_SIMT && h->tc_dblock) {
                 int rc = tc_dblock0(h->tc_state, h->mode, x_dev, d0, B, L, sd, h->err, &h->launches);
                 if (rc) return rc;
@@ -567,7 +598,13 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             const dim3 grid((Tin + 31) / 32, B);
             ScopedTimer tm(h, KC_UPSAMPLE, st);
             bool up_done = false;
-#ifndef FD_EMU
+#ifdef FD_EMU
+            if (n >= 1 && h->mode == FD_MODE_TC_3XF16 && h->tc_upsample) {
+                int rc = emu_upsample_tc(h, n, blk_in, cur, B, Tin, st);
+                if (rc) return rc;
+                up_done = true;
+            }
+#else
             if (n >= 1 && h->mode != FD_MODE_FP32_SIMT && h->tc_upsample) {
                 int rc = tc_upsample(h->tc_state, h->mode, n, blk_in, cur, B, Tin, st, h->err, &h->launches);
                 if (rc) return rc;

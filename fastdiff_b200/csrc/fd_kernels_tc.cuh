@@ -838,16 +838,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
 }
-template <int N> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]);
-template <> __device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld_32x32b_x8(taddr, v); }
-template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x32b_x16(taddr, v); }
-template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+#endif  // !FD_EMU
+// ---- small helpers shared by the kernels that also compile for the emulator ----
+template <int N> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]);
+template <> __device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld_32x32b_x8(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x32b_x16(taddr, v); }
+template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
 // tf32 pieces by Veltkamp splitting (3 FP ops): hi = x rounded to nearest at 11 significant bits (low 13 mantissa bits
 // zero -> exactly a tf32), lo = x - hi exactly.  lo is handed to the tensor core as is (its own tf32 conversion of lo costs
 // <= 2^-11 |lo| <= 2^-22 |x|).  `cvt.rna.tf32.f32` is emulated with ~8 integer instructions on sm_100a (ncu: it was the
@@ -860,6 +862,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
     hi = make_float4(split_hi(v.x), split_hi(v.y), split_hi(v.z), split_hi(v.w));
     lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
 }
+#ifndef FD_EMU
 // gate non-linearities from ex2.approx/rcp.approx: abs error ~2e-7 (the precise tanhf/expf forms cost ~10x the instructions)
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + exp2f(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + exp2f(2.8853900817779268f * x)); }
@@ -1959,7 +1962,6 @@ k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ m
     }
 }
 
-#ifndef FD_EMU
 // ---------------------------------------------------------------------------------------------------------
 // K3+K4  first_audio_conv + DiffusionDBlock 0 on tensor cores (FastDiff_model.py:89, modules.py:127-138):
 //   xs[o] = first_conv(audio)[4 o]  (evaluated only at the kept positions);
@@ -1983,7 +1985,7 @@ struct DbTcParams {
 
 __global__ void __launch_bounds__(512, 1)
 k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ out, int B, int L, int To, int three_pass) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* a_tile0 = smem;                                          // two ping-pong tiles, each hi | lo, rows 0..143 (row r at r + 8)
     unsigned char* x_hi = smem + 4 * DT_ATILE;                             // xs (pre-activation) for the 1x1 residual, 128 rows
@@ -1998,11 +2000,8 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
     uint32_t* tmem_base_s = (uint32_t*)(bar + 2);
 
     const int tid = threadIdx.x, gw = tid >> 5, lane = tid & 31;
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (tid < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(64u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init_fence(); }
+    if (tid < 32) tmem_alloc(tmem_base_s, 64u);
     {
         const float4* sh = reinterpret_cast<const float4*>(p.cw_hi); const float4* sl = reinterpret_cast<const float4*>(p.cw_lo);
         for (int i = tid; i < 3 * 3 * 256; i += 512) {   // i = (layer*3 + tap)*256 + float4 within the 4 KB tap tile
@@ -2092,7 +2091,7 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
             if (gw_u == 0) {
                 tc_fence_after();
                 uint32_t at = smem_u + (uint32_t)(src * 2 * DT_ATILE), wt = smem_u + 4 * DT_ATILE + 2 * 16384 + (uint32_t)(layer * 24576);
-                asm volatile("" : "+r"(at), "+r"(wt));
+                FD_OPAQUE2(at, wt);
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
@@ -2179,7 +2178,7 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
     __syncthreads();
     if (tid < 32) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(64u) : "memory");
+        tmem_dealloc(*tmem_base_s, 64u);
     }
 }
 
@@ -2199,7 +2198,7 @@ template <int R>
 __global__ void __launch_bounds__(512, (R == 4 ? 2 : 1))
 k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, const float* __restrict__ bias,
               const float* __restrict__ in, float* __restrict__ out, int B, int Tin, int three_pass) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* a_hi = smem;                          // tile row ar <-> input row m0 - 1 + ar
     unsigned char* a_lo = a_hi + UT_ATILE;               // raw rows land here
@@ -2210,11 +2209,8 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
     constexpr uint32_t NCOLS = R * 64;
 
     const int tid = threadIdx.x, gw = tid >> 5, lane = tid & 31;
-    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    if (tid < 32) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(NCOLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init_fence(); }
+    if (tid < 32) tmem_alloc(tmem_base_s, NCOLS);
     for (int i = tid; i < 2 * R * 256; i += 512) {   // i = tap*256 + float4 within the 4 KB tap tile
         const int k = i >> 8, w = i & 255;
         reinterpret_cast<float4*>(wt + k * 8192)[w] = reinterpret_cast<const float4*>(w_hi)[i];
@@ -2268,7 +2264,7 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
         if (gw_u == 0) {
             tc_fence_after();
             uint32_t at = smem_u, wu = smem_u + 2 * UT_ATILE;
-            asm volatile("" : "+r"(at), "+r"(wu));
+            FD_OPAQUE2(at, wu);
             if (elect_one()) {
 #pragma unroll
                 for (int ph = 0; ph < R; ++ph) {
@@ -2329,11 +2325,12 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
     __syncthreads();
     if (tid < 32) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "r"(NCOLS) : "memory");
+        tmem_dealloc(*tmem_base_s, NCOLS);
     }
 }
 
 // x_in/x_out: (B,T,32); skip: (B,T,32) buffer or (block 2) the audio (B,T); kern: this layer's slice of the predicted kernels.
+#ifndef FD_EMU
 static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const float* x_in, const float* skip, const float* kern,
                                float* x_out, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches,
                                bool* done) {

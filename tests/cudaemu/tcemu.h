@@ -67,6 +67,7 @@ inline uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 constexpr uint32_t umma_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+constexpr uint32_t umma_idesc_tf32(int M, int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
 inline float emu_f16_at(uint32_t desc_start, uint32_t sbo, int row, int k) {   // element (row, k) of a K-major SWIZZLE_128B operand slice
     const uint32_t lin = desc_start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 128u + (uint32_t)k * 2u;
@@ -90,6 +91,34 @@ inline void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t
         for (int n = 0; n < N; ++n) {
             float acc = accumulate ? emu_tmem[lane0 + m][col0 + n] : 0.f;
             for (int k = 0; k < 16; ++k) acc += a[k] * bt[n][k];
+            emu_tmem[lane0 + m][col0 + n] = acc;
+        }
+    }
+}
+// kind::tf32: K = 8 fp32 elements per instruction (32 bytes of a K-major row).  The pieces the kernels feed have at most 11
+// significant bits (hi) or are tiny (lo), so the products are formed in fp32 without modelling the operand conversion to tf32.
+inline float emu_f32_at(uint32_t desc_start, uint32_t sbo, int row, int k) {
+    const uint32_t lin = desc_start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 128u + (uint32_t)k * 4u;
+    const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
+    float f;
+    memcpy(&f, emu_smem_ptr(phys), 4);
+    return f;
+}
+inline void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+    const uint32_t a0 = (uint32_t)(a_desc & 0x3FFF) << 4, b0 = (uint32_t)(b_desc & 0x3FFF) << 4;
+    const uint32_t sa = (uint32_t)((a_desc >> 32) & 0x3FFF) << 4, sb = (uint32_t)((b_desc >> 32) & 0x3FFF) << 4;
+    if (M != 128 || ((a_desc >> 61) & 7) != 2 || ((b_desc >> 61) & 7) != 2) { fprintf(stderr, "tcemu: unsupported MMA shape/layout\n"); abort(); }
+    const int lane0 = (int)(d_tmem >> 16), col0 = (int)(d_tmem & 0xFFFF);
+    float bt[256][8];
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < 8; ++k) bt[n][k] = emu_f32_at(b0, sb, n, k);
+    for (int m = 0; m < M; ++m) {
+        float a[8];
+        for (int k = 0; k < 8; ++k) a[k] = emu_f32_at(a0, sa, m, k);
+        for (int n = 0; n < N; ++n) {
+            float acc = accumulate ? emu_tmem[lane0 + m][col0 + n] : 0.f;
+            for (int k = 0; k < 8; ++k) acc += a[k] * bt[n][k];
             emu_tmem[lane0 + m][col0 + n] = acc;
         }
     }

@@ -57,10 +57,11 @@ def test_emulated_sampler_config0_vs_oracle(synth, emu_lib, ddim):
 
 @pytest.mark.parametrize("B,Tm", [(1, 5), (2, 33), (3, 1), (2, 129)])
 def test_emulated_tensor_core_mode_vs_oracle(synth, emu_lib, B, Tm):
-    """Mode tc_3xf16 on the CPU: k_kp_hidden_tc and k_lvc_layer_h run on a functional model of tcgen05.mma / TMEM / mbarrier /
-    cp.async.bulk (tests/cudaemu/tcemu.h: descriptors, SWIZZLE_128B with absolute-address XOR, kind::f16 K = 16, fp32 accumulation);
-    the kernel_conv GEMM is the FFMA one followed by an independent statement of the piece layout (k_emu_kern_to_pieces).  Checks
-    every LVC block and eps against the oracle -- the same assertions the GPU test makes."""
+    """Mode tc_3xf16 on the CPU: k_kp_hidden_tc, k_lvc_layer_h (kind::f16) and k_dblock0_tc, k_upsample_tc (kind::tf32) run on a
+    functional model of tcgen05.mma / TMEM / mbarrier / cp.async.bulk (tests/cudaemu/tcemu.h: real descriptors, SWIZZLE_128B with
+    absolute-address XOR, shifted start addresses, fp32 accumulation); the kernel_conv GEMM is the FFMA one followed by an
+    independent statement of the piece layout (k_emu_kern_to_pieces).  Checks the DBlocks, every LVC block and eps against the
+    oracle -- the same assertions the GPU test makes."""
     from fastdiff_b200.synthetic import make_inputs
     from oracle import fastdiff_oracle as O
     import torch.nn.functional as F
@@ -74,6 +75,9 @@ def test_emulated_tensor_core_mode_vs_oracle(synth, emu_lib, B, Tm):
     eng = net.engine()
     assert eng.get_mode() == 3
     assert (eps - ref).abs().max() < 5e-5
+    L = Tm * 256
+    for n, T in enumerate((L // 4, L // 32, L // 256)):          # down0 comes from the tensor-core DBlock 0
+        assert (eng.debug_read(f"down{n}", B, Tm).reshape(B, 32, T) - inter[f"down{n}"]).abs().max() < 2e-5
     e = inter["embed"]
     for n in range(3):
         p = f"lvc_blocks.{n}"
