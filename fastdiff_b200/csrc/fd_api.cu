@@ -29,6 +29,7 @@ struct fd_handle {
     int tc_upsample = 1;         // LVC-block upsample (blocks 1, 2) on tensor cores in the TC modes (option "tc_upsample")
     int tc_dblock = 1;           // DBlock 0 on tensor cores in the TC modes (option "tc_dblock")
     int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
+    int emu_gemm_tc = 1;         // emulation build, mode tc_3xf16: 1 = the CTA-pair GEMM on the tcgen05 model, 0 = FFMA GEMM + k_emu_kern_to_pieces
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
@@ -283,6 +284,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_kp")) { h->tc_kp = (int)value; return FD_OK; }
     if (!strcmp(key, "overlap")) { h->overlap = (int)value; return FD_OK; }
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
+    if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
         h->emb_slots = (int)value; return FD_OK;
@@ -418,6 +420,29 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
     return FD_OK;
 }
 
+// The CTA-pair kernel_conv GEMM (k_kc_gemm_tc2<true, 16>: 2-SM TMA, cta_group::2 MMA, multicast commit, remote arrives) on the model.
+static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st) {
+    KcgMaps maps;
+    const uint64_t rows = (uint64_t)B * (Tm + 2);
+    float inv[NBLK];
+    for (int n = 0; n < NBLK; ++n) {
+        const float* w16 = sec(h, FD_S_LB0_KCT_F16 + n);
+        emu_make_map_2d(&maps.w_hi[n], w16, KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM);
+        emu_make_map_2d(&maps.w_lo[n], w16 + (size_t)KCN * (KCK / 2), KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM);
+        emu_make_map_2d(&maps.h_hi[n], hk_hi + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128);
+        emu_make_map_2d(&maps.h_lo[n], hk_lo + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128);
+        inv[n] = 1.f / (emu_scale16(h, n) * S16_HK);
+    }
+    const int M = B * (Tm + 2) - 2;
+    const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
+    const int clusters = items < 8 ? items : 8;
+    auto k = k_kc_gemm_tc2<true, 16>;
+    FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
+                       sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+    FD_CHECK_LAUNCH(h, "k_kc_gemm_tc2");
+    return FD_OK;
+}
+
 // DBlock 0 and the upsampling of blocks 1/2 still run the 3xTF32 kernels in mode tc_3xf16: modelled as well
 static int emu_dblock0_tc(fd_handle* h, const float* audio, float* d0, int B, int L, cudaStream_t st) {
     DbTcParams p;
@@ -550,7 +575,12 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         }
     }
 #ifdef FD_EMU
-    const bool simt_gemm = true;
+    const bool simt_gemm = !(h->mode == FD_MODE_TC_3XF16 && h->emu_gemm_tc);
+    if (!simt_gemm) {
+        ScopedTimer tm(h, KC_KC_GEMM, st);
+        int rc = emu_kc_gemm_tc2(h, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st);
+        if (rc) return rc;
+    }
 #else
     const bool simt_gemm = h->mode == FD_MODE_FP32_SIMT;
 #endif

@@ -164,6 +164,15 @@ __device__ __forceinline__ uint32_t pack_f16x2_sat(float upper, float lower) {
 __device__ __forceinline__ float2 unpack_f16x2(uint32_t u) { return __half22float2(*reinterpret_cast<const __half2*>(&u)); }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {   // the same warp of both CTAs of a pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t base, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
+}
+// one float -> fp16 bits, round to nearest even, saturating at +-65504
+__device__ __forceinline__ uint16_t f16_sat_bits(float f) { uint16_t h; asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(f)); return h; }
 // opaque to the optimiser: keeps ptxas from hoisting ~100 descriptors out of a tile loop
 #define FD_OPAQUE(x) asm volatile("" : "+r"(x))
 #define FD_OPAQUE2(x, y) asm volatile("" : "+r"(x), "+r"(y))
@@ -171,6 +180,7 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 // ---------------------------------------------------------------------------------------------------------
 // kernel_conv GEMM
 // ---------------------------------------------------------------------------------------------------------
+#endif  // !FD_EMU
 constexpr int KCG_BM = 128;                 // n rows per tile (MMA M)
 constexpr int KCG_BN = 256;                 // frames per tile (MMA N)
 constexpr int KCG_KATOM = 32;               // floats per 128-byte swizzle row
@@ -185,6 +195,7 @@ struct KcgMaps {               // per LVC block: weights hi/lo, hidden hi/lo
     CUtensorMap w_hi[NBLK], w_lo[NBLK], h_hi[NBLK], h_lo[NBLK];
 };
 
+#ifndef FD_EMU
 __global__ void __launch_bounds__(320, 1)
 k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
              const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass) {
@@ -342,12 +353,14 @@ k_kc_gemm_tc(const __grid_constant__ KcgMaps maps, const float* __restrict__ bia
 //   * epilogue warps of both CTAs arrive (remotely for the peer) on the leader's tmem-empty barrier.
 // 3-stage ring of 64 KB per CTA, 2 x 256-column accumulators, 8 epilogue warps per CTA as in the 1-CTA kernel.
 // ---------------------------------------------------------------------------------------------------------
+#endif  // !FD_EMU
 constexpr int KC2_STAGES = 3;
 constexpr int KC2_A_BYTES = 128 * 128;       // 16 KB: 128 weight rows x one 32-float k-atom
 constexpr int KC2_B_BYTES = 128 * 128;       // 16 KB: this CTA's 128 of the 256 frame rows
 constexpr int KC2_STAGE_BYTES = 2 * KC2_A_BYTES + 2 * KC2_B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 64 KB
 constexpr int KC2_SMEM_BYTES = KC2_STAGES * KC2_STAGE_BYTES + 1024 + 256;
 
+#ifndef FD_EMU
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -383,6 +396,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 
 }
 
+#endif  // !FD_EMU
 // F16 = true (mode tc_3xf16): the operands are fp16 pieces (weights LBn_KCT_F16 prescaled per tensor, hidden rows of 64 fp16
 // = 128 B prescaled by S16_HK), a k-atom is 64 values = one tap of the im2col (box at row p + a), every MMA is kind::f16 with
 // K = 16, and the epilogue undoes the scales: kern = acc * inv[blk] + bias.  Half the MMAs and half the operand bytes of the
@@ -401,7 +415,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
               float inv0, float inv1, float inv2, int exp_mask) {
     constexpr int NATOM = F16 ? 3 : 6;
     constexpr int CPW = 256 / (EPW / 4);   // frame columns per epilogue warp
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* bars = (uint64_t*)(smem + KC2_STAGES * KC2_STAGE_BYTES);
     uint64_t* full_bar = bars;                     // [STAGES]  (leader's copy is used) TMA of both CTAs -> leader MMA
@@ -423,11 +437,10 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
     if (threadIdx.x == 0) {
         for (int s = 0; s < KC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * EPW); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_init_fence();
     }
     if (warp == 0) {   // collective over the pair: the same warp of both CTAs
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        tmem_alloc_2sm(tmem_base_s, 512u);
     }
     tc_fence_before();
     cluster_sync_all();     // barriers of both CTAs initialised and TMEM allocated before any remote access
@@ -535,18 +548,18 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             [[maybe_unused]] const int odd = lane & 1;
             auto put_pieces = [&](uint16_t* ph, uint16_t* pl, float accv) {
                 const float sv = fmaf(accv, inv_s, bv_s);
-                uint16_t h16, l16;
-                asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h16) : "f"(sv));
+                uint16_t l16;
+                const uint16_t h16 = f16_sat_bits(sv);
 #if KC_STORE_SHFL
                 // even lane (element i) keeps the hi halves of (i, i+1), odd lane the lo halves; ph/pl point at the even element's halfword
                 const float hi_f = f16_bits_to_float(h16), lo_f = sv - hi_f;
                 const float recv = __shfl_xor_sync(0xffffffffu, odd ? hi_f : lo_f, 1);
                 uint32_t packed;
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(odd ? lo_f : recv), "f"(odd ? recv : hi_f));
+                packed = pack_f16x2_sat(odd ? lo_f : recv, odd ? recv : hi_f);
                 *reinterpret_cast<uint32_t*>(odd ? pl : ph) = packed;
                 (void)l16;
 #else
-                asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(l16) : "f"(sv - f16_bits_to_float(h16)));
+                l16 = f16_sat_bits(sv - f16_bits_to_float(h16));
 #if KC_STORE_CS
                 asm volatile("st.global.cs.b16 [%0], %1;" ::"l"(ph), "h"(h16) : "memory");
                 asm volatile("st.global.cs.b16 [%0], %1;" ::"l"(pl), "h"(l16) : "memory");
@@ -647,10 +660,11 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
     cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still touch its smem / barriers
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        tmem_dealloc_2sm(tmem_base, 512u);
     }
 }
 
+#ifndef FD_EMU
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------

@@ -41,8 +41,11 @@ extern thread_local dim3 t_threadIdx, t_blockIdx;
 extern dim3 g_blockDim, g_gridDim;
 extern thread_local unsigned char* t_dyn_smem;
 extern thread_local size_t t_dyn_smem_bytes;
-extern thread_local unsigned t_linear_tid;
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+extern thread_local unsigned t_linear_tid, t_cta_rank;
+void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body, unsigned cluster = 1);
+unsigned cluster_rank();                  // CTA pairs (cluster = 2): both CTAs of a pair run as one fibre set on one OS thread
+unsigned char* cluster_smem(unsigned rank);
+void cluster_barrier();
 void syncthreads();
 void syncwarp();
 void barrier(int key, int expected);   // key 1..15: named barrier (bar.sync key, expected)
@@ -57,6 +60,8 @@ void cta_end();
 static inline void __syncthreads() { emu::syncthreads(); }
 
 #define FD_LAUNCH(kern, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); })
+#define FD_LAUNCH_CLUSTER2(kern, grid, block, smem, stream, ...) emu::launch((grid), (block), (smem), [=]() { kern(__VA_ARGS__); }, 2)
+#define __cluster_dims__(...)
 #define FD_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::t_dyn_smem)
 
 // arithmetic intrinsics (compile with -ffp-contract=off so the _rn forms are honoured)

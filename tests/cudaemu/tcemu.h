@@ -18,7 +18,8 @@ static_assert(sizeof(EmuMbar) <= 12, "mbarrier state");
 struct EmuMbar8 { int16_t pending; int16_t count; int32_t tx_phase; };            // tx in the upper 31 bits (signed), phase in bit 0
 static_assert(sizeof(EmuMbar8) == 8, "mbarrier state");
 
-inline thread_local float emu_tmem[128][512];
+inline thread_local float emu_tmem_all[2][128][512];   // one TMEM per CTA of a pair
+#define emu_tmem (emu_tmem_all[emu::t_cta_rank])
 
 inline uint32_t smem_u32(const void* p) { return (uint32_t)((const unsigned char*)p - emu::t_dyn_smem); }
 inline unsigned char* emu_smem_ptr(uint32_t a) { return emu::t_dyn_smem + a; }
@@ -123,6 +124,82 @@ inline void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_
         }
     }
 }
+inline uint16_t emu_f16_sat(float f);
+// ---- CTA pairs (cta_group::2): the kernel_conv GEMM ---------------------------------------------------------------------------
+// TMA tensor maps: the driver's opaque CUtensorMap is replaced by a plain description of the 2-D fp32-sized tensor and its box.
+struct CUtensorMap { unsigned char opaque[128]; } __attribute__((aligned(64)));
+struct EmuTmap { const unsigned char* base; uint64_t cols, rows, stride_bytes; uint32_t box_cols, box_rows; };
+static_assert(sizeof(EmuTmap) <= sizeof(CUtensorMap), "tensor map model");
+inline void emu_make_map_2d(CUtensorMap* m, const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_cols,
+                            uint32_t box_rows) {
+    EmuTmap t{(const unsigned char*)base, cols, rows, row_stride_bytes, box_cols, box_rows};
+    memset(m, 0, sizeof *m);
+    memcpy(m, &t, sizeof t);
+}
+inline uint32_t cluster_ctarank() { return emu::cluster_rank(); }
+inline void cluster_sync_all() { emu::cluster_barrier(); }
+inline uint64_t* emu_bar_of_rank(uint64_t* bar, unsigned rank) {   // the barrier at the same shared-memory offset in CTA `rank` of the pair
+    return (uint64_t*)(emu::cluster_smem(rank) + ((unsigned char*)bar - emu::t_dyn_smem));
+}
+// cp.async.bulk.tensor.2d ... cta_group::2: box {c0 .. c0+box_cols, c1 .. c1+box_rows} (out-of-range rows/cols read as zero) into
+// this CTA's shared memory as 128-byte rows, SWIZZLE_128B (dst is 1024-byte aligned: chunk j of row r at position j ^ (r & 7));
+// the bytes complete on the LEADER's copy of the barrier.
+inline void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    EmuTmap t;
+    memcpy(&t, map, sizeof t);
+    if (t.box_cols != 32) { fprintf(stderr, "tcemu: TMA box must be 128 bytes wide\n"); abort(); }
+    unsigned char* dst = (unsigned char*)smem_dst;
+    for (uint32_t r = 0; r < t.box_rows; ++r) {
+        const int64_t row = (int64_t)c1 + r;
+        for (uint32_t j = 0; j < 8; ++j) {
+            float chunk[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int e = 0; e < 4; ++e) {
+                const int64_t col = (int64_t)c0 + j * 4 + e;
+                if (row >= 0 && (uint64_t)row < t.rows && col >= 0 && (uint64_t)col < t.cols)
+                    memcpy(&chunk[e], t.base + (uint64_t)row * t.stride_bytes + (uint64_t)col * 4, 4);
+            }
+            memcpy(dst + r * 128 + ((j ^ (r & 7)) << 4), chunk, 16);
+        }
+    }
+    emu_mbar_complete_tx(emu_bar_of_rank(bar, 0), t.box_rows * 128u);
+}
+inline void tc_commit_2sm(uint64_t* bar) { mbar_arrive(emu_bar_of_rank(bar, 0)); mbar_arrive(emu_bar_of_rank(bar, 1)); }
+inline void mbar_arrive_leader(uint64_t* bar) { mbar_arrive(emu_bar_of_rank(bar, 0)); }
+inline void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t) { *dst_smem = 0; }
+inline void tmem_dealloc_2sm(uint32_t, uint32_t) {}
+inline float emu_f16_at_rank(unsigned rank, uint32_t desc_start, uint32_t sbo, int row, int k) {
+    const uint32_t lin = desc_start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 128u + (uint32_t)k * 2u;
+    const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
+    uint16_t h;
+    memcpy(&h, emu::cluster_smem(rank) + phys, 2);
+    return f16_bits_to_float_soft(h);
+}
+// tcgen05.mma.cta_group::2.kind::f16, M = 256, N = 256: CTA r of the pair supplies A rows [128 r, +128) and B rows [128 r, +128) from
+// the same shared-memory offsets; CTA r's TMEM receives its 128 rows of D (all 256 columns).
+inline void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
+    if (M != 256 || N != 256) { fprintf(stderr, "tcemu: unsupported 2-CTA MMA shape\n"); abort(); }
+    const uint32_t a0 = (uint32_t)(a_desc & 0x3FFF) << 4, b0 = (uint32_t)(b_desc & 0x3FFF) << 4;
+    const uint32_t sa = (uint32_t)((a_desc >> 32) & 0x3FFF) << 4, sb = (uint32_t)((b_desc >> 32) & 0x3FFF) << 4;
+    const int lane0 = (int)(d_tmem >> 16), col0 = (int)(d_tmem & 0xFFFF);
+    static thread_local float bt[256][16];
+    for (int n = 0; n < 256; ++n)
+        for (int k = 0; k < 16; ++k) bt[n][k] = emu_f16_at_rank((unsigned)(n >> 7), b0, sb, n & 127, k);
+    for (unsigned r = 0; r < 2; ++r)
+        for (int m = 0; m < 128; ++m) {
+            float a[16];
+            for (int k = 0; k < 16; ++k) a[k] = emu_f16_at_rank(r, a0, sa, m, k);
+            float* drow = &emu_tmem_all[r][lane0 + m][col0];
+            for (int n = 0; n < 256; ++n) {
+                float acc = accumulate ? drow[n] : 0.f;
+                for (int k = 0; k < 16; ++k) acc += a[k] * bt[n][k];
+                drow[n] = acc;
+            }
+        }
+}
+inline void umma_tf32_2sm(uint32_t, uint64_t, uint64_t, uint32_t, uint32_t) { fprintf(stderr, "tcemu: the tf32 CTA-pair GEMM is not modelled\n"); abort(); }
+inline uint16_t f16_sat_bits(float f) { return emu_f16_sat(f); }
+
 template <int N> inline void emu_tmem_ld(uint32_t taddr, uint32_t (&v)[N]) {
     const int lane = (int)(taddr >> 16) + (int)(emu::t_linear_tid & 31), col = (int)(taddr & 0xFFFF);
     for (int i = 0; i < N; ++i) memcpy(&v[i], &emu_tmem[lane][col + i], 4);

@@ -57,11 +57,12 @@ def test_emulated_sampler_config0_vs_oracle(synth, emu_lib, ddim):
 
 @pytest.mark.parametrize("B,Tm", [(1, 5), (2, 33), (3, 1), (2, 129)])
 def test_emulated_tensor_core_mode_vs_oracle(synth, emu_lib, B, Tm):
-    """Mode tc_3xf16 on the CPU: k_kp_hidden_tc, k_lvc_layer_h (kind::f16) and k_dblock0_tc, k_upsample_tc (kind::tf32) run on a
-    functional model of tcgen05.mma / TMEM / mbarrier / cp.async.bulk (tests/cudaemu/tcemu.h: real descriptors, SWIZZLE_128B with
-    absolute-address XOR, shifted start addresses, fp32 accumulation); the kernel_conv GEMM is the FFMA one followed by an
-    independent statement of the piece layout (k_emu_kern_to_pieces).  Checks the DBlocks, every LVC block and eps against the
-    oracle -- the same assertions the GPU test makes."""
+    """Mode tc_3xf16 on the CPU, every kernel of the default path: k_kp_hidden_tc, k_lvc_layer_h, the CTA-pair k_kc_gemm_tc2
+    (kind::f16; 2-SM TMA boxes, cta_group::2 MMA, multicast commit, remote arrives) and k_dblock0_tc, k_upsample_tc (kind::tf32) run
+    on a functional model of tcgen05 / TMEM / mbarrier / TMA / cp.async.bulk (tests/cudaemu/tcemu.h: real descriptors, SWIZZLE_128B
+    with absolute-address XOR, shifted start addresses, fp32 accumulation).  Checks the DBlocks, the predicted kernels, every LVC
+    block and eps against the oracle -- the same assertions the GPU test makes -- and the GEMM's fp16-piece output against an
+    independent statement of that layout (FFMA GEMM + k_emu_kern_to_pieces, option emu_gemm_tc = 0)."""
     from fastdiff_b200.synthetic import make_inputs
     from oracle import fastdiff_oracle as O
     import torch.nn.functional as F
@@ -91,6 +92,13 @@ def test_emulated_tensor_core_mode_vs_oracle(synth, emu_lib, B, Tm):
     net((x, mel, t))
     assert (eng.debug_read("lvc1", B, Tm).reshape(B, 32, Tm * 64) - inter["lvc1"]).abs().max() < 2e-4
     eng.set_option("stop_after", 99)
+    k_tc = [eng.debug_read(f"kernels{n}", B, Tm).clone() for n in range(3)]
+    eng.set_option("emu_gemm_tc", 0)
+    eps_conv = net((x, mel, t))
+    eng.set_option("emu_gemm_tc", 1)
+    for n in range(3):
+        assert (eng.debug_read(f"kernels{n}", B, Tm) - k_tc[n]).abs().max() < 2e-5
+    assert (eps_conv - eps).abs().max() < 5e-5
     net.mode = "fp32_simt"
     assert (net((x, mel, t)) - eps).abs().max() < 5e-5
 
