@@ -116,3 +116,23 @@ def test_emulated_tensor_core_mode_is_batch_and_tiling_independent(synth, emu_li
     full = net((x, mel, t))
     for lo, hi in ((0, 1), (1, 3)):
         assert torch.equal(net((x[lo:hi], mel[lo:hi], t[lo:hi])), full[lo:hi])
+
+
+def test_emulated_tensor_core_sampler_vs_oracle(synth, emu_lib):
+    """N = 4 reverse loop in mode tc_3xf16 on the model, the reference's RNG stream, every intermediate x_t."""
+    import fastdiff_b200 as fb
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    B, Tm = 2, 20
+    _, mel = make_inputs(B, Tm, 5)
+    dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
+    torch.manual_seed(11)
+    ref = O.sample(W, (B, 1, Tm * 256), dh, torch.FloatTensor(N4), mel, return_sequence=True)
+    torch.manual_seed(11)
+    got = fb.sampling_given_noise_schedule(net, (B, 1, Tm * 256), dh, torch.FloatTensor(N4), condition=mel, return_sequence=True)
+    assert net.engine().get_mode() == 3
+    for i in range(1, 5):
+        assert (got[i] - ref[i]).abs().max() < 5e-4, i
