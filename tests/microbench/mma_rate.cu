@@ -4,13 +4,11 @@
 #include <cstdio>
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include "../../include/fastdiff_b200.h"
 #include "fd_kernels_tc.cuh"
 using namespace fd;
 
-__device__ __forceinline__ void umma_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
-}
+// (umma_f16 comes from fd_kernels_tc.cuh)
 
 template <int N, int KIND /*0 tf32, 1 bf16*/, int NACC, int SWZ>
 __global__ void __launch_bounds__(128, 1) k_rate(unsigned long long* out, int iters) {
