@@ -4,6 +4,7 @@ batch of 2 (23 + 22 frames)."""
 import os
 import sys
 
+import pytest
 import torch
 import torch.multiprocessing as mp
 
@@ -12,7 +13,7 @@ N4 = [3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]
 B, TM = 2, 45
 
 
-def _worker(rank, world, port, emu_lib, q):
+def _worker(rank, world, port, emu_lib, q, mode):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -24,6 +25,7 @@ def _worker(rank, world, port, emu_lib, q):
     from fastdiff_b200.timeshard import TimeShardedSampler
     sd = make_state_dict(1234, g_jitter=0.1) if rank == 0 else None
     sh = ShardedFastDiff(sd, device="cpu", lib_path=emu_lib)           # weights: one broadcast
+    sh.engine.set_mode(mode)
     ts = TimeShardedSampler(sh.engine)
     _, mel = make_inputs(B, TM, 8)
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
@@ -35,7 +37,8 @@ def _worker(rank, world, port, emu_lib, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_time_shard_matches_unsharded(emu_lib, synth):
+@pytest.mark.parametrize("mode", ["fp32_simt", "tc_3xf16"])
+def test_two_rank_time_shard_matches_unsharded(emu_lib, synth, mode):
     import fastdiff_b200 as fb
     from fastdiff_b200.engine import Engine
     from fastdiff_b200.sampler import build_steps
@@ -43,8 +46,8 @@ def test_two_rank_time_shard_matches_unsharded(emu_lib, synth):
     from fastdiff_b200.weights import pack_state_dict
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, emu_lib, q)) for r in range(2)]
+    port = 31500 + os.getpid() % 2000 + (7 if mode == "tc_3xf16" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, emu_lib, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     import queue
@@ -62,6 +65,7 @@ def test_two_rank_time_shard_matches_unsharded(emu_lib, synth):
     sd, _ = synth
     eng = Engine(device="cpu", lib_path=emu_lib)
     eng.load_blob(pack_state_dict(sd))
+    eng.set_mode(mode)
     _, mel = make_inputs(B, TM, 8)
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
     _, steps = build_steps(dh, torch.FloatTensor(N4))
@@ -72,4 +76,4 @@ def test_two_rank_time_shard_matches_unsharded(emu_lib, synth):
     eng.sample(x, mel, steps, noise=zs)
     assert got.shape == x.shape
     err = (got - x).abs().max().item()
-    assert err <= 1e-6, err          # same arithmetic per output sample; only the tiling differs
+    assert err <= 1e-6, err          # same arithmetic per output sample; only the tiling differs (tc_3xf16: the tensor-core model)
