@@ -136,3 +136,18 @@ def test_emulated_tensor_core_sampler_vs_oracle(synth, emu_lib):
     assert net.engine().get_mode() == 3
     for i in range(1, 5):
         assert (got[i] - ref[i]).abs().max() < 5e-4, i
+
+
+@pytest.mark.parametrize("B,Tm", [(1, 2), (1, 9), (3, 17), (1, 65), (5, 7), (1, 113), (1, 225)])
+def test_emulated_tensor_core_mode_ragged_shapes(synth, emu_lib, B, Tm):
+    """Tile-boundary shapes of the tensor-core kernels (kernel-predictor tiles of 112 frames, LVC tiles of 128 steps with 64- and
+    256-step frames, GEMM tiles of 256 frames): eps against the oracle on the model.  The emulation launches few CTAs, so every
+    group walks several tiles (carried halo rows, kernel reuse, ring wrap-around) even at these sizes."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    x, mel = make_inputs(B, Tm, 10 + Tm)
+    t = torch.linspace(3.0, 900.0, B).reshape(B, 1)
+    assert (net((x, mel, t)) - O.denoise(W, x, mel, t)).abs().max() < 5e-5
