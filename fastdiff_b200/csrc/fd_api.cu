@@ -31,6 +31,8 @@ struct fd_handle {
     int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
     int emu_gemm_tc = 1;         // emulation build, mode tc_3xf16: 1 = the CTA-pair GEMM on the tcgen05 model, 0 = FFMA GEMM + k_emu_kern_to_pieces
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
+    int tc_b0 = 0;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h)
+    int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
                                  // (option "overlap"; forked from / joined into the caller's stream with events inside every call)
@@ -284,6 +286,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_kp")) { h->tc_kp = (int)value; return FD_OK; }
     if (!strcmp(key, "overlap")) { h->overlap = (int)value; return FD_OK; }
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
+    if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
@@ -467,6 +470,20 @@ static int emu_upsample_tc(fd_handle* h, int blk, const float* in, float* out, i
     FD_CHECK_LAUNCH(h, "k_upsample_tc");
     return FD_OK;
 }
+static int emu_lvc_layer_b0(fd_handle* h, int layer, const float* x_in, const float* skip, const float* kern, float* x_out,
+                            int B, int T, int Tm, int dil, cudaStream_t st) {
+    LvcHParams hp;
+    hp.cw16 = sec(h, FD_S_LB0_CONV_F16) + (size_t)layer * (LH_CW_BYTES / 4);
+    hp.conv_b = sec(h, FD_S_LB0_CONV_B) + layer * C;
+    hp.first_w = nullptr; hp.first_b = nullptr;
+    const float inv_c = 1.f / (S16_ACT * emu_scale16(h, 4 + layer)), inv_l = 1.f / (S16_ACT * S16_KERN);
+    const int tiles = B * ((T + LT_TT - 1) / LT_TT);
+    int grid = (tiles + 2) / 3; if (grid < 1) grid = 1; if (grid > 8) grid = 8;   // several tiles per CTA: the ring runs across tiles
+    FD_LAUNCH(k_lvc_layer_b0h, dim3(grid), dim3(512), LB0_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l,
+              layer == 0 ? 1 : 0, layer < LAYERS - 1 ? 1 : 0);
+    FD_CHECK_LAUNCH(h, "k_lvc_layer_b0h");
+    return FD_OK;
+}
 #endif  // FD_EMU
 
 static int launch_embed(fd_handle* h, const float* t_dev, const EmbedSteps& ts, int nslots, int B, float* ws, cudaStream_t st) {
@@ -494,6 +511,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     const int slot = emb_slot < 0 ? 0 : emb_slot;
     float* cnoise = ws + w.cnoise + (size_t)slot * NBLK * B * COND; float* hk = ws + w.hk; float* kern = ws + w.kern;
     float* d0 = ws + w.d0; float* d1 = ws + w.d1; float* d2 = ws + w.d2; float* xa = ws + w.xa; float* xb = ws + w.xb;
+    h->b0_converted = 0;
 
     // -- first_audio_conv + the three DiffusionDBlocks: independent of the kernel-predictor path, so they run on the side stream
     //    (forked here, joined before the first LVC block) unless a debugging stop or the option "overlap" = 0 asks for serial order
@@ -649,6 +667,18 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         }
         const float* skip = (n == 0) ? d1 : (n == 1 ? d0 : x_dev);
         const float* kern_n = kern + (size_t)n * B * Tm * KCN;
+        const bool b0_tc = (n == 0 && h->tc_b0 && h->mode == FD_MODE_TC_3XF16);
+        if (b0_tc) {   // experimental: the GEMM's fp32 panel image of block 0 -> fp16 pieces, in place, all layers
+            ScopedTimer tm(h, KC_LVC0, st);
+#ifdef FD_EMU
+            FD_LAUNCH(k_b0_panel_to_pieces, dim3(B * Tm * LAYERS), dim3(256), 0, st, kern, B * Tm);
+            FD_CHECK_LAUNCH(h, "k_b0_panel_to_pieces");
+#else
+            int rc = tc_b0_convert(h->tc_state, kern, B, Tm, st, h->err, &h->launches);
+            if (rc) return rc;
+#endif
+            h->b0_converted = 1;
+        }
         for (int i = 0; i < LAYERS; ++i) {
             LvcParams p;
             p.conv_w = sec(h, FD_S_LB0_CONV_W + n * FD_LB_STRIDE) + i * KK * C;
@@ -659,13 +689,21 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             bool done = false;
             ScopedTimer tm(h, KC_LVC0 + n, st);
 #ifdef FD_EMU
-            if (h->mode == FD_MODE_TC_3XF16 && n >= 1) {
+            if (b0_tc) {
+                int rc = emu_lvc_layer_b0(h, i, cur, skip, kl, oth, B, T, Tm, dil, st);
+                if (rc) return rc;
+                done = true;
+            } else if (h->mode == FD_MODE_TC_3XF16 && n >= 1) {
                 int rc = emu_lvc_layer_h(h, n, i, cur, skip, kl, oth, B, T, Tm, dil, st);
                 if (rc) return rc;
                 done = true;
             }
 #else
-            if (h->mode != FD_MODE_FP32_SIMT) {
+            if (b0_tc) {
+                int rc = tc_lvc_layer_b0(h->tc_state, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches);
+                if (rc) return rc;
+                done = true;
+            } else if (h->mode != FD_MODE_FP32_SIMT) {
                 int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done);
                 if (rc) return rc;
             }
@@ -877,7 +915,7 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         *count = want_bias ? (size_t)B * LAYERS * LVC_OUT * Tm : (size_t)B * LAYERS * C * LVC_OUT * KS * Tm;
         if (!out_dev) return FD_OK;
         FD_LAUNCH(k_kern_to_ref, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, ws + w.kern + (size_t)n * B * Tm * KCN, out_dev, B, Tm, want_bias,
-                  n == 0 ? 1 : (h->mode == FD_MODE_TC_3XF16 ? 2 : 0));
+                  n == 0 ? (h->b0_converted ? 2 : 1) : (h->mode == FD_MODE_TC_3XF16 ? 2 : 0));
         FD_CHECK_LAUNCH(h, "k_kern_to_ref");
         return FD_OK;
     }

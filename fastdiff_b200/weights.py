@@ -194,7 +194,7 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         scales[n] = sc
         hi, lo = f16_split(kct, sc)
         S[f"LB{n}_KCT_F16"] = _u16_as_f32(np.stack([hi, lo]))
-    for n in (1, 2):
+    for n in (0, 1, 2):
         cw = torch.stack([W[f"lvc_blocks.{n}.convs.{i}.weight"] for i in range(LAYERS)]).numpy()   # [l][co][ci][k]
         rows = np.zeros((LAYERS, KS, C, 8, 8), dtype=np.uint16)                          # [l][k][co][chunk position][8 fp16]
         for l in range(LAYERS):
@@ -240,6 +240,7 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
                 slots[10 + 3 * l + j, 0] = _tile(np.ascontiguousarray(hi[:, :, j]))
                 slots[10 + 3 * l + j, 1] = _tile(np.ascontiguousarray(lo[:, :, j]))
         S[f"LB{n}_KPW_F16"] = _u16_as_f32(slots)
+    S["LB0_CONV_F16"] = conv16[0]
     S["SCALES16"] = torch.from_numpy(scales)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}

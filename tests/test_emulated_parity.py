@@ -151,3 +151,42 @@ def test_emulated_tensor_core_mode_ragged_shapes(synth, emu_lib, B, Tm):
     x, mel = make_inputs(B, Tm, 10 + Tm)
     t = torch.linspace(3.0, 900.0, B).reshape(B, 1)
     assert (net((x, mel, t)) - O.denoise(W, x, mel, t)).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize("B,Tm", [(1, 5), (2, 33), (1, 129), (3, 17)])
+def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm):
+    """Option tc_b0 (experimental, default off): LVC block 0 (hop 8) on the tensor-core model in swapped-operand form --
+    k_b0_panel_to_pieces + k_lvc_layer_b0h (kernels of a frame pair as the M = 128 operand, 16 step columns, 3-slot kernel ring
+    across tiles, second MMA pass for the halo rows, tanh/sigmoid exchange through shared memory).  Block-0 output, the decoded
+    pieces and eps against the oracle, and against the default (SIMT block 0) path."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    import torch.nn.functional as F
+    sd, W = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    x, mel = make_inputs(B, Tm, 21)
+    t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
+    ref, inter = O.denoise(W, x, mel, t, return_intermediates=True)
+    eng = net.engine()
+    eps_default = net((x, mel, t))
+    eng.set_option("tc_b0", 1)
+    eps = net((x, mel, t))
+    assert (eps - ref).abs().max() < 5e-5
+    assert (eps - eps_default).abs().max() < 5e-5
+    noise = F.linear(inter["embed"], W["lvc_blocks.0.fc_t.weight"], W["lvc_blocks.0.fc_t.bias"]).unsqueeze(-1)
+    k, bb = O.kernel_predictor(W, "lvc_blocks.0.kernel_predictor", mel + noise)
+    assert (eng.debug_read("kernels0", B, Tm).reshape(k.shape) - k).abs().max() < 4e-5      # decoded from the converted pieces
+    assert (eng.debug_read("kbias0", B, Tm).reshape(bb.shape) - bb).abs().max() < 4e-5
+    eng.set_option("stop_after", 3)
+    net((x, mel, t))
+    assert (eng.debug_read("lvc0", B, Tm).reshape(B, 32, Tm * 8) - inter["lvc0"]).abs().max() < 1e-4
+    eng.set_option("stop_after", 1)                 # the GEMM only: block 0's kernels are still the fp32 panel image
+    net((x, mel, t))
+    assert (eng.debug_read("kernels0", B, Tm).reshape(k.shape) - k).abs().max() < 4e-5
+    eng.set_option("stop_after", 99)
+    # an item evaluated alone = the same item inside the batch, bitwise (per-tile work is independent of the tile walk)
+    if B > 1:
+        assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), eps[1:2])
+    net.mode = "fp32_simt"                          # the option only applies to mode tc_3xf16
+    assert (net((x, mel, t)) - ref).abs().max() < 5e-5
