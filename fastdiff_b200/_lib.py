@@ -42,6 +42,7 @@ SYMBOLS = {
     "fd_denoise": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "fd_sample": (C.c_int, [_P, _P, _P, C.POINTER(fd_step), C.c_int, _P, C.c_int, C.c_uint64, C.c_int, C.c_int, _P,
                             C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "fd_reverse_update": (C.c_int, [_P, _P, _P, _P, C.POINTER(fd_step), C.c_int, C.c_uint64, C.c_uint32, _P, C.c_size_t, _P]),
     "fd_wav_int16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "fd_mel_frontend": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fd_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_size_t), C.c_int, C.c_int, _P, _P]),

@@ -850,6 +850,22 @@ extern "C" int fd_mel_frontend(fd_handle* h, const float* wav_dev, int B, int n_
     return FD_OK;
 }
 
+extern "C" int fd_reverse_update(fd_handle* h, float* x_dev, const float* eps_dev, const float* z_dev, const fd_step* step, int ddim,
+                                 uint64_t seed, uint32_t draw, float* seq_dev, size_t count, void* stream) {
+    if (!h || !x_dev || !eps_dev || !step || count < 1) return fail(h, FD_ERR_INVALID, "fd_reverse_update: bad argument");
+    if (count > (size_t)0x7fffffff * 1024) return fail(h, FD_ERR_INVALID, "fd_reverse_update: count too large for one launch");
+    FD_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    UpdateParams p;
+    p.coef = step->coef_eps; p.div = step->div; p.sigma = step->sigma; p.c1 = step->c1; p.c2 = step->c2; p.c3 = step->c3;
+    p.ddim = ddim ? 1 : 0; p.add_noise = step->add_noise ? 1 : 0; p.draw = draw; p.seed = seed;
+    const uintptr_t al = (uintptr_t)x_dev | (uintptr_t)eps_dev | (uintptr_t)seq_dev;
+    const unsigned blocks = (unsigned)((count + 1023) / 1024);
+    FD_LAUNCH(k_reverse_update, dim3(blocks), dim3(256), 0, st, p, x_dev, eps_dev, z_dev, seq_dev, count, (al & 15) == 0 ? 1 : 0);
+    FD_CHECK_LAUNCH(h, "k_reverse_update");
+    return FD_OK;
+}
+
 extern "C" int fd_wav_int16(fd_handle* h, const float* x_dev, int16_t* out_dev, int B, int L, void* workspace_dev, void* stream) {
     if (!h || !x_dev || !out_dev || !workspace_dev || B < 1 || L < 1) return fail(h, FD_ERR_INVALID, "fd_wav_int16: bad argument");
     FD_CUDA(h, cudaSetDevice(h->device));

@@ -765,6 +765,49 @@ __global__ void __launch_bounds__(256) k_final(FinalParams p, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// One reverse-step update on its own (util.py:219-229), for denoisers other than FastDiff that share the sampler (SURVEY.md 8f.4:
+// the network then is the caller's torch module, only the update runs here).  The same operation sequence as the tail of k_final:
+//   ddim == 0:  x = (x - coef*eps) / div;  if (add_noise) x = x + sigma*z        ddim != 0:  x = c1*x + c2*eps + c3*eps
+// z == nullptr with add_noise: Philox4x32-10 draw (element index, draw number, seed), as in fd_sample's device-noise mode.
+// 4 elements per thread (float4 when the tensors are 16-byte aligned), one pass: 12-16 B read + 4 B written per element.
+// ------------------------------------------------------------------------------------------------
+struct UpdateParams {
+    float coef, div, sigma, c1, c2, c3;
+    int ddim, add_noise;
+    uint32_t draw;
+    uint64_t seed;
+};
+
+__device__ __forceinline__ float reverse_update_one(const UpdateParams& p, float x, float eps, const float* z, size_t e) {
+    if (p.ddim) return __fadd_rn(__fadd_rn(__fmul_rn(p.c1, x), __fmul_rn(p.c2, eps)), __fmul_rn(p.c3, eps));
+    float r = __fdiv_rn(__fsub_rn(x, __fmul_rn(p.coef, eps)), p.div);
+    if (p.add_noise) r = __fadd_rn(r, __fmul_rn(p.sigma, z ? z[e] : philox_normal(e, p.draw, p.seed)));
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_reverse_update(UpdateParams p, float* __restrict__ x, const float* __restrict__ eps,
+                                                        const float* __restrict__ z, float* __restrict__ seq_out, size_t n, int vec) {
+    const size_t i0 = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i0 >= n) return;
+    if (vec && i0 + 4 <= n) {
+        float4 xv = *reinterpret_cast<const float4*>(x + i0);
+        const float4 ev = *reinterpret_cast<const float4*>(eps + i0);
+        xv.x = reverse_update_one(p, xv.x, ev.x, z, i0);
+        xv.y = reverse_update_one(p, xv.y, ev.y, z, i0 + 1);
+        xv.z = reverse_update_one(p, xv.z, ev.z, z, i0 + 2);
+        xv.w = reverse_update_one(p, xv.w, ev.w, z, i0 + 3);
+        *reinterpret_cast<float4*>(x + i0) = xv;
+        if (seq_out) *reinterpret_cast<float4*>(seq_out + i0) = xv;
+        return;
+    }
+    for (size_t e = i0; e < n && e < i0 + 4; ++e) {
+        const float r = reverse_update_one(p, x[e], eps[e], z, e);
+        x[e] = r;
+        if (seq_out) seq_out[e] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // The step after the path: wav / |wav|.max() per utterance (task/FastDiff.py:110) then the int16 encode of
 // utils/audio.py:11-16 (wav *= 32767; astype(int16) = truncation toward zero), so only 2 bytes/sample leave the GPU.
 // Same fp32 operation sequence as the reference (divide, then multiply, both round-to-nearest) -> bit-identical int16.

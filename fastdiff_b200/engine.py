@@ -168,6 +168,24 @@ class Engine:
         self._check(rc, "fd_sample")
         return x
 
+    def reverse_update(self, x: torch.Tensor, eps: torch.Tensor, step: fd_step, z: Optional[torch.Tensor] = None, ddim: bool = False,
+                       seed: int = 0, draw: int = 0, seq: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One reverse-step update in place on ``x`` (util.py:219-229); ``eps`` = the denoiser's output for this step."""
+        assert x.device == self.device and x.dtype == torch.float32 and x.is_contiguous()
+        eps = self._dev(eps, x.shape)
+        zp = None
+        if z is not None:
+            z = self._dev(z, x.shape)
+            zp = z.data_ptr()
+        sp = None
+        if seq is not None:
+            assert seq.device == self.device and seq.dtype == torch.float32 and seq.is_contiguous() and seq.shape == x.shape
+            sp = seq.data_ptr()
+        rc = self.lib.fd_reverse_update(self.h, x.data_ptr(), eps.data_ptr(), zp, C.byref(step), int(ddim), int(seed), int(draw), sp,
+                                        x.numel(), self._stream())
+        self._check(rc, "fd_reverse_update")
+        return x
+
     def wav_int16(self, x: torch.Tensor) -> torch.Tensor:
         """(B,1,L) fp32 waveform -> (B,L) int16: wav/|wav|.max() then *32767 and truncate (task/FastDiff.py:110, utils/audio.py:11-16)."""
         B, L = x.shape[0], x.shape[-1]

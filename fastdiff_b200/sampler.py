@@ -82,6 +82,9 @@ def calc_diffusion_step_embedding(diffusion_steps, diffusion_step_embed_dim_in):
     return torch.cat((torch.sin(_embed), torch.cos(_embed)), 1)
 
 
+calc_noise_scale_embedding = calc_diffusion_step_embedding   # util.py:71-99: the same formula under its DiffWave name (WaveNet.py:6)
+
+
 def build_steps(diffusion_hyperparams, inference_noise_schedule, ddim=False):
     """Host prologue of util.py:180-204 -> (steps_infer list, [fd_step] in execution order n = N-1..0)."""
     _dh = diffusion_hyperparams
@@ -136,6 +139,8 @@ def sampling_given_noise_schedule(net, size, diffusion_hyperparams, inference_no
     print('begin sampling, total number of reverse steps = %s' % N)
 
     dev = next(net.parameters()).device
+    if not hasattr(net, "engine"):
+        return _sample_with_foreign_net(net, size, steps, steps_infer, condition, ddim, return_sequence, dev)
     eng = net.engine(dev)
     B, _, L = size
     if condition is None:
@@ -164,3 +169,41 @@ def sampling_given_noise_schedule(net, size, diffusion_hyperparams, inference_no
     if return_sequence:
         return [seq[i] for i in range(N + 1)]
     return x
+
+
+_update_engines = {}
+
+
+def _update_engine(dev):
+    """A weight-less handle per device for fd_reverse_update (the kernel needs no network)."""
+    from .engine import Engine
+    key = str(dev)
+    if key not in _update_engines:
+        _update_engines[key] = Engine(device=dev)
+    return _update_engines[key]
+
+
+def _sample_with_foreign_net(net, size, steps, steps_infer, condition, ddim, return_sequence, dev):
+    """The loop of util.py:210-234 for any OTHER denoiser with the reference's `net((x, condition, diffusion_steps))` signature --
+    the reference's WaveNet_vocoder (modules/FastDiff/module/WaveNet.py:156) and ParallelWaveGANGenerator_Diffusion
+    (modules/parallel_wavegan/models/parallel_wavegan.py:23) share this sampler.  The network is the caller's torch module and runs
+    as it is; each reverse-step update (the reference's 3-6 eager ops) is one in-place CUDA kernel (fd_reverse_update).  Same RNG
+    stream as the reference: x_T, then one CPU draw after every network call with n > 0."""
+    if dev.type != "cuda" and str(dev) not in _update_engines:   # (the CPU test-suite registers its emulation build of the library here)
+        raise RuntimeError("sampling_given_noise_schedule: the network must live on a CUDA device (there is no CPU path)")
+    eng = _update_engine(dev)
+    N = len(steps)
+    x = torch.normal(0, 1, size=size).to(dev)
+    xs = [x.clone()] if return_sequence else None
+    with torch.no_grad():
+        for i, st in enumerate(steps):                      # execution order n = N-1 .. 0
+            n = N - 1 - i
+            diffusion_steps = (steps_infer[n] * torch.ones((size[0], 1))).to(dev)
+            eps = net((x, condition, diffusion_steps,))
+            if tuple(eps.shape) != tuple(x.shape):
+                raise ValueError(f"the network returned shape {tuple(eps.shape)}, expected {tuple(x.shape)}")
+            z = torch.normal(0, 1, size=size).to(dev) if (st.add_noise and not ddim) else None
+            eng.reverse_update(x, eps, st, z=z, ddim=ddim)
+            if return_sequence:
+                xs.append(x.clone())
+    return xs if return_sequence else x

@@ -127,6 +127,15 @@ int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const fd_step* s
               const float* noise_dev, int n_noise, uint64_t seed, int fill_xT, int ddim,
               float* seq_dev, int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* One reverse-step update by itself, in place on x_dev -- the two update rules of sampling_given_noise_schedule
+ * (modules/FastDiff/module/util.py:219-229) for denoisers other than FastDiff that share the sampler
+ * (modules/FastDiff/module/WaveNet.py:156, modules/parallel_wavegan/models/parallel_wavegan.py:23): the caller evaluates
+ * eps = net((x, c, t)) itself and passes it here.  `step` is one HOST fd_step (see above).  z_dev: the Gaussian draw of this step
+ * (count floats) or NULL -> Philox4x32-10 keyed by (element, draw, seed) when step->add_noise; ignored when ddim.
+ * seq_dev: optional second destination (return_sequence).  x, eps, z, seq: `count` contiguous floats.  Needs no weights. */
+int fd_reverse_update(fd_handle* h, float* x_dev, const float* eps_dev, const float* z_dev, const fd_step* step, int ddim,
+                      uint64_t seed, uint32_t draw, float* seq_dev, size_t count, void* stream);
+
 /* The step before the path: waveform -> log10-mel on the device, the reference's process_utterance
  * (data_gen/tts/data_gen_utils.py:93-147: librosa 0.8.0 stft(1024, hop 256, periodic Hann, zero centre padding), magnitude,
  * librosa.filters.mel(22050, 1024, 80, 80, 7600), log10(max(1e-6, .))).  wav_dev (B, n_samples) fp32 -> mel_dev
