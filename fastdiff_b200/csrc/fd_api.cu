@@ -31,7 +31,8 @@ struct fd_handle {
     int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
     int emu_gemm_tc = 1;         // emulation build, mode tc_3xf16: 1 = the CTA-pair GEMM on the tcgen05 model, 0 = FFMA GEMM + k_emu_kern_to_pieces
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
-    int tc_b0 = 0;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h)
+    int tc_b0 = 0;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h): 1 = the GEMM
+                                 // writes the block's kernels as fp16 pieces (k_kc_gemm_tc2<true, 16, true>), 2 = converter pass (k_b0_panel_to_pieces)
     int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
@@ -424,12 +425,12 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
 }
 
 // The CTA-pair kernel_conv GEMM (k_kc_gemm_tc2<true, 16>: 2-SM TMA, cta_group::2 MMA, multicast commit, remote arrives) on the model.
-static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st) {
+static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st, int b0_pieces) {
     KcgMaps maps;
     const uint64_t rows = (uint64_t)B * (Tm + 2);
     float inv[NBLK];
     for (int n = 0; n < NBLK; ++n) {
-        const float* w16 = sec(h, FD_S_LB0_KCT_F16 + n);
+        const float* w16 = (n == 0 && b0_pieces) ? sec(h, FD_S_LB0_KCT_F16P) : sec(h, FD_S_LB0_KCT_F16 + n);
         emu_make_map_2d(&maps.w_hi[n], w16, KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM);
         emu_make_map_2d(&maps.w_lo[n], w16 + (size_t)KCN * (KCK / 2), KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM);
         emu_make_map_2d(&maps.h_hi[n], hk_hi + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128);
@@ -439,9 +440,15 @@ static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo,
     const int M = B * (Tm + 2) - 2;
     const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
     const int clusters = items < 8 ? items : 8;
-    auto k = k_kc_gemm_tc2<true, 16>;
-    FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
-                       sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+    if (b0_pieces) {
+        auto k = k_kc_gemm_tc2<true, 16, true>;
+        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+    } else {
+        auto k = k_kc_gemm_tc2<true, 16>;
+        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+    }
     FD_CHECK_LAUNCH(h, "k_kc_gemm_tc2");
     return FD_OK;
 }
@@ -594,13 +601,19 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     }
 #ifdef FD_EMU
     const bool simt_gemm = !(h->mode == FD_MODE_TC_3XF16 && h->emu_gemm_tc);
-    if (!simt_gemm) {
-        ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = emu_kc_gemm_tc2(h, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st);
-        if (rc) return rc;
-    }
 #else
     const bool simt_gemm = h->mode == FD_MODE_FP32_SIMT;
+#endif
+    // experimental option tc_b0 (mode tc_3xf16): 1 = the GEMM writes block 0's kernels as fp16 pieces itself, 2 (or a GEMM that cannot)
+    // = they are converted in place before the first block-0 layer
+    const bool b0_tc = h->tc_b0 && h->mode == FD_MODE_TC_3XF16;
+    const bool b0_gemm_pieces = b0_tc && h->tc_b0 == 1 && !simt_gemm;
+#ifdef FD_EMU
+    if (!simt_gemm) {
+        ScopedTimer tm(h, KC_KC_GEMM, st);
+        int rc = emu_kc_gemm_tc2(h, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, b0_gemm_pieces ? 1 : 0);
+        if (rc) return rc;
+    }
 #endif
     if (simt_gemm) {
         KcParams p;
@@ -619,10 +632,11 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     } else {
 #ifndef FD_EMU
         ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches);
+        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0);
         if (rc) return rc;
 #endif
     }
+    if (b0_gemm_pieces) h->b0_converted = 1;
     if (h->stop_after <= 1) return FD_OK;
 
     if (!forked) { int rc = run_dblocks(st); if (rc) return rc; }
@@ -667,8 +681,8 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         }
         const float* skip = (n == 0) ? d1 : (n == 1 ? d0 : x_dev);
         const float* kern_n = kern + (size_t)n * B * Tm * KCN;
-        const bool b0_tc = (n == 0 && h->tc_b0 && h->mode == FD_MODE_TC_3XF16);
-        if (b0_tc) {   // experimental: the GEMM's fp32 panel image of block 0 -> fp16 pieces, in place, all layers
+        const bool b0_here = (n == 0 && b0_tc);
+        if (b0_here && !b0_gemm_pieces) {   // experimental: the GEMM's fp32 panel image of block 0 -> fp16 pieces, in place, all layers
             ScopedTimer tm(h, KC_LVC0, st);
 #ifdef FD_EMU
             FD_LAUNCH(k_b0_panel_to_pieces, dim3(B * Tm * LAYERS), dim3(256), 0, st, kern, B * Tm);
@@ -689,7 +703,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             bool done = false;
             ScopedTimer tm(h, KC_LVC0 + n, st);
 #ifdef FD_EMU
-            if (b0_tc) {
+            if (b0_here) {
                 int rc = emu_lvc_layer_b0(h, i, cur, skip, kl, oth, B, T, Tm, dil, st);
                 if (rc) return rc;
                 done = true;
@@ -699,7 +713,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 done = true;
             }
 #else
-            if (b0_tc) {
+            if (b0_here) {
                 int rc = tc_lvc_layer_b0(h->tc_state, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches);
                 if (rc) return rc;
                 done = true;

@@ -42,6 +42,9 @@
  * fp16-piece operands (mode tc_3xf16; two fp16 values per fp32 blob element, little endian).  w*S = hi + lo with
  * hi = RN_f16(w*S), lo = RN_f16(w*S - hi); S = the per-tensor power of two that puts max|w|*S in (8192, 16384] (SCALES16):
  *   LBn_KCT_F16 [2 planes: hi, lo][24832 n][192 kk] fp16   the LBn_KCT matrix (K-major rows of 384 B: the tcgen05 A operand)
+ *   LB0_KCT_F16P / LB0_KC_BP  block 0's LB0_KCT_F16 / LB0_KC_B with the rows in the SWIZZLE_128B image order of blocks 1 and 2 instead of
+ *             panel order (same values, same scale): the kernel_conv GEMM then writes block 0 as fp16 pieces for the experimental
+ *             tensor-core block-0 LVC kernel (option tc_b0)
  *   LBn_CONV_F16 (n = 0, 1, 2; n = 0 is used by the experimental tensor-core block-0 LVC kernel only) [4 layers][3 k][32 co] rows of 128 B = [32 ci hi | 32 ci lo] fp16, the 16-byte chunk c (8 values) of
  *             row co stored at chunk position c ^ (co & 7): SWIZZLE_128B K-major B-operand tiles of the dilated convs
  *   LBn_KPW_F16 [28 slots][16 KB]  kernel-predictor hidden stack as B-operand tiles in consumption order (tensor-core k_kp_hidden_tc):
@@ -56,7 +59,7 @@
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 11ULL
+#define FD_BLOB_VERSION 12ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */
@@ -75,7 +78,7 @@
     X(DB0_CONVT_HI) X(DB0_CONVT_LO) X(DB0_REST_HI) X(DB0_REST_LO) \
     X(LB1_UPT_HI) X(LB1_UPT_LO) X(LB2_UPT_HI) X(LB2_UPT_LO) \
     X(LB0_KCT_F16) X(LB1_KCT_F16) X(LB2_KCT_F16) X(LB1_CONV_F16) X(LB2_CONV_F16) \
-    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(LB0_CONV_F16) X(SCALES16)
+    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(LB0_CONV_F16) X(LB0_KCT_F16P) X(LB0_KC_BP) X(SCALES16)
 /* FD_SECTIONS_END */
 
 enum fd_section {

@@ -408,7 +408,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 #define KC_STORE_SHFL 0   // 1: adjacent lanes swap one piece and store 32-bit words (one 128-byte line per warp store) instead of two 16-bit stores
 #endif
 // EPW = epilogue warps per CTA (8 or 16: EPW/4 per TMEM lane quarter, each taking 256/(EPW/4) of the 256 frame columns).
-template <bool F16, int EPW>
+// B0P (experimental, option "tc_b0" = 1): block 0's predicted kernels are written as fp16 pieces as well (its weight rows then come
+// in the same SWIZZLE_128B image order as blocks 1 and 2: sections LB0_KCT_F16P / LB0_KC_BP) for the tensor-core block-0 consumer.
+template <bool F16, int EPW, bool B0P = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
               const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass,
@@ -530,7 +532,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             // into the SWIZZLE_128B smem image of the LVC B operand -- per (layer, tap) 64 rows (o) of 128 B = [32 i hi | 32 i lo],
             // 16-byte chunk c at position c ^ (o & 7) -- in the SAME 24,576 bytes the fp32 image occupies.  Lane n holds element
             // (l, k, o, i) and the 32 lanes of a warp the 32 i of one row.  The 64 biases per layer stay fp32.
-            const bool pieces = F16 && blk >= 1 && !(exp_mask & 32);   // exp 32: timing experiment, fp32 full-line stores for every block (WRONG for the LVC consumer)
+            const bool pieces = F16 && (B0P || blk >= 1) && !(exp_mask & 32);   // exp 32: timing experiment, fp32 full-line stores for every block (WRONG for the LVC consumer)
             const int rem = n % KPL;
             const bool is_w = rem < KK * LVC_OUT;          // warp-uniform: 6144 and KPL are multiples of 32
             // two 16-bit stores per value (a warp covers the 64 contiguous bytes of the hi half and of the lo half of one row: full sectors)
@@ -679,6 +681,8 @@ struct TcState {
     uint64_t sec_off[FD_S_COUNT];
     CUtensorMap w_hi[NBLK], w_lo[NBLK];
     CUtensorMap w16_hi[NBLK], w16_lo[NBLK];   // fp16 pieces (LBn_KCT_F16): rows of 96 fp32-sized elements = 192 fp16
+    CUtensorMap w16p_hi, w16p_lo;             // block 0 in image row order (LB0_KCT_F16P; experimental, built on first use)
+    int b0p_ready = 0;
     float scales16[64];                       // host copy of section SCALES16
     int kc_2cta = 1;       // kernel_conv GEMM on CTA pairs (cta_group::2, default); option "kc_2cta" = 0 selects the 1-CTA kernel
     int kc_exp = 0;        // timing experiments only (option "kc_exp"): 1 = epilogue does nothing, 2 = hi*hi MMAs only (WRONG results)
@@ -745,9 +749,17 @@ static inline int tc_init(void** state, int device, const float* blob, const uin
 
 // hk_hi / hk_lo: (3, B, T'+2, 64) each, written by k_kp_hidden.
 static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st,
-                             std::string& err, uint64_t* launches) {
+                             std::string& err, uint64_t* launches, int b0_pieces = 0) {
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    if (b0_pieces && mode == FD_MODE_TC_3XF16 && !s->b0p_ready) {   // experimental path: maps + attribute on first use only
+        const float* w16 = s->blob + s->sec_off[FD_S_LB0_KCT_F16P];
+        if (tc_make_map_2d(s, &s->w16p_hi, w16, KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
+        if (tc_make_map_2d(s, &s->w16p_lo, w16 + (size_t)KCN * (KCK / 2), KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
+        cudaError_t ea = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
+        if (ea != cudaSuccess) { err = std::string("k_kc_gemm_tc2<f16, b0 pieces>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
+        s->b0p_ready = 1;
+    }
     KcgMaps maps;
     const uint64_t rows = (uint64_t)B * (Tm + 2);
     for (int n = 0; n < NBLK; ++n) {
@@ -766,6 +778,11 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
         float inv[NBLK];
         for (int n = 0; n < NBLK; ++n) inv[n] = 1.f / (s->scales16[n] * S16_HK);
+        if (b0_pieces) {
+            maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
+            k_kc_gemm_tc2<true, 16, true><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                                      s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp);
+        } else
         k_kc_gemm_tc2<true, 16><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
                                                                   s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp);
         cudaError_t e2 = cudaGetLastError();

@@ -150,6 +150,7 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         kc = W[f"{kp}.kernel_conv.weight"].reshape(LAYERS, 8, 4, LVC_OUT, KS, HID, 3)  # [l][i8][i4][o][k][c][j]
         kc = kc.permute(6, 5, 0, 4, 3, 1, 2).reshape(3 * HID, LAYERS, KS, LVC_OUT, 8, 4)  # [j*64+c][l][k][o][i8][i4]
         if n == 0:   # block 0 (hop 8) is consumed by the SIMT kernel straight from HBM: panel order [k][i8][o][i4], coalesced per lane
+            kc_img = kc[:, :, :, _SWZ_O, _SWZ_SRC, :].reshape(3 * HID, LAYERS, KK * LVC_OUT)   # image order as well (experimental tc_b0 path)
             kc = kc.permute(0, 1, 2, 4, 3, 5).reshape(3 * HID, LAYERS, KK * LVC_OUT)
         else:
             kc = kc[:, :, :, _SWZ_O, _SWZ_SRC, :].reshape(3 * HID, LAYERS, KK * LVC_OUT)   # position p of row o <- chunk p ^ (o&7)
@@ -158,6 +159,9 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         S[f"LB{n}_KC_W"] = torch.cat([kc, bc], dim=2).reshape(3 * HID, KCN).contiguous()
         kcb = W[f"{kp}.kernel_conv.bias"].reshape(LAYERS, 8, 4, LVC_OUT, KS).permute(0, 4, 3, 1, 2)  # [l][k][o][i8][i4]
         if n == 0:
+            kc0_img = torch.cat([kc_img, bc], dim=2).reshape(3 * HID, KCN).t().contiguous().numpy()    # [24832][192] K-major rows
+            kcb_img = kcb[:, :, _SWZ_O, _SWZ_SRC, :].reshape(LAYERS, KK * LVC_OUT)
+            b0_image_bias = torch.cat([kcb_img, W[f"{kp}.bias_conv.bias"].reshape(LAYERS, LVC_OUT)], dim=1).reshape(KCN).contiguous()
             kcb = kcb.permute(0, 1, 3, 2, 4).reshape(LAYERS, KK * LVC_OUT)
         else:
             kcb = kcb[:, :, _SWZ_O, _SWZ_SRC, :].reshape(LAYERS, KK * LVC_OUT)
@@ -194,6 +198,10 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         scales[n] = sc
         hi, lo = f16_split(kct, sc)
         S[f"LB{n}_KCT_F16"] = _u16_as_f32(np.stack([hi, lo]))
+        if n == 0:   # the same matrix with its rows in image order: same values -> same scale
+            assert f16_scale(kc0_img) == sc
+            hi, lo = f16_split(kc0_img, sc)
+            b0_image_f16 = _u16_as_f32(np.stack([hi, lo]))
     for n in (0, 1, 2):
         cw = torch.stack([W[f"lvc_blocks.{n}.convs.{i}.weight"] for i in range(LAYERS)]).numpy()   # [l][co][ci][k]
         rows = np.zeros((LAYERS, KS, C, 8, 8), dtype=np.uint16)                          # [l][k][co][chunk position][8 fp16]
@@ -241,6 +249,7 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
                 slots[10 + 3 * l + j, 1] = _tile(np.ascontiguousarray(lo[:, :, j]))
         S[f"LB{n}_KPW_F16"] = _u16_as_f32(slots)
     S["LB0_CONV_F16"] = conv16[0]
+    S["LB0_KCT_F16P"], S["LB0_KC_BP"] = b0_image_f16, b0_image_bias
     S["SCALES16"] = torch.from_numpy(scales)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}

@@ -26,13 +26,15 @@ def main():
         eng = net.engine()
         eng.set_option("tc_b0", 0)
         e0 = net((x.to(dev), mel.to(dev), t.to(dev))).cpu()
+        eng.set_option("tc_b0", 2)
+        e2 = net((x.to(dev), mel.to(dev), t.to(dev))).cpu()
         eng.set_option("tc_b0", 1)
         e1 = net((x.to(dev), mel.to(dev), t.to(dev))).cpu()
         eng.set_option("stop_after", 3)
         net((x.to(dev), mel.to(dev), t.to(dev)))
         l0 = eng.debug_read("lvc0", B, Tm).reshape(B, 32, Tm * 8).cpu()
         eng.set_option("stop_after", 99)
-        errs = {"eps_default": (e0 - ref).abs().max().item(), "eps_tc_b0": (e1 - ref).abs().max().item(),
+        errs = {"eps_default": (e0 - ref).abs().max().item(), "eps_tc_b0": (e1 - ref).abs().max().item(), "v1_equals_v2": bool(torch.equal(e1, e2)),
                 "lvc0_tc_b0": (l0 - inter["lvc0"]).abs().max().item()}
         print(B, Tm, errs)
         ok &= errs["eps_tc_b0"] < 5e-5 and errs["lvc0_tc_b0"] < 1e-4
@@ -41,7 +43,7 @@ def main():
     x, mel = x.to(dev), mel.to(dev)
     t = torch.full((B, 1), 74.99228, device=dev)
     eng = net.engine()
-    for opt in (0, 1):
+    for opt in (0, 1, 2):
         eng.set_option("tc_b0", opt)
         for _ in range(3):
             net((x, mel, t))

@@ -153,12 +153,13 @@ def test_emulated_tensor_core_mode_ragged_shapes(synth, emu_lib, B, Tm):
     assert (net((x, mel, t)) - O.denoise(W, x, mel, t)).abs().max() < 5e-5
 
 
-@pytest.mark.parametrize("B,Tm", [(1, 5), (2, 33), (1, 129), (3, 17)])
-def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm):
+@pytest.mark.parametrize("B,Tm,variant", [(1, 5, 1), (2, 33, 1), (1, 129, 1), (3, 17, 2), (2, 33, 2)])
+def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm, variant):
     """Option tc_b0 (experimental, default off): LVC block 0 (hop 8) on the tensor-core model in swapped-operand form --
-    k_b0_panel_to_pieces + k_lvc_layer_b0h (kernels of a frame pair as the M = 128 operand, 16 step columns, 3-slot kernel ring
-    across tiles, second MMA pass for the halo rows, tanh/sigmoid exchange through shared memory).  Block-0 output, the decoded
-    pieces and eps against the oracle, and against the default (SIMT block 0) path."""
+    k_lvc_layer_b0h (kernels of a frame pair as the M = 128 operand, 16 step columns, 3-slot kernel ring across tiles, second MMA
+    pass for the halo rows, tanh/sigmoid exchange through shared memory), fed either by the GEMM writing block 0 as fp16 pieces
+    itself (variant 1: k_kc_gemm_tc2<true, 16, true> on the image-ordered weight rows LB0_KCT_F16P) or by the in-place converter
+    (variant 2: k_b0_panel_to_pieces).  Block-0 output, the decoded pieces and eps against the oracle and the default path."""
     from fastdiff_b200.synthetic import make_inputs
     from oracle import fastdiff_oracle as O
     import torch.nn.functional as F
@@ -170,10 +171,14 @@ def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm):
     ref, inter = O.denoise(W, x, mel, t, return_intermediates=True)
     eng = net.engine()
     eps_default = net((x, mel, t))
-    eng.set_option("tc_b0", 1)
+    eng.set_option("tc_b0", variant)
     eps = net((x, mel, t))
     assert (eps - ref).abs().max() < 5e-5
     assert (eps - eps_default).abs().max() < 5e-5
+    if variant == 1:     # both feeds hold the same pieces: identical bits downstream; so does the FFMA GEMM + converter fallback
+        eng.set_option("tc_b0", 2)
+        assert torch.equal(net((x, mel, t)), eps)
+        eng.set_option("tc_b0", 1)
     noise = F.linear(inter["embed"], W["lvc_blocks.0.fc_t.weight"], W["lvc_blocks.0.fc_t.bias"]).unsqueeze(-1)
     k, bb = O.kernel_predictor(W, "lvc_blocks.0.kernel_predictor", mel + noise)
     assert (eng.debug_read("kernels0", B, Tm).reshape(k.shape) - k).abs().max() < 4e-5      # decoded from the converted pieces
@@ -181,7 +186,7 @@ def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm):
     eng.set_option("stop_after", 3)
     net((x, mel, t))
     assert (eng.debug_read("lvc0", B, Tm).reshape(B, 32, Tm * 8) - inter["lvc0"]).abs().max() < 1e-4
-    eng.set_option("stop_after", 1)                 # the GEMM only: block 0's kernels are still the fp32 panel image
+    eng.set_option("stop_after", 1)                 # the GEMM only (variant 2: block 0's kernels are still the fp32 panel image)
     net((x, mel, t))
     assert (eng.debug_read("kernels0", B, Tm).reshape(k.shape) - k).abs().max() < 4e-5
     eng.set_option("stop_after", 99)

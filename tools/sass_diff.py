@@ -32,10 +32,12 @@ def main():
     print(f"{len(same)} kernels identical, {len(diff)} differ, {len(set(a) - set(b))} removed, {len(set(b) - set(a))} added")
     for k in diff:
         print("  DIFF", k, len(a[k]), "->", len(b[k]), "instructions")
+    gone = sorted(set(a) - set(b))
     for k in sorted(set(b) - set(a)):
-        print("  NEW ", k, len(b[k]), "instructions")
-    for k in sorted(set(a) - set(b)):
-        print("  GONE", k)
+        twin = [g for g in gone if a[g] == b[k]]     # e.g. a template that gained a defaulted parameter: new name, same code
+        print("  NEW ", k, len(b[k]), "instructions" + (f"  == body of removed {twin[0]}" if twin else ""))
+    for k in gone:
+        print("  GONE", k, "(identical body present under a new name)" if any(a[k] == v for v in b.values()) else "")
     return 1 if diff else 0
 
 
