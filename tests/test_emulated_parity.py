@@ -153,7 +153,7 @@ def test_emulated_tensor_core_mode_ragged_shapes(synth, emu_lib, B, Tm):
     assert (net((x, mel, t)) - O.denoise(W, x, mel, t)).abs().max() < 5e-5
 
 
-@pytest.mark.parametrize("B,Tm,variant", [(1, 5, 1), (2, 33, 1), (1, 129, 1), (3, 17, 2), (2, 33, 2)])
+@pytest.mark.parametrize("B,Tm,variant", [(2, 33, 1), (1, 129, 1), (3, 17, 2)])
 def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm, variant):
     """Option tc_b0 (experimental, default off): LVC block 0 (hop 8) on the tensor-core model in swapped-operand form --
     k_lvc_layer_b0h (kernels of a frame pair as the M = 128 operand, 16 step columns, 3-slot kernel ring across tiles, second MMA

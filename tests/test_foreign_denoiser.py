@@ -160,7 +160,7 @@ def test_fused_loop_equals_denoise_plus_reverse_update(synth, emu_lib, ddim):
     net._lib_path = emu_lib
     net.load_state_dict(sd)
     eng = net.engine()
-    B, Tm = 2, 3
+    B, Tm = 2, 2
     x0, mel = make_inputs(B, Tm, 8)
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
     _, steps = build_steps(dh, torch.FloatTensor([3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]), ddim)
