@@ -33,6 +33,8 @@ struct fd_handle {
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
     int tc_b0 = 0;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h): 1 = the GEMM
                                  // writes the block's kernels as fp16 pieces (k_kc_gemm_tc2<true, 16, true>), 2 = converter pass (k_b0_panel_to_pieces)
+    int b2_skipbuf = 0;          // EXPERIMENTAL (mode tc_3xf16, option "b2_skipbuf"): first_conv(audio) is written once per evaluation as rows
+                                 // (over block 0's dead predicted kernels) and LVC block 2 reads it like block 1 reads its skip tensor
     int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
@@ -288,6 +290,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "overlap")) { h->overlap = (int)value; return FD_OK; }
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
+    if (!strcmp(key, "b2_skipbuf")) { h->b2_skipbuf = (int)value; return FD_OK; }
     if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
@@ -407,7 +410,7 @@ static int emu_kp_hidden_tc(fd_handle* h, const float* mel, const float* cnoise,
 }
 
 static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, const float* skip, const float* kern, float* x_out,
-                           int B, int T, int Tm, int dil, cudaStream_t st) {
+                           int B, int T, int Tm, int dil, cudaStream_t st, int b2_skip_rows = 0) {
     LvcHParams hp;
     hp.cw16 = sec(h, blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16) + (size_t)layer * (LH_CW_BYTES / 4);
     hp.conv_b = sec(h, FD_S_LB0_CONV_B + blk * FD_LB_STRIDE) + layer * C;
@@ -415,10 +418,12 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
     hp.first_b = sec(h, FD_S_FIRST_B);
     const float inv_c = 1.f / (S16_ACT * emu_scale16(h, 4 + 4 * blk + layer)), inv_l = 1.f / (S16_ACT * S16_KERN);
     const int tiles = B * ((T + LT_TT - 1) / LT_TT);
-    const int skip_in = (blk == 2 || layer == 0) ? 1 : 0, skip_out = (blk == 1 && layer < LAYERS - 1) ? 1 : 0;
+    const bool rows = blk == 1 || b2_skip_rows;   // the skip comes as (B,T,32) rows: added on the way in by layer 0, on the way out by layers 0..2
+    const int skip_in = (!rows || layer == 0) ? 1 : 0, skip_out = (rows && layer < LAYERS - 1) ? 1 : 0;
     // a small grid on purpose: every group then walks a chunk of several tiles (carried halo rows, kernel reuse, prefetch one tile ahead)
     int grid = (tiles + 5) / 6; if (grid < 1) grid = 1; if (grid > 8) grid = 8;
-    if (blk == 1) { auto k = k_lvc_layer_h<64, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<64, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
+    if (blk == 2 && b2_skip_rows) { auto k = k_lvc_layer_h<256, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<256, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
+    else if (blk == 1) { auto k = k_lvc_layer_h<64, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<64, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
     else          { auto k = k_lvc_layer_h<256, true, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<256, true, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
     FD_CHECK_LAUNCH(h, "k_lvc_layer_h");
     return FD_OK;
@@ -681,6 +686,14 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         }
         const float* skip = (n == 0) ? d1 : (n == 1 ? d0 : x_dev);
         const float* kern_n = kern + (size_t)n * B * Tm * KCN;
+        const bool b2_rows = (n == 2 && h->b2_skipbuf && h->mode == FD_MODE_TC_3XF16);
+        if (b2_rows) {   // experimental: first_conv(audio) as rows, once, over block 0's predicted kernels (dead by now: 8192 of its 24832 floats per frame)
+            ScopedTimer tm(h, KC_LVC2, st);
+            FD_LAUNCH(k_first_conv_rows, dim3((T + 31) / 32, B), dim3(256), 0, st, sec(h, FD_S_FIRST_W), sec(h, FD_S_FIRST_B), x_dev, kern, T);
+            FD_CHECK_LAUNCH(h, "k_first_conv_rows");
+            skip = kern;
+            h->b0_converted = -1;   // "kernels0" / "kbias0" are gone for fd_debug_read
+        }
         const bool b0_here = (n == 0 && b0_tc);
         if (b0_here && !b0_gemm_pieces) {   // experimental: the GEMM's fp32 panel image of block 0 -> fp16 pieces, in place, all layers
             ScopedTimer tm(h, KC_LVC0, st);
@@ -708,7 +721,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 if (rc) return rc;
                 done = true;
             } else if (h->mode == FD_MODE_TC_3XF16 && n >= 1) {
-                int rc = emu_lvc_layer_h(h, n, i, cur, skip, kl, oth, B, T, Tm, dil, st);
+                int rc = emu_lvc_layer_h(h, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, b2_rows ? 1 : 0);
                 if (rc) return rc;
                 done = true;
             }
@@ -718,7 +731,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 if (rc) return rc;
                 done = true;
             } else if (h->mode != FD_MODE_FP32_SIMT) {
-                int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done);
+                int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done, b2_rows ? 1 : 0);
                 if (rc) return rc;
             }
 #endif
@@ -941,11 +954,12 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         return gather(block_out_buffer(ws, B, Tm, n), (int)T, C, C, T * C, 0);
     }
     if ((!strncmp(name, "kernels", 7) || !strncmp(name, "kbias", 5)) && n >= 0) {
+        if (n == 0 && h->b0_converted < 0) return fail(h, FD_ERR_STATE, "fd_debug_read: block 0's kernels were overwritten (option b2_skipbuf)");
         const int want_bias = name[1] == 'b';
         *count = want_bias ? (size_t)B * LAYERS * LVC_OUT * Tm : (size_t)B * LAYERS * C * LVC_OUT * KS * Tm;
         if (!out_dev) return FD_OK;
         FD_LAUNCH(k_kern_to_ref, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, ws + w.kern + (size_t)n * B * Tm * KCN, out_dev, B, Tm, want_bias,
-                  n == 0 ? (h->b0_converted ? 2 : 1) : (h->mode == FD_MODE_TC_3XF16 ? 2 : 0));
+                  n == 0 ? (h->b0_converted > 0 ? 2 : 1) : (h->mode == FD_MODE_TC_3XF16 ? 2 : 0));
         FD_CHECK_LAUNCH(h, "k_kern_to_ref");
         return FD_OK;
     }

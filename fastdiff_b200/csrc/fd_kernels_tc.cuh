@@ -689,6 +689,7 @@ struct TcState {
     int lvc_exp = 0;       // timing experiments only (option "lvc_exp"): 1 = no second conv pass, 2 / 4 = hi*hi only in the LVC / conv (WRONG results)
     int lvc_groups = 2;    // tc_3xf16, block 2: independent 8-warp groups per CTA (2 or 3; option "lvc_groups")
     int b0_attr_set = 0;   // experimental block-0 kernel: attribute set on first use
+    int b2f_attr_set = 0;  // experimental block-2 flavour with skip rows from memory: likewise
     int lvc_swizzle = 0;   // LVC operand tiles: 0 = no-swizzle panels, 1 = SWIZZLE_128B + base_offset, 2 = SWIZZLE_128B, base_offset 0
     bool ok = false;
 };
@@ -2704,11 +2705,33 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
 #ifndef FD_EMU
 static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const float* x_in, const float* skip, const float* kern,
                                float* x_out, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches,
-                               bool* done) {
+                               bool* done, int b2_skip_rows = 0) {
     *done = false;
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (blk == 0) return 0;   // hop 8: stays on the SIMT kernel
+    if (mode == FD_MODE_TC_3XF16 && blk == 2 && b2_skip_rows) {
+        // experimental option "b2_skipbuf": `skip` = first_conv(audio) as (B,T,32) rows; block 2 then runs the block-1 flavour of the
+        // kernel (skip rows bulk-loaded by the first layer, added to the produced rows by layers 0..2)
+        if (!s->b2f_attr_set) {
+            cudaError_t ea = cudaFuncSetAttribute(k_lvc_layer_h<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lh_smem_bytes<256, false, 2>());
+            if (ea != cudaSuccess) { err = std::string("k_lvc_layer_h<256, false, 2>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
+            s->b2f_attr_set = 1;
+        }
+        LvcHParams hp;
+        hp.cw16 = s->blob + s->sec_off[FD_S_LB2_CONV_F16] + (size_t)layer * (LH_CW_BYTES / 4);
+        hp.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + 2 * FD_LB_STRIDE] + layer * C;
+        hp.first_w = nullptr; hp.first_b = nullptr;
+        const float inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * 2 + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
+        const int tiles = B * ((T + LT_TT - 1) / LT_TT), per = (tiles + 1) / 2, grid = per < s->sm_count ? per : s->sm_count;
+        k_lvc_layer_h<256, false, 2><<<grid, 512, lh_smem_bytes<256, false, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp,
+                                                                                  layer == 0 ? 1 : 0, layer < LAYERS - 1 ? 1 : 0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_h<256, false, 2> failed: ") + cudaGetErrorString(e); return -3; }
+        ++*launches;
+        *done = true;
+        return 0;
+    }
     if (mode == FD_MODE_TC_3XF16) {
         LvcHParams hp;
         hp.cw16 = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16] + (size_t)layer * (LH_CW_BYTES / 4);

@@ -1,4 +1,4 @@
-"""Round-2 GPU check of the experimental block-0 tensor-core LVC kernel (option tc_b0; NOT collected by pytest on purpose: the kernel
+"""Round-2 GPU check of the experimental options tc_b0 (block-0 tensor-core LVC kernel) and b2_skipbuf (block 2 with skip rows from memory) ( NOT collected by pytest on purpose: the kernel
 has only run on the CPU model so far -- run this under `timeout`):   timeout 120 python tests/gpu_b0_check.py
 Parity of block 0 / eps against the oracle and the default path at small shapes, then the per-class kernel times at config 2."""
 import json
@@ -55,6 +55,29 @@ def main():
         rep = eng.timing_report()
         eng.timing_enable(False)
         print("tc_b0 =", opt, json.dumps({k: round(v["ms"] / 5, 4) for k, v in rep.items() if v["n"]}))
+    # option b2_skipbuf: LVC block 2 with skip rows from memory -- must give the default's bits; per-class times
+    x2, mel2 = make_inputs(2, 33, 5)
+    t2 = torch.tensor([[7.413235], [498.0537]], device=dev)
+    eng.set_option("tc_b0", 0)
+    eng.set_option("b2_skipbuf", 0)
+    ea = net((x2.to(dev), mel2.to(dev), t2))
+    eng.set_option("b2_skipbuf", 1)
+    eb = net((x2.to(dev), mel2.to(dev), t2))
+    same = bool(torch.equal(ea, eb))
+    print("b2_skipbuf bitwise equal to default:", same)
+    ok &= same
+    for opt in (0, 1):
+        eng.set_option("b2_skipbuf", opt)
+        for _ in range(3):
+            net((x, mel, t))
+        torch.cuda.synchronize()
+        eng.timing_enable(True)
+        for _ in range(5):
+            net((x, mel, t))
+        torch.cuda.synchronize()
+        rep = eng.timing_report()
+        eng.timing_enable(False)
+        print("b2_skipbuf =", opt, json.dumps({k: round(v["ms"] / 5, 4) for k, v in rep.items() if v["n"]}))
     print("PARITY", "OK" if ok else "FAILED")
     return 0 if ok else 1
 

@@ -195,3 +195,30 @@ def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm, variant):
         assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), eps[1:2])
     net.mode = "fp32_simt"                          # the option only applies to mode tc_3xf16
     assert (net((x, mel, t)) - ref).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize("B,Tm", [(2, 9), (1, 33)])
+def test_emulated_block2_skip_rows_option(synth, emu_lib, B, Tm):
+    """Option b2_skipbuf (experimental, default off): first_conv(audio) is written once per evaluation as (B,T,32) rows
+    (k_first_conv_rows, over block 0's dead predicted kernels) and LVC block 2 runs the block-1 flavour of the kernel
+    (k_lvc_layer_h<256, false, 2>: skip rows bulk-loaded by layer 0, added to the produced rows by layers 0..2) instead of
+    recomputing the 7-tap conv over 184 rows x 32 channels in every layer.  Same operation order -> the same bits as the default."""
+    from fastdiff_b200._lib import FdError
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    x, mel = make_inputs(B, Tm, 31)
+    t = torch.tensor([7.413235, 498.0537][:B]).reshape(B, 1)
+    eng = net.engine()
+    eps_default = net((x, mel, t))
+    eng.set_option("b2_skipbuf", 1)
+    eps = net((x, mel, t))
+    assert torch.equal(eps, eps_default)
+    assert (eps - O.denoise(W, x, mel, t)).abs().max() < 5e-5
+    with pytest.raises(FdError, match="overwritten"):          # block 0's kernels made room for the skip rows
+        eng.debug_read("kernels0", B, Tm)
+    eng.debug_read("kernels1", B, Tm)
+    eng.set_option("tc_b0", 1)                                  # together with the tensor-core block 0
+    assert (net((x, mel, t)) - eps).abs().max() < 5e-5
