@@ -1366,6 +1366,9 @@ __device__ __forceinline__ void split4_f16_pre(const float sx, const float sy, c
 #ifndef LH_GATE_ASM
 #define LH_GATE_ASM 1
 #endif
+#ifndef LH_ROW_SPREAD
+#define LH_ROW_SPREAD 0
+#endif
 __device__ __forceinline__ float gate_st(float a, float b) {
     const float bc = fmaxf(b, -15.f);   // E = e^-2b must stay finite (E -> 0 for large b is harmless); tanh(-15) = -1 to fp32 precision
 #if !LH_GATE_ASM
@@ -1437,6 +1440,14 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 64);
 
     const int c4 = gt & 7;   // this thread's channel quad in the A transform
+    // its row within each 32-row block of the A transform.  LH_ROW_SPREAD = 1 (experiment, off: not measured yet) gives a warp the rows
+    // r, r+4, r+8, r+12 instead of 4 consecutive ones: their swizzle XOR then differs in bit 2, so the hi (and lo) 8-byte piece stores of
+    // a warp cover both halves of the 128-byte bank line -- 2 shared-memory wavefronts per STS.64 instead of 4 (ncu: 1.8 M excess per launch)
+#if LH_ROW_SPREAD
+    const int prow = ((gw >> 2) << 4) + (gw & 3) + ((lane >> 3) << 2);
+#else
+    const int prow = gt >> 3;
+#endif
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
     const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * SLOT);
     const uint32_t cw_u = smem_u32(cw);
@@ -1545,7 +1556,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             float4 xv[1536 / GT], sv[1536 / GT];
 #pragma unroll
             for (int i = 0; i < 1536 / GT; ++i) {
-                const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
+                const int ar = r_lo + prow + i * (GT / 8), t = t0 - 28 + ar;
                 xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); sv[i] = xv[i];
                 if (ar < r_hi && t >= 0 && t < T) {
                     xv[i] = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
@@ -1555,7 +1566,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             __syncwarp();   // the 8 lanes of a row sit in one warp: every raw chunk has been read before any row is overwritten
 #pragma unroll
             for (int i = 0; i < 1536 / GT; ++i) {
-                const int ar = r_lo + (gt >> 3) + i * (GT / 8), t = t0 - 28 + ar;
+                const int ar = r_lo + prow + i * (GT / 8), t = t0 - 28 + ar;
                 const bool active = ar < r_hi;
                 float4 pre = xv[i];   // zero outside [0,T)
                 if (skip_in && active && t >= 0 && t < T) {
@@ -1839,6 +1850,8 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
     const uint32_t smem_u = smem_u32(smem);
     constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 16);
     const int c4 = tid & 7;
+    // row within each 64-row block of the A transform: a warp takes rows r, r+4, r+8, r+12 (2 instead of 4 wavefronts per piece store)
+    const int prow = ((gw >> 2) << 4) + (gw & 3) + ((lane >> 3) << 2);
 
     const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt;
     const int r_lo = 27 - dil, r_hi = 157 + dil;
@@ -1895,7 +1908,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
             float4 xv[3], sv[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const int ar = r_lo + (tid >> 3) + i * 64, t = t0 - 28 + ar;
+                const int ar = r_lo + prow + i * 64, t = t0 - 28 + ar;
                 xv[i] = make_float4(0.f, 0.f, 0.f, 0.f); sv[i] = xv[i];
                 if (ar < r_hi && t >= 0 && t < T) {
                     xv[i] = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
@@ -1905,7 +1918,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
-                const int ar = r_lo + (tid >> 3) + i * 64;
+                const int ar = r_lo + prow + i * 64;
                 const float4 pre = make_float4(xv[i].x + sv[i].x, xv[i].y + sv[i].y, xv[i].z + sv[i].z, xv[i].w + sv[i].w);
                 uint2 hi, lo;
                 split4_f16_pre(lrelu02_s(pre.x), lrelu02_s(pre.y), lrelu02_s(pre.z), lrelu02_s(pre.w), hi, lo);

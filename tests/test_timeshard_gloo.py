@@ -10,10 +10,10 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 N4 = [3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]
-B, TM = 2, 45
+TM = 45
 
 
-def _worker(rank, world, port, emu_lib, q, mode):
+def _worker(rank, world, port, emu_lib, q, mode, B):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -37,8 +37,8 @@ def _worker(rank, world, port, emu_lib, q, mode):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["fp32_simt", "tc_3xf16"])
-def test_two_rank_time_shard_matches_unsharded(emu_lib, synth, mode):
+@pytest.mark.parametrize("mode,B", [("fp32_simt", 1), ("tc_3xf16", 2)])
+def test_two_rank_time_shard_matches_unsharded(emu_lib, synth, mode, B):
     import fastdiff_b200 as fb
     from fastdiff_b200.engine import Engine
     from fastdiff_b200.sampler import build_steps
@@ -47,7 +47,7 @@ def test_two_rank_time_shard_matches_unsharded(emu_lib, synth, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 31500 + os.getpid() % 2000 + (7 if mode == "tc_3xf16" else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, emu_lib, q, mode)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, emu_lib, q, mode, B)) for r in range(2)]
     for p in procs:
         p.start()
     import queue
