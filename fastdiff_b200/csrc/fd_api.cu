@@ -33,6 +33,7 @@ struct fd_handle {
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
     int tc_b0 = 0;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h): 1 = the GEMM
                                  // writes the block's kernels as fp16 pieces (k_kc_gemm_tc2<true, 16, true>), 2 = converter pass (k_b0_panel_to_pieces)
+    int kc_stage = 0;            // EXPERIMENTAL (mode tc_3xf16, option "kc_stage"): kernel_conv GEMM epilogue through shared memory + bulk stores
     int b2_skipbuf = 0;          // EXPERIMENTAL (mode tc_3xf16, option "b2_skipbuf"): first_conv(audio) is written once per evaluation as rows
                                  // (over block 0's dead predicted kernels) and LVC block 2 reads it like block 1 reads its skip tensor
     int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
@@ -291,6 +292,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "b2_skipbuf")) { h->b2_skipbuf = (int)value; return FD_OK; }
+    if (!strcmp(key, "kc_stage")) { h->kc_stage = (int)value; return FD_OK; }
     if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
@@ -431,6 +433,7 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
 
 // The CTA-pair kernel_conv GEMM (k_kc_gemm_tc2<true, 16>: 2-SM TMA, cta_group::2 MMA, multicast commit, remote arrives) on the model.
 static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st, int b0_pieces) {
+    const int stage = h->kc_stage;
     KcgMaps maps;
     const uint64_t rows = (uint64_t)B * (Tm + 2);
     float inv[NBLK];
@@ -445,7 +448,15 @@ static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo,
     const int M = B * (Tm + 2) - 2;
     const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
     const int clusters = items < 8 ? items : 8;
-    if (b0_pieces) {
+    if (stage && b0_pieces) {
+        auto k = k_kc_gemm_tc2<true, 16, true, true>;
+        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES + KC2_STG_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+    } else if (stage) {
+        auto k = k_kc_gemm_tc2<true, 16, false, true>;
+        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES + KC2_STG_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+    } else if (b0_pieces) {
         auto k = k_kc_gemm_tc2<true, 16, true>;
         FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
                            sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
@@ -637,7 +648,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     } else {
 #ifndef FD_EMU
         ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0);
+        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0, h->kc_stage);
         if (rc) return rc;
 #endif
     }

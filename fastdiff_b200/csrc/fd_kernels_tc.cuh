@@ -172,6 +172,27 @@ __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t base, uint32_t ncols) 
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(ncols) : "memory");
 }
 // one float -> fp16 bits, round to nearest even, saturating at +-65504
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// shared -> global bulk copy tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources may be overwritten
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }          // writes complete
 __device__ __forceinline__ uint16_t f16_sat_bits(float f) { uint16_t h; asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(f)); return h; }
 // opaque to the optimiser: keeps ptxas from hoisting ~100 descriptors out of a tile loop
 #define FD_OPAQUE(x) asm volatile("" : "+r"(x))
@@ -410,7 +431,15 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 // EPW = epilogue warps per CTA (8 or 16: EPW/4 per TMEM lane quarter, each taking 256/(EPW/4) of the 256 frame columns).
 // B0P (experimental, option "tc_b0" = 1): block 0's predicted kernels are written as fp16 pieces as well (its weight rows then come
 // in the same SWIZZLE_128B image order as blocks 1 and 2: sections LB0_KCT_F16P / LB0_KC_BP) for the tensor-core block-0 consumer.
-template <bool F16, int EPW, bool B0P = false>
+// STG (experimental, option "kc_stage"): the epilogue stages its rows in shared memory and writes them with cp.async.bulk: the 4 warps
+// of a column group (lane quarters 0..3 = 4 consecutive 128-byte rows of the record = the CTA's 512 contiguous bytes per frame) fill
+// a [8 frames][512 B] buffer, one named barrier, then 8 lanes of one warp issue one 512-byte shared->global bulk copy each (frames
+// outside the utterances are simply skipped).  Two buffers per group: the copies of chunk i read one while chunk i+1 fills the other;
+// the issuing warp waits for the previous chunk's smem reads (wait_group.read) BEFORE the barrier, so after it every warp may refill.
+// Motivation: the 2-byte LSU stores run into the global-store queue limit (lg_throttle) and keep the whole
+// kernel at store speed; bulk copies take them off the LSU path in 512-byte requests.
+constexpr int KC2_STG_BYTES = 4 * 2 * 8 * 512;   // 4 column groups x 2 buffers x 8 frames x 512 B = 32 KB
+template <bool F16, int EPW, bool B0P = false, bool STG = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
               const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass,
@@ -571,6 +600,52 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
 #endif
 #endif
             };
+            if constexpr (STG) {
+                static_assert(EPW == 16, "staged epilogue: 4 warps per 64-column group");
+                unsigned char* stg = smem + KC2_STAGES * KC2_STAGE_BYTES + 256 + cpart * 8192;
+                const bool issuer = (q == 0);               // warp-uniform
+                int off_a = q * 128 + lane * 4, off_b = 0;   // fp32 row: word n | piece row: hi / lo halfword of element i = lane
+                if (pieces && is_w) {
+                    const int oo = (rem >> 5) & 63, ci = ((((lane >> 2) & 7) ^ (oo & 7)) << 2) + (lane & 3);
+                    off_a = q * 128 + 2 * ((((ci >> 3) ^ (oo & 7)) << 3) + (ci & 7));
+                    off_b = q * 128 + 2 * ((((4 + (ci >> 3)) ^ (oo & 7)) << 3) + (ci & 7));
+                }
+                const int p0 = ft * 256 + cpart * CPW;
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * CPW;
+#pragma unroll 1
+                for (int ch = 0; ch < CPW / 8; ++ch) {
+                    unsigned char* buf = stg + (ch & 1) * 4096;
+                    uint32_t v[8];
+                    tmem_ld_32x32b_x8(taddr + ch * 8, v);
+                    tmem_ld_wait();
+                    if (as_pieces) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float sv = fmaf(__uint_as_float(v[j]), inv_s, bv_s);
+                            const uint16_t h16 = f16_sat_bits(sv);
+                            *reinterpret_cast<uint16_t*>(buf + j * 512 + off_a) = h16;
+                            *reinterpret_cast<uint16_t*>(buf + j * 512 + off_b) = f16_sat_bits(sv - f16_bits_to_float(h16));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float*>(buf + j * 512 + off_a) = F16 ? fmaf(__uint_as_float(v[j]), inv, bv) : __uint_as_float(v[j]) + bv;
+                    }
+                    fence_async_smem();
+                    if (issuer) bulk_wait_read0();           // the previous chunk's copies are done with the other buffer
+                    group_sync(1 + cpart, 128);
+                    if (issuer) {
+                        if (lane < 8) {
+                            const int pc = p0 + ch * 8 + lane, center = pc + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
+                            if (pc < M && fp >= 1 && fp <= Tm)
+                                bulk_s2g(kern + ((size_t)bb * Tm + (fp - 1)) * KCN + nt * 128, buf + lane * 512, 512);
+                        }
+                        bulk_commit();
+                    }
+                }
+            } else {
             int p = ft * 256 + cpart * CPW;
             int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
             const bool fast = __shfl_sync(0xffffffffu, (int)((fp >= 1) && (fp + CPW - 1 <= Tm) && (p + CPW - 1 < M)), 0) != 0;
@@ -652,11 +727,13 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     }
                 }
             }
+            }   // !STG
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if constexpr (STG) bulk_wait_all();   // (threads without copies return at once) the staging buffers stay valid until read
     }
     tc_fence_before();
     cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still touch its smem / barriers
@@ -683,6 +760,7 @@ struct TcState {
     CUtensorMap w16_hi[NBLK], w16_lo[NBLK];   // fp16 pieces (LBn_KCT_F16): rows of 96 fp32-sized elements = 192 fp16
     CUtensorMap w16p_hi, w16p_lo;             // block 0 in image row order (LB0_KCT_F16P; experimental, built on first use)
     int b0p_ready = 0;
+    int stg_ready[2] = {0, 0};                // staged-epilogue instantiations (option "kc_stage"): attribute set on first use
     float scales16[64];                       // host copy of section SCALES16
     int kc_2cta = 1;       // kernel_conv GEMM on CTA pairs (cta_group::2, default); option "kc_2cta" = 0 selects the 1-CTA kernel
     int kc_exp = 0;        // timing experiments only (option "kc_exp"): 1 = epilogue does nothing, 2 = hi*hi MMAs only (WRONG results)
@@ -750,7 +828,7 @@ static inline int tc_init(void** state, int device, const float* blob, const uin
 
 // hk_hi / hk_lo: (3, B, T'+2, 64) each, written by k_kp_hidden.
 static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st,
-                             std::string& err, uint64_t* launches, int b0_pieces = 0) {
+                             std::string& err, uint64_t* launches, int b0_pieces = 0, int stage = 0) {
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (b0_pieces && mode == FD_MODE_TC_3XF16 && !s->b0p_ready) {   // experimental path: maps + attribute on first use only
@@ -779,6 +857,23 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
         float inv[NBLK];
         for (int n = 0; n < NBLK; ++n) inv[n] = 1.f / (s->scales16[n] * S16_HK);
+        if (stage) {   // experimental staged epilogue (bulk shared->global stores)
+            const int smem_bytes = KC2_SMEM_BYTES + KC2_STG_BYTES;
+            if (!s->stg_ready[b0_pieces ? 1 : 0]) {
+                cudaError_t ea = b0_pieces ? cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                                           : cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+                if (ea != cudaSuccess) { err = std::string("k_kc_gemm_tc2<staged>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
+                s->stg_ready[b0_pieces ? 1 : 0] = 1;
+            }
+            if (b0_pieces) {
+                maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
+                k_kc_gemm_tc2<true, 16, true, true><<<2 * clusters, 64 + 32 * 16, smem_bytes, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                                            s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+            } else {
+                k_kc_gemm_tc2<true, 16, false, true><<<2 * clusters, 64 + 32 * 16, smem_bytes, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                                             s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+            }
+        } else
         if (b0_pieces) {
             maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
             k_kc_gemm_tc2<true, 16, true><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
@@ -859,20 +954,6 @@ constexpr int lt_smem_bytes() { return GROUPS * (lt_slot_bytes<HOP>() + lt_small
 
 __device__ __forceinline__ uint32_t swz128(int row, int c) { return (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4)); }
 #ifndef FD_EMU
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void group_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");

@@ -48,6 +48,12 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { memcpy(smem_dst, gsrc, bytes); emu_mbar_complete_tx(bar, bytes); }
 inline void bulk_prefetch_l2(const void*, uint32_t) {}
+// shared -> global bulk copy (bulk async-groups): copied at issue, so commit / wait have nothing left to do.  Source-reuse hazards
+// (overwriting a staging buffer before wait_group.read) are therefore NOT detected by the model.
+inline void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) { memcpy(gdst, smem_src, bytes); }
+inline void bulk_commit() {}
+inline void bulk_wait_read0() {}
+inline void bulk_wait_all() {}
 inline bool elect_one() { return (emu::t_linear_tid & 31) == 0; }
 inline void tc_fence_before() {}
 inline void tc_fence_after() {}

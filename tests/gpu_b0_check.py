@@ -78,6 +78,26 @@ def main():
         rep = eng.timing_report()
         eng.timing_enable(False)
         print("b2_skipbuf =", opt, json.dumps({k: round(v["ms"] / 5, 4) for k, v in rep.items() if v["n"]}))
+    # option kc_stage: GEMM epilogue through shared memory + bulk stores -- the default's bits; kc_gemm class time
+    eng.set_option("b2_skipbuf", 0)
+    eng.set_option("kc_stage", 1)
+    ec = net((x2.to(dev), mel2.to(dev), t2))
+    same = bool(torch.equal(ea, ec))
+    print("kc_stage bitwise equal to default:", same)
+    ok &= same
+    for opt in (0, 1):
+        eng.set_option("kc_stage", opt)
+        for _ in range(3):
+            net((x, mel, t))
+        torch.cuda.synchronize()
+        eng.timing_enable(True)
+        for _ in range(5):
+            net((x, mel, t))
+        torch.cuda.synchronize()
+        rep = eng.timing_report()
+        eng.timing_enable(False)
+        print("kc_stage =", opt, json.dumps({k: round(v["ms"] / 5, 4) for k, v in rep.items() if v["n"]}))
+    eng.set_option("kc_stage", 0)
     print("PARITY", "OK" if ok else "FAILED")
     return 0 if ok else 1
 

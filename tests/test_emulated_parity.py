@@ -222,3 +222,30 @@ def test_emulated_block2_skip_rows_option(synth, emu_lib, B, Tm):
     eng.debug_read("kernels1", B, Tm)
     eng.set_option("tc_b0", 1)                                  # together with the tensor-core block 0
     assert (net((x, mel, t)) - eps).abs().max() < 5e-5
+
+
+@pytest.mark.parametrize("B,Tm", [(2, 33), (2, 129)])
+def test_emulated_gemm_staged_epilogue_option(synth, emu_lib, B, Tm):
+    """Option kc_stage (experimental, default off): the kernel_conv GEMM stages its output rows in shared memory ([8 frames][512 B] per
+    column group, two buffers) and writes them with 512-byte cp.async.bulk shared->global copies instead of 2-byte LSU stores --
+    k_kc_gemm_tc2<true, 16, *, true>.  Same values, same addresses: predicted kernels (pieces and fp32 rows), biases and eps are
+    bit-identical to the default epilogue, alone and combined with tc_b0 (block 0 as pieces).  (2,129): two frame tiles, the pad
+    columns between the two utterances fall inside a chunk and are skipped.)"""
+    from fastdiff_b200.synthetic import make_inputs
+    sd, _ = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    x, mel = make_inputs(B, Tm, 41)
+    t = torch.tensor([7.413235, 498.0537]).reshape(B, 1)
+    eng = net.engine()
+    eps0 = net((x, mel, t))
+    k0 = [eng.debug_read(f"{nm}{n}", B, Tm).clone() for n in range(3) for nm in ("kernels", "kbias")]
+    eng.set_option("kc_stage", 1)
+    eps1 = net((x, mel, t))
+    k1 = [eng.debug_read(f"{nm}{n}", B, Tm) for n in range(3) for nm in ("kernels", "kbias")]
+    assert torch.equal(eps0, eps1)
+    assert all(torch.equal(a, b) for a, b in zip(k0, k1))
+    eng.set_option("tc_b0", 1)
+    eps2 = net((x, mel, t))
+    eng.set_option("kc_stage", 0)
+    assert torch.equal(net((x, mel, t)), eps2)
