@@ -1,5 +1,5 @@
 """Round-2 GPU check of the experimental options tc_b0 (block-0 tensor-core LVC kernel) and b2_skipbuf (block 2 with skip rows from memory) ( NOT collected by pytest on purpose: the kernel
-has only run on the CPU model so far -- run this under `timeout`):   timeout 120 python tests/gpu_b0_check.py
+has only run on the CPU model so far -- run this under `timeout`):   timeout 120 python tests/gpu_options_check.py
 Parity of block 0 / eps against the oracle and the default path at small shapes, then the per-class kernel times at config 2."""
 import json
 import sys
