@@ -964,6 +964,21 @@ template <int N> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, ui
 template <> __device__ __forceinline__ void tmem_ld_cols<8>(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld_32x32b_x8(taddr, v); }
 template <> __device__ __forceinline__ void tmem_ld_cols<16>(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld_32x32b_x16(taddr, v); }
 template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tmem_ld_32x32b_x32(taddr, v); }
+// 8 consecutive floats (32-byte aligned) to global memory.  FD_VEC256 = 1 (experiment, off: not measured yet) uses the 256-bit store of
+// sm_100 (STG.E.ENL2.256): the epilogues below write rows with one lane per row, so a 16-byte store fills half a 32-byte sector per
+// lane and a warp store touches 32 half-sectors; the 256-bit form writes whole sectors with half the store instructions.
+#ifndef FD_VEC256
+#define FD_VEC256 0
+#endif
+__device__ __forceinline__ void st_global_f8(float* p, const float4 a, const float4 b) {
+#if FD_VEC256 && !defined(FD_EMU)
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+#else
+    *reinterpret_cast<float4*>(p) = a;
+    *reinterpret_cast<float4*>(p + 4) = b;
+#endif
+}
 // tf32 pieces by Veltkamp splitting (3 FP ops): hi = x rounded to nearest at 11 significant bits (low 13 mantissa bits
 // zero -> exactly a tf32), lo = x - hi exactly.  lo is handed to the tensor core as is (its own tf32 conversion of lo costs
 // <= 2^-11 |lo| <= 2^-22 |x|).  `cvt.rna.tf32.f32` is emulated with ~8 integer instructions on sm_100a (ncu: it was the
@@ -1848,6 +1863,9 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             tmem_ld_wait();
             if (t < T) {
                 const float* lb = lbias + fi * 64 + part * 16;
+#if FD_VEC256
+                float4 o_prev = make_float4(0.f, 0.f, 0.f, 0.f);
+#endif
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float4 o4;
@@ -1858,7 +1876,11 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                     if (skip_out) {   // the next layer's "x += audio_down": (x + gate) + skip, the reference's rounding sequence
                         o4.x = __fadd_rn(o4.x, so[c].x); o4.y = __fadd_rn(o4.y, so[c].y); o4.z = __fadd_rn(o4.z, so[c].z); o4.w = __fadd_rn(o4.w, so[c].w);
                     }
+#if FD_VEC256
+                    if (c & 1) st_global_f8(x_out + row + (c - 1) * 4, o_prev, o4); else o_prev = o4;
+#else
                     *reinterpret_cast<float4*>(x_out + row + c * 4) = o4;
+#endif
                 }
             }
         }
@@ -2779,8 +2801,12 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
                 if (m < Tin) {
                     float4 o0 = make_float4(__uint_as_float(v[0]) + bb[0], __uint_as_float(v[1]) + bb[1], __uint_as_float(v[2]) + bb[2], __uint_as_float(v[3]) + bb[3]);
                     float4 o1 = make_float4(__uint_as_float(v[4]) + bb[4], __uint_as_float(v[5]) + bb[5], __uint_as_float(v[6]) + bb[6], __uint_as_float(v[7]) + bb[7]);
+#if FD_VEC256
+                    st_global_f8(dst + ph * C, o0, o1);
+#else
                     *reinterpret_cast<float4*>(dst + ph * C) = o0;
                     *reinterpret_cast<float4*>(dst + ph * C + 4) = o1;
+#endif
                 }
             }
         }
