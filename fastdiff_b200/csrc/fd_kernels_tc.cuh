@@ -2653,8 +2653,12 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
                     o1v.x = __uint_as_float(v[4]) + bias[4] + rb[4]; o1v.y = __uint_as_float(v[5]) + bias[5] + rb[5];
                     o1v.z = __uint_as_float(v[6]) + bias[6] + rb[6]; o1v.w = __uint_as_float(v[7]) + bias[7] + rb[7];
                     float* dstg = out + ((size_t)b * To + o) * C + part * 8;
+#if FD_VEC256
+                    st_global_f8(dstg, o0v, o1v);
+#else
                     *reinterpret_cast<float4*>(dstg) = o0v;
                     *reinterpret_cast<float4*>(dstg + 4) = o1v;
+#endif
                 }
             }
             fence_async_smem();
