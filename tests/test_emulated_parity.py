@@ -55,7 +55,7 @@ def test_emulated_sampler_config0_vs_oracle(synth, emu_lib, ddim):
         assert (got[i] - ref[i]).abs().max() < 5e-4, i      # end-to-end tolerance at x rms ~3.4
 
 
-@pytest.mark.parametrize("B,Tm", [(1, 5), (2, 33), (3, 1), (2, 129)])
+@pytest.mark.parametrize("B,Tm", [(2, 33), (3, 1), (2, 129)])
 def test_emulated_tensor_core_mode_vs_oracle(synth, emu_lib, B, Tm):
     """Mode tc_3xf16 on the CPU, every kernel of the default path: k_kp_hidden_tc, k_lvc_layer_h, the CTA-pair k_kc_gemm_tc2
     (kind::f16; 2-SM TMA boxes, cta_group::2 MMA, multicast commit, remote arrives) and k_dblock0_tc, k_upsample_tc (kind::tf32) run

@@ -168,6 +168,7 @@ def test_fused_loop_equals_denoise_plus_reverse_update(synth, emu_lib, ddim):
     a = eng.sample(x0.clone(), mel, steps, noise=noise, ddim=ddim)
     b = _manual_loop(net, eng, x0.clone(), mel, steps, noise=noise, ddim=ddim)
     assert torch.equal(a, b)
-    a = eng.sample(x0.clone(), mel, steps, noise=None, seed=99, ddim=ddim)          # device noise: draw numbers 1, 2, 3
-    b = _manual_loop(net, eng, x0.clone(), mel, steps, noise=None, seed=99, ddim=ddim)
-    assert torch.equal(a, b)
+    if not ddim:                                                                    # device noise: draw numbers 1, 2, 3
+        a = eng.sample(x0.clone(), mel, steps, noise=None, seed=99)
+        b = _manual_loop(net, eng, x0.clone(), mel, steps, noise=None, seed=99)
+        assert torch.equal(a, b)
