@@ -1465,6 +1465,9 @@ __device__ __forceinline__ void split4_f16_pre(const float sx, const float sy, c
 #ifndef LH_ROW_SPREAD
 #define LH_ROW_SPREAD 0
 #endif
+#ifndef LH_PREFETCH_EPI
+#define LH_PREFETCH_EPI 0
+#endif
 __device__ __forceinline__ float gate_st(float a, float b) {
     const float bc = fmaxf(b, -15.f);   // E = e^-2b must stay finite (E -> 0 for large b is harmless); tanh(-15) = -1 to fp32 precision
 #if !LH_GATE_ASM
@@ -1572,6 +1575,11 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             if (!SKIP_FIRST && skip_in) bulk_g2s(s_t + ar0 * 128, skip + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
         }
         if (SKIP_FIRST && i1 > i0) bulk_g2s(au + i0, skip + (size_t)b * T + (t0 - 32 + i0), (uint32_t)(i1 - i0) * 4u, &bar[2]);
+#if LH_PREFETCH_EPI
+        // experiment (off: not measured yet): the gate epilogue of a skip_out layer reads the tile's 128 skip rows from global memory and
+        // stalls on them (block 1, ncu: 25 % of the stall samples sit on the first use of those loads) -- pull them into L2 one tile ahead
+        if (!SKIP_FIRST && skip_out && t0 < T) bulk_prefetch_l2(skip + ((size_t)b * T + t0) * C, (uint32_t)min(LT_TT, T - t0) * 128u);
+#endif
 #pragma unroll
         for (int fi = 0; fi < NF; ++fi) {
             const int f = t0 / HOP + fi;
