@@ -397,6 +397,7 @@ def run_ours(args):
                    "arith_mode": mode_name, "noise": "on-device Philox4x32-10 (inside the timed region)",
                    "l2": "inputs+activations per call (>=450 MB) exceed the 126 MB L2; no explicit flush"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        **({"experiment": {"options": args.opt, "nvcc_extra": os.environ.get("FD_NVCC_EXTRA", "")}} if (args.opt or os.environ.get("FD_NVCC_EXTRA")) else {}),
         "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in per_kernel.items()},
         "kernel_ms_note": "CUDA events around every launch on its own stream; the DBlock chain runs on a side stream concurrently with embed / "
                           "kernel predictor / GEMM, so those classes include time spent sharing the SMs and the classes sum to more than ms_per_step",
