@@ -1468,6 +1468,9 @@ __device__ __forceinline__ void split4_f16_pre(const float sx, const float sy, c
 #ifndef LH_PREFETCH_EPI
 #define LH_PREFETCH_EPI 0
 #endif
+#ifndef LH_NO_END_SYNC
+#define LH_NO_END_SYNC 0
+#endif
 __device__ __forceinline__ float gate_st(float a, float b) {
     const float bc = fmaxf(b, -15.f);   // E = e^-2b must stay finite (E -> 0 for large b is harmless); tanh(-15) = -1 to fp32 precision
 #if !LH_GATE_ASM
@@ -1893,7 +1896,15 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             }
         }
         tc_fence_before();
+#if LH_NO_END_SYNC
+        // experiment (off: not measured yet; block 1 spends 10 % of its stall samples here): without xs rows in shared memory (!SKIP_FIRST)
+        // nothing the gate epilogue touches is written before the next group barrier -- the next tile's phase 1 works on the A / skip tiles
+        // (loaded after this tile's LVC MMAs completed), the lbias buffers alternate, and every later MMA issue sits behind a barrier
+        // that a warp reaches only after it has finished its TMEM reads here
+        if (SKIP_FIRST) group_sync(1 + g, GT);
+#else
         group_sync(1 + g, GT);   // the group's TMEM columns and xs rows are free for its next tile
+#endif
         if (--tt < 0) { tt = ntt - 1; --b; }
     }
     tc_fence_before();

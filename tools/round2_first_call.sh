@@ -19,7 +19,7 @@ for o in tc_b0=1 tc_b0=2 b2_skipbuf=1 kc_stage=1; do
 done
 timeout 120 $B --opt tc_b0=1 --opt b2_skipbuf=1 --opt kc_stage=1 > "$OUT/bench_all_options.json" 2> "$OUT/bench_all_options.err"
 
-for d in LH_ROW_SPREAD FINAL_BATCH_LOADS FD_VEC256 LH_PREFETCH_EPI; do
+for d in LH_ROW_SPREAD FINAL_BATCH_LOADS FD_VEC256 LH_PREFETCH_EPI LH_NO_END_SYNC; do
     FD_NVCC_EXTRA="-D$d=1" python -c "import __graft_entry__ as g; g.build_cuda(force=True)" > "$OUT/build_$d.log" 2>&1 || continue
     timeout 120 $B > "$OUT/bench_$d.json" 2> "$OUT/bench_$d.err"; echo "$d rc=$?" >> "$OUT/bench_rc.log"
     timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tensor_core_mode_vs_oracle or full_size" > "$OUT/parity_$d.log" 2>&1
