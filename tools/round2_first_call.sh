@@ -11,7 +11,9 @@ mkdir -p "$OUT"
 B="python bench.py --steps 10 --warmup 3 --no-cpu"
 
 timeout 600 python -m pytest tests -m gpu -x -q > "$OUT/gpu_tests.log" 2>&1; echo "pytest rc=$?" >> "$OUT/gpu_tests.log"
-timeout 300 python tests/gpu_options_check.py > "$OUT/options_check.log" 2>&1; echo "rc=$?" >> "$OUT/options_check.log"
+for o in tc_b0 b2_skipbuf kc_stage; do
+    timeout 150 python tests/gpu_options_check.py $o > "$OUT/options_check_$o.log" 2>&1; echo "rc=$?" >> "$OUT/options_check_$o.log"
+done
 
 timeout 120 $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
 for o in tc_b0=1 tc_b0=2 b2_skipbuf=1 kc_stage=1; do
