@@ -33,6 +33,7 @@ struct fd_handle {
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
     int tc_b0 = 0;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h): 1 = the GEMM
                                  // writes the block's kernels as fp16 pieces (k_kc_gemm_tc2<true, 16, true>), 2 = converter pass (k_b0_panel_to_pieces)
+    int lvc_pipe = 0;            // EXPERIMENTAL (mode tc_3xf16, option "lvc_pipe"): LVC block 2 with software-pipelined tiles (k_lvc_layer_p)
     int kc_stage = 0;            // EXPERIMENTAL (mode tc_3xf16, option "kc_stage"): kernel_conv GEMM epilogue through shared memory + bulk stores
     int b2_skipbuf = 0;          // EXPERIMENTAL (mode tc_3xf16, option "b2_skipbuf"): first_conv(audio) is written once per evaluation as rows
                                  // (over block 0's dead predicted kernels) and LVC block 2 reads it like block 1 reads its skip tensor
@@ -293,6 +294,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "b2_skipbuf")) { h->b2_skipbuf = (int)value; return FD_OK; }
     if (!strcmp(key, "kc_stage")) { h->kc_stage = (int)value; return FD_OK; }
+    if (!strcmp(key, "lvc_pipe")) { h->lvc_pipe = (int)value; return FD_OK; }
     if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
@@ -424,6 +426,11 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
     const int skip_in = (!rows || layer == 0) ? 1 : 0, skip_out = (rows && layer < LAYERS - 1) ? 1 : 0;
     // a small grid on purpose: every group then walks a chunk of several tiles (carried halo rows, kernel reuse, prefetch one tile ahead)
     int grid = (tiles + 5) / 6; if (grid < 1) grid = 1; if (grid > 8) grid = 8;
+    if (blk == 2 && h->lvc_pipe && !b2_skip_rows) {
+        FD_LAUNCH(k_lvc_layer_p, dim3(grid), dim3(512), LP_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l);
+        FD_CHECK_LAUNCH(h, "k_lvc_layer_p");
+        return FD_OK;
+    }
     if (blk == 2 && b2_skip_rows) { auto k = k_lvc_layer_h<256, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<256, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
     else if (blk == 1) { auto k = k_lvc_layer_h<64, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<64, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
     else          { auto k = k_lvc_layer_h<256, true, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<256, true, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
@@ -742,7 +749,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 if (rc) return rc;
                 done = true;
             } else if (h->mode != FD_MODE_FP32_SIMT) {
-                int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done, b2_rows ? 1 : 0);
+                int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done, b2_rows ? 1 : 0, h->lvc_pipe);
                 if (rc) return rc;
             }
 #endif

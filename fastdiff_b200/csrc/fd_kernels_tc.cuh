@@ -768,6 +768,7 @@ struct TcState {
     int lvc_groups = 2;    // tc_3xf16, block 2: independent 8-warp groups per CTA (2 or 3; option "lvc_groups")
     int b0_attr_set = 0;   // experimental block-0 kernel: attribute set on first use
     int b2f_attr_set = 0;  // experimental block-2 flavour with skip rows from memory: likewise
+    int b2p_attr_set = 0;  // experimental pipelined block-2 kernel: likewise
     int lvc_swizzle = 0;   // LVC operand tiles: 0 = no-swizzle panels, 1 = SWIZZLE_128B + base_offset, 2 = SWIZZLE_128B, base_offset 0
     bool ok = false;
 };
@@ -1916,6 +1917,327 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (option "lvc_pipe", default off; written against the round-1 ncu capture, validated on the CPU model only): LVC block 2
+// (hop 256, skip = first_conv(audio) recomputed on the way in) with the phases of consecutive tiles of a group SOFTWARE-PIPELINED, so
+// that a group's own SIMT work runs while its MMAs are in flight instead of the group sleeping on the mbarrier (18 % of the stall
+// samples of k_lvc_layer_h<256, true, 2> are those two waits, 8 % the end-of-tile barrier):
+//     iteration i:   P1(i) rows -> pieces   | issue conv MMAs(i) | P5(i-1) gate epilogue   | P3(i) conv -> Y pieces | issue LVC MMAs(i)
+//                    [LVC MMAs(i-1) running]                      [conv MMAs(i) running]                              (run during P1(i+1))
+// Everything a tile owns is double-buffered per group -- A/Y tile, xs rows, TMEM column set, lbias -- and the loads are issued at
+// the point where their target is known to be free: the x rows / audio of tile i+1 and the kernels / biases of tile i right after
+// LVC MMAs(i-1) have completed (the wait P5(i-1) starts with).  Two group barriers per tile (after P1, after P3) instead of four.
+// Arithmetic, tile walk (descending chunks, carried halo rows, second-pass fallback) and results are those of k_lvc_layer_h.
+// Hazards (the model cannot see them; argued here):  XS[s], TM[s], lbias[s] are written in iteration i and last read in iteration
+// i+1 (P5(i)); their next writers run in iteration i+2, behind the two barriers of iteration i+1.  AY[s^1] receives the rows of tile
+// i+1 only after LVC MMAs(i-1), its last reader, have completed.  The single audio buffer is read in P1(i) (before the first barrier
+// of iteration i) and refilled after it.  LW is refilled after LVC MMAs(i-1) and awaited (bar 3) before LVC MMAs(i) are issued.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LP_SLOT = 2 * LH_A_BYTES + 2 * LH_XS_BYTES + LH_LW_BYTES;        // 106,496 B per group
+constexpr int LP_SMALL = 2 * 256 + LT_AU * 4;                                  // lbias x 2 | audio
+constexpr int LP_SMEM_BYTES = 2 * (LP_SLOT + LP_SMALL) + LH_CW_BYTES + (7 * C + C + C + C) * 4 + 2 * 512 + 2 * 8 * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(512, 1)
+k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
+              float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l) {
+    constexpr int HOP = 256, GROUPS = 2, GT = 256;
+    FD_DYN_SMEM(unsigned char, smem_raw);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* cw = smem + GROUPS * LP_SLOT;                 // [3 taps][32 rows][128 B]
+    unsigned char* small0 = cw + LH_CW_BYTES;                    // [GROUPS][lbias 0 | lbias 1 | audio]
+    float* fw_s = (float*)(small0 + GROUPS * LP_SMALL);          // [7][32]
+    float* fb_s = fw_s + 7 * C;
+    float* cb_s = fb_s + C;
+    float* cbs_s = cb_s + C;                                     // conv bias * S16_ACT
+    unsigned char* carry_s = (unsigned char*)(cbs_s + C);        // [GROUPS][2][256 B]
+    uint64_t* bars = (uint64_t*)(carry_s + GROUPS * 512);        // [GROUPS][8]: 0 conv MMAs, 1 LVC MMAs, 2 rows + audio, 3 kernels + biases
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 8 * GROUPS);
+
+    const int tid = threadIdx.x, g = tid / GT, gt = tid % GT, gw = gt >> 5, lane = tid & 31;
+    unsigned char* slot = smem + g * LP_SLOT;
+    unsigned char* lw = slot + 2 * LH_A_BYTES + 2 * LH_XS_BYTES;
+    unsigned char* small = small0 + g * LP_SMALL;
+    float* au_s = (float*)(small + 512);
+    uint64_t* bar = bars + 8 * g;
+    unsigned char* carry = carry_s + g * 512;
+
+    if (tid == 0) {
+        for (int i = 0; i < 8 * GROUPS; ++i) mbar_init(&bars[i], 1);
+        mbar_init_fence();
+    }
+    if (tid < 32) tmem_alloc(tmem_base_s, 512u);
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.cw16);
+        for (int i = tid; i < LH_CW_BYTES / 16; i += GT * GROUPS) reinterpret_cast<float4*>(cw)[i] = src[i];
+        if (tid < 7 * C) fw_s[tid] = p.first_w[tid];
+        if (tid < C) { fb_s[tid] = p.first_b[tid]; cb_s[tid] = p.conv_b[tid]; cbs_s[tid] = p.conv_b[tid] * S16_ACT; }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // TMEM: group g at g * 256, column set s at + s * 128: conv [0,32), LVC [32,96), second conv pass [96,128)
+    const uint32_t tmem_g = *tmem_base_s + g * 256;
+    constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 64);
+    const int c4 = gt & 7;
+    const int prow = ((gw >> 2) << 4) + (gw & 3) + ((lane >> 3) << 2);   // rows r, r+4, r+8, r+12 per warp (conflict-free piece stores)
+    const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
+    const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * LP_SLOT);
+    const uint32_t cw_u = smem_u32(cw);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_g, 0);
+
+    const int ntt = (T + LT_TT - 1) / LT_TT, total = B * ntt;
+    const int r_lo = 27 - dil, r_hi = 157 + dil;
+    const int ngroups = gridDim.x * GROUPS, chunk = (total + ngroups - 1) / ngroups;
+    const int tile_lo = (blockIdx.x * GROUPS + g) * chunk, tile_hi = min(total, tile_lo + chunk) - 1;
+
+    // ---- loads (ONE thread) ----
+    auto issue_rows = [&](int tile, int s) {          // x rows -> AY[s], audio window -> au_s   (bar 2)
+        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
+        const int ar0 = max(r_lo, 28 - t0), ar1 = min(r_hi, T - t0 + 28);
+        const int i0 = max(0, 32 - t0), i1 = min(LT_AU, T - t0 + 32);
+        uint32_t bytes = 0;
+        if (ar1 > ar0) bytes += (uint32_t)(ar1 - ar0) * 128u;
+        if (i1 > i0) bytes += (uint32_t)(i1 - i0) * 4u;
+        mbar_expect_tx(&bar[2], bytes);
+        if (ar1 > ar0) bulk_g2s(slot + s * LH_A_BYTES + ar0 * 128, x_in + ((size_t)b * T + (t0 - 28 + ar0)) * C, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
+        if (i1 > i0) bulk_g2s(au_s + i0, skip + (size_t)b * T + (t0 - 32 + i0), (uint32_t)(i1 - i0) * 4u, &bar[2]);
+    };
+    auto issue_lw = [&](int tile, int s, bool keep_lw) {   // predicted kernels -> LW (unless the frame is already there), biases -> lbias[s]   (bar 3)
+        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT, f = t0 / HOP;
+        uint32_t bytes = 0;
+        if (f < Tm) bytes = (keep_lw ? 0u : (uint32_t)LH_LW_BYTES) + 256u;
+        mbar_expect_tx(&bar[3], bytes);
+        if (f < Tm) {
+            const float* src = kern + ((size_t)b * Tm + f) * KCN;
+            if (!keep_lw) bulk_g2s(lw, src, LH_LW_BYTES, &bar[3]);
+            bulk_g2s(small + s * 256, src + KK * LVC_OUT, 256, &bar[3]);
+        }
+    };
+
+    // ---- P1: raw x rows (+ first_conv(audio)) -> fp16 pieces in place, xs rows -> XS[s] ----
+    auto phase1 = [&](int t0, int s) {
+        unsigned char* a_t = slot + s * LH_A_BYTES;
+        unsigned char* xs_t = slot + 2 * LH_A_BYTES + s * LH_XS_BYTES;
+        if (gt < LT_AU) { const int pos = t0 - 32 + gt; if (pos < 0 || pos >= T) au_s[gt] = 0.f; }   // the first conv zero-pads
+        group_sync(1 + g, GT);
+        float fwr[7][4], fbr[4];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const float4 w4 = *reinterpret_cast<const float4*>(fw_s + k * C + c4 * 4);
+            fwr[k][0] = w4.x; fwr[k][1] = w4.y; fwr[k][2] = w4.z; fwr[k][3] = w4.w;
+        }
+        {
+            const float4 b4 = *reinterpret_cast<const float4*>(fb_s + c4 * 4);
+            fbr[0] = b4.x; fbr[1] = b4.y; fbr[2] = b4.z; fbr[3] = b4.w;
+        }
+        float4 xv[1536 / GT];
+#pragma unroll
+        for (int i = 0; i < 1536 / GT; ++i) {
+            const int ar = r_lo + prow + i * (GT / 8), t = t0 - 28 + ar;
+            xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ar < r_hi && t >= 0 && t < T) xv[i] = *reinterpret_cast<const float4*>(a_t + ar * 128 + c4 * 16);
+        }
+        __syncwarp();   // the 8 lanes of a row sit in one warp: every raw chunk has been read before any row is overwritten
+#pragma unroll
+        for (int i = 0; i < 1536 / GT; ++i) {
+            const int ar = r_lo + prow + i * (GT / 8), t = t0 - 28 + ar;
+            const bool active = ar < r_hi;
+            float4 pre = xv[i];   // zero outside [0,T)
+            if (active && t >= 0 && t < T) {
+                float4 sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const float a = au_s[ar + k + 1];
+                    sk.x = fmaf(fwr[k][0], a, sk.x); sk.y = fmaf(fwr[k][1], a, sk.y);
+                    sk.z = fmaf(fwr[k][2], a, sk.z); sk.w = fmaf(fwr[k][3], a, sk.w);
+                }
+                pre = make_float4(xv[i].x + sk.x, xv[i].y + sk.y, xv[i].z + sk.z, xv[i].w + sk.w);
+            }
+            uint2 hi, lo;
+            split4_f16_pre(lrelu02_s(pre.x), lrelu02_s(pre.y), lrelu02_s(pre.z), lrelu02_s(pre.w), hi, lo);
+            if (active) {
+                const int sw = ar & 7;
+                *reinterpret_cast<uint2*>(a_t + ar * 128 + (((c4 >> 1) ^ sw) << 4) + (c4 & 1) * 8) = hi;
+                *reinterpret_cast<uint2*>(a_t + ar * 128 + (((4 + (c4 >> 1)) ^ sw) << 4) + (c4 & 1) * 8) = lo;
+                if (ar >= 28 && ar < 28 + LT_TT)
+                    *reinterpret_cast<float4*>(xs_t + (ar - 28) * 128 + ((c4 ^ ((ar - 28) & 7)) << 4)) = pre;
+            }
+        }
+    };
+    // ---- conv MMAs of a tile (ONE thread): A rows of AY[s] x conv weights -> TM[s].conv (+ second pass -> TM[s] + 96) ----
+    auto issue_conv = [&](int s, bool have_carry, uint32_t at, uint32_t cwt) {
+        const uint32_t d = tmem_u + s * 128;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1 && have_carry) break;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t sh = (uint32_t)(pass * 128 + 27 + (k - 1) * dil) * 128u;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint64_t dah = umma_desc_sw128(at + sh + j * 32), dal = umma_desc_sw128(at + sh + 64 + j * 32);
+                    const uint64_t dbh = umma_desc_sw128(cwt + k * 4096 + j * 32), dbl = umma_desc_sw128(cwt + k * 4096 + 64 + j * 32);
+                    umma_f16(d + pass * 96, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
+                    umma_f16(d + pass * 96, dah, dbl, idesc_conv, 1u);
+                    umma_f16(d + pass * 96, dal, dbh, idesc_conv, 1u);
+                }
+            }
+        }
+        tc_commit(&bar[0]);
+    };
+    // ---- P3: y = lrelu(conv + b) -> pieces, rows of the Y tile (over the A tile AY[s]) ----
+    auto phase3 = [&](int t0, int s, bool have_carry, int it) {
+        unsigned char* a_t = slot + s * LH_A_BYTES;
+        const uint32_t tm = tmem_g + s * 128;
+        const int q3 = gw & 3, part3 = gw >> 2;
+        const float inv_cs = inv_c * S16_ACT;
+        auto emit_row = [&](const uint32_t (&v)[16], int yr, unsigned char* copy_to) {
+            const int t = t0 - 1 + yr;
+            const bool in = (t >= 0 && t < T);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                float y[8];
+                const int cb0 = part3 * 16 + cc * 8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float tt2 = fmaf(__uint_as_float(v[cc * 8 + e]), inv_cs, cbs_s[cb0 + e]);
+                    y[e] = in ? fmaxf(tt2, 0.2f * tt2) : 0.f;
+                }
+                uint2 h0, l0, h1, l1;
+                split4_f16_pre(y[0], y[1], y[2], y[3], h0, l0);
+                split4_f16_pre(y[4], y[5], y[6], y[7], h1, l1);
+                const int chunk = part3 * 2 + cc, sw = yr & 7;
+                *reinterpret_cast<uint4*>(a_t + yr * 128 + ((chunk ^ sw) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                *reinterpret_cast<uint4*>(a_t + yr * 128 + (((4 + chunk) ^ sw) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                if (copy_to) {
+                    *reinterpret_cast<uint4*>(copy_to + yr * 128 + ((chunk ^ sw) << 4)) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                    *reinterpret_cast<uint4*>(copy_to + yr * 128 + (((4 + chunk) ^ sw) << 4)) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                }
+            }
+        };
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tm + ((uint32_t)(q3 * 32) << 16) + part3 * 16, v);
+        tmem_ld_wait();
+        emit_row(v, q3 * 32 + lane, (q3 == 0 && lane < 2) ? carry + (it & 1) * 256 : nullptr);
+        if (have_carry) {
+            if (gt < 16) reinterpret_cast<uint4*>(a_t + 128 * 128)[gt] = reinterpret_cast<const uint4*>(carry + ((it & 1) ^ 1) * 256)[gt];
+        } else if (q3 == 0) {
+            tmem_ld_32x32b_x16(tm + 96 + part3 * 16, v);
+            tmem_ld_wait();
+            if (lane < 2) emit_row(v, 128 + lane, nullptr);
+        }
+    };
+    // ---- LVC MMAs of a tile (ONE thread): Y rows of AY[s] x predicted kernels -> TM[s].lvc ----
+    auto issue_lvc = [&](int s, uint32_t at, uint32_t lwb) {
+        const uint32_t d = tmem_u + s * 128 + 32;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint64_t dah = umma_desc_sw128(at + k * 128 + j * 32), dal = umma_desc_sw128(at + k * 128 + 64 + j * 32);
+                const uint64_t dbh = umma_desc_sw128(lwb + k * 8192 + j * 32), dbl = umma_desc_sw128(lwb + k * 8192 + 64 + j * 32);
+                umma_f16(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
+                umma_f16(d, dah, dbl, idesc_lvc, 1u);
+                umma_f16(d, dal, dbh, idesc_lvc, 1u);
+            }
+        tc_commit(&bar[1]);
+    };
+    // ---- P5: gate + residual -> global (tile (b, t0), buffer set s, barrier parity ph); `after_wait` runs in warp 0 once the LVC MMAs are done ----
+    auto phase5 = [&](int b, int t0, int s, uint32_t ph, auto&& after_wait) {
+        const unsigned char* xs_t = slot + 2 * LH_A_BYTES + s * LH_XS_BYTES;
+        const float* lbias = (const float*)(small + s * 256);
+        const int q = gw & 3, part = gw >> 2;
+        const int r = q * 32 + lane, t = t0 + r;
+        const size_t row = ((size_t)b * T + (t < T ? t : 0)) * C + part * 16;
+        float4 xs[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) xs[c] = *reinterpret_cast<const float4*>(xs_t + r * 128 + (((part * 4 + c) ^ (r & 7)) << 4));
+        mbar_wait(&bar[1], ph);
+        tc_fence_after();
+        after_wait();
+        uint32_t zs[16], zt[16];
+        const uint32_t ta = tmem_g + s * 128 + ((uint32_t)(q * 32) << 16) + 32 + part * 16;
+        tmem_ld_32x32b_x16(ta, zs);
+        tmem_ld_32x32b_x16(ta + 32, zt);
+        tmem_ld_wait();
+        if (t < T) {
+            const float* lb = lbias + part * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float4 o4;
+                o4.x = xs[c].x + gate_st(fmaf(__uint_as_float(zs[c * 4 + 0]), inv_l, lb[c * 4 + 0]), fmaf(__uint_as_float(zt[c * 4 + 0]), inv_l, lb[32 + c * 4 + 0]));
+                o4.y = xs[c].y + gate_st(fmaf(__uint_as_float(zs[c * 4 + 1]), inv_l, lb[c * 4 + 1]), fmaf(__uint_as_float(zt[c * 4 + 1]), inv_l, lb[32 + c * 4 + 1]));
+                o4.z = xs[c].z + gate_st(fmaf(__uint_as_float(zs[c * 4 + 2]), inv_l, lb[c * 4 + 2]), fmaf(__uint_as_float(zt[c * 4 + 2]), inv_l, lb[32 + c * 4 + 2]));
+                o4.w = xs[c].w + gate_st(fmaf(__uint_as_float(zs[c * 4 + 3]), inv_l, lb[c * 4 + 3]), fmaf(__uint_as_float(zt[c * 4 + 3]), inv_l, lb[32 + c * 4 + 3]));
+                *reinterpret_cast<float4*>(x_out + row + c * 4) = o4;
+            }
+        }
+    };
+
+    // ---- the pipelined tile walk of this group: tiles tile_hi, tile_hi - 1, ..., tile_lo ----
+    if (tile_hi >= tile_lo && gw_u == 0) {
+        if (elect_one()) { issue_rows(tile_hi, 0); issue_lw(tile_hi, 0, false); }
+        __syncwarp();
+    }
+    int pb = 0, pt0 = 0;    // the previous tile (whose gate epilogue is still to come)
+    int it = 0;
+    for (int tile = tile_hi; tile >= tile_lo; --tile, ++it) {
+        const int b = tile / ntt, tt = tile % ntt, t0 = tt * LT_TT;
+        const int s = it & 1;
+        const uint32_t ph = (uint32_t)(it & 1);
+        const bool have_carry = (tile != tile_hi) && (tt != ntt - 1);
+        // P1(i)
+        mbar_wait(&bar[2], ph);
+        phase1(t0, s);
+        fence_async_smem();
+        group_sync(1 + g, GT);
+        // conv MMAs(i)
+        if (gw_u == 0) {
+            tc_fence_after();
+            uint32_t at = slot_u + (uint32_t)(s * LH_A_BYTES), cwt = cw_u;
+            FD_OPAQUE2(at, cwt);
+            if (elect_one()) issue_conv(s, have_carry, at, cwt);
+            __syncwarp();
+        }
+        // P5(i-1) while they run; its MMA wait also frees AY[s^1] / LW: request tile i+1's rows and this tile's kernels there
+        auto loads_after_lvc = [&]() {
+            if (gw_u == 0) {
+                if (elect_one()) {
+                    if (tile - 1 >= tile_lo) issue_rows(tile - 1, s ^ 1);
+                    if (it > 0) issue_lw(tile, s, (tt & 1) == 0 && tt + 1 < ntt && tile != tile_hi);   // (b, tt + 1) was the previous tile: same frame
+                }
+                __syncwarp();
+            }
+        };
+        if (it > 0) phase5(pb, pt0, s ^ 1, ph ^ 1, loads_after_lvc);
+        else loads_after_lvc();
+        // P3(i)
+        mbar_wait(&bar[0], ph);
+        tc_fence_after();
+        phase3(t0, s, have_carry, it);
+        fence_async_smem();
+        tc_fence_before();
+        group_sync(1 + g, GT);
+        // LVC MMAs(i)
+        if (gw_u == 0) {
+            tc_fence_after();
+            uint32_t at = slot_u + (uint32_t)(s * LH_A_BYTES), lwb = slot_u + (uint32_t)(2 * LH_A_BYTES + 2 * LH_XS_BYTES);
+            FD_OPAQUE2(at, lwb);
+            if (elect_one()) { mbar_wait(&bar[3], ph); issue_lvc(s, at, lwb); }
+            __syncwarp();
+        }
+        pb = b; pt0 = t0;
+    }
+    if (it > 0) phase5(pb, pt0, (it - 1) & 1, (uint32_t)((it - 1) & 1), [] {});
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        tmem_dealloc(*tmem_base_s, 512u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // EXPERIMENTAL (option "tc_b0", default off; developed on the CPU model, to be measured in round 2): one LVC layer of block 0
 // (hop 8) on tensor cores in SWAPPED-operand form.  With 8 samples per frame an M = 128 time-step tile would use 8 rows per
 // predicted kernel; instead the kernels are the M side:
@@ -2848,11 +3170,31 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
 #ifndef FD_EMU
 static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const float* x_in, const float* skip, const float* kern,
                                float* x_out, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches,
-                               bool* done, int b2_skip_rows = 0) {
+                               bool* done, int b2_skip_rows = 0, int b2_pipe = 0) {
     *done = false;
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (blk == 0) return 0;   // hop 8: stays on the SIMT kernel
+    if (mode == FD_MODE_TC_3XF16 && blk == 2 && b2_pipe && !b2_skip_rows) {   // experimental option "lvc_pipe": software-pipelined tile walk
+        if (!s->b2p_attr_set) {
+            cudaError_t ea = cudaFuncSetAttribute(k_lvc_layer_p, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM_BYTES);
+            if (ea != cudaSuccess) { err = std::string("k_lvc_layer_p: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
+            s->b2p_attr_set = 1;
+        }
+        LvcHParams hp;
+        hp.cw16 = s->blob + s->sec_off[FD_S_LB2_CONV_F16] + (size_t)layer * (LH_CW_BYTES / 4);
+        hp.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + 2 * FD_LB_STRIDE] + layer * C;
+        hp.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
+        hp.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
+        const float inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * 2 + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
+        const int tiles = B * ((T + LT_TT - 1) / LT_TT), per = (tiles + 1) / 2, grid = per < s->sm_count ? per : s->sm_count;
+        k_lvc_layer_p<<<grid, 512, LP_SMEM_BYTES, st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_p failed: ") + cudaGetErrorString(e); return -3; }
+        ++*launches;
+        *done = true;
+        return 0;
+    }
     if (mode == FD_MODE_TC_3XF16 && blk == 2 && b2_skip_rows) {
         // experimental option "b2_skipbuf": `skip` = first_conv(audio) as (B,T,32) rows; block 2 then runs the block-1 flavour of the
         // kernel (skip rows bulk-loaded by the first layer, added to the produced rows by layers 0..2)

@@ -111,7 +111,8 @@ int fd_get_mode(fd_handle* h);
  * "tc_b0" [0] EXPERIMENTAL tensor-core kernel for LVC block 0 in mode tc_3xf16 (validated on the CPU model only):
  * 1 = fed by the GEMM writing block 0 as fp16 pieces, 2 = fed by an in-place converter pass; "b2_skipbuf" [0] EXPERIMENTAL: LVC block 2
  * reads first_conv(audio) as rows written once per evaluation instead of recomputing it in every layer (same bits); "kc_stage" [0]
- * EXPERIMENTAL: kernel_conv GEMM epilogue through shared memory + cp.async.bulk stores (same bits). */
+ * EXPERIMENTAL: kernel_conv GEMM epilogue through shared memory + cp.async.bulk stores (same bits); "lvc_pipe" [0] EXPERIMENTAL: LVC
+ * block 2 with software-pipelined tiles (same bits). */
 int fd_set_option(fd_handle* h, const char* key, int64_t value);
 
 /* eps = FastDiff.forward((x_t, mel, t))   (modules/FastDiff/module/FastDiff_model.py:74-102).

@@ -1,7 +1,7 @@
 """Round-2 GPU check of the options that are OFF by default and have only run on the CPU model so far (NOT collected by pytest on
 purpose; one option per process, each under its own `timeout`, so that a kernel that hangs or faults costs its own step only):
 
-    for o in tc_b0 b2_skipbuf kc_stage; do timeout 150 python tests/gpu_options_check.py $o; done
+    for o in tc_b0 b2_skipbuf kc_stage lvc_pipe; do timeout 150 python tests/gpu_options_check.py $o; done
 
 Per option: parity at small shapes (eps against the oracle and against the default path; bitwise where the option promises the same bits),
 then the per-class kernel times at config 2 (B = 8, T' = 861) with the option off and on.  `--emu` runs the same script on the CPU
@@ -16,8 +16,8 @@ import fastdiff_b200 as fb  # noqa: E402
 from fastdiff_b200.synthetic import make_inputs, make_state_dict  # noqa: E402
 from oracle import fastdiff_oracle as O  # noqa: E402
 
-VALUES = {"tc_b0": (1, 2), "b2_skipbuf": (1,), "kc_stage": (1,)}
-BITWISE = {"tc_b0": False, "b2_skipbuf": True, "kc_stage": True}
+VALUES = {"tc_b0": (1, 2), "b2_skipbuf": (1,), "kc_stage": (1,), "lvc_pipe": (1,)}
+BITWISE = {"tc_b0": False, "b2_skipbuf": True, "kc_stage": True, "lvc_pipe": True}
 
 
 def main():

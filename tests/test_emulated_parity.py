@@ -249,3 +249,26 @@ def test_emulated_gemm_staged_epilogue_option(synth, emu_lib, B, Tm):
     eps2 = net((x, mel, t))
     eng.set_option("kc_stage", 0)
     assert torch.equal(net((x, mel, t)), eps2)
+
+
+@pytest.mark.parametrize("B,Tm", [(1, 1), (3, 17), (1, 40)])
+def test_emulated_block2_pipelined_tile_walk_option(synth, emu_lib, B, Tm):
+    """Option lvc_pipe (experimental, default off): k_lvc_layer_p runs LVC block 2 with the phases of consecutive tiles of a group
+    software-pipelined (P1(i) | conv MMAs(i) | gate epilogue(i-1) | P3(i) | LVC MMAs(i)), every per-tile buffer doubled (A/Y tile, xs
+    rows, TMEM column set, lbias) and the loads re-timed.  Same arithmetic and tile walk -> the default's bits, for single-tile
+    groups, chunks of several tiles (carried halo rows, kernel reuse across the two tiles of a frame) and ragged batches."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    x, mel = make_inputs(B, Tm, 51)
+    t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
+    eng = net.engine()
+    eps0 = net((x, mel, t))
+    eng.set_option("lvc_pipe", 1)
+    eps1 = net((x, mel, t))
+    assert torch.equal(eps0, eps1)
+    assert (eps1 - O.denoise(W, x, mel, t)).abs().max() < 5e-5
+    if B > 1:      # an item alone = the same item inside the batch, bitwise
+        assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), eps1[1:2])

@@ -2,7 +2,7 @@
 # First GPU call of round 2 (run from the repo root through gpurun, ~12 GPU-minutes):
 #   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 # 1. the GPU test-suite on the default path; 2. parity + per-class kernel times of the run-time options that are OFF by default
-# (tc_b0, b2_skipbuf, kc_stage; tests/gpu_options_check.py); 3. bench.py for the default and for each option; 4. one rebuild + bench per
+# (tc_b0, b2_skipbuf, kc_stage, lvc_pipe; tests/gpu_options_check.py); 3. bench.py for the default and for each option; 4. one rebuild + bench per
 # compile-time switch.  Everything lands in gpurun_out/r2_first/.  Each step has its own timeout: an experimental kernel that hangs
 # costs its step, not the call.
 set -u
@@ -11,12 +11,12 @@ mkdir -p "$OUT"
 B="python bench.py --steps 10 --warmup 3 --no-cpu"
 
 timeout 600 python -m pytest tests -m gpu -x -q > "$OUT/gpu_tests.log" 2>&1; echo "pytest rc=$?" >> "$OUT/gpu_tests.log"
-for o in tc_b0 b2_skipbuf kc_stage; do
+for o in tc_b0 b2_skipbuf kc_stage lvc_pipe; do
     timeout 150 python tests/gpu_options_check.py $o > "$OUT/options_check_$o.log" 2>&1; echo "rc=$?" >> "$OUT/options_check_$o.log"
 done
 
 timeout 120 $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
-for o in tc_b0=1 tc_b0=2 b2_skipbuf=1 kc_stage=1; do
+for o in tc_b0=1 tc_b0=2 b2_skipbuf=1 kc_stage=1 lvc_pipe=1; do
     timeout 120 $B --opt $o > "$OUT/bench_$o.json" 2> "$OUT/bench_$o.err"; echo "$o rc=$?" >> "$OUT/bench_rc.log"
 done
 timeout 120 $B --opt tc_b0=1 --opt b2_skipbuf=1 --opt kc_stage=1 > "$OUT/bench_all_options.json" 2> "$OUT/bench_all_options.err"
