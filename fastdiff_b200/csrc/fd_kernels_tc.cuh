@@ -2218,12 +2218,15 @@ k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         fence_async_smem();
         tc_fence_before();
         group_sync(1 + g, GT);
-        // LVC MMAs(i)
+        // LVC MMAs(i).  Every thread takes the kernels + biases barrier here (not only the issuing one): it is the acquire for the lbias
+        // values its gate epilogue reads next iteration, and at this point the barrier cannot be a phase ahead (the next refill is
+        // issued in the next iteration)
+        mbar_wait(&bar[3], ph);
         if (gw_u == 0) {
             tc_fence_after();
             uint32_t at = slot_u + (uint32_t)(s * LH_A_BYTES), lwb = slot_u + (uint32_t)(2 * LH_A_BYTES + 2 * LH_XS_BYTES);
             FD_OPAQUE2(at, lwb);
-            if (elect_one()) { mbar_wait(&bar[3], ph); issue_lvc(s, at, lwb); }
+            if (elect_one()) issue_lvc(s, at, lwb);
             __syncwarp();
         }
         pb = b; pt0 = t0;
