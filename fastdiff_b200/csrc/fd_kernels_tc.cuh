@@ -436,6 +436,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 // a [8 frames][512 B] buffer, one named barrier, then 8 lanes of one warp issue one 512-byte shared->global bulk copy each (frames
 // outside the utterances are simply skipped).  Two buffers per group: the copies of chunk i read one while chunk i+1 fills the other;
 // the issuing warp waits for the previous chunk's smem reads (wait_group.read) BEFORE the barrier, so after it every warp may refill.
+// (The CPU model performs a bulk store when its thread waits for it, the latest legal moment: dropping that wait breaks the parity test.)
 // Motivation: the 2-byte LSU stores run into the global-store queue limit (lg_throttle) and keep the whole
 // kernel at store speed; bulk copies take them off the LSU path in 512-byte requests.
 constexpr int KC2_STG_BYTES = 4 * 2 * 8 * 512;   // 4 column groups x 2 buffers x 8 frames x 512 B = 32 KB

@@ -8,6 +8,7 @@
 //     XORs ABSOLUTE address bits [7,10) into [4,7) (descriptor base_offset 0, as measured on B200), D = 128 lanes x N fp32 columns;
 //   * TMEM = 128 lanes x 512 fp32 columns per CTA.
 #pragma once
+#include <vector>
 #include <stdio.h>
 
 namespace fd {
@@ -48,12 +49,27 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { memcpy(smem_dst, gsrc, bytes); emu_mbar_complete_tx(bar, bytes); }
 inline void bulk_prefetch_l2(const void*, uint32_t) {}
-// shared -> global bulk copy (bulk async-groups): copied at issue, so commit / wait have nothing left to do.  Source-reuse hazards
-// (overwriting a staging buffer before wait_group.read) are therefore NOT detected by the model.
-inline void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) { memcpy(gdst, smem_src, bytes); }
+// shared -> global bulk copy (bulk async-groups).  The model performs the copy as LATE as the program allows -- when the issuing thread
+// executes wait_group(.read) -- so a staging buffer that is overwritten before its copies were waited for delivers the wrong bytes and
+// the parity tests see it (the adversarial schedule for source-reuse hazards).  A kernel must end with bulk_wait_all() in every issuing
+// thread (the real one must, too).
+struct EmuBulkStore { void* dst; const void* src; uint32_t bytes; unsigned who; };
+inline std::vector<EmuBulkStore>& emu_bulk_pending() { static thread_local std::vector<EmuBulkStore> v; return v; }   // per OS thread = per CTA (pair) in flight
+inline unsigned emu_bulk_me() { return emu::t_linear_tid + 65536u * emu::t_cta_rank; }
+inline void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) { emu_bulk_pending().push_back({gdst, smem_src, bytes, emu_bulk_me()}); }
+inline void emu_bulk_flush() {
+    auto& v = emu_bulk_pending();
+    const unsigned me = emu_bulk_me();
+    size_t keep = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (v[i].who == me) memcpy(v[i].dst, v[i].src, v[i].bytes);
+        else v[keep++] = v[i];
+    }
+    v.resize(keep);
+}
 inline void bulk_commit() {}
-inline void bulk_wait_read0() {}
-inline void bulk_wait_all() {}
+inline void bulk_wait_read0() { emu_bulk_flush(); }
+inline void bulk_wait_all() { emu_bulk_flush(); }
 inline bool elect_one() { return (emu::t_linear_tid & 31) == 0; }
 inline void tc_fence_before() {}
 inline void tc_fence_after() {}
