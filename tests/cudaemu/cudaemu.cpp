@@ -11,6 +11,8 @@ dim3 g_blockDim, g_gridDim;
 thread_local unsigned char* t_dyn_smem = nullptr;
 thread_local size_t t_dyn_smem_bytes = 0;
 thread_local unsigned t_linear_tid = 0, t_cta_rank = 0;
+thread_local unsigned t_cta_serial = 0;
+int g_bulk_late = 0;
 
 namespace {
 constexpr size_t kStack = 512 * 1024;
@@ -167,6 +169,8 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     for (auto& x : th) x.join();
 }
 
-void cta_begin() {}
+void cta_begin() { ++t_cta_serial; }
 void cta_end() {}
 }  // namespace emu
+
+extern "C" void cudaemu_set_bulk_late(int on) { emu::g_bulk_late = on ? 1 : 0; }

@@ -2,7 +2,8 @@
 // (fastdiff_b200/csrc/fd_kernels_f16.cuh), for the CPU fibre emulator.  TEST INFRASTRUCTURE, never shipped.
 //   * shared-memory "addresses" are byte offsets into the CTA's dynamic shared memory (1024-byte aligned like the real window);
 //   * an mbarrier keeps its state in its own 64-bit word {pending arrivals, arrival count, outstanding tx bytes, phase};
-//   * cp.async.bulk copies synchronously and completes its bytes at once; tcgen05.mma executes synchronously at issue (so
+//   * cp.async.bulk global->shared lands its bytes at issue or, on request, when its mbarrier is first polled (two legal schedules, see
+//     bulk_g2s); shared->global lands when the issuing thread waits for it; tcgen05.mma executes synchronously at issue (so
 //     tcgen05.commit is a plain arrive); polling loops yield to the other fibres of the CTA;
 //   * tcgen05.mma kind::f16, cta_group::1, K = 16, both operands K-major SWIZZLE_128B from shared-memory descriptors: the swizzle
 //     XORs ABSOLUTE address bits [7,10) into [4,7) (descriptor base_offset 0, as measured on B200), D = 128 lanes x N fp32 columns;
@@ -38,16 +39,38 @@ inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {   // mbarrier.arrive
 }
 inline void mbar_arrive(uint64_t* bar) { EmuMbar8* b = (EmuMbar8*)bar; --b->pending; emu_mbar_settle(b); }
 inline void emu_mbar_complete_tx(uint64_t* bar, uint32_t bytes) { EmuMbar8* b = (EmuMbar8*)bar; b->tx_phase -= (int32_t)(bytes << 1); emu_mbar_settle(b); }
+// global -> shared bulk copies.  Two schedules, both legal on the hardware, chosen by cudaemu_set_bulk_late():
+//   early (default): the bytes land at issue -- the adversarial case for a target that something still READS (write-after-read);
+//   late: the bytes land when a thread first polls the copy's mbarrier -- the adversarial case for a target that is read, or written
+//         by ordinary stores, BEFORE the barrier was waited for.
+// The emulated parity tests run the pipelined / ring-fed kernels under both.
+struct EmuBulkLoad { void* dst; const void* src; uint32_t bytes; uint64_t* bar; unsigned serial; };
+inline std::vector<EmuBulkLoad>& emu_load_pending() { static thread_local std::vector<EmuBulkLoad> v; return v; }
+inline void emu_deliver_loads(uint64_t* bar) {
+    auto& v = emu_load_pending();
+    size_t keep = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (v[i].serial != emu::t_cta_serial) continue;                       // left over from an earlier CTA of this OS thread
+        if (v[i].bar == bar) { memcpy(v[i].dst, v[i].src, v[i].bytes); emu_mbar_complete_tx(bar, v[i].bytes); }
+        else v[keep++] = v[i];
+    }
+    v.resize(keep);
+}
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     const EmuMbar8* b = (const EmuMbar8*)bar;
     for (uint32_t it = 0; it < (1u << 22); ++it) {
+        if (emu::g_bulk_late && !emu_load_pending().empty()) emu_deliver_loads(bar);
         if ((uint32_t)(b->tx_phase & 1) != (parity & 1)) return;
         emu::yield();
     }
     fprintf(stderr, "tcemu: mbarrier wait timed out (protocol bug)\n");
     abort();
 }
-inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { memcpy(smem_dst, gsrc, bytes); emu_mbar_complete_tx(bar, bytes); }
+inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    if (emu::g_bulk_late) { emu_load_pending().push_back({smem_dst, gsrc, bytes, bar, emu::t_cta_serial}); return; }
+    memcpy(smem_dst, gsrc, bytes);
+    emu_mbar_complete_tx(bar, bytes);
+}
 inline void bulk_prefetch_l2(const void*, uint32_t) {}
 // shared -> global bulk copy (bulk async-groups).  The model performs the copy as LATE as the program allows -- when the issuing thread
 // executes wait_group(.read) -- so a staging buffer that is overwritten before its copies were waited for delivers the wrong bytes and

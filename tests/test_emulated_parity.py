@@ -272,3 +272,32 @@ def test_emulated_block2_pipelined_tile_walk_option(synth, emu_lib, B, Tm):
     assert (eps1 - O.denoise(W, x, mel, t)).abs().max() < 5e-5
     if B > 1:      # an item alone = the same item inside the batch, bitwise
         assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), eps1[1:2])
+
+
+def test_emulated_kernels_under_both_bulk_copy_schedules(synth, emu_lib):
+    """cp.async.bulk global->shared copies are asynchronous: the model can land their bytes at issue (the adversarial schedule for a
+    target something still reads) or when the copy's mbarrier is first polled (adversarial for a target that is read or written
+    before the barrier was waited for).  The default path and every optional kernel that re-times its loads (ring-fed block 0,
+    pipelined block 2, skip rows, staged GEMM epilogue) must give the same bits under both."""
+    import ctypes
+    from fastdiff_b200.synthetic import make_inputs
+    sd, _ = synth
+    net = _net(sd, emu_lib)
+    net.mode = "tc_3xf16"
+    eng = net.engine()
+    model = ctypes.CDLL(emu_lib)
+    x, mel = make_inputs(2, 40, 4)
+    t = torch.tensor([[7.413235], [498.0537]])
+    names = ("lvc_pipe", "tc_b0", "b2_skipbuf", "kc_stage")
+    out = {}
+    try:
+        for late in (0, 1):
+            model.cudaemu_set_bulk_late(late)
+            for on in (None,) + names:
+                for k in names:
+                    eng.set_option(k, 1 if k == on else 0)
+                out[(late, on)] = net((x, mel, t))
+    finally:
+        model.cudaemu_set_bulk_late(0)
+    for on in (None,) + names:
+        assert torch.equal(out[(0, on)], out[(1, on)]), on
