@@ -13,6 +13,7 @@ thread_local size_t t_dyn_smem_bytes = 0;
 thread_local unsigned t_linear_tid = 0, t_cta_rank = 0;
 thread_local unsigned t_cta_serial = 0;
 int g_bulk_late = 0;
+long long g_late_ops[2] = {0, 0};
 
 namespace {
 constexpr size_t kStack = 512 * 1024;
@@ -173,4 +174,5 @@ void cta_begin() { ++t_cta_serial; }
 void cta_end() {}
 }  // namespace emu
 
-extern "C" void cudaemu_set_bulk_late(int on) { emu::g_bulk_late = on ? 1 : 0; }
+extern "C" long long cudaemu_late_ops(int which) { return __atomic_load_n(&emu::g_late_ops[which & 1], __ATOMIC_RELAXED); }
+extern "C" void cudaemu_set_bulk_late(int mask) { emu::g_bulk_late = mask & 3; }   // bit 0: late bulk loads, bit 1: late MMAs (tcemu.h)

@@ -43,7 +43,8 @@ extern thread_local unsigned char* t_dyn_smem;
 extern thread_local size_t t_dyn_smem_bytes;
 extern thread_local unsigned t_linear_tid, t_cta_rank;
 extern thread_local unsigned t_cta_serial;   // bumped for every CTA (pair) an OS thread starts: lets per-CTA model state expire
-extern int g_bulk_late;                       // tcemu.h: 1 = global->shared bulk copies land when their mbarrier is first polled (see there)
+extern long long g_late_ops[2];               // how many bulk loads / MMAs actually took the late path (tests assert the schedule was exercised)
+extern int g_bulk_late;                       // tcemu.h: bit 0 = global->shared bulk copies land when their mbarrier is first polled, bit 1 = MMAs run then
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body, unsigned cluster = 1);
 unsigned cluster_rank();                  // CTA pairs (cluster = 2): both CTAs of a pair run as one fibre set on one OS thread
 unsigned char* cluster_smem(unsigned rank);

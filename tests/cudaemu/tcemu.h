@@ -39,7 +39,7 @@ inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {   // mbarrier.arrive
 }
 inline void mbar_arrive(uint64_t* bar) { EmuMbar8* b = (EmuMbar8*)bar; --b->pending; emu_mbar_settle(b); }
 inline void emu_mbar_complete_tx(uint64_t* bar, uint32_t bytes) { EmuMbar8* b = (EmuMbar8*)bar; b->tx_phase -= (int32_t)(bytes << 1); emu_mbar_settle(b); }
-// global -> shared bulk copies.  Two schedules, both legal on the hardware, chosen by cudaemu_set_bulk_late():
+// global -> shared bulk copies.  Two schedules, both legal on the hardware, chosen by bit 0 of cudaemu_set_bulk_late():
 //   early (default): the bytes land at issue -- the adversarial case for a target that something still READS (write-after-read);
 //   late: the bytes land when a thread first polls the copy's mbarrier -- the adversarial case for a target that is read, or written
 //         by ordinary stores, BEFORE the barrier was waited for.
@@ -51,15 +51,22 @@ inline void emu_deliver_loads(uint64_t* bar) {
     size_t keep = 0;
     for (size_t i = 0; i < v.size(); ++i) {
         if (v[i].serial != emu::t_cta_serial) continue;                       // left over from an earlier CTA of this OS thread
-        if (v[i].bar == bar) { memcpy(v[i].dst, v[i].src, v[i].bytes); emu_mbar_complete_tx(bar, v[i].bytes); }
+        if (v[i].bar == bar) { memcpy(v[i].dst, v[i].src, v[i].bytes); emu_mbar_complete_tx(bar, v[i].bytes); __atomic_fetch_add(&emu::g_late_ops[0], 1, __ATOMIC_RELAXED); }
         else v[keep++] = v[i];
     }
     v.resize(keep);
 }
+inline bool emu_mma_queue_empty();
+inline void emu_run_mmas_until(uint64_t* bar);
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     const EmuMbar8* b = (const EmuMbar8*)bar;
     for (uint32_t it = 0; it < (1u << 22); ++it) {
-        if (emu::g_bulk_late && !emu_load_pending().empty()) emu_deliver_loads(bar);
+        // late schedules: hold the asynchronous work back until this thread has polled for two full rounds of the fibre scheduler, i.e.
+        // until every other fibre of the CTA has run as far as it can without it (blocked at a barrier or polling as well)
+        if (it >= 2) {
+            if ((emu::g_bulk_late & 1) && !emu_load_pending().empty()) emu_deliver_loads(bar);
+            if ((emu::g_bulk_late & 2) && !emu_mma_queue_empty()) emu_run_mmas_until(bar);
+        }
         if ((uint32_t)(b->tx_phase & 1) != (parity & 1)) return;
         emu::yield();
     }
@@ -67,7 +74,7 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     abort();
 }
 inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    if (emu::g_bulk_late) { emu_load_pending().push_back({smem_dst, gsrc, bytes, bar, emu::t_cta_serial}); return; }
+    if (emu::g_bulk_late & 1) { emu_load_pending().push_back({smem_dst, gsrc, bytes, bar, emu::t_cta_serial}); return; }
     memcpy(smem_dst, gsrc, bytes);
     emu_mbar_complete_tx(bar, bytes);
 }
@@ -97,7 +104,39 @@ inline bool elect_one() { return (emu::t_linear_tid & 31) == 0; }
 inline void tc_fence_before() {}
 inline void tc_fence_after() {}
 inline void fence_async_smem() {}
-inline void tc_commit(uint64_t* bar) { mbar_arrive(bar); }
+// tcgen05.mma is asynchronous as well.  Early schedule (default): it executes at issue and tcgen05.commit is a plain arrive.  Late schedule
+// (bit 1 of cudaemu_set_bulk_late(), 1-CTA kind::f16 MMAs): MMAs and commits queue up in program order and run when a thread first polls a
+// committed mbarrier -- an operand tile refilled, or an accumulator read, before the commit was waited for then shows in the results.
+struct EmuMmaOp { int kind; uint32_t d; uint64_t a, b; uint32_t idesc, acc; uint64_t* bar; unsigned serial, who; };   // kind 0 = mma, 1 = commit
+inline std::vector<EmuMmaOp>& emu_mma_pending() { static thread_local std::vector<EmuMmaOp> v; return v; }
+inline void emu_mma_f16_now(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate);
+inline bool emu_mma_queue_empty() { return emu_mma_pending().empty(); }
+inline void emu_run_mmas_until(uint64_t* bar) {       // run the issuing thread's queue in order up to (and including) its first commit on `bar`
+    auto& v = emu_mma_pending();
+    size_t keep = 0;
+    for (size_t i = 0; i < v.size(); ++i)              // entries left over from an earlier CTA of this OS thread
+        if (v[i].serial == emu::t_cta_serial) v[keep++] = v[i];
+    v.resize(keep);
+    size_t upto = 0;
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i].kind == 1 && v[i].bar == bar) { upto = i + 1; break; }
+    if (!upto) return;
+    const unsigned who = v[upto - 1].who;              // only that thread's MMAs are ordered before this commit: the other issuers' stay queued
+    keep = 0;
+    for (size_t i = 0; i < v.size(); ++i) {
+        if (i < upto && v[i].who == who) {
+            if (v[i].kind == 0) { emu_mma_f16_now(v[i].d, v[i].a, v[i].b, v[i].idesc, v[i].acc); __atomic_fetch_add(&emu::g_late_ops[1], 1, __ATOMIC_RELAXED); }
+            else mbar_arrive(v[i].bar);
+        } else {
+            v[keep++] = v[i];
+        }
+    }
+    v.resize(keep);
+}
+inline void tc_commit(uint64_t* bar) {
+    if (emu::g_bulk_late & 2) { emu_mma_pending().push_back({1, 0, 0, 0, 0, 0, bar, emu::t_cta_serial, emu_bulk_me()}); return; }
+    mbar_arrive(bar);
+}
 inline void tmem_alloc(uint32_t* dst_smem, uint32_t) { *dst_smem = 0; }
 inline void tmem_dealloc(uint32_t, uint32_t) {}
 inline void group_sync(int id, int nthreads) { emu::barrier(id, nthreads); }
@@ -123,6 +162,10 @@ inline float emu_f16_at(uint32_t desc_start, uint32_t sbo, int row, int k) {   /
     return f16_bits_to_float_soft(h);
 }
 inline void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (emu::g_bulk_late & 2) { emu_mma_pending().push_back({0, d_tmem, a_desc, b_desc, idesc, accumulate, nullptr, emu::t_cta_serial, emu_bulk_me()}); return; }
+    emu_mma_f16_now(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+inline void emu_mma_f16_now(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
     const uint32_t a0 = (uint32_t)(a_desc & 0x3FFF) << 4, b0 = (uint32_t)(b_desc & 0x3FFF) << 4;
     const uint32_t sa = (uint32_t)((a_desc >> 32) & 0x3FFF) << 4, sb = (uint32_t)((b_desc >> 32) & 0x3FFF) << 4;

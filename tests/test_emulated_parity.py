@@ -274,11 +274,12 @@ def test_emulated_block2_pipelined_tile_walk_option(synth, emu_lib, B, Tm):
         assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), eps1[1:2])
 
 
-def test_emulated_kernels_under_both_bulk_copy_schedules(synth, emu_lib):
-    """cp.async.bulk global->shared copies are asynchronous: the model can land their bytes at issue (the adversarial schedule for a
-    target something still reads) or when the copy's mbarrier is first polled (adversarial for a target that is read or written
-    before the barrier was waited for).  The default path and every optional kernel that re-times its loads (ring-fed block 0,
-    pipelined block 2, skip rows, staged GEMM epilogue) must give the same bits under both."""
+def test_emulated_kernels_under_all_async_schedules(synth, emu_lib):
+    """cp.async.bulk global->shared copies and tcgen05.mma are asynchronous.  The model can land a copy's bytes at issue (adversarial for
+    a target something still reads) or when its mbarrier is first polled (adversarial for a target read or written before the wait),
+    and can run the MMAs at issue or when their commit barrier is first polled (adversarial for an operand tile refilled, or an
+    accumulator read, too early).  The default path and every optional kernel that re-times its loads or its MMAs (ring-fed block 0,
+    pipelined block 2, skip rows, staged GEMM epilogue) must give the same bits under all four combinations."""
     import ctypes
     from fastdiff_b200.synthetic import make_inputs
     sd, _ = synth
@@ -286,12 +287,12 @@ def test_emulated_kernels_under_both_bulk_copy_schedules(synth, emu_lib):
     net.mode = "tc_3xf16"
     eng = net.engine()
     model = ctypes.CDLL(emu_lib)
-    x, mel = make_inputs(2, 40, 4)
+    x, mel = make_inputs(2, 20, 4)
     t = torch.tensor([[7.413235], [498.0537]])
     names = ("lvc_pipe", "tc_b0", "b2_skipbuf", "kc_stage")
     out = {}
     try:
-        for late in (0, 1):
+        for late in (0, 1, 2, 3):
             model.cudaemu_set_bulk_late(late)
             for on in (None,) + names:
                 for k in names:
@@ -300,4 +301,5 @@ def test_emulated_kernels_under_both_bulk_copy_schedules(synth, emu_lib):
     finally:
         model.cudaemu_set_bulk_late(0)
     for on in (None,) + names:
-        assert torch.equal(out[(0, on)], out[(1, on)]), on
+        for late in (1, 2, 3):
+            assert torch.equal(out[(0, on)], out[(late, on)]), (on, late)
