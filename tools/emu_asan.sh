@@ -1,6 +1,6 @@
 #!/bin/sh
 # AddressSanitizer pass over the CUDA source under the CPU emulator (TEST INFRASTRUCTURE): every kernel of the default mode
-# (tensor-core model) and of the FFMA mode at two shapes; catches out-of-bounds global / shared-memory accesses.
+# (tensor-core model) and of the FFMA mode at two shapes, plus the optional kernels; catches out-of-bounds global / shared-memory accesses.
 #   sh tools/emu_asan.sh
 set -e
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
@@ -24,5 +24,22 @@ for mode in ("tc_3xf16", "fp32_simt"):
         err = (net((x, mel, t)) - O.denoise(W, x, mel, t)).abs().max().item()
         print(mode, B, Tm, "max|eps - oracle| =", err, flush=True)
         assert err < 5e-5
+# the kernels that are OFF by default, one at a time and all together, and the stand-alone reverse-step update
+net.mode = "tc_3xf16"
+eng = net.engine()
+x, mel = make_inputs(2, 33, 3); t = torch.tensor([[7.413235], [498.0537]])
+ref = O.denoise(W, x, mel, t)
+opts = ("tc_b0", "b2_skipbuf", "kc_stage", "lvc_pipe")
+for on in opts + ("all",):
+    for k in opts:
+        eng.set_option(k, 1 if (on == "all" and k != "b2_skipbuf") or k == on else 0)
+    err = (net((x, mel, t)) - ref).abs().max().item()
+    print("option", on, "max|eps - oracle| =", err, flush=True)
+    assert err < 5e-5
+for k in opts:
+    eng.set_option(k, 0)
+from fastdiff_b200._lib import fd_step
+st = fd_step(); st.coef_eps, st.div, st.sigma, st.add_noise = 0.15, 0.98, 0.05, 1
+xx = torch.randn(4099); eng.reverse_update(xx, torch.randn(4099), st, z=torch.randn(4099)); eng.reverse_update(xx, torch.randn(4099), st, seed=3, draw=1)
 print("ASan pass complete: no errors")
 PY
