@@ -426,8 +426,9 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
     const int skip_in = (!rows || layer == 0) ? 1 : 0, skip_out = (rows && layer < LAYERS - 1) ? 1 : 0;
     // a small grid on purpose: every group then walks a chunk of several tiles (carried halo rows, kernel reuse, prefetch one tile ahead)
     int grid = (tiles + 5) / 6; if (grid < 1) grid = 1; if (grid > 8) grid = 8;
-    if (blk == 2 && h->lvc_pipe && !b2_skip_rows) {
-        FD_LAUNCH(k_lvc_layer_p, dim3(grid), dim3(512), LP_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l);
+    if (blk == 2 && h->lvc_pipe && (!b2_skip_rows || layer > 0)) {
+        if (b2_skip_rows) { auto k = k_lvc_layer_p<true>;  FD_LAUNCH(k, dim3(grid), dim3(512), LP_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, skip_out); }
+        else              { auto k = k_lvc_layer_p<false>; FD_LAUNCH(k, dim3(grid), dim3(512), LP_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0); }
         FD_CHECK_LAUNCH(h, "k_lvc_layer_p");
         return FD_OK;
     }

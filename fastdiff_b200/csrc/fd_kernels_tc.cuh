@@ -2518,9 +2518,12 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (blk == 0) return 0;   // hop 8: stays on the SIMT kernel
-    if (mode == FD_MODE_TC_3XF16 && blk == 2 && b2_pipe && !b2_skip_rows) {   // experimental option "lvc_pipe": software-pipelined tile walk
+    // experimental option "lvc_pipe": software-pipelined tile walk; together with "b2_skipbuf" for the layers whose input rows already
+    // carry the skip (1..3; layer 0 loads the skip tile and runs the block-1 flavour below)
+    if (mode == FD_MODE_TC_3XF16 && blk == 2 && b2_pipe && (!b2_skip_rows || layer > 0)) {
         if (!s->b2p_attr_set) {
-            cudaError_t ea = cudaFuncSetAttribute(k_lvc_layer_p, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM_BYTES);
+            cudaError_t ea = cudaFuncSetAttribute(k_lvc_layer_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM_BYTES);
+            if (ea == cudaSuccess) ea = cudaFuncSetAttribute(k_lvc_layer_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM_BYTES);
             if (ea != cudaSuccess) { err = std::string("k_lvc_layer_p: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
             s->b2p_attr_set = 1;
         }
@@ -2531,7 +2534,8 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
         hp.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
         const float inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * 2 + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
         const int tiles = B * ((T + LT_TT - 1) / LT_TT), per = (tiles + 1) / 2, grid = per < s->sm_count ? per : s->sm_count;
-        k_lvc_layer_p<<<grid, 512, LP_SMEM_BYTES, st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l);
+        if (b2_skip_rows) k_lvc_layer_p<true><<<grid, 512, LP_SMEM_BYTES, st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, layer < LAYERS - 1 ? 1 : 0);
+        else              k_lvc_layer_p<false><<<grid, 512, LP_SMEM_BYTES, st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_p failed: ") + cudaGetErrorString(e); return -3; }
         ++*launches;

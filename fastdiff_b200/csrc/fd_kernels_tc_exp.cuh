@@ -26,10 +26,15 @@ constexpr int LP_SLOT = 2 * LH_A_BYTES + 2 * LH_XS_BYTES + LH_LW_BYTES;        /
 constexpr int LP_SMALL = 2 * 256 + LT_AU * 4;                                  // lbias x 2 | audio
 constexpr int LP_SMEM_BYTES = 2 * (LP_SLOT + LP_SMALL) + LH_CW_BYTES + (7 * C + C + C + C) * 4 + 2 * 512 + 2 * 8 * 8 + 16 + 1024;
 
+// ROWS = true: the flavour for layers 1..3 under option "b2_skipbuf" -- the input rows already carry the skip (added by the previous
+// layer's epilogue), so P1 is load / lrelu / split only, and the epilogue adds the (B,T,32) skip rows read from global memory for the
+// next layer when skip_out is set.  ROWS = false: skip = the audio, first_conv recomputed on the way in (the default arithmetic).
+template <bool ROWS>
 __global__ void __launch_bounds__(512, 1)
 k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
-              float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l) {
+              float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l, int skip_out_rt) {
     constexpr int HOP = 256, GROUPS = 2, GT = 256;
+    const bool skip_out = ROWS && skip_out_rt != 0;
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* cw = smem + GROUPS * LP_SLOT;                 // [3 taps][32 rows][128 B]
@@ -58,8 +63,8 @@ k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     {
         const float4* src = reinterpret_cast<const float4*>(p.cw16);
         for (int i = tid; i < LH_CW_BYTES / 16; i += GT * GROUPS) reinterpret_cast<float4*>(cw)[i] = src[i];
-        if (tid < 7 * C) fw_s[tid] = p.first_w[tid];
-        if (tid < C) { fb_s[tid] = p.first_b[tid]; cb_s[tid] = p.conv_b[tid]; cbs_s[tid] = p.conv_b[tid] * S16_ACT; }
+        if (tid < 7 * C) fw_s[tid] = ROWS ? 0.f : p.first_w[tid];
+        if (tid < C) { fb_s[tid] = ROWS ? 0.f : p.first_b[tid]; cb_s[tid] = p.conv_b[tid]; cbs_s[tid] = p.conv_b[tid] * S16_ACT; }
     }
     fence_async_smem();
     tc_fence_before();
@@ -87,10 +92,10 @@ k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         const int i0 = max(0, 32 - t0), i1 = min(LT_AU, T - t0 + 32);
         uint32_t bytes = 0;
         if (ar1 > ar0) bytes += (uint32_t)(ar1 - ar0) * 128u;
-        if (i1 > i0) bytes += (uint32_t)(i1 - i0) * 4u;
+        if (!ROWS && i1 > i0) bytes += (uint32_t)(i1 - i0) * 4u;
         mbar_expect_tx(&bar[2], bytes);
         if (ar1 > ar0) bulk_g2s(slot + s * LH_A_BYTES + ar0 * 128, x_in + ((size_t)b * T + (t0 - 28 + ar0)) * C, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
-        if (i1 > i0) bulk_g2s(au_s + i0, skip + (size_t)b * T + (t0 - 32 + i0), (uint32_t)(i1 - i0) * 4u, &bar[2]);
+        if (!ROWS && i1 > i0) bulk_g2s(au_s + i0, skip + (size_t)b * T + (t0 - 32 + i0), (uint32_t)(i1 - i0) * 4u, &bar[2]);
     };
     auto issue_lw = [&](int tile, int s, bool keep_lw) {   // predicted kernels -> LW (unless the frame is already there), biases -> lbias[s]   (bar 3)
         const int b = tile / ntt, t0 = (tile % ntt) * LT_TT, f = t0 / HOP;
@@ -108,15 +113,15 @@ k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     auto phase1 = [&](int t0, int s) {
         unsigned char* a_t = slot + s * LH_A_BYTES;
         unsigned char* xs_t = slot + 2 * LH_A_BYTES + s * LH_XS_BYTES;
-        if (gt < LT_AU) { const int pos = t0 - 32 + gt; if (pos < 0 || pos >= T) au_s[gt] = 0.f; }   // the first conv zero-pads
-        group_sync(1 + g, GT);
         float fwr[7][4], fbr[4];
+        if (!ROWS) {
+            if (gt < LT_AU) { const int pos = t0 - 32 + gt; if (pos < 0 || pos >= T) au_s[gt] = 0.f; }   // the first conv zero-pads
+            group_sync(1 + g, GT);
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const float4 w4 = *reinterpret_cast<const float4*>(fw_s + k * C + c4 * 4);
-            fwr[k][0] = w4.x; fwr[k][1] = w4.y; fwr[k][2] = w4.z; fwr[k][3] = w4.w;
-        }
-        {
+            for (int k = 0; k < 7; ++k) {
+                const float4 w4 = *reinterpret_cast<const float4*>(fw_s + k * C + c4 * 4);
+                fwr[k][0] = w4.x; fwr[k][1] = w4.y; fwr[k][2] = w4.z; fwr[k][3] = w4.w;
+            }
             const float4 b4 = *reinterpret_cast<const float4*>(fb_s + c4 * 4);
             fbr[0] = b4.x; fbr[1] = b4.y; fbr[2] = b4.z; fbr[3] = b4.w;
         }
@@ -133,7 +138,7 @@ k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             const int ar = r_lo + prow + i * (GT / 8), t = t0 - 28 + ar;
             const bool active = ar < r_hi;
             float4 pre = xv[i];   // zero outside [0,T)
-            if (active && t >= 0 && t < T) {
+            if (!ROWS && active && t >= 0 && t < T) {
                 float4 sk = make_float4(fbr[0], fbr[1], fbr[2], fbr[3]);
 #pragma unroll
                 for (int k = 0; k < 7; ++k) {
@@ -239,9 +244,13 @@ k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restr
         const int q = gw & 3, part = gw >> 2;
         const int r = q * 32 + lane, t = t0 + r;
         const size_t row = ((size_t)b * T + (t < T ? t : 0)) * C + part * 16;
-        float4 xs[4];
+        float4 xs[4], so[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) xs[c] = *reinterpret_cast<const float4*>(xs_t + r * 128 + (((part * 4 + c) ^ (r & 7)) << 4));
+        for (int c = 0; c < 4; ++c) {
+            xs[c] = *reinterpret_cast<const float4*>(xs_t + r * 128 + (((part * 4 + c) ^ (r & 7)) << 4));
+            so[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (skip_out) so[c] = *reinterpret_cast<const float4*>(skip + row + c * 4);
+        }
         mbar_wait(&bar[1], ph);
         tc_fence_after();
         after_wait();
@@ -259,6 +268,9 @@ k_lvc_layer_p(LvcHParams p, const float* __restrict__ x_in, const float* __restr
                 o4.y = xs[c].y + gate_st(fmaf(__uint_as_float(zs[c * 4 + 1]), inv_l, lb[c * 4 + 1]), fmaf(__uint_as_float(zt[c * 4 + 1]), inv_l, lb[32 + c * 4 + 1]));
                 o4.z = xs[c].z + gate_st(fmaf(__uint_as_float(zs[c * 4 + 2]), inv_l, lb[c * 4 + 2]), fmaf(__uint_as_float(zt[c * 4 + 2]), inv_l, lb[32 + c * 4 + 2]));
                 o4.w = xs[c].w + gate_st(fmaf(__uint_as_float(zs[c * 4 + 3]), inv_l, lb[c * 4 + 3]), fmaf(__uint_as_float(zt[c * 4 + 3]), inv_l, lb[32 + c * 4 + 3]));
+                if (skip_out) {   // the next layer's "x += audio_down": (x + gate) + skip, the reference's rounding sequence
+                    o4.x = __fadd_rn(o4.x, so[c].x); o4.y = __fadd_rn(o4.y, so[c].y); o4.z = __fadd_rn(o4.z, so[c].z); o4.w = __fadd_rn(o4.w, so[c].w);
+                }
                 *reinterpret_cast<float4*>(x_out + row + c * 4) = o4;
             }
         }

@@ -272,6 +272,8 @@ def test_emulated_block2_pipelined_tile_walk_option(synth, emu_lib, B, Tm):
     assert (eps1 - O.denoise(W, x, mel, t)).abs().max() < 5e-5
     if B > 1:      # an item alone = the same item inside the batch, bitwise
         assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), eps1[1:2])
+    eng.set_option("b2_skipbuf", 1)     # combined: layer 0 loads the skip tile (k_lvc_layer_h<256, false, 2>), layers 1..3 run k_lvc_layer_p<true>
+    assert torch.equal(net((x, mel, t)), eps0)
 
 
 def test_emulated_kernels_under_all_async_schedules(synth, emu_lib):
@@ -294,12 +296,12 @@ def test_emulated_kernels_under_all_async_schedules(synth, emu_lib):
     try:
         for late in (0, 1, 2, 3):
             model.cudaemu_set_bulk_late(late)
-            for on in (None,) + names:
+            for on in (None,) + names + ("pipe+rows",):
                 for k in names:
-                    eng.set_option(k, 1 if k == on else 0)
+                    eng.set_option(k, 1 if (k == on or (on == "pipe+rows" and k in ("lvc_pipe", "b2_skipbuf"))) else 0)
                 out[(late, on)] = net((x, mel, t))
     finally:
         model.cudaemu_set_bulk_late(0)
-    for on in (None,) + names:
+    for on in (None,) + names + ("pipe+rows",):
         for late in (1, 2, 3):
             assert torch.equal(out[(0, on)], out[(late, on)]), (on, late)

@@ -19,7 +19,8 @@ timeout 120 $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
 for o in tc_b0=1 tc_b0=2 b2_skipbuf=1 kc_stage=1 lvc_pipe=1; do
     timeout 120 $B --opt $o > "$OUT/bench_$o.json" 2> "$OUT/bench_$o.err"; echo "$o rc=$?" >> "$OUT/bench_rc.log"
 done
-timeout 120 $B --opt tc_b0=1 --opt b2_skipbuf=1 --opt kc_stage=1 > "$OUT/bench_all_options.json" 2> "$OUT/bench_all_options.err"
+timeout 120 $B --opt b2_skipbuf=1 --opt lvc_pipe=1 > "$OUT/bench_pipe_rows.json" 2> "$OUT/bench_pipe_rows.err"
+timeout 120 $B --opt tc_b0=1 --opt b2_skipbuf=1 --opt lvc_pipe=1 --opt kc_stage=1 > "$OUT/bench_all_options.json" 2> "$OUT/bench_all_options.err"
 
 for d in LH_ROW_SPREAD FINAL_BATCH_LOADS FD_VEC256 LH_PREFETCH_EPI LH_NO_END_SYNC; do
     FD_NVCC_EXTRA="-D$d=1" python -c "import __graft_entry__ as g; g.build_cuda(force=True)" > "$OUT/build_$d.log" 2>&1 || continue
