@@ -12,7 +12,7 @@ thread_local unsigned char* t_dyn_smem = nullptr;
 thread_local size_t t_dyn_smem_bytes = 0;
 thread_local unsigned t_linear_tid = 0, t_cta_rank = 0;
 thread_local unsigned t_cta_serial = 0;
-int g_bulk_late = 0;
+int g_bulk_late = getenv("FD_EMU_SCHEDULE") ? atoi(getenv("FD_EMU_SCHEDULE")) & 3 : 0;   // see tcemu.h; the whole suite can be run under a late schedule this way
 long long g_late_ops[2] = {0, 0};
 
 namespace {
