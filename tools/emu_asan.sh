@@ -30,9 +30,9 @@ eng = net.engine()
 x, mel = make_inputs(2, 33, 3); t = torch.tensor([[7.413235], [498.0537]])
 ref = O.denoise(W, x, mel, t)
 opts = ("tc_b0", "b2_skipbuf", "kc_stage", "lvc_pipe")
-for on in opts + ("all",):
+for on in opts + ("all",):          # "all" includes lvc_pipe + b2_skipbuf = k_lvc_layer_p<true> for layers 1..3
     for k in opts:
-        eng.set_option(k, 1 if (on == "all" and k != "b2_skipbuf") or k == on else 0)
+        eng.set_option(k, 1 if on == "all" or k == on else 0)
     err = (net((x, mel, t)) - ref).abs().max().item()
     print("option", on, "max|eps - oracle| =", err, flush=True)
     assert err < 5e-5
