@@ -1,7 +1,7 @@
 """Round-2 GPU check of the options that are OFF by default and have only run on the CPU model so far (NOT collected by pytest on
 purpose; one option per process, each under its own `timeout`, so that a kernel that hangs or faults costs its own step only):
 
-    for o in tc_b0 b2_skipbuf kc_stage lvc_pipe; do timeout 150 python tests/gpu_options_check.py $o; done
+    for o in tc_b0 b2_skipbuf kc_stage lvc_pipe pipe_rows; do timeout 150 python tests/gpu_options_check.py $o; done
 
 Per option: parity at small shapes (eps against the oracle and against the default path; bitwise where the option promises the same bits),
 then the per-class kernel times at config 2 (B = 8, T' = 861) with the option off and on.  `--emu` runs the same script on the CPU
@@ -16,8 +16,8 @@ import fastdiff_b200 as fb  # noqa: E402
 from fastdiff_b200.synthetic import make_inputs, make_state_dict  # noqa: E402
 from oracle import fastdiff_oracle as O  # noqa: E402
 
-VALUES = {"tc_b0": (1, 2), "b2_skipbuf": (1,), "kc_stage": (1,), "lvc_pipe": (1,)}
-BITWISE = {"tc_b0": False, "b2_skipbuf": True, "kc_stage": True, "lvc_pipe": True}
+VALUES = {"tc_b0": (1, 2), "b2_skipbuf": (1,), "kc_stage": (1,), "lvc_pipe": (1,), "pipe_rows": (1,)}   # pipe_rows = lvc_pipe + b2_skipbuf
+BITWISE = {"tc_b0": False, "b2_skipbuf": True, "kc_stage": True, "lvc_pipe": True, "pipe_rows": True}
 
 
 def main():
@@ -27,6 +27,10 @@ def main():
         print(__doc__)
         return 2
     opt = args[0]
+
+    def set_opt(eng, v):
+        for key in (("lvc_pipe", "b2_skipbuf") if opt == "pipe_rows" else (opt,)):
+            eng.set_option(key, v)
     dev = torch.device("cpu" if emu else "cuda:0")
     sd = make_state_dict(1234, g_jitter=0.1)
     W = O.fold_weight_norm(sd)
@@ -46,13 +50,13 @@ def main():
         e0 = net((xd, md, td)).cpu()
         eng = net.engine()
         for v in VALUES[opt]:
-            eng.set_option(opt, v)
+            set_opt(eng, v)
             e1 = net((xd, md, td)).cpu()
             eng.set_option("stop_after", 3)
             net((xd, md, td))
             l0 = eng.debug_read("lvc0", B, Tm).reshape(B, 32, Tm * 8).cpu()
             eng.set_option("stop_after", 99)
-            eng.set_option(opt, 0)
+            set_opt(eng, 0)
             res = {"eps_default_vs_oracle": (e0 - ref).abs().max().item(), "eps_option_vs_oracle": (e1 - ref).abs().max().item(),
                    "option_vs_default": (e1 - e0).abs().max().item(), "bitwise": bool(torch.equal(e0, e1)),
                    "lvc0_vs_oracle": (l0 - inter["lvc0"]).abs().max().item()}
@@ -65,7 +69,7 @@ def main():
     eng = net.engine()
     n_rep = 1 if emu else 5
     for v in (0,) + VALUES[opt]:
-        eng.set_option(opt, v)
+        set_opt(eng, v)
         for _ in range(0 if emu else 3):
             net((x, mel, t))
         sync()
@@ -76,7 +80,7 @@ def main():
         rep = eng.timing_report()
         eng.timing_enable(False)
         print(f"{opt}={v} kernel ms per evaluation:", json.dumps({k: round(val["ms"] / n_rep, 4) for k, val in rep.items() if val["n"]}), flush=True)
-    eng.set_option(opt, 0)
+    set_opt(eng, 0)
     print(opt, "PARITY", "OK" if ok else "FAILED")
     return 0 if ok else 1
 
