@@ -1,6 +1,6 @@
 #!/bin/bash
-# First GPU call of round 2 (run from the repo root through gpurun, ~12 GPU-minutes):
-#   gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
+# First GPU call of round 2 (run from the repo root through gpurun, ~25 GPU-minutes):
+#   gpurun --timeout 2400 -- 'bash tools/round2_first_call.sh'
 # 1. the GPU test-suite on the default path; 2. parity + per-class kernel times of the run-time options that are OFF by default
 # (tc_b0, b2_skipbuf, kc_stage, lvc_pipe; tests/gpu_options_check.py); 3. bench.py for the default and for each option; 4. one rebuild + bench per
 # compile-time switch.  Everything lands in gpurun_out/r2_first/.  Each step has its own timeout: an experimental kernel that hangs
@@ -25,7 +25,7 @@ timeout 120 $B --opt tc_b0=1 --opt b2_skipbuf=1 --opt lvc_pipe=1 --opt kc_stage=
 for d in LH_ROW_SPREAD FINAL_BATCH_LOADS FD_VEC256 LH_PREFETCH_EPI LH_NO_END_SYNC; do
     FD_NVCC_EXTRA="-D$d=1" python -c "import __graft_entry__ as g; g.build_cuda(force=True)" > "$OUT/build_$d.log" 2>&1 || continue
     timeout 120 $B > "$OUT/bench_$d.json" 2> "$OUT/bench_$d.err"; echo "$d rc=$?" >> "$OUT/bench_rc.log"
-    timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tensor_core_mode_vs_oracle or full_size" > "$OUT/parity_$d.log" 2>&1
+    timeout 200 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "(tensor_core_mode_vs_oracle and tc_3xf16) or full_size" > "$OUT/parity_$d.log" 2>&1
 done
 python -c "import __graft_entry__ as g; g.build_cuda(force=True)" > "$OUT/build_default.log" 2>&1
 grep -h '"value"' "$OUT"/bench_*.json | python -c "
