@@ -277,3 +277,108 @@ def test_wav_int16_encode_on_device_bitwise(synth, cuda_lib):
         a *= 32767
         ref.append(a.astype(np.int16))
     assert np.array_equal(got, np.stack(ref))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Parity at the BENCHMARKED shapes (round-1 verdict, weak #1): the tile walk of the tensor-core LVC kernels depends on the number of
+# tiles per tile-group, so the carried-halo-row branch that dominates at T' = 861 is only exercised against truth at these sizes.
+# ---------------------------------------------------------------------------------------------------------------------------------
+def _oracle_items(O, W, x, mel, t, items):
+    """Oracle eps for selected batch items only (every op of the path is per item)."""
+    idx = torch.tensor(items)
+    return O.denoise(W, x[idx], mel[idx], t[idx])
+
+
+@gpu
+@pytest.mark.parametrize("mode", ["tc_3xf16", "fp32_simt"])
+def test_benchmark_shape_1x861_vs_oracle(synth, cuda_lib, mode):
+    """BASELINE.json configs[1] utterance length (10 s, T' = 861), one item: eps against the oracle."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    x, mel = make_inputs(1, 861, 31)
+    t = torch.tensor([[74.99228]])
+    ref = O.denoise(W, x, mel, t)
+    net = _net(sd, mode)
+    eps = net((x.cuda(), mel.cuda(), t.cuda())).cpu()
+    err = (eps - ref).abs().max().item()
+    assert err < EPS_TOL, err
+
+
+@gpu
+@pytest.mark.parametrize("mode", ["tc_3xf16", "fp32_simt"])
+def test_benchmark_shape_8x861_items_vs_oracle(synth, cuda_lib, mode):
+    """BASELINE.json configs[1] exactly (B = 8 x 10 s): items 0 and 7 of the batch against the oracle (the oracle is run on those two
+    items only), per-item diffusion steps that differ."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    B, Tm = 8, 861
+    x, mel = make_inputs(B, Tm, 32)
+    t = torch.tensor([7.413235, 23.46759, 74.99228, 498.0537, 7.413235, 23.46759, 74.99228, 498.0537]).reshape(B, 1)
+    ref = _oracle_items(O, W, x, mel, t, [0, 7])
+    net = _net(sd, mode)
+    eps = net((x.cuda(), mel.cuda(), t.cuda())).cpu()
+    for j, it in enumerate((0, 7)):
+        err = (eps[it] - ref[j]).abs().max().item()
+        assert err < EPS_TOL, (it, err)
+
+
+@gpu
+def test_long_utterance_1x2583_vs_oracle(synth, cuda_lib):
+    """30 s utterance (T' = 2583, BASELINE.json configs[4] sweep end), default mode."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    x, mel = make_inputs(1, 2583, 33)
+    t = torch.tensor([[23.46759]])
+    ref = O.denoise(W, x, mel, t)
+    eps = _net(sd)((x.cuda(), mel.cuda(), t.cuda())).cpu()
+    err = (eps - ref).abs().max().item()
+    assert err < EPS_TOL, err
+
+
+@gpu
+def test_batch64_items_vs_oracle(synth, cuda_lib):
+    """BASELINE.json configs[3] per-node batch on ONE GPU (B = 64 x 10 s, ~20 GB of workspace): two items against the oracle."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    B, Tm = 64, 861
+    x, mel = make_inputs(B, Tm, 34)
+    t = torch.full((B, 1), 74.99228)
+    t[63, 0] = 498.0537
+    ref = _oracle_items(O, W, x, mel, t, [5, 63])
+    net = _net(sd)
+    eps = net((x.cuda(), mel.cuda(), t.cuda()))
+    got = eps[[5, 63]].cpu()
+    del eps
+    net.engine()._ws.clear()
+    torch.cuda.empty_cache()
+    for j in range(2):
+        err = (got[j] - ref[j]).abs().max().item()
+        assert err < EPS_TOL, (j, err)
+
+
+@gpu
+def test_full_schedule_n1000_vs_oracle(synth, cuda_lib):
+    """BASELINE.json configs[2] loop length (N = 1000, the training schedule linspace(1e-6, 0.01, 1000), task/FastDiff.py:76-77) on a
+    tiny shape (1 x 4 frames) under the reference's RNG stream: every 100th x_t and x_0 against the oracle.  The N-step loop is
+    chaotic only through eps, whose per-step error is ~1e-5, damped by coef_eps <= 0.1: the accumulated bound stays at 5e-4."""
+    import fastdiff_b200 as fb
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    B, Tm = 1, 4
+    _, mel = make_inputs(B, Tm, 35)
+    beta = torch.linspace(1e-6, 0.01, 1000)
+    dh = fb.compute_hyperparams_given_schedule(beta.clone())
+    torch.manual_seed(13)
+    ref = O.sample(W, (B, 1, Tm * 256), dh, beta.clone(), mel, return_sequence=True)
+    torch.manual_seed(13)
+    net = _net(sd)
+    got = fb.sampling_given_noise_schedule(net, (B, 1, Tm * 256), dh, beta.clone(), condition=mel.cuda(), return_sequence=True)
+    assert len(got) == len(ref) == 1001
+    for i in list(range(0, 1001, 100)) + [1000]:
+        err = (got[i].cpu() - ref[i]).abs().max().item()
+        assert err < 5e-4, (i, err)

@@ -10,7 +10,7 @@ OUT=gpurun_out/r2_first
 mkdir -p "$OUT"
 B="python bench.py --steps 10 --warmup 3 --no-cpu"
 
-timeout 600 python -m pytest tests -m gpu -x -q > "$OUT/gpu_tests.log" 2>&1; echo "pytest rc=$?" >> "$OUT/gpu_tests.log"
+timeout 900 python -m pytest tests -m gpu -q > "$OUT/gpu_tests.log" 2>&1; echo "pytest rc=$?" >> "$OUT/gpu_tests.log"
 for o in tc_b0 b2_skipbuf kc_stage lvc_pipe pipe_rows; do
     timeout 150 python tests/gpu_options_check.py $o > "$OUT/options_check_$o.log" 2>&1; echo "rc=$?" >> "$OUT/options_check_$o.log"
 done
