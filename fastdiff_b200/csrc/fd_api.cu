@@ -31,7 +31,7 @@ struct fd_handle {
     int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
     int emu_gemm_tc = 1;         // emulation build, mode tc_3xf16: 1 = the CTA-pair GEMM on the tcgen05 model, 0 = FFMA GEMM + k_emu_kern_to_pieces
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
-    int tc_b0 = 0;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h): 1 = the GEMM
+    int tc_b0 = 1;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h): 1 = the GEMM
                                  // writes the block's kernels as fp16 pieces (k_kc_gemm_tc2<true, 16, true>), 2 = converter pass (k_b0_panel_to_pieces)
     int lvc_pipe = 0;            // EXPERIMENTAL (mode tc_3xf16, option "lvc_pipe"): LVC block 2 with software-pipelined tiles (k_lvc_layer_p)
     int kc_stage = 0;            // EXPERIMENTAL (mode tc_3xf16, option "kc_stage"): kernel_conv GEMM epilogue through shared memory + bulk stores

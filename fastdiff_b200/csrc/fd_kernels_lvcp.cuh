@@ -1,0 +1,460 @@
+// K11 + K12 + K13 for LVC blocks 1 and 2, mode tc_3xf16, "P protocol": one warp-specialised, software-pipelined kernel per LVC layer
+// (modules.py:208-217 -- x += skip; y = lrelu(conv_dil(lrelu(x))); y = LVC(y, kernels, bias); x = x + sigmoid(y[:32]) * tanh(y[32:])).
+//
+// What is different from k_lvc_layer_h (fd_kernels_tc.cuh), which it replaces on the default path:
+//   * THE STATE TRAVELS AS OPERAND PIECES.  Between the layers of a block the activation z = x + skip is not stored as fp32 rows but as
+//     the tcgen05 A operand of the next layer's dilated conv: per time step one 128-byte row [32 ch hi | 32 ch lo] of fp16 pieces of
+//     16 * lrelu_0.2(z), 16-byte chunk c at position c ^ (t & 7) -- the SWIZZLE_128B image of a tile whose row 0 is a multiple of 8.
+//     A layer therefore bulk-copies its input rows straight into the MMA tile: the whole "phase 1" of the old kernel (load raw rows,
+//     add skip, lrelu, split, store: 39 % of its instructions, and its shared-memory bank conflicts) is gone, and the skip of block 2
+//     (first_conv(audio), 7 taps) is evaluated once per produced row instead of once per loaded row (184 per 128).  The residual base
+//     z of the gate epilogue is recovered from the same pieces: z = (hi + lo) / 16, times 5 where negative (lrelu is invertible);
+//     hi + lo carries 22 significant bits of z, the 2 bits lost against fp32 cost ~2e-6 on eps (measured against fp64: at the fp32
+//     noise floor of the reference itself, tests/test_f16_pieces.py).  The first layer's rows are written by the upsampling kernel
+//     (k_upsample_tc<R, true>), the last layer of a block writes plain fp32 rows for its consumer.
+//   * Rows outside [0, T) come from memory: the piece buffers carry 32 zero rows before the first item and 64 between items
+//     (k_zero_pads), so the loads need no clamping and the conv sees the reference's zero padding.
+//   * WARP SPECIALISATION.  22 warps: 4 conv-epilogue warps (TMEM -> lrelu -> pieces -> Y tile), 16 gate-epilogue warps (TMEM -> gate,
+//     residual, skip, lrelu, pieces -> output), one loader (cp.async.bulk, 3 input stages + 2 kernel stages), one MMA issuer.  Conv
+//     MMAs of tile n+1 are issued before the LVC MMAs of tile n; accumulators, Y tiles and output staging are double-buffered, so the
+//     tensor pipe, both epilogues and the loads of three consecutive tiles overlap (the old kernel ran its five phases back to back
+//     per 8-warp group: tensor pipe 16 % active, issue slots 42 %).
+//   * Block 2 stages its output rows in shared memory and writes them with one cp.async.bulk per tile (whole 16 KB, no half-filled
+//     sectors); block 1 (hop 64: two frames of predicted kernels per tile fill the shared memory) stores 16-byte chunks directly.
+// Tile = 128 time steps, walked in DESCENDING order inside a CTA's contiguous chunk so that conv rows 128, 129 (needed by the last LVC
+// taps) are Y rows 0, 1 of the tile processed just before (carried in 512 B of smem); chunk starts and utterance ends take them from a
+// second MMA pass over A rows +128 -- the same instruction sequence, hence the same bits whatever the chunking.
+// Compiles for the CPU fibre emulator too (tests/cudaemu).
+#pragma once
+
+namespace fd {
+
+constexpr int LP_TT = 128;
+constexpr int LP_HEAD_ROWS = 32;                 // zero rows before item 0
+constexpr int LP_PAD_ROWS = 64;                  // zero rows after every item (32 tail + 32 head of the next item)
+constexpr int LP_SLACK_ROWS = 192;               // readable (not necessarily zero) rows after the last pad: the last tile's window
+constexpr int LP_STAGE_BYTES = 26624;            // 192 A rows (24576) | lbias 2 x 256 | audio window 136 floats (544) | pad -> multiple of 1024
+constexpr int LP_NA = 3;
+constexpr int LP_Y_BYTES = 17408;                // 136 rows x 128 B (130 used)
+constexpr int LP_OUT_BYTES = 16384;              // 128 output rows
+constexpr int LP_CW_BYTES = 3 * C * 128;         // 12288
+constexpr int LP_AU = 136;                       // audio positions t0-4 .. t0+131
+constexpr int LP_THREADS = 704;                  // warps 0-3 conv epilogue, 4-19 gate epilogue, 20 loader, 21 MMA issuer
+constexpr int LP_E2_THREADS = 512;
+
+__host__ __device__ inline size_t lp_rows(int B, int T) { return (size_t)LP_HEAD_ROWS + (size_t)B * (T + LP_PAD_ROWS) + LP_SLACK_ROWS; }
+__host__ __device__ inline size_t lp_row_of(int b, int T, int t) { return (size_t)LP_HEAD_ROWS + (size_t)b * (T + LP_PAD_ROWS) + t; }
+
+template <int HOP> __host__ __device__ constexpr int lp_nf() { return HOP >= LP_TT ? 1 : LP_TT / HOP; }
+template <int HOP> __host__ __device__ constexpr int lp_smem_bytes() {
+    return LP_NA * LP_STAGE_BYTES + 2 * LP_Y_BYTES + 2 * lp_nf<HOP>() * 24576 + (HOP == 256 ? 2 * LP_OUT_BYTES : 0) + LP_CW_BYTES +
+           (7 * C + C + C) * 4 + 512 + 24 * 8 + 64 + 1024;
+}
+
+struct LvcPParams {
+    const float* cw16;       // [3 taps][32 co][128 B] SWIZZLE_128B image of this layer's dilated conv (LBn_CONV_F16)
+    const float* conv_b;     // [32]
+    const float* first_w;    // [7][32]  (hop 256: skip = first_conv(audio))
+    const float* first_b;    // [32]
+    const float* p_in;       // padded piece rows of z = x + skip (input of this layer)
+    const float* skip;       // hop 256: audio (B, T); hop 64: skip rows (B, T, 32) fp32
+    const float* kern;       // this layer's slice of the predicted kernels: per (b, frame) at stride KCN floats
+    float* p_out;            // padded piece rows of the next layer's input, or nullptr (last layer of a block)
+    float* f_out;            // fp32 rows (B, T, 32) of the block output (last layer), or nullptr
+    unsigned int* sat;       // sticky flag: an fp16 piece saturated (|16 * activation| > 65504); may be nullptr
+    int B, T, Tm, dil;
+    float inv_c, inv_l;
+};
+
+// zero rows of a padded piece buffer: block 0 -> the 32 head rows, block i >= 1 -> the 64 rows after item i - 1
+__global__ void __launch_bounds__(256) k_zero_pads(float* __restrict__ buf, int B, int T) {
+    const int i = blockIdx.x;
+    const size_t row0 = i == 0 ? 0 : (size_t)LP_HEAD_ROWS + (size_t)(i - 1) * (T + LP_PAD_ROWS) + T;
+    const int nrows = i == 0 ? LP_HEAD_ROWS : LP_PAD_ROWS;
+    float4* dst = reinterpret_cast<float4*>(buf + row0 * C);
+    for (int k = threadIdx.x; k < nrows * 8; k += 256) dst[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// 8 values that already carry the x16 prescale -> one 16-byte chunk of hi pieces and one of lo pieces; m tracks max |v| (saturation guard)
+__device__ __forceinline__ void lp_split8(const float (&v)[8], uint4& hi, uint4& lo, float& m) {
+    uint2 h0, l0, h1, l1;
+    split4_f16_pre(v[0], v[1], v[2], v[3], h0, l0);
+    split4_f16_pre(v[4], v[5], v[6], v[7], h1, l1);
+    hi = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    lo = make_uint4(l0.x, l0.y, l1.x, l1.y);
+    m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3]))),
+                       fmaxf(fmaxf(fabsf(v[4]), fabsf(v[5])), fmaxf(fabsf(v[6]), fabsf(v[7])))));
+}
+
+template <int HOP>
+__global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
+    constexpr int NF = lp_nf<HOP>();
+    constexpr bool STAGE_OUT = (HOP == 256);
+    constexpr int W_BYTES = NF * 24576;
+    constexpr uint32_t LACC0 = 128, LSTRIDE = NF * 64;
+    constexpr uint32_t TCOLS = (LACC0 + 2 * LSTRIDE) <= 256 ? 256 : 512;
+    FD_DYN_SMEM(unsigned char, smem_raw);
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* a_st = smem;                                        // [3][LP_STAGE_BYTES]
+    unsigned char* y_t = a_st + LP_NA * LP_STAGE_BYTES;                // [2][LP_Y_BYTES]
+    unsigned char* w_t = y_t + 2 * LP_Y_BYTES;                         // [2][W_BYTES]
+    unsigned char* o_t = w_t + 2 * W_BYTES;                            // [2][LP_OUT_BYTES] (STAGE_OUT)
+    unsigned char* cw = o_t + (STAGE_OUT ? 2 * LP_OUT_BYTES : 0);      // [3 taps][32 rows][128 B]
+    float* fw_s = (float*)(cw + LP_CW_BYTES);                          // [7][32]
+    float* fb_s = fw_s + 7 * C;                                        // [32]
+    float* cbs_s = fb_s + C;                                           // [32] conv bias * S16_ACT
+    unsigned char* carry = (unsigned char*)(cbs_s + C);                // [2][256 B]: Y rows 0, 1 of the previous tile
+    uint64_t* bars = (uint64_t*)(carry + 512);
+    uint64_t* a_full = bars;            // [3] loader -> MMA, gate epilogue (tx)
+    uint64_t* a_free = bars + 3;        // [3] gate epilogue (16 warps) -> loader
+    uint64_t* w_full = bars + 6;        // [2] loader -> MMA (tx)
+    uint64_t* w_free = bars + 8;        // [2] MMA commit -> loader
+    uint64_t* cacc_full = bars + 10;    // [2] conv MMAs committed -> conv epilogue
+    uint64_t* cacc_free = bars + 12;    // [2] conv epilogue (4 warps) -> MMA
+    uint64_t* y_full = bars + 14;       // [2] conv epilogue (4 warps) -> MMA
+    uint64_t* lacc_full = bars + 16;    // [2] LVC MMAs committed -> gate epilogue; also "Y tile free" for the conv epilogue
+    uint64_t* lacc_free = bars + 18;    // [2] gate epilogue (16 warps) -> MMA
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 24);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_free[i], 16); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&w_full[i], 1); mbar_init(&w_free[i], 1);
+            mbar_init(&cacc_full[i], 1); mbar_init(&cacc_free[i], 4);
+            mbar_init(&y_full[i], 4); mbar_init(&lacc_full[i], 1); mbar_init(&lacc_free[i], 16);
+        }
+        mbar_init_fence();
+    }
+    if (warp == 0) tmem_alloc(tmem_base_s, TCOLS);
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.cw16);
+        for (int i = tid; i < LP_CW_BYTES / 16; i += LP_THREADS) reinterpret_cast<float4*>(cw)[i] = src[i];
+        if (tid < 7 * C) fw_s[tid] = HOP == 256 ? p.first_w[tid] : 0.f;
+        if (tid < C) { fb_s[tid] = HOP == 256 ? p.first_b[tid] : 0.f; cbs_s[tid] = p.conv_b[tid] * S16_ACT; }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+    const int B = p.B, T = p.T, Tm = p.Tm, dil = p.dil;
+    const int ntt = (T + LP_TT - 1) / LP_TT, total = B * ntt;
+    const int chunk = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int tile_lo = (int)blockIdx.x * chunk, tile_hi = min(total, tile_lo + chunk);
+    const int ntile = tile_hi > tile_lo ? tile_hi - tile_lo : 0;          // this CTA walks tiles tile_hi-1 .. tile_lo
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+
+    if (warp_u == 20) {
+        // =========================================== loader ===========================================
+        if (elect_one()) {
+            int wc = 0;
+            long long prev_frame = -1;
+            for (int n = 0; n < ntile; ++n) {
+                const int tile = tile_hi - 1 - n, b = tile / ntt, t0 = (tile % ntt) * LP_TT;
+                const int s = n % LP_NA;
+                unsigned char* a = a_st + s * LP_STAGE_BYTES;
+                float* lbias = (float*)(a + 24576);
+                float* au = lbias + 128;
+                mbar_wait(&a_free[s], (uint32_t)(((n / LP_NA) & 1) ^ 1));
+                const int ar0 = 31 - dil, nrows = 130 + 2 * dil;
+                int i0 = 0, i1 = 0;
+                if (HOP == 256) { i0 = t0 == 0 ? 4 : 0; i1 = min(LP_AU, T - t0 + 4); }
+                uint32_t bytes = (uint32_t)nrows * 128u + (uint32_t)(i1 - i0) * 4u;
+#pragma unroll
+                for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) bytes += 256u;
+                mbar_expect_tx(&a_full[s], bytes);
+                bulk_g2s(a + ar0 * 128, p.p_in + (lp_row_of(b, T, t0 - 32 + ar0)) * C, (uint32_t)nrows * 128u, &a_full[s]);
+                if (HOP == 256) bulk_g2s(au + i0, p.skip + (size_t)b * T + (t0 - 4 + i0), (uint32_t)(i1 - i0) * 4u, &a_full[s]);
+#pragma unroll
+                for (int fi = 0; fi < NF; ++fi) {
+                    const int f = t0 / HOP + fi;
+                    if (f < Tm) bulk_g2s(lbias + fi * 64, p.kern + ((size_t)b * Tm + f) * KCN + KK * LVC_OUT, 256u, &a_full[s]);
+                }
+                // predicted kernels: hop 256 -> one frame serves two tiles (walked back to back); hop 64 -> two frames per tile
+                if (HOP == 256) {
+                    const long long frame = (long long)b * Tm + t0 / HOP;
+                    if (frame != prev_frame) {
+                        const int ws = wc & 1;
+                        mbar_wait(&w_free[ws], (uint32_t)(((wc >> 1) & 1) ^ 1));
+                        mbar_expect_tx(&w_full[ws], 24576u);
+                        bulk_g2s(w_t + ws * W_BYTES, p.kern + (size_t)frame * KCN, 24576u, &w_full[ws]);
+                        prev_frame = frame; ++wc;
+                    }
+                } else {
+                    const int ws = n & 1;
+                    mbar_wait(&w_free[ws], (uint32_t)(((n >> 1) & 1) ^ 1));
+                    uint32_t wb = 0;
+#pragma unroll
+                    for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) wb += 24576u;
+                    mbar_expect_tx(&w_full[ws], wb);
+#pragma unroll
+                    for (int fi = 0; fi < NF; ++fi) {
+                        const int f = t0 / HOP + fi;
+                        if (f < Tm) bulk_g2s(w_t + ws * W_BYTES + fi * 24576, p.kern + ((size_t)b * Tm + f) * KCN, 24576u, &w_full[ws]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp_u == 21) {
+        // =========================================== MMA issuer ===========================================
+        constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 64);
+        const uint32_t a_u = smem_u32(a_st), y_u = smem_u32(y_t), w_u = smem_u32(w_t), cw_u = smem_u32(cw);
+        int wc = 0, cur_ws = 0;
+        long long prev_frame = -1;
+        auto lvc_mmas = [&](int m) {     // M2(m): LVC MMAs of the CTA's m-th tile
+            const int tile = tile_hi - 1 - m, b = tile / ntt, t0 = (tile % ntt) * LP_TT;
+            const int ys = m & 1;
+            mbar_wait(&y_full[ys], (uint32_t)((m >> 1) & 1));
+            bool last_use = true;
+            if (HOP == 256) {
+                const long long frame = (long long)b * Tm + t0 / HOP;
+                if (frame != prev_frame) {
+                    cur_ws = wc & 1;
+                    mbar_wait(&w_full[cur_ws], (uint32_t)((wc >> 1) & 1));
+                    prev_frame = frame; ++wc;
+                }
+                if (m + 1 < ntile) {   // the next tile of the walk uses the same frame iff it is (b, tt - 1) with tt odd
+                    const int tn = tile - 1;
+                    last_use = !((tn / ntt) == b && ((tn % ntt) * LP_TT) / HOP == t0 / HOP);
+                }
+            } else {
+                cur_ws = m & 1;
+                mbar_wait(&w_full[cur_ws], (uint32_t)((m >> 1) & 1));
+            }
+            mbar_wait(&lacc_free[ys], (uint32_t)(((m >> 1) & 1) ^ 1));
+            tc_fence_after();
+            uint32_t yt = y_u + (uint32_t)ys * LP_Y_BYTES, wt = w_u + (uint32_t)cur_ws * W_BYTES;
+            FD_OPAQUE2(yt, wt);
+            if (elect_one()) {
+#pragma unroll
+                for (int fi = 0; fi < NF; ++fi) {
+                    if (t0 / HOP + fi < Tm) {
+                        const uint32_t d = tmem_base + LACC0 + (uint32_t)ys * LSTRIDE + fi * 64;
+                        const uint32_t lwb = wt + fi * 24576;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t dah = umma_desc_sw128(yt + k * 128 + j * 32), dal = umma_desc_sw128(yt + k * 128 + 64 + j * 32);
+                                const uint64_t dbh = umma_desc_sw128(lwb + k * 8192 + j * 32), dbl = umma_desc_sw128(lwb + k * 8192 + 64 + j * 32);
+                                umma_f16(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
+                                umma_f16(d, dah, dbl, idesc_lvc, 1u);
+                                umma_f16(d, dal, dbh, idesc_lvc, 1u);
+                            }
+                        }
+                    }
+                }
+                tc_commit(&lacc_full[ys]);
+                if (last_use) tc_commit(&w_free[cur_ws]);
+            }
+            __syncwarp();
+        };
+        for (int n = 0; n < ntile; ++n) {
+            const int tile = tile_hi - 1 - n, tt = tile % ntt;
+            const int s = n % LP_NA, cs = n & 1;
+            const bool have_carry = (n > 0) && (tt != ntt - 1);
+            mbar_wait(&a_full[s], (uint32_t)((n / LP_NA) & 1));
+            mbar_wait(&cacc_free[cs], (uint32_t)(((n >> 1) & 1) ^ 1));
+            tc_fence_after();
+            uint32_t at = a_u + (uint32_t)s * LP_STAGE_BYTES, cwt = cw_u;
+            FD_OPAQUE2(at, cwt);
+            if (elect_one()) {
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    // pass 1 (rows +128): its output rows 0, 1 are conv rows 128, 129; the other rows read past the loaded window and are never used
+                    if (pass == 1 && have_carry) break;
+                    const uint32_t d = tmem_base + (pass ? 64u : 0u) + (uint32_t)cs * 32;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t sh = (uint32_t)(pass * 128 + 31 + (k - 1) * dil) * 128u;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint64_t dah = umma_desc_sw128(at + sh + j * 32), dal = umma_desc_sw128(at + sh + 64 + j * 32);
+                            const uint64_t dbh = umma_desc_sw128(cwt + k * 4096 + j * 32), dbl = umma_desc_sw128(cwt + k * 4096 + 64 + j * 32);
+                            umma_f16(d, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
+                            umma_f16(d, dah, dbl, idesc_conv, 1u);
+                            umma_f16(d, dal, dbh, idesc_conv, 1u);
+                        }
+                    }
+                }
+                tc_commit(&cacc_full[cs]);
+            }
+            __syncwarp();
+            if (n >= 1) lvc_mmas(n - 1);
+        }
+        if (ntile > 0) lvc_mmas(ntile - 1);
+    } else if (warp_u < 4) {
+        // =========================================== conv epilogue (4 warps) ===========================================
+        const int q = warp;                       // TMEM lane quarter
+        const int yr = q * 32 + lane;             // Y row of this thread <-> t = t0 - 1 + yr
+        const float inv_cs = p.inv_c * S16_ACT;
+        float vmax = 0.f;
+        for (int n = 0; n < ntile; ++n) {
+            const int tile = tile_hi - 1 - n, tt = tile % ntt, t0 = tt * LP_TT;
+            const int cs = n & 1;
+            const bool have_carry = (n > 0) && (tt != ntt - 1);
+            unsigned char* yt = y_t + cs * LP_Y_BYTES;
+            mbar_wait(&cacc_full[cs], (uint32_t)((n >> 1) & 1));
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cs * 32, v);
+            tmem_ld_wait();
+            if (n >= 2) mbar_wait(&lacc_full[cs], (uint32_t)(((n >> 1) - 1) & 1));   // the LVC MMAs of tile n-2 have read this Y tile
+            auto emit_row = [&](const uint32_t (&acc)[32], int row, unsigned char* copy_to) {
+                const int t = t0 - 1 + row;
+                const bool in = (t >= 0 && t < T);
+                const int sw = row & 7;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float y[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float a = fmaf(__uint_as_float(acc[c * 8 + e]), inv_cs, cbs_s[c * 8 + e]);
+                        y[e] = in ? fmaxf(a, 0.2f * a) : 0.f;
+                    }
+                    uint4 hi, lo;
+                    lp_split8(y, hi, lo, vmax);
+                    *reinterpret_cast<uint4*>(yt + row * 128 + ((c ^ sw) << 4)) = hi;
+                    *reinterpret_cast<uint4*>(yt + row * 128 + (((4 + c) ^ sw) << 4)) = lo;
+                    if (copy_to) {   // rows 0, 1 again for the next tile (a 2-row image in the same layout: 128 & 7 == 0, 129 & 7 == 1)
+                        *reinterpret_cast<uint4*>(copy_to + row * 128 + ((c ^ sw) << 4)) = hi;
+                        *reinterpret_cast<uint4*>(copy_to + row * 128 + (((4 + c) ^ sw) << 4)) = lo;
+                    }
+                }
+            };
+            emit_row(v, yr, (q == 0 && lane < 2) ? carry + cs * 256 : nullptr);
+            if (q == 0) {
+                if (have_carry) {   // rows 128, 129 = rows 0, 1 of the previous tile, already pieces in exactly this 256-byte layout
+                    if (lane < 16) reinterpret_cast<uint4*>(yt + 128 * 128)[lane] = reinterpret_cast<const uint4*>(carry + (cs ^ 1) * 256)[lane];
+                } else {            // ... or rows 0, 1 of the second MMA pass (TMEM lanes 0, 1 of its accumulator)
+                    tmem_ld_32x32b_x32(tmem_base + 64u + (uint32_t)cs * 32, v);
+                    tmem_ld_wait();
+                    if (lane < 2) emit_row(v, 128 + lane, nullptr);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cacc_free[cs]);   // both accumulators of this stage have been read
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&y_full[cs]);
+        }
+        if (p.sat && vmax > F16_MAX) *p.sat = 1u;
+    } else {
+        // =========================================== gate epilogue (16 warps) ===========================================
+        const int e = warp - 4, q = warp & 3, j = e >> 2;      // TMEM lane quarter, channel octet (gate channels 8j .. 8j+7)
+        const int r = q * 32 + lane;                            // output row of this thread
+        const int etid = tid - 128;                             // 0 .. 511
+        const int fi = (HOP >= LP_TT) ? 0 : r / HOP;            // warp-uniform (HOP is a multiple of 32)
+        float vmax = 0.f;
+        for (int n = 0; n < ntile; ++n) {
+            const int tile = tile_hi - 1 - n, b = tile / ntt, t0 = (tile % ntt) * LP_TT;
+            const int s = n % LP_NA, ls = n & 1, t = t0 + r;
+            const unsigned char* a = a_st + s * LP_STAGE_BYTES;
+            const float* lbias = (const float*)(a + 24576);
+            float* au = (float*)(a + 24576) + 128;
+            mbar_wait(&a_full[s], (uint32_t)((n / LP_NA) & 1));
+            if (HOP == 256 && (t0 == 0 || t0 + LP_AU - 4 > T)) {   // audio positions outside [0, T) are zero (the first conv zero-pads)
+                if (etid < LP_AU) { const int pos = t0 - 4 + etid; if (pos < 0 || pos >= T) au[etid] = 0.f; }
+                group_sync(2, LP_E2_THREADS);
+            }
+            float sk[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sk[c] = 0.f;
+            if (p.p_out) {   // the skip of the NEXT layer's "x += audio_down", added to the rows this layer produces
+                if (HOP == 256) {
+                    const float4 b0 = *reinterpret_cast<const float4*>(fb_s + j * 8), b1 = *reinterpret_cast<const float4*>(fb_s + j * 8 + 4);
+                    sk[0] = b0.x; sk[1] = b0.y; sk[2] = b0.z; sk[3] = b0.w; sk[4] = b1.x; sk[5] = b1.y; sk[6] = b1.z; sk[7] = b1.w;
+#pragma unroll
+                    for (int k = 0; k < 7; ++k) {
+                        const float x = au[r + 1 + k];          // audio position t + k - 3
+                        const float4 w0 = *reinterpret_cast<const float4*>(fw_s + k * C + j * 8), w1 = *reinterpret_cast<const float4*>(fw_s + k * C + j * 8 + 4);
+                        sk[0] = fmaf(w0.x, x, sk[0]); sk[1] = fmaf(w0.y, x, sk[1]); sk[2] = fmaf(w0.z, x, sk[2]); sk[3] = fmaf(w0.w, x, sk[3]);
+                        sk[4] = fmaf(w1.x, x, sk[4]); sk[5] = fmaf(w1.y, x, sk[5]); sk[6] = fmaf(w1.z, x, sk[6]); sk[7] = fmaf(w1.w, x, sk[7]);
+                    }
+                } else if (t < T) {
+                    const float4* sp = reinterpret_cast<const float4*>(p.skip + ((size_t)b * T + t) * C + j * 8);
+                    const float4 s0 = sp[0], s1 = sp[1];
+                    sk[0] = s0.x; sk[1] = s0.y; sk[2] = s0.z; sk[3] = s0.w; sk[4] = s1.x; sk[5] = s1.y; sk[6] = s1.z; sk[7] = s1.w;
+                }
+            }
+            // residual base z = x + skip of this row, recovered from the pieces of 16 * lrelu(z) that fed the conv
+            float z[8];
+            {
+                const int ar = 32 + r, sw = ar & 7;
+                const uint4 h = *reinterpret_cast<const uint4*>(a + ar * 128 + ((j ^ sw) << 4));
+                const uint4 l = *reinterpret_cast<const uint4*>(a + ar * 128 + (((4 + j) ^ sw) << 4));
+                const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float2 hf = unpack_f16x2(hh[c]), lf = unpack_f16x2(ll[c]);
+                    const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
+                    z[2 * c] = v0 * (v0 < 0.f ? (1.f / (0.2f * S16_ACT)) : (1.f / S16_ACT));
+                    z[2 * c + 1] = v1 * (v1 < 0.f ? (1.f / (0.2f * S16_ACT)) : (1.f / S16_ACT));
+                }
+            }
+            float lb[16];
+            {
+                const float4* lp = reinterpret_cast<const float4*>(lbias + fi * 64 + j * 8);
+                const float4 a0 = lp[0], a1 = lp[1], b0 = lp[8], b1 = lp[9];   // sigmoid half [8j, 8j+8), tanh half [32 + 8j, ...)
+                lb[0] = a0.x; lb[1] = a0.y; lb[2] = a0.z; lb[3] = a0.w; lb[4] = a1.x; lb[5] = a1.y; lb[6] = a1.z; lb[7] = a1.w;
+                lb[8] = b0.x; lb[9] = b0.y; lb[10] = b0.z; lb[11] = b0.w; lb[12] = b1.x; lb[13] = b1.y; lb[14] = b1.z; lb[15] = b1.w;
+            }
+            mbar_wait(&lacc_full[ls], (uint32_t)((n >> 1) & 1));
+            tc_fence_after();
+            uint32_t zs[8], zt[8];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + LACC0 + (uint32_t)ls * LSTRIDE + fi * 64 + j * 8;
+            tmem_ld_32x32b_x8(ta, zs);
+            tmem_ld_32x32b_x8(ta + 32, zt);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&lacc_free[ls]);
+            float xn[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                xn[c] = z[c] + gate_st(fmaf(__uint_as_float(zs[c]), p.inv_l, lb[c]), fmaf(__uint_as_float(zt[c]), p.inv_l, lb[8 + c]));
+            if (p.f_out) {
+                if (t < T) st_global_f8(p.f_out + ((size_t)b * T + t) * C + j * 8, make_float4(xn[0], xn[1], xn[2], xn[3]), make_float4(xn[4], xn[5], xn[6], xn[7]));
+            } else {
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = lrelu02_s(__fadd_rn(xn[c], sk[c]));   // (x + gate) + skip: the reference's rounding sequence
+                uint4 hi, lo;
+                lp_split8(v, hi, lo, vmax);
+                const int sw = r & 7;                                                   // == t & 7 (t0 is a multiple of 128)
+                if (STAGE_OUT) {
+                    unsigned char* ot = o_t + ls * LP_OUT_BYTES;
+                    *reinterpret_cast<uint4*>(ot + r * 128 + ((j ^ sw) << 4)) = hi;
+                    *reinterpret_cast<uint4*>(ot + r * 128 + (((4 + j) ^ sw) << 4)) = lo;
+                    fence_async_smem();
+                    if (etid == 0) bulk_wait_read0();        // the bulk store of tile n-1 has read its buffer: free for tile n+1 after the barrier
+                    group_sync(1, LP_E2_THREADS);
+                    if (etid == 0) {
+                        const int rows = min(LP_TT, T - t0);
+                        bulk_s2g(p.p_out + lp_row_of(b, T, t0) * C, ot, (uint32_t)rows * 128u);
+                        bulk_commit();
+                    }
+                } else if (t < T) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.p_out + lp_row_of(b, T, t) * C);
+                    dst[j ^ sw] = hi;
+                    dst[(4 + j) ^ sw] = lo;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_free[s]);
+        }
+        if (STAGE_OUT && etid == 0) bulk_wait_all();
+        if (p.sat && vmax > F16_MAX) *p.sat = 1u;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TCOLS);
+    }
+}
+
+}  // namespace fd

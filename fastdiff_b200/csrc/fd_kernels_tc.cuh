@@ -970,7 +970,7 @@ template <> __device__ __forceinline__ void tmem_ld_cols<32>(uint32_t taddr, uin
 // sm_100 (STG.E.ENL2.256): the epilogues below write rows with one lane per row, so a 16-byte store fills half a 32-byte sector per
 // lane and a warp store touches 32 half-sectors; the 256-bit form writes whole sectors with half the store instructions.
 #ifndef FD_VEC256
-#define FD_VEC256 0
+#define FD_VEC256 1   // measured on B200 (round 2): upsample 0.79 -> 0.64, LVC block 2 4.47 -> 4.31 ms per N=4 call at config 2
 #endif
 __device__ __forceinline__ void st_global_f8(float* p, const float4 a, const float4 b) {
 #if FD_VEC256 && !defined(FD_EMU)
@@ -1919,6 +1919,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
 
 }  // namespace fd
 #include "fd_kernels_tc_exp.cuh"   // k_lvc_layer_p, k_lvc_layer_b0h, k_b0_panel_to_pieces (experimental, off by default)
+#include "fd_kernels_lvcp.cuh"     // k_lvc_p: LVC layers of blocks 1, 2 on the default path (piece-row protocol, warp-specialised pipeline)
 namespace fd {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2368,12 +2369,24 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 constexpr int UT_AROWS = 136;                          // input rows m0-1 .. m0+128 (+pad)
 constexpr int UT_ATILE = UT_AROWS * 128;               // 17408 B per piece
+constexpr int UT_PEXTRA = 4096;                        // POUT, r = 4: audio window (128 r + 8 floats) + first conv taps and bias
 template <int R> constexpr int ut_smem_bytes() { return 2 * UT_ATILE + 2 * R * 8192 + 256 + 64 + 1024; }
 
-template <int R>
+// POUT (the default path of mode tc_3xf16): the epilogue adds the block's skip (r = 8: rows of the DBlock output; r = 4:
+// first_conv(audio), 7 taps) -- the reference's first "x += audio_down" -- and writes z = up + skip as the PIECE ROWS the first LVC
+// layer consumes (fd_kernels_lvcp.cuh: fp16 hi | lo of 16 * lrelu(z), chunk c at c ^ (t & 7), padded row layout) instead of fp32 rows.
+struct UpPOut {
+    const float* skip;       // r = 8: (B, T, 32) rows; r = 4: audio (B, T)
+    const float* first_w;    // [7][32]  (r = 4)
+    const float* first_b;    // [32]
+    float* p_out;            // padded piece rows (B items of T = r Tin rows)
+    unsigned int* sat;
+};
+
+template <int R, bool POUT = false>
 __global__ void __launch_bounds__(512, (R == 4 ? 2 : 1))
 k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, const float* __restrict__ bias,
-              const float* __restrict__ in, float* __restrict__ out, int B, int Tin, int three_pass) {
+              const float* __restrict__ in, float* __restrict__ out, int B, int Tin, int three_pass, const UpPOut po = UpPOut()) {
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* a_hi = smem;                          // tile row ar <-> input row m0 - 1 + ar
@@ -2382,11 +2395,19 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
     float* b_s = (float*)(wt + 2 * R * 8192);
     uint64_t* bar = (uint64_t*)(b_s + 64);               // [0] MMAs, [1] loads
     uint32_t* tmem_base_s = (uint32_t*)(bar + 2);
+    float* au_s = (float*)(tmem_base_s + 4);             // POUT, r = 4: audio positions r m0 - 4 .. r m0 + 128 r + 3
+    float* pfw_s = au_s + 128 * R + 8;                   // [7][32]
+    float* pfb_s = pfw_s + 7 * C;                        // [32]
     constexpr uint32_t NCOLS = R * 64;
 
     const int tid = threadIdx.x, gw = tid >> 5, lane = tid & 31;
     if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init_fence(); }
     if (tid < 32) tmem_alloc(tmem_base_s, NCOLS);
+    if (POUT && R == 4) {
+        if (tid < 7 * C) pfw_s[tid] = po.first_w[tid];
+        if (tid < C) pfb_s[tid] = po.first_b[tid];
+    }
+    float vmax = 0.f;
     for (int i = tid; i < 2 * R * 256; i += 512) {   // i = tap*256 + float4 within the 4 KB tap tile
         const int k = i >> 8, w = i & 255;
         reinterpret_cast<float4*>(wt + k * 8192)[w] = reinterpret_cast<const float4*>(w_hi)[i];
@@ -2416,6 +2437,13 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
     uint32_t parity = 0;
     for (; tile < total; tile += gridDim.x, parity ^= 1) {
         const int b = tile / ntt, m0 = (tile % ntt) * 128;
+        if (POUT && R == 4) {   // audio window of this tile's outputs (zero outside the utterance); read by the epilogue, after two barriers
+            const int Tout = Tin * R;
+            for (int i = tid; i < 128 * R + 8; i += 512) {
+                const int pos = R * m0 - 4 + i;
+                au_s[i] = (pos >= 0 && pos < Tout) ? po.skip[(size_t)b * Tout + pos] : 0.f;
+            }
+        }
         mbar_wait(&bar[1], parity);
         // ---- lrelu + tf32 split, in place (8 lanes per row) ----
 #pragma unroll
@@ -2486,6 +2514,36 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
                     for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
                 }
                 tmem_ld_wait();
+                if (POUT) {
+                    if (m < Tin) {
+                        const int Tout = Tin * R, t = R * m + ph;
+                        float sk[8];
+                        if (R == 4) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(pfb_s + part * 8), b1 = *reinterpret_cast<const float4*>(pfb_s + part * 8 + 4);
+                            sk[0] = b0.x; sk[1] = b0.y; sk[2] = b0.z; sk[3] = b0.w; sk[4] = b1.x; sk[5] = b1.y; sk[6] = b1.z; sk[7] = b1.w;
+#pragma unroll
+                            for (int k = 0; k < 7; ++k) {
+                                const float x = au_s[t - R * m0 + 1 + k];   // audio position t + k - 3
+                                const float4 w0 = *reinterpret_cast<const float4*>(pfw_s + k * C + part * 8), w1 = *reinterpret_cast<const float4*>(pfw_s + k * C + part * 8 + 4);
+                                sk[0] = fmaf(w0.x, x, sk[0]); sk[1] = fmaf(w0.y, x, sk[1]); sk[2] = fmaf(w0.z, x, sk[2]); sk[3] = fmaf(w0.w, x, sk[3]);
+                                sk[4] = fmaf(w1.x, x, sk[4]); sk[5] = fmaf(w1.y, x, sk[5]); sk[6] = fmaf(w1.z, x, sk[6]); sk[7] = fmaf(w1.w, x, sk[7]);
+                            }
+                        } else {
+                            const float4* sp = reinterpret_cast<const float4*>(po.skip + ((size_t)b * Tout + t) * C + part * 8);
+                            const float4 s0 = sp[0], s1 = sp[1];
+                            sk[0] = s0.x; sk[1] = s0.y; sk[2] = s0.z; sk[3] = s0.w; sk[4] = s1.x; sk[5] = s1.y; sk[6] = s1.z; sk[7] = s1.w;
+                        }
+                        float z[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) z[i] = lrelu02_s(__fadd_rn(__uint_as_float(v[i]) + bb[i], sk[i]));   // up + skip, the reference's order
+                        uint4 hi, lo;
+                        lp_split8(z, hi, lo, vmax);
+                        uint4* dst = reinterpret_cast<uint4*>(po.p_out + lp_row_of(b, Tout, t) * C);
+                        const int sw = t & 7;
+                        dst[part ^ sw] = hi;
+                        dst[(4 + part) ^ sw] = lo;
+                    }
+                } else
                 if (m < Tin) {
                     float4 o0 = make_float4(__uint_as_float(v[0]) + bb[0], __uint_as_float(v[1]) + bb[1], __uint_as_float(v[2]) + bb[2], __uint_as_float(v[3]) + bb[3]);
                     float4 o1 = make_float4(__uint_as_float(v[4]) + bb[4], __uint_as_float(v[5]) + bb[5], __uint_as_float(v[6]) + bb[6], __uint_as_float(v[7]) + bb[7]);
@@ -2501,6 +2559,7 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
         tc_fence_before();
         __syncthreads();
     }
+    if (POUT && po.sat && vmax > F16_MAX) *po.sat = 1u;
     tc_fence_before();
     __syncthreads();
     if (tid < 32) {
@@ -2705,6 +2764,63 @@ static inline int tc_kp_hidden(void* state, const float* mel, const float* cnois
     return 0;
 }
 
+// ---- default path of mode tc_3xf16 for LVC blocks 1, 2: piece-row protocol (fd_kernels_lvcp.cuh) ----
+// up-sampling + first skip add -> piece rows of layer 0
+static inline int tc_upsample_p(void* state, int blk, const float* in, const float* skip, float* p_out, unsigned int* sat, int B, int Tin,
+                                cudaStream_t st, std::string& err, uint64_t* launches) {
+    TcState* s = (TcState*)state;
+    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    const float* wh = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_UPT_HI : FD_S_LB2_UPT_HI];
+    const float* wl = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_UPT_LO : FD_S_LB2_UPT_LO];
+    const float* bias = s->blob + s->sec_off[FD_S_LB0_UP_B + blk * FD_LB_STRIDE];
+    UpPOut po;
+    po.skip = skip; po.first_w = s->blob + s->sec_off[FD_S_FIRST_W]; po.first_b = s->blob + s->sec_off[FD_S_FIRST_B]; po.p_out = p_out; po.sat = sat;
+    const int total = B * ((Tin + 127) / 128);
+    if (blk == 1) {
+        const int grid = total < s->sm_count ? total : s->sm_count;
+        k_upsample_tc<8, true><<<grid, 512, ut_smem_bytes<8>() + UT_PEXTRA, st>>>(wh, wl, bias, in, p_out, B, Tin, 1, po);
+    } else {
+        const int grid = total < 2 * s->sm_count ? total : 2 * s->sm_count;
+        k_upsample_tc<4, true><<<grid, 512, ut_smem_bytes<4>() + UT_PEXTRA, st>>>(wh, wl, bias, in, p_out, B, Tin, 1, po);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_upsample_tc<POUT> failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    return 0;
+}
+
+// one LVC layer of block 1 / 2: piece rows in -> piece rows out (p_out) or fp32 rows out (f_out, last layer of the block)
+static inline int tc_lvc_p_layer(void* state, int blk, int layer, const float* p_in, const float* skip, const float* kern, float* p_out,
+                                 float* f_out, unsigned int* sat, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches) {
+    TcState* s = (TcState*)state;
+    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    LvcPParams p;
+    p.cw16 = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16] + (size_t)layer * (LP_CW_BYTES / 4);
+    p.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + blk * FD_LB_STRIDE] + layer * C;
+    p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
+    p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
+    p.p_in = p_in; p.skip = skip; p.kern = kern; p.p_out = p_out; p.f_out = f_out; p.sat = sat;
+    p.B = B; p.T = T; p.Tm = Tm; p.dil = dil;
+    p.inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * blk + layer]);
+    p.inv_l = 1.f / (S16_ACT * S16_KERN);
+    const int tiles = B * ((T + LP_TT - 1) / LP_TT);
+    const int grid = tiles < s->sm_count ? tiles : s->sm_count;
+    if (blk == 1) k_lvc_p<64><<<grid, LP_THREADS, lp_smem_bytes<64>(), st>>>(p);
+    else          k_lvc_p<256><<<grid, LP_THREADS, lp_smem_bytes<256>(), st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_lvc_p failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    return 0;
+}
+
+static inline int tc_zero_pads(float* buf, int B, int T, cudaStream_t st, std::string& err, uint64_t* launches) {
+    k_zero_pads<<<B + 1, 256, 0, st>>>(buf, B, T);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_zero_pads failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    return 0;
+}
+
 static inline cudaError_t tc_set_lvc_attrs() {
     {
         cudaError_t ek = cudaFuncSetAttribute(k_kp_hidden_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM_BYTES);
@@ -2719,6 +2835,14 @@ static inline cudaError_t tc_set_lvc_attrs() {
     e0 = cudaFuncSetAttribute(k_upsample_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<4>());
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_upsample_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<8>());
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_upsample_tc<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<4>() + UT_PEXTRA);
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_upsample_tc<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<8>() + UT_PEXTRA);
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_lvc_p<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, lp_smem_bytes<64>());
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_lvc_p<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, lp_smem_bytes<256>());
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_lvc_layer_h<64, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lh_smem_bytes<64, false, 2>());
     if (e0 != cudaSuccess) return e0;

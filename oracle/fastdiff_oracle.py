@@ -166,9 +166,25 @@ def kernel_predictor(W, prefix: str, cond: torch.Tensor, layers=4, cin=32, cout=
 
 
 def lvc(x: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor, hop: int) -> torch.Tensor:
-    """Closed form of modules.py:220-253 at dilation 1:
+    """modules.py:220-253 at dilation 1 (the only value the reference passes, :216):
     out[b,o,t] = bias[b,o,t//hop] + sum_{i,k} xpad[b,i,t+k] * kernel[b,i,o,k,t//hop],
-    xpad = x zero-padded by (ksz-1)/2 at both sequence ends."""
+    xpad = x zero-padded by (ksz-1)/2 at both sequence ends.
+    Evaluated the way the reference evaluates it -- frame windows by `unfold`, taps by a second `unfold`, ONE einsum over
+    (i, k) that ATen lowers to a batched GEMM -- so that this port costs the same ATen work as the reference when it serves as a
+    CPU yardstick.  `lvc_taps` below is the independent closed form (three shifted einsums) the tests cross-check it with."""
+    B, Ci, T = x.shape
+    _, _, Co, K, Tm = kernel.shape
+    assert T == Tm * hop, "length of (x, kernel) is not matched"
+    p = (K - 1) // 2
+    win = F.pad(x, (p, p)).unfold(2, hop + 2 * p, hop)          # (B, Ci, Tm, hop + K - 1): frame l sees its hop samples + halo
+    win = win.unfold(3, K, 1)                                   # (B, Ci, Tm, hop, K): tap k of sample s
+    out = torch.einsum("bilsk,biokl->bols", win, kernel)        # (B, Co, Tm, hop)
+    out = out + bias.unsqueeze(-1)
+    return out.reshape(B, Co, T)
+
+
+def lvc_taps(x: torch.Tensor, kernel: torch.Tensor, bias: torch.Tensor, hop: int) -> torch.Tensor:
+    """The same sum written tap by tap (no unfold): the cross-check of `lvc`."""
     B, Ci, T = x.shape
     _, _, Co, K, Tm = kernel.shape
     assert T == Tm * hop, "length of (x, kernel) is not matched"

@@ -375,8 +375,8 @@ def test_full_schedule_n1000_vs_oracle(synth, cuda_lib):
     dh = fb.compute_hyperparams_given_schedule(beta.clone())
     torch.manual_seed(13)
     ref = O.sample(W, (B, 1, Tm * 256), dh, beta.clone(), mel, return_sequence=True)
+    net = _net(sd)                      # (module construction draws from the default generator: build it BEFORE seeding)
     torch.manual_seed(13)
-    net = _net(sd)
     got = fb.sampling_given_noise_schedule(net, (B, 1, Tm * 256), dh, beta.clone(), condition=mel.cuda(), return_sequence=True)
     assert len(got) == len(ref) == 1001
     for i in list(range(0, 1001, 100)) + [1000]:
