@@ -47,6 +47,7 @@ SYMBOLS = {
     "fd_mel_frontend": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fd_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_size_t), C.c_int, C.c_int, _P, _P]),
     "fd_launch_count": (C.c_uint64, [_P]),
+    "fd_check_saturation": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, _P]),
     "fd_timing_enable": (C.c_int, [_P, C.c_int]),
     "fd_timing_report": (C.c_int, [_P, C.c_char_p, C.c_size_t]),
     "fd_last_error": (C.c_char_p, [_P]),

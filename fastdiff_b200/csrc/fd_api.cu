@@ -39,6 +39,8 @@ struct fd_handle {
                                  // (over block 0's dead predicted kernels) and LVC block 2 reads it like block 1 reads its skip tensor
     int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
+    int lvc_p = 1;               // mode tc_3xf16: LVC blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>; option "lvc_p", 0 = k_lvc_layer_h)
+    unsigned int* sat_flag = nullptr;   // device word, sticky: an fp16 piece saturated in a tensor-core kernel (fd_check_saturation)
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
                                  // (option "overlap"; forked from / joined into the caller's stream with events inside every call)
 #ifndef FD_EMU
@@ -123,8 +125,8 @@ static WsLayout ws_layout(int B, int Tm) {
     w.d0 = o;     o += al((size_t)B * (L / 4) * C);
     w.d1 = o;     o += al((size_t)B * (L / 32) * C);
     w.d2 = o;     o += al((size_t)B * Tm * C);
-    w.xa = o;     o += al((size_t)B * L * C);
-    w.xb = o;     o += al((size_t)B * L * C);
+    w.xa = o;     o += al(lp_rows(B, (int)L) * C);   // (B,L,32) fp32 rows, or the padded piece rows of a layer input (fd_kernels_lvcp.cuh)
+    w.xb = o;     o += al(lp_rows(B, (int)L) * C);
     w.total = o;
     return w;
 }
@@ -166,6 +168,8 @@ extern "C" int fd_create(const fd_config* cfg, int device, fd_handle** out) {
         return fail(nullptr, FD_ERR_CUDA, "fd_create: creating the side stream / events failed");
     }
 #endif
+    if (cudaMalloc((void**)&h->sat_flag, 64) != cudaSuccess) { delete h; return fail(nullptr, FD_ERR_CUDA, "fd_create: cudaMalloc failed"); }
+    cudaMemset(h->sat_flag, 0, 64);
     *out = h;
     return FD_OK;
 }
@@ -184,18 +188,20 @@ extern "C" void fd_destroy(fd_handle* h) {
     if (h->side) cudaStreamDestroy(h->side);
 #endif
     if (h->blob) cudaFree(h->blob);
+    if (h->sat_flag) cudaFree(h->sat_flag);
     delete h;
 }
 
-static int parse_header(fd_handle* h, const uint64_t* hdr, size_t bytes) {
+// Validates the header into `off` / `cnt` (local to the caller): a rejected blob leaves the handle exactly as it was.
+static int parse_header(fd_handle* h, const uint64_t* hdr, size_t bytes, uint64_t* off, uint64_t* cnt) {
     if (bytes < 24 || hdr[0] != FD_BLOB_MAGIC) return fail(h, FD_ERR_INVALID, "weight blob: bad magic");
     if (hdr[1] != FD_BLOB_VERSION) return fail(h, FD_ERR_INVALID, "weight blob: version %ld, library expects %ld", (long)hdr[1], (long)FD_BLOB_VERSION);
     if (hdr[2] != FD_S_COUNT) return fail(h, FD_ERR_INVALID, "weight blob: %ld sections, library expects %ld", (long)hdr[2], (long)FD_S_COUNT);
     if (bytes < (3 + 2 * (size_t)FD_S_COUNT) * 8) return fail(h, FD_ERR_INVALID, "weight blob: truncated header");
     for (int s = 0; s < FD_S_COUNT; ++s) {
-        h->sec_off[s] = hdr[3 + 2 * s];
-        h->sec_cnt[s] = hdr[4 + 2 * s];
-        if ((h->sec_off[s] + h->sec_cnt[s]) * 4 > bytes || (h->sec_off[s] & 63))
+        off[s] = hdr[3 + 2 * s];
+        cnt[s] = hdr[4 + 2 * s];
+        if ((off[s] + cnt[s]) * 4 > bytes || (off[s] & 63))
             return fail(h, FD_ERR_INVALID, "weight blob: section %d out of range or misaligned", s);
     }
     // expected sizes of the sections whose shapes the kernels hard-code
@@ -206,7 +212,7 @@ static int parse_header(fd_handle* h, const uint64_t* hdr, size_t bytes) {
         {FD_S_LB0_KPRES_W, 6 * 3 * HID * HID}, {FD_S_LB0_KC_W, (size_t)KCK * KCN}, {FD_S_LB2_KC_B, KCN},
         {FD_S_LB0_KCT_HI, (size_t)KCK * KCN}, {FD_S_LB2_KCT_LO, (size_t)KCK * KCN}};
     for (auto& c : chk)
-        if (h->sec_cnt[c.s] != c.n) return fail(h, FD_ERR_INVALID, "weight blob: section %d has the wrong size (%ld)", c.s, (long)h->sec_cnt[c.s]);
+        if (cnt[c.s] != c.n) return fail(h, FD_ERR_INVALID, "weight blob: section %d has the wrong size (%ld)", c.s, (long)cnt[c.s]);
     return FD_OK;
 }
 
@@ -217,12 +223,16 @@ static int finish_load(fd_handle* h, const uint64_t* hdr_host) {
 
 extern "C" int fd_load_weights(fd_handle* h, const void* blob_host, size_t bytes) {
     if (!h || !blob_host) return fail(h, FD_ERR_INVALID, "fd_load_weights: null argument");
-    int rc = parse_header(h, (const uint64_t*)blob_host, bytes);
+    uint64_t off[FD_S_COUNT], cnt[FD_S_COUNT];
+    int rc = parse_header(h, (const uint64_t*)blob_host, bytes, off, cnt);
     if (rc) return rc;
     FD_CUDA(h, cudaSetDevice(h->device));
-    if (h->blob) { cudaFree(h->blob); h->blob = nullptr; }
-    FD_CUDA(h, cudaMalloc((void**)&h->blob, bytes));
-    FD_CUDA(h, cudaMemcpy(h->blob, blob_host, bytes, cudaMemcpyHostToDevice));
+    float* nb = nullptr;
+    FD_CUDA(h, cudaMalloc((void**)&nb, bytes));
+    if (cudaMemcpy(nb, blob_host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(nb); return fail(h, FD_ERR_CUDA, "fd_load_weights: copying the blob failed"); }
+    if (h->blob) cudaFree(h->blob);
+    h->blob = nb;
+    memcpy(h->sec_off, off, sizeof off); memcpy(h->sec_cnt, cnt, sizeof cnt);
     h->blob_floats = bytes / 4;
     const float* hb = (const float*)blob_host;
     memcpy(h->final_w, hb + h->sec_off[FD_S_FINAL_W], sizeof h->final_w);
@@ -240,19 +250,27 @@ extern "C" int fd_load_weights_dev(fd_handle* h, const void* blob_dev, size_t by
     FD_CUDA(h, cudaSetDevice(h->device));
     const size_t hdr_bytes = (3 + 2 * (size_t)FD_S_COUNT) * 8;
     if (bytes < hdr_bytes) return fail(h, FD_ERR_INVALID, "weight blob: truncated header");
-    uint64_t* hdr = (uint64_t*)malloc(hdr_bytes);
+    std::vector<uint64_t> hdr(hdr_bytes / 8);
     cudaStream_t st = (cudaStream_t)stream;
-    FD_CUDA(h, cudaMemcpyAsync(hdr, blob_dev, hdr_bytes, cudaMemcpyDeviceToHost, st));
+    FD_CUDA(h, cudaMemcpyAsync(hdr.data(), blob_dev, hdr_bytes, cudaMemcpyDeviceToHost, st));
     FD_CUDA(h, cudaStreamSynchronize(st));
-    int rc = parse_header(h, hdr, bytes);
-    free(hdr);
+    uint64_t off[FD_S_COUNT], cnt[FD_S_COUNT];
+    int rc = parse_header(h, hdr.data(), bytes, off, cnt);
     if (rc) return rc;
-    if (h->blob) { cudaFree(h->blob); h->blob = nullptr; }
-    FD_CUDA(h, cudaMalloc((void**)&h->blob, bytes));
-    FD_CUDA(h, cudaMemcpyAsync(h->blob, blob_dev, bytes, cudaMemcpyDeviceToDevice, st));
-    FD_CUDA(h, cudaMemcpyAsync(h->final_w, (const float*)blob_dev + h->sec_off[FD_S_FINAL_W], sizeof h->final_w, cudaMemcpyDeviceToHost, st));
-    FD_CUDA(h, cudaMemcpyAsync(&h->final_b, (const float*)blob_dev + h->sec_off[FD_S_FINAL_B], 4, cudaMemcpyDeviceToHost, st));
-    FD_CUDA(h, cudaStreamSynchronize(st));
+    float* nb = nullptr;
+    FD_CUDA(h, cudaMalloc((void**)&nb, bytes));
+    float fw[7 * C], fb = 0.f;
+    if (cudaMemcpyAsync(nb, blob_dev, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(fw, (const float*)blob_dev + off[FD_S_FINAL_W], sizeof fw, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(&fb, (const float*)blob_dev + off[FD_S_FINAL_B], 4, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        cudaFree(nb);
+        return fail(h, FD_ERR_CUDA, "fd_load_weights_dev: copying the blob failed");
+    }
+    if (h->blob) cudaFree(h->blob);
+    h->blob = nb;
+    memcpy(h->sec_off, off, sizeof off); memcpy(h->sec_cnt, cnt, sizeof cnt);
+    memcpy(h->final_w, fw, sizeof fw); h->final_b = fb;
     h->blob_floats = bytes / 4;
 #ifndef FD_EMU
     rc = tc_init(&h->tc_state, h->device, h->blob, h->sec_off, h->err);
@@ -292,6 +310,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "overlap")) { h->overlap = (int)value; return FD_OK; }
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
+    if (!strcmp(key, "lvc_p")) { h->lvc_p = (int)value; return FD_OK; }
     if (!strcmp(key, "b2_skipbuf")) { h->b2_skipbuf = (int)value; return FD_OK; }
     if (!strcmp(key, "kc_stage")) { h->kc_stage = (int)value; return FD_OK; }
     if (!strcmp(key, "lvc_pipe")) { h->lvc_pipe = (int)value; return FD_OK; }
@@ -312,6 +331,18 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
 }
 
 extern "C" uint64_t fd_launch_count(fd_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int fd_check_saturation(fd_handle* h, int* flag, int reset, void* stream) {
+    if (!h || !flag) return fail(h, FD_ERR_INVALID, "fd_check_saturation: null argument");
+    FD_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int v = 0;
+    FD_CUDA(h, cudaMemcpyAsync(&v, h->sat_flag, 4, cudaMemcpyDeviceToHost, st));
+    FD_CUDA(h, cudaStreamSynchronize(st));
+    if (reset && v) FD_CUDA(h, cudaMemsetAsync(h->sat_flag, 0, 4, st));
+    *flag = v ? 1 : 0;
+    return FD_OK;
+}
 
 extern "C" int fd_timing_enable(fd_handle* h, int on) {
     if (!h) return FD_ERR_INVALID;
@@ -496,8 +527,8 @@ static int emu_upsample_tc(fd_handle* h, int blk, const float* in, float* out, i
     const float* bias = sec(h, FD_S_LB0_UP_B + blk * FD_LB_STRIDE);
     const int total = B * ((Tin + 127) / 128);
     const int grid = total < 6 ? total : 6;
-    if (blk == 1) { auto k = k_upsample_tc<8>; FD_LAUNCH(k, dim3(grid), dim3(512), (ut_smem_bytes<8>()), st, wh, wl, bias, in, out, B, Tin, 1); }
-    else          { auto k = k_upsample_tc<4>; FD_LAUNCH(k, dim3(grid), dim3(512), (ut_smem_bytes<4>()), st, wh, wl, bias, in, out, B, Tin, 1); }
+    if (blk == 1) { auto k = k_upsample_tc<8>; FD_LAUNCH(k, dim3(grid), dim3(512), (ut_smem_bytes<8>()), st, wh, wl, bias, in, out, B, Tin, 1, UpPOut()); }
+    else          { auto k = k_upsample_tc<4>; FD_LAUNCH(k, dim3(grid), dim3(512), (ut_smem_bytes<4>()), st, wh, wl, bias, in, out, B, Tin, 1, UpPOut()); }
     FD_CHECK_LAUNCH(h, "k_upsample_tc");
     return FD_OK;
 }
@@ -513,6 +544,42 @@ static int emu_lvc_layer_b0(fd_handle* h, int layer, const float* x_in, const fl
     FD_LAUNCH(k_lvc_layer_b0h, dim3(grid), dim3(512), LB0_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l,
               layer == 0 ? 1 : 0, layer < LAYERS - 1 ? 1 : 0);
     FD_CHECK_LAUNCH(h, "k_lvc_layer_b0h");
+    return FD_OK;
+}
+// piece-row protocol (fd_kernels_lvcp.cuh) on the model
+static int emu_zero_pads(fd_handle* h, float* buf, int B, int T, cudaStream_t st) {
+    FD_LAUNCH(k_zero_pads, dim3(B + 1), dim3(256), 0, st, buf, B, T);
+    FD_CHECK_LAUNCH(h, "k_zero_pads");
+    return FD_OK;
+}
+static int emu_upsample_p(fd_handle* h, int blk, const float* in, const float* skip, float* p_out, int B, int Tin, cudaStream_t st) {
+    const float* wh = sec(h, blk == 1 ? FD_S_LB1_UPT_HI : FD_S_LB2_UPT_HI);
+    const float* wl = sec(h, blk == 1 ? FD_S_LB1_UPT_LO : FD_S_LB2_UPT_LO);
+    const float* bias = sec(h, FD_S_LB0_UP_B + blk * FD_LB_STRIDE);
+    UpPOut po;
+    po.skip = skip; po.first_w = sec(h, FD_S_FIRST_W); po.first_b = sec(h, FD_S_FIRST_B); po.p_out = p_out; po.sat = h->sat_flag;
+    const int total = B * ((Tin + 127) / 128);
+    const int grid = total < 6 ? total : 6;
+    if (blk == 1) { auto k = k_upsample_tc<8, true>; FD_LAUNCH(k, dim3(grid), dim3(512), (ut_smem_bytes<8>() + UT_PEXTRA), st, wh, wl, bias, in, p_out, B, Tin, 1, po); }
+    else          { auto k = k_upsample_tc<4, true>; FD_LAUNCH(k, dim3(grid), dim3(512), (ut_smem_bytes<4>() + UT_PEXTRA), st, wh, wl, bias, in, p_out, B, Tin, 1, po); }
+    FD_CHECK_LAUNCH(h, "k_upsample_tc<POUT>");
+    return FD_OK;
+}
+static int emu_lvc_p_layer(fd_handle* h, int blk, int layer, const float* p_in, const float* skip, const float* kern, float* p_out, float* f_out,
+                           int B, int T, int Tm, int dil, cudaStream_t st) {
+    LvcPParams p;
+    p.cw16 = sec(h, blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16) + (size_t)layer * (LP_CW_BYTES / 4);
+    p.conv_b = sec(h, FD_S_LB0_CONV_B + blk * FD_LB_STRIDE) + layer * C;
+    p.first_w = sec(h, FD_S_FIRST_W); p.first_b = sec(h, FD_S_FIRST_B);
+    p.p_in = p_in; p.skip = skip; p.kern = kern; p.p_out = p_out; p.f_out = f_out; p.sat = h->sat_flag;
+    p.B = B; p.T = T; p.Tm = Tm; p.dil = dil;
+    p.inv_c = 1.f / (S16_ACT * emu_scale16(h, 4 + 4 * blk + layer));
+    p.inv_l = 1.f / (S16_ACT * S16_KERN);
+    const int tiles = B * ((T + LP_TT - 1) / LP_TT);
+    int grid = (tiles + 3) / 4; if (grid < 1) grid = 1; if (grid > 8) grid = 8;   // a few tiles per CTA: carried rows, kernel reuse, every ring wraps
+    if (blk == 1) { auto k = k_lvc_p<64>;  FD_LAUNCH(k, dim3(grid), dim3(LP_THREADS), (lp_smem_bytes<64>()), st, p); }
+    else          { auto k = k_lvc_p<256>; FD_LAUNCH(k, dim3(grid), dim3(LP_THREADS), (lp_smem_bytes<256>()), st, p); }
+    FD_CHECK_LAUNCH(h, "k_lvc_p");
     return FD_OK;
 }
 #endif  // FD_EMU
@@ -680,6 +747,22 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         const int r = ratio_of(n), T = Tin * r;
         const float* upw = sec(h, FD_S_LB0_UP_W + n * FD_LB_STRIDE);
         const float* upb = sec(h, FD_S_LB0_UP_B + n * FD_LB_STRIDE);
+        const float* skip = (n == 0) ? d1 : (n == 1 ? d0 : x_dev);
+        // default path of mode tc_3xf16 for blocks 1, 2: the state travels between layers as fp16 operand pieces (fd_kernels_lvcp.cuh)
+        const bool use_p = (n >= 1 && h->mode == FD_MODE_TC_3XF16 && h->lvc_p && h->tc_upsample);
+        if (use_p) {   // blk_in lives in `oth`: zero the pads of `cur`, up-sample into it, then zero the pads of `oth` for layer 0's output
+            ScopedTimer tm(h, KC_UPSAMPLE, st);
+#ifdef FD_EMU
+            int rc = emu_zero_pads(h, cur, B, T, st);
+            if (!rc) rc = emu_upsample_p(h, n, blk_in, skip, cur, B, Tin, st);
+            if (!rc) rc = emu_zero_pads(h, oth, B, T, st);
+#else
+            int rc = tc_zero_pads(cur, B, T, st, h->err, &h->launches);
+            if (!rc) rc = tc_upsample_p(h->tc_state, n, blk_in, skip, cur, h->sat_flag, B, Tin, st, h->err, &h->launches);
+            if (!rc) rc = tc_zero_pads(oth, B, T, st, h->err, &h->launches);
+#endif
+            if (rc) return rc;
+        } else
         {
             const dim3 grid((Tin + 31) / 32, B);
             ScopedTimer tm(h, KC_UPSAMPLE, st);
@@ -703,9 +786,8 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 FD_CHECK_LAUNCH(h, "k_upsample");
             }
         }
-        const float* skip = (n == 0) ? d1 : (n == 1 ? d0 : x_dev);
         const float* kern_n = kern + (size_t)n * B * Tm * KCN;
-        const bool b2_rows = (n == 2 && h->b2_skipbuf && h->mode == FD_MODE_TC_3XF16);
+        const bool b2_rows = (n == 2 && h->b2_skipbuf && h->mode == FD_MODE_TC_3XF16 && !use_p);
         if (b2_rows) {   // experimental: first_conv(audio) as rows, once, over block 0's predicted kernels (dead by now: 8192 of its 24832 floats per frame)
             ScopedTimer tm(h, KC_LVC2, st);
             FD_LAUNCH(k_first_conv_rows, dim3((T + 31) / 32, B), dim3(256), 0, st, sec(h, FD_S_FIRST_W), sec(h, FD_S_FIRST_B), x_dev, kern, T);
@@ -734,8 +816,19 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             const float* kl = kern_n + i * KPL;
             bool done = false;
             ScopedTimer tm(h, KC_LVC0 + n, st);
+            if (use_p) {
+                float* p_out = i < LAYERS - 1 ? oth : nullptr;
+                float* f_out = i < LAYERS - 1 ? nullptr : oth;
 #ifdef FD_EMU
-            if (b0_here) {
+                int rc = emu_lvc_p_layer(h, n, i, cur, skip, kl, p_out, f_out, B, T, Tm, dil, st);
+#else
+                int rc = tc_lvc_p_layer(h->tc_state, n, i, cur, skip, kl, p_out, f_out, h->sat_flag, B, T, Tm, dil, st, h->err, &h->launches);
+#endif
+                if (rc) return rc;
+                done = true;
+            }
+#ifdef FD_EMU
+            else if (b0_here) {
                 int rc = emu_lvc_layer_b0(h, i, cur, skip, kl, oth, B, T, Tm, dil, st);
                 if (rc) return rc;
                 done = true;
@@ -745,7 +838,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 done = true;
             }
 #else
-            if (b0_here) {
+            else if (b0_here) {
                 int rc = tc_lvc_layer_b0(h->tc_state, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches);
                 if (rc) return rc;
                 done = true;

@@ -796,8 +796,12 @@ static inline void tc_set_lvc_exp(void* st, int v) { if (st) ((TcState*)st)->lvc
 static inline void tc_set_kc_exp(void* st, int v) { if (st) ((TcState*)st)->kc_exp = v; }
 
 static inline int tc_init(void** state, int device, const float* blob, const uint64_t* sec_off, std::string& err) {
-    tc_destroy(*state);
+    TcState* old = (TcState*)*state;
     TcState* s = new TcState();
+    if (old) {   // a weight reload keeps the tuning options set through fd_set_option
+        s->lvc_swizzle = old->lvc_swizzle; s->kc_2cta = old->kc_2cta; s->lvc_groups = old->lvc_groups; s->lvc_exp = old->lvc_exp; s->kc_exp = old->kc_exp;
+    }
+    tc_destroy(old);
     *state = s;
     s->device = device; s->blob = blob;
     for (int i = 0; i < FD_S_COUNT; ++i) s->sec_off[i] = sec_off[i];

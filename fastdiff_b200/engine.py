@@ -118,6 +118,12 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.fd_launch_count(self.h))
 
+    def check_saturation(self, reset: bool = True) -> bool:
+        """True if an fp16 operand piece saturated in a tensor-core kernel since the last reset (mode tc_3xf16 only; synchronises)."""
+        flag = C.c_int(0)
+        self._check(self.lib.fd_check_saturation(self.h, C.byref(flag), int(reset), self._stream()), "fd_check_saturation")
+        return bool(flag.value)
+
     def timing_enable(self, on: bool = True):
         self._check(self.lib.fd_timing_enable(self.h, int(on)), "fd_timing_enable")
 

@@ -168,6 +168,13 @@ int fd_debug_read(fd_handle* h, const char* name, float* out_dev, size_t* count,
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
 uint64_t fd_launch_count(fd_handle* h);
 
+/* Range guard of the default arithmetic mode (tc_3xf16): operands of the tensor-core kernels are fp16 pieces of 16 x activation
+ * (64 x predicted kernel) and SATURATE at |piece| = 65504 instead of overflowing.  Every kernel that forms pieces raises a sticky
+ * device flag when a value left the range (|activation| >= 4094); this call synchronises `stream`, returns the flag in *flag (0 / 1)
+ * and clears it when `reset` != 0.  A raised flag means the results of the calls since the last reset are NOT fp32-level: re-run in
+ * FD_MODE_TC_3XTF32 (fp32 range).  The reference has no counterpart (it computes in fp32, FastDiff_model.py:74-102). */
+int fd_check_saturation(fd_handle* h, int* flag, int reset, void* stream);
+
 /* Optional device timing per kernel class (CUDA events around every launch on the caller's stream).
  * After the caller has synchronised the stream, fd_timing_report writes one JSON object
  * {"kc_gemm": {"ms": total, "n": launches}, ...} for the launches since the previous report. */
