@@ -235,12 +235,18 @@ def run_reference(args):
 
 
 def run_ours(args):
+    """This repo's arm.  Every rank drives the PRODUCT multi-GPU API -- fastdiff_b200.shard.ShardedFastDiff (one NCCL broadcast of the
+    packed weights at construction, then `sample()` on this rank's slice of the global batch, no per-step collective) -- also at N = 1,
+    where it degenerates to one engine.  Three timed regions:
+      value  device-resident: mel already in HBM, noise drawn on the device (Philox), CUDA events, max over ranks;
+      e2e    the same call with HOST buffers: pinned mel -> device and waveform -> pinned host inside the timed region;
+      e2e_reference_noise (N = 1)  `fastdiff_b200.sampling_given_noise_schedule` in its drop-in default `noise_mode="reference"`:
+             x_T and the N-1 noise tensors are drawn on the CPU default generator in the reference's order and copied H2D
+             (bit-compatible RNG stream; host RNG time inside the timed region)."""
     import torch.distributed as dist
     import fastdiff_b200 as fb
-    from fastdiff_b200.sampler import build_steps
+    from fastdiff_b200.shard import ShardedFastDiff
     from fastdiff_b200.synthetic import make_inputs, make_state_dict
-    from fastdiff_b200.weights import pack_state_dict
-    from fastdiff_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -251,32 +257,18 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    B, Tm = args.batch, args.frames
+    B, Tm = args.batch, args.frames          # per GPU (weak scaling)
     L = Tm * 256
+    GB = world * B
 
-    # ---- weights: rank 0 packs, one broadcast of the blob, every rank loads from device memory -------------
-    if world > 1:
-        if rank == 0:
-            blob = torch.from_numpy(pack_state_dict(make_state_dict(1234))).to(dev)
-            n = torch.tensor([blob.numel()], device=dev, dtype=torch.int64)
-        else:
-            n = torch.zeros(1, device=dev, dtype=torch.int64)
-        dist.broadcast(n, 0)
-        if rank != 0:
-            blob = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
-        dist.broadcast(blob, 0)   # the only collective on the path
-        eng = Engine(device=dev)
-        eng.load_blob_device(blob)
-        net = None
-    else:
-        net = fb.FastDiff().to(dev).eval()
-        net.load_state_dict(make_state_dict(1234))
-        net.noise_mode = "device"
-        eng = net.engine(dev)
+    # ---- weights: rank 0 packs, ONE broadcast of the blob (inside ShardedFastDiff), every rank loads from device memory -------
+    t_load0 = time.perf_counter()
+    sh = ShardedFastDiff(make_state_dict(1234) if rank == 0 else None, device=dev)
+    torch.cuda.synchronize()
+    load_s = time.perf_counter() - t_load0
+    eng = sh.engine
     if args.mode:
         eng.set_mode(args.mode)
-        if net is not None:
-            net.mode = args.mode
     for kv in args.opt:
         key, val = kv.split("=")
         eng.set_option(key, int(val))
@@ -284,13 +276,14 @@ def run_ours(args):
 
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
     sched = torch.FloatTensor(N4_SCHEDULE)
-    _, steps = build_steps(dh, sched)
-    _, mel_host = make_inputs(B, Tm, seed=rank)  # each rank owns its own utterances
-    mel = mel_host.to(dev)
-    x = torch.empty((B, 1, L), dtype=torch.float32, device=dev)
+    # the global batch of mels: every rank builds the same tensor and ShardedFastDiff slices its own utterances out of it
+    mel_host = torch.cat([make_inputs(B, Tm, seed=r)[1] for r in range(world)], 0)
+    mel_dev = mel_host.to(dev)
+    size = (GB, 1, L)
 
     def one_call(i):
-        eng.sample(x, mel, steps, noise=None, seed=1000 + i, fill_xT=True)
+        with contextlib.redirect_stdout(sys.stderr):
+            return sh.sample(size, dh, sched, mel_dev, seed=1000 + i)
 
     def barrier():
         if world > 1:
@@ -304,9 +297,7 @@ def run_ours(args):
         one_call(i)
     barrier()
 
-    # ---- timed region: device-resident inputs ------------------------------------------------------------
-    eng.timing_enable(True)
-    eng.timing_report()  # drop warm-up records
+    # ---- timed region 1: device-resident inputs (the library replays its captured CUDA graph of the whole call) -------------
     l0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -321,41 +312,42 @@ def run_ours(args):
         clocks.mark_end()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - l0
-    per_kernel = eng.timing_report()
-    eng.timing_enable(False)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = world * B * L / (ms_per_step * 1e-3)
+    value = GB * L / (ms_per_step * 1e-3)
 
-    # ---- e2e: public API, host buffers, H2D/D2H inside the timed region ------------------------------------
-    e2e = None
-    try:
-        mel_pinned = mel_host.pin_memory()
-        out_host = torch.empty((B, 1, L), dtype=torch.float32).pin_memory()
-        if net is None:
-            # multi-rank: same call sequence as sampling_given_noise_schedule, on this rank's shard
-            def e2e_call(i):
-                m = mel_pinned.to(dev, non_blocking=True)
-                eng.sample(x, m, steps, noise=None, seed=5000 + i, fill_xT=True)
-                out_host.copy_(x, non_blocking=True)
-                torch.cuda.synchronize()
-        else:
-            def e2e_call(i):
-                net.seed = 5000 + i
-                with contextlib.redirect_stdout(sys.stderr):
-                    y = fb.sampling_given_noise_schedule(net, (B, 1, L), dh, sched, condition=mel_pinned.to(dev, non_blocking=True))
-                out_host.copy_(y, non_blocking=True)
-                torch.cuda.synchronize()
-        e2e_call(0)
+    # ---- timed region 1b: the same K calls with two CUDA events around EVERY kernel launch (on its own stream): per-kernel durations for the
+    #      roofline.  Event recording forces plain launches (no graph replay), so this loop is a little slower than region 1.
+    eng.timing_enable(True)
+    eng.timing_report()
+    evi0, evi1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    if clocks:
+        clocks.mark_begin()
+    evi0.record()
+    for i in range(args.steps):
+        one_call(args.warmup + args.steps + i)
+    evi1.record()
+    barrier()
+    if clocks:
+        clocks.mark_end()
+    ms_instr = evi0.elapsed_time(evi1) / args.steps
+    per_kernel = eng.timing_report()
+    eng.timing_enable(False)
+    saturated = eng.check_saturation()
+
+    # ---- timed region 2: e2e, host buffers (H2D of the mels, D2H of the waveform inside) ------------------------------------
+    def timed_host_loop(fn):
+        fn(0)
         barrier()
         if clocks:
             clocks.mark_begin()
         t0 = time.perf_counter()
         for i in range(args.steps):
-            e2e_call(1 + i)
+            fn(1 + i)
         barrier()
         dt = time.perf_counter() - t0
         if clocks:
@@ -363,12 +355,59 @@ def run_ours(args):
         tt = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-        e2e = {"value": world * B * L * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": world * mel_host.numel() * 4,
-               "d2h_bytes_per_step": world * B * L * 4, "ms_per_step": dt / args.steps * 1e3,
-               "api": "fastdiff_b200.sampling_given_noise_schedule" if net is not None else "Engine.sample (batch shard)"}
+        return float(tt.item())
+
+    e2e = None
+    e2e_ref_noise = None
+    lo, hi = sh.my_slice(GB)
+    try:
+        mel_pinned = mel_host.pin_memory()
+        out_host = torch.empty((hi - lo, 1, L), dtype=torch.float32).pin_memory()
+
+        def e2e_call(i):
+            with contextlib.redirect_stdout(sys.stderr):
+                y = sh.sample(size, dh, sched, mel_pinned[lo:hi].to(dev, non_blocking=True), seed=5000 + i, presliced=True)
+            out_host.copy_(y, non_blocking=True)
+            torch.cuda.synchronize()
+        dt = timed_host_loop(e2e_call)
+        e2e = {"value": GB * L * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": GB * 80 * Tm * 4, "d2h_bytes_per_step": GB * L * 4,
+               "ms_per_step": dt / args.steps * 1e3, "api": "fastdiff_b200.shard.ShardedFastDiff.sample (pinned host mel in, pinned host waveform out)",
+               "noise": "device (Philox4x32-10)"}
     except Exception as e:  # pragma: no cover
         log("e2e leg failed:", repr(e))
+    if world == 1:
+        try:   # the drop-in default: reference RNG stream drawn on the host
+            net = fb.FastDiff().to(dev).eval()
+            net.load_state_dict(make_state_dict(1234))
+            net.noise_mode = "reference"
+            if args.mode:
+                net.mode = args.mode
+            eng_r = net.engine(dev)
+            for kv in args.opt:
+                key, val = kv.split("=")
+                eng_r.set_option(key, int(val))
+            n_ref = max(2, min(args.steps, 5))
+            out_r = torch.empty((B, 1, L), dtype=torch.float32).pin_memory()
+
+            def ref_call(i):
+                with contextlib.redirect_stdout(sys.stderr):
+                    y = fb.sampling_given_noise_schedule(net, (B, 1, L), dh, sched, condition=mel_pinned.to(dev, non_blocking=True))
+                out_r.copy_(y, non_blocking=True)
+                torch.cuda.synchronize()
+            ref_call(0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(n_ref):
+                ref_call(i)
+            dt = time.perf_counter() - t0
+            e2e_ref_noise = {"value": B * L * n_ref / dt, "unit": UNIT, "ms_per_step": dt / n_ref * 1e3, "steps": n_ref,
+                             "h2d_bytes_per_step": B * 80 * Tm * 4 + 4 * B * L * 4, "d2h_bytes_per_step": B * L * 4,
+                             "api": "fastdiff_b200.sampling_given_noise_schedule, noise_mode='reference' (the drop-in default: x_T and 3 noise "
+                                    "tensors drawn on the CPU default generator in the reference's order, copied H2D)",
+                             "host_threads": torch.get_num_threads()}
+            del net, eng_r
+        except Exception as e:  # pragma: no cover
+            log("e2e (reference noise) leg failed:", repr(e))
 
     clk = clocks.stop() if clocks else None
     if rank != 0:
@@ -376,41 +415,48 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (live CUDA-event time inside the timed region) -------------------
+    # ---- roofline of the dominant kernel (live CUDA-event time inside the timed region) -------------------------------------
     peaks = measured_peaks()
-    total_ms = sum(v["ms"] for v in per_kernel.values()) or 1.0
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms"]) if per_kernel else None
     roofline = None
-    if dom:
+    frames = B * Tm
+    samples = B * L
+    flop_table = {
+        "kc_gemm": KC_FLOP_PER_FRAME * frames * 3,                    # one launch covers the 3 LVC blocks
+        "lvc_layer_b2": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples,     # dilated conv + LVC at full rate
+        "lvc_layer_b1": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 4,
+        "lvc_layer_b0": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 32,
+    }
+    traffic_tab = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            traffic_tab = json.load(f)
+    except Exception:
+        pass
+    if dom and dom in flop_table:
         n_dom = per_kernel[dom]["n"]
         avg_ms = per_kernel[dom]["ms"] / n_dom
-        frames = B * Tm
-        samples = B * L
-        flop_per_launch = {
-            "kc_gemm": KC_FLOP_PER_FRAME * frames * 3,                    # one launch covers the 3 LVC blocks
-            "lvc_layer_b2": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples,     # dilated conv + LVC at full rate
-            "lvc_layer_b1": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 4,
-            "lvc_layer_b0": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 32,
-        }.get(dom)
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                tr = json.load(f).get(dom)
-            if tr and B == 8 and Tm == 861:
-                traffic = {"bytes_per_launch": tr["bytes_per_launch"], "algorithmic_bytes_per_launch": tr["algorithmic_bytes_per_launch"],
-                           "source": "ncu --set full, " + tr["source"]}
-        except Exception:
-            pass
-        if flop_per_launch:
-            ach = flop_per_launch / (avg_ms * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tensor"], "traffic": traffic, "peak_source": peaks["src"] + " bf16_tflops_sustained (of measured)",
-                        "avg_launch_ms": avg_ms, "launches": n_dom, "share_of_step": per_kernel[dom]["ms"] / (ms_per_step * args.steps),
-                        "algorithmic_flop_per_launch": flop_per_launch, "mode": mode_name}
-    whole = {"achieved_tflops": FLOP_PER_SAMPLE_STEP * 4 * world * B * L / (ms_per_step * 1e-3) / 1e12,
-             "frac_of_bf16_sustained": FLOP_PER_SAMPLE_STEP * 4 * B * L / (ms_per_step * 1e-3) / 1e12 / peaks["tensor"]}
+        flop_per_launch = flop_table[dom]
+        ach = flop_per_launch / (avg_ms * 1e-3) / 1e12
+        tr = traffic_tab.get(dom) if (B, Tm) == (8, 861) else None
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["tensor"], "traffic": tr["dram_bytes_per_launch"] if tr else None,
+                    "traffic_note": ({"source": tr["source"], "layout_minimum_bytes_per_launch": tr.get("layout_minimum_bytes_per_launch"),
+                                      "what": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full); layout_minimum = the bytes this "
+                                              "kernel's data layout must move (rows in + rows out + predicted kernels), NOT SURVEY 8(d)'s algorithmic bytes"}
+                                     if tr else None),
+                    "peak_source": peaks["src"] + " bf16_tflops_sustained (of measured)",
+                    "avg_launch_ms": avg_ms, "launches": n_dom, "share_of_step": per_kernel[dom]["ms"] / (ms_instr * args.steps),
+                    "algorithmic_flop_per_launch": flop_per_launch, "mode": mode_name,
+                    "note": "fp32-level mode: every algorithmic FLOP costs 3 fp16 MMAs, so this kernel's own tensor ceiling is 1/3 of the bf16 peak"}
+    step_alg_bytes = samples * 12 + frames * 320 + 61e6   # x in/out + z per sample, mel, folded fp32 weights once per reverse step
+    whole = {"achieved_tflops": FLOP_PER_SAMPLE_STEP * 4 * GB * L / (ms_per_step * 1e-3) / 1e12,
+             "frac_of_bf16_sustained": FLOP_PER_SAMPLE_STEP * 4 * B * L / (ms_per_step * 1e-3) / 1e12 / peaks["tensor"],
+             "algorithmic_bytes_per_reverse_step": step_alg_bytes,
+             "dram_bytes_per_reverse_step": traffic_tab.get("_per_reverse_step", {}).get("dram_bytes") if (B, Tm) == (8, 861) else None,
+             "dram_bytes_source": traffic_tab.get("_per_reverse_step", {}).get("source") if (B, Tm) == (8, 861) else None}
 
-    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ---------------------------------------------
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ----------------------------------------------------------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
         try:
@@ -430,14 +476,20 @@ def run_ours(args):
         "dtype": "f32" if mode_name != "tc_tf32" else "tf32", "data": "synthetic",
         "config": (bench_config(world) if (B, Tm) == (8, 861) else
                    {**bench_config(world), "workload": f"batch={B} x {Tm * 256 / 22050:.1f} s synthetic mel (T'={Tm}) per GPU, N=4, LJSpeech config, "
-                    "random-init weights", "global_batch": world * B, "frames_per_utterance": Tm}),
-        "arith_mode": mode_name, "noise": "on-device Philox4x32-10 (inside the timed region)",
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+                    "random-init weights", "global_batch": GB, "frames_per_utterance": Tm}),
+        "arith_mode": mode_name, "noise": "on-device Philox4x32-10 (inside the timed region)", "fp16_piece_saturation": bool(saturated),
+        "api": "fastdiff_b200.shard.ShardedFastDiff.sample",
+        "clocks": clk, "e2e": e2e, "e2e_reference_noise": e2e_ref_noise, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "load": {"seconds_incl_pack": load_s, "blob_bytes": sh.blob_bytes, "broadcasts": 1 if world > 1 else 0},
         **({"experiment": {"options": args.opt, "nvcc_extra": os.environ.get("FD_NVCC_EXTRA", "")}} if (args.opt or os.environ.get("FD_NVCC_EXTRA")) else {}),
         "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in per_kernel.items()},
-        "kernel_ms_note": "CUDA events around every launch on its own stream; the DBlock chain runs on a side stream concurrently with embed / "
+        "ms_per_step_instrumented": ms_instr,
+        "kernel_ms_note": "second timed loop of the same K calls with CUDA events around every launch on its own stream (plain launches; `value` comes "
+                          "from the first loop, which replays the library's CUDA graph); the DBlock chain runs on a side stream concurrently with embed / "
                           "kernel predictor / GEMM, so those classes include time spent sharing the SMs and the classes sum to more than ms_per_step",
         "whole_step": whole,
+        "limiter": ("per-step: LVC layers of blocks 1/2 (SIMT epilogues + HBM rows), then the kernel_conv GEMM's 2 GB store stream; "
+                    "across GPUs: nothing collective in the loop -- the residual is max-over-ranks under sw_power_cap"),
     }
     emit(line)
     if world > 1:

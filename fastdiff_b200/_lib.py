@@ -46,6 +46,7 @@ SYMBOLS = {
     "fd_wav_int16": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P]),
     "fd_mel_frontend": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "fd_debug_read": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_size_t), C.c_int, C.c_int, _P, _P]),
+    "fd_set_noise_window": (C.c_int, [_P, C.c_int64, C.c_int64]),
     "fd_launch_count": (C.c_uint64, [_P]),
     "fd_check_saturation": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, _P]),
     "fd_timing_enable": (C.c_int, [_P, C.c_int]),

@@ -39,6 +39,10 @@ struct fd_handle {
                                  // (over block 0's dead predicted kernels) and LVC block 2 reads it like block 1 reads its skip tensor
     int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
+    long long noise_win_L = 0, noise_win_off = 0;   // Philox element window of the device-noise mode (fd_set_noise_window; time-shard mode)
+    int graphs = 1;              // fd_sample in device-noise mode: capture the whole call (all N <= 64 steps) in a CUDA graph on first use and
+                                 // replay it afterwards (option "graphs"; the workspace, shapes, schedule and options are the cache key)
+    uint64_t epoch = 0;          // bumped by everything that changes what a captured graph would do (mode, options, weights, noise window)
     int lvc_p = 1;               // mode tc_3xf16: LVC blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>; option "lvc_p", 0 = k_lvc_layer_h)
     unsigned int* sat_flag = nullptr;   // device word, sticky: an fp16 piece saturated in a tensor-core kernel (fd_check_saturation)
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
@@ -49,6 +53,15 @@ struct fd_handle {
 #endif
     int attrs_set = 0;
     uint64_t launches = 0;
+#ifndef FD_EMU
+    struct GraphEntry {
+        void* ws; int B, Tm, n_steps, ddim, fill_xT; uint64_t epoch; std::vector<fd_step> steps;
+        cudaGraphExec_t exec; uint64_t n_launches; uint64_t last_use;
+    };
+    std::vector<GraphEntry> gcache;
+    uint64_t gtick = 0, graph_replays = 0, graph_captures = 0;
+    unsigned long long* seed_dev = nullptr;   // device word read by the captured noise kernels
+#endif
     std::string err;
     void* tc_state = nullptr;    // tensor-core path resources (tensor maps etc.)
     // optional per-kernel-class device timing (bench.py's live roofline number)
@@ -109,7 +122,7 @@ static const float* sec(const fd_handle* h, int s) { return h->blob + h->sec_off
 
 // ---- workspace layout (floats) ------------------------------------------------------------------
 struct WsLayout {
-    size_t emb, cnoise, hk, hk_hi, hk_lo, kern, d0, d1, d2, xa, xb, total;
+    size_t emb, cnoise, hk, hk_hi, hk_lo, kern, d0, d1, d2, xa, xb, melc, xc, total;
 };
 static WsLayout ws_layout(int B, int Tm) {
     WsLayout w;
@@ -127,6 +140,8 @@ static WsLayout ws_layout(int B, int Tm) {
     w.d2 = o;     o += al((size_t)B * Tm * C);
     w.xa = o;     o += al(lp_rows(B, (int)L) * C);   // (B,L,32) fp32 rows, or the padded piece rows of a layer input (fd_kernels_lvcp.cuh)
     w.xb = o;     o += al(lp_rows(B, (int)L) * C);
+    w.melc = o;   o += al((size_t)B * COND * Tm);   // graph replay (fd_sample): the captured kernels read / write these copies, not the caller's tensors
+    w.xc = o;     o += al((size_t)B * L);
     w.total = o;
     return w;
 }
@@ -170,6 +185,9 @@ extern "C" int fd_create(const fd_config* cfg, int device, fd_handle** out) {
 #endif
     if (cudaMalloc((void**)&h->sat_flag, 64) != cudaSuccess) { delete h; return fail(nullptr, FD_ERR_CUDA, "fd_create: cudaMalloc failed"); }
     cudaMemset(h->sat_flag, 0, 64);
+#ifndef FD_EMU
+    h->seed_dev = reinterpret_cast<unsigned long long*>(h->sat_flag + 4);
+#endif
     *out = h;
     return FD_OK;
 }
@@ -186,6 +204,9 @@ extern "C" void fd_destroy(fd_handle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
+#endif
+#ifndef FD_EMU
+    for (auto& g : h->gcache) cudaGraphExecDestroy(g.exec);
 #endif
     if (h->blob) cudaFree(h->blob);
     if (h->sat_flag) cudaFree(h->sat_flag);
@@ -232,6 +253,7 @@ extern "C" int fd_load_weights(fd_handle* h, const void* blob_host, size_t bytes
     if (cudaMemcpy(nb, blob_host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(nb); return fail(h, FD_ERR_CUDA, "fd_load_weights: copying the blob failed"); }
     if (h->blob) cudaFree(h->blob);
     h->blob = nb;
+    ++h->epoch;
     memcpy(h->sec_off, off, sizeof off); memcpy(h->sec_cnt, cnt, sizeof cnt);
     h->blob_floats = bytes / 4;
     const float* hb = (const float*)blob_host;
@@ -269,6 +291,7 @@ extern "C" int fd_load_weights_dev(fd_handle* h, const void* blob_dev, size_t by
     }
     if (h->blob) cudaFree(h->blob);
     h->blob = nb;
+    ++h->epoch;
     memcpy(h->sec_off, off, sizeof off); memcpy(h->sec_cnt, cnt, sizeof cnt);
     memcpy(h->final_w, fw, sizeof fw); h->final_b = fb;
     h->blob_floats = bytes / 4;
@@ -298,12 +321,22 @@ extern "C" int fd_set_mode(fd_handle* h, int mode) {
 #endif
     h->mode = mode;
     h->mode_set_by_user = 1;
+    ++h->epoch;
     return FD_OK;
 }
 extern "C" int fd_get_mode(fd_handle* h) { return h ? h->mode : FD_ERR_INVALID; }
 
+extern "C" int fd_set_noise_window(fd_handle* h, int64_t total_samples, int64_t offset) {
+    if (!h || total_samples < 0 || offset < 0 || (total_samples && offset >= total_samples)) return fail(h, FD_ERR_INVALID, "fd_set_noise_window: bad window");
+    h->noise_win_L = total_samples; h->noise_win_off = offset;
+    ++h->epoch;
+    return FD_OK;
+}
+
 extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!h || !key) return FD_ERR_INVALID;
+    ++h->epoch;
+    if (!strcmp(key, "graphs")) { h->graphs = (int)value; return FD_OK; }
     if (!strcmp(key, "stop_after")) { h->stop_after = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_dblock")) { h->tc_dblock = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_kp")) { h->tc_kp = (int)value; return FD_OK; }
@@ -570,11 +603,12 @@ static int emu_lvc_p_layer(fd_handle* h, int blk, int layer, const float* p_in, 
     LvcPParams p;
     p.cw16 = sec(h, blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16) + (size_t)layer * (LP_CW_BYTES / 4);
     p.conv_b = sec(h, FD_S_LB0_CONV_B + blk * FD_LB_STRIDE) + layer * C;
-    p.first_w = sec(h, FD_S_FIRST_W); p.first_b = sec(h, FD_S_FIRST_B);
+    p.first16 = sec(h, FD_S_FIRST_F16);
     p.p_in = p_in; p.skip = skip; p.kern = kern; p.p_out = p_out; p.f_out = f_out; p.sat = h->sat_flag;
     p.B = B; p.T = T; p.Tm = Tm; p.dil = dil;
     p.inv_c = 1.f / (S16_ACT * emu_scale16(h, 4 + 4 * blk + layer));
     p.inv_l = 1.f / (S16_ACT * S16_KERN);
+    p.inv_sk = 1.f / (LP_S_AU * emu_scale16(h, 40));
     const int tiles = B * ((T + LP_TT - 1) / LP_TT);
     int grid = (tiles + 3) / 4; if (grid < 1) grid = 1; if (grid > 8) grid = 8;   // a few tiles per CTA: carried rows, kernel reuse, every ring wraps
     if (blk == 1) { auto k = k_lvc_p<64>;  FD_LAUNCH(k, dim3(grid), dim3(LP_THREADS), (lp_smem_bytes<64>()), st, p); }
@@ -889,6 +923,7 @@ static void fill_final(const fd_handle* h, FinalParams& fp) {
     memcpy(fp.w, h->final_w, sizeof fp.w);
     fp.b = h->final_b;
     fp.mode = 0; fp.coef = 0; fp.div = 1; fp.sigma = 0; fp.c1 = fp.c2 = fp.c3 = 0; fp.add_noise = 0; fp.draw = 0; fp.seed = 0;
+    fp.win.win_L = h->noise_win_L; fp.win.win_off = h->noise_win_off; fp.seed_ptr = nullptr;
 }
 
 extern "C" int fd_denoise(fd_handle* h, const float* x_dev, const float* mel_dev, const float* t_dev, float* eps_dev,
@@ -917,27 +952,19 @@ extern "C" int fd_denoise(fd_handle* h, const float* x_dev, const float* mel_dev
     return FD_OK;
 }
 
-extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const fd_step* steps, int n_steps,
-                         const float* noise_dev, int n_noise, uint64_t seed, int fill_xT, int ddim, float* seq_dev,
-                         int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream) {
-    int rc = check_args(h, x_dev, mel_dev, steps, B, Tm, workspace_dev, workspace_bytes);
-    if (rc) return rc;
-    if (n_steps < 0) return fail(h, FD_ERR_INVALID, "n_steps < 0");
-    int need = 0;
-    if (!ddim) for (int i = 0; i < n_steps; ++i) need += steps[i].add_noise ? 1 : 0;
-    if (noise_dev && n_noise < need) return fail(h, FD_ERR_INVALID, "noise_dev holds %d draws, the schedule needs %d", n_noise, need);
-    FD_CUDA(h, cudaSetDevice(h->device));
-    rc = setup_attrs(h);
-    if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    float* ws = (float*)workspace_dev;
+// The N-step loop of util.py:216-234 as a sequence of launches on `st` (no host synchronisation).  seed_ptr != nullptr: the noise kernels
+// read the seed from that device word (graph replay).
+static int sample_body(fd_handle* h, float* x_dev, const float* mel_dev, const fd_step* steps, int n_steps, const float* noise_dev, uint64_t seed,
+                       const unsigned long long* seed_ptr, int fill_xT, int ddim, float* seq_dev, int B, int Tm, float* ws, cudaStream_t st) {
     const WsLayout w = ws_layout(B, Tm);
     const int L = Tm * HOP_TOTAL;
     const size_t n = (size_t)B * L;
+    int rc;
     FD_CUDA(h, cudaMemsetAsync(ws + w.hk, 0, (w.kern - w.hk) * 4, st));
+    NoiseWin win; win.win_L = h->noise_win_L; win.win_off = h->noise_win_off;
     if (fill_xT) {
         ScopedTimer tm(h, KC_FILL, st);
-        FD_LAUNCH(k_fill_normal, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x_dev, n, seed, 0u);
+        FD_LAUNCH(k_fill_normal, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x_dev, L, n, seed, 0u, win, seed_ptr);
         FD_CHECK_LAUNCH(h, "k_fill_normal");
     }
     if (seq_dev) FD_CUDA(h, cudaMemcpyAsync(seq_dev, x_dev, n * 4, cudaMemcpyDeviceToDevice, st));
@@ -954,6 +981,7 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
         if (rc) return rc;
         FinalParams fp;
         fill_final(h, fp);
+        fp.seed_ptr = seed_ptr;
         const float* z = nullptr;
         if (ddim) {
             fp.mode = 2; fp.c1 = steps[i].c1; fp.c2 = steps[i].c2; fp.c3 = steps[i].c3;
@@ -973,6 +1001,69 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
         FD_CHECK_LAUNCH(h, "k_final");
     }
     return FD_OK;
+}
+
+extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const fd_step* steps, int n_steps,
+                         const float* noise_dev, int n_noise, uint64_t seed, int fill_xT, int ddim, float* seq_dev,
+                         int B, int Tm, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    int rc = check_args(h, x_dev, mel_dev, steps, B, Tm, workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    if (n_steps < 0) return fail(h, FD_ERR_INVALID, "n_steps < 0");
+    int need = 0;
+    if (!ddim) for (int i = 0; i < n_steps; ++i) need += steps[i].add_noise ? 1 : 0;
+    if (noise_dev && n_noise < need) return fail(h, FD_ERR_INVALID, "noise_dev holds %d draws, the schedule needs %d", n_noise, need);
+    FD_CUDA(h, cudaSetDevice(h->device));
+    rc = setup_attrs(h);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ws = (float*)workspace_dev;
+#ifndef FD_EMU
+    // ---- graph replay: device-noise mode, the whole call (N <= 64 reverse steps) captured once per (workspace, shape, schedule, options) ----
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (h->graphs && !h->timing && !noise_dev && !seq_dev && n_steps >= 1 && n_steps <= h->emb_slots && h->stop_after >= 99 &&
+        cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+        const WsLayout w = ws_layout(B, Tm);
+        const size_t nx = (size_t)B * Tm * HOP_TOTAL;
+        fd_handle::GraphEntry* hit = nullptr;
+        for (auto& g : h->gcache)
+            if (g.ws == workspace_dev && g.B == B && g.Tm == Tm && g.n_steps == n_steps && g.ddim == (ddim ? 1 : 0) && g.fill_xT == (fill_xT ? 1 : 0) &&
+                g.epoch == h->epoch && !memcmp(g.steps.data(), steps, sizeof(fd_step) * n_steps)) { hit = &g; break; }
+        if (!hit) {
+            cudaGraph_t graph = nullptr;
+            const uint64_t l0 = h->launches;
+            FD_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = sample_body(h, ws + w.xc, ws + w.melc, steps, n_steps, nullptr, 0, h->seed_dev, fill_xT, ddim, nullptr, B, Tm, ws, st);
+            cudaError_t ec = cudaStreamEndCapture(st, &graph);
+            const uint64_t nl = h->launches - l0;
+            h->launches = l0;
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ec != cudaSuccess || !graph) return fail(h, FD_ERR_CUDA, "fd_sample: stream capture failed: %s", cudaGetErrorString(ec));
+            cudaGraphExec_t exec = nullptr;
+            ec = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ec != cudaSuccess) return fail(h, FD_ERR_CUDA, "fd_sample: cudaGraphInstantiate failed: %s", cudaGetErrorString(ec));
+            if (h->gcache.size() >= 6) {   // drop the least recently used entry
+                size_t lru = 0;
+                for (size_t i = 1; i < h->gcache.size(); ++i) if (h->gcache[i].last_use < h->gcache[lru].last_use) lru = i;
+                cudaGraphExecDestroy(h->gcache[lru].exec);
+                h->gcache.erase(h->gcache.begin() + lru);
+            }
+            h->gcache.push_back({workspace_dev, B, Tm, n_steps, ddim ? 1 : 0, fill_xT ? 1 : 0, h->epoch, std::vector<fd_step>(steps, steps + n_steps), exec, nl, 0});
+            hit = &h->gcache.back();
+            ++h->graph_captures;
+        }
+        hit->last_use = ++h->gtick;
+        FD_CUDA(h, cudaMemcpyAsync(ws + w.melc, mel_dev, (size_t)B * COND * Tm * 4, cudaMemcpyDeviceToDevice, st));
+        if (!fill_xT) FD_CUDA(h, cudaMemcpyAsync(ws + w.xc, x_dev, nx * 4, cudaMemcpyDeviceToDevice, st));
+        k_set_u64<<<1, 1, 0, st>>>(h->seed_dev, (unsigned long long)seed);
+        FD_CUDA(h, cudaGraphLaunch(hit->exec, st));
+        FD_CUDA(h, cudaMemcpyAsync(x_dev, ws + w.xc, nx * 4, cudaMemcpyDeviceToDevice, st));
+        h->launches += hit->n_launches + 1;
+        ++h->graph_replays;
+        return FD_OK;
+    }
+#endif
+    return sample_body(h, x_dev, mel_dev, steps, n_steps, noise_dev, seed, nullptr, fill_xT, ddim, seq_dev, B, Tm, ws, st);
 }
 
 // The step before the path: wav (B, n) -> log10-mel (B, 80, 1 + n/256), the reference's process_utterance

@@ -53,13 +53,15 @@
  *                           {ci 64..79: one tile with rows [16 ci hi (32 B) | 16 ci lo (32 B) | 64 B zero], then 8 KB unused}
  *             slots 10..27: residual convs l = 0..5, taps j = 0..2: {hi tile 8 KB | lo tile 8 KB} over the 64 input channels
  *   SCALES16  [64]  S of: kernel_conv block n at [n]; lvc_blocks.n.convs.l at [4 + 4 n + l];
- *                   kernel predictor of block n: input_conv at [16 + 8 n], residual conv l at [17 + 8 n + l]
+ *                   kernel predictor of block n: input_conv at [16 + 8 n], residual conv l at [17 + 8 n + l]; FIRST_F16 at [40]
+ *   FIRST_F16 [32 co][128 B]  first_audio_conv as the B operand of the skip MMA of LVC block 2 (fd_kernels_lvcp.cuh): per output channel
+ *                   K = 16 fp16 [tap 0..6, bias, 0 x 8] hi (chunks 0, 1) | the same lo (chunks 2, 3) | zeros; 16-byte chunk c at c ^ (co & 7)
  */
 #ifndef FD_BLOB_H
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 12ULL
+#define FD_BLOB_VERSION 13ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */
@@ -78,7 +80,7 @@
     X(DB0_CONVT_HI) X(DB0_CONVT_LO) X(DB0_REST_HI) X(DB0_REST_LO) \
     X(LB1_UPT_HI) X(LB1_UPT_LO) X(LB2_UPT_HI) X(LB2_UPT_LO) \
     X(LB0_KCT_F16) X(LB1_KCT_F16) X(LB2_KCT_F16) X(LB1_CONV_F16) X(LB2_CONV_F16) \
-    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(LB0_CONV_F16) X(LB0_KCT_F16P) X(LB0_KC_BP) X(SCALES16)
+    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(LB0_CONV_F16) X(LB0_KCT_F16P) X(LB0_KC_BP) X(FIRST_F16) X(SCALES16)
 /* FD_SECTIONS_END */
 
 enum fd_section {

@@ -46,16 +46,18 @@ __host__ __device__ inline size_t lp_rows(int B, int T) { return (size_t)LP_HEAD
 __host__ __device__ inline size_t lp_row_of(int b, int T, int t) { return (size_t)LP_HEAD_ROWS + (size_t)b * (T + LP_PAD_ROWS) + t; }
 
 template <int HOP> __host__ __device__ constexpr int lp_nf() { return HOP >= LP_TT ? 1 : LP_TT / HOP; }
+constexpr int LP_SKA_BYTES = 16384;              // hop 256: audio im2col tile of the skip MMA, 128 rows x 128 B (64 B used)
+constexpr int LP_SKB_BYTES = 4096;               // hop 256: first_audio_conv pieces (FIRST_F16), 32 rows x 128 B
+constexpr float LP_S_AU = 256.f;                 // prescale of the audio pieces (|audio| < 255 before saturation)
 template <int HOP> __host__ __device__ constexpr int lp_smem_bytes() {
-    return LP_NA * LP_STAGE_BYTES + 2 * LP_Y_BYTES + 2 * lp_nf<HOP>() * 24576 + (HOP == 256 ? 2 * LP_OUT_BYTES : 0) + LP_CW_BYTES +
-           (7 * C + C + C) * 4 + 512 + 24 * 8 + 64 + 1024;
+    return LP_NA * LP_STAGE_BYTES + 2 * LP_Y_BYTES + 2 * lp_nf<HOP>() * 24576 + (HOP == 256 ? 2 * LP_OUT_BYTES + LP_SKA_BYTES + LP_SKB_BYTES : 0) +
+           LP_CW_BYTES + C * 4 + 512 + 24 * 8 + 64 + 1024;
 }
 
 struct LvcPParams {
     const float* cw16;       // [3 taps][32 co][128 B] SWIZZLE_128B image of this layer's dilated conv (LBn_CONV_F16)
     const float* conv_b;     // [32]
-    const float* first_w;    // [7][32]  (hop 256: skip = first_conv(audio))
-    const float* first_b;    // [32]
+    const float* first16;    // hop 256: FIRST_F16 image (skip = first_conv(audio) as a K = 16 MMA: 7 taps + bias against a constant one)
     const float* p_in;       // padded piece rows of z = x + skip (input of this layer)
     const float* skip;       // hop 256: audio (B, T); hop 64: skip rows (B, T, 32) fp32
     const float* kern;       // this layer's slice of the predicted kernels: per (b, frame) at stride KCN floats
@@ -64,6 +66,7 @@ struct LvcPParams {
     unsigned int* sat;       // sticky flag: an fp16 piece saturated (|16 * activation| > 65504); may be nullptr
     int B, T, Tm, dil;
     float inv_c, inv_l;
+    float inv_sk;            // hop 256: 1 / (LP_S_AU * S(FIRST_F16))
 };
 
 // zero rows of a padded piece buffer: block 0 -> the 32 head rows, block i >= 1 -> the 64 rows after item i - 1
@@ -90,29 +93,30 @@ template <int HOP>
 __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     constexpr int NF = lp_nf<HOP>();
     constexpr bool STAGE_OUT = (HOP == 256);
+    constexpr bool SKIP_MMA = (HOP == 256);            // skip = first_conv(audio) on the tensor core; hop 64 loads skip rows from memory
     constexpr int W_BYTES = NF * 24576;
-    constexpr uint32_t LACC0 = 128, LSTRIDE = NF * 64;
-    constexpr uint32_t TCOLS = (LACC0 + 2 * LSTRIDE) <= 256 ? 256 : 512;
+    constexpr uint32_t LACC0 = 128, LSTRIDE = NF * 64, SKACC0 = 384;
+    constexpr uint32_t TCOLS = 512;
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* a_st = smem;                                        // [3][LP_STAGE_BYTES]
     unsigned char* y_t = a_st + LP_NA * LP_STAGE_BYTES;                // [2][LP_Y_BYTES]
     unsigned char* w_t = y_t + 2 * LP_Y_BYTES;                         // [2][W_BYTES]
     unsigned char* o_t = w_t + 2 * W_BYTES;                            // [2][LP_OUT_BYTES] (STAGE_OUT)
-    unsigned char* cw = o_t + (STAGE_OUT ? 2 * LP_OUT_BYTES : 0);      // [3 taps][32 rows][128 B]
-    float* fw_s = (float*)(cw + LP_CW_BYTES);                          // [7][32]
-    float* fb_s = fw_s + 7 * C;                                        // [32]
-    float* cbs_s = fb_s + C;                                           // [32] conv bias * S16_ACT
+    unsigned char* sk_a = o_t + (STAGE_OUT ? 2 * LP_OUT_BYTES : 0);    // [128 rows][128 B] audio im2col pieces (SKIP_MMA)
+    unsigned char* sk_b = sk_a + (SKIP_MMA ? LP_SKA_BYTES : 0);        // [32 rows][128 B] first conv pieces (SKIP_MMA)
+    unsigned char* cw = sk_b + (SKIP_MMA ? LP_SKB_BYTES : 0);          // [3 taps][32 rows][128 B]
+    float* cbs_s = (float*)(cw + LP_CW_BYTES);                         // [32] conv bias * S16_ACT
     unsigned char* carry = (unsigned char*)(cbs_s + C);                // [2][256 B]: Y rows 0, 1 of the previous tile
     uint64_t* bars = (uint64_t*)(carry + 512);
-    uint64_t* a_full = bars;            // [3] loader -> MMA, gate epilogue (tx)
+    uint64_t* a_full = bars;            // [3] loader -> MMA, both epilogues (tx)
     uint64_t* a_free = bars + 3;        // [3] gate epilogue (16 warps) -> loader
     uint64_t* w_full = bars + 6;        // [2] loader -> MMA (tx)
     uint64_t* w_free = bars + 8;        // [2] MMA commit -> loader
     uint64_t* cacc_full = bars + 10;    // [2] conv MMAs committed -> conv epilogue
     uint64_t* cacc_free = bars + 12;    // [2] conv epilogue (4 warps) -> MMA
-    uint64_t* y_full = bars + 14;       // [2] conv epilogue (4 warps) -> MMA
-    uint64_t* lacc_full = bars + 16;    // [2] LVC MMAs committed -> gate epilogue; also "Y tile free" for the conv epilogue
+    uint64_t* y_full = bars + 14;       // [2] conv epilogue (4 warps) -> MMA: Y tile, skip operand tile, prescaled LVC bias are in place
+    uint64_t* lacc_full = bars + 16;    // [2] LVC (+ skip) MMAs committed -> gate epilogue; also "Y tile / skip tile free" for the conv epilogue
     uint64_t* lacc_free = bars + 18;    // [2] gate epilogue (16 warps) -> MMA
     uint32_t* tmem_base_s = (uint32_t*)(bars + 24);
 
@@ -130,8 +134,12 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     {
         const float4* src = reinterpret_cast<const float4*>(p.cw16);
         for (int i = tid; i < LP_CW_BYTES / 16; i += LP_THREADS) reinterpret_cast<float4*>(cw)[i] = src[i];
-        if (tid < 7 * C) fw_s[tid] = HOP == 256 ? p.first_w[tid] : 0.f;
-        if (tid < C) { fb_s[tid] = HOP == 256 ? p.first_b[tid] : 0.f; cbs_s[tid] = p.conv_b[tid] * S16_ACT; }
+        if (SKIP_MMA) {
+            const float4* s16 = reinterpret_cast<const float4*>(p.first16);
+            for (int i = tid; i < LP_SKB_BYTES / 16; i += LP_THREADS) reinterpret_cast<float4*>(sk_b)[i] = s16[i];
+            for (int i = tid; i < LP_SKA_BYTES / 16; i += LP_THREADS) reinterpret_cast<float4*>(sk_a)[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // K 8..15 stay zero
+        }
+        if (tid < C) cbs_s[tid] = p.conv_b[tid] * S16_ACT;
     }
     fence_async_smem();
     tc_fence_before();
@@ -142,58 +150,59 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     const int ntt = (T + LP_TT - 1) / LP_TT, total = B * ntt;
     const int chunk = (total + (int)gridDim.x - 1) / (int)gridDim.x;
     const int tile_lo = (int)blockIdx.x * chunk, tile_hi = min(total, tile_lo + chunk);
-    const int ntile = tile_hi > tile_lo ? tile_hi - tile_lo : 0;          // this CTA walks tiles tile_hi-1 .. tile_lo
+    const int ntile = tile_hi > tile_lo ? tile_hi - tile_lo : 0;          // this CTA walks tiles tile_hi-1 .. tile_lo (descending)
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    // (b, tt) of the walk's first tile; every role then steps them down itself (no per-tile division)
+    const int b_first = ntile ? (tile_hi - 1) / ntt : 0, tt_first = ntile ? (tile_hi - 1) % ntt : 0;
+    const bool has_skip = (p.p_out != nullptr);   // the skip of the NEXT layer's "x += audio_down" is added to the rows this layer produces
 
     if (warp_u == 20) {
         // =========================================== loader ===========================================
         if (elect_one()) {
-            int wc = 0;
-            long long prev_frame = -1;
+            int wc = 0, b = b_first, tt = tt_first, s = 0, sn = 0;     // s = n % 3, sn = n / 3
+            bool new_frame = true;
             for (int n = 0; n < ntile; ++n) {
-                const int tile = tile_hi - 1 - n, b = tile / ntt, t0 = (tile % ntt) * LP_TT;
-                const int s = n % LP_NA;
+                const int t0 = tt * LP_TT;
                 unsigned char* a = a_st + s * LP_STAGE_BYTES;
                 float* lbias = (float*)(a + 24576);
                 float* au = lbias + 128;
-                mbar_wait(&a_free[s], (uint32_t)(((n / LP_NA) & 1) ^ 1));
+                mbar_wait(&a_free[s], (uint32_t)((sn & 1) ^ 1));
                 const int ar0 = 31 - dil, nrows = 130 + 2 * dil;
                 int i0 = 0, i1 = 0;
-                if (HOP == 256) { i0 = t0 == 0 ? 4 : 0; i1 = min(LP_AU, T - t0 + 4); }
+                if (SKIP_MMA && has_skip) { i0 = t0 == 0 ? 4 : 0; i1 = min(LP_AU, T - t0 + 4); }
+                const int f0 = t0 / HOP;
                 uint32_t bytes = (uint32_t)nrows * 128u + (uint32_t)(i1 - i0) * 4u;
 #pragma unroll
-                for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) bytes += 256u;
+                for (int fi = 0; fi < NF; ++fi) if (f0 + fi < Tm) bytes += 256u;
                 mbar_expect_tx(&a_full[s], bytes);
                 bulk_g2s(a + ar0 * 128, p.p_in + (lp_row_of(b, T, t0 - 32 + ar0)) * C, (uint32_t)nrows * 128u, &a_full[s]);
-                if (HOP == 256) bulk_g2s(au + i0, p.skip + (size_t)b * T + (t0 - 4 + i0), (uint32_t)(i1 - i0) * 4u, &a_full[s]);
+                if (i1 > i0) bulk_g2s(au + i0, p.skip + (size_t)b * T + (t0 - 4 + i0), (uint32_t)(i1 - i0) * 4u, &a_full[s]);
 #pragma unroll
-                for (int fi = 0; fi < NF; ++fi) {
-                    const int f = t0 / HOP + fi;
-                    if (f < Tm) bulk_g2s(lbias + fi * 64, p.kern + ((size_t)b * Tm + f) * KCN + KK * LVC_OUT, 256u, &a_full[s]);
-                }
+                for (int fi = 0; fi < NF; ++fi)
+                    if (f0 + fi < Tm) bulk_g2s(lbias + fi * 64, p.kern + ((size_t)b * Tm + f0 + fi) * KCN + KK * LVC_OUT, 256u, &a_full[s]);
                 // predicted kernels: hop 256 -> one frame serves two tiles (walked back to back); hop 64 -> two frames per tile
                 if (HOP == 256) {
-                    const long long frame = (long long)b * Tm + t0 / HOP;
-                    if (frame != prev_frame) {
+                    if (new_frame) {
                         const int ws = wc & 1;
                         mbar_wait(&w_free[ws], (uint32_t)(((wc >> 1) & 1) ^ 1));
                         mbar_expect_tx(&w_full[ws], 24576u);
-                        bulk_g2s(w_t + ws * W_BYTES, p.kern + (size_t)frame * KCN, 24576u, &w_full[ws]);
-                        prev_frame = frame; ++wc;
+                        bulk_g2s(w_t + ws * W_BYTES, p.kern + ((size_t)b * Tm + f0) * KCN, 24576u, &w_full[ws]);
+                        ++wc;
                     }
+                    new_frame = !(tt & 1);      // the next tile (b, tt - 1) shares this frame iff tt is odd
                 } else {
                     const int ws = n & 1;
                     mbar_wait(&w_free[ws], (uint32_t)(((n >> 1) & 1) ^ 1));
                     uint32_t wb = 0;
 #pragma unroll
-                    for (int fi = 0; fi < NF; ++fi) if (t0 / HOP + fi < Tm) wb += 24576u;
+                    for (int fi = 0; fi < NF; ++fi) if (f0 + fi < Tm) wb += 24576u;
                     mbar_expect_tx(&w_full[ws], wb);
 #pragma unroll
-                    for (int fi = 0; fi < NF; ++fi) {
-                        const int f = t0 / HOP + fi;
-                        if (f < Tm) bulk_g2s(w_t + ws * W_BYTES + fi * 24576, p.kern + ((size_t)b * Tm + f) * KCN, 24576u, &w_full[ws]);
-                    }
+                    for (int fi = 0; fi < NF; ++fi)
+                        if (f0 + fi < Tm) bulk_g2s(w_t + ws * W_BYTES + fi * 24576, p.kern + ((size_t)b * Tm + f0 + fi) * KCN, 24576u, &w_full[ws]);
                 }
+                if (--tt < 0) { tt = ntt - 1; --b; new_frame = true; }
+                if (++s == LP_NA) { s = 0; ++sn; }
             }
         }
         __syncwarp();
@@ -201,24 +210,22 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
         // =========================================== MMA issuer ===========================================
         constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 64);
         const uint32_t a_u = smem_u32(a_st), y_u = smem_u32(y_t), w_u = smem_u32(w_t), cw_u = smem_u32(cw);
-        int wc = 0, cur_ws = 0;
-        long long prev_frame = -1;
-        auto lvc_mmas = [&](int m) {     // M2(m): LVC MMAs of the CTA's m-th tile
-            const int tile = tile_hi - 1 - m, b = tile / ntt, t0 = (tile % ntt) * LP_TT;
+        const uint32_t ska_u = smem_u32(sk_a), skb_u = smem_u32(sk_b);
+        int wc = 0, cur_ws = 0, mb_tt = tt_first;                 // M2 runs one tile behind C: its own tile-in-item counter
+        bool m_new_frame = true;
+        auto lvc_mmas = [&](int m) {     // M2(m): LVC (+ skip) MMAs of the CTA's m-th tile
+            const int t0 = mb_tt * LP_TT, f0 = t0 / HOP;
             const int ys = m & 1;
             mbar_wait(&y_full[ys], (uint32_t)((m >> 1) & 1));
             bool last_use = true;
             if (HOP == 256) {
-                const long long frame = (long long)b * Tm + t0 / HOP;
-                if (frame != prev_frame) {
+                if (m_new_frame) {
                     cur_ws = wc & 1;
                     mbar_wait(&w_full[cur_ws], (uint32_t)((wc >> 1) & 1));
-                    prev_frame = frame; ++wc;
+                    ++wc;
                 }
-                if (m + 1 < ntile) {   // the next tile of the walk uses the same frame iff it is (b, tt - 1) with tt odd
-                    const int tn = tile - 1;
-                    last_use = !((tn / ntt) == b && ((tn % ntt) * LP_TT) / HOP == t0 / HOP);
-                }
+                last_use = !((mb_tt & 1) && m + 1 < ntile);   // the next tile of the walk uses the same frame iff tt is odd (and it exists)
+                m_new_frame = !(mb_tt & 1);
             } else {
                 cur_ws = m & 1;
                 mbar_wait(&w_full[cur_ws], (uint32_t)((m >> 1) & 1));
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             if (elect_one()) {
 #pragma unroll
                 for (int fi = 0; fi < NF; ++fi) {
-                    if (t0 / HOP + fi < Tm) {
+                    if (f0 + fi < Tm) {
                         const uint32_t d = tmem_base + LACC0 + (uint32_t)ys * LSTRIDE + fi * 64;
                         const uint32_t lwb = wt + fi * 24576;
 #pragma unroll
@@ -246,16 +253,27 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                         }
                     }
                 }
+                if (SKIP_MMA && has_skip) {   // skip[128 x 32] = audio im2col [128 x 16] x first conv [16 x 32], three piece passes
+                    uint32_t sa = ska_u, sb = skb_u;
+                    FD_OPAQUE2(sa, sb);
+                    const uint32_t d = tmem_base + SKACC0 + (uint32_t)ys * 32;
+                    const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + 32);
+                    const uint64_t bh = umma_desc_sw128(sb), bl = umma_desc_sw128(sb + 32);
+                    umma_f16(d, ah, bh, idesc_conv, 0u);
+                    umma_f16(d, ah, bl, idesc_conv, 1u);
+                    umma_f16(d, al, bh, idesc_conv, 1u);
+                }
                 tc_commit(&lacc_full[ys]);
                 if (last_use) tc_commit(&w_free[cur_ws]);
             }
             __syncwarp();
+            if (--mb_tt < 0) { mb_tt = ntt - 1; m_new_frame = true; }
         };
+        int tt = tt_first, s = 0, sn = 0;
         for (int n = 0; n < ntile; ++n) {
-            const int tile = tile_hi - 1 - n, tt = tile % ntt;
-            const int s = n % LP_NA, cs = n & 1;
+            const int cs = n & 1;
             const bool have_carry = (n > 0) && (tt != ntt - 1);
-            mbar_wait(&a_full[s], (uint32_t)((n / LP_NA) & 1));
+            mbar_wait(&a_full[s], (uint32_t)(sn & 1));
             mbar_wait(&cacc_free[cs], (uint32_t)(((n >> 1) & 1) ^ 1));
             tc_fence_after();
             uint32_t at = a_u + (uint32_t)s * LP_STAGE_BYTES, cwt = cw_u;
@@ -283,19 +301,25 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             }
             __syncwarp();
             if (n >= 1) lvc_mmas(n - 1);
+            if (--tt < 0) tt = ntt - 1;
+            if (++s == LP_NA) { s = 0; ++sn; }
         }
         if (ntile > 0) lvc_mmas(ntile - 1);
     } else if (warp_u < 4) {
         // =========================================== conv epilogue (4 warps) ===========================================
         const int q = warp;                       // TMEM lane quarter
-        const int yr = q * 32 + lane;             // Y row of this thread <-> t = t0 - 1 + yr
+        const int yr = q * 32 + lane;             // Y row of this thread <-> t = t0 - 1 + yr; also skip-operand row <-> t = t0 + yr
         const float inv_cs = p.inv_c * S16_ACT;
         float vmax = 0.f;
+        int tt = tt_first, s = 0, sn = 0;
         for (int n = 0; n < ntile; ++n) {
-            const int tile = tile_hi - 1 - n, tt = tile % ntt, t0 = tt * LP_TT;
+            const int t0 = tt * LP_TT;
             const int cs = n & 1;
             const bool have_carry = (n > 0) && (tt != ntt - 1);
             unsigned char* yt = y_t + cs * LP_Y_BYTES;
+            unsigned char* a = a_st + s * LP_STAGE_BYTES;
+            float* lbias = (float*)(a + 24576);
+            float* au = lbias + 128;
             mbar_wait(&cacc_full[cs], (uint32_t)((n >> 1) & 1));
             tc_fence_after();
             uint32_t v[32];
@@ -311,8 +335,8 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                     float y[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float a = fmaf(__uint_as_float(acc[c * 8 + e]), inv_cs, cbs_s[c * 8 + e]);
-                        y[e] = in ? fmaxf(a, 0.2f * a) : 0.f;
+                        const float x = fmaf(__uint_as_float(acc[c * 8 + e]), inv_cs, cbs_s[c * 8 + e]);
+                        y[e] = in ? fmaxf(x, 0.2f * x) : 0.f;
                     }
                     uint4 hi, lo;
                     lp_split8(y, hi, lo, vmax);
@@ -337,9 +361,30 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&cacc_free[cs]);   // both accumulators of this stage have been read
+            // ---- work taken off the gate epilogue's hands: LVC bias prescaled by the gate's exponent constants; skip operand tile ----
+            mbar_wait(&a_full[s], (uint32_t)(sn & 1));
+            if (yr < NF * 64) lbias[yr] *= ((yr & 63) < 32) ? -1.4426950408889634f : -2.8853900817779268f;   // sigmoid half: e^-a; tanh half: e^-2b
+            if (SKIP_MMA && has_skip) {
+                if (t0 == 0 || t0 + LP_AU - 4 > T) {   // audio positions outside [0, T) are zero (the first conv zero-pads); only utterance ends
+                    for (int i = yr; i < LP_AU; i += 128) { const int pos = t0 - 4 + i; if (pos < 0 || pos >= T) au[i] = 0.f; }
+                    group_sync(2, 128);
+                }
+                if (n >= 1) mbar_wait(&lacc_full[cs ^ 1], (uint32_t)(((n - 1) >> 1) & 1));   // the skip MMAs of tile n-1 have read the operand tile
+                float x[8];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) x[k] = au[yr + 1 + k] * LP_S_AU;    // audio position t + k - 3
+                x[7] = LP_S_AU;                                                  // constant one: the bias rides as an eighth tap
+                uint4 hi, lo;
+                lp_split8(x, hi, lo, vmax);
+                const int sw = yr & 7;
+                *reinterpret_cast<uint4*>(sk_a + yr * 128 + ((0 ^ sw) << 4)) = hi;
+                *reinterpret_cast<uint4*>(sk_a + yr * 128 + ((2 ^ sw) << 4)) = lo;
+            }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&y_full[cs]);
+            if (--tt < 0) tt = ntt - 1;
+            if (++s == LP_NA) { s = 0; ++sn; }
         }
         if (p.sat && vmax > F16_MAX) *p.sat = 1u;
     } else {
@@ -348,39 +393,25 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
         const int r = q * 32 + lane;                            // output row of this thread
         const int etid = tid - 128;                             // 0 .. 511
         const int fi = (HOP >= LP_TT) ? 0 : r / HOP;            // warp-uniform (HOP is a multiple of 32)
+        // everything below runs in the x16 domain of the pieces (exact: powers of two): z16 = 16 z, gate x 16, skip x 16
+        const float c_s = p.inv_l * -1.4426950408889634f, c_t = p.inv_l * -2.8853900817779268f, c_sk = p.inv_sk * S16_ACT;
         float vmax = 0.f;
+        int b = b_first, tt = tt_first, s = 0, sn = 0;
         for (int n = 0; n < ntile; ++n) {
-            const int tile = tile_hi - 1 - n, b = tile / ntt, t0 = (tile % ntt) * LP_TT;
-            const int s = n % LP_NA, ls = n & 1, t = t0 + r;
+            const int t0 = tt * LP_TT;
+            const int ls = n & 1, t = t0 + r;
             const unsigned char* a = a_st + s * LP_STAGE_BYTES;
             const float* lbias = (const float*)(a + 24576);
-            float* au = (float*)(a + 24576) + 128;
-            mbar_wait(&a_full[s], (uint32_t)((n / LP_NA) & 1));
-            if (HOP == 256 && (t0 == 0 || t0 + LP_AU - 4 > T)) {   // audio positions outside [0, T) are zero (the first conv zero-pads)
-                if (etid < LP_AU) { const int pos = t0 - 4 + etid; if (pos < 0 || pos >= T) au[etid] = 0.f; }
-                group_sync(2, LP_E2_THREADS);
-            }
+            mbar_wait(&a_full[s], (uint32_t)(sn & 1));
             float sk[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) sk[c] = 0.f;
-            if (p.p_out) {   // the skip of the NEXT layer's "x += audio_down", added to the rows this layer produces
-                if (HOP == 256) {
-                    const float4 b0 = *reinterpret_cast<const float4*>(fb_s + j * 8), b1 = *reinterpret_cast<const float4*>(fb_s + j * 8 + 4);
-                    sk[0] = b0.x; sk[1] = b0.y; sk[2] = b0.z; sk[3] = b0.w; sk[4] = b1.x; sk[5] = b1.y; sk[6] = b1.z; sk[7] = b1.w;
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) {
-                        const float x = au[r + 1 + k];          // audio position t + k - 3
-                        const float4 w0 = *reinterpret_cast<const float4*>(fw_s + k * C + j * 8), w1 = *reinterpret_cast<const float4*>(fw_s + k * C + j * 8 + 4);
-                        sk[0] = fmaf(w0.x, x, sk[0]); sk[1] = fmaf(w0.y, x, sk[1]); sk[2] = fmaf(w0.z, x, sk[2]); sk[3] = fmaf(w0.w, x, sk[3]);
-                        sk[4] = fmaf(w1.x, x, sk[4]); sk[5] = fmaf(w1.y, x, sk[5]); sk[6] = fmaf(w1.z, x, sk[6]); sk[7] = fmaf(w1.w, x, sk[7]);
-                    }
-                } else if (t < T) {
-                    const float4* sp = reinterpret_cast<const float4*>(p.skip + ((size_t)b * T + t) * C + j * 8);
-                    const float4 s0 = sp[0], s1 = sp[1];
-                    sk[0] = s0.x; sk[1] = s0.y; sk[2] = s0.z; sk[3] = s0.w; sk[4] = s1.x; sk[5] = s1.y; sk[6] = s1.z; sk[7] = s1.w;
-                }
+            if (!SKIP_MMA && has_skip && t < T) {   // hop 64: skip rows of the DBlock output
+                const float4* sp = reinterpret_cast<const float4*>(p.skip + ((size_t)b * T + t) * C + j * 8);
+                const float4 s0 = sp[0], s1 = sp[1];
+                sk[0] = s0.x; sk[1] = s0.y; sk[2] = s0.z; sk[3] = s0.w; sk[4] = s1.x; sk[5] = s1.y; sk[6] = s1.z; sk[7] = s1.w;
             }
-            // residual base z = x + skip of this row, recovered from the pieces of 16 * lrelu(z) that fed the conv
+            // residual base z16 = 16 (x + skip) of this row, recovered from the pieces of 16 * lrelu(z) that fed the conv (lrelu^-1: x5 where negative)
             float z[8];
             {
                 const int ar = 32 + r, sw = ar & 7;
@@ -391,37 +422,48 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 for (int c = 0; c < 4; ++c) {
                     const float2 hf = unpack_f16x2(hh[c]), lf = unpack_f16x2(ll[c]);
                     const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
-                    z[2 * c] = v0 * (v0 < 0.f ? (1.f / (0.2f * S16_ACT)) : (1.f / S16_ACT));
-                    z[2 * c + 1] = v1 * (v1 < 0.f ? (1.f / (0.2f * S16_ACT)) : (1.f / S16_ACT));
+                    z[2 * c] = fminf(v0, 5.f * v0);
+                    z[2 * c + 1] = fminf(v1, 5.f * v1);
                 }
-            }
-            float lb[16];
-            {
-                const float4* lp = reinterpret_cast<const float4*>(lbias + fi * 64 + j * 8);
-                const float4 a0 = lp[0], a1 = lp[1], b0 = lp[8], b1 = lp[9];   // sigmoid half [8j, 8j+8), tanh half [32 + 8j, ...)
-                lb[0] = a0.x; lb[1] = a0.y; lb[2] = a0.z; lb[3] = a0.w; lb[4] = a1.x; lb[5] = a1.y; lb[6] = a1.z; lb[7] = a1.w;
-                lb[8] = b0.x; lb[9] = b0.y; lb[10] = b0.z; lb[11] = b0.w; lb[12] = b1.x; lb[13] = b1.y; lb[14] = b1.z; lb[15] = b1.w;
             }
             mbar_wait(&lacc_full[ls], (uint32_t)((n >> 1) & 1));
             tc_fence_after();
-            uint32_t zs[8], zt[8];
+            uint32_t zs[8], zt[8], za[8];
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + LACC0 + (uint32_t)ls * LSTRIDE + fi * 64 + j * 8;
             tmem_ld_32x32b_x8(ta, zs);
             tmem_ld_32x32b_x8(ta + 32, zt);
+            if (SKIP_MMA && has_skip) tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + SKACC0 + (uint32_t)ls * 32 + j * 8, za);
+            float lb[16];   // prescaled by the conv epilogue: sigmoid half x -log2(e), tanh half x -2 log2(e)
+            {
+                const float4* lp = reinterpret_cast<const float4*>(lbias + fi * 64 + j * 8);
+                const float4 a0 = lp[0], a1 = lp[1], b0 = lp[8], b1 = lp[9];
+                lb[0] = a0.x; lb[1] = a0.y; lb[2] = a0.z; lb[3] = a0.w; lb[4] = a1.x; lb[5] = a1.y; lb[6] = a1.z; lb[7] = a1.w;
+                lb[8] = b0.x; lb[9] = b0.y; lb[10] = b0.z; lb[11] = b0.w; lb[12] = b1.x; lb[13] = b1.y; lb[14] = b1.z; lb[15] = b1.w;
+            }
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&lacc_free[ls]);
+            // sigmoid(a) tanh(b) = (1 - E) / ((1 + A)(1 + E)), A = e^-a, E = e^-2b (b clamped at -15: E finite, tanh(-15) = -1 in fp32)
             float xn[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                xn[c] = z[c] + gate_st(fmaf(__uint_as_float(zs[c]), p.inv_l, lb[c]), fmaf(__uint_as_float(zt[c]), p.inv_l, lb[8 + c]));
+            for (int c = 0; c < 8; ++c) {
+                const float A = ex2_approx(fmaf(__uint_as_float(zs[c]), c_s, lb[c]));
+                const float E = ex2_approx(fminf(fmaf(__uint_as_float(zt[c]), c_t, lb[8 + c]), 43.280851226668903f));
+                const float rinv = rcp_approx((1.f + A) * (1.f + E));
+                xn[c] = fmaf(fmaf(E, -S16_ACT, S16_ACT), rinv, z[c]);        // 16 (x + gate)
+            }
             if (p.f_out) {
-                if (t < T) st_global_f8(p.f_out + ((size_t)b * T + t) * C + j * 8, make_float4(xn[0], xn[1], xn[2], xn[3]), make_float4(xn[4], xn[5], xn[6], xn[7]));
+                if (t < T) st_global_f8(p.f_out + ((size_t)b * T + t) * C + j * 8,
+                                        make_float4(xn[0] * (1.f / S16_ACT), xn[1] * (1.f / S16_ACT), xn[2] * (1.f / S16_ACT), xn[3] * (1.f / S16_ACT)),
+                                        make_float4(xn[4] * (1.f / S16_ACT), xn[5] * (1.f / S16_ACT), xn[6] * (1.f / S16_ACT), xn[7] * (1.f / S16_ACT)));
             } else {
                 float v[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = lrelu02_s(__fadd_rn(xn[c], sk[c]));   // (x + gate) + skip: the reference's rounding sequence
+                for (int c = 0; c < 8; ++c) {   // (x + gate) + skip, one rounding like the reference's add; then 16 lrelu
+                    const float zz = SKIP_MMA ? fmaf(__uint_as_float(za[c]), c_sk, xn[c]) : fmaf(sk[c], S16_ACT, xn[c]);
+                    v[c] = fmaxf(zz, 0.2f * zz);
+                }
                 uint4 hi, lo;
                 lp_split8(v, hi, lo, vmax);
                 const int sw = r & 7;                                                   // == t & 7 (t0 is a multiple of 128)
@@ -445,6 +487,8 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_free[s]);
+            if (--tt < 0) { tt = ntt - 1; --b; }
+            if (++s == LP_NA) { s = 0; ++sn; }
         }
         if (STAGE_OUT && etid == 0) bulk_wait_all();
         if (p.sat && vmax > F16_MAX) *p.sat = 1u;

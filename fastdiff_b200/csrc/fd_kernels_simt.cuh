@@ -681,10 +681,19 @@ __device__ __forceinline__ float philox_normal(uint64_t elem, uint32_t draw, uin
     return rad * ((sel & 1) ? sinf(ang) : cosf(ang));
 }
 
-__global__ void __launch_bounds__(256) k_fill_normal(float* __restrict__ out, size_t n, uint64_t seed, uint32_t draw) {
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i < n) out[i] = philox_normal(i, draw, seed);
+// Philox element index of local sample (b, t): b * win_L + win_off + t.  win_L = 0 means "the tensor itself" (b * L + t); a rank that
+// holds the time window [win_off, win_off + L) of a longer utterance of win_L samples (time-shard mode) draws the SAME numbers the
+// unsharded call would.  seed_ptr (optional) overrides `seed` with a device word: lets a captured graph be replayed with a new seed.
+struct NoiseWin { long long win_L, win_off; };
+__device__ __forceinline__ size_t noise_elem(const NoiseWin w, int b, int L, int t) {
+    return w.win_L ? (size_t)b * (size_t)w.win_L + (size_t)w.win_off + t : (size_t)b * L + t;
 }
+__global__ void __launch_bounds__(256) k_fill_normal(float* __restrict__ out, int L, size_t n, uint64_t seed, uint32_t draw, NoiseWin win,
+                                                     const unsigned long long* __restrict__ seed_ptr) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = philox_normal(noise_elem(win, (int)(i / L), L, (int)(i % L)), draw, seed_ptr ? (uint64_t)*seed_ptr : seed);
+}
+__global__ void k_set_u64(unsigned long long* dst, unsigned long long v) { *dst = v; }
 
 // ------------------------------------------------------------------------------------------------
 // K14+K15  final_conv (FastDiff_model.py:100) fused with the sampler update (util.py:219-229).
@@ -702,6 +711,8 @@ struct FinalParams {
     int add_noise;
     uint32_t draw;
     uint64_t seed;
+    NoiseWin win;
+    const unsigned long long* seed_ptr;
 };
 
 #ifndef FINAL_BATCH_LOADS
@@ -775,7 +786,7 @@ __global__ void __launch_bounds__(256) k_final(FinalParams p, const float* __res
     } else if (p.mode == 1) {
         r = __fdiv_rn(__fsub_rn(x_t[e], __fmul_rn(p.coef, eps)), p.div);
         if (p.add_noise) {
-            const float zz = z ? z[e] : philox_normal(e, p.draw, p.seed);
+            const float zz = z ? z[e] : philox_normal(noise_elem(p.win, b, L, t0 + tid), p.draw, p.seed_ptr ? (uint64_t)*p.seed_ptr : p.seed);
             r = __fadd_rn(r, __fmul_rn(p.sigma, zz));
         }
     } else {

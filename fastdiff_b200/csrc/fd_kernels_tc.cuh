@@ -2801,12 +2801,12 @@ static inline int tc_lvc_p_layer(void* state, int blk, int layer, const float* p
     LvcPParams p;
     p.cw16 = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16] + (size_t)layer * (LP_CW_BYTES / 4);
     p.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + blk * FD_LB_STRIDE] + layer * C;
-    p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
-    p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
+    p.first16 = s->blob + s->sec_off[FD_S_FIRST_F16];
     p.p_in = p_in; p.skip = skip; p.kern = kern; p.p_out = p_out; p.f_out = f_out; p.sat = sat;
     p.B = B; p.T = T; p.Tm = Tm; p.dil = dil;
     p.inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * blk + layer]);
     p.inv_l = 1.f / (S16_ACT * S16_KERN);
+    p.inv_sk = 1.f / (LP_S_AU * s->scales16[40]);
     const int tiles = B * ((T + LP_TT - 1) / LP_TT);
     const int grid = tiles < s->sm_count ? tiles : s->sm_count;
     if (blk == 1) k_lvc_p<64><<<grid, LP_THREADS, lp_smem_bytes<64>(), st>>>(p);

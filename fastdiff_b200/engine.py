@@ -115,6 +115,10 @@ class Engine:
     def set_option(self, key: str, value: int):
         self._check(self.lib.fd_set_option(self.h, key.encode(), int(value)), "fd_set_option")
 
+    def set_noise_window(self, total_samples: int = 0, offset: int = 0):
+        """Device-noise mode: this engine's tensors are the window [offset, offset + L) of utterances of `total_samples` samples (time shard)."""
+        self._check(self.lib.fd_set_noise_window(self.h, int(total_samples), int(offset)), "fd_set_noise_window")
+
     def launch_count(self) -> int:
         return int(self.lib.fd_launch_count(self.h))
 

@@ -44,12 +44,17 @@ class FastDiffVocoder:
         if seed is not None:
             self.model.noise_mode, self.model.seed = "device", int(seed)
 
-    def spec2wav(self, mel, **kwargs):
+    def spec2wav(self, mel, int16: bool = False, **kwargs):
+        """mel [T, 80] -> wav [T * 256] float32 (vocoders/base_vocoder.py:24-31).  int16=True additionally applies the step AFTER the
+        path on the device -- peak-normalise, x 32767, truncate to int16 (task/FastDiff.py:110, utils/audio.py:11-16; fd_wav_int16,
+        bit-identical to the reference's float ops) -- so that only 2 bytes per sample leave the GPU."""
         c = torch.as_tensor(np.asarray(mel), dtype=torch.float32).t().unsqueeze(0).to(self.device)
         import contextlib
         import io
         with contextlib.redirect_stdout(io.StringIO()):
             y = sampling_given_noise_schedule(self.model, (1, 1, c.shape[-1] * 256), self.dh, self.schedule.clone(), condition=c)
+        if int16:
+            return self.model.engine(self.device).wav_int16(y).view(-1).cpu().numpy()
         return y.view(-1).cpu().numpy()
 
     @staticmethod

@@ -58,14 +58,18 @@ class ShardedFastDiff:
         return self._gather(out, x.shape[0]) if gather else out
 
     def sample(self, size, diffusion_hyperparams, schedule, condition, noise=None, seed: int = 0, ddim: bool = False,
-               gather: bool = False):
-        """Reverse loop on this rank's slice.  noise (optional): host tensors [x_T, z_...] for the WHOLE batch in the
-        reference's draw order; each rank slices the same indices so sharded == unsharded bitwise."""
+               gather: bool = False, presliced: bool = False):
+        """Reverse loop on this rank's slice.  size = (B,1,L) of the WHOLE batch; condition = the whole batch's mels, or -- presliced --
+        only this rank's.  noise (optional): host tensors [x_T, z_...] for the WHOLE batch in the reference's draw order; each rank
+        slices the same indices so sharded == unsharded bitwise.  A rank whose slice is empty (B < world) runs nothing but still
+        takes part in the gather."""
         B, _, L = size
         lo, hi = self.my_slice(B)
         _, steps = build_steps(diffusion_hyperparams, schedule, ddim)
-        cond = condition[lo:hi]
-        if noise is not None:
+        cond = condition if presliced else condition[lo:hi]
+        if hi == lo:
+            x = torch.empty((0, 1, L), dtype=torch.float32, device=self.device)
+        elif noise is not None:
             x = noise[0][lo:hi].to(self.device, torch.float32).contiguous()
             zs = torch.stack([z[lo:hi] for z in noise[1:]]).to(self.device) if len(noise) > 1 else None
             self.engine.sample(x, cond, steps, noise=zs, ddim=ddim)

@@ -250,6 +250,19 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         S[f"LB{n}_KPW_F16"] = _u16_as_f32(slots)
     S["LB0_CONV_F16"] = conv16[0]
     S["LB0_KCT_F16P"], S["LB0_KC_BP"] = b0_image_f16, b0_image_bias
+    # first_audio_conv (+ bias as an 8th tap against a constant-one input) as a K = 16 fp16-piece operand: LVC block 2 evaluates the skip
+    # first_conv(audio) of the rows it produces as one small MMA (k_lvc_p) instead of 7 FMA per channel per row
+    fw = np.zeros((C, 16), dtype=np.float32)
+    fw[:, :7] = W["first_audio_conv.weight"][:, 0, :].numpy()
+    fw[:, 7] = W["first_audio_conv.bias"].numpy()
+    sc = f16_scale(fw)
+    scales[40] = sc
+    hi, lo = f16_split(fw, sc)
+    img = np.zeros((C, 8, 8), dtype=np.uint16)                  # [co][physical chunk][8 halves]
+    for co in range(C):
+        for c, src in ((0, hi[co, 0:8]), (1, hi[co, 8:16]), (2, lo[co, 0:8]), (3, lo[co, 8:16])):
+            img[co, c ^ (co & 7)] = src
+    S["FIRST_F16"] = _u16_as_f32(img)
     S["SCALES16"] = torch.from_numpy(scales)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}

@@ -166,6 +166,11 @@ int fd_debug_read(fd_handle* h, const char* name, float* out_dev, size_t* count,
                   void* workspace_dev, void* stream);
 
 /* Number of kernels launched by this handle since creation (bench.py's gpu_launches). */
+/* Device-noise mode (noise_dev == NULL): Philox element index of local sample (b, t) = b * total_samples + offset + t.  The default
+ * (0, 0) indexes the tensor itself.  A rank that holds the time window [offset, offset + L) of utterances of total_samples samples
+ * (time-shard mode, fastdiff_b200/timeshard.py) draws exactly the numbers the unsharded call draws for those samples. */
+int fd_set_noise_window(fd_handle* h, int64_t total_samples, int64_t offset);
+
 uint64_t fd_launch_count(fd_handle* h);
 
 /* Range guard of the default arithmetic mode (tc_3xf16): operands of the tensor-core kernels are fp16 pieces of 16 x activation

@@ -21,7 +21,8 @@ _orig_tensor_cuda = torch.Tensor.cuda
 
 
 def reference_root():
-    for c in _CANDIDATES:
+    forced = os.environ.get("FD_REFERENCE_ROOT")            # tests: force the staged copy even where /root/reference exists
+    for c in ((forced,) if forced else _CANDIDATES):
         if os.path.isdir(os.path.join(c, "modules", "FastDiff", "module")):
             return c
     return None
@@ -32,17 +33,31 @@ def shim_cuda_to_cpu(on: bool = True):
     torch.Tensor.cuda = (lambda self, *a, **k: self) if on else _orig_tensor_cuda
 
 
+# packages the reference's task / data-prep import chain pulls in that are absent from this image, with the attributes its
+# `from X import name` statements need.  None of them is used by the code the tests run (test_step, the mel-dir loader, spec2wav).
+_STUBS = {
+    "chardet": (), "librosa": (), "librosa.filters": (), "resemblyzer": ("VoiceEncoder",), "parselmouth": (), "skimage": (),
+    "skimage.transform": ("resize",), "webrtcvad": (), "pyloudnorm": (), "scipy.ndimage.morphology": ("binary_dilation",),
+    "matplotlib": (), "matplotlib.pyplot": (), "h5py": (), "pyworld": (), "g2p_en": (), "soundfile": (), "pypinyin": (), "textgrid": (),
+}
+
+
 def stub_missing_deps():
-    for name in ("chardet", "librosa", "librosa.filters", "resemblyzer"):
-        if name not in sys.modules:
-            try:
-                __import__(name)
-            except Exception:
-                sys.modules[name] = types.ModuleType(name)
-    if not hasattr(sys.modules["resemblyzer"], "VoiceEncoder"):
-        sys.modules["resemblyzer"].VoiceEncoder = object
-    if not hasattr(sys.modules["librosa"], "filters"):
-        sys.modules["librosa"].filters = sys.modules["librosa.filters"]
+    import importlib
+    for name, attrs in _STUBS.items():
+        if name in sys.modules:
+            continue
+        try:
+            importlib.import_module(name)
+        except Exception:
+            mod = types.ModuleType(name)
+            for a in attrs:
+                setattr(mod, a, object)
+            sys.modules[name] = mod
+            if "." in name:
+                parent, child = name.rsplit(".", 1)
+                if parent in sys.modules and not hasattr(sys.modules[parent], child):
+                    setattr(sys.modules[parent], child, mod)
 
 
 def load(device: str = "cpu"):

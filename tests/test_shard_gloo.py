@@ -25,8 +25,17 @@ def _worker(rank, world, port, emu_lib, q):
     t = torch.tensor([7.413235, 498.0537, 74.99228])
     full = sh.denoise(x, mel, t, gather=True)
     lo, hi = sh.my_slice(B)
+    # B < world: rank 1's slice is empty -- it must skip the engine call and still take part in the gather (no hang, no FdError)
+    import fastdiff_b200 as fb
+    x1, mel1 = make_inputs(1, 1, 5)
+    one = sh.denoise(x1, mel1, torch.tensor([74.99228]), gather=True)
+    dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
+    torch.manual_seed(5)
+    noise = [torch.normal(0, 1, size=(1, 1, 256)) for _ in range(4)]
+    smp = sh.sample((1, 1, 256), dh, torch.FloatTensor([3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]), mel1, noise=noise, gather=True)
+    assert tuple(one.shape) == (1, 1, 256) and tuple(smp.shape) == (1, 1, 256) and sh.my_slice(1) == ((0, 1) if rank == 0 else (1, 1))
     if rank == 0:
-        q.put((full, sh.blob_bytes))
+        q.put((full, sh.blob_bytes, one, smp))
     else:
         q.put((lo, hi, sh.blob_bytes))
     dist.barrier()
@@ -67,3 +76,6 @@ def test_two_rank_batch_shard_matches_unsharded(emu_lib, synth):
     unsharded = eng.denoise(x, mel, t)
     assert torch.equal(full[0], unsharded)
     assert (unsharded - O.denoise(W, x, mel, t.reshape(3, 1))).abs().max() < 5e-5
+    x1, mel1 = make_inputs(1, 1, 5)
+    assert torch.equal(full[2], eng.denoise(x1, mel1, torch.tensor([74.99228])))       # B = 1 on 2 ranks == unsharded, bitwise
+    assert torch.isfinite(full[3]).all()
