@@ -31,24 +31,21 @@ struct fd_handle {
     int tc_kp = 1;               // kernel-predictor hidden stack on tensor cores in mode tc_3xf16 (option "tc_kp")
     int emu_gemm_tc = 1;         // emulation build, mode tc_3xf16: 1 = the CTA-pair GEMM on the tcgen05 model, 0 = FFMA GEMM + k_emu_kern_to_pieces
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
-    int tc_b0 = 1;               // EXPERIMENTAL: LVC block 0 on tensor cores in mode tc_3xf16 (option "tc_b0"; k_lvc_layer_b0h): 1 = the GEMM
-                                 // writes the block's kernels as fp16 pieces (k_kc_gemm_tc2<true, 16, true>), 2 = converter pass (k_b0_panel_to_pieces)
-    int lvc_pipe = 0;            // EXPERIMENTAL (mode tc_3xf16, option "lvc_pipe"): LVC block 2 with software-pipelined tiles (k_lvc_layer_p)
-    int kc_stage = 0;            // EXPERIMENTAL (mode tc_3xf16, option "kc_stage"): kernel_conv GEMM epilogue through shared memory + bulk stores
-    int b2_skipbuf = 0;          // EXPERIMENTAL (mode tc_3xf16, option "b2_skipbuf"): first_conv(audio) is written once per evaluation as rows
-                                 // (over block 0's dead predicted kernels) and LVC block 2 reads it like block 1 reads its skip tensor
+    int tc_b0 = 1;               // mode tc_3xf16: LVC block 0 on tensor cores (k_lvc_layer_b0h, its kernels written as fp16 pieces by the GEMM; option "tc_b0", 0 = SIMT k_lvc_layer<8>)
     int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
     long long noise_win_L = 0, noise_win_off = 0;   // Philox element window of the device-noise mode (fd_set_noise_window; time-shard mode)
     int graphs = 1;              // fd_sample in device-noise mode: capture the whole call (all N <= 64 steps) in a CUDA graph on first use and
                                  // replay it afterwards (option "graphs"; the workspace, shapes, schedule and options are the cache key)
     uint64_t epoch = 0;          // bumped by everything that changes what a captured graph would do (mode, options, weights, noise window)
+    int kc_unswap = 1;           // mode tc_3xf16 with tc_b0: kernel_conv GEMM with the frames on the MMA's M side (k_kc_gemm_tc2<.., UNSW>; option "kc_unswap")
     int lvc_p = 1;               // mode tc_3xf16: LVC blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>; option "lvc_p", 0 = k_lvc_layer_h)
     unsigned int* sat_flag = nullptr;   // device word, sticky: an fp16 piece saturated in a tensor-core kernel (fd_check_saturation)
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
                                  // (option "overlap"; forked from / joined into the caller's stream with events inside every call)
 #ifndef FD_EMU
     cudaStream_t side = nullptr;
+    cudaStream_t cap = nullptr;      // capture stream of the graph path (the caller's stream may be the legacy default stream, which cannot capture)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 #endif
     int attrs_set = 0;
@@ -177,6 +174,7 @@ extern "C" int fd_create(const fd_config* cfg, int device, fd_handle** out) {
     h->device = device;
 #ifndef FD_EMU
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
         delete h;
@@ -204,6 +202,7 @@ extern "C" void fd_destroy(fd_handle* h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->cap) cudaStreamDestroy(h->cap);
 #endif
 #ifndef FD_EMU
     for (auto& g : h->gcache) cudaGraphExecDestroy(g.exec);
@@ -344,9 +343,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "lvc_p")) { h->lvc_p = (int)value; return FD_OK; }
-    if (!strcmp(key, "b2_skipbuf")) { h->b2_skipbuf = (int)value; return FD_OK; }
-    if (!strcmp(key, "kc_stage")) { h->kc_stage = (int)value; return FD_OK; }
-    if (!strcmp(key, "lvc_pipe")) { h->lvc_pipe = (int)value; return FD_OK; }
+    if (!strcmp(key, "kc_unswap")) { h->kc_unswap = (int)value; return FD_OK; }
     if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
@@ -356,7 +353,6 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "kc_2cta")) { tc_set_kc_2cta(h->tc_state, (int)value); return FD_OK; }
-    if (!strcmp(key, "lvc_groups")) { tc_set_lvc_groups(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "lvc_exp")) { tc_set_lvc_exp(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "kc_exp")) { tc_set_kc_exp(h->tc_state, (int)value); return FD_OK; }
 #endif
@@ -478,7 +474,7 @@ static int emu_kp_hidden_tc(fd_handle* h, const float* mel, const float* cnoise,
 }
 
 static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, const float* skip, const float* kern, float* x_out,
-                           int B, int T, int Tm, int dil, cudaStream_t st, int b2_skip_rows = 0) {
+                           int B, int T, int Tm, int dil, cudaStream_t st) {
     LvcHParams hp;
     hp.cw16 = sec(h, blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16) + (size_t)layer * (LH_CW_BYTES / 4);
     hp.conv_b = sec(h, FD_S_LB0_CONV_B + blk * FD_LB_STRIDE) + layer * C;
@@ -486,18 +482,10 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
     hp.first_b = sec(h, FD_S_FIRST_B);
     const float inv_c = 1.f / (S16_ACT * emu_scale16(h, 4 + 4 * blk + layer)), inv_l = 1.f / (S16_ACT * S16_KERN);
     const int tiles = B * ((T + LT_TT - 1) / LT_TT);
-    const bool rows = blk == 1 || b2_skip_rows;   // the skip comes as (B,T,32) rows: added on the way in by layer 0, on the way out by layers 0..2
-    const int skip_in = (!rows || layer == 0) ? 1 : 0, skip_out = (rows && layer < LAYERS - 1) ? 1 : 0;
+    const int skip_in = (blk == 2 || layer == 0) ? 1 : 0, skip_out = (blk == 1 && layer < LAYERS - 1) ? 1 : 0;
     // a small grid on purpose: every group then walks a chunk of several tiles (carried halo rows, kernel reuse, prefetch one tile ahead)
     int grid = (tiles + 5) / 6; if (grid < 1) grid = 1; if (grid > 8) grid = 8;
-    if (blk == 2 && h->lvc_pipe && (!b2_skip_rows || layer > 0)) {
-        if (b2_skip_rows) { auto k = k_lvc_layer_p<true>;  FD_LAUNCH(k, dim3(grid), dim3(512), LP_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, skip_out); }
-        else              { auto k = k_lvc_layer_p<false>; FD_LAUNCH(k, dim3(grid), dim3(512), LP_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0); }
-        FD_CHECK_LAUNCH(h, "k_lvc_layer_p");
-        return FD_OK;
-    }
-    if (blk == 2 && b2_skip_rows) { auto k = k_lvc_layer_h<256, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<256, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
-    else if (blk == 1) { auto k = k_lvc_layer_h<64, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<64, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
+    if (blk == 1) { auto k = k_lvc_layer_h<64, false, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<64, false, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
     else          { auto k = k_lvc_layer_h<256, true, 2>;  FD_LAUNCH(k, dim3(grid), dim3(512), (lh_smem_bytes<256, true, 2>()), st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0, skip_in, skip_out); }
     FD_CHECK_LAUNCH(h, "k_lvc_layer_h");
     return FD_OK;
@@ -505,7 +493,6 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
 
 // The CTA-pair kernel_conv GEMM (k_kc_gemm_tc2<true, 16>: 2-SM TMA, cta_group::2 MMA, multicast commit, remote arrives) on the model.
 static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st, int b0_pieces) {
-    const int stage = h->kc_stage;
     KcgMaps maps;
     const uint64_t rows = (uint64_t)B * (Tm + 2);
     float inv[NBLK];
@@ -520,22 +507,18 @@ static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo,
     const int M = B * (Tm + 2) - 2;
     const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
     const int clusters = items < 8 ? items : 8;
-    if (stage && b0_pieces) {
+    if (b0_pieces && h->kc_unswap) {
         auto k = k_kc_gemm_tc2<true, 16, true, true>;
-        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES + KC2_STG_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
-    } else if (stage) {
-        auto k = k_kc_gemm_tc2<true, 16, false, true>;
-        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES + KC2_STG_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2U_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0, h->sat_flag);
     } else if (b0_pieces) {
         auto k = k_kc_gemm_tc2<true, 16, true>;
         FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0, (unsigned int*)nullptr);
     } else {
         auto k = k_kc_gemm_tc2<true, 16>;
         FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0, (unsigned int*)nullptr);
     }
     FD_CHECK_LAUNCH(h, "k_kc_gemm_tc2");
     return FD_OK;
@@ -729,10 +712,9 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
 #else
     const bool simt_gemm = h->mode == FD_MODE_FP32_SIMT;
 #endif
-    // experimental option tc_b0 (mode tc_3xf16): 1 = the GEMM writes block 0's kernels as fp16 pieces itself, 2 (or a GEMM that cannot)
-    // = they are converted in place before the first block-0 layer
-    const bool b0_tc = h->tc_b0 && h->mode == FD_MODE_TC_3XF16;
-    const bool b0_gemm_pieces = b0_tc && h->tc_b0 == 1 && !simt_gemm;
+    // LVC block 0 on tensor cores (mode tc_3xf16, option tc_b0): the GEMM writes the block's kernels as fp16 pieces itself
+    const bool b0_tc = h->tc_b0 && h->mode == FD_MODE_TC_3XF16 && !simt_gemm;
+    const bool b0_gemm_pieces = b0_tc;
 #ifdef FD_EMU
     if (!simt_gemm) {
         ScopedTimer tm(h, KC_KC_GEMM, st);
@@ -757,7 +739,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     } else {
 #ifndef FD_EMU
         ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0, h->kc_stage);
+        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0, h->kc_unswap, h->sat_flag);
         if (rc) return rc;
 #endif
     }
@@ -821,26 +803,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             }
         }
         const float* kern_n = kern + (size_t)n * B * Tm * KCN;
-        const bool b2_rows = (n == 2 && h->b2_skipbuf && h->mode == FD_MODE_TC_3XF16 && !use_p);
-        if (b2_rows) {   // experimental: first_conv(audio) as rows, once, over block 0's predicted kernels (dead by now: 8192 of its 24832 floats per frame)
-            ScopedTimer tm(h, KC_LVC2, st);
-            FD_LAUNCH(k_first_conv_rows, dim3((T + 31) / 32, B), dim3(256), 0, st, sec(h, FD_S_FIRST_W), sec(h, FD_S_FIRST_B), x_dev, kern, T);
-            FD_CHECK_LAUNCH(h, "k_first_conv_rows");
-            skip = kern;
-            h->b0_converted = -1;   // "kernels0" / "kbias0" are gone for fd_debug_read
-        }
         const bool b0_here = (n == 0 && b0_tc);
-        if (b0_here && !b0_gemm_pieces) {   // experimental: the GEMM's fp32 panel image of block 0 -> fp16 pieces, in place, all layers
-            ScopedTimer tm(h, KC_LVC0, st);
-#ifdef FD_EMU
-            FD_LAUNCH(k_b0_panel_to_pieces, dim3(B * Tm * LAYERS), dim3(256), 0, st, kern, B * Tm);
-            FD_CHECK_LAUNCH(h, "k_b0_panel_to_pieces");
-#else
-            int rc = tc_b0_convert(h->tc_state, kern, B, Tm, st, h->err, &h->launches);
-            if (rc) return rc;
-#endif
-            h->b0_converted = 1;
-        }
         for (int i = 0; i < LAYERS; ++i) {
             LvcParams p;
             p.conv_w = sec(h, FD_S_LB0_CONV_W + n * FD_LB_STRIDE) + i * KK * C;
@@ -867,7 +830,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 if (rc) return rc;
                 done = true;
             } else if (h->mode == FD_MODE_TC_3XF16 && n >= 1) {
-                int rc = emu_lvc_layer_h(h, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, b2_rows ? 1 : 0);
+                int rc = emu_lvc_layer_h(h, n, i, cur, skip, kl, oth, B, T, Tm, dil, st);
                 if (rc) return rc;
                 done = true;
             }
@@ -877,7 +840,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 if (rc) return rc;
                 done = true;
             } else if (h->mode != FD_MODE_FP32_SIMT) {
-                int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done, b2_rows ? 1 : 0, h->lvc_pipe);
+                int rc = tc_lvc_layer(h->tc_state, h->mode, n, i, cur, skip, kl, oth, B, T, Tm, dil, st, h->err, &h->launches, &done);
                 if (rc) return rc;
             }
 #endif
@@ -1021,7 +984,7 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
     // ---- graph replay: device-noise mode, the whole call (N <= 64 reverse steps) captured once per (workspace, shape, schedule, options) ----
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (h->graphs && !h->timing && !noise_dev && !seq_dev && n_steps >= 1 && n_steps <= h->emb_slots && h->stop_after >= 99 &&
-        cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+        h->cap && cudaStreamIsCapturing(st, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
         const WsLayout w = ws_layout(B, Tm);
         const size_t nx = (size_t)B * Tm * HOP_TOTAL;
         fd_handle::GraphEntry* hit = nullptr;
@@ -1031,9 +994,13 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
         if (!hit) {
             cudaGraph_t graph = nullptr;
             const uint64_t l0 = h->launches;
-            FD_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            rc = sample_body(h, ws + w.xc, ws + w.melc, steps, n_steps, nullptr, 0, h->seed_dev, fill_xT, ddim, nullptr, B, Tm, ws, st);
-            cudaError_t ec = cudaStreamEndCapture(st, &graph);
+            if (cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+                cudaGetLastError();
+                h->graphs = 0;   // capture unavailable in this context: plain launches from now on
+                return sample_body(h, x_dev, mel_dev, steps, n_steps, noise_dev, seed, nullptr, fill_xT, ddim, seq_dev, B, Tm, ws, st);
+            }
+            rc = sample_body(h, ws + w.xc, ws + w.melc, steps, n_steps, nullptr, 0, h->seed_dev, fill_xT, ddim, nullptr, B, Tm, ws, h->cap);
+            cudaError_t ec = cudaStreamEndCapture(h->cap, &graph);
             const uint64_t nl = h->launches - l0;
             h->launches = l0;
             if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -1157,7 +1124,6 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         return gather(block_out_buffer(ws, B, Tm, n), (int)T, C, C, T * C, 0);
     }
     if ((!strncmp(name, "kernels", 7) || !strncmp(name, "kbias", 5)) && n >= 0) {
-        if (n == 0 && h->b0_converted < 0) return fail(h, FD_ERR_STATE, "fd_debug_read: block 0's kernels were overwritten (option b2_skipbuf)");
         const int want_bias = name[1] == 'b';
         *count = want_bias ? (size_t)B * LAYERS * LVC_OUT * Tm : (size_t)B * LAYERS * C * LVC_OUT * KS * Tm;
         if (!out_dev) return FD_OK;

@@ -14,7 +14,7 @@
 //     (k_upsample_tc<R, true>), the last layer of a block writes plain fp32 rows for its consumer.
 //   * Rows outside [0, T) come from memory: the piece buffers carry 32 zero rows before the first item and 64 between items
 //     (k_zero_pads), so the loads need no clamping and the conv sees the reference's zero padding.
-//   * WARP SPECIALISATION.  22 warps: 4 conv-epilogue warps (TMEM -> lrelu -> pieces -> Y tile), 16 gate-epilogue warps (TMEM -> gate,
+//   * WARP SPECIALISATION.  26 warps: 8 conv-epilogue warps (TMEM -> lrelu -> pieces -> Y tile), 16 gate-epilogue warps (TMEM -> gate,
 //     residual, skip, lrelu, pieces -> output), one loader (cp.async.bulk, 3 input stages + 2 kernel stages), one MMA issuer.  Conv
 //     MMAs of tile n+1 are issued before the LVC MMAs of tile n; accumulators, Y tiles and output staging are double-buffered, so the
 //     tensor pipe, both epilogues and the loads of three consecutive tiles overlap (the old kernel ran its five phases back to back
@@ -39,7 +39,7 @@ constexpr int LP_Y_BYTES = 17408;                // 136 rows x 128 B (130 used)
 constexpr int LP_OUT_BYTES = 16384;              // 128 output rows
 constexpr int LP_CW_BYTES = 3 * C * 128;         // 12288
 constexpr int LP_AU = 136;                       // audio positions t0-4 .. t0+131
-constexpr int LP_THREADS = 704;                  // warps 0-3 conv epilogue, 4-19 gate epilogue, 20 loader, 21 MMA issuer
+constexpr int LP_THREADS = 832;                  // warps 0-7 conv epilogue, 8-23 gate epilogue, 24 loader, 25 MMA issuer
 constexpr int LP_E2_THREADS = 512;
 
 __host__ __device__ inline size_t lp_rows(int B, int T) { return (size_t)LP_HEAD_ROWS + (size_t)B * (T + LP_PAD_ROWS) + LP_SLACK_ROWS; }
@@ -125,8 +125,8 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
         for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_free[i], 16); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&w_full[i], 1); mbar_init(&w_free[i], 1);
-            mbar_init(&cacc_full[i], 1); mbar_init(&cacc_free[i], 4);
-            mbar_init(&y_full[i], 4); mbar_init(&lacc_full[i], 1); mbar_init(&lacc_free[i], 16);
+            mbar_init(&cacc_full[i], 1); mbar_init(&cacc_free[i], 8);
+            mbar_init(&y_full[i], 8); mbar_init(&lacc_full[i], 1); mbar_init(&lacc_free[i], 16);
         }
         mbar_init_fence();
     }
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     const int b_first = ntile ? (tile_hi - 1) / ntt : 0, tt_first = ntile ? (tile_hi - 1) % ntt : 0;
     const bool has_skip = (p.p_out != nullptr);   // the skip of the NEXT layer's "x += audio_down" is added to the rows this layer produces
 
-    if (warp_u == 20) {
+    if (warp_u == 24) {
         // =========================================== loader ===========================================
         if (elect_one()) {
             int wc = 0, b = b_first, tt = tt_first, s = 0, sn = 0;     // s = n % 3, sn = n / 3
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             }
         }
         __syncwarp();
-    } else if (warp_u == 21) {
+    } else if (warp_u == 25) {
         // =========================================== MMA issuer ===========================================
         constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 64);
         const uint32_t a_u = smem_u32(a_st), y_u = smem_u32(y_t), w_u = smem_u32(w_t), cw_u = smem_u32(cw);
@@ -305,10 +305,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             if (++s == LP_NA) { s = 0; ++sn; }
         }
         if (ntile > 0) lvc_mmas(ntile - 1);
-    } else if (warp_u < 4) {
-        // =========================================== conv epilogue (4 warps) ===========================================
-        const int q = warp;                       // TMEM lane quarter
-        const int yr = q * 32 + lane;             // Y row of this thread <-> t = t0 - 1 + yr; also skip-operand row <-> t = t0 + yr
+    } else if (warp_u < 8) {
+        // =========================================== conv epilogue (8 warps) ===========================================
+        const int q = warp & 3, part = warp >> 2;  // TMEM lane quarter; which 16 of the 32 conv channels
+        const int yr = q * 32 + lane;              // Y row of this thread <-> t = t0 - 1 + yr; (part 0) also skip-operand row <-> t = t0 + yr
         const float inv_cs = p.inv_c * S16_ACT;
         float vmax = 0.f;
         int tt = tt_first, s = 0, sn = 0;
@@ -322,24 +322,26 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             float* au = lbias + 128;
             mbar_wait(&cacc_full[cs], (uint32_t)((n >> 1) & 1));
             tc_fence_after();
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cs * 32, v);
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cs * 32 + part * 16, v);
             tmem_ld_wait();
             if (n >= 2) mbar_wait(&lacc_full[cs], (uint32_t)(((n >> 1) - 1) & 1));   // the LVC MMAs of tile n-2 have read this Y tile
-            auto emit_row = [&](const uint32_t (&acc)[32], int row, unsigned char* copy_to) {
+            // 16 accumulator columns of row `row` -> 16 lrelu(acc * inv + b) -> pieces: logical chunks 2 part, 2 part + 1 (hi) and 4 + ... (lo)
+            auto emit_row = [&](const uint32_t (&acc)[16], int row, unsigned char* copy_to) {
                 const int t = t0 - 1 + row;
                 const bool in = (t >= 0 && t < T);
                 const int sw = row & 7;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int cc = 0; cc < 2; ++cc) {
                     float y[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float x = fmaf(__uint_as_float(acc[c * 8 + e]), inv_cs, cbs_s[c * 8 + e]);
+                        const float x = fmaf(__uint_as_float(acc[cc * 8 + e]), inv_cs, cbs_s[part * 16 + cc * 8 + e]);
                         y[e] = in ? fmaxf(x, 0.2f * x) : 0.f;
                     }
                     uint4 hi, lo;
                     lp_split8(y, hi, lo, vmax);
+                    const int c = part * 2 + cc;
                     *reinterpret_cast<uint4*>(yt + row * 128 + ((c ^ sw) << 4)) = hi;
                     *reinterpret_cast<uint4*>(yt + row * 128 + (((4 + c) ^ sw) << 4)) = lo;
                     if (copy_to) {   // rows 0, 1 again for the next tile (a 2-row image in the same layout: 128 & 7 == 0, 129 & 7 == 1)
@@ -350,10 +352,13 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             };
             emit_row(v, yr, (q == 0 && lane < 2) ? carry + cs * 256 : nullptr);
             if (q == 0) {
-                if (have_carry) {   // rows 128, 129 = rows 0, 1 of the previous tile, already pieces in exactly this 256-byte layout
-                    if (lane < 16) reinterpret_cast<uint4*>(yt + 128 * 128)[lane] = reinterpret_cast<const uint4*>(carry + (cs ^ 1) * 256)[lane];
+                if (have_carry) {   // rows 128, 129 = rows 0, 1 of the previous tile: every warp copies back the four chunks per row it wrote itself
+                    if (lane < 8) {
+                        const int row = lane >> 2, c = part * 2 + (lane & 1) + ((lane & 2) ? 4 : 0), pc = c ^ row;   // row & 7 == row for rows 0, 1
+                        reinterpret_cast<uint4*>(yt + 128 * 128)[row * 8 + pc] = reinterpret_cast<const uint4*>(carry + (cs ^ 1) * 256)[row * 8 + pc];
+                    }
                 } else {            // ... or rows 0, 1 of the second MMA pass (TMEM lanes 0, 1 of its accumulator)
-                    tmem_ld_32x32b_x32(tmem_base + 64u + (uint32_t)cs * 32, v);
+                    tmem_ld_32x32b_x16(tmem_base + 64u + (uint32_t)cs * 32 + part * 16, v);
                     tmem_ld_wait();
                     if (lane < 2) emit_row(v, 128 + lane, nullptr);
                 }
@@ -361,10 +366,11 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&cacc_free[cs]);   // both accumulators of this stage have been read
-            // ---- work taken off the gate epilogue's hands: LVC bias prescaled by the gate's exponent constants; skip operand tile ----
+            // ---- work taken off the gate epilogue's hands: LVC bias prescaled by the gate's exponent constants (part 1); skip operand tile (part 0) ----
             mbar_wait(&a_full[s], (uint32_t)(sn & 1));
-            if (yr < NF * 64) lbias[yr] *= ((yr & 63) < 32) ? -1.4426950408889634f : -2.8853900817779268f;   // sigmoid half: e^-a; tanh half: e^-2b
-            if (SKIP_MMA && has_skip) {
+            if (part == 1) {
+                if (yr < NF * 64) lbias[yr] *= ((yr & 63) < 32) ? -1.4426950408889634f : -2.8853900817779268f;   // sigmoid half: e^-a; tanh half: e^-2b
+            } else if (SKIP_MMA && has_skip) {
                 if (t0 == 0 || t0 + LP_AU - 4 > T) {   // audio positions outside [0, T) are zero (the first conv zero-pads); only utterance ends
                     for (int i = yr; i < LP_AU; i += 128) { const int pos = t0 - 4 + i; if (pos < 0 || pos >= T) au[i] = 0.f; }
                     group_sync(2, 128);
@@ -389,9 +395,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
         if (p.sat && vmax > F16_MAX) *p.sat = 1u;
     } else {
         // =========================================== gate epilogue (16 warps) ===========================================
-        const int e = warp - 4, q = warp & 3, j = e >> 2;      // TMEM lane quarter, channel octet (gate channels 8j .. 8j+7)
+        const int e = warp - 8, q = warp & 3, j = e >> 2;      // TMEM lane quarter, channel octet (gate channels 8j .. 8j+7)
         const int r = q * 32 + lane;                            // output row of this thread
-        const int etid = tid - 128;                             // 0 .. 511
+        const int etid = tid - 256;                             // 0 .. 511
         const int fi = (HOP >= LP_TT) ? 0 : r / HOP;            // warp-uniform (HOP is a multiple of 32)
         // everything below runs in the x16 domain of the pieces (exact: powers of two): z16 = 16 z, gate x 16, skip x 16
         const float c_s = p.inv_l * -1.4426950408889634f, c_t = p.inv_l * -2.8853900817779268f, c_sk = p.inv_sk * S16_ACT;

@@ -797,32 +797,6 @@ __global__ void __launch_bounds__(256) k_final(FinalParams p, const float* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// first_audio_conv (FastDiff_model.py:81: Conv1d(1, 32, 7, padding 3)) at every position, as rows: out[b][t][c].  Only used by the
-// experimental option "b2_skipbuf" (LVC block 2 reading its skip rows from memory like block 1 instead of recomputing them per
-// layer); the sum runs in the order of the in-kernel version (bias, then taps 0..6 by fmaf), so both give the same bits.
-// Thread = (position, channel quad); a warp writes 4 complete 128-byte rows.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_first_conv_rows(const float* __restrict__ fw, const float* __restrict__ fb,
-                                                         const float* __restrict__ audio, float* __restrict__ out, int L) {
-    __shared__ float au[32 + 6];
-    __shared__ float w_s[7 * C + C];
-    const int tid = threadIdx.x, t0 = blockIdx.x * 32, b = blockIdx.y;
-    if (tid < 38) { const int pos = t0 - 3 + tid; au[tid] = (pos >= 0 && pos < L) ? audio[(size_t)b * L + pos] : 0.f; }
-    for (int i = tid; i < 7 * C + C; i += 256) w_s[i] = i < 7 * C ? fw[i] : fb[i - 7 * C];
-    __syncthreads();
-    const int r = tid >> 3, c4 = tid & 7, t = t0 + r;
-    if (t >= L) return;
-    float4 sk = *reinterpret_cast<const float4*>(w_s + 7 * C + c4 * 4);
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        const float a = au[r + k];
-        const float4 w = *reinterpret_cast<const float4*>(w_s + k * C + c4 * 4);
-        sk.x = fmaf(w.x, a, sk.x); sk.y = fmaf(w.y, a, sk.y); sk.z = fmaf(w.z, a, sk.z); sk.w = fmaf(w.w, a, sk.w);
-    }
-    *reinterpret_cast<float4*>(out + ((size_t)b * L + t) * C + c4 * 4) = sk;
-}
-
-// ------------------------------------------------------------------------------------------------
 // One reverse-step update on its own (util.py:219-229), for denoisers other than FastDiff that share the sampler (SURVEY.md 8f.4:
 // the network then is the caller's torch module, only the update runs here).  The same operation sequence as the tail of k_final:
 //   ddim == 0:  x = (x - coef*eps) / div;  if (add_noise) x = x + sigma*z        ddim != 0:  x = c1*x + c2*eps + c3*eps

@@ -180,6 +180,9 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x4(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
@@ -431,20 +434,18 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 // EPW = epilogue warps per CTA (8 or 16: EPW/4 per TMEM lane quarter, each taking 256/(EPW/4) of the 256 frame columns).
 // B0P (experimental, option "tc_b0" = 1): block 0's predicted kernels are written as fp16 pieces as well (its weight rows then come
 // in the same SWIZZLE_128B image order as blocks 1 and 2: sections LB0_KCT_F16P / LB0_KC_BP) for the tensor-core block-0 consumer.
-// STG (experimental, option "kc_stage"): the epilogue stages its rows in shared memory and writes them with cp.async.bulk: the 4 warps
-// of a column group (lane quarters 0..3 = 4 consecutive 128-byte rows of the record = the CTA's 512 contiguous bytes per frame) fill
-// a [8 frames][512 B] buffer, one named barrier, then 8 lanes of one warp issue one 512-byte shared->global bulk copy each (frames
-// outside the utterances are simply skipped).  Two buffers per group: the copies of chunk i read one while chunk i+1 fills the other;
-// the issuing warp waits for the previous chunk's smem reads (wait_group.read) BEFORE the barrier, so after it every warp may refill.
-// (The CPU model performs a bulk store when its thread waits for it, the latest legal moment: dropping that wait breaks the parity test.)
-// Motivation: the 2-byte LSU stores run into the global-store queue limit (lg_throttle) and keep the whole
-// kernel at store speed; bulk copies take them off the LSU path in 512-byte requests.
-constexpr int KC2_STG_BYTES = 4 * 2 * 8 * 512;   // 4 column groups x 2 buffers x 8 frames x 512 B = 32 KB
-template <bool F16, int EPW, bool B0P = false, bool STG = false>
+// UNSW (the default of mode tc_3xf16 since round 2; needs F16, B0P, EPW = 16): the MMA takes the FRAME rows as its M side and the weight
+// rows as N (the two operand tiles of a stage simply swap descriptor slots), so D has lane = frame, column = output channel n and an
+// epilogue thread owns one frame's values for 64 consecutive n = two complete 128-byte rows of the LVC operand image: it writes them
+// with 16-byte stores (8 per row, one full line) instead of the 2-byte stores of the swapped form (lane = n: 64 STG.U16 per 32 values;
+// ncu round 1: the kernel ran at the speed of its 2 GB store stream, lg_throttle 27 %).  The column order inside an image row is the
+// fp32-swizzled one of the weight rows, so the TMEM loads fetch the 4-column groups in the order the piece chunks need them.
+constexpr int KC2U_SMEM_BYTES = KC2_SMEM_BYTES + 4096;   // + per-warp bias staging (16 warps x 64 floats)
+template <bool F16, int EPW, bool B0P = false, bool UNSW = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
               const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass,
-              float inv0, float inv1, float inv2, int exp_mask) {
+              float inv0, float inv1, float inv2, int exp_mask, unsigned int* __restrict__ sat = nullptr) {
     constexpr int NATOM = F16 ? 3 : 6;
     constexpr int CPW = 256 / (EPW / 4);   // frame columns per epilogue warp
     FD_DYN_SMEM(unsigned char, smem_raw);
@@ -524,7 +525,11 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
-                        if (F16) {
+                        if (F16 && UNSW) {   // frames = M side, weights = N side
+                            umma_f16_2sm(d_tmem, b_hi + adv, a_hi + adv, idesc, (a | k) ? 1u : 0u);
+                            umma_f16_2sm(d_tmem, b_lo + adv, a_hi + adv, idesc, 1u);   // same product order as the swapped form: w_hi h_lo, then w_lo h_hi
+                            umma_f16_2sm(d_tmem, b_hi + adv, a_lo + adv, idesc, 1u);
+                        } else if (F16) {
                             umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
                             if (three_pass && !(exp_mask & 2)) {
                                 umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -550,9 +555,80 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
         const int q = warp & 3;
         const int cpart = (warp - 2) >> 2;
         uint32_t acc = 0, acc_phase = 0;
+        [[maybe_unused]] float vmax = 0.f;
         for (int item = pair_id; item < total_items; item += n_clusters) {
             const int blk = item / items_per_blk, r = item % items_per_blk;
             const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
+            if constexpr (UNSW) {
+                static_assert(F16 && B0P && EPW == 16, "unswapped epilogue: fp16 pieces for all three blocks, 4 warps per lane quarter");
+                const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
+                const float inv = blk == 0 ? inv0 : (blk == 1 ? inv1 : inv2), inv_s = inv * S16_KERN;
+                float* kern = kern_all + (size_t)blk * B * Tm * KCN;
+                const int ncol0 = (r % n_pairs) * 256 + cpart * 64;       // this warp's 64 columns = two 32-element image rows (or bias groups)
+                const int p = ft * 256 + (int)rank * 128 + q * 32 + lane;  // this lane's padded frame row
+                const int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
+                const bool valid = p < M && fp >= 1 && fp <= Tm;
+                float* rec = kern + ((size_t)bb * Tm + (valid ? fp - 1 : 0)) * KCN;
+                float* bs = reinterpret_cast<float*>(smem + KC2_SMEM_BYTES) + (warp - 2) * 64;
+                __syncwarp();
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {   // the 64 biases in consumption order (weights: element i <- column 4 ((i/4) ^ (o & 7)) + i % 4), prescaled
+                    const int nb = ncol0 + g * 32, rem = nb % KPL;
+                    const bool is_w = rem < KK * LVC_OUT;
+                    const int m = (rem >> 5) & 7;
+                    const int j = is_w ? ((((lane >> 2) ^ m) << 2) + (lane & 3)) : lane;
+                    bs[g * 32 + lane] = bias[nb + j] * (is_w ? S16_KERN : 1.f);
+                }
+                __syncwarp();
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * 64;
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {
+                    const int nb = ncol0 + g * 32, rem = nb % KPL;
+                    const bool is_w = rem < KK * LVC_OUT;     // warp-uniform
+                    const int m = (rem >> 5) & 7;              // o & 7 of this image row
+                    uint32_t v[32];
+                    if (is_w) {
+#pragma unroll
+                        for (int c8 = 0; c8 < 8; ++c8) tmem_ld_32x32b_x4(tbase + g * 32 + 4 * (c8 ^ m), &v[4 * c8]);   // elements 4 c8 .. 4 c8 + 3
+                    } else {
+                        tmem_ld_32x32b_x32(tbase + g * 32, v);
+                    }
+                    tmem_ld_wait();
+                    if (valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(rec + nb);    // the 128-byte row of (layer, tap, o), or 32 fp32 biases
+                        if (is_w) {
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                float x[8];
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    x[e] = fmaf(__uint_as_float(v[8 * c + e]), inv_s, bs[g * 32 + 8 * c + e]);
+                                    vmax = fmaxf(vmax, fabsf(x[e]));
+                                }
+                                uint4 hi, lo;
+                                hi.x = pack_f16x2_sat(x[1], x[0]); hi.y = pack_f16x2_sat(x[3], x[2]); hi.z = pack_f16x2_sat(x[5], x[4]); hi.w = pack_f16x2_sat(x[7], x[6]);
+                                const float2 h0 = unpack_f16x2(hi.x), h1 = unpack_f16x2(hi.y), h2 = unpack_f16x2(hi.z), h3 = unpack_f16x2(hi.w);
+                                lo.x = pack_f16x2_sat(x[1] - h0.y, x[0] - h0.x); lo.y = pack_f16x2_sat(x[3] - h1.y, x[2] - h1.x);
+                                lo.z = pack_f16x2_sat(x[5] - h2.y, x[4] - h2.x); lo.w = pack_f16x2_sat(x[7] - h3.y, x[6] - h3.x);
+                                dst[c ^ m] = hi;
+                                dst[(4 + c) ^ m] = lo;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                reinterpret_cast<float4*>(dst)[c] = make_float4(fmaf(__uint_as_float(v[4 * c]), inv, bs[g * 32 + 4 * c]), fmaf(__uint_as_float(v[4 * c + 1]), inv, bs[g * 32 + 4 * c + 1]),
+                                                                               fmaf(__uint_as_float(v[4 * c + 2]), inv, bs[g * 32 + 4 * c + 2]), fmaf(__uint_as_float(v[4 * c + 3]), inv, bs[g * 32 + 4 * c + 3]));
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                continue;
+            }
             const int n = nt * 128 + q * 32 + lane;
             const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
             const float bv = bias[n];
@@ -601,52 +677,6 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
 #endif
 #endif
             };
-            if constexpr (STG) {
-                static_assert(EPW == 16, "staged epilogue: 4 warps per 64-column group");
-                unsigned char* stg = smem + KC2_STAGES * KC2_STAGE_BYTES + 256 + cpart * 8192;
-                const bool issuer = (q == 0);               // warp-uniform
-                int off_a = q * 128 + lane * 4, off_b = 0;   // fp32 row: word n | piece row: hi / lo halfword of element i = lane
-                if (pieces && is_w) {
-                    const int oo = (rem >> 5) & 63, ci = ((((lane >> 2) & 7) ^ (oo & 7)) << 2) + (lane & 3);
-                    off_a = q * 128 + 2 * ((((ci >> 3) ^ (oo & 7)) << 3) + (ci & 7));
-                    off_b = q * 128 + 2 * ((((4 + (ci >> 3)) ^ (oo & 7)) << 3) + (ci & 7));
-                }
-                const int p0 = ft * 256 + cpart * CPW;
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * CPW;
-#pragma unroll 1
-                for (int ch = 0; ch < CPW / 8; ++ch) {
-                    unsigned char* buf = stg + (ch & 1) * 4096;
-                    uint32_t v[8];
-                    tmem_ld_32x32b_x8(taddr + ch * 8, v);
-                    tmem_ld_wait();
-                    if (as_pieces) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float sv = fmaf(__uint_as_float(v[j]), inv_s, bv_s);
-                            const uint16_t h16 = f16_sat_bits(sv);
-                            *reinterpret_cast<uint16_t*>(buf + j * 512 + off_a) = h16;
-                            *reinterpret_cast<uint16_t*>(buf + j * 512 + off_b) = f16_sat_bits(sv - f16_bits_to_float(h16));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float*>(buf + j * 512 + off_a) = F16 ? fmaf(__uint_as_float(v[j]), inv, bv) : __uint_as_float(v[j]) + bv;
-                    }
-                    fence_async_smem();
-                    if (issuer) bulk_wait_read0();           // the previous chunk's copies are done with the other buffer
-                    group_sync(1 + cpart, 128);
-                    if (issuer) {
-                        if (lane < 8) {
-                            const int pc = p0 + ch * 8 + lane, center = pc + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
-                            if (pc < M && fp >= 1 && fp <= Tm)
-                                bulk_s2g(kern + ((size_t)bb * Tm + (fp - 1)) * KCN + nt * 128, buf + lane * 512, 512);
-                        }
-                        bulk_commit();
-                    }
-                }
-            } else {
             int p = ft * 256 + cpart * CPW;
             int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
             const bool fast = __shfl_sync(0xffffffffu, (int)((fp >= 1) && (fp + CPW - 1 <= Tm) && (p + CPW - 1 < M)), 0) != 0;
@@ -728,13 +758,12 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     }
                 }
             }
-            }   // !STG
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if constexpr (STG) bulk_wait_all();   // (threads without copies return at once) the staging buffers stay valid until read
+        if constexpr (UNSW) { if (sat && vmax > F16_MAX) *sat = 1u; }   // a predicted kernel left the fp16 range (|k| >= 1023)
     }
     tc_fence_before();
     cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still touch its smem / barriers
@@ -761,15 +790,12 @@ struct TcState {
     CUtensorMap w16_hi[NBLK], w16_lo[NBLK];   // fp16 pieces (LBn_KCT_F16): rows of 96 fp32-sized elements = 192 fp16
     CUtensorMap w16p_hi, w16p_lo;             // block 0 in image row order (LB0_KCT_F16P; experimental, built on first use)
     int b0p_ready = 0;
-    int stg_ready[2] = {0, 0};                // staged-epilogue instantiations (option "kc_stage"): attribute set on first use
     float scales16[64];                       // host copy of section SCALES16
     int kc_2cta = 1;       // kernel_conv GEMM on CTA pairs (cta_group::2, default); option "kc_2cta" = 0 selects the 1-CTA kernel
     int kc_exp = 0;        // timing experiments only (option "kc_exp"): 1 = epilogue does nothing, 2 = hi*hi MMAs only (WRONG results)
     int lvc_exp = 0;       // timing experiments only (option "lvc_exp"): 1 = no second conv pass, 2 / 4 = hi*hi only in the LVC / conv (WRONG results)
     int lvc_groups = 2;    // tc_3xf16, block 2: independent 8-warp groups per CTA (2 or 3; option "lvc_groups")
     int b0_attr_set = 0;   // experimental block-0 kernel: attribute set on first use
-    int b2f_attr_set = 0;  // experimental block-2 flavour with skip rows from memory: likewise
-    int b2p_attr_set = 0;  // experimental pipelined block-2 kernel: likewise
     int lvc_swizzle = 0;   // LVC operand tiles: 0 = no-swizzle panels, 1 = SWIZZLE_128B + base_offset, 2 = SWIZZLE_128B, base_offset 0
     bool ok = false;
 };
@@ -834,7 +860,7 @@ static inline int tc_init(void** state, int device, const float* blob, const uin
 
 // hk_hi / hk_lo: (3, B, T'+2, 64) each, written by k_kp_hidden.
 static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st,
-                             std::string& err, uint64_t* launches, int b0_pieces = 0, int stage = 0) {
+                             std::string& err, uint64_t* launches, int b0_pieces = 0, int unswap = 0, unsigned int* sat = nullptr) {
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (b0_pieces && mode == FD_MODE_TC_3XF16 && !s->b0p_ready) {   // experimental path: maps + attribute on first use only
@@ -842,6 +868,7 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         if (tc_make_map_2d(s, &s->w16p_hi, w16, KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
         if (tc_make_map_2d(s, &s->w16p_lo, w16 + (size_t)KCN * (KCK / 2), KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
         cudaError_t ea = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
+        if (ea == cudaSuccess) ea = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2U_SMEM_BYTES);
         if (ea != cudaSuccess) { err = std::string("k_kc_gemm_tc2<f16, b0 pieces>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
         s->b0p_ready = 1;
     }
@@ -863,22 +890,10 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
         float inv[NBLK];
         for (int n = 0; n < NBLK; ++n) inv[n] = 1.f / (s->scales16[n] * S16_HK);
-        if (stage) {   // experimental staged epilogue (bulk shared->global stores)
-            const int smem_bytes = KC2_SMEM_BYTES + KC2_STG_BYTES;
-            if (!s->stg_ready[b0_pieces ? 1 : 0]) {
-                cudaError_t ea = b0_pieces ? cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
-                                           : cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-                if (ea != cudaSuccess) { err = std::string("k_kc_gemm_tc2<staged>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
-                s->stg_ready[b0_pieces ? 1 : 0] = 1;
-            }
-            if (b0_pieces) {
-                maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
-                k_kc_gemm_tc2<true, 16, true, true><<<2 * clusters, 64 + 32 * 16, smem_bytes, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
-                                                                            s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
-            } else {
-                k_kc_gemm_tc2<true, 16, false, true><<<2 * clusters, 64 + 32 * 16, smem_bytes, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
-                                                                             s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
-            }
+        if (b0_pieces && unswap) {   // default: frames on the M side, 16-byte stores of complete operand rows
+            maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
+            k_kc_gemm_tc2<true, 16, true, true><<<2 * clusters, 64 + 32 * 16, KC2U_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                                          s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], 0, sat);
         } else
         if (b0_pieces) {
             maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
@@ -1468,15 +1483,6 @@ __device__ __forceinline__ void split4_f16_pre(const float sx, const float sy, c
 #ifndef LH_GATE_ASM
 #define LH_GATE_ASM 1
 #endif
-#ifndef LH_ROW_SPREAD
-#define LH_ROW_SPREAD 0
-#endif
-#ifndef LH_PREFETCH_EPI
-#define LH_PREFETCH_EPI 0
-#endif
-#ifndef LH_NO_END_SYNC
-#define LH_NO_END_SYNC 0
-#endif
 __device__ __forceinline__ float gate_st(float a, float b) {
     const float bc = fmaxf(b, -15.f);   // E = e^-2b must stay finite (E -> 0 for large b is harmless); tanh(-15) = -1 to fp32 precision
 #if !LH_GATE_ASM
@@ -1551,11 +1557,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
     // its row within each 32-row block of the A transform.  LH_ROW_SPREAD = 1 (experiment, off: not measured yet) gives a warp the rows
     // r, r+4, r+8, r+12 instead of 4 consecutive ones: their swizzle XOR then differs in bit 2, so the hi (and lo) 8-byte piece stores of
     // a warp cover both halves of the 128-byte bank line -- 2 shared-memory wavefronts per STS.64 instead of 4 (ncu: 1.8 M excess per launch)
-#if LH_ROW_SPREAD
-    const int prow = ((gw >> 2) << 4) + (gw & 3) + ((lane >> 3) << 2);
-#else
     const int prow = gt >> 3;
-#endif
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0), g_u = __shfl_sync(0xffffffffu, g, 0);
     const uint32_t slot_u = smem_u32(smem) + (uint32_t)(g_u * SLOT);
     const uint32_t cw_u = smem_u32(cw);
@@ -1584,11 +1586,6 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             if (!SKIP_FIRST && skip_in) bulk_g2s(s_t + ar0 * 128, skip + off, (uint32_t)(ar1 - ar0) * 128u, &bar[2]);
         }
         if (SKIP_FIRST && i1 > i0) bulk_g2s(au + i0, skip + (size_t)b * T + (t0 - 32 + i0), (uint32_t)(i1 - i0) * 4u, &bar[2]);
-#if LH_PREFETCH_EPI
-        // experiment (off: not measured yet): the gate epilogue of a skip_out layer reads the tile's 128 skip rows from global memory and
-        // stalls on them (block 1, ncu: 25 % of the stall samples sit on the first use of those loads) -- pull them into L2 one tile ahead
-        if (!SKIP_FIRST && skip_out && t0 < T) bulk_prefetch_l2(skip + ((size_t)b * T + t0) * C, (uint32_t)min(LT_TT, T - t0) * 128u);
-#endif
 #pragma unroll
         for (int fi = 0; fi < NF; ++fi) {
             const int f = t0 / HOP + fi;
@@ -1902,15 +1899,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
             }
         }
         tc_fence_before();
-#if LH_NO_END_SYNC
-        // experiment (off: not measured yet; block 1 spends 10 % of its stall samples here): without xs rows in shared memory (!SKIP_FIRST)
-        // nothing the gate epilogue touches is written before the next group barrier -- the next tile's phase 1 works on the A / skip tiles
-        // (loaded after this tile's LVC MMAs completed), the lbias buffers alternate, and every later MMA issue sits behind a barrier
-        // that a warp reaches only after it has finished its TMEM reads here
-        if (SKIP_FIRST) group_sync(1 + g, GT);
-#else
         group_sync(1 + g, GT);   // the group's TMEM columns and xs rows are free for its next tile
-#endif
         if (--tt < 0) { tt = ntt - 1; --b; }
     }
     tc_fence_before();
@@ -1922,7 +1911,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
 }
 
 }  // namespace fd
-#include "fd_kernels_tc_exp.cuh"   // k_lvc_layer_p, k_lvc_layer_b0h, k_b0_panel_to_pieces (experimental, off by default)
+#include "fd_kernels_lvc_b0.cuh"   // k_lvc_layer_b0h: LVC block 0 (hop 8) in swapped-operand form
 #include "fd_kernels_lvcp.cuh"     // k_lvc_p: LVC layers of blocks 1, 2 on the default path (piece-row protocol, warp-specialised pipeline)
 namespace fd {
 
@@ -2576,57 +2565,11 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
 #ifndef FD_EMU
 static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const float* x_in, const float* skip, const float* kern,
                                float* x_out, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches,
-                               bool* done, int b2_skip_rows = 0, int b2_pipe = 0) {
+                               bool* done) {
     *done = false;
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (blk == 0) return 0;   // hop 8: stays on the SIMT kernel
-    // experimental option "lvc_pipe": software-pipelined tile walk; together with "b2_skipbuf" for the layers whose input rows already
-    // carry the skip (1..3; layer 0 loads the skip tile and runs the block-1 flavour below)
-    if (mode == FD_MODE_TC_3XF16 && blk == 2 && b2_pipe && (!b2_skip_rows || layer > 0)) {
-        if (!s->b2p_attr_set) {
-            cudaError_t ea = cudaFuncSetAttribute(k_lvc_layer_p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM_BYTES);
-            if (ea == cudaSuccess) ea = cudaFuncSetAttribute(k_lvc_layer_p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP_SMEM_BYTES);
-            if (ea != cudaSuccess) { err = std::string("k_lvc_layer_p: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
-            s->b2p_attr_set = 1;
-        }
-        LvcHParams hp;
-        hp.cw16 = s->blob + s->sec_off[FD_S_LB2_CONV_F16] + (size_t)layer * (LH_CW_BYTES / 4);
-        hp.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + 2 * FD_LB_STRIDE] + layer * C;
-        hp.first_w = s->blob + s->sec_off[FD_S_FIRST_W];
-        hp.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
-        const float inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * 2 + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
-        const int tiles = B * ((T + LT_TT - 1) / LT_TT), per = (tiles + 1) / 2, grid = per < s->sm_count ? per : s->sm_count;
-        if (b2_skip_rows) k_lvc_layer_p<true><<<grid, 512, LP_SMEM_BYTES, st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, layer < LAYERS - 1 ? 1 : 0);
-        else              k_lvc_layer_p<false><<<grid, 512, LP_SMEM_BYTES, st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, 0);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_p failed: ") + cudaGetErrorString(e); return -3; }
-        ++*launches;
-        *done = true;
-        return 0;
-    }
-    if (mode == FD_MODE_TC_3XF16 && blk == 2 && b2_skip_rows) {
-        // experimental option "b2_skipbuf": `skip` = first_conv(audio) as (B,T,32) rows; block 2 then runs the block-1 flavour of the
-        // kernel (skip rows bulk-loaded by the first layer, added to the produced rows by layers 0..2)
-        if (!s->b2f_attr_set) {
-            cudaError_t ea = cudaFuncSetAttribute(k_lvc_layer_h<256, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lh_smem_bytes<256, false, 2>());
-            if (ea != cudaSuccess) { err = std::string("k_lvc_layer_h<256, false, 2>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
-            s->b2f_attr_set = 1;
-        }
-        LvcHParams hp;
-        hp.cw16 = s->blob + s->sec_off[FD_S_LB2_CONV_F16] + (size_t)layer * (LH_CW_BYTES / 4);
-        hp.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + 2 * FD_LB_STRIDE] + layer * C;
-        hp.first_w = nullptr; hp.first_b = nullptr;
-        const float inv_c = 1.f / (S16_ACT * s->scales16[4 + 4 * 2 + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
-        const int tiles = B * ((T + LT_TT - 1) / LT_TT), per = (tiles + 1) / 2, grid = per < s->sm_count ? per : s->sm_count;
-        k_lvc_layer_h<256, false, 2><<<grid, 512, lh_smem_bytes<256, false, 2>(), st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, s->lvc_exp,
-                                                                                  layer == 0 ? 1 : 0, layer < LAYERS - 1 ? 1 : 0);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_h<256, false, 2> failed: ") + cudaGetErrorString(e); return -3; }
-        ++*launches;
-        *done = true;
-        return 0;
-    }
     if (mode == FD_MODE_TC_3XF16) {
         LvcHParams hp;
         hp.cw16 = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16] + (size_t)layer * (LH_CW_BYTES / 4);
@@ -2672,18 +2615,7 @@ static inline int tc_lvc_layer(void* state, int mode, int blk, int layer, const 
     return 0;
 }
 
-// EXPERIMENTAL (option "tc_b0"): block 0 on tensor cores.  tc_b0_convert rewrites the block's predicted kernels (all layers) from the
-// GEMM's fp32 panel image to fp16 pieces, in place; tc_lvc_layer_b0 runs one layer.  The kernel's shared-memory attribute is set
-// here on first use, not in tc_set_lvc_attrs: nothing of this path is touched unless the option is on.
-static inline int tc_b0_convert(void* state, float* kern0, int B, int Tm, cudaStream_t st, std::string& err, uint64_t* launches) {
-    TcState* s = (TcState*)state;
-    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
-    k_b0_panel_to_pieces<<<B * Tm * LAYERS, 256, 0, st>>>(kern0, B * Tm);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { err = std::string("launch of k_b0_panel_to_pieces failed: ") + cudaGetErrorString(e); return -3; }
-    ++*launches;
-    return 0;
-}
+// LVC block 0 on tensor cores (k_lvc_layer_b0h); the kernel's shared-memory attribute is set here on first use.
 static inline int tc_lvc_layer_b0(void* state, int layer, const float* x_in, const float* skip, const float* kern, float* x_out,
                                   int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches) {
     TcState* s = (TcState*)state;

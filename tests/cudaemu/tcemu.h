@@ -295,6 +295,7 @@ template <int N> inline void emu_tmem_ld(uint32_t taddr, uint32_t (&v)[N]) {
 inline void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) { emu_tmem_ld<32>(taddr, v); }
 inline void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) { emu_tmem_ld<16>(taddr, v); }
 inline void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&v)[8]) { emu_tmem_ld<8>(taddr, v); }
+inline void tmem_ld_32x32b_x4(uint32_t taddr, uint32_t* v) { uint32_t t[4]; emu_tmem_ld<4>(taddr, t); for (int i = 0; i < 4; ++i) v[i] = t[i]; }
 
 // packed fp16 helpers (cvt.rn.satfinite.f16x2.f32 d, a, b: a -> upper half, b -> lower half)
 inline uint16_t emu_f16_sat(float f) {

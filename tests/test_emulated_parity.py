@@ -153,13 +153,12 @@ def test_emulated_tensor_core_mode_ragged_shapes(synth, emu_lib, B, Tm):
     assert (net((x, mel, t)) - O.denoise(W, x, mel, t)).abs().max() < 5e-5
 
 
-@pytest.mark.parametrize("B,Tm,variant", [(2, 33, 1), (1, 129, 1), (3, 17, 2)])
-def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm, variant):
-    """Option tc_b0 (experimental, default off): LVC block 0 (hop 8) on the tensor-core model in swapped-operand form --
-    k_lvc_layer_b0h (kernels of a frame pair as the M = 128 operand, 16 step columns, 3-slot kernel ring across tiles, second MMA
-    pass for the halo rows, tanh/sigmoid exchange through shared memory), fed either by the GEMM writing block 0 as fp16 pieces
-    itself (variant 1: k_kc_gemm_tc2<true, 16, true> on the image-ordered weight rows LB0_KCT_F16P) or by the in-place converter
-    (variant 2: k_b0_panel_to_pieces).  Block-0 output, the decoded pieces and eps against the oracle and the default path."""
+@pytest.mark.parametrize("B,Tm", [(2, 33), (1, 129), (3, 17)])
+def test_emulated_block0_tensor_core(synth, emu_lib, B, Tm):
+    """LVC block 0 (hop 8) on the tensor-core model in swapped-operand form (default of mode tc_3xf16 since round 2) -- k_lvc_layer_b0h
+    (kernels of a frame pair as the M = 128 operand, 16 step columns, 3-slot kernel ring across tiles, second MMA pass for the halo rows,
+    tanh/sigmoid exchange through shared memory), fed by the GEMM writing block 0 as fp16 pieces itself (k_kc_gemm_tc2<true, 16, true> on
+    the image-ordered weight rows LB0_KCT_F16P).  Block-0 output, the decoded pieces and eps against the oracle and the SIMT block-0 path."""
     from fastdiff_b200.synthetic import make_inputs
     from oracle import fastdiff_oracle as O
     import torch.nn.functional as F
@@ -170,118 +169,82 @@ def test_emulated_block0_tensor_core_option(synth, emu_lib, B, Tm, variant):
     t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
     ref, inter = O.denoise(W, x, mel, t, return_intermediates=True)
     eng = net.engine()
-    eps_default = net((x, mel, t))
-    eng.set_option("tc_b0", variant)
     eps = net((x, mel, t))
     assert (eps - ref).abs().max() < 5e-5
-    assert (eps - eps_default).abs().max() < 5e-5
-    if variant == 1:     # both feeds hold the same pieces: identical bits downstream; so does the FFMA GEMM + converter fallback
-        eng.set_option("tc_b0", 2)
-        assert torch.equal(net((x, mel, t)), eps)
-        eng.set_option("tc_b0", 1)
     noise = F.linear(inter["embed"], W["lvc_blocks.0.fc_t.weight"], W["lvc_blocks.0.fc_t.bias"]).unsqueeze(-1)
     k, bb = O.kernel_predictor(W, "lvc_blocks.0.kernel_predictor", mel + noise)
-    assert (eng.debug_read("kernels0", B, Tm).reshape(k.shape) - k).abs().max() < 4e-5      # decoded from the converted pieces
+    assert (eng.debug_read("kernels0", B, Tm).reshape(k.shape) - k).abs().max() < 4e-5      # decoded from the pieces
     assert (eng.debug_read("kbias0", B, Tm).reshape(bb.shape) - bb).abs().max() < 4e-5
     eng.set_option("stop_after", 3)
     net((x, mel, t))
     assert (eng.debug_read("lvc0", B, Tm).reshape(B, 32, Tm * 8) - inter["lvc0"]).abs().max() < 1e-4
-    eng.set_option("stop_after", 1)                 # the GEMM only (variant 2: block 0's kernels are still the fp32 panel image)
-    net((x, mel, t))
-    assert (eng.debug_read("kernels0", B, Tm).reshape(k.shape) - k).abs().max() < 4e-5
     eng.set_option("stop_after", 99)
-    # an item evaluated alone = the same item inside the batch, bitwise (per-tile work is independent of the tile walk)
-    if B > 1:
+    if B > 1:      # an item evaluated alone = the same item inside the batch, bitwise (per-tile work is independent of the tile walk)
         assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), eps[1:2])
+    eng.set_option("tc_b0", 0)                      # SIMT block 0 (fp32 panel image of the kernels)
+    eps_simt_b0 = net((x, mel, t))
+    eng.set_option("tc_b0", 1)
+    assert (eps_simt_b0 - ref).abs().max() < 5e-5 and (eps_simt_b0 - eps).abs().max() < 5e-5
     net.mode = "fp32_simt"                          # the option only applies to mode tc_3xf16
     assert (net((x, mel, t)) - ref).abs().max() < 5e-5
 
 
-@pytest.mark.parametrize("B,Tm", [(2, 9), (1, 33)])
-def test_emulated_block2_skip_rows_option(synth, emu_lib, B, Tm):
-    """Option b2_skipbuf (experimental, default off): first_conv(audio) is written once per evaluation as (B,T,32) rows
-    (k_first_conv_rows, over block 0's dead predicted kernels) and LVC block 2 runs the block-1 flavour of the kernel
-    (k_lvc_layer_h<256, false, 2>: skip rows bulk-loaded by layer 0, added to the produced rows by layers 0..2) instead of
-    recomputing the 7-tap conv over 184 rows x 32 channels in every layer.  Same operation order -> the same bits as the default."""
-    from fastdiff_b200._lib import FdError
+@pytest.mark.parametrize("B,Tm", [(1, 3), (2, 9), (3, 17), (1, 40)])
+def test_emulated_piece_row_path_vs_row_path(synth, emu_lib, B, Tm):
+    """Blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>, the default; fd_kernels_lvcp.cuh) against the oracle and
+    against the fp32-row kernels they replace (k_lvc_layer_h, option lvc_p = 0): lvc1 / lvc2 stage outputs and eps.  The two paths
+    differ by the 22-bit state carry only (~2e-6 on eps).  (1,3): single-tile CTAs; (2,9), (3,17): odd T' -> a half tile ends every
+    item of block 1; (1,40): chunks of several tiles (carried rows, kernel reuse across the two tiles of a hop-256 frame, ring wrap)."""
     from fastdiff_b200.synthetic import make_inputs
     from oracle import fastdiff_oracle as O
     sd, W = synth
     net = _net(sd, emu_lib)
     net.mode = "tc_3xf16"
-    x, mel = make_inputs(B, Tm, 31)
-    t = torch.tensor([7.413235, 498.0537][:B]).reshape(B, 1)
+    x, mel = make_inputs(B, Tm, 61)
+    t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
+    ref, inter = O.denoise(W, x, mel, t, return_intermediates=True)
     eng = net.engine()
-    eps_default = net((x, mel, t))
-    eng.set_option("b2_skipbuf", 1)
-    eps = net((x, mel, t))
-    assert torch.equal(eps, eps_default)
-    assert (eps - O.denoise(W, x, mel, t)).abs().max() < 5e-5
-    with pytest.raises(FdError, match="overwritten"):          # block 0's kernels made room for the skip rows
-        eng.debug_read("kernels0", B, Tm)
-    eng.debug_read("kernels1", B, Tm)
-    eng.set_option("tc_b0", 1)                                  # together with the tensor-core block 0
-    assert (net((x, mel, t)) - eps).abs().max() < 5e-5
+    out = {}
+    for lp in (1, 0):
+        eng.set_option("lvc_p", lp)
+        out[lp] = net((x, mel, t))
+        assert (out[lp] - ref).abs().max() < 5e-5
+        assert (eng.debug_read("lvc2", B, Tm).reshape(B, 32, Tm * 256) - inter["lvc2"]).abs().max() < 2e-4
+        eng.set_option("stop_after", 4)
+        net((x, mel, t))
+        assert (eng.debug_read("lvc1", B, Tm).reshape(B, 32, Tm * 64) - inter["lvc1"]).abs().max() < 2e-4
+        eng.set_option("stop_after", 99)
+    eng.set_option("lvc_p", 1)
+    assert (out[1] - out[0]).abs().max() < 1e-5
+    assert not eng.check_saturation()
+    if B > 1:      # an item alone = the same item inside the batch, bitwise
+        assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), out[1][1:2])
 
 
-@pytest.mark.parametrize("B,Tm", [(2, 33), (2, 129)])
-def test_emulated_gemm_staged_epilogue_option(synth, emu_lib, B, Tm):
-    """Option kc_stage (experimental, default off): the kernel_conv GEMM stages its output rows in shared memory ([8 frames][512 B] per
-    column group, two buffers) and writes them with 512-byte cp.async.bulk shared->global copies instead of 2-byte LSU stores --
-    k_kc_gemm_tc2<true, 16, *, true>.  Same values, same addresses: predicted kernels (pieces and fp32 rows), biases and eps are
-    bit-identical to the default epilogue, alone and combined with tc_b0 (block 0 as pieces).  (2,129): two frame tiles, the pad
-    columns between the two utterances fall inside a chunk and are skipped.)"""
+def test_emulated_saturation_flag(synth, emu_lib):
+    """The range guard of mode tc_3xf16: operands are fp16 pieces of 16 x activation and saturate at 65504 instead of overflowing; every
+    kernel that forms pieces raises a sticky device flag (fd_check_saturation) -- ADVICE round 1: the mode must not fail silently."""
     from fastdiff_b200.synthetic import make_inputs
     sd, _ = synth
     net = _net(sd, emu_lib)
     net.mode = "tc_3xf16"
-    x, mel = make_inputs(B, Tm, 41)
-    t = torch.tensor([7.413235, 498.0537]).reshape(B, 1)
+    x, mel = make_inputs(1, 3, 62)
+    t = torch.tensor([[74.99228]])
     eng = net.engine()
-    eps0 = net((x, mel, t))
-    k0 = [eng.debug_read(f"{nm}{n}", B, Tm).clone() for n in range(3) for nm in ("kernels", "kbias")]
-    eng.set_option("kc_stage", 1)
-    eps1 = net((x, mel, t))
-    k1 = [eng.debug_read(f"{nm}{n}", B, Tm) for n in range(3) for nm in ("kernels", "kbias")]
-    assert torch.equal(eps0, eps1)
-    assert all(torch.equal(a, b) for a, b in zip(k0, k1))
-    eng.set_option("tc_b0", 1)
-    eps2 = net((x, mel, t))
-    eng.set_option("kc_stage", 0)
-    assert torch.equal(net((x, mel, t)), eps2)
-
-
-@pytest.mark.parametrize("B,Tm", [(1, 1), (3, 17), (1, 40)])
-def test_emulated_block2_pipelined_tile_walk_option(synth, emu_lib, B, Tm):
-    """Option lvc_pipe (experimental, default off): k_lvc_layer_p runs LVC block 2 with the phases of consecutive tiles of a group
-    software-pipelined (P1(i) | conv MMAs(i) | gate epilogue(i-1) | P3(i) | LVC MMAs(i)), every per-tile buffer doubled (A/Y tile, xs
-    rows, TMEM column set, lbias) and the loads re-timed.  Same arithmetic and tile walk -> the default's bits, for single-tile
-    groups, chunks of several tiles (carried halo rows, kernel reuse across the two tiles of a frame) and ragged batches."""
-    from fastdiff_b200.synthetic import make_inputs
-    from oracle import fastdiff_oracle as O
-    sd, W = synth
-    net = _net(sd, emu_lib)
-    net.mode = "tc_3xf16"
-    x, mel = make_inputs(B, Tm, 51)
-    t = torch.tensor([7.413235, 498.0537, 74.99228][:B]).reshape(B, 1)
-    eng = net.engine()
-    eps0 = net((x, mel, t))
-    eng.set_option("lvc_pipe", 1)
-    eps1 = net((x, mel, t))
-    assert torch.equal(eps0, eps1)
-    assert (eps1 - O.denoise(W, x, mel, t)).abs().max() < 5e-5
-    if B > 1:      # an item alone = the same item inside the batch, bitwise
-        assert torch.equal(net((x[1:2], mel[1:2], t[1:2])), eps1[1:2])
-    eng.set_option("b2_skipbuf", 1)     # combined: layer 0 loads the skip tile (k_lvc_layer_h<256, false, 2>), layers 1..3 run k_lvc_layer_p<true>
-    assert torch.equal(net((x, mel, t)), eps0)
+    net((x, mel, t))
+    assert not eng.check_saturation()
+    out = net((x * 3e4, mel, t))                    # |activation| * 16 >> 65504
+    assert torch.isfinite(out).all()
+    assert eng.check_saturation()                   # raised ... and cleared by the call
+    assert not eng.check_saturation()
 
 
 def test_emulated_kernels_under_all_async_schedules(synth, emu_lib):
     """cp.async.bulk global->shared copies and tcgen05.mma are asynchronous.  The model can land a copy's bytes at issue (adversarial for
     a target something still reads) or when its mbarrier is first polled (adversarial for a target read or written before the wait),
     and can run the MMAs at issue or when their commit barrier is first polled (adversarial for an operand tile refilled, or an
-    accumulator read, too early).  The default path and every optional kernel that re-times its loads or its MMAs (ring-fed block 0,
-    pipelined block 2, skip rows, staged GEMM epilogue) must give the same bits under all of them."""
+    accumulator read, too early).  The default path (warp-specialised k_lvc_p with its 3 + 2 + 2 stage rings, ring-fed block 0) and the
+    fp32-row kernels behind the options must give the same bits under all of them."""
     import ctypes
     from fastdiff_b200.synthetic import make_inputs
     sd, _ = synth
@@ -291,17 +254,19 @@ def test_emulated_kernels_under_all_async_schedules(synth, emu_lib):
     model = ctypes.CDLL(emu_lib)
     x, mel = make_inputs(2, 12, 4)
     t = torch.tensor([[7.413235], [498.0537]])
-    names = ("lvc_pipe", "tc_b0", "b2_skipbuf", "kc_stage")
+    variants = {"default": {}, "rows": {"lvc_p": 0}, "simt_b0": {"tc_b0": 0}}
     out = {}
     try:
-        for late in (0, 2, 3):          # early / late MMAs with early loads / everything late (late loads alone is covered by 3)
+        for late in (0, 1, 2, 3):       # early / late loads / late MMAs / everything late
             model.cudaemu_set_bulk_late(late)
-            for on in (None,) + names + ("pipe+rows",):
-                for k in names:
-                    eng.set_option(k, 1 if (k == on or (on == "pipe+rows" and k in ("lvc_pipe", "b2_skipbuf"))) else 0)
-                out[(late, on)] = net((x, mel, t))
+            for name, opts in variants.items():
+                eng.set_option("lvc_p", opts.get("lvc_p", 1))
+                eng.set_option("tc_b0", opts.get("tc_b0", 1))
+                out[(late, name)] = net((x, mel, t))
     finally:
         model.cudaemu_set_bulk_late(0)
-    for on in (None,) + names + ("pipe+rows",):
-        for late in (2, 3):
-            assert torch.equal(out[(0, on)], out[(late, on)]), (on, late)
+        eng.set_option("lvc_p", 1)
+        eng.set_option("tc_b0", 1)
+    for name in variants:
+        for late in (1, 2, 3):
+            assert torch.equal(out[(0, name)], out[(late, name)]), (name, late)

@@ -405,7 +405,8 @@ def test_full_schedule_n1000_vs_oracle(synth, cuda_lib):
             assert err < 5e-4, (i, err)
     for i in list(range(100, 1000, 100)) + [998, 999]:      # teacher-forced single steps across the rest of the schedule
         err = (got[i + 1] - oracle_step(got[i], i)).abs().max().item()
-        assert err < 5e-5, (i, err)
+        scale = max(1.0, got[i].abs().max().item())        # the random-init network lets |x| grow to ~200 over the loop: the bound is relative
+        assert err < 5e-5 * scale, (i, err, scale)
     assert torch.isfinite(got[-1]).all()
 
 

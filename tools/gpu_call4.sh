@@ -1,9 +1,9 @@
 #!/bin/bash
-# Round-2 call 3: k_lvc_p v2 (skip on the tensor core, leaner epilogues), CUDA-graph replay, reference-on-GPU + drop-in tests, FFMA2 probe.
+# Round-2 call 4: k_lvc_p v3 (8 conv-epilogue warps), un-swapped kernel_conv GEMM, graph replay on an internal capture stream.
 set -u
-OUT=gpurun_out/r2_c3
+OUT=gpurun_out/r2_c4
 mkdir -p "$OUT"
-timeout 60 tests/microbench/ffma2 > "$OUT/ffma2.log" 2>&1
+
 timeout 300 python tests/gpu_lvcp_check.py > "$OUT/lvcp_check.log" 2>&1; echo "rc=$?" >> "$OUT/lvcp_check.log"
 if ! grep -q "PARITY OK" "$OUT/lvcp_check.log"; then echo "quick parity failed" > "$OUT/summary.txt"; tail -30 "$OUT/lvcp_check.log" >> "$OUT/summary.txt"; fi
 timeout 1200 python -m pytest tests -m gpu -q > "$OUT/gpu_tests.log" 2>&1; echo "pytest rc=$?" >> "$OUT/gpu_tests.log"
@@ -15,6 +15,7 @@ timeout 150 $B --no-cpu --batch 1 --frames 86 --opt graphs=0 > "$OUT/bench_1x86_
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file "$OUT/launches.csv" python bench.py --steps 1 --warmup 1 --no-cpu --opt graphs=0 > "$OUT/ncu_list.log" 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_lvc_p -s 12 -c 2 -o "$OUT/lvcp" python bench.py --steps 1 --warmup 1 --no-cpu --opt graphs=0 > "$OUT/ncu_full.log" 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_kc_gemm -s 4 -c 1 -o "$OUT/gemm" python bench.py --steps 1 --warmup 1 --no-cpu --opt graphs=0 > "$OUT/ncu_gemm.log" 2>&1
 grep -h '"value"' "$OUT"/bench_*.json | python -c "
 import sys, json
 for l in sys.stdin:
