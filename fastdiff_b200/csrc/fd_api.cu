@@ -34,6 +34,8 @@ struct fd_handle {
     int tc_b0 = 1;               // mode tc_3xf16: LVC block 0 on tensor cores (k_lvc_layer_b0h, its kernels written as fp16 pieces by the GEMM; option "tc_b0", 0 = SIMT k_lvc_layer<8>)
     int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
+    int noise_draw_base = 0;     // device-noise mode: Philox draw number of a call's first noisy step minus one (option "noise_draw_base": callers that run
+                                 // the reverse loop one fd_sample call per step -- time-shard mode -- keep the draw numbers of the single-call loop)
     long long noise_win_L = 0, noise_win_off = 0;   // Philox element window of the device-noise mode (fd_set_noise_window; time-shard mode)
     int graphs = 1;              // fd_sample in device-noise mode: capture the whole call (all N <= 64 steps) in a CUDA graph on first use and
                                  // replay it afterwards (option "graphs"; the workspace, shapes, schedule and options are the cache key)
@@ -52,7 +54,7 @@ struct fd_handle {
     uint64_t launches = 0;
 #ifndef FD_EMU
     struct GraphEntry {
-        void* ws; int B, Tm, n_steps, ddim, fill_xT; uint64_t epoch; std::vector<fd_step> steps;
+        void* ws; int B, Tm, n_steps, ddim, fill_xT, draw_base; uint64_t epoch; std::vector<fd_step> steps;
         cudaGraphExec_t exec; uint64_t n_launches; uint64_t last_use;
     };
     std::vector<GraphEntry> gcache;
@@ -334,6 +336,7 @@ extern "C" int fd_set_noise_window(fd_handle* h, int64_t total_samples, int64_t 
 
 extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!h || !key) return FD_ERR_INVALID;
+    if (!strcmp(key, "noise_draw_base")) { h->noise_draw_base = (int)value; return FD_OK; }   // part of the graph key: no epoch bump
     ++h->epoch;
     if (!strcmp(key, "graphs")) { h->graphs = (int)value; return FD_OK; }
     if (!strcmp(key, "stop_after")) { h->stop_after = (int)value; return FD_OK; }
@@ -953,7 +956,7 @@ static int sample_body(fd_handle* h, float* x_dev, const float* mel_dev, const f
             fp.add_noise = steps[i].add_noise ? 1 : 0;
             if (fp.add_noise) {
                 if (noise_dev) z = noise_dev + (size_t)draw * n;
-                fp.draw = (uint32_t)(draw + 1); fp.seed = seed;
+                fp.draw = (uint32_t)(h->noise_draw_base + draw + 1); fp.seed = seed;
                 ++draw;
             }
         }
@@ -990,7 +993,7 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
         fd_handle::GraphEntry* hit = nullptr;
         for (auto& g : h->gcache)
             if (g.ws == workspace_dev && g.B == B && g.Tm == Tm && g.n_steps == n_steps && g.ddim == (ddim ? 1 : 0) && g.fill_xT == (fill_xT ? 1 : 0) &&
-                g.epoch == h->epoch && !memcmp(g.steps.data(), steps, sizeof(fd_step) * n_steps)) { hit = &g; break; }
+                g.epoch == h->epoch && g.draw_base == h->noise_draw_base && !memcmp(g.steps.data(), steps, sizeof(fd_step) * n_steps)) { hit = &g; break; }
         if (!hit) {
             cudaGraph_t graph = nullptr;
             const uint64_t l0 = h->launches;
@@ -1015,7 +1018,7 @@ extern "C" int fd_sample(fd_handle* h, float* x_dev, const float* mel_dev, const
                 cudaGraphExecDestroy(h->gcache[lru].exec);
                 h->gcache.erase(h->gcache.begin() + lru);
             }
-            h->gcache.push_back({workspace_dev, B, Tm, n_steps, ddim ? 1 : 0, fill_xT ? 1 : 0, h->epoch, std::vector<fd_step>(steps, steps + n_steps), exec, nl, 0});
+            h->gcache.push_back({workspace_dev, B, Tm, n_steps, ddim ? 1 : 0, fill_xT ? 1 : 0, h->noise_draw_base, h->epoch, std::vector<fd_step>(steps, steps + n_steps), exec, nl, 0});
             hit = &h->gcache.back();
             ++h->graph_captures;
         }

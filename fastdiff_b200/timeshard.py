@@ -7,8 +7,12 @@ ranks exchange exact boundary samples with their neighbours (one send + one rece
 which makes the sharded result equal to the unsharded one for any number of steps.  This is the only mode with a per-step exchange;
 batch-shard mode (shard.py) needs none.  The reference has no counterpart (its test_step is batch-1 on one GPU).
 
-Noise: the reference's RNG stream (CPU default generator, x_T then one draw per noisy step, util.py:216-234) is drawn at full size
-on every rank from the same seed and sliced, so the result also equals the single-GPU parity-mode result.
+Noise, two modes.  "reference": the reference's RNG stream (CPU default generator, x_T then one draw per noisy step, util.py:216-234) is
+drawn at full size on every rank from the same seed and sliced, so the result equals the single-GPU parity-mode result (a correctness
+mode: every rank pays the full-size host draws).  "device" (the LATENCY mode): every rank draws only its own window on the GPU -- the
+Philox element index of a sample is its position in the WHOLE utterance (fd_set_noise_window) and the draw number that of the
+single-call loop (option noise_draw_base) -- so the sharded result is bit-identical to the single-GPU device-noise result with the
+same seed, and nothing but the halo samples crosses NVLink.
 """
 from __future__ import annotations
 
@@ -39,9 +43,10 @@ class TimeShardedSampler:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = engine.device
 
-    def sample(self, size, diffusion_hyperparams, schedule, condition, ddim: bool = False, gather: bool = True) -> torch.Tensor:
+    def sample(self, size, diffusion_hyperparams, schedule, condition, ddim: bool = False, gather: bool = True, noise: str = "reference",
+               seed: int = 0) -> torch.Tensor:
         """size = (B,1,L), condition (B,80,T') on any device, L = 256*T'.  Returns the full (B,1,L) waveform on every rank
-        (gather=True) or this rank's interior (B,1,256*(f_hi-f_lo))."""
+        (gather=True) or this rank's interior (B,1,256*(f_hi-f_lo)).  noise: "reference" | "device" (see the module docstring)."""
         B, _, L = size
         Tm = condition.shape[-1]
         if Tm * HOP != L:
@@ -56,14 +61,29 @@ class TimeShardedSampler:
         _, steps = build_steps(diffusion_hyperparams, schedule, ddim)
         mel = condition[:, :, e_lo:e_hi].to(self.device, torch.float32).contiguous()
         sl = slice(e_lo * HOP, e_hi * HOP)
-        x = torch.normal(0, 1, size=size)[:, :, sl].to(self.device).contiguous()        # x_T: same CPU draw on every rank
-        with torch.no_grad():
-            for st in steps:
-                z = None
-                if st.add_noise and not ddim:
-                    z = torch.normal(0, 1, size=size)[:, :, sl].to(self.device).contiguous().unsqueeze(0)
-                self.engine.sample(x, mel, [st], noise=z, ddim=ddim)
-                self._exchange(x, hl, hr)
+        if noise == "device":
+            x = torch.empty((B, 1, (e_hi - e_lo) * HOP), dtype=torch.float32, device=self.device)
+            self.engine.set_noise_window(L, e_lo * HOP)          # my samples are [e_lo*256, e_hi*256) of utterances of L samples
+            try:
+                with torch.no_grad():
+                    draws = 0
+                    for i, st in enumerate(steps):
+                        self.engine.set_option("noise_draw_base", draws)
+                        self.engine.sample(x, mel, [st], noise=None, seed=seed, fill_xT=(i == 0), ddim=ddim)
+                        draws += 1 if (st.add_noise and not ddim) else 0
+                        self._exchange(x, hl, hr)
+            finally:
+                self.engine.set_option("noise_draw_base", 0)
+                self.engine.set_noise_window(0, 0)
+        else:
+            x = torch.normal(0, 1, size=size)[:, :, sl].to(self.device).contiguous()        # x_T: same CPU draw on every rank
+            with torch.no_grad():
+                for st in steps:
+                    z = None
+                    if st.add_noise and not ddim:
+                        z = torch.normal(0, 1, size=size)[:, :, sl].to(self.device).contiguous().unsqueeze(0)
+                    self.engine.sample(x, mel, [st], noise=z, ddim=ddim)
+                    self._exchange(x, hl, hr)
         interior = x[:, :, hl * HOP: hl * HOP + (f_hi - f_lo) * HOP].contiguous()
         return self._gather(interior, B, ranges) if gather else interior
 

@@ -13,7 +13,7 @@ N4 = [3.2176e-04, 2.5743e-03, 2.5376e-02, 7.0414e-01]
 TM = 45
 
 
-def _worker(rank, world, port, emu_lib, q, mode, B):
+def _worker(rank, world, port, emu_lib, q, mode, B, noise):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -30,15 +30,17 @@ def _worker(rank, world, port, emu_lib, q, mode, B):
     _, mel = make_inputs(B, TM, 8)
     dh = fb.compute_hyperparams_given_schedule(torch.linspace(1e-6, 0.01, 1000))
     torch.manual_seed(21)                                              # same stream on every rank
-    out = ts.sample((B, 1, TM * 256), dh, torch.FloatTensor(N4), mel, gather=True)
+    out = ts.sample((B, 1, TM * 256), dh, torch.FloatTensor(N4), mel, gather=True, noise=noise, seed=77)
     if rank == 0:
         q.put(out)
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,B", [("fp32_simt", 1), ("tc_3xf16", 2)])
-def test_two_rank_time_shard_matches_unsharded(emu_lib, synth, mode, B):
+@pytest.mark.parametrize("mode,B,noise", [("fp32_simt", 1, "reference"), ("tc_3xf16", 2, "reference"), ("tc_3xf16", 2, "device")])
+def test_two_rank_time_shard_matches_unsharded(emu_lib, synth, mode, B, noise):
+    """noise = "device" is the latency mode: every rank draws only its own window on the device (Philox indexed by the sample's position in
+    the whole utterance, draw numbers of the single-call loop) and must reproduce the single-engine device-noise result."""
     import fastdiff_b200 as fb
     from fastdiff_b200.engine import Engine
     from fastdiff_b200.sampler import build_steps
@@ -46,8 +48,8 @@ def test_two_rank_time_shard_matches_unsharded(emu_lib, synth, mode, B):
     from fastdiff_b200.weights import pack_state_dict
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000 + (7 if mode == "tc_3xf16" else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, emu_lib, q, mode, B)) for r in range(2)]
+    port = 31500 + os.getpid() % 2000 + (7 if mode == "tc_3xf16" else 0) + (13 if noise == "device" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, emu_lib, q, mode, B, noise)) for r in range(2)]
     for p in procs:
         p.start()
     import queue
@@ -71,9 +73,13 @@ def test_two_rank_time_shard_matches_unsharded(emu_lib, synth, mode, B):
     _, steps = build_steps(dh, torch.FloatTensor(N4))
     torch.manual_seed(21)
     size = (B, 1, TM * 256)
-    x = torch.normal(0, 1, size=size)
-    zs = torch.stack([torch.normal(0, 1, size=size) for _ in range(3)])
-    eng.sample(x, mel, steps, noise=zs)
+    if noise == "device":
+        x = torch.empty(size)
+        eng.sample(x, mel, steps, noise=None, seed=77, fill_xT=True)
+    else:
+        x = torch.normal(0, 1, size=size)
+        zs = torch.stack([torch.normal(0, 1, size=size) for _ in range(3)])
+        eng.sample(x, mel, steps, noise=zs)
     assert got.shape == x.shape
     err = (got - x).abs().max().item()
     assert err <= 1e-6, err          # same arithmetic per output sample; only the tiling differs (tc_3xf16: the tensor-core model)
