@@ -40,7 +40,6 @@ struct fd_handle {
     int graphs = 1;              // fd_sample in device-noise mode: capture the whole call (all N <= 64 steps) in a CUDA graph on first use and
                                  // replay it afterwards (option "graphs"; the workspace, shapes, schedule and options are the cache key)
     uint64_t epoch = 0;          // bumped by everything that changes what a captured graph would do (mode, options, weights, noise window)
-    int kc_unswap = 1;           // mode tc_3xf16 with tc_b0: kernel_conv GEMM with the frames on the MMA's M side (k_kc_gemm_tc2<.., UNSW>; option "kc_unswap")
     int lvc_p = 1;               // mode tc_3xf16: LVC blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>; option "lvc_p", 0 = k_lvc_layer_h)
     unsigned int* sat_flag = nullptr;   // device word, sticky: an fp16 piece saturated in a tensor-core kernel (fd_check_saturation)
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
@@ -346,7 +345,6 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "lvc_p")) { h->lvc_p = (int)value; return FD_OK; }
-    if (!strcmp(key, "kc_unswap")) { h->kc_unswap = (int)value; return FD_OK; }
     if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
@@ -510,18 +508,14 @@ static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo,
     const int M = B * (Tm + 2) - 2;
     const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
     const int clusters = items < 8 ? items : 8;
-    if (b0_pieces && h->kc_unswap) {
-        auto k = k_kc_gemm_tc2<true, 16, true, true>;
-        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2U_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0, h->sat_flag);
-    } else if (b0_pieces) {
+    if (b0_pieces) {
         auto k = k_kc_gemm_tc2<true, 16, true>;
         FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0, (unsigned int*)nullptr);
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
     } else {
         auto k = k_kc_gemm_tc2<true, 16>;
         FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0, (unsigned int*)nullptr);
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
     }
     FD_CHECK_LAUNCH(h, "k_kc_gemm_tc2");
     return FD_OK;
@@ -742,7 +736,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     } else {
 #ifndef FD_EMU
         ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0, h->kc_unswap, h->sat_flag);
+        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0);
         if (rc) return rc;
 #endif
     }

@@ -39,7 +39,9 @@ constexpr int LP_Y_BYTES = 17408;                // 136 rows x 128 B (130 used)
 constexpr int LP_OUT_BYTES = 16384;              // 128 output rows
 constexpr int LP_CW_BYTES = 3 * C * 128;         // 12288
 constexpr int LP_AU = 136;                       // audio positions t0-4 .. t0+131
-constexpr int LP_THREADS = 832;                  // warps 0-7 conv epilogue, 8-23 gate epilogue, 24 loader, 25 MMA issuer
+constexpr int LP_THREADS = 832;                  // warps 0-15 gate epilogue, 16-23 conv epilogue, 24 loader, 25 MMA issuer.  The hardware's warp
+                                                 // arbiter favours HIGH warp ids: the roles on the critical path (MMA issue, loads, conv epilogue -- each
+                                                 // tile's LVC MMAs wait for it) sit above the 16 gate warps, which otherwise starve them (ncu, round 2)
 constexpr int LP_E2_THREADS = 512;
 
 __host__ __device__ inline size_t lp_rows(int B, int T) { return (size_t)LP_HEAD_ROWS + (size_t)B * (T + LP_PAD_ROWS) + LP_SLACK_ROWS; }
@@ -305,9 +307,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             if (++s == LP_NA) { s = 0; ++sn; }
         }
         if (ntile > 0) lvc_mmas(ntile - 1);
-    } else if (warp_u < 8) {
-        // =========================================== conv epilogue (8 warps) ===========================================
-        const int q = warp & 3, part = warp >> 2;  // TMEM lane quarter; which 16 of the 32 conv channels
+    } else if (warp_u >= 16) {
+        // =========================================== conv epilogue (8 warps: 16..23) ===========================================
+        const int q = warp & 3, part = (warp - 16) >> 2;  // TMEM lane quarter; which 16 of the 32 conv channels
         const int yr = q * 32 + lane;              // Y row of this thread <-> t = t0 - 1 + yr; (part 0) also skip-operand row <-> t = t0 + yr
         const float inv_cs = p.inv_c * S16_ACT;
         float vmax = 0.f;
@@ -394,10 +396,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
         }
         if (p.sat && vmax > F16_MAX) *p.sat = 1u;
     } else {
-        // =========================================== gate epilogue (16 warps) ===========================================
-        const int e = warp - 8, q = warp & 3, j = e >> 2;      // TMEM lane quarter, channel octet (gate channels 8j .. 8j+7)
+        // =========================================== gate epilogue (16 warps: 0..15) ===========================================
+        const int q = warp & 3, j = warp >> 2;                  // TMEM lane quarter, channel octet (gate channels 8j .. 8j+7)
         const int r = q * 32 + lane;                            // output row of this thread
-        const int etid = tid - 256;                             // 0 .. 511
+        const int etid = tid;                                   // 0 .. 511
         const int fi = (HOP >= LP_TT) ? 0 : r / HOP;            // warp-uniform (HOP is a multiple of 32)
         // everything below runs in the x16 domain of the pieces (exact: powers of two): z16 = 16 z, gate x 16, skip x 16
         const float c_s = p.inv_l * -1.4426950408889634f, c_t = p.inv_l * -2.8853900817779268f, c_sk = p.inv_sk * S16_ACT;

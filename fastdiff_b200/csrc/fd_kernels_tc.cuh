@@ -434,18 +434,14 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 // EPW = epilogue warps per CTA (8 or 16: EPW/4 per TMEM lane quarter, each taking 256/(EPW/4) of the 256 frame columns).
 // B0P (experimental, option "tc_b0" = 1): block 0's predicted kernels are written as fp16 pieces as well (its weight rows then come
 // in the same SWIZZLE_128B image order as blocks 1 and 2: sections LB0_KCT_F16P / LB0_KC_BP) for the tensor-core block-0 consumer.
-// UNSW (the default of mode tc_3xf16 since round 2; needs F16, B0P, EPW = 16): the MMA takes the FRAME rows as its M side and the weight
-// rows as N (the two operand tiles of a stage simply swap descriptor slots), so D has lane = frame, column = output channel n and an
-// epilogue thread owns one frame's values for 64 consecutive n = two complete 128-byte rows of the LVC operand image: it writes them
-// with 16-byte stores (8 per row, one full line) instead of the 2-byte stores of the swapped form (lane = n: 64 STG.U16 per 32 values;
-// ncu round 1: the kernel ran at the speed of its 2 GB store stream, lg_throttle 27 %).  The column order inside an image row is the
-// fp32-swizzled one of the weight rows, so the TMEM loads fetch the 4-column groups in the order the piece chunks need them.
-constexpr int KC2U_SMEM_BYTES = KC2_SMEM_BYTES + 4096;   // + per-warp bias staging (16 warps x 64 floats)
-template <bool F16, int EPW, bool B0P = false, bool UNSW = false>
+// (Measured and dropped in round 2: the un-swapped form -- frames on the MMA's M side, so that an epilogue thread owns whole 128-byte operand
+// rows and writes them with 16-byte stores, bit-identical output -- ran at 1.60 ms per launch against 0.61 ms: a warp store then touches 32
+// different lines with 16 bytes each, and the L2 request rate, not the instruction count, is what bounds this store stream.)
+template <bool F16, int EPW, bool B0P = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
               const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass,
-              float inv0, float inv1, float inv2, int exp_mask, unsigned int* __restrict__ sat = nullptr) {
+              float inv0, float inv1, float inv2, int exp_mask) {
     constexpr int NATOM = F16 ? 3 : 6;
     constexpr int CPW = 256 / (EPW / 4);   // frame columns per epilogue warp
     FD_DYN_SMEM(unsigned char, smem_raw);
@@ -525,11 +521,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t adv = (uint64_t)(k * 2);
-                        if (F16 && UNSW) {   // frames = M side, weights = N side
-                            umma_f16_2sm(d_tmem, b_hi + adv, a_hi + adv, idesc, (a | k) ? 1u : 0u);
-                            umma_f16_2sm(d_tmem, b_lo + adv, a_hi + adv, idesc, 1u);   // same product order as the swapped form: w_hi h_lo, then w_lo h_hi
-                            umma_f16_2sm(d_tmem, b_hi + adv, a_lo + adv, idesc, 1u);
-                        } else if (F16) {
+                        if (F16) {
                             umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
                             if (three_pass && !(exp_mask & 2)) {
                                 umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -555,80 +547,9 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
         const int q = warp & 3;
         const int cpart = (warp - 2) >> 2;
         uint32_t acc = 0, acc_phase = 0;
-        [[maybe_unused]] float vmax = 0.f;
         for (int item = pair_id; item < total_items; item += n_clusters) {
             const int blk = item / items_per_blk, r = item % items_per_blk;
             const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
-            if constexpr (UNSW) {
-                static_assert(F16 && B0P && EPW == 16, "unswapped epilogue: fp16 pieces for all three blocks, 4 warps per lane quarter");
-                const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
-                const float inv = blk == 0 ? inv0 : (blk == 1 ? inv1 : inv2), inv_s = inv * S16_KERN;
-                float* kern = kern_all + (size_t)blk * B * Tm * KCN;
-                const int ncol0 = (r % n_pairs) * 256 + cpart * 64;       // this warp's 64 columns = two 32-element image rows (or bias groups)
-                const int p = ft * 256 + (int)rank * 128 + q * 32 + lane;  // this lane's padded frame row
-                const int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
-                const bool valid = p < M && fp >= 1 && fp <= Tm;
-                float* rec = kern + ((size_t)bb * Tm + (valid ? fp - 1 : 0)) * KCN;
-                float* bs = reinterpret_cast<float*>(smem + KC2_SMEM_BYTES) + (warp - 2) * 64;
-                __syncwarp();
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {   // the 64 biases in consumption order (weights: element i <- column 4 ((i/4) ^ (o & 7)) + i % 4), prescaled
-                    const int nb = ncol0 + g * 32, rem = nb % KPL;
-                    const bool is_w = rem < KK * LVC_OUT;
-                    const int m = (rem >> 5) & 7;
-                    const int j = is_w ? ((((lane >> 2) ^ m) << 2) + (lane & 3)) : lane;
-                    bs[g * 32 + lane] = bias[nb + j] * (is_w ? S16_KERN : 1.f);
-                }
-                __syncwarp();
-                mbar_wait(&tfull_bar[acc], acc_phase);
-                tc_fence_after();
-                const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * 64;
-#pragma unroll 1
-                for (int g = 0; g < 2; ++g) {
-                    const int nb = ncol0 + g * 32, rem = nb % KPL;
-                    const bool is_w = rem < KK * LVC_OUT;     // warp-uniform
-                    const int m = (rem >> 5) & 7;              // o & 7 of this image row
-                    uint32_t v[32];
-                    if (is_w) {
-#pragma unroll
-                        for (int c8 = 0; c8 < 8; ++c8) tmem_ld_32x32b_x4(tbase + g * 32 + 4 * (c8 ^ m), &v[4 * c8]);   // elements 4 c8 .. 4 c8 + 3
-                    } else {
-                        tmem_ld_32x32b_x32(tbase + g * 32, v);
-                    }
-                    tmem_ld_wait();
-                    if (valid) {
-                        uint4* dst = reinterpret_cast<uint4*>(rec + nb);    // the 128-byte row of (layer, tap, o), or 32 fp32 biases
-                        if (is_w) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                float x[8];
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) {
-                                    x[e] = fmaf(__uint_as_float(v[8 * c + e]), inv_s, bs[g * 32 + 8 * c + e]);
-                                    vmax = fmaxf(vmax, fabsf(x[e]));
-                                }
-                                uint4 hi, lo;
-                                hi.x = pack_f16x2_sat(x[1], x[0]); hi.y = pack_f16x2_sat(x[3], x[2]); hi.z = pack_f16x2_sat(x[5], x[4]); hi.w = pack_f16x2_sat(x[7], x[6]);
-                                const float2 h0 = unpack_f16x2(hi.x), h1 = unpack_f16x2(hi.y), h2 = unpack_f16x2(hi.z), h3 = unpack_f16x2(hi.w);
-                                lo.x = pack_f16x2_sat(x[1] - h0.y, x[0] - h0.x); lo.y = pack_f16x2_sat(x[3] - h1.y, x[2] - h1.x);
-                                lo.z = pack_f16x2_sat(x[5] - h2.y, x[4] - h2.x); lo.w = pack_f16x2_sat(x[7] - h3.y, x[6] - h3.x);
-                                dst[c ^ m] = hi;
-                                dst[(4 + c) ^ m] = lo;
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                reinterpret_cast<float4*>(dst)[c] = make_float4(fmaf(__uint_as_float(v[4 * c]), inv, bs[g * 32 + 4 * c]), fmaf(__uint_as_float(v[4 * c + 1]), inv, bs[g * 32 + 4 * c + 1]),
-                                                                               fmaf(__uint_as_float(v[4 * c + 2]), inv, bs[g * 32 + 4 * c + 2]), fmaf(__uint_as_float(v[4 * c + 3]), inv, bs[g * 32 + 4 * c + 3]));
-                        }
-                    }
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                continue;
-            }
             const int n = nt * 128 + q * 32 + lane;
             const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
             const float bv = bias[n];
@@ -763,7 +684,6 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if constexpr (UNSW) { if (sat && vmax > F16_MAX) *sat = 1u; }   // a predicted kernel left the fp16 range (|k| >= 1023)
     }
     tc_fence_before();
     cluster_sync_all();     // no CTA of the pair exits (or frees TMEM) while the other may still touch its smem / barriers
@@ -860,7 +780,7 @@ static inline int tc_init(void** state, int device, const float* blob, const uin
 
 // hk_hi / hk_lo: (3, B, T'+2, 64) each, written by k_kp_hidden.
 static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st,
-                             std::string& err, uint64_t* launches, int b0_pieces = 0, int unswap = 0, unsigned int* sat = nullptr) {
+                             std::string& err, uint64_t* launches, int b0_pieces = 0) {
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (b0_pieces && mode == FD_MODE_TC_3XF16 && !s->b0p_ready) {   // experimental path: maps + attribute on first use only
@@ -868,7 +788,6 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         if (tc_make_map_2d(s, &s->w16p_hi, w16, KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
         if (tc_make_map_2d(s, &s->w16p_lo, w16 + (size_t)KCN * (KCK / 2), KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
         cudaError_t ea = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
-        if (ea == cudaSuccess) ea = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2U_SMEM_BYTES);
         if (ea != cudaSuccess) { err = std::string("k_kc_gemm_tc2<f16, b0 pieces>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
         s->b0p_ready = 1;
     }
@@ -890,11 +809,6 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
         float inv[NBLK];
         for (int n = 0; n < NBLK; ++n) inv[n] = 1.f / (s->scales16[n] * S16_HK);
-        if (b0_pieces && unswap) {   // default: frames on the M side, 16-byte stores of complete operand rows
-            maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
-            k_kc_gemm_tc2<true, 16, true, true><<<2 * clusters, 64 + 32 * 16, KC2U_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
-                                                                          s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], 0, sat);
-        } else
         if (b0_pieces) {
             maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
             k_kc_gemm_tc2<true, 16, true><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],

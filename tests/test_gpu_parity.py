@@ -403,10 +403,19 @@ def test_full_schedule_n1000_vs_oracle(synth, cuda_lib):
         if i % 10 == 9:
             err = (got[i + 1] - x).abs().max().item()
             assert err < 5e-4, (i, err)
-    for i in list(range(100, 1000, 100)) + [998, 999]:      # teacher-forced single steps across the rest of the schedule
+    # teacher-forced single steps across the rest of the schedule.  The random-init network is no denoiser: |x| grows without bound over
+    # the loop (measured ~200 at step 300, ~1400 at step 400), so the bound is relative -- and once 16 |activation| passes the fp16 range the
+    # default mode's pieces saturate: from there on the RANGE GUARD must have fired instead (fd_check_saturation), which is what a user sees.
+    left_range = False
+    for i in list(range(100, 1000, 100)) + [998, 999]:
+        scale = max(1.0, got[i].abs().max().item())
+        if scale > 250.0:
+            left_range = True
+            continue
         err = (got[i + 1] - oracle_step(got[i], i)).abs().max().item()
-        scale = max(1.0, got[i].abs().max().item())        # the random-init network lets |x| grow to ~200 over the loop: the bound is relative
         assert err < 5e-5 * scale, (i, err, scale)
+    if left_range:
+        assert net.engine().check_saturation(), "activations left the fp16-piece range but the saturation flag was not raised"
     assert torch.isfinite(got[-1]).all()
 
 
