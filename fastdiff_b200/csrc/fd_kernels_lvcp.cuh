@@ -50,7 +50,7 @@ __host__ __device__ inline size_t lp_row_of(int b, int T, int t) { return (size_
 template <int HOP> __host__ __device__ constexpr int lp_nf() { return HOP >= LP_TT ? 1 : LP_TT / HOP; }
 constexpr int LP_SKA_BYTES = 16384;              // hop 256: audio im2col tile of the skip MMA, 128 rows x 128 B (64 B used)
 constexpr int LP_SKB_BYTES = 4096;               // hop 256: first_audio_conv pieces (FIRST_F16), 32 rows x 128 B
-constexpr float LP_S_AU = 256.f;                 // prescale of the audio pieces (|audio| < 255 before saturation)
+constexpr float LP_S_AU = 16.f;                  // prescale of the audio pieces: the same range as the activations (|audio| < 4094 before saturation)
 template <int HOP> __host__ __device__ constexpr int lp_smem_bytes() {
     return LP_NA * LP_STAGE_BYTES + 2 * LP_Y_BYTES + 2 * lp_nf<HOP>() * 24576 + (HOP == 256 ? 2 * LP_OUT_BYTES + LP_SKA_BYTES + LP_SKB_BYTES : 0) +
            LP_CW_BYTES + C * 4 + 512 + 24 * 8 + 64 + 1024;

@@ -56,6 +56,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait: a protocol bug traps instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
+#pragma unroll 1   // (ptxas otherwise unrolls the poll 32 times at every wait site: ~70 of the 357 instructions of k_lvc_p's gate loop, I-cache misses)
     for (uint32_t it = 0; it < (1u << 22); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"

@@ -1,7 +1,7 @@
 #!/bin/bash
-# Round-2 call 4: k_lvc_p v3 (8 conv-epilogue warps), un-swapped kernel_conv GEMM, graph replay on an internal capture stream.
+# Round-2 call 5: k_lvc_p with the critical-path roles on the high warp ids, bounded-poll loops not unrolled; sweep tool (1 GPU).
 set -u
-OUT=gpurun_out/r2_c4
+OUT=gpurun_out/r2_c5
 mkdir -p "$OUT"
 
 timeout 300 python tests/gpu_lvcp_check.py > "$OUT/lvcp_check.log" 2>&1; echo "rc=$?" >> "$OUT/lvcp_check.log"
@@ -15,7 +15,7 @@ timeout 150 $B --no-cpu --batch 1 --frames 86 --opt graphs=0 > "$OUT/bench_1x86_
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference.json" 2> "$OUT/bench_reference.err"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file "$OUT/launches.csv" python bench.py --steps 1 --warmup 1 --no-cpu --opt graphs=0 > "$OUT/ncu_list.log" 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_lvc_p -s 12 -c 2 -o "$OUT/lvcp" python bench.py --steps 1 --warmup 1 --no-cpu --opt graphs=0 > "$OUT/ncu_full.log" 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_kc_gemm -s 4 -c 1 -o "$OUT/gemm" python bench.py --steps 1 --warmup 1 --no-cpu --opt graphs=0 > "$OUT/ncu_gemm.log" 2>&1
+timeout 400 python tools/sweep.py --no-n1000 > "$OUT/sweep_1gpu.md" 2> "$OUT/sweep_1gpu.err"
 grep -h '"value"' "$OUT"/bench_*.json | python -c "
 import sys, json
 for l in sys.stdin:
