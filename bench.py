@@ -321,6 +321,9 @@ def run_ours(args):
 
     # ---- timed region 1b: the same K calls with two CUDA events around EVERY kernel launch (on its own stream): per-kernel durations for the
     #      roofline.  Event recording forces plain launches (no graph replay), so this loop is a little slower than region 1.
+    eng.set_option("overlap", 0)   # serial order: every class is timed alone (with the side stream on, the DBlock chain shares the SMs with embed / KP / GEMM)
+    for i in range(2):
+        one_call(i)
     eng.timing_enable(True)
     eng.timing_report()
     evi0, evi1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -337,6 +340,7 @@ def run_ours(args):
     ms_instr = evi0.elapsed_time(evi1) / args.steps
     per_kernel = eng.timing_report()
     eng.timing_enable(False)
+    eng.set_option("overlap", 1)
     saturated = eng.check_saturation()
 
     # ---- timed region 2: e2e, host buffers (H2D of the mels, D2H of the waveform inside) ------------------------------------
@@ -421,11 +425,14 @@ def run_ours(args):
     roofline = None
     frames = B * Tm
     samples = B * L
-    flop_table = {
+    n_rev = 4 * args.steps                                            # reverse steps inside the instrumented loop
+    lvc_flop = 2.0 * 96 * 32 + 2.0 * 96 * 64                          # dilated conv + LVC per sample and layer
+    flop_per_rev_step = {                                             # algorithmic FLOPs of a class per reverse step (SURVEY 8(d) breakdown)
         "kc_gemm": KC_FLOP_PER_FRAME * frames * 3,                    # one launch covers the 3 LVC blocks
-        "lvc_layer_b2": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples,     # dilated conv + LVC at full rate
-        "lvc_layer_b1": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 4,
-        "lvc_layer_b0": (2.0 * 96 * 32 + 2.0 * 96 * 64) * samples / 32,
+        "lvc_layer_b2": 4 * lvc_flop * samples, "lvc_layer_b1": 4 * lvc_flop * samples / 4, "lvc_layer_b0": 4 * lvc_flop * samples / 32,
+        "dblock": 7880.0 * samples, "upsample": 5248.0 * samples, "final_update": 448.0 * samples,
+        "kp_hidden": (114072.0 - 110592.0 - 1152.0) * samples,       # kernel predictor minus kernel_conv / bias_conv
+        "embed": 0.9e6 * B,
     }
     traffic_tab = {}
     try:
@@ -433,10 +440,16 @@ def run_ours(args):
             traffic_tab = json.load(f)
     except Exception:
         pass
-    if dom and dom in flop_table:
+    class_roofline = {}
+    for k, v in per_kernel.items():
+        if k in flop_per_rev_step and v["ms"] > 0:
+            a = flop_per_rev_step[k] * n_rev / (v["ms"] * 1e-3) / 1e12
+            class_roofline[k] = {"tflops": a, "frac": a / peaks["tensor"], "launches_per_reverse_step": v["n"] / n_rev,
+                                 "ms_per_reverse_step": v["ms"] / n_rev}
+    if dom and dom in flop_per_rev_step:
         n_dom = per_kernel[dom]["n"]
         avg_ms = per_kernel[dom]["ms"] / n_dom
-        flop_per_launch = flop_table[dom]
+        flop_per_launch = flop_per_rev_step[dom] * n_rev / n_dom
         ach = flop_per_launch / (avg_ms * 1e-3) / 1e12
         tr = traffic_tab.get(dom) if (B, Tm) == (8, 861) else None
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peaks["tensor"], "unit": "TFLOP/s",
@@ -448,6 +461,7 @@ def run_ours(args):
                     "peak_source": peaks["src"] + " bf16_tflops_sustained (of measured)",
                     "avg_launch_ms": avg_ms, "launches": n_dom, "share_of_step": per_kernel[dom]["ms"] / (ms_instr * args.steps),
                     "algorithmic_flop_per_launch": flop_per_launch, "mode": mode_name,
+                    "timed": "CUDA events around every launch of the class on its own stream, serial kernel order (side stream off), inside bench.py",
                     "note": "fp32-level mode: every algorithmic FLOP costs 3 fp16 MMAs, so this kernel's own tensor ceiling is 1/3 of the bf16 peak"}
     step_alg_bytes = samples * 12 + frames * 320 + 61e6   # x in/out + z per sample, mel, folded fp32 weights once per reverse step
     whole = {"achieved_tflops": FLOP_PER_SAMPLE_STEP * 4 * GB * L / (ms_per_step * 1e-3) / 1e12,
@@ -479,14 +493,15 @@ def run_ours(args):
                     "random-init weights", "global_batch": GB, "frames_per_utterance": Tm}),
         "arith_mode": mode_name, "noise": "on-device Philox4x32-10 (inside the timed region)", "fp16_piece_saturation": bool(saturated),
         "api": "fastdiff_b200.shard.ShardedFastDiff.sample",
-        "clocks": clk, "e2e": e2e, "e2e_reference_noise": e2e_ref_noise, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clk, "e2e": e2e, "e2e_reference_noise": e2e_ref_noise, "gpu_launches": int(launches), "roofline": roofline, "class_roofline": class_roofline,
+        "cpu_baseline": cpu_baseline,
         "load": {"seconds_incl_pack": load_s, "blob_bytes": sh.blob_bytes, "broadcasts": 1 if world > 1 else 0},
         **({"experiment": {"options": args.opt, "nvcc_extra": os.environ.get("FD_NVCC_EXTRA", "")}} if (args.opt or os.environ.get("FD_NVCC_EXTRA")) else {}),
         "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in per_kernel.items()},
         "ms_per_step_instrumented": ms_instr,
-        "kernel_ms_note": "second timed loop of the same K calls with CUDA events around every launch on its own stream (plain launches; `value` comes "
-                          "from the first loop, which replays the library's CUDA graph); the DBlock chain runs on a side stream concurrently with embed / "
-                          "kernel predictor / GEMM, so those classes include time spent sharing the SMs and the classes sum to more than ms_per_step",
+        "kernel_ms_note": "second timed loop of the same K calls with CUDA events around every launch (plain launches in serial order, side stream off, so "
+                          "every class is timed alone; `value` comes from the first loop, which replays the library's CUDA graph with the DBlock chain "
+                          "overlapping embed / kernel predictor / GEMM on the side stream)",
         "whole_step": whole,
         "limiter": ("per-step: LVC layers of blocks 1/2 (SIMT epilogues + HBM rows), then the kernel_conv GEMM's 2 GB store stream; "
                     "across GPUs: nothing collective in the loop -- the residual is max-over-ranks under sw_power_cap"),

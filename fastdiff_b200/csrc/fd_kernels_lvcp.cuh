@@ -56,6 +56,20 @@ template <int HOP> __host__ __device__ constexpr int lp_smem_bytes() {
            LP_CW_BYTES + C * 4 + 512 + 24 * 8 + 64 + 1024;
 }
 
+// Optional role timeline (-DLP_TIMELINE=1, GPU build only): CTA 0 of the block-2 launch with dilation LP_TL_DIL stamps clock64 at the
+// protocol points of its first 24 tiles -- [role 0 loader | 1 MMA issuer | 2 conv epilogue (warp 16) | 3 gate epilogue (warp 0)][tile][8 slots];
+// read with fd_debug_read("lp_timeline") (tests/gpu_lp_timeline.py).
+#if defined(LP_TIMELINE) && !defined(FD_EMU)
+#ifndef LP_TL_DIL
+#define LP_TL_DIL 9
+#endif
+constexpr int LP_TL_TILES = 24;
+__device__ unsigned long long g_lp_timeline[4 * LP_TL_TILES * 8];
+#define LP_STAMP(role, tile, slot) do { if (tl_on && (tile) < LP_TL_TILES && (tile) >= 0) g_lp_timeline[((role) * LP_TL_TILES + (tile)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define LP_STAMP(role, tile, slot) do { } while (0)
+#endif
+
 struct LvcPParams {
     const float* cw16;       // [3 taps][32 co][128 B] SWIZZLE_128B image of this layer's dilated conv (LBn_CONV_F16)
     const float* conv_b;     // [32]
@@ -157,6 +171,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     // (b, tt) of the walk's first tile; every role then steps them down itself (no per-tile division)
     const int b_first = ntile ? (tile_hi - 1) / ntt : 0, tt_first = ntile ? (tile_hi - 1) % ntt : 0;
     const bool has_skip = (p.p_out != nullptr);   // the skip of the NEXT layer's "x += audio_down" is added to the rows this layer produces
+#if defined(LP_TIMELINE) && !defined(FD_EMU)
+    const bool tl_on = (HOP == 256) && blockIdx.x == 0 && p.dil == LP_TL_DIL;
+#endif
 
     if (warp_u == 24) {
         // =========================================== loader ===========================================
@@ -168,7 +185,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 unsigned char* a = a_st + s * LP_STAGE_BYTES;
                 float* lbias = (float*)(a + 24576);
                 float* au = lbias + 128;
+                LP_STAMP(0, n, 0);
                 mbar_wait(&a_free[s], (uint32_t)((sn & 1) ^ 1));
+                LP_STAMP(0, n, 1);
                 const int ar0 = 31 - dil, nrows = 130 + 2 * dil;
                 int i0 = 0, i1 = 0;
                 if (SKIP_MMA && has_skip) { i0 = t0 == 0 ? 4 : 0; i1 = min(LP_AU, T - t0 + 4); }
@@ -203,6 +222,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                     for (int fi = 0; fi < NF; ++fi)
                         if (f0 + fi < Tm) bulk_g2s(w_t + ws * W_BYTES + fi * 24576, p.kern + ((size_t)b * Tm + f0 + fi) * KCN, 24576u, &w_full[ws]);
                 }
+                LP_STAMP(0, n, 2);
                 if (--tt < 0) { tt = ntt - 1; --b; new_frame = true; }
                 if (++s == LP_NA) { s = 0; ++sn; }
             }
@@ -218,7 +238,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
         auto lvc_mmas = [&](int m) {     // M2(m): LVC (+ skip) MMAs of the CTA's m-th tile
             const int t0 = mb_tt * LP_TT, f0 = t0 / HOP;
             const int ys = m & 1;
+            LP_STAMP(1, m, 3);
             mbar_wait(&y_full[ys], (uint32_t)((m >> 1) & 1));
+            LP_STAMP(1, m, 4);
             bool last_use = true;
             if (HOP == 256) {
                 if (m_new_frame) {
@@ -233,6 +255,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 mbar_wait(&w_full[cur_ws], (uint32_t)((m >> 1) & 1));
             }
             mbar_wait(&lacc_free[ys], (uint32_t)(((m >> 1) & 1) ^ 1));
+            LP_STAMP(1, m, 5);
             tc_fence_after();
             uint32_t yt = y_u + (uint32_t)ys * LP_Y_BYTES, wt = w_u + (uint32_t)cur_ws * W_BYTES;
             FD_OPAQUE2(yt, wt);
@@ -269,14 +292,17 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 if (last_use) tc_commit(&w_free[cur_ws]);
             }
             __syncwarp();
+            LP_STAMP(1, m, 6);
             if (--mb_tt < 0) { mb_tt = ntt - 1; m_new_frame = true; }
         };
         int tt = tt_first, s = 0, sn = 0;
         for (int n = 0; n < ntile; ++n) {
             const int cs = n & 1;
             const bool have_carry = (n > 0) && (tt != ntt - 1);
+            LP_STAMP(1, n, 0);
             mbar_wait(&a_full[s], (uint32_t)(sn & 1));
             mbar_wait(&cacc_free[cs], (uint32_t)(((n >> 1) & 1) ^ 1));
+            LP_STAMP(1, n, 1);
             tc_fence_after();
             uint32_t at = a_u + (uint32_t)s * LP_STAGE_BYTES, cwt = cw_u;
             FD_OPAQUE2(at, cwt);
@@ -302,6 +328,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 tc_commit(&cacc_full[cs]);
             }
             __syncwarp();
+            LP_STAMP(1, n, 2);
             if (n >= 1) lvc_mmas(n - 1);
             if (--tt < 0) tt = ntt - 1;
             if (++s == LP_NA) { s = 0; ++sn; }
@@ -322,12 +349,15 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             unsigned char* a = a_st + s * LP_STAGE_BYTES;
             float* lbias = (float*)(a + 24576);
             float* au = lbias + 128;
+            if (warp == 16 && lane == 0) LP_STAMP(2, n, 0);
             mbar_wait(&cacc_full[cs], (uint32_t)((n >> 1) & 1));
+            if (warp == 16 && lane == 0) LP_STAMP(2, n, 1);
             tc_fence_after();
             uint32_t v[16];
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cs * 32 + part * 16, v);
             tmem_ld_wait();
             if (n >= 2) mbar_wait(&lacc_full[cs], (uint32_t)(((n >> 1) - 1) & 1));   // the LVC MMAs of tile n-2 have read this Y tile
+            if (warp == 16 && lane == 0) LP_STAMP(2, n, 2);
             // 16 accumulator columns of row `row` -> 16 lrelu(acc * inv + b) -> pieces: logical chunks 2 part, 2 part + 1 (hi) and 4 + ... (lo)
             auto emit_row = [&](const uint32_t (&acc)[16], int row, unsigned char* copy_to) {
                 const int t = t0 - 1 + row;
@@ -368,8 +398,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&cacc_free[cs]);   // both accumulators of this stage have been read
+            if (warp == 16 && lane == 0) LP_STAMP(2, n, 3);
             // ---- work taken off the gate epilogue's hands: LVC bias prescaled by the gate's exponent constants (part 1); skip operand tile (part 0) ----
             mbar_wait(&a_full[s], (uint32_t)(sn & 1));
+            if (warp == 16 && lane == 0) LP_STAMP(2, n, 4);
             if (part == 1) {
                 if (yr < NF * 64) lbias[yr] *= ((yr & 63) < 32) ? -1.4426950408889634f : -2.8853900817779268f;   // sigmoid half: e^-a; tanh half: e^-2b
             } else if (SKIP_MMA && has_skip) {
@@ -391,6 +423,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&y_full[cs]);
+            if (warp == 16 && lane == 0) LP_STAMP(2, n, 5);
             if (--tt < 0) tt = ntt - 1;
             if (++s == LP_NA) { s = 0; ++sn; }
         }
@@ -410,7 +443,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             const int ls = n & 1, t = t0 + r;
             const unsigned char* a = a_st + s * LP_STAGE_BYTES;
             const float* lbias = (const float*)(a + 24576);
+            if (warp == 0 && lane == 0) LP_STAMP(3, n, 0);
             mbar_wait(&a_full[s], (uint32_t)(sn & 1));
+            if (warp == 0 && lane == 0) LP_STAMP(3, n, 1);
             float sk[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) sk[c] = 0.f;
@@ -434,7 +469,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                     z[2 * c + 1] = fminf(v1, 5.f * v1);
                 }
             }
+            if (warp == 0 && lane == 0) LP_STAMP(3, n, 2);
             mbar_wait(&lacc_full[ls], (uint32_t)((n >> 1) & 1));
+            if (warp == 0 && lane == 0) LP_STAMP(3, n, 3);
             tc_fence_after();
             uint32_t zs[8], zt[8], za[8];
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + LACC0 + (uint32_t)ls * LSTRIDE + fi * 64 + j * 8;
@@ -452,6 +489,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&lacc_free[ls]);
+            if (warp == 0 && lane == 0) LP_STAMP(3, n, 4);
             // sigmoid(a) tanh(b) = (1 - E) / ((1 + A)(1 + E)), A = e^-a, E = e^-2b (b clamped at -15: E finite, tanh(-15) = -1 in fp32)
             float xn[8];
 #pragma unroll
@@ -461,6 +499,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 const float rinv = rcp_approx((1.f + A) * (1.f + E));
                 xn[c] = fmaf(fmaf(E, -S16_ACT, S16_ACT), rinv, z[c]);        // 16 (x + gate)
             }
+            if (warp == 0 && lane == 0) LP_STAMP(3, n, 5);
             if (p.f_out) {
                 if (t < T) st_global_f8(p.f_out + ((size_t)b * T + t) * C + j * 8,
                                         make_float4(xn[0] * (1.f / S16_ACT), xn[1] * (1.f / S16_ACT), xn[2] * (1.f / S16_ACT), xn[3] * (1.f / S16_ACT)),
@@ -495,6 +534,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_free[s]);
+            if (warp == 0 && lane == 0) LP_STAMP(3, n, 6);
             if (--tt < 0) { tt = ntt - 1; --b; }
             if (++s == LP_NA) { s = 0; ++sn; }
         }

@@ -54,15 +54,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug traps instead of hanging the GPU box.
+// MBAR_HINT_NS > 0: try_wait carries a suspend-time hint, so a waiting warp sleeps in hardware up to that long per poll instead of
+// re-issuing the poll loop every ~100 cycles (ncu, round 2: a third of k_lvc_p's issued instructions were polls).
+#ifndef MBAR_HINT_NS
+#define MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
 #pragma unroll 1   // (ptxas otherwise unrolls the poll 32 times at every wait site: ~70 of the 357 instructions of k_lvc_p's gate loop, I-cache misses)
     for (uint32_t it = 0; it < (1u << 22); ++it) {
+#if MBAR_HINT_NS > 0
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)MBAR_HINT_NS) : "memory");
+#else
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
         if (done) return;
     }
     __trap();
