@@ -32,6 +32,7 @@ struct fd_handle {
     int emu_gemm_tc = 1;         // emulation build, mode tc_3xf16: 1 = the CTA-pair GEMM on the tcgen05 model, 0 = FFMA GEMM + k_emu_kern_to_pieces
     int emb_slots = EMB_SLOTS;   // reverse steps whose embeddings one k_embed launch computes (option "emb_slots", 1..64; tests use small values)
     int tc_b0 = 1;               // mode tc_3xf16: LVC block 0 on tensor cores (k_lvc_layer_b0h, its kernels written as fp16 pieces by the GEMM; option "tc_b0", 0 = SIMT k_lvc_layer<8>)
+    int kimg_last = 0;           // the last run_denoiser wrote blocks 1, 2 in the merged-N image (fd_debug_read "kernels1/2")
     int b0_converted = 0;        // the last run_denoiser rewrote block 0's predicted kernels as fp16 pieces (fd_debug_read "kernels0")
     int b0_prefetch = 0;         // SIMT LVC kernel (block 0): bulk L2 prefetch of each warp's predicted kernels (option "b0_prefetch")
     int noise_draw_base = 0;     // device-noise mode: Philox draw number of a call's first noisy step minus one (option "noise_draw_base": callers that run
@@ -456,6 +457,34 @@ __global__ void __launch_bounds__(256) k_emu_kern_to_pieces(float* __restrict__ 
         out[(((4 + (i >> 3)) ^ (o & 7)) << 3) + (i & 7)] = lo;
     }
 }
+// merged-N image (layout in k_kc_gemm_tc2, exp_mask bit 64), one thread per (frame, layer): reads the layer's 192 fp32 rows first, then writes the
+// piece tiles T01 / T2 over the same 24,576 bytes (an independent statement of the layout the GPU epilogue writes)
+__global__ void __launch_bounds__(64) k_emu_kern_to_pieces_m(float* __restrict__ kern, size_t n_layers) {
+    const size_t r = (size_t)blockIdx.x * 64 + threadIdx.x;   // (frame * LAYERS + l)
+    if (r >= n_layers) return;
+    const size_t frame = r / LAYERS;
+    const int l = (int)(r % LAYERS);
+    float* lp = kern + frame * KCN + (size_t)l * KPL;
+    static thread_local float w[3][64][32];
+    for (int k = 0; k < 3; ++k)
+        for (int o = 0; o < 64; ++o)
+            for (int i = 0; i < 32; ++i) w[k][o][i] = lp[(k * 64 + o) * 32 + (((i >> 2) ^ (o & 7)) << 2) + (i & 3)];
+    uint16_t* out = reinterpret_cast<uint16_t*>(lp);
+    for (int k = 0; k < 3; ++k)
+        for (int o = 0; o < 64; ++o)
+            for (int i = 0; i < 32; ++i) {
+                uint16_t hi, lo;
+                f16_split(w[k][o][i], S16_KERN, hi, lo);
+                if (k < 2) {
+                    const int pos = ((((k << 2) + (i >> 3)) ^ (o & 7)) << 3) + (i & 7);
+                    out[o * 64 + pos] = hi;
+                    out[(64 + o) * 64 + pos] = lo;
+                } else {
+                    out[8192 + o * 64 + (((i >> 3) ^ (o & 7)) << 3) + (i & 7)] = hi;
+                    out[8192 + o * 64 + (((4 + (i >> 3)) ^ (o & 7)) << 3) + (i & 7)] = lo;
+                }
+            }
+}
 
 static float emu_scale16(const fd_handle* h, int idx) { return h->blob[h->sec_off[FD_S_SCALES16] + idx]; }
 
@@ -493,7 +522,7 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
 }
 
 // The CTA-pair kernel_conv GEMM (k_kc_gemm_tc2<true, 16>: 2-SM TMA, cta_group::2 MMA, multicast commit, remote arrives) on the model.
-static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st, int b0_pieces) {
+static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st, int b0_pieces, int kimg) {
     KcgMaps maps;
     const uint64_t rows = (uint64_t)B * (Tm + 2);
     float inv[NBLK];
@@ -511,11 +540,11 @@ static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo,
     if (b0_pieces) {
         auto k = k_kc_gemm_tc2<true, 16, true>;
         FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], kimg ? 64 : 0);
     } else {
         auto k = k_kc_gemm_tc2<true, 16>;
         FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
-                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], 0);
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], kimg ? 64 : 0);
     }
     FD_CHECK_LAUNCH(h, "k_kc_gemm_tc2");
     return FD_OK;
@@ -581,7 +610,7 @@ static int emu_upsample_p(fd_handle* h, int blk, const float* in, const float* s
 static int emu_lvc_p_layer(fd_handle* h, int blk, int layer, const float* p_in, const float* skip, const float* kern, float* p_out, float* f_out,
                            int B, int T, int Tm, int dil, cudaStream_t st) {
     LvcPParams p;
-    p.cw16 = sec(h, blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16) + (size_t)layer * (LP_CW_BYTES / 4);
+    p.cw16 = sec(h, blk == 1 ? FD_S_LB1_CONV_F16M : FD_S_LB2_CONV_F16M) + (size_t)layer * (LP_CW_BYTES / 4);
     p.conv_b = sec(h, FD_S_LB0_CONV_B + blk * FD_LB_STRIDE) + layer * C;
     p.first16 = sec(h, FD_S_FIRST_F16);
     p.p_in = p_in; p.skip = skip; p.kern = kern; p.p_out = p_out; p.f_out = f_out; p.sat = h->sat_flag;
@@ -712,10 +741,13 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     // LVC block 0 on tensor cores (mode tc_3xf16, option tc_b0): the GEMM writes the block's kernels as fp16 pieces itself
     const bool b0_tc = h->tc_b0 && h->mode == FD_MODE_TC_3XF16 && !simt_gemm;
     const bool b0_gemm_pieces = b0_tc;
+    // blocks 1, 2 consumed by k_lvc_p: the GEMM writes their predicted kernels in the merged-N (SWIZZLE_64B, piece-major) operand image
+    const int kimg = (h->mode == FD_MODE_TC_3XF16 && h->lvc_p && h->tc_upsample) ? 1 : 0;
+    h->kimg_last = kimg;
 #ifdef FD_EMU
     if (!simt_gemm) {
         ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = emu_kc_gemm_tc2(h, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, b0_gemm_pieces ? 1 : 0);
+        int rc = emu_kc_gemm_tc2(h, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, b0_gemm_pieces ? 1 : 0, kimg);
         if (rc) return rc;
     }
 #endif
@@ -729,14 +761,19 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
 #ifdef FD_EMU
         if (h->mode == FD_MODE_TC_3XF16) {   // blocks 1, 2: fp32 image -> fp16-piece image (see k_emu_kern_to_pieces)
             const size_t n_rows = (size_t)2 * B * Tm * LAYERS * 3 * 64;
-            FD_LAUNCH(k_emu_kern_to_pieces, dim3((unsigned)((n_rows + 255) / 256)), dim3(256), 0, st, kern + (size_t)B * Tm * KCN, n_rows);
+            if (kimg) {   // merged-N image of k_lvc_p
+                const size_t n_layers = (size_t)2 * B * Tm * LAYERS;
+                FD_LAUNCH(k_emu_kern_to_pieces_m, dim3((unsigned)((n_layers + 63) / 64)), dim3(64), 0, st, kern + (size_t)B * Tm * KCN, n_layers);
+            } else {
+                FD_LAUNCH(k_emu_kern_to_pieces, dim3((unsigned)((n_rows + 255) / 256)), dim3(256), 0, st, kern + (size_t)B * Tm * KCN, n_rows);
+            }
             FD_CHECK_LAUNCH(h, "k_emu_kern_to_pieces");
         }
 #endif
     } else {
 #ifndef FD_EMU
         ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0);
+        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0, kimg);
         if (rc) return rc;
 #endif
     }
@@ -1142,7 +1179,7 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         *count = want_bias ? (size_t)B * LAYERS * LVC_OUT * Tm : (size_t)B * LAYERS * C * LVC_OUT * KS * Tm;
         if (!out_dev) return FD_OK;
         FD_LAUNCH(k_kern_to_ref, dim3((unsigned)((*count + 255) / 256)), dim3(256), 0, st, ws + w.kern + (size_t)n * B * Tm * KCN, out_dev, B, Tm, want_bias,
-                  n == 0 ? (h->b0_converted > 0 ? 2 : 1) : (h->mode == FD_MODE_TC_3XF16 ? 2 : 0));
+                  n == 0 ? (h->b0_converted > 0 ? 2 : 1) : (h->mode == FD_MODE_TC_3XF16 ? (h->kimg_last ? 3 : 2) : 0));
         FD_CHECK_LAUNCH(h, "k_kern_to_ref");
         return FD_OK;
     }

@@ -47,6 +47,10 @@
  *             tensor-core block-0 LVC kernel (option tc_b0)
  *   LBn_CONV_F16 (n = 0, 1, 2; n = 0 is used by the experimental tensor-core block-0 LVC kernel only) [4 layers][3 k][32 co] rows of 128 B = [32 ci hi | 32 ci lo] fp16, the 16-byte chunk c (8 values) of
  *             row co stored at chunk position c ^ (co & 7): SWIZZLE_128B K-major B-operand tiles of the dilated convs
+ *   LBn_CONV_F16M (n = 1, 2; k_lvc_p, merged-N form) [4 layers][12 KB], SWIZZLE_128B K-major B-operand tiles:
+ *             T01 [64 rows x 128 B]: row R = piece * 32 + co = [tap 0: 32 ci | tap 1: 32 ci] of that piece (hi rows, then lo rows), chunk c at c ^ (R & 7):
+ *                 ONE N = 64 MMA per activation piece and K-slice forms the hi- and the lo-weight products of taps 0 and 1;
+ *             T2  [32 rows x 128 B]: row co = [32 ci hi | 32 ci lo] of tap 2, chunk c at c ^ (co & 7) (three-pass form)
  *   LBn_KPW_F16 [28 slots][16 KB]  kernel-predictor hidden stack as B-operand tiles in consumption order (tensor-core k_kp_hidden_tc):
  *             a tile = 64 rows (co) x 128 B, 16-byte chunk c at position c ^ (co & 7).
  *             slots 0..9  : input_conv taps j = 0..4, two slots per tap: {ci 0..63: hi tile 8 KB | lo tile 8 KB},
@@ -61,7 +65,7 @@
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 13ULL
+#define FD_BLOB_VERSION 14ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */
@@ -80,7 +84,7 @@
     X(DB0_CONVT_HI) X(DB0_CONVT_LO) X(DB0_REST_HI) X(DB0_REST_LO) \
     X(LB1_UPT_HI) X(LB1_UPT_LO) X(LB2_UPT_HI) X(LB2_UPT_LO) \
     X(LB0_KCT_F16) X(LB1_KCT_F16) X(LB2_KCT_F16) X(LB1_CONV_F16) X(LB2_CONV_F16) \
-    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(LB0_CONV_F16) X(LB0_KCT_F16P) X(LB0_KC_BP) X(FIRST_F16) X(SCALES16)
+    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(LB0_CONV_F16) X(LB0_KCT_F16P) X(LB0_KC_BP) X(FIRST_F16) X(LB1_CONV_F16M) X(LB2_CONV_F16M) X(SCALES16)
 /* FD_SECTIONS_END */
 
 enum fd_section {

@@ -150,15 +150,16 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
             uint32_t at = smem_u, cwt = smem_u32(cw);
             FD_OPAQUE2(at, cwt);
             if (elect_one()) {
+                const uint32_t a_lo = umma_desc_lo(at), cw_lo = umma_desc_lo(cwt);   // one add per descriptor (offsets in 16-byte units)
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const uint32_t sh = (uint32_t)(pass * 128 + 27 + (k - 1) * dil) * 128u;
+                        const uint32_t sh = (uint32_t)(pass * 128 + 27 + (k - 1) * dil) * 8u;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const uint64_t dah = umma_desc_sw128(at + sh + j * 32), dal = umma_desc_sw128(at + sh + 64 + j * 32);
-                            const uint64_t dbh = umma_desc_sw128(cwt + k * 4096 + j * 32), dbl = umma_desc_sw128(cwt + k * 4096 + 64 + j * 32);
+                            const uint64_t dah = umma_desc_at(a_lo + sh + j * 2), dal = umma_desc_at(a_lo + sh + 4 + j * 2);
+                            const uint64_t dbh = umma_desc_at(cw_lo + k * 256 + j * 2), dbl = umma_desc_at(cw_lo + k * 256 + 4 + j * 2);
                             umma_f16(tmem_u + pass * 32, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
                             umma_f16(tmem_u + pass * 32, dah, dbl, idesc_conv, 1u);
                             umma_f16(tmem_u + pass * 32, dal, dbh, idesc_conv, 1u);
@@ -223,15 +224,15 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
                     const uint32_t rs = lu % LB0_NSLOT;
                     mbar_wait(&ring_full[rs], (lu / LB0_NSLOT) & 1);
                     tc_fence_after();
-                    const uint32_t wt = smem_u32(ring) + rs * LB0_PAIR_BYTES;
+                    const uint32_t w_lo = umma_desc_lo(smem_u32(ring) + rs * LB0_PAIR_BYTES), y_lo = umma_desc_lo(smem_u);
                     const uint32_t d = tmem_u + 64 + pp * 16;
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const uint32_t ysh = (uint32_t)(16 * pp + k) * 128u;
+                        const uint32_t ysh = (uint32_t)(16 * pp + k) * 8u;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const uint64_t dwh = umma_desc_sw128(wt + k * 16384 + j * 32), dwl = umma_desc_sw128(wt + k * 16384 + 64 + j * 32);
-                            const uint64_t dyh = umma_desc_sw128(smem_u + ysh + j * 32), dyl = umma_desc_sw128(smem_u + ysh + 64 + j * 32);
+                            const uint64_t dwh = umma_desc_at(w_lo + k * 1024 + j * 2), dwl = umma_desc_at(w_lo + k * 1024 + 4 + j * 2);
+                            const uint64_t dyh = umma_desc_at(y_lo + ysh + j * 2), dyl = umma_desc_at(y_lo + ysh + 4 + j * 2);
                             umma_f16(d, dwh, dyh, idesc_lvc, (k | j) ? 1u : 0u);
                             umma_f16(d, dwh, dyl, idesc_lvc, 1u);
                             umma_f16(d, dwl, dyh, idesc_lvc, 1u);

@@ -111,7 +111,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     constexpr bool STAGE_OUT = (HOP == 256);
     constexpr bool SKIP_MMA = (HOP == 256);            // skip = first_conv(audio) on the tensor core; hop 64 loads skip rows from memory
     constexpr int W_BYTES = NF * 24576;
-    constexpr uint32_t LACC0 = 128, LSTRIDE = NF * 64, SKACC0 = 384;
+    // TMEM columns: conv accumulators 2 stages x 64 (hi-weight products | lo-weight products) at 0; second conv pass (rows +128, single-buffered,
+    // rare) 64 at 128; skip MMA 2 x 32 at 192; LVC accumulators 2 stages x 128 at 256 (hop 256: hi-kernel | lo-kernel products of the 64
+    // outputs; hop 64: the two frames of the tile, 64 outputs each)
+    constexpr uint32_t C2ACC0 = 128, SKACC0 = 192, LACC0 = 256, LSTRIDE = 128;
     constexpr uint32_t TCOLS = 512;
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -186,9 +189,19 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 float* lbias = (float*)(a + 24576);
                 float* au = lbias + 128;
                 LP_STAMP(0, n, 0);
+                const int ar0 = 31 - dil, nrows = 130 + 2 * dil;
+                if (n + 1 < ntile) {   // L2 prefetch of the NEXT tile's rows and kernels: its stage frees up about one tile time from now, and the
+                                       // load latency sits on the critical cycle (stage free -> loads -> conv -> LVC -> gate -> stage free)
+                    const int tt2 = tt > 0 ? tt - 1 : ntt - 1, b2 = tt > 0 ? b : b - 1, t02 = tt2 * LP_TT, f02 = t02 / HOP;
+                    bulk_prefetch_l2(p.p_in + (lp_row_of(b2, T, t02 - 32 + ar0)) * C, (uint32_t)nrows * 128u);
+                    if (HOP != 256 || tt == 0 || !(tt & 1)) {   // hop 256: only when the next tile starts a new frame
+#pragma unroll
+                        for (int fi = 0; fi < NF; ++fi)
+                            if (f02 + fi < Tm) bulk_prefetch_l2(p.kern + ((size_t)b2 * Tm + f02 + fi) * KCN, (uint32_t)(KPL * 4));
+                    }
+                }
                 mbar_wait(&a_free[s], (uint32_t)((sn & 1) ^ 1));
                 LP_STAMP(0, n, 1);
-                const int ar0 = 31 - dil, nrows = 130 + 2 * dil;
                 int i0 = 0, i1 = 0;
                 if (SKIP_MMA && has_skip) { i0 = t0 == 0 ? 4 : 0; i1 = min(LP_AU, T - t0 + 4); }
                 const int f0 = t0 / HOP;
@@ -218,11 +231,16 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
 #pragma unroll
                     for (int fi = 0; fi < NF; ++fi) if (f0 + fi < Tm) wb += 24576u;
                     mbar_expect_tx(&w_full[ws], wb);
+                    // stage = [T01 hi rows f0 | f1 (8 KB each)][T01 lo rows f0 | f1][T2 f0 | f1]: every MMA covers both frames of the tile (N = 128)
 #pragma unroll
                     for (int fi = 0; fi < NF; ++fi)
-                        if (f0 + fi < Tm) bulk_g2s(w_t + ws * W_BYTES + fi * 24576, p.kern + ((size_t)b * Tm + f0 + fi) * KCN, 24576u, &w_full[ws]);
+                        if (f0 + fi < Tm) {
+                            const float* kf = p.kern + ((size_t)b * Tm + f0 + fi) * KCN;
+#pragma unroll
+                            for (int part = 0; part < 3; ++part)
+                                bulk_g2s(w_t + ws * W_BYTES + part * 16384 + fi * 8192, kf + part * 2048, 8192u, &w_full[ws]);
+                        }
                 }
-                LP_STAMP(0, n, 2);
                 if (--tt < 0) { tt = ntt - 1; --b; new_frame = true; }
                 if (++s == LP_NA) { s = 0; ++sn; }
             }
@@ -230,13 +248,12 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
         __syncwarp();
     } else if (warp_u == 25) {
         // =========================================== MMA issuer ===========================================
-        constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 64);
+        constexpr uint32_t idesc_sk = umma_idesc_f16(128, 32), idesc_conv = umma_idesc_f16(128, 64), idesc_lvc = umma_idesc_f16(128, 128), idesc_l64 = umma_idesc_f16(128, 64);
         const uint32_t a_u = smem_u32(a_st), y_u = smem_u32(y_t), w_u = smem_u32(w_t), cw_u = smem_u32(cw);
         const uint32_t ska_u = smem_u32(sk_a), skb_u = smem_u32(sk_b);
         int wc = 0, cur_ws = 0, mb_tt = tt_first;                 // M2 runs one tile behind C: its own tile-in-item counter
         bool m_new_frame = true;
         auto lvc_mmas = [&](int m) {     // M2(m): LVC (+ skip) MMAs of the CTA's m-th tile
-            const int t0 = mb_tt * LP_TT, f0 = t0 / HOP;
             const int ys = m & 1;
             LP_STAMP(1, m, 3);
             mbar_wait(&y_full[ys], (uint32_t)((m >> 1) & 1));
@@ -260,33 +277,50 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             uint32_t yt = y_u + (uint32_t)ys * LP_Y_BYTES, wt = w_u + (uint32_t)cur_ws * W_BYTES;
             FD_OPAQUE2(yt, wt);
             if (elect_one()) {
+                // MERGED-N passes (kernel image: k_kc_gemm_tc2, exp_mask bit 64): taps 0 and 1 share 128-byte B rows [tap 0 | tap 1] with the hi and the
+                // lo kernel pieces as separate ROWS, so one N = 128 MMA per activation piece forms both products (lo x lo rides along); tap 2 keeps
+                // the three-pass form on its [hi | lo] rows.
+                // DESCRIPTORS ARE ONE ADD EACH (umma_desc_lo / umma_desc_at): this single thread's instruction stream is what paces the tensor
+                // pipe -- with descriptors rebuilt from addresses (shift, two masks, or: ~6 dependent uniform ops each) the issue loop of a tile
+                // was ~360 instructions and took ~2,500 cycles whatever the number or shape of its MMAs (round-2 timelines).
+                const uint32_t d = tmem_base + LACC0 + (uint32_t)ys * LSTRIDE;
+                const uint32_t y_lo = umma_desc_lo(yt), w_lo = umma_desc_lo(wt);    // offsets below are in 16-byte units
 #pragma unroll
-                for (int fi = 0; fi < NF; ++fi) {
-                    if (f0 + fi < Tm) {
-                        const uint32_t d = tmem_base + LACC0 + (uint32_t)ys * LSTRIDE + fi * 64;
-                        const uint32_t lwb = wt + fi * 24576;
+                for (int k = 0; k < 3; ++k) {
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) {
-#pragma unroll
-                            for (int j = 0; j < 2; ++j) {
-                                const uint64_t dah = umma_desc_sw128(yt + k * 128 + j * 32), dal = umma_desc_sw128(yt + k * 128 + 64 + j * 32);
-                                const uint64_t dbh = umma_desc_sw128(lwb + k * 8192 + j * 32), dbl = umma_desc_sw128(lwb + k * 8192 + 64 + j * 32);
-                                umma_f16(d, dah, dbh, idesc_lvc, (k | j) ? 1u : 0u);
-                                umma_f16(d, dah, dbl, idesc_lvc, 1u);
-                                umma_f16(d, dal, dbh, idesc_lvc, 1u);
+                    for (int j = 0; j < 2; ++j) {
+                        const uint64_t dah = umma_desc_at(y_lo + k * 8 + j * 2), dal = umma_desc_at(y_lo + k * 8 + 4 + j * 2);
+                        const uint32_t acc = (k | j) ? 1u : 0u;
+                        if (HOP == 256) {
+                            if (k < 2) {   // rows 0..63 K_hi(o), 64..127 K_lo(o): D[:, o] += Y K_hi, D[:, 64 + o] += Y K_lo
+                                const uint64_t db = umma_desc_at(w_lo + k * 4 + j * 2);
+                                umma_f16(d, dah, db, idesc_lvc, acc);
+                                umma_f16(d, dal, db, idesc_lvc, 1u);
+                            } else {       // tap 2: D[:, o] += Y_hi K_hi + Y_hi K_lo + Y_lo K_hi
+                                const uint64_t dbh = umma_desc_at(w_lo + 1024 + j * 2), dbl = umma_desc_at(w_lo + 1024 + 4 + j * 2);
+                                umma_f16(d, dah, dbh, idesc_l64, 1u);
+                                umma_f16(d, dah, dbl, idesc_l64, 1u);
+                                umma_f16(d, dal, dbh, idesc_l64, 1u);
                             }
+                        } else {           // hop 64: rows fi * 64 + o (both frames per MMA) -> D[:, fi * 64 + o], three passes
+                            const uint64_t dbh = umma_desc_at(k < 2 ? w_lo + k * 4 + j * 2 : w_lo + 2048 + j * 2);
+                            const uint64_t dbl = umma_desc_at(k < 2 ? w_lo + 1024 + k * 4 + j * 2 : w_lo + 2048 + 4 + j * 2);
+                            umma_f16(d, dah, dbh, idesc_lvc, acc);
+                            umma_f16(d, dah, dbl, idesc_lvc, 1u);
+                            umma_f16(d, dal, dbh, idesc_lvc, 1u);
                         }
                     }
                 }
                 if (SKIP_MMA && has_skip) {   // skip[128 x 32] = audio im2col [128 x 16] x first conv [16 x 32], three piece passes
                     uint32_t sa = ska_u, sb = skb_u;
                     FD_OPAQUE2(sa, sb);
-                    const uint32_t d = tmem_base + SKACC0 + (uint32_t)ys * 32;
-                    const uint64_t ah = umma_desc_sw128(sa), al = umma_desc_sw128(sa + 32);
-                    const uint64_t bh = umma_desc_sw128(sb), bl = umma_desc_sw128(sb + 32);
-                    umma_f16(d, ah, bh, idesc_conv, 0u);
-                    umma_f16(d, ah, bl, idesc_conv, 1u);
-                    umma_f16(d, al, bh, idesc_conv, 1u);
+                    const uint32_t d2 = tmem_base + SKACC0 + (uint32_t)ys * 32;
+                    const uint32_t sa_lo = umma_desc_lo(sa), sb_lo = umma_desc_lo(sb);
+                    const uint64_t ah = umma_desc_at(sa_lo + ys * 4), al = umma_desc_at(sa_lo + ys * 4 + 2);   // column half ys of the operand tile
+                    const uint64_t bh = umma_desc_at(sb_lo), bl = umma_desc_at(sb_lo + 2);
+                    umma_f16(d2, ah, bh, idesc_sk, 0u);
+                    umma_f16(d2, ah, bl, idesc_sk, 1u);
+                    umma_f16(d2, al, bh, idesc_sk, 1u);
                 }
                 tc_commit(&lacc_full[ys]);
                 if (last_use) tc_commit(&w_free[cur_ws]);
@@ -306,22 +340,31 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             tc_fence_after();
             uint32_t at = a_u + (uint32_t)s * LP_STAGE_BYTES, cwt = cw_u;
             FD_OPAQUE2(at, cwt);
+            // the second pass (rows +128; chunk starts and utterance ends only) has ONE accumulator: the conv epilogue must have read tile n-1's
+            if (!have_carry && n >= 1) mbar_wait(&cacc_free[cs ^ 1], (uint32_t)(((n - 1) >> 1) & 1));
             if (elect_one()) {
+                const uint32_t a_lo = umma_desc_lo(at), cw_lo = umma_desc_lo(cwt);   // offsets in 16-byte units: a 128-byte row = 8
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     // pass 1 (rows +128): its output rows 0, 1 are conv rows 128, 129; the other rows read past the loaded window and are never used
                     if (pass == 1 && have_carry) break;
-                    const uint32_t d = tmem_base + (pass ? 64u : 0u) + (uint32_t)cs * 32;
+                    const uint32_t d = tmem_base + (pass ? C2ACC0 : (uint32_t)cs * 64);
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const uint32_t sh = (uint32_t)(pass * 128 + 31 + (k - 1) * dil) * 128u;
+                        const uint32_t sh = (uint32_t)(pass * 128 + 31 + (k - 1) * dil) * 8u;
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            const uint64_t dah = umma_desc_sw128(at + sh + j * 32), dal = umma_desc_sw128(at + sh + 64 + j * 32);
-                            const uint64_t dbh = umma_desc_sw128(cwt + k * 4096 + j * 32), dbl = umma_desc_sw128(cwt + k * 4096 + 64 + j * 32);
-                            umma_f16(d, dah, dbh, idesc_conv, (k | j) ? 1u : 0u);
-                            umma_f16(d, dah, dbl, idesc_conv, 1u);
-                            umma_f16(d, dal, dbh, idesc_conv, 1u);
+                            const uint64_t dah = umma_desc_at(a_lo + sh + j * 2), dal = umma_desc_at(a_lo + sh + 4 + j * 2);
+                            if (k < 2) {   // merged-N (image LBn_CONV_F16M): rows 0..31 W_hi(co), 32..63 W_lo(co) of [tap 0 | tap 1] -> D[:, co], D[:, 32 + co]
+                                const uint64_t db = umma_desc_at(cw_lo + k * 4 + j * 2);
+                                umma_f16(d, dah, db, idesc_conv, (k | j) ? 1u : 0u);
+                                umma_f16(d, dal, db, idesc_conv, 1u);
+                            } else {       // tap 2, three passes on its [hi | lo] rows -> D[:, co]
+                                const uint64_t dbh = umma_desc_at(cw_lo + 512 + j * 2), dbl = umma_desc_at(cw_lo + 512 + 4 + j * 2);
+                                umma_f16(d, dah, dbh, idesc_sk, 1u);
+                                umma_f16(d, dah, dbl, idesc_sk, 1u);
+                                umma_f16(d, dal, dbh, idesc_sk, 1u);
+                            }
                         }
                     }
                 }
@@ -353,13 +396,14 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             mbar_wait(&cacc_full[cs], (uint32_t)((n >> 1) & 1));
             if (warp == 16 && lane == 0) LP_STAMP(2, n, 1);
             tc_fence_after();
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cs * 32 + part * 16, v);
+            uint32_t v[16], v2[16];   // products with the hi and with the lo pieces of the weights
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cs * 64 + part * 16, v);
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cs * 64 + 32 + part * 16, v2);
             tmem_ld_wait();
             if (n >= 2) mbar_wait(&lacc_full[cs], (uint32_t)(((n >> 1) - 1) & 1));   // the LVC MMAs of tile n-2 have read this Y tile
             if (warp == 16 && lane == 0) LP_STAMP(2, n, 2);
             // 16 accumulator columns of row `row` -> 16 lrelu(acc * inv + b) -> pieces: logical chunks 2 part, 2 part + 1 (hi) and 4 + ... (lo)
-            auto emit_row = [&](const uint32_t (&acc)[16], int row, unsigned char* copy_to) {
+            auto emit_row = [&](const uint32_t (&acc)[16], const uint32_t (&acc2)[16], int row, unsigned char* copy_to) {
                 const int t = t0 - 1 + row;
                 const bool in = (t >= 0 && t < T);
                 const int sw = row & 7;
@@ -368,7 +412,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                     float y[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float x = fmaf(__uint_as_float(acc[cc * 8 + e]), inv_cs, cbs_s[part * 16 + cc * 8 + e]);
+                        const float x = fmaf(__uint_as_float(acc[cc * 8 + e]) + __uint_as_float(acc2[cc * 8 + e]), inv_cs, cbs_s[part * 16 + cc * 8 + e]);
                         y[e] = in ? fmaxf(x, 0.2f * x) : 0.f;
                     }
                     uint4 hi, lo;
@@ -382,7 +426,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                     }
                 }
             };
-            emit_row(v, yr, (q == 0 && lane < 2) ? carry + cs * 256 : nullptr);
+            emit_row(v, v2, yr, (q == 0 && lane < 2) ? carry + cs * 256 : nullptr);
             if (q == 0) {
                 if (have_carry) {   // rows 128, 129 = rows 0, 1 of the previous tile: every warp copies back the four chunks per row it wrote itself
                     if (lane < 8) {
@@ -390,9 +434,10 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                         reinterpret_cast<uint4*>(yt + 128 * 128)[row * 8 + pc] = reinterpret_cast<const uint4*>(carry + (cs ^ 1) * 256)[row * 8 + pc];
                     }
                 } else {            // ... or rows 0, 1 of the second MMA pass (TMEM lanes 0, 1 of its accumulator)
-                    tmem_ld_32x32b_x16(tmem_base + 64u + (uint32_t)cs * 32 + part * 16, v);
+                    tmem_ld_32x32b_x16(tmem_base + C2ACC0 + part * 16, v);
+                    tmem_ld_32x32b_x16(tmem_base + C2ACC0 + 32 + part * 16, v2);
                     tmem_ld_wait();
-                    if (lane < 2) emit_row(v, 128 + lane, nullptr);
+                    if (lane < 2) emit_row(v, v2, 128 + lane, nullptr);
                 }
             }
             tc_fence_before();
@@ -409,7 +454,8 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                     for (int i = yr; i < LP_AU; i += 128) { const int pos = t0 - 4 + i; if (pos < 0 || pos >= T) au[i] = 0.f; }
                     group_sync(2, 128);
                 }
-                if (n >= 1) mbar_wait(&lacc_full[cs ^ 1], (uint32_t)(((n - 1) >> 1) & 1));   // the skip MMAs of tile n-1 have read the operand tile
+                // the operand tile is double-buffered in its two 64-byte column halves (tile n -> half n & 1); the skip MMAs of tile n-2, which read
+                // this half, completed with that tile's LVC MMAs (lacc_full, waited for above before the Y tile was rewritten)
                 float x[8];
 #pragma unroll
                 for (int k = 0; k < 7; ++k) x[k] = au[yr + 1 + k] * LP_S_AU;    // audio position t + k - 3
@@ -417,8 +463,8 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 uint4 hi, lo;
                 lp_split8(x, hi, lo, vmax);
                 const int sw = yr & 7;
-                *reinterpret_cast<uint4*>(sk_a + yr * 128 + ((0 ^ sw) << 4)) = hi;
-                *reinterpret_cast<uint4*>(sk_a + yr * 128 + ((2 ^ sw) << 4)) = lo;
+                *reinterpret_cast<uint4*>(sk_a + yr * 128 + (((cs * 4 + 0) ^ sw) << 4)) = hi;
+                *reinterpret_cast<uint4*>(sk_a + yr * 128 + (((cs * 4 + 2) ^ sw) << 4)) = lo;
             }
             fence_async_smem();
             __syncwarp();
@@ -477,6 +523,17 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + LACC0 + (uint32_t)ls * LSTRIDE + fi * 64 + j * 8;
             tmem_ld_32x32b_x8(ta, zs);
             tmem_ld_32x32b_x8(ta + 32, zt);
+            if (HOP == 256) {   // merged-N: columns 64.. hold the products with the lo pieces of the kernels
+                uint32_t zs2[8], zt2[8];
+                tmem_ld_32x32b_x8(ta + 64, zs2);
+                tmem_ld_32x32b_x8(ta + 96, zt2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    zs[c] = __float_as_uint(__uint_as_float(zs[c]) + __uint_as_float(zs2[c]));
+                    zt[c] = __float_as_uint(__uint_as_float(zt[c]) + __uint_as_float(zt2[c]));
+                }
+            }
             if (SKIP_MMA && has_skip) tmem_ld_32x32b_x8(tmem_base + ((uint32_t)(q * 32) << 16) + SKACC0 + (uint32_t)ls * 32 + j * 8, za);
             float lb[16];   // prescaled by the conv epilogue: sigmoid half x -log2(e), tanh half x -2 log2(e)
             {

@@ -948,6 +948,20 @@ __global__ void __launch_bounds__(256) k_kern_to_ref(const float* __restrict__ k
         const int ci = (int)(q % C); q /= C;
         const int l = (int)(q % LAYERS); q /= LAYERS;
         const int b = (int)q;
+        if (panel == 3) {   // merged-N piece image (k_lvc_p; layout in k_kc_gemm_tc2): T01 rows (piece, o) x [tap 0 | tap 1], T2 rows o x [hi | lo] of tap 2
+            const uint16_t* lp = reinterpret_cast<const uint16_t*>(kern + ((size_t)b * Tm + f) * KCN + l * KPL);
+            float hi, lo;
+            if (k < 2) {
+                const int pos = ((((k << 2) + (ci >> 3)) ^ (o & 7)) << 3) + (ci & 7);
+                hi = f16_bits_to_float(lp[o * 64 + pos]); lo = f16_bits_to_float(lp[(64 + o) * 64 + pos]);
+            } else {
+                const uint16_t* rowp = lp + 8192 + o * 64;
+                hi = f16_bits_to_float(rowp[(((ci >> 3) ^ (o & 7)) << 3) + (ci & 7)]);
+                lo = f16_bits_to_float(rowp[(((4 + (ci >> 3)) ^ (o & 7)) << 3) + (ci & 7)]);
+            }
+            out[i] = (hi + lo) * (1.f / S16_KERN);
+            return;
+        }
         if (panel == 2) {   // fp16 pieces of w*S16_KERN: row (k,o) = [32 i hi | 32 i lo], chunk c (8 values) at position c ^ (o & 7)
             const uint16_t* rowp = reinterpret_cast<const uint16_t*>(kern + ((size_t)b * Tm + f) * KCN + l * KPL) + (k * LVC_OUT + o) * 64;
             const float hi = f16_bits_to_float(rowp[(((ci >> 3) ^ (o & 7)) << 3) + (ci & 7)]);

@@ -132,6 +132,21 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;              // SWIZZLE_128B
     return d;
 }
+// The same descriptor in two steps for issue loops that build many of them: the low word of the descriptor of `smem_addr` once, then every
+// other start address of the same tile is that word plus the byte offset / 16 (no carry out of the 14-bit field below 256 KB) -- one add.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc_at(uint32_t lo) { return ((uint64_t)0x40004040u << 32) | lo; }   // SBO 1024, version 1, SWIZZLE_128B
+// K-major, SWIZZLE_64B operand tile: rows of 64 bytes, 8-row groups 512 B apart, 16-byte chunk c of row r at position c ^ ((r >> 1) & 3)
+// (layout type 4; addressing confirmed on B200 with tests/microbench/tc_probe.cu, probe 2: start + 32 B selects the second K = 16 slice).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;     // SBO: 8 rows * 64 B
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;              // SWIZZLE_64B
+    return d;
+}
 // K-major, no swizzle ("interleave"): 8-row x 16-byte core matrices, LBO between K chunks, SBO between 8-row groups (microbenchmark only).
 __device__ __forceinline__ uint64_t umma_desc_ns(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -580,9 +595,28 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             int word = n, hw_hi = 0, hw_lo = 0;             // 32-bit word / 16-bit halfword indices inside the frame record
             if (pieces && is_w) {
                 const int ko = rem >> 5, oo = ko & 63, ci = ((((rem >> 2) & 7) ^ (oo & 7)) << 2) + (rem & 3);
+                if ((exp_mask & 64) && blk >= 1) {
+                    // merged-N image (k_lvc_p, blocks 1 and 2), all SWIZZLE_128B: per layer
+                    //   T01 [128 rows x 128 B]: row R = piece * 64 + o holds [tap 0: 32 i | tap 1: 32 i] of that piece, chunk c at c ^ (R & 7) -- the B
+                    //       operand of ONE N = 128 MMA per activation piece and K-slice for taps 0 and 1 (hi and lo kernel products side by side);
+                    //   T2  [64 rows x 128 B]: row o = [32 i hi | 32 i lo] of tap 2, chunk c at c ^ (o & 7) (three-pass form).
+                    // (A 64-byte-row SWIZZLE_64B image holding all three taps merged was measured first: its B rows fetch ~2.5x slower.)
+                    // A warp (the 32 i of one (k, o)) still writes two runs of 64 contiguous, 64-byte-aligned bytes.
+                    const int tap = ko >> 6, sw = oo & 7;
+                    if (tap < 2) {
+                        const int base = 2 * (n - rem) + oo * 64 + ((((tap << 2) + (ci >> 3)) ^ sw) << 3) + (ci & 7);
+                        hw_hi = base;
+                        hw_lo = base + 64 * 64;
+                    } else {
+                        const int base = 2 * (n - rem) + 8192 + oo * 64 + (ci & 7);
+                        hw_hi = base + (((ci >> 3) ^ sw) << 3);
+                        hw_lo = base + (((4 + (ci >> 3)) ^ sw) << 3);
+                    }
+                } else {
                 const int base = 2 * ((n - rem) + ko * 32) + (KC_STORE_SHFL ? (ci & 6) : (ci & 7));
                 hw_hi = base + (((ci >> 3) ^ (oo & 7)) << 3);
                 hw_lo = base + (((4 + (ci >> 3)) ^ (oo & 7)) << 3);
+                }
             }
             const float inv_s = inv * S16_KERN, bv_s = bv * S16_KERN;
             // warp-uniform; broadcast from lane 0 so that ptxas KNOWS it (otherwise every store below re-materialises its uniform
@@ -793,8 +827,9 @@ static inline int tc_init(void** state, int device, const float* blob, const uin
 }
 
 // hk_hi / hk_lo: (3, B, T'+2, 64) each, written by k_kp_hidden.
+// kimg (mode tc_3xf16): 1 = blocks 1, 2 written in the merged-N image of k_lvc_p (exp_mask bit 64), 0 = the [hi | lo] row image of k_lvc_layer_h
 static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st,
-                             std::string& err, uint64_t* launches, int b0_pieces = 0) {
+                             std::string& err, uint64_t* launches, int b0_pieces = 0, int kimg = 0) {
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (b0_pieces && mode == FD_MODE_TC_3XF16 && !s->b0p_ready) {   // experimental path: maps + attribute on first use only
@@ -826,10 +861,10 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         if (b0_pieces) {
             maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
             k_kc_gemm_tc2<true, 16, true><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
-                                                                      s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp);
+                                                                      s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp | (kimg ? 64 : 0));
         } else
         k_kc_gemm_tc2<true, 16><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
-                                                                  s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp);
+                                                                  s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp | (kimg ? 64 : 0));
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc2<f16> failed: ") + cudaGetErrorString(e2); return -3; }
         ++*launches;
@@ -1967,6 +2002,7 @@ k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ m
                         mbar_wait(&full_bar[rs], (ld_used / KT_NSLOT) & 1);
                         tc_fence_after();
                         const uint32_t wt = ringu + rs * KT_SLOT;
+                        const uint32_t w_lo = umma_desc_lo(wt), a_lo = umma_desc_lo(at);   // descriptors below: one add each (offsets in 16-byte units)
                         if (layer == 0 && (sidx & 1)) {   // cond channels 64..79 of tap j: one K = 16 step, pieces at byte 0 (hi) and 32 (lo)
                             const int j = sidx >> 1;
                             const uint32_t sh = (uint32_t)(KT_PAD + j - 2) * 128u;
@@ -1976,11 +2012,11 @@ k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ m
                             umma_f16(tmem_u, da + 2, db, idesc, 1u);        // A_lo x W_hi
                         } else {
                             const int j = layer == 0 ? (sidx >> 1) : sidx;
-                            const uint32_t sh = (uint32_t)(KT_PAD + j - (layer == 0 ? 2 : 1)) * 128u;
+                            const uint32_t sh = (uint32_t)(KT_PAD + j - (layer == 0 ? 2 : 1)) * 8u;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t dah = umma_desc_sw128(at + sh + ks * 32), dal = umma_desc_sw128(at + KT_TILE + sh + ks * 32);
-                                const uint64_t dbh = umma_desc_sw128(wt + ks * 32), dbl = umma_desc_sw128(wt + 8192 + ks * 32);
+                                const uint64_t dah = umma_desc_at(a_lo + sh + ks * 2), dal = umma_desc_at(a_lo + KT_TILE / 16 + sh + ks * 2);
+                                const uint64_t dbh = umma_desc_at(w_lo + ks * 2), dbl = umma_desc_at(w_lo + 512 + ks * 2);
                                 umma_f16(tmem_u, dah, dbh, idesc, (sidx | ks) ? 1u : 0u);
                                 umma_f16(tmem_u, dah, dbl, idesc, 1u);
                                 umma_f16(tmem_u, dal, dbh, idesc, 1u);
@@ -2187,13 +2223,14 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
                 uint32_t at = smem_u + (uint32_t)(src * 2 * DT_ATILE), wt = smem_u + 4 * DT_ATILE + 2 * 16384 + (uint32_t)(layer * 24576);
                 FD_OPAQUE2(at, wt);
                 if (elect_one()) {
+                    const uint32_t a_lo = umma_desc_lo(at), w_lo = umma_desc_lo(wt);   // descriptors: one add each (offsets in 16-byte units)
 #pragma unroll
                     for (int k = 0; k < 3; ++k) {
-                        const uint32_t sh = (uint32_t)(DT_PAD + (k - 1) * dil) * 128u;
+                        const uint32_t sh = (uint32_t)(DT_PAD + (k - 1) * dil) * 8u;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint64_t dah = umma_desc_sw128(at + sh + j * 32), dal = umma_desc_sw128(at + DT_ATILE + sh + j * 32);
-                            const uint64_t db = umma_desc_sw128(wt + k * 8192 + j * 32);   // rows 0-31 W_hi, 32-63 W_lo
+                            const uint64_t dah = umma_desc_at(a_lo + sh + j * 2), dal = umma_desc_at(a_lo + DT_ATILE / 16 + sh + j * 2);
+                            const uint64_t db = umma_desc_at(w_lo + k * 512 + j * 2);   // rows 0-31 W_hi, 32-63 W_lo
                             if (three_pass) {
                                 umma_tf32(tmem_u, dah, db, idesc64, (k | j) ? 1u : 0u);
                                 umma_tf32(tmem_u, dal, db, idesc32, 1u);
@@ -2391,17 +2428,18 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
             uint32_t at = smem_u, wu = smem_u + 2 * UT_ATILE;
             FD_OPAQUE2(at, wu);
             if (elect_one()) {
+                const uint32_t a_lo = umma_desc_lo(at), w_lo = umma_desc_lo(wu);   // descriptors: one add each (offsets in 16-byte units)
 #pragma unroll
                 for (int ph = 0; ph < R; ++ph) {
                     const int sh = (ph + R / 2) / R, kk1 = (ph + R / 2) % R;
                     const uint32_t d = tmem_u + ph * 64;
 #pragma unroll
                     for (int tap = 0; tap < 2; ++tap) {   // tap 0: input m + sh (weights kk1); tap 1: input m + sh - 1 (weights kk1 + R)
-                        const uint32_t arow = (uint32_t)(1 + sh - tap) * 128u, kk = (uint32_t)(kk1 + tap * R);
+                        const uint32_t arow = (uint32_t)(1 + sh - tap) * 8u, kk = (uint32_t)(kk1 + tap * R);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            const uint64_t dah = umma_desc_sw128(at + arow + j * 32), dal = umma_desc_sw128(at + UT_ATILE + arow + j * 32);
-                            const uint64_t db = umma_desc_sw128(wu + kk * 8192 + j * 32);
+                            const uint64_t dah = umma_desc_at(a_lo + arow + j * 2), dal = umma_desc_at(a_lo + UT_ATILE / 16 + arow + j * 2);
+                            const uint64_t db = umma_desc_at(w_lo + kk * 512 + j * 2);
                             if (three_pass) {
                                 umma_tf32(d, dah, db, idesc64, (tap | j) ? 1u : 0u);
                                 umma_tf32(d, dal, db, idesc32, 1u);
@@ -2659,7 +2697,7 @@ static inline int tc_lvc_p_layer(void* state, int blk, int layer, const float* p
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     LvcPParams p;
-    p.cw16 = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_CONV_F16 : FD_S_LB2_CONV_F16] + (size_t)layer * (LP_CW_BYTES / 4);
+    p.cw16 = s->blob + s->sec_off[blk == 1 ? FD_S_LB1_CONV_F16M : FD_S_LB2_CONV_F16M] + (size_t)layer * (LP_CW_BYTES / 4);
     p.conv_b = s->blob + s->sec_off[FD_S_LB0_CONV_B + blk * FD_LB_STRIDE] + layer * C;
     p.first16 = s->blob + s->sec_off[FD_S_FIRST_F16];
     p.p_in = p_in; p.skip = skip; p.kern = kern; p.p_out = p_out; p.f_out = f_out; p.sat = sat;

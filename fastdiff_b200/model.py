@@ -161,14 +161,11 @@ class FastDiff(nn.Module):
     def invalidate_weights(self):
         """Force a re-pack of the weight blob on the next call.  REQUIRED after edits that autograd cannot see -- ``p.data.copy_()``,
         EMA swaps, manual ``.data`` assignment: they keep the storage pointer and do not bump ``p._version``, so `_weights_version`
-        cannot notice them.  ``load_state_dict``, ``remove_weight_norm``, ``.to()`` and in-place ops on the parameters are detected
-        automatically; a module in ``train()`` mode re-packs on every call."""
+        cannot notice them.  ``load_state_dict``, ``remove_weight_norm``, ``.to()`` and in-place ops on the parameters (optimizer steps
+        included) are detected automatically."""
         self._packed_version = None
 
     def _weights_version(self):
-        if self.training:          # weights are expected to move: never trust a cached blob
-            self._train_tick = getattr(self, "_train_tick", 0) + 1
-            return ("train", self._train_tick)
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def engine(self, device=None) -> Engine:

@@ -263,6 +263,25 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
         for c, src in ((0, hi[co, 0:8]), (1, hi[co, 8:16]), (2, lo[co, 0:8]), (3, lo[co, 8:16])):
             img[co, c ^ (co & 7)] = src
     S["FIRST_F16"] = _u16_as_f32(img)
+    # merged-N conv operand of k_lvc_p (blocks 1, 2), SWIZZLE_128B K-major tiles, same values and scales as LBn_CONV_F16; per layer 12 KB:
+    #   T01 [64 rows x 128 B]: row R = piece * 32 + co holds [tap 0: 32 ci | tap 1: 32 ci] of that piece, 16-byte chunk c at position c ^ (R & 7)
+    #   T2  [32 rows x 128 B]: row co = [32 ci hi | 32 ci lo] of tap 2, chunk c at c ^ (co & 7)
+    for n in (1, 2):
+        cw = torch.stack([W[f"lvc_blocks.{n}.convs.{i}.weight"] for i in range(LAYERS)]).numpy()   # [l][co][ci][k]
+        img = np.zeros((LAYERS, 96, 8, 8), dtype=np.uint16)                               # [l][64 rows of T01 + 32 rows of T2][chunk position][8 fp16]
+        for l in range(LAYERS):
+            hi, lo = f16_split(cw[l], float(scales[4 + 4 * n + l]))                      # [co][ci][k]
+            for piece, src in ((0, hi), (1, lo)):
+                for co in range(C):
+                    r = piece * C + co
+                    row = np.concatenate([src[co, :, 0], src[co, :, 1]]).reshape(8, 8)    # chunks 0-3 tap 0, 4-7 tap 1
+                    for c in range(8):
+                        img[l, r, c ^ (r & 7)] = row[c]
+            for co in range(C):
+                row = np.concatenate([hi[co, :, 2], lo[co, :, 2]]).reshape(8, 8)          # chunks 0-3 hi, 4-7 lo
+                for c in range(8):
+                    img[l, 64 + co, c ^ (co & 7)] = row[c]
+        S[f"LB{n}_CONV_F16M"] = _u16_as_f32(img)
     S["SCALES16"] = torch.from_numpy(scales)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}

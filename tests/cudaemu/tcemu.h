@@ -154,9 +154,23 @@ inline uint64_t umma_desc_sw128(uint32_t smem_addr) {
 constexpr uint32_t umma_idesc_f16(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 constexpr uint32_t umma_idesc_tf32(int M, int N) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
-inline float emu_f16_at(uint32_t desc_start, uint32_t sbo, int row, int k) {   // element (row, k) of a K-major SWIZZLE_128B operand slice
-    const uint32_t lin = desc_start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * 128u + (uint32_t)k * 2u;
-    const uint32_t phys = lin ^ (((lin >> 7) & 7u) << 4);
+inline uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+inline uint64_t umma_desc_at(uint32_t lo) { return ((uint64_t)0x40004040u << 32) | lo; }
+inline uint64_t umma_desc_sw64(uint32_t smem_addr) {   // K-major SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart (layout type 4)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+// element (row, k) of a K-major operand slice: layout 2 = SWIZZLE_128B (128-byte rows, address bits [7,10) XORed into [4,7)),
+// layout 4 = SWIZZLE_64B (64-byte rows, bits [7,9) XORed into [4,6)) -- both on ABSOLUTE address bits, as measured on B200 (tests/microbench/tc_probe.cu)
+inline float emu_f16_at(uint32_t desc_start, uint32_t sbo, int row, int k, int layout = 2) {
+    const uint32_t pitch = layout == 4 ? 64u : 128u;
+    const uint32_t lin = desc_start + (uint32_t)(row >> 3) * sbo + (uint32_t)(row & 7) * pitch + (uint32_t)k * 2u;
+    const uint32_t phys = layout == 4 ? (lin ^ (((lin >> 7) & 3u) << 4)) : (lin ^ (((lin >> 7) & 7u) << 4));
     uint16_t h;
     memcpy(&h, emu_smem_ptr(phys), 2);
     return f16_bits_to_float_soft(h);
@@ -169,14 +183,15 @@ inline void emu_mma_f16_now(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, u
     const int N = (int)((idesc >> 17) & 0x3F) << 3, M = (int)((idesc >> 24) & 0x1F) << 4;
     const uint32_t a0 = (uint32_t)(a_desc & 0x3FFF) << 4, b0 = (uint32_t)(b_desc & 0x3FFF) << 4;
     const uint32_t sa = (uint32_t)((a_desc >> 32) & 0x3FFF) << 4, sb = (uint32_t)((b_desc >> 32) & 0x3FFF) << 4;
-    if (M != 128 || ((a_desc >> 61) & 7) != 2 || ((b_desc >> 61) & 7) != 2) { fprintf(stderr, "tcemu: unsupported MMA shape/layout\n"); abort(); }
+    const int la = (int)((a_desc >> 61) & 7), lb = (int)((b_desc >> 61) & 7);
+    if (M != 128 || (la != 2 && la != 4) || (lb != 2 && lb != 4)) { fprintf(stderr, "tcemu: unsupported MMA shape/layout\n"); abort(); }
     const int lane0 = (int)(d_tmem >> 16), col0 = (int)(d_tmem & 0xFFFF);
     float bt[256][16];
     for (int n = 0; n < N; ++n)
-        for (int k = 0; k < 16; ++k) bt[n][k] = emu_f16_at(b0, sb, n, k);
+        for (int k = 0; k < 16; ++k) bt[n][k] = emu_f16_at(b0, sb, n, k, lb);
     for (int m = 0; m < M; ++m) {
         float a[16];
-        for (int k = 0; k < 16; ++k) a[k] = emu_f16_at(a0, sa, m, k);
+        for (int k = 0; k < 16; ++k) a[k] = emu_f16_at(a0, sa, m, k, la);
         for (int n = 0; n < N; ++n) {
             float acc = accumulate ? emu_tmem[lane0 + m][col0 + n] : 0.f;
             for (int k = 0; k < 16; ++k) acc += a[k] * bt[n][k];
