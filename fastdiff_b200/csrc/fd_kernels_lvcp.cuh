@@ -34,15 +34,13 @@ constexpr int LP_HEAD_ROWS = 32;                 // zero rows before item 0
 constexpr int LP_PAD_ROWS = 64;                  // zero rows after every item (32 tail + 32 head of the next item)
 constexpr int LP_SLACK_ROWS = 192;               // readable (not necessarily zero) rows after the last pad: the last tile's window
 constexpr int LP_STAGE_BYTES = 26624;            // 192 A rows (24576) | lbias 2 x 256 | audio window 136 floats (544) | pad -> multiple of 1024
-constexpr int LP_NA = 3;
+template <int HOP> __host__ __device__ constexpr int lp_na() { return HOP == 256 ? 4 : 3; }   // input stages (hop 64: two frames of kernels per tile fill the smem)
 constexpr int LP_Y_BYTES = 17408;                // 136 rows x 128 B (130 used)
-constexpr int LP_OUT_BYTES = 16384;              // 128 output rows
 constexpr int LP_CW_BYTES = 3 * C * 128;         // 12288
 constexpr int LP_AU = 136;                       // audio positions t0-4 .. t0+131
-constexpr int LP_THREADS = 832;                  // warps 0-15 gate epilogue, 16-23 conv epilogue, 24 loader, 25 MMA issuer.  The hardware's warp
+constexpr int LP_THREADS = 864;                  // warps 0-15 gate epilogue, 16-23 conv epilogue, 24 loader, 25 MMA issuer, 26 output storer.  The hardware's warp
                                                  // arbiter favours HIGH warp ids: the roles on the critical path (MMA issue, loads, conv epilogue -- each
                                                  // tile's LVC MMAs wait for it) sit above the 16 gate warps, which otherwise starve them (ncu, round 2)
-constexpr int LP_E2_THREADS = 512;
 
 __host__ __device__ inline size_t lp_rows(int B, int T) { return (size_t)LP_HEAD_ROWS + (size_t)B * (T + LP_PAD_ROWS) + LP_SLACK_ROWS; }
 __host__ __device__ inline size_t lp_row_of(int b, int T, int t) { return (size_t)LP_HEAD_ROWS + (size_t)b * (T + LP_PAD_ROWS) + t; }
@@ -52,8 +50,8 @@ constexpr int LP_SKA_BYTES = 16384;              // hop 256: audio im2col tile o
 constexpr int LP_SKB_BYTES = 4096;               // hop 256: first_audio_conv pieces (FIRST_F16), 32 rows x 128 B
 constexpr float LP_S_AU = 16.f;                  // prescale of the audio pieces: the same range as the activations (|audio| < 4094 before saturation)
 template <int HOP> __host__ __device__ constexpr int lp_smem_bytes() {
-    return LP_NA * LP_STAGE_BYTES + 2 * LP_Y_BYTES + 2 * lp_nf<HOP>() * 24576 + (HOP == 256 ? 2 * LP_OUT_BYTES + LP_SKA_BYTES + LP_SKB_BYTES : 0) +
-           LP_CW_BYTES + C * 4 + 512 + 24 * 8 + 64 + 1024;
+    return lp_na<HOP>() * LP_STAGE_BYTES + 2 * LP_Y_BYTES + 2 * lp_nf<HOP>() * 24576 + (HOP == 256 ? LP_SKA_BYTES + LP_SKB_BYTES : 0) +
+           LP_CW_BYTES + C * 4 + 512 + 32 * 8 + 64 + 1024;
 }
 
 // Optional role timeline (-DLP_TIMELINE=1, GPU build only): CTA 0 of the block-2 launch with dilation LP_TL_DIL stamps clock64 at the
@@ -109,6 +107,7 @@ template <int HOP>
 __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     constexpr int NF = lp_nf<HOP>();
     constexpr bool STAGE_OUT = (HOP == 256);
+    constexpr int NA = lp_na<HOP>();
     constexpr bool SKIP_MMA = (HOP == 256);            // skip = first_conv(audio) on the tensor core; hop 64 loads skip rows from memory
     constexpr int W_BYTES = NF * 24576;
     // TMEM columns: conv accumulators 2 stages x 64 (hi-weight products | lo-weight products) at 0; second conv pass (rows +128, single-buffered,
@@ -119,29 +118,31 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* a_st = smem;                                        // [3][LP_STAGE_BYTES]
-    unsigned char* y_t = a_st + LP_NA * LP_STAGE_BYTES;                // [2][LP_Y_BYTES]
+    unsigned char* y_t = a_st + NA * LP_STAGE_BYTES;                   // [2][LP_Y_BYTES]
     unsigned char* w_t = y_t + 2 * LP_Y_BYTES;                         // [2][W_BYTES]
-    unsigned char* o_t = w_t + 2 * W_BYTES;                            // [2][LP_OUT_BYTES] (STAGE_OUT)
-    unsigned char* sk_a = o_t + (STAGE_OUT ? 2 * LP_OUT_BYTES : 0);    // [128 rows][128 B] audio im2col pieces (SKIP_MMA)
+    unsigned char* sk_a = w_t + 2 * W_BYTES;                           // [128 rows][128 B] audio im2col pieces (SKIP_MMA), two column halves
     unsigned char* sk_b = sk_a + (SKIP_MMA ? LP_SKA_BYTES : 0);        // [32 rows][128 B] first conv pieces (SKIP_MMA)
     unsigned char* cw = sk_b + (SKIP_MMA ? LP_SKB_BYTES : 0);          // [3 taps][32 rows][128 B]
     float* cbs_s = (float*)(cw + LP_CW_BYTES);                         // [32] conv bias * S16_ACT
     unsigned char* carry = (unsigned char*)(cbs_s + C);                // [2][256 B]: Y rows 0, 1 of the previous tile
     uint64_t* bars = (uint64_t*)(carry + 512);
-    uint64_t* a_full = bars;            // [3] loader -> MMA, both epilogues (tx)
-    uint64_t* a_free = bars + 3;        // [3] gate epilogue (16 warps) -> loader
-    uint64_t* w_full = bars + 6;        // [2] loader -> MMA (tx)
-    uint64_t* w_free = bars + 8;        // [2] MMA commit -> loader
-    uint64_t* cacc_full = bars + 10;    // [2] conv MMAs committed -> conv epilogue
-    uint64_t* cacc_free = bars + 12;    // [2] conv epilogue (4 warps) -> MMA
-    uint64_t* y_full = bars + 14;       // [2] conv epilogue (4 warps) -> MMA: Y tile, skip operand tile, prescaled LVC bias are in place
-    uint64_t* lacc_full = bars + 16;    // [2] LVC (+ skip) MMAs committed -> gate epilogue; also "Y tile / skip tile free" for the conv epilogue
-    uint64_t* lacc_free = bars + 18;    // [2] gate epilogue (16 warps) -> MMA
-    uint32_t* tmem_base_s = (uint32_t*)(bars + 24);
+    uint64_t* a_full = bars;            // [NA] loader -> MMA, both epilogues (tx)
+    uint64_t* a_free = bars + 4;        // [NA] gate epilogue (16 warps) -> loader
+    uint64_t* w_full = bars + 8;        // [2] loader -> MMA (tx)
+    uint64_t* w_free = bars + 10;       // [2] MMA commit -> loader
+    uint64_t* cacc_full = bars + 12;    // [2] conv MMAs committed -> conv epilogue
+    uint64_t* cacc_free = bars + 14;    // [2] conv epilogue (8 warps) -> MMA
+    uint64_t* y_full = bars + 16;       // [2] conv epilogue (8 warps) -> MMA: Y tile, skip operand tile, prescaled LVC bias are in place
+    uint64_t* lacc_full = bars + 18;    // [2] LVC (+ skip) MMAs committed -> gate epilogue; also "Y tile / skip tile free" for the conv epilogue
+    uint64_t* lacc_free = bars + 20;    // [2] gate epilogue (16 warps) -> MMA
+    uint64_t* out_full = bars + 24;     // [NA] (hop 256, layers 0-2) gate epilogue (16 warps) -> storer: the output rows are staged in the input stage
+    uint32_t* tmem_base_s = (uint32_t*)(bars + 28);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_free[i], 16); }
+        // staged output (hop 256, a next layer exists): the storer releases a stage once its bulk copy has read it; otherwise the 16 gate warps do
+        const uint32_t free_cnt = (STAGE_OUT && p.p_out != nullptr) ? 1u : 16u;
+        for (int i = 0; i < NA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_free[i], free_cnt); mbar_init(&out_full[i], 16); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&w_full[i], 1); mbar_init(&w_free[i], 1);
             mbar_init(&cacc_full[i], 1); mbar_init(&cacc_free[i], 8);
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     if (warp_u == 24) {
         // =========================================== loader ===========================================
         if (elect_one()) {
-            int wc = 0, b = b_first, tt = tt_first, s = 0, sn = 0;     // s = n % 3, sn = n / 3
+            int wc = 0, b = b_first, tt = tt_first, s = 0, sn = 0;     // s = n % NA, sn = n / NA
             bool new_frame = true;
             for (int n = 0; n < ntile; ++n) {
                 const int t0 = tt * LP_TT;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                         }
                 }
                 if (--tt < 0) { tt = ntt - 1; --b; new_frame = true; }
-                if (++s == LP_NA) { s = 0; ++sn; }
+                if (++s == NA) { s = 0; ++sn; }
             }
         }
         __syncwarp();
@@ -374,9 +375,30 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             LP_STAMP(1, n, 2);
             if (n >= 1) lvc_mmas(n - 1);
             if (--tt < 0) tt = ntt - 1;
-            if (++s == LP_NA) { s = 0; ++sn; }
+            if (++s == NA) { s = 0; ++sn; }
         }
         if (ntile > 0) lvc_mmas(ntile - 1);
+    } else if (warp_u == 26) {
+        // =========================================== output storer ===========================================
+        // One thread: waits until the 16 gate warps have staged a tile's 128 output rows (in place, rows 32..159 of the tile's input stage), writes
+        // them with ONE bulk copy and releases the stage when the copy has read it.  (When a gate warp did this, its wait for the copy's read
+        // held back all 16 warps at the next tile's barrier: ~1,200 of the gate loop's ~3,200 cycles per tile.)
+        if (STAGE_OUT && p.p_out != nullptr && elect_one()) {
+            int b = b_first, tt = tt_first, s = 0, sn = 0;
+            for (int n = 0; n < ntile; ++n) {
+                const int t0 = tt * LP_TT;
+                mbar_wait(&out_full[s], (uint32_t)(sn & 1));
+                const int rows = min(LP_TT, T - t0);
+                bulk_s2g(p.p_out + lp_row_of(b, T, t0) * C, a_st + s * LP_STAGE_BYTES + 32 * 128, (uint32_t)rows * 128u);
+                bulk_commit();
+                bulk_wait_read0();
+                mbar_arrive(&a_free[s]);
+                if (--tt < 0) { tt = ntt - 1; --b; }
+                if (++s == NA) { s = 0; ++sn; }
+            }
+            bulk_wait_all();
+        }
+        __syncwarp();
     } else if (warp_u >= 16) {
         // =========================================== conv epilogue (8 warps: 16..23) ===========================================
         const int q = warp & 3, part = (warp - 16) >> 2;  // TMEM lane quarter; which 16 of the 32 conv channels
@@ -471,14 +493,13 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             if (lane == 0) mbar_arrive(&y_full[cs]);
             if (warp == 16 && lane == 0) LP_STAMP(2, n, 5);
             if (--tt < 0) tt = ntt - 1;
-            if (++s == LP_NA) { s = 0; ++sn; }
+            if (++s == NA) { s = 0; ++sn; }
         }
         if (p.sat && vmax > F16_MAX) *p.sat = 1u;
     } else {
         // =========================================== gate epilogue (16 warps: 0..15) ===========================================
         const int q = warp & 3, j = warp >> 2;                  // TMEM lane quarter, channel octet (gate channels 8j .. 8j+7)
         const int r = q * 32 + lane;                            // output row of this thread
-        const int etid = tid;                                   // 0 .. 511
         const int fi = (HOP >= LP_TT) ? 0 : r / HOP;            // warp-uniform (HOP is a multiple of 32)
         // everything below runs in the x16 domain of the pieces (exact: powers of two): z16 = 16 z, gate x 16, skip x 16
         const float c_s = p.inv_l * -1.4426950408889634f, c_t = p.inv_l * -2.8853900817779268f, c_sk = p.inv_sk * S16_ACT;
@@ -572,17 +593,15 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 lp_split8(v, hi, lo, vmax);
                 const int sw = r & 7;                                                   // == t & 7 (t0 is a multiple of 128)
                 if (STAGE_OUT) {
-                    unsigned char* ot = o_t + ls * LP_OUT_BYTES;
+                    // staged IN PLACE: the output pieces of row r, chunks j and 4 + j, go over the input pieces of the same row and chunks in the
+                    // stage -- cells only this thread reads (z, above) -- and one bulk copy writes the 128 rows; the stage is released once
+                    // the copy has read it (the shared memory of a separate staging tile buys the fourth input stage instead)
+                    unsigned char* ot = const_cast<unsigned char*>(a) + 32 * 128;
                     *reinterpret_cast<uint4*>(ot + r * 128 + ((j ^ sw) << 4)) = hi;
                     *reinterpret_cast<uint4*>(ot + r * 128 + (((4 + j) ^ sw) << 4)) = lo;
                     fence_async_smem();
-                    if (etid == 0) bulk_wait_read0();        // the bulk store of tile n-1 has read its buffer: free for tile n+1 after the barrier
-                    group_sync(1, LP_E2_THREADS);
-                    if (etid == 0) {
-                        const int rows = min(LP_TT, T - t0);
-                        bulk_s2g(p.p_out + lp_row_of(b, T, t0) * C, ot, (uint32_t)rows * 128u);
-                        bulk_commit();
-                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&out_full[s]);   // -> storer (which also releases the stage)
                 } else if (t < T) {
                     uint4* dst = reinterpret_cast<uint4*>(p.p_out + lp_row_of(b, T, t) * C);
                     dst[j ^ sw] = hi;
@@ -590,12 +609,11 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_free[s]);
+            if (!(STAGE_OUT && p.p_out != nullptr) && lane == 0) mbar_arrive(&a_free[s]);
             if (warp == 0 && lane == 0) LP_STAMP(3, n, 6);
             if (--tt < 0) { tt = ntt - 1; --b; }
-            if (++s == LP_NA) { s = 0; ++sn; }
+            if (++s == NA) { s = 0; ++sn; }
         }
-        if (STAGE_OUT && etid == 0) bulk_wait_all();
         if (p.sat && vmax > F16_MAX) *p.sat = 1u;
     }
     tc_fence_before();

@@ -466,6 +466,15 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 // (Measured and dropped in round 2: the un-swapped form -- frames on the MMA's M side, so that an epilogue thread owns whole 128-byte operand
 // rows and writes them with 16-byte stores, bit-identical output -- ran at 1.60 ms per launch against 0.61 ms: a warp store then touches 32
 // different lines with 16 bytes each, and the L2 request rate, not the instruction count, is what bounds this store stream.)
+// Optional role timeline of the kernel_conv GEMM (-DKC_TIMELINE=1, GPU build): CTA 0 stamps clock64 for its first 32 items --
+// [role 0 TMA producer | 1 MMA issuer | 2 epilogue warp 2][item][8 slots]; fd_debug_read("kc_timeline"), tests/gpu_kc_timeline.py.
+#if defined(KC_TIMELINE) && !defined(FD_EMU)
+constexpr int KC_TL_ITEMS = 32;
+__device__ unsigned long long g_kc_timeline[3 * KC_TL_ITEMS * 8];
+#define KC_STAMP(role, it, slot) do { if (blockIdx.x == 0 && (it) < KC_TL_ITEMS) g_kc_timeline[((role) * KC_TL_ITEMS + (it)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define KC_STAMP(role, it, slot) do { } while (0)
+#endif
 template <bool F16, int EPW, bool B0P = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
@@ -509,13 +518,16 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
         // ================= TMA producer (each CTA loads its own A rows and its half of the frames) =================
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
-            for (int item = pair_id; item < total_items; item += n_clusters) {
+            [[maybe_unused]] int it_no = 0;
+            for (int item = pair_id; item < total_items; item += n_clusters, ++it_no) {
                 const int blk = item / items_per_blk, r = item % items_per_blk;
                 const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
                 const CUtensorMap* wh = &maps.w_hi[blk]; const CUtensorMap* wl = &maps.w_lo[blk];
+                KC_STAMP(0, it_no, 0);
                 const CUtensorMap* hh = &maps.h_hi[blk]; const CUtensorMap* hl = &maps.h_lo[blk];
                 for (int a = 0; a < NATOM; ++a) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    KC_STAMP(0, it_no, 1 + a);
                     unsigned char* st = smem + stage * KC2_STAGE_BYTES;
                     // timing experiment (exp_mask & 16, WRONG results): weights loaded for the first tile only -> half the operand feed
                     const bool skip_a = (exp_mask & 16) && item != pair_id;
@@ -537,12 +549,16 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
         if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc = F16 ? umma_idesc_f16(256, 256) : umma_idesc_tf32(256, 256);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (int item = pair_id; item < total_items; item += n_clusters) {
+            [[maybe_unused]] int it_no = 0;
+            for (int item = pair_id; item < total_items; item += n_clusters, ++it_no) {
+                KC_STAMP(1, it_no, 0);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                KC_STAMP(1, it_no, 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int a = 0; a < NATOM; ++a) {
                     mbar_wait(&full_bar[stage], phase);
+                    KC_STAMP(1, it_no, 2 + a);
                     tc_fence_after();
                     const uint32_t st = smem_u32(smem + stage * KC2_STAGE_BYTES);
                     const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + KC2_A_BYTES);
@@ -568,6 +584,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     if (++stage == KC2_STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit_2sm(&tfull_bar[acc]);
+                KC_STAMP(1, it_no, 5);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -576,10 +593,12 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
         const int q = warp & 3;
         const int cpart = (warp - 2) >> 2;
         uint32_t acc = 0, acc_phase = 0;
-        for (int item = pair_id; item < total_items; item += n_clusters) {
+        [[maybe_unused]] int it_no = 0;
+        for (int item = pair_id; item < total_items; item += n_clusters, ++it_no) {
             const int blk = item / items_per_blk, r = item % items_per_blk;
             const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
             const int n = nt * 128 + q * 32 + lane;
+            if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 0);
             const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
             const float bv = bias[n];
             const float inv = F16 ? (blk == 0 ? inv0 : (blk == 1 ? inv1 : inv2)) : 1.f;
@@ -650,6 +669,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             int center = p + 1, bb = center / (Tm + 2), fp = center % (Tm + 2);
             const bool fast = __shfl_sync(0xffffffffu, (int)((fp >= 1) && (fp + CPW - 1 <= Tm) && (p + CPW - 1 < M)), 0) != 0;
             mbar_wait(&tfull_bar[acc], acc_phase);
+            if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * CPW;
             if (exp_mask & 1) {
@@ -693,8 +713,10 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                         uint32_t v[32];
                         tmem_ld_32x32b_x32(taddr + c0, v);
                         tmem_ld_wait();
+                        if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 2 + (c0 >> 5) * 2);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) put_pieces(ph + (size_t)j * (2 * KCN), pl + (size_t)j * (2 * KCN), __uint_as_float(v[j]));
+                        if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 3 + (c0 >> 5) * 2);
                         ph += (size_t)64 * KCN; pl += (size_t)64 * KCN;
                     }
                 } else {
@@ -709,7 +731,30 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                         o += (size_t)32 * KCN;
                     }
                 }
-            } else {
+            } else if (Tm + 2 > 34) {
+                // GAP path: the 64-frame span crosses an utterance boundary (30 % of the items at T' = 861 have one such warp group) or the end of the
+                // tensor.  Rows of padded index p map to frame records consecutively except for the two pad rows between utterances, so per 32-row
+                // sub-chunk there is one record base, at most one gap (rows j1, j1 + 1 skipped, later rows shifted by two records), possibly a leading
+                // pad row and a row limit -- all warp-uniform.  (The generic per-row walk below cost ~14,000 cycles per item against ~5,000 for the
+                // straight path and set the pace of the whole kernel: round-2 GEMM timeline.)
+#pragma unroll 1
+                for (int c0 = 0; c0 < CPW; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(taddr + c0, v);
+                    tmem_ld_wait();
+                    const int pc = p + c0, cen = pc + 1, bbc = cen / (Tm + 2), fpc = cen % (Tm + 2);
+                    const int j1 = Tm + 1 - fpc, jlo = fpc == 0 ? 1 : 0, jhi = M - pc;   // end pad row; leading pad row; rows past the end
+                    float* rec0 = kern + ((long long)bbc * Tm + fpc - 1) * KCN;           // record of row 0 (never dereferenced when row 0 is a pad row)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j >= jlo && j < jhi && j != j1 && j != j1 + 1) {
+                            float* rec = rec0 + (long long)(j - (j > j1 ? 2 : 0)) * KCN;
+                            if (as_pieces) put_pieces(reinterpret_cast<uint16_t*>(rec) + hw_hi, reinterpret_cast<uint16_t*>(rec) + hw_lo, __uint_as_float(v[j]));
+                            else rec[word] = F16 ? fmaf(__uint_as_float(v[j]), inv, bv) : __uint_as_float(v[j]) + bv;
+                        }
+                    }
+                }
+            } else {   // tiny utterances (several boundaries per sub-chunk): generic per-row walk
 #pragma unroll 1
                 for (int c0 = 0; c0 < CPW; c0 += 32) {
                     uint32_t v[32];
@@ -730,6 +775,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+            if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 6);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }

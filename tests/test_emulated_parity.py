@@ -189,12 +189,13 @@ def test_emulated_block0_tensor_core(synth, emu_lib, B, Tm):
     assert (net((x, mel, t)) - ref).abs().max() < 5e-5
 
 
-@pytest.mark.parametrize("B,Tm", [(1, 3), (2, 9), (3, 17), (1, 40)])
+@pytest.mark.parametrize("B,Tm", [(1, 3), (2, 9), (3, 17), (1, 40), (2, 35)])
 def test_emulated_piece_row_path_vs_row_path(synth, emu_lib, B, Tm):
     """Blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>, the default; fd_kernels_lvcp.cuh) against the oracle and
     against the fp32-row kernels they replace (k_lvc_layer_h, option lvc_p = 0): lvc1 / lvc2 stage outputs and eps.  The two paths
     differ by the 22-bit state carry only (~2e-6 on eps).  (1,3): single-tile CTAs; (2,9), (3,17): odd T' -> a half tile ends every
-    item of block 1; (1,40): chunks of several tiles (carried rows, kernel reuse across the two tiles of a hop-256 frame, ring wrap)."""
+    item of block 1; (1,40): chunks of several tiles (carried rows, kernel reuse across the two tiles of a hop-256 frame, ring wrap); (2,35): an
+    utterance boundary inside a 32-frame sub-chunk of the kernel_conv GEMM epilogue (its gap path: T' + 2 > 34) and rows past the end."""
     from fastdiff_b200.synthetic import make_inputs
     from oracle import fastdiff_oracle as O
     sd, W = synth
