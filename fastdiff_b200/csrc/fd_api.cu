@@ -1140,6 +1140,23 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         FD_CUDA(h, cudaStreamSynchronize(st));
         return FD_OK;
     }
+#if defined(UT_TIMELINE)
+    if (!strcmp(name, "ut_timeline")) {   // k_upsample_tc<4, POUT> phase timeline
+        constexpr int NW = 24 * 8;
+        *count = NW;
+        if (!out_dev) return FD_OK;
+        static unsigned long long host[NW];
+        static float rel[NW];
+        FD_CUDA(h, cudaStreamSynchronize(st));
+        FD_CUDA(h, cudaMemcpyFromSymbol(host, g_ut_timeline, sizeof host));
+        unsigned long long mn = ~0ull;
+        for (int i = 0; i < NW; ++i) if (host[i] && host[i] < mn) mn = host[i];
+        for (int i = 0; i < NW; ++i) rel[i] = host[i] ? (float)(double)(host[i] - mn + 1) : 0.f;
+        FD_CUDA(h, cudaMemcpyAsync(out_dev, rel, sizeof rel, cudaMemcpyHostToDevice, st));
+        FD_CUDA(h, cudaStreamSynchronize(st));
+        return FD_OK;
+    }
+#endif
 #if defined(KC_TIMELINE)
     if (!strcmp(name, "kc_timeline")) {   // kernel_conv GEMM role timeline (fd_kernels_tc.cuh): cycles relative to the earliest stamp, 0 where unset
         constexpr int NW = 3 * KC_TL_ITEMS * 8;

@@ -742,15 +742,33 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c0, v);
                     tmem_ld_wait();
-                    const int pc = p + c0, cen = pc + 1, bbc = cen / (Tm + 2), fpc = cen % (Tm + 2);
+                    // (broadcast from lane 0 so that ptxas KNOWS these are warp-uniform: uniform predicates and branches, no per-store R2UR)
+                    const int pc = __shfl_sync(0xffffffffu, p + c0, 0), cen = pc + 1, bbc = cen / (Tm + 2), fpc = cen % (Tm + 2);
                     const int j1 = Tm + 1 - fpc, jlo = fpc == 0 ? 1 : 0, jhi = M - pc;   // end pad row; leading pad row; rows past the end
                     float* rec0 = kern + ((long long)bbc * Tm + fpc - 1) * KCN;           // record of row 0 (never dereferenced when row 0 is a pad row)
+                    // rows before the gap: record row0 + j; rows after it: row0 + j - 2 -- two base pointers, constant offsets, uniform predicates
+                    const int ja = j1 < jhi ? j1 : jhi;        // rows [jlo, ja) via base A; rows (j1 + 1, jhi) via base B
+                    if (as_pieces) {
+                        uint16_t* pha = reinterpret_cast<uint16_t*>(rec0) + hw_hi;
+                        uint16_t* pla = reinterpret_cast<uint16_t*>(rec0) + hw_lo;
+                        uint16_t* phb = pha - 4 * KCN;
+                        uint16_t* plb = pla - 4 * KCN;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (j >= jlo && j < jhi && j != j1 && j != j1 + 1) {
-                            float* rec = rec0 + (long long)(j - (j > j1 ? 2 : 0)) * KCN;
-                            if (as_pieces) put_pieces(reinterpret_cast<uint16_t*>(rec) + hw_hi, reinterpret_cast<uint16_t*>(rec) + hw_lo, __uint_as_float(v[j]));
-                            else rec[word] = F16 ? fmaf(__uint_as_float(v[j]), inv, bv) : __uint_as_float(v[j]) + bv;
+                        for (int j = 0; j < 32; ++j) {
+                            const float sv = fmaf(__uint_as_float(v[j]), inv_s, bv_s);
+                            const uint16_t h16 = f16_sat_bits(sv);
+                            const uint16_t l16 = f16_sat_bits(sv - f16_bits_to_float(h16));
+                            if (j >= jlo && j < ja) { pha[(size_t)j * (2 * KCN)] = h16; pla[(size_t)j * (2 * KCN)] = l16; }
+                            else if (j > j1 + 1 && j < jhi) { phb[(size_t)j * (2 * KCN)] = h16; plb[(size_t)j * (2 * KCN)] = l16; }
+                        }
+                    } else {
+                        float* oa = rec0 + word;
+                        float* ob = oa - 2 * KCN;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float val = F16 ? fmaf(__uint_as_float(v[j]), inv, bv) : __uint_as_float(v[j]) + bv;
+                            if (j >= jlo && j < ja) oa[(size_t)j * KCN] = val;
+                            else if (j > j1 + 1 && j < jhi) ob[(size_t)j * KCN] = val;
                         }
                     }
                 }
@@ -2387,6 +2405,13 @@ struct UpPOut {
     unsigned int* sat;
 };
 
+// Optional phase timeline (-DUT_TIMELINE=1, GPU build): thread 0 of CTA 0 of the r = 4 piece-row launch stamps clock64 per tile (8 slots x 24 tiles).
+#if defined(UT_TIMELINE) && !defined(FD_EMU)
+__device__ unsigned long long g_ut_timeline[24 * 8];
+#define UT_STAMP(slot) do { if (R == 4 && POUT && blockIdx.x == 0 && tid == 0 && tl_n < 24) g_ut_timeline[tl_n * 8 + (slot)] = clock64(); } while (0)
+#else
+#define UT_STAMP(slot) do { } while (0)
+#endif
 template <int R, bool POUT = false>
 __global__ void __launch_bounds__(512, (R == 4 ? 2 : 1))
 k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, const float* __restrict__ bias,
@@ -2439,8 +2464,10 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
     int tile = blockIdx.x;
     if (tile < total && gw_u == 0) { if (elect_one()) issue_rows(tile); __syncwarp(); }
     uint32_t parity = 0;
-    for (; tile < total; tile += gridDim.x, parity ^= 1) {
+    [[maybe_unused]] int tl_n = 0;
+    for (; tile < total; tile += gridDim.x, parity ^= 1, ++tl_n) {
         const int b = tile / ntt, m0 = (tile % ntt) * 128;
+        UT_STAMP(0);
         if (POUT && R == 4) {   // audio window of this tile's outputs (zero outside the utterance); read by the epilogue, after two barriers
             const int Tout = Tin * R;
             for (int i = tid; i < 128 * R + 8; i += 512) {
@@ -2449,6 +2476,7 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
             }
         }
         mbar_wait(&bar[1], parity);
+        UT_STAMP(1);
         // ---- lrelu + tf32 split, in place (8 lanes per row) ----
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -2469,6 +2497,7 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
         }
         fence_async_smem();
         __syncthreads();
+        UT_STAMP(2);
         if (gw_u == 0) {
             tc_fence_after();
             uint32_t at = smem_u, wu = smem_u + 2 * UT_ATILE;
@@ -2499,7 +2528,9 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
             }
             __syncwarp();
         }
+        UT_STAMP(3);
         mbar_wait(&bar[0], parity);
+        UT_STAMP(4);
         tc_fence_after();
         if (gw_u == 0 && tile + (int)gridDim.x < total) { if (elect_one()) issue_rows(tile + gridDim.x); __syncwarp(); }   // tile is free
         {   // epilogue: thread = (input row m, 8 channels); its r outputs are consecutive rows r m + ph
@@ -2561,8 +2592,10 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
                 }
             }
         }
+        UT_STAMP(5);
         tc_fence_before();
         __syncthreads();
+        UT_STAMP(6);
     }
     if (POUT && po.sat && vmax > F16_MAX) *po.sat = 1u;
     tc_fence_before();

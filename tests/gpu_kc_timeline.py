@@ -31,3 +31,10 @@ for r in range(3):
 m = tl[1, :, 5]
 per = [(m[n + 1] - m[n]).item() for n in range(8, NI - 1)]
 print("steady-state cycles per item (MMA commits):", sum(per) / len(per))
+try:
+    ut = eng.debug_read("ut_timeline", B, Tm).cpu().reshape(24, 8).double()
+    print("== k_upsample_tc<4, POUT> CTA 0: top | loads ok | split+sync | mma issued | mma done | epilogue done | end sync")
+    for n in range(12):
+        print(f"  tile {n:2d}: " + " ".join(f"{int(ut[n, k]):8d}" for k in range(7)))
+except Exception as e:  # built without -DUT_TIMELINE
+    print("no ut_timeline:", e)
