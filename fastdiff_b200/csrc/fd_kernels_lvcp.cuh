@@ -405,6 +405,9 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
         const int yr = q * 32 + lane;              // Y row of this thread <-> t = t0 - 1 + yr; (part 0) also skip-operand row <-> t = t0 + yr
         const float inv_cs = p.inv_c * S16_ACT;
         float vmax = 0.f;
+        float cb[16];                              // this thread's 16 conv biases (x 16), loop-invariant
+#pragma unroll
+        for (int e = 0; e < 16; ++e) cb[e] = cbs_s[part * 16 + e];
         int tt = tt_first, s = 0, sn = 0;
         for (int n = 0; n < ntile; ++n) {
             const int t0 = tt * LP_TT;
@@ -434,11 +437,12 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                     float y[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        const float x = fmaf(__uint_as_float(acc[cc * 8 + e]) + __uint_as_float(acc2[cc * 8 + e]), inv_cs, cbs_s[part * 16 + cc * 8 + e]);
-                        y[e] = in ? fmaxf(x, 0.2f * x) : 0.f;
+                        const float x = fmaf(__uint_as_float(acc[cc * 8 + e]) + __uint_as_float(acc2[cc * 8 + e]), inv_cs, cb[cc * 8 + e]);
+                        y[e] = fmaxf(x, 0.2f * x);
                     }
                     uint4 hi, lo;
                     lp_split8(y, hi, lo, vmax);
+                    if (!in) hi = lo = make_uint4(0u, 0u, 0u, 0u);   // rows outside [0, T): the reference's zero padding of the LVC input (utterance ends only)
                     const int c = part * 2 + cc;
                     *reinterpret_cast<uint4*>(yt + row * 128 + ((c ^ sw) << 4)) = hi;
                     *reinterpret_cast<uint4*>(yt + row * 128 + (((4 + c) ^ sw) << 4)) = lo;
@@ -574,7 +578,8 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
             for (int c = 0; c < 8; ++c) {
                 const float A = ex2_approx(fmaf(__uint_as_float(zs[c]), c_s, lb[c]));
                 const float E = ex2_approx(fminf(fmaf(__uint_as_float(zt[c]), c_t, lb[8 + c]), 43.280851226668903f));
-                const float rinv = rcp_approx((1.f + A) * (1.f + E));
+                const float e1 = 1.f + E;
+                const float rinv = rcp_approx(fmaf(A, e1, e1));              // 1 / ((1 + A)(1 + E))
                 xn[c] = fmaf(fmaf(E, -S16_ACT, S16_ACT), rinv, z[c]);        // 16 (x + gate)
             }
             if (warp == 0 && lane == 0) LP_STAMP(3, n, 5);
