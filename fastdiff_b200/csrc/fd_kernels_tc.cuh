@@ -2391,7 +2391,7 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
 // ---------------------------------------------------------------------------------------------------------
 constexpr int UT_AROWS = 136;                          // input rows m0-1 .. m0+128 (+pad)
 constexpr int UT_ATILE = UT_AROWS * 128;               // 17408 B per piece
-constexpr int UT_PEXTRA = 4096;                        // POUT, r = 4: audio window (128 r + 8 floats) + first conv taps and bias
+constexpr int UT_PEXTRA = 6144;                        // POUT, r = 4: two audio windows (128 r + 8 floats each) + first conv taps and bias
 template <int R> constexpr int ut_smem_bytes() { return 2 * UT_ATILE + 2 * R * 8192 + 256 + 64 + 1024; }
 
 // POUT (the default path of mode tc_3xf16): the epilogue adds the block's skip (r = 8: rows of the DBlock output; r = 4:
@@ -2424,8 +2424,9 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
     float* b_s = (float*)(wt + 2 * R * 8192);
     uint64_t* bar = (uint64_t*)(b_s + 64);               // [0] MMAs, [1] loads
     uint32_t* tmem_base_s = (uint32_t*)(bar + 2);
-    float* au_s = (float*)(tmem_base_s + 4);             // POUT, r = 4: audio positions r m0 - 4 .. r m0 + 128 r + 3
-    float* pfw_s = au_s + 128 * R + 8;                   // [7][32]
+    float* au_s = (float*)(tmem_base_s + 4);             // POUT, r = 4: [2] audio positions r m0 - 4 .. r m0 + 128 r + 3 (bulk-copied one tile ahead)
+    constexpr int AUW = 128 * R + 8;
+    float* pfw_s = au_s + 2 * AUW;                       // [7][32]
     float* pfb_s = pfw_s + 7 * C;                        // [32]
     constexpr uint32_t NCOLS = R * 64;
 
@@ -2454,26 +2455,32 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
     constexpr uint32_t idesc32 = umma_idesc_tf32(128, 32), idesc64 = umma_idesc_tf32(128, 64);
 
     const int ntt = (Tin + 127) / 128, total = B * ntt;
-    auto issue_rows = [&](int tile) {
+    auto issue_rows = [&](int tile, uint32_t buf) {
         const int b = tile / ntt, m0 = (tile % ntt) * 128;
         const int ar0 = m0 == 0 ? 1 : 0, ar1 = min(130, Tin - m0 + 1);   // rows inside [0, Tin)
         const uint32_t bytes = (uint32_t)(ar1 - ar0) * 128u;
-        mbar_expect_tx(&bar[1], bytes);
+        // POUT, r = 4: the audio window of the tile's outputs rides on the same barrier (positions inside [0, Tout): whole 16-byte groups)
+        const int i0 = m0 == 0 ? 4 : 0, i1 = min(AUW, R * (Tin - m0) + 4);
+        const uint32_t abytes = (POUT && R == 4) ? (uint32_t)(i1 - i0) * 4u : 0u;
+        mbar_expect_tx(&bar[1], bytes + abytes);
         bulk_g2s(a_lo + ar0 * 128, in + ((size_t)b * Tin + (m0 - 1 + ar0)) * C, bytes, &bar[1]);
+        if (POUT && R == 4) bulk_g2s(au_s + buf * AUW + i0, po.skip + (size_t)b * Tin * R + (R * m0 - 4 + i0), abytes, &bar[1]);
     };
     int tile = blockIdx.x;
-    if (tile < total && gw_u == 0) { if (elect_one()) issue_rows(tile); __syncwarp(); }
+    if (tile < total && gw_u == 0) { if (elect_one()) issue_rows(tile, 0u); __syncwarp(); }
     uint32_t parity = 0;
     [[maybe_unused]] int tl_n = 0;
     for (; tile < total; tile += gridDim.x, parity ^= 1, ++tl_n) {
         const int b = tile / ntt, m0 = (tile % ntt) * 128;
         UT_STAMP(0);
-        if (POUT && R == 4) {   // audio window of this tile's outputs (zero outside the utterance); read by the epilogue, after two barriers
+        const float* au_t = au_s + parity * AUW;   // this tile's window (buffer = tile parity)
+        if (POUT && R == 4) {   // positions outside the utterance are zero (the first conv zero-pads): utterance ends only; the copy never touches them
             const int Tout = Tin * R;
-            for (int i = tid; i < 128 * R + 8; i += 512) {
-                const int pos = R * m0 - 4 + i;
-                au_s[i] = (pos >= 0 && pos < Tout) ? po.skip[(size_t)b * Tout + pos] : 0.f;
-            }
+            if (m0 == 0 || R * m0 + AUW - 4 > Tout)
+                for (int i = tid; i < AUW; i += 512) {
+                    const int pos = R * m0 - 4 + i;
+                    if (pos < 0 || pos >= Tout) au_s[parity * AUW + i] = 0.f;
+                }
         }
         mbar_wait(&bar[1], parity);
         UT_STAMP(1);
@@ -2532,7 +2539,7 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
         mbar_wait(&bar[0], parity);
         UT_STAMP(4);
         tc_fence_after();
-        if (gw_u == 0 && tile + (int)gridDim.x < total) { if (elect_one()) issue_rows(tile + gridDim.x); __syncwarp(); }   // tile is free
+        if (gw_u == 0 && tile + (int)gridDim.x < total) { if (elect_one()) issue_rows(tile + gridDim.x, parity ^ 1u); __syncwarp(); }   // tile is free
         {   // epilogue: thread = (input row m, 8 channels); its r outputs are consecutive rows r m + ph
             const int q = gw & 3, part = gw >> 2, m = m0 + q * 32 + lane;
             const float* bb = b_s + part * 8;
@@ -2559,7 +2566,7 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
                             sk[0] = b0.x; sk[1] = b0.y; sk[2] = b0.z; sk[3] = b0.w; sk[4] = b1.x; sk[5] = b1.y; sk[6] = b1.z; sk[7] = b1.w;
 #pragma unroll
                             for (int k = 0; k < 7; ++k) {
-                                const float x = au_s[t - R * m0 + 1 + k];   // audio position t + k - 3
+                                const float x = au_t[t - R * m0 + 1 + k];   // audio position t + k - 3
                                 const float4 w0 = *reinterpret_cast<const float4*>(pfw_s + k * C + part * 8), w1 = *reinterpret_cast<const float4*>(pfw_s + k * C + part * 8 + 4);
                                 sk[0] = fmaf(w0.x, x, sk[0]); sk[1] = fmaf(w0.y, x, sk[1]); sk[2] = fmaf(w0.z, x, sk[2]); sk[3] = fmaf(w0.w, x, sk[3]);
                                 sk[4] = fmaf(w1.x, x, sk[4]); sk[5] = fmaf(w1.y, x, sk[5]); sk[6] = fmaf(w1.z, x, sk[6]); sk[7] = fmaf(w1.w, x, sk[7]);
