@@ -748,7 +748,14 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     float* rec0 = kern + ((long long)bbc * Tm + fpc - 1) * KCN;           // record of row 0 (never dereferenced when row 0 is a pad row)
                     // rows before the gap: record row0 + j; rows after it: row0 + j - 2 -- two base pointers, constant offsets, uniform predicates
                     const int ja = j1 < jhi ? j1 : jhi;        // rows [jlo, ja) via base A; rows (j1 + 1, jhi) via base B
-                    if (as_pieces) {
+                    // most sub-chunks of a gap span have no gap INSIDE: all 32 rows on one base -> the straight store sequence
+                    const bool all_a = jlo == 0 && j1 >= 32 && jhi >= 32, all_b = j1 + 1 < 0 && jhi >= 32;
+                    if (as_pieces && (all_a || all_b)) {
+                        uint16_t* ph1 = reinterpret_cast<uint16_t*>(rec0) + hw_hi - (all_b ? 4 * KCN : 0);
+                        uint16_t* pl1 = reinterpret_cast<uint16_t*>(rec0) + hw_lo - (all_b ? 4 * KCN : 0);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) put_pieces(ph1 + (size_t)j * (2 * KCN), pl1 + (size_t)j * (2 * KCN), __uint_as_float(v[j]));
+                    } else if (as_pieces) {
                         uint16_t* pha = reinterpret_cast<uint16_t*>(rec0) + hw_hi;
                         uint16_t* pla = reinterpret_cast<uint16_t*>(rec0) + hw_lo;
                         uint16_t* phb = pha - 4 * KCN;
