@@ -594,13 +594,22 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
         const int cpart = (warp - 2) >> 2;
         uint32_t acc = 0, acc_phase = 0;
         [[maybe_unused]] int it_no = 0;
+        // the bias of the NEXT item is loaded one item ahead: a dependent global load at the top of every item (~1,000 of the ~7,000 cycles an
+        // item's epilogue took) sat between the accumulator hand-over and the first store (round-2 GEMM timeline)
+        auto bias_of = [&](int item) -> float {
+            if (item >= total_items) return 0.f;
+            const int blk = item / items_per_blk, nt = ((item % items_per_blk) % n_pairs) * 2 + (int)rank;
+            const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
+            return bias[nt * 128 + q * 32 + lane];
+        };
+        float bv_next = bias_of(pair_id);
         for (int item = pair_id; item < total_items; item += n_clusters, ++it_no) {
             const int blk = item / items_per_blk, r = item % items_per_blk;
             const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
             const int n = nt * 128 + q * 32 + lane;
             if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 0);
-            const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
-            const float bv = bias[n];
+            const float bv = bv_next;
+            bv_next = bias_of(item + n_clusters);
             const float inv = F16 ? (blk == 0 ? inv0 : (blk == 1 ? inv1 : inv2)) : 1.f;
             float* kern = kern_all + (size_t)blk * B * Tm * KCN;
             // F16, blocks 1 and 2 (tensor-core LVC consumers): the predicted kernel w is written as fp16 pieces of w*S16_KERN straight
