@@ -656,6 +656,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
 
     // -- first_audio_conv + the three DiffusionDBlocks: independent of the kernel-predictor path, so they run on the side stream
     //    (forked here, joined before the first LVC block) unless a debugging stop or the option "overlap" = 0 asks for serial order
+    bool up0_done = false;
     auto run_dblocks = [&](cudaStream_t sd) -> int {
         DbParams p;
         p.first_w = sec(h, FD_S_FIRST_W); p.first_b = sec(h, FD_S_FIRST_B);
@@ -686,7 +687,16 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             else        { auto k = k_dblock<8, false>; FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<8>(), sd, p, ins[n], outs[n], tin[n], tout[n]); }
             FD_CHECK_LAUNCH(h, "k_dblock");
         }
-            return FD_OK;
+        // LVC block 0's upsampling reads the last DBlock output only: it rides on the same stream (off the critical path when the chain is
+        // forked to the side stream: embed -> kernel predictor -> GEMM take longer than DBlocks + this launch)
+        if (h->stop_after > 2) {
+            ScopedTimer tm(h, KC_UPSAMPLE, sd);
+            auto k = k_upsample<8>;
+            FD_LAUNCH(k, dim3((Tm + 31) / 32, B), dim3(256), 0, sd, sec(h, FD_S_LB0_UP_W), sec(h, FD_S_LB0_UP_B), d2, xa, Tm);
+            FD_CHECK_LAUNCH(h, "k_upsample");
+            up0_done = true;
+        }
+        return FD_OK;
     };
     bool forked = false;
 #ifndef FD_EMU
@@ -830,6 +840,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
                 up_done = true;
             }
 #endif
+            if (n == 0 && up0_done) up_done = true;   // launched with the DBlock chain
             if (!up_done) {
                 if (r == 8) { auto k = k_upsample<8>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
                 else        { auto k = k_upsample<4>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
