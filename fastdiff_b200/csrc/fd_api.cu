@@ -41,6 +41,7 @@ struct fd_handle {
     int graphs = 1;              // fd_sample in device-noise mode: capture the whole call (all N <= 64 steps) in a CUDA graph on first use and
                                  // replay it afterwards (option "graphs"; the workspace, shapes, schedule and options are the cache key)
     uint64_t epoch = 0;          // bumped by everything that changes what a captured graph would do (mode, options, weights, noise window)
+    int up4 = 1;                 // piece-row path: block 2 upsampling + skip by k_upsample_p4 (option "up4", 0 = k_upsample_tc<4, true>)
     int lvc_p = 1;               // mode tc_3xf16: LVC blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>; option "lvc_p", 0 = k_lvc_layer_h)
     unsigned int* sat_flag = nullptr;   // device word, sticky: an fp16 piece saturated in a tensor-core kernel (fd_check_saturation)
     int overlap = 1;             // run the DBlock chain on an internal side stream, concurrently with embed -> kernel predictor -> GEMM
@@ -346,6 +347,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "b0_prefetch")) { h->b0_prefetch = (int)value; return FD_OK; }
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "lvc_p")) { h->lvc_p = (int)value; return FD_OK; }
+    if (!strcmp(key, "up4")) { h->up4 = (int)value; return FD_OK; }
     if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
@@ -607,6 +609,16 @@ static int emu_upsample_p(fd_handle* h, int blk, const float* in, const float* s
     FD_CHECK_LAUNCH(h, "k_upsample_tc<POUT>");
     return FD_OK;
 }
+static int emu_upsample_p4(fd_handle* h, const float* in, const float* audio, float* p_out, int B, int Tin, cudaStream_t st) {
+    Up4Params p;
+    p.w16 = sec(h, FD_S_LB2_UP_F16M); p.first16u = sec(h, FD_S_FIRST_F16U); p.bias = sec(h, FD_S_LB0_UP_B + 2 * FD_LB_STRIDE);
+    p.in = in; p.audio = audio; p.p_out = p_out; p.sat = h->sat_flag; p.B = B; p.Tin = Tin;
+    p.inv = 1.f / (S16_ACT * emu_scale16(h, 41));
+    const int total = B * ((Tin + 127) / 128);
+    FD_LAUNCH(k_upsample_p4, dim3(total < 6 ? total : 6), dim3(512), U4_SMEM_BYTES, st, p);
+    FD_CHECK_LAUNCH(h, "k_upsample_p4");
+    return FD_OK;
+}
 static int emu_lvc_p_layer(fd_handle* h, int blk, int layer, const float* p_in, const float* skip, const float* kern, float* p_out, float* f_out,
                            int B, int T, int Tm, int dil, cudaStream_t st) {
     LvcPParams p;
@@ -814,11 +826,12 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             ScopedTimer tm(h, KC_UPSAMPLE, st);
 #ifdef FD_EMU
             int rc = emu_zero_pads(h, cur, B, T, st);
-            if (!rc) rc = emu_upsample_p(h, n, blk_in, skip, cur, B, Tin, st);
+            if (!rc) rc = (n == 2 && h->up4) ? emu_upsample_p4(h, blk_in, skip, cur, B, Tin, st) : emu_upsample_p(h, n, blk_in, skip, cur, B, Tin, st);
             if (!rc) rc = emu_zero_pads(h, oth, B, T, st);
 #else
             int rc = tc_zero_pads(cur, B, T, st, h->err, &h->launches);
-            if (!rc) rc = tc_upsample_p(h->tc_state, n, blk_in, skip, cur, h->sat_flag, B, Tin, st, h->err, &h->launches);
+            if (!rc) rc = (n == 2 && h->up4) ? tc_upsample_p4(h->tc_state, blk_in, skip, cur, h->sat_flag, B, Tin, st, h->err, &h->launches)
+                                             : tc_upsample_p(h->tc_state, n, blk_in, skip, cur, h->sat_flag, B, Tin, st, h->err, &h->launches);
             if (!rc) rc = tc_zero_pads(oth, B, T, st, h->err, &h->launches);
 #endif
             if (rc) return rc;

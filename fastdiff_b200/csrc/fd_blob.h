@@ -51,13 +51,19 @@
  *             T01 [64 rows x 128 B]: row R = piece * 32 + co = [tap 0: 32 ci | tap 1: 32 ci] of that piece (hi rows, then lo rows), chunk c at c ^ (R & 7):
  *                 ONE N = 64 MMA per activation piece and K-slice forms the hi- and the lo-weight products of taps 0 and 1;
  *             T2  [32 rows x 128 B]: row co = [32 ci hi | 32 ci lo] of tap 2, chunk c at c ^ (co & 7) (three-pass form)
+ *   LB2_UP_F16M [4 phases][64 rows][128 B] (k_upsample_p4): lvc_blocks.2.upsample (ConvTranspose1d weight (ci, co, k), k = 8, stride 4) as merged-N
+ *             SWIZZLE_128B tiles per output phase ph (t = 4 m + ph; taps kk1 = (ph + 2) % 4 on input m + (ph + 2) / 4 and kk1 + 4 on the row before):
+ *             row R = piece * 32 + co = [tap kk1: 32 ci | tap kk1 + 4: 32 ci] of that piece, chunk c at c ^ (R & 7); scale SCALES16[41]
+ *   FIRST_F16U [128 rows = ph * 32 + co][64 B] (k_upsample_p4): first_audio_conv as four Toeplitz tiles over the audio window a_m = audio[4 m - 3 .. 4 m + 6]:
+ *             K = 16 values W_ph[i] = first_w[co][i - ph] (0 <= i - ph <= 6), W_ph[10] = first_b[co], else 0; 32 B hi pieces | 32 B lo pieces; scale SCALES16[41]
+ *             (SCALES16[41] = the smaller of the two tensors' own scales, so that both products accumulate into one TMEM tile)
  *   LBn_KPW_F16 [28 slots][16 KB]  kernel-predictor hidden stack as B-operand tiles in consumption order (tensor-core k_kp_hidden_tc):
  *             a tile = 64 rows (co) x 128 B, 16-byte chunk c at position c ^ (co & 7).
  *             slots 0..9  : input_conv taps j = 0..4, two slots per tap: {ci 0..63: hi tile 8 KB | lo tile 8 KB},
  *                           {ci 64..79: one tile with rows [16 ci hi (32 B) | 16 ci lo (32 B) | 64 B zero], then 8 KB unused}
  *             slots 10..27: residual convs l = 0..5, taps j = 0..2: {hi tile 8 KB | lo tile 8 KB} over the 64 input channels
  *   SCALES16  [64]  S of: kernel_conv block n at [n]; lvc_blocks.n.convs.l at [4 + 4 n + l];
- *                   kernel predictor of block n: input_conv at [16 + 8 n], residual conv l at [17 + 8 n + l]; FIRST_F16 at [40]
+ *                   kernel predictor of block n: input_conv at [16 + 8 n], residual conv l at [17 + 8 n + l]; FIRST_F16 at [40]; LB2_UP_F16M and FIRST_F16U at [41]
  *   FIRST_F16 [32 co][128 B]  first_audio_conv as the B operand of the skip MMA of LVC block 2 (fd_kernels_lvcp.cuh): per output channel
  *                   K = 16 fp16 [tap 0..6, bias, 0 x 8] hi (chunks 0, 1) | the same lo (chunks 2, 3) | zeros; 16-byte chunk c at c ^ (co & 7)
  */
@@ -65,7 +71,7 @@
 #define FD_BLOB_H
 
 #define FD_BLOB_MAGIC 0x3142303032444646ULL /* "FFD200B1" */
-#define FD_BLOB_VERSION 14ULL
+#define FD_BLOB_VERSION 15ULL
 
 /* The packer reads the names between FD_SECTIONS_BEGIN / FD_SECTIONS_END in this order. */
 /* FD_SECTIONS_BEGIN */
@@ -84,7 +90,7 @@
     X(DB0_CONVT_HI) X(DB0_CONVT_LO) X(DB0_REST_HI) X(DB0_REST_LO) \
     X(LB1_UPT_HI) X(LB1_UPT_LO) X(LB2_UPT_HI) X(LB2_UPT_LO) \
     X(LB0_KCT_F16) X(LB1_KCT_F16) X(LB2_KCT_F16) X(LB1_CONV_F16) X(LB2_CONV_F16) \
-    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(LB0_CONV_F16) X(LB0_KCT_F16P) X(LB0_KC_BP) X(FIRST_F16) X(LB1_CONV_F16M) X(LB2_CONV_F16M) X(SCALES16)
+    X(LB0_KPW_F16) X(LB1_KPW_F16) X(LB2_KPW_F16) X(LB0_CONV_F16) X(LB0_KCT_F16P) X(LB0_KC_BP) X(FIRST_F16) X(LB1_CONV_F16M) X(LB2_CONV_F16M) X(LB2_UP_F16M) X(FIRST_F16U) X(SCALES16)
 /* FD_SECTIONS_END */
 
 enum fd_section {

@@ -1956,6 +1956,7 @@ k_lvc_layer_h(LvcHParams p, const float* __restrict__ x_in, const float* __restr
 }  // namespace fd
 #include "fd_kernels_lvc_b0.cuh"   // k_lvc_layer_b0h: LVC block 0 (hop 8) in swapped-operand form
 #include "fd_kernels_lvcp.cuh"     // k_lvc_p: LVC layers of blocks 1, 2 on the default path (piece-row protocol, warp-specialised pipeline)
+#include "fd_kernels_up4.cuh"      // k_upsample_p4: block 2 upsampling + skip on kind::f16 pieces (default path)
 namespace fd {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -2793,6 +2794,26 @@ static inline int tc_upsample_p(void* state, int blk, const float* in, const flo
     return 0;
 }
 
+// block 2 upsampling + skip on kind::f16 pieces (k_upsample_p4, fd_kernels_up4.cuh)
+static inline int tc_upsample_p4(void* state, const float* in, const float* audio, float* p_out, unsigned int* sat, int B, int Tin,
+                                 cudaStream_t st, std::string& err, uint64_t* launches) {
+    TcState* s = (TcState*)state;
+    if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
+    Up4Params p;
+    p.w16 = s->blob + s->sec_off[FD_S_LB2_UP_F16M];
+    p.first16u = s->blob + s->sec_off[FD_S_FIRST_F16U];
+    p.bias = s->blob + s->sec_off[FD_S_LB0_UP_B + 2 * FD_LB_STRIDE];
+    p.in = in; p.audio = audio; p.p_out = p_out; p.sat = sat; p.B = B; p.Tin = Tin;
+    p.inv = 1.f / (S16_ACT * s->scales16[41]);
+    const int total = B * ((Tin + 127) / 128);
+    const int grid = total < 2 * s->sm_count ? total : 2 * s->sm_count;
+    k_upsample_p4<<<grid, 512, U4_SMEM_BYTES, st>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("launch of k_upsample_p4 failed: ") + cudaGetErrorString(e); return -3; }
+    ++*launches;
+    return 0;
+}
+
 // one LVC layer of block 1 / 2: piece rows in -> piece rows out (p_out) or fp32 rows out (f_out, last layer of the block)
 static inline int tc_lvc_p_layer(void* state, int blk, int layer, const float* p_in, const float* skip, const float* kern, float* p_out,
                                  float* f_out, unsigned int* sat, int B, int T, int Tm, int dil, cudaStream_t st, std::string& err, uint64_t* launches) {
@@ -2839,6 +2860,8 @@ static inline cudaError_t tc_set_lvc_attrs() {
     e0 = cudaFuncSetAttribute(k_upsample_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<4>());
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_upsample_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<8>());
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_upsample_p4, cudaFuncAttributeMaxDynamicSharedMemorySize, U4_SMEM_BYTES);
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_upsample_tc<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<4>() + UT_PEXTRA);
     if (e0 != cudaSuccess) return e0;

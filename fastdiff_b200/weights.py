@@ -282,6 +282,30 @@ def build_sections(sd: Mapping[str, torch.Tensor]) -> Dict[str, np.ndarray]:
                 for c in range(8):
                     img[l, 64 + co, c ^ (co & 7)] = row[c]
         S[f"LB{n}_CONV_F16M"] = _u16_as_f32(img)
+    # k_upsample_p4 (block 2 upsampling + skip on kind::f16 pieces): both weight tensors at ONE power-of-two scale
+    uw2 = W["lvc_blocks.2.upsample.weight"].numpy()                                      # (ci, co, k = 8)
+    fwb = np.zeros((C, 11), dtype=np.float32)
+    fwb[:, :7] = W["first_audio_conv.weight"][:, 0, :].numpy()
+    fwb[:, 10] = W["first_audio_conv.bias"].numpy()
+    sc = min(f16_scale(uw2), f16_scale(fwb))
+    scales[41] = sc
+    hi, lo = f16_split(uw2, sc)                                                          # [ci][co][k]
+    up_img = np.zeros((4, 2 * C, 8, 8), dtype=np.uint16)                                 # [ph][row][chunk position][8 fp16]
+    for ph in range(4):
+        kk1 = (ph + 2) % 4
+        for piece, src in ((0, hi), (1, lo)):
+            for co in range(C):
+                r = piece * C + co
+                row = np.concatenate([src[:, co, kk1], src[:, co, kk1 + 4]]).reshape(8, 8)   # chunks 0-3: tap kk1 (32 ci), 4-7: tap kk1 + 4
+                for c in range(8):
+                    up_img[ph, r, c ^ (r & 7)] = row[c]
+    S["LB2_UP_F16M"] = _u16_as_f32(up_img)
+    toep = np.zeros((4, C, 16), dtype=np.float32)
+    for ph in range(4):
+        toep[ph, :, ph:ph + 7] = fwb[:, :7]
+        toep[ph, :, 10] = fwb[:, 10]
+    hi, lo = f16_split(toep, sc)
+    S["FIRST_F16U"] = _u16_as_f32(np.concatenate([hi, lo], axis=2).reshape(4 * C, 32))   # row ph * 32 + co: 16 hi | 16 lo
     S["SCALES16"] = torch.from_numpy(scales)
     assert list(S.keys()) == SECTION_NAMES, "packer sections out of sync with fd_blob.h"
     return {k: v.detach().to(torch.float32).contiguous().numpy().reshape(-1) for k, v in S.items()}

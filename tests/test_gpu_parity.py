@@ -110,6 +110,31 @@ def test_tensor_core_mode_vs_oracle(synth, cuda_lib, B, Tm, mode):
 
 
 @gpu
+@pytest.mark.parametrize("B,Tm", [(3, 35), (3, 61), (2, 62), (2, 63), (3, 64), (2, 126), (4, 130)])
+def test_kernel_conv_gemm_utterance_boundaries(synth, cuda_lib, B, Tm):
+    """The kernel_conv GEMM epilogue at utterance boundaries (k_kc_gemm_tc2, gap path): the pad rows between items fall at every position
+    of a 32-frame sub-chunk over these shapes (first row, last row, across sub-chunks and 64-frame spans, past the end of the tensor).
+    Predicted kernels of all three blocks -- block 0 in the [hi | lo]-row image, blocks 1 / 2 in the merged-N T01 / T2 image -- and their
+    biases against the oracle, and eps."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    x, mel = make_inputs(B, Tm, 11)
+    t = torch.tensor([7.413235, 498.0537, 74.99228, 23.46759][:B]).reshape(B, 1)
+    eps_ref, inter = O.denoise(W, x, mel, t, return_intermediates=True)
+    net = _net(sd, "tc_3xf16")
+    eng = net.engine()
+    eps = net((x.cuda(), mel.cuda(), t.cuda())).cpu()
+    assert (eps - eps_ref).abs().max() < EPS_TOL
+    kp = _oracle_stage_refs(O, W, mel, inter)
+    for n in range(3):
+        k = eng.debug_read(f"kernels{n}", B, Tm).cpu().reshape(kp[n][0].shape)
+        b = eng.debug_read(f"kbias{n}", B, Tm).cpu().reshape(kp[n][1].shape)
+        assert (k - kp[n][0]).abs().max() < STAGE_TOL_TC["kernels"], f"kernels{n}"
+        assert (b - kp[n][1]).abs().max() < STAGE_TOL_TC["kbias"], f"kbias{n}"
+
+
+@gpu
 def test_f16_mode_options_and_guards(synth, cuda_lib):
     """tc_3xf16 building blocks: the tensor-core kernel-predictor stack against the FFMA one, the side-stream overlap against the
     serial order (bitwise), the cross_check guard, and saturation (finite output, flagged by cross_check) beyond the fp16 range."""
