@@ -348,6 +348,9 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "lvc_p")) { h->lvc_p = (int)value; return FD_OK; }
     if (!strcmp(key, "up4")) { h->up4 = (int)value; return FD_OK; }
+#ifndef FD_EMU
+    if (!strcmp(key, "pdl")) { g_fd_pdl = value ? 1 : 0; return FD_OK; }   // programmatic dependent launch of the step's kernels (process-wide)
+#endif
     if (!strcmp(key, "emu_gemm_tc")) { h->emu_gemm_tc = (int)value; return FD_OK; }
     if (!strcmp(key, "emb_slots")) {
         if (value < 1 || value > EMB_SLOTS) return fail(h, FD_ERR_INVALID, "fd_set_option: emb_slots must be in [1, %d]", EMB_SLOTS);
@@ -650,7 +653,7 @@ static int launch_embed(fd_handle* h, const float* t_dev, const EmbedSteps& ts, 
         p.fct_b[n] = sec(h, FD_S_LB0_FCT_B + n * FD_LB_STRIDE);
     }
     ScopedTimer tm(h, KC_EMBED, st);
-    FD_LAUNCH(k_embed, dim3(B, nslots), dim3(512), 0, st, p, t_dev, ts, ws + w.emb, ws + w.cnoise, B);
+    FD_LAUNCH_PDL(k_embed, dim3(B, nslots), dim3(512), 0, st, p, t_dev, ts, ws + w.emb, ws + w.cnoise, B);
     FD_CHECK_LAUNCH(h, "k_embed");
     return FD_OK;
 }
@@ -695,8 +698,8 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
             }
 #endif
             if (done_tc) continue;
-            if (n == 0) { auto k = k_dblock<4, true>;  FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<4>(), sd, p, ins[n], outs[n], tin[n], tout[n]); }
-            else        { auto k = k_dblock<8, false>; FD_LAUNCH(k, grid, dim3(256), db_smem_bytes<8>(), sd, p, ins[n], outs[n], tin[n], tout[n]); }
+            if (n == 0) { auto k = k_dblock<4, true>;  FD_LAUNCH_PDL(k, grid, dim3(256), db_smem_bytes<4>(), sd, p, ins[n], outs[n], tin[n], tout[n]); }
+            else        { auto k = k_dblock<8, false>; FD_LAUNCH_PDL(k, grid, dim3(256), db_smem_bytes<8>(), sd, p, ins[n], outs[n], tin[n], tout[n]); }
             FD_CHECK_LAUNCH(h, "k_dblock");
         }
         // LVC block 0's upsampling reads the last DBlock output only: it rides on the same stream (off the critical path when the chain is
@@ -704,7 +707,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
         if (h->stop_after > 2) {
             ScopedTimer tm(h, KC_UPSAMPLE, sd);
             auto k = k_upsample<8>;
-            FD_LAUNCH(k, dim3((Tm + 31) / 32, B), dim3(256), 0, sd, sec(h, FD_S_LB0_UP_W), sec(h, FD_S_LB0_UP_B), d2, xa, Tm);
+            FD_LAUNCH_PDL(k, dim3((Tm + 31) / 32, B), dim3(256), 0, sd, sec(h, FD_S_LB0_UP_W), sec(h, FD_S_LB0_UP_B), d2, xa, Tm);
             FD_CHECK_LAUNCH(h, "k_upsample");
             up0_done = true;
         }
@@ -855,8 +858,8 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
 #endif
             if (n == 0 && up0_done) up_done = true;   // launched with the DBlock chain
             if (!up_done) {
-                if (r == 8) { auto k = k_upsample<8>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
-                else        { auto k = k_upsample<4>; FD_LAUNCH(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
+                if (r == 8) { auto k = k_upsample<8>; FD_LAUNCH_PDL(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
+                else        { auto k = k_upsample<4>; FD_LAUNCH_PDL(k, grid, dim3(256), 0, st, upw, upb, blk_in, cur, Tin); }
                 FD_CHECK_LAUNCH(h, "k_upsample");
             }
         }
@@ -967,7 +970,7 @@ extern "C" int fd_denoise(fd_handle* h, const float* x_dev, const float* mel_dev
     const int L = Tm * HOP_TOTAL;
     {
         ScopedTimer tm(h, KC_FINAL, st);
-        FD_LAUNCH(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), x_dev, (const float*)nullptr, eps_dev, (float*)nullptr, L);
+        FD_LAUNCH_PDL(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), x_dev, (const float*)nullptr, eps_dev, (float*)nullptr, L);
         FD_CHECK_LAUNCH(h, "k_final");
     }
     return FD_OK;
@@ -985,7 +988,7 @@ static int sample_body(fd_handle* h, float* x_dev, const float* mel_dev, const f
     NoiseWin win; win.win_L = h->noise_win_L; win.win_off = h->noise_win_off;
     if (fill_xT) {
         ScopedTimer tm(h, KC_FILL, st);
-        FD_LAUNCH(k_fill_normal, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x_dev, L, n, seed, 0u, win, seed_ptr);
+        FD_LAUNCH_PDL(k_fill_normal, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x_dev, L, n, seed, 0u, win, seed_ptr);
         FD_CHECK_LAUNCH(h, "k_fill_normal");
     }
     if (seq_dev) FD_CUDA(h, cudaMemcpyAsync(seq_dev, x_dev, n * 4, cudaMemcpyDeviceToDevice, st));
@@ -1017,7 +1020,7 @@ static int sample_body(fd_handle* h, float* x_dev, const float* mel_dev, const f
         }
         // in-place: every thread reads only its own x element
         ScopedTimer tm(h, KC_FINAL, st);
-        FD_LAUNCH(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), (const float*)x_dev, z, x_dev,
+        FD_LAUNCH_PDL(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), (const float*)x_dev, z, x_dev,
                   seq_dev ? seq_dev + (size_t)(i + 1) * n : (float*)nullptr, L);
         FD_CHECK_LAUNCH(h, "k_final");
     }

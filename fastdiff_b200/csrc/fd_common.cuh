@@ -9,10 +9,36 @@
 
 #ifdef FD_EMU
 #include "cudaemu.h"
+#define FD_LAUNCH_PDL FD_LAUNCH
+namespace fd { inline void pdl_wait() {} inline void pdl_trigger() {} }
 #else
 #include <cuda_runtime.h>
 #define FD_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define FD_DYN_SMEM(type, name) extern __shared__ __align__(1024) unsigned char name##_raw_[]; type* name = reinterpret_cast<type*>(name##_raw_)
+// Programmatic dependent launch: the kernels of a reverse step form one dependent chain of ~25 launches, each with a prologue that touches
+// no data of its predecessor (barrier init, TMEM allocation, weight images into shared memory) and a tail in which most SMs idle.  Launched
+// with the programmatic-serialization attribute, a kernel's CTAs are scheduled as soon as its predecessor's CTAs have all called
+// pdl_trigger() (their first statement) and leave SM resources free; they run their prologue and then block in pdl_wait() until the
+// predecessor has completed and flushed.  RULES: every kernel launched through FD_LAUNCH_PDL calls pdl_wait() before its first access
+// to data another kernel writes or reads-then-overwrites, and writes nothing but shared memory / TMEM before it.
+namespace fd {
+static int g_fd_pdl = 0;   // fd_set_option("pdl", 1) sets the attribute.  OFF by default: measured on B200 (round 2, graph replay of the N=4 call)
+                           // 1 s utterance 1.122 ms with / 1.052 ms without, config 2 9.80 / 9.70 ms -- the hand-over of a programmatic edge costs more
+                           // than the overlapped prologues save (griddepcontrol.* are no-ops without the attribute)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t fd_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_fd_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+}
+#define FD_LAUNCH_PDL(kern, grid, block, smem, stream, ...) fd::fd_launch_pdl(kern, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)
 #endif
 
 #include <stdint.h>

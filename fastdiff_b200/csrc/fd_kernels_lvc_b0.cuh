@@ -28,6 +28,8 @@ constexpr int LB0_SMEM_BYTES = 2 * LH_A_BYTES + 16384 + LH_CW_BYTES + LB0_NSLOT 
 __global__ void __launch_bounds__(512, 1)
 k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __restrict__ skip, const float* __restrict__ kern,
                 float* __restrict__ x_out, int B, int T, int Tm, int dil, float inv_c, float inv_l, int skip_in_rt, int skip_out_rt) {
+    pdl_trigger();
+
     const bool skip_in = skip_in_rt != 0, skip_out = skip_out_rt != 0;
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -59,6 +61,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
     tc_fence_after();
     // TMEM columns: conv [0,32), second conv pass [32,64), LVC pair p at [64 + 16 p, +16)
     const uint32_t tmem_base = *tmem_base_s;
+    pdl_wait();   // programmatic dependent launch: everything above touched constants, shared memory and TMEM only
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_u = smem_u32(smem);
     constexpr uint32_t idesc_conv = umma_idesc_f16(128, 32), idesc_lvc = umma_idesc_f16(128, 16);

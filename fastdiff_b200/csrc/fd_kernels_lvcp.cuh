@@ -85,6 +85,8 @@ struct LvcPParams {
 
 // zero rows of a padded piece buffer: block 0 -> the 32 head rows, block i >= 1 -> the 64 rows after item i - 1
 __global__ void __launch_bounds__(256) k_zero_pads(float* __restrict__ buf, int B, int T) {
+    pdl_trigger();
+    pdl_wait();
     const int i = blockIdx.x;
     const size_t row0 = i == 0 ? 0 : (size_t)LP_HEAD_ROWS + (size_t)(i - 1) * (T + LP_PAD_ROWS) + T;
     const int nrows = i == 0 ? LP_HEAD_ROWS : LP_PAD_ROWS;
@@ -105,6 +107,8 @@ __device__ __forceinline__ void lp_split8(const float (&v)[8], uint4& hi, uint4&
 
 template <int HOP>
 __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
+    pdl_trigger();
+
     constexpr int NF = lp_nf<HOP>();
     constexpr bool STAGE_OUT = (HOP == 256);
     constexpr int NA = lp_na<HOP>();
@@ -166,6 +170,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pdl_wait();   // programmatic dependent launch: everything above touched constants, shared memory and TMEM only
     const int B = p.B, T = p.T, Tm = p.Tm, dil = p.dil;
     const int ntt = (T + LP_TT - 1) / LP_TT, total = B * ntt;
     const int chunk = (total + (int)gridDim.x - 1) / (int)gridDim.x;

@@ -28,6 +28,8 @@ struct EmbedSteps { float t[EMB_SLOTS]; };
 
 __global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __restrict__ t_dev, EmbedSteps ts,
                                                float* __restrict__ emb_all, float* __restrict__ cnoise_all, int B) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float s_in[EMB_IN];
     __shared__ float s_mid[EMB_MID];
     __shared__ float s_out[EMB_OUT];
@@ -329,6 +331,8 @@ constexpr int db_smem_bytes() { return (2 * DB_ROWS * C + DB_TO * C + 3 * KK * C
 template <int F, bool FIRST>
 __global__ void __launch_bounds__(256) k_dblock(DbParams p, const float* __restrict__ in, float* __restrict__ out,
                                                 int Tin, int To) {
+    pdl_trigger();
+    pdl_wait();
     FD_DYN_SMEM(float, sm);
     float* sa = sm;                      // [DB_ROWS][32], row index = r + DB_PAD
     float* sb = sa + DB_ROWS * C;
@@ -425,6 +429,8 @@ __global__ void __launch_bounds__(256) k_dblock(DbParams p, const float* __restr
 template <int R>
 __global__ void __launch_bounds__(256) k_upsample(const float* __restrict__ w, const float* __restrict__ bias,
                                                   const float* __restrict__ in, float* __restrict__ out, int Tin) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int TI = 32;
     __shared__ __align__(16) float in_s[(TI + 2) * C];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -690,6 +696,8 @@ __device__ __forceinline__ size_t noise_elem(const NoiseWin w, int b, int L, int
 }
 __global__ void __launch_bounds__(256) k_fill_normal(float* __restrict__ out, int L, size_t n, uint64_t seed, uint32_t draw, NoiseWin win,
                                                      const unsigned long long* __restrict__ seed_ptr) {
+    pdl_trigger();
+    pdl_wait();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i < n) out[i] = philox_normal(noise_elem(win, (int)(i / L), L, (int)(i % L)), draw, seed_ptr ? (uint64_t)*seed_ptr : seed);
 }
@@ -721,6 +729,8 @@ struct FinalParams {
 __global__ void __launch_bounds__(256) k_final(FinalParams p, const float* __restrict__ h, const float* __restrict__ x_t,
                                                const float* __restrict__ z, float* __restrict__ out,
                                                float* __restrict__ seq_out, int L) {
+    pdl_trigger();
+    pdl_wait();
     // h rows t0-3 .. t0+258 staged as float4 chunks, chunk c4 of row r at position c4 ^ (r & 7) (conflict-free both ways).
     // Thread (q = tid/4, cg = tid%4) accumulates the 4 outputs 4q..4q+3 over channels 8cg..8cg+7 from 10 rows (2 LDS.128 per row:
     // 2.8x less shared-memory traffic than one output per thread), the 4 channel-group partials are summed in a fixed order.

@@ -480,6 +480,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
               const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass,
               float inv0, float inv1, float inv2, int exp_mask) {
+    pdl_trigger();
+
     constexpr int NATOM = F16 ? 3 : 6;
     constexpr int CPW = 256 / (EPW / 4);   // frame columns per epilogue warp
     FD_DYN_SMEM(unsigned char, smem_raw);
@@ -513,6 +515,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
     cluster_sync_all();     // barriers of both CTAs initialised and TMEM allocated before any remote access
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pdl_wait();   // programmatic dependent launch: everything above touched constants, shared memory and TMEM only
 
     if (warp == 0) {
         // ================= TMA producer (each CTA loads its own A rows and its half of the frames) =================
@@ -940,10 +943,10 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         for (int n = 0; n < NBLK; ++n) inv[n] = 1.f / (s->scales16[n] * S16_HK);
         if (b0_pieces) {
             maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
-            k_kc_gemm_tc2<true, 16, true><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
+            fd_launch_pdl(k_kc_gemm_tc2<true, 16, true>, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
                                                                       s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp | (kimg ? 64 : 0));
         } else
-        k_kc_gemm_tc2<true, 16><<<2 * clusters, 64 + 32 * 16, KC2_SMEM_BYTES, st>>>(maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
+        fd_launch_pdl(k_kc_gemm_tc2<true, 16>, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
                                                                   s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp | (kimg ? 64 : 0));
         cudaError_t e2 = cudaGetLastError();
         if (e2 != cudaSuccess) { err = std::string("launch of k_kc_gemm_tc2<f16> failed: ") + cudaGetErrorString(e2); return -3; }
@@ -1989,6 +1992,8 @@ struct KpTcParams {
 __global__ void __launch_bounds__(512, 1)
 k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ mel, const float* __restrict__ cnoise,
                float* __restrict__ hk_all, float* __restrict__ hk_hi_all, float* __restrict__ hk_lo_all, int B, int Tm) {
+    pdl_trigger();
+
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     // tiles: 0 = P_hi, 1 = P_lo (cond ch 0..63, then odd layers' output), 2 = Q_hi, 3 = Q_lo (even layers' output), 4 = cond ch 64..79
@@ -2014,6 +2019,7 @@ k_kp_hidden_tc(const __grid_constant__ KpTcParams p, const float* __restrict__ m
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pdl_wait();   // programmatic dependent launch: everything above touched constants, shared memory and TMEM only
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_u = smem_u32(smem);
     constexpr uint32_t idesc = umma_idesc_f16(128, 64);
@@ -2196,6 +2202,8 @@ struct DbTcParams {
 
 __global__ void __launch_bounds__(512, 1)
 k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ out, int B, int L, int To, int three_pass) {
+    pdl_trigger();
+
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* a_tile0 = smem;                                          // two ping-pong tiles, each hi | lo, rows 0..143 (row r at r + 8)
@@ -2234,6 +2242,7 @@ k_dblock0_tc(DbTcParams p, const float* __restrict__ audio, float* __restrict__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pdl_wait();   // programmatic dependent launch: everything above touched constants, shared memory and TMEM only
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0);
     const uint32_t smem_u = smem_u32(smem);
@@ -2433,6 +2442,7 @@ template <int R, bool POUT = false>
 __global__ void __launch_bounds__(512, (R == 4 ? 2 : 1))
 k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, const float* __restrict__ bias,
               const float* __restrict__ in, float* __restrict__ out, int B, int Tin, int three_pass, const UpPOut po = UpPOut()) {
+    pdl_trigger();
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* a_hi = smem;                          // tile row ar <-> input row m0 - 1 + ar
@@ -2466,6 +2476,7 @@ k_upsample_tc(const float* __restrict__ w_hi, const float* __restrict__ w_lo, co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pdl_wait();   // programmatic dependent launch: everything above touched constants, shared memory and TMEM only
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0);
     const uint32_t smem_u = smem_u32(smem);
@@ -2700,7 +2711,7 @@ static inline int tc_lvc_layer_b0(void* state, int layer, const float* x_in, con
     hp.first_w = nullptr; hp.first_b = nullptr;
     const float inv_c = 1.f / (S16_ACT * s->scales16[4 + layer]), inv_l = 1.f / (S16_ACT * S16_KERN);
     const int tiles = B * ((T + LT_TT - 1) / LT_TT), grid = tiles < s->sm_count ? tiles : s->sm_count;
-    k_lvc_layer_b0h<<<grid, 512, LB0_SMEM_BYTES, st>>>(hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, layer == 0 ? 1 : 0, layer < LAYERS - 1 ? 1 : 0);
+    fd_launch_pdl(k_lvc_layer_b0h, dim3(grid), dim3(512), LB0_SMEM_BYTES, st, hp, x_in, skip, kern, x_out, B, T, Tm, dil, inv_c, inv_l, layer == 0 ? 1 : 0, layer < LAYERS - 1 ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_lvc_layer_b0h failed: ") + cudaGetErrorString(e); return -3; }
     ++*launches;
@@ -2741,7 +2752,7 @@ static inline int tc_dblock0(void* state, int mode, const float* audio, float* d
     p.first_w = s->blob + s->sec_off[FD_S_FIRST_W];    p.first_b = s->blob + s->sec_off[FD_S_FIRST_B];
     const int To = L / 4, total = B * ((To + DT_VALID - 1) / DT_VALID);
     const int grid = total < s->sm_count ? total : s->sm_count;
-    k_dblock0_tc<<<grid, 512, DT_SMEM_BYTES, st>>>(p, audio, d0, B, L, To, mode != FD_MODE_TC_TF32 ? 1 : 0);
+    fd_launch_pdl(k_dblock0_tc, dim3(grid), dim3(512), DT_SMEM_BYTES, st, p, audio, d0, B, L, To, mode != FD_MODE_TC_TF32 ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_dblock0_tc failed: ") + cudaGetErrorString(e); return -3; }
     ++*launches;
@@ -2762,7 +2773,7 @@ static inline int tc_kp_hidden(void* state, const float* mel, const float* cnois
     }
     const int total = NBLK * B * ((Tm + KT_VALID - 1) / KT_VALID);
     const int grid = total < s->sm_count ? total : s->sm_count;
-    k_kp_hidden_tc<<<grid, 512, KT_SMEM_BYTES, st>>>(p, mel, cnoise, hk, hk_hi, hk_lo, B, Tm);
+    fd_launch_pdl(k_kp_hidden_tc, dim3(grid), dim3(512), KT_SMEM_BYTES, st, p, mel, cnoise, hk, hk_hi, hk_lo, B, Tm);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_kp_hidden_tc failed: ") + cudaGetErrorString(e); return -3; }
     ++*launches;
@@ -2783,10 +2794,10 @@ static inline int tc_upsample_p(void* state, int blk, const float* in, const flo
     const int total = B * ((Tin + 127) / 128);
     if (blk == 1) {
         const int grid = total < s->sm_count ? total : s->sm_count;
-        k_upsample_tc<8, true><<<grid, 512, ut_smem_bytes<8>() + UT_PEXTRA, st>>>(wh, wl, bias, in, p_out, B, Tin, 1, po);
+        fd_launch_pdl(k_upsample_tc<8, true>, dim3(grid), dim3(512), ut_smem_bytes<8>() + UT_PEXTRA, st, wh, wl, bias, in, p_out, B, Tin, 1, po);
     } else {
         const int grid = total < 2 * s->sm_count ? total : 2 * s->sm_count;
-        k_upsample_tc<4, true><<<grid, 512, ut_smem_bytes<4>() + UT_PEXTRA, st>>>(wh, wl, bias, in, p_out, B, Tin, 1, po);
+        fd_launch_pdl(k_upsample_tc<4, true>, dim3(grid), dim3(512), ut_smem_bytes<4>() + UT_PEXTRA, st, wh, wl, bias, in, p_out, B, Tin, 1, po);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_upsample_tc<POUT> failed: ") + cudaGetErrorString(e); return -3; }
@@ -2807,7 +2818,7 @@ static inline int tc_upsample_p4(void* state, const float* in, const float* audi
     p.inv = 1.f / (S16_ACT * s->scales16[41]);
     const int total = B * ((Tin + 127) / 128);
     const int grid = total < 2 * s->sm_count ? total : 2 * s->sm_count;
-    k_upsample_p4<<<grid, 512, U4_SMEM_BYTES, st>>>(p);
+    fd_launch_pdl(k_upsample_p4, dim3(grid), dim3(512), U4_SMEM_BYTES, st, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_upsample_p4 failed: ") + cudaGetErrorString(e); return -3; }
     ++*launches;
@@ -2830,8 +2841,8 @@ static inline int tc_lvc_p_layer(void* state, int blk, int layer, const float* p
     p.inv_sk = 1.f / (LP_S_AU * s->scales16[40]);
     const int tiles = B * ((T + LP_TT - 1) / LP_TT);
     const int grid = tiles < s->sm_count ? tiles : s->sm_count;
-    if (blk == 1) k_lvc_p<64><<<grid, LP_THREADS, lp_smem_bytes<64>(), st>>>(p);
-    else          k_lvc_p<256><<<grid, LP_THREADS, lp_smem_bytes<256>(), st>>>(p);
+    if (blk == 1) fd_launch_pdl(k_lvc_p<64>, dim3(grid), dim3(LP_THREADS), lp_smem_bytes<64>(), st, p);
+    else          fd_launch_pdl(k_lvc_p<256>, dim3(grid), dim3(LP_THREADS), lp_smem_bytes<256>(), st, p);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_lvc_p failed: ") + cudaGetErrorString(e); return -3; }
     ++*launches;
@@ -2839,7 +2850,7 @@ static inline int tc_lvc_p_layer(void* state, int blk, int layer, const float* p
 }
 
 static inline int tc_zero_pads(float* buf, int B, int T, cudaStream_t st, std::string& err, uint64_t* launches) {
-    k_zero_pads<<<B + 1, 256, 0, st>>>(buf, B, T);
+    fd_launch_pdl(k_zero_pads, dim3(B + 1), dim3(256), 0, st, buf, B, T);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { err = std::string("launch of k_zero_pads failed: ") + cudaGetErrorString(e); return -3; }
     ++*launches;

@@ -38,6 +38,8 @@ struct Up4Params {
 };
 
 __global__ void __launch_bounds__(512, 2) k_upsample_p4(const Up4Params p) {
+    pdl_trigger();
+
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* raw = smem;                           // bulk-copied fp32 rows: row ar <-> input row m0 - 1 + ar
@@ -66,6 +68,7 @@ __global__ void __launch_bounds__(512, 2) k_upsample_p4(const Up4Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    pdl_wait();   // programmatic dependent launch: everything above touched constants, shared memory and TMEM only
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int gw_u = __shfl_sync(0xffffffffu, gw, 0);
     constexpr uint32_t idesc64 = umma_idesc_f16(128, 64), idesc32 = umma_idesc_f16(128, 32);
