@@ -26,7 +26,7 @@ struct EmbedParams {
 constexpr int EMB_SLOTS = 64;
 struct EmbedSteps { float t[EMB_SLOTS]; };
 
-__global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __restrict__ t_dev, EmbedSteps ts,
+__global__ void __launch_bounds__(512, 1) k_embed(EmbedParams p, const float* __restrict__ t_dev, EmbedSteps ts,
                                                float* __restrict__ emb_all, float* __restrict__ cnoise_all, int B) {
     pdl_trigger();
     pdl_wait();
@@ -45,14 +45,14 @@ __global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __res
     __syncthreads();
     {
         float acc = p.b1[j];
-#pragma unroll 16
-        for (int i = 0; i < EMB_IN; ++i) acc = fmaf(s_in[i], __ldg(p.w1t + i * EMB_MID + j), acc);   // 16 independent loads in flight, same summation order
+#pragma unroll 32
+        for (int i = 0; i < EMB_IN; ++i) acc = fmaf(s_in[i], __ldg(p.w1t + i * EMB_MID + j), acc);   // 32 independent loads in flight (the chain is pure L2 latency), same summation order
         s_mid[j] = acc * sigmoidf_(acc);
     }
     __syncthreads();
     {
         float acc = p.b2[j];
-#pragma unroll 16
+#pragma unroll 32
         for (int i = 0; i < EMB_MID; ++i) acc = fmaf(s_mid[i], __ldg(p.w2t + i * EMB_OUT + j), acc);
         acc = acc * sigmoidf_(acc);
         s_out[j] = acc;
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(512) k_embed(EmbedParams p, const float* __res
         const int blk = j / COND, c = j % COND;
         const float* w = FD_SEL3(p.fct_wt, blk);
         float acc = FD_SEL3(p.fct_b, blk)[c];
-#pragma unroll 16
+#pragma unroll 32
         for (int i = 0; i < EMB_OUT; ++i) acc = fmaf(s_out[i], __ldg(w + i * COND + c), acc);
         cnoise[(blk * B + b) * COND + c] = acc;
     }

@@ -683,8 +683,16 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             mbar_wait(&tfull_bar[acc], acc_phase);
             if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 1);
             tc_fence_after();
+            // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld has completed -- half an item's stores
+            // earlier than at the end of the item: the two accumulator stages both take about the store time, so every cycle of hand-over counts.
+            auto release_acc = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+            };
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + cpart * CPW;
             if (exp_mask & 1) {
+                release_acc();
                 // timing experiment: no epilogue work at all
             } else if (exp_mask & 4) {
                 // timing experiment: TMEM loads + arithmetic, no global stores (the store is predicated on a value that never occurs)
@@ -693,6 +701,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c0, v);
                     tmem_ld_wait();
+                        if (c0 + 32 >= CPW) release_acc();   // the accumulator is in registers: hand it back before the stores
                     float acc2 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc2 += fmaf(__uint_as_float(v[j]), inv_s, bv_s);
@@ -707,6 +716,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c0, v);
                     tmem_ld_wait();
+                        if (c0 + 32 >= CPW) release_acc();   // the accumulator is in registers: hand it back before the stores
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         float* r = o + (size_t)(j + (lane & 7)) * KCN;
@@ -725,6 +735,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                         uint32_t v[32];
                         tmem_ld_32x32b_x32(taddr + c0, v);
                         tmem_ld_wait();
+                        if (c0 + 32 >= CPW) release_acc();   // the accumulator is in registers: hand it back before the stores
                         if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 2 + (c0 >> 5) * 2);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) put_pieces(ph + (size_t)j * (2 * KCN), pl + (size_t)j * (2 * KCN), __uint_as_float(v[j]));
@@ -738,6 +749,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                         uint32_t v[32];
                         tmem_ld_32x32b_x32(taddr + c0, v);
                         tmem_ld_wait();
+                        if (c0 + 32 >= CPW) release_acc();   // the accumulator is in registers: hand it back before the stores
 #pragma unroll
                         for (int j = 0; j < 32; ++j) o[(size_t)j * KCN] = F16 ? fmaf(__uint_as_float(v[j]), inv, bv) : __uint_as_float(v[j]) + bv;
                         o += (size_t)32 * KCN;
@@ -754,6 +766,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c0, v);
                     tmem_ld_wait();
+                        if (c0 + 32 >= CPW) release_acc();   // the accumulator is in registers: hand it back before the stores
                     // (broadcast from lane 0 so that ptxas KNOWS these are warp-uniform: uniform predicates and branches, no per-store R2UR)
                     const int pc = __shfl_sync(0xffffffffu, p + c0, 0), cen = pc + 1, bbc = cen / (Tm + 2), fpc = cen % (Tm + 2);
                     const int j1 = Tm + 1 - fpc, jlo = fpc == 0 ? 1 : 0, jhi = M - pc;   // end pad row; leading pad row; rows past the end
@@ -797,6 +810,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     uint32_t v[32];
                     tmem_ld_32x32b_x32(taddr + c0, v);
                     tmem_ld_wait();
+                        if (c0 + 32 >= CPW) release_acc();   // the accumulator is in registers: hand it back before the stores
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         if (p < M && fp >= 1 && fp <= Tm) {   // uniform across the warp (depends on the column only)
@@ -809,9 +823,6 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
             if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 6);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
