@@ -41,6 +41,7 @@ struct fd_handle {
     int graphs = 1;              // fd_sample in device-noise mode: capture the whole call (all N <= 64 steps) in a CUDA graph on first use and
                                  // replay it afterwards (option "graphs"; the workspace, shapes, schedule and options are the cache key)
     uint64_t epoch = 0;          // bumped by everything that changes what a captured graph would do (mode, options, weights, noise window)
+    int final_stream = 1;        // final conv + update as the streaming warp kernel k_final_w (option "final_w", 0 = k_final with shared-memory staging)
     int up4 = 1;                 // piece-row path: block 2 upsampling + skip by k_upsample_p4 (option "up4", 0 = k_upsample_tc<4, true>)
     int lvc_p = 1;               // mode tc_3xf16: LVC blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>; option "lvc_p", 0 = k_lvc_layer_h)
     unsigned int* sat_flag = nullptr;   // device word, sticky: an fp16 piece saturated in a tensor-core kernel (fd_check_saturation)
@@ -348,6 +349,7 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "lvc_p")) { h->lvc_p = (int)value; return FD_OK; }
     if (!strcmp(key, "up4")) { h->up4 = (int)value; return FD_OK; }
+    if (!strcmp(key, "final_w")) { h->final_stream = (int)value; return FD_OK; }
 #ifndef FD_EMU
     if (!strcmp(key, "pdl")) { g_fd_pdl = value ? 1 : 0; return FD_OK; }   // programmatic dependent launch of the step's kernels (process-wide)
 #endif
@@ -970,7 +972,8 @@ extern "C" int fd_denoise(fd_handle* h, const float* x_dev, const float* mel_dev
     const int L = Tm * HOP_TOTAL;
     {
         ScopedTimer tm(h, KC_FINAL, st);
-        FD_LAUNCH_PDL(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), x_dev, (const float*)nullptr, eps_dev, (float*)nullptr, L);
+        if (h->final_stream) FD_LAUNCH_PDL(k_final_w, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), x_dev, (const float*)nullptr, eps_dev, (float*)nullptr, L);
+        else            FD_LAUNCH_PDL(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), x_dev, (const float*)nullptr, eps_dev, (float*)nullptr, L);
         FD_CHECK_LAUNCH(h, "k_final");
     }
     return FD_OK;
@@ -1020,8 +1023,10 @@ static int sample_body(fd_handle* h, float* x_dev, const float* mel_dev, const f
         }
         // in-place: every thread reads only its own x element
         ScopedTimer tm(h, KC_FINAL, st);
-        FD_LAUNCH_PDL(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), (const float*)x_dev, z, x_dev,
-                  seq_dev ? seq_dev + (size_t)(i + 1) * n : (float*)nullptr, L);
+        if (h->final_stream) FD_LAUNCH_PDL(k_final_w, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), (const float*)x_dev, z, x_dev,
+                                      seq_dev ? seq_dev + (size_t)(i + 1) * n : (float*)nullptr, L);
+        else            FD_LAUNCH_PDL(k_final, dim3(L / 256, B), dim3(256), 0, st, fp, final_buffer(ws, B, Tm), (const float*)x_dev, z, x_dev,
+                                      seq_dev ? seq_dev + (size_t)(i + 1) * n : (float*)nullptr, L);
         FD_CHECK_LAUNCH(h, "k_final");
     }
     return FD_OK;

@@ -806,6 +806,68 @@ __global__ void __launch_bounds__(256) k_final(FinalParams p, const float* __res
     if (seq_out) seq_out[e] = r;
 }
 
+// K14 + K15 again, as a streaming kernel without shared memory (the default; k_final above stays selectable with fd_set_option("final_w", 0)):
+// a warp owns 32 consecutive outputs of one item, lane c = channel c.  It loads the 38 rows t0-3 .. t0+34 with one coalesced 128-byte
+// request each (all in flight before the first use), every lane accumulates its channel's contribution to the 32 outputs over the 7 taps
+// (224 FMA per lane), a 31-shuffle transpose-reduce leaves output t0 + l in lane l, and the lanes apply the reverse-step update and store
+// coalesced.  k_final staged 262 rows per CTA through shared memory (33 KB written, 82 KB read back, two barriers) and reached 3 TB/s;
+// the sums are associated differently (channel-major per lane, then across lanes), well inside the stated tolerance.
+__global__ void __launch_bounds__(256) k_final_w(FinalParams p, const float* __restrict__ h, const float* __restrict__ x_t,
+                                                 const float* __restrict__ z, float* __restrict__ out,
+                                                 float* __restrict__ seq_out, int L) {
+    pdl_trigger();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, b = blockIdx.y;
+    const int t0 = blockIdx.x * 256 + wid * 32;
+    float w[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) w[k] = p.w[k * C + lane];
+    const float* hb = h + (size_t)b * L * C + lane;
+    float x[38];
+#pragma unroll
+    for (int r = 0; r < 38; ++r) {
+        const int t = t0 - 3 + r;
+        x[r] = (t >= 0 && t < L) ? hb[(size_t)t * C] : 0.f;
+    }
+    float v[32];
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) a = fmaf(w[k], x[o + k], a);   // output t0 + o reads rows t0 + o + k - 3
+        v[o] = a;
+    }
+    // transpose-reduce: after the step with stride s a lane keeps the half of its values whose index bit s equals its lane bit s
+#pragma unroll
+    for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+        const bool up = (lane & s2) != 0;
+#pragma unroll
+        for (int i = 0; i < s2; ++i) {
+            const float send = up ? v[i] : v[i + s2];
+            const float keep = up ? v[i + s2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s2);
+        }
+    }
+    const float eps = p.b + v[0];
+    const int t = t0 + lane;
+    const size_t e = (size_t)b * L + t;
+    float r;
+    if (p.mode == 0) {
+        r = eps;
+    } else if (p.mode == 1) {
+        r = __fdiv_rn(__fsub_rn(x_t[e], __fmul_rn(p.coef, eps)), p.div);
+        if (p.add_noise) {
+            const float zz = z ? z[e] : philox_normal(noise_elem(p.win, b, L, t), p.draw, p.seed_ptr ? (uint64_t)*p.seed_ptr : p.seed);
+            r = __fadd_rn(r, __fmul_rn(p.sigma, zz));
+        }
+    } else {
+        r = __fadd_rn(__fadd_rn(__fmul_rn(p.c1, x_t[e]), __fmul_rn(p.c2, eps)), __fmul_rn(p.c3, eps));
+    }
+    out[e] = r;
+    if (seq_out) seq_out[e] = r;
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // One reverse-step update on its own (util.py:219-229), for denoisers other than FastDiff that share the sampler (SURVEY.md 8f.4:
 // the network then is the caller's torch module, only the update runs here).  The same operation sequence as the tail of k_final:

@@ -103,3 +103,15 @@ static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n)
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, int, int) { return cudaSuccess; }
+// a real lane exchange (k_final_w's transpose-reduce): the warp's fibres publish their values, meet at the warp barrier, read the partner's
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+    static thread_local unsigned long long buf[2048];   // per OS thread = per CTA (pair) in flight
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    const unsigned me = emu::t_linear_tid + 1024u * emu::t_cta_rank;
+    memcpy(&buf[me], &v, sizeof(T));
+    emu::syncwarp();
+    T r;
+    memcpy(&r, &buf[me ^ (unsigned)lane_mask], sizeof(T));
+    emu::syncwarp();
+    return r;
+}

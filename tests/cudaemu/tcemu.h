@@ -330,3 +330,4 @@ inline float rcp_approx(float x) { return 1.f / x; }
 // warp primitives as the kernels use them: lane-0 broadcasts of warp-uniform values, and __syncwarp as a real barrier
 template <typename T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 static inline void __syncwarp() { emu::syncwarp(); }
+
