@@ -41,7 +41,8 @@ struct fd_handle {
     int graphs = 1;              // fd_sample in device-noise mode: capture the whole call (all N <= 64 steps) in a CUDA graph on first use and
                                  // replay it afterwards (option "graphs"; the workspace, shapes, schedule and options are the cache key)
     uint64_t epoch = 0;          // bumped by everything that changes what a captured graph would do (mode, options, weights, noise window)
-    int final_stream = 1;        // final conv + update as the streaming warp kernel k_final_w (option "final_w", 0 = k_final with shared-memory staging)
+    int final_stream = 0;        // option "final_w" = 1: final conv + update as the streaming warp kernel k_final_w.  Measured SLOWER than k_final (0.466 vs 0.335 ms
+                                 // per N=4 call at config 2, round 2): kept as a cross-check of k_final's arithmetic, off by default
     int up4 = 1;                 // piece-row path: block 2 upsampling + skip by k_upsample_p4 (option "up4", 0 = k_upsample_tc<4, true>)
     int lvc_p = 1;               // mode tc_3xf16: LVC blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>; option "lvc_p", 0 = k_lvc_layer_h)
     unsigned int* sat_flag = nullptr;   // device word, sticky: an fp16 piece saturated in a tensor-core kernel (fd_check_saturation)

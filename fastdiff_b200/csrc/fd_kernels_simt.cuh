@@ -806,7 +806,8 @@ __global__ void __launch_bounds__(256) k_final(FinalParams p, const float* __res
     if (seq_out) seq_out[e] = r;
 }
 
-// K14 + K15 again, as a streaming kernel without shared memory (the default; k_final above stays selectable with fd_set_option("final_w", 0)):
+// K14 + K15 again, as a streaming kernel without shared memory (fd_set_option("final_w", 1); OFF by default: measured slower than k_final --
+// 0.116 vs 0.084 ms per launch at config 2 -- although it moves the same bytes with no staging: a warp is one long dependent chain here):
 // a warp owns 32 consecutive outputs of one item, lane c = channel c.  It loads the 38 rows t0-3 .. t0+34 with one coalesced 128-byte
 // request each (all in flight before the first use), every lane accumulates its channel's contribution to the 32 outputs over the 7 taps
 // (224 FMA per lane), a 31-shuffle transpose-reduce leaves output t0 + l in lane l, and the lanes apply the reverse-step update and store
