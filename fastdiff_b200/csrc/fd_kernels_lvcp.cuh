@@ -56,7 +56,7 @@ template <int HOP> __host__ __device__ constexpr int lp_smem_bytes() {
 
 // Optional role timeline (-DLP_TIMELINE=1, GPU build only): CTA 0 of the block-2 launch with dilation LP_TL_DIL stamps clock64 at the
 // protocol points of its first 24 tiles -- [role 0 loader | 1 MMA issuer | 2 conv epilogue (warp 16) | 3 gate epilogue (warp 0)][tile][8 slots];
-// read with fd_debug_read("lp_timeline") (tools/gpu/lp_timeline.py).
+// read with fd_debug_read("lp_timeline") (tests/gpu_scripts/lp_timeline.py).
 #if defined(LP_TIMELINE) && !defined(FD_EMU)
 #ifndef LP_TL_DIL
 #define LP_TL_DIL 9

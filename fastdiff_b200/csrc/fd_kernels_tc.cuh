@@ -467,7 +467,7 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 // rows and writes them with 16-byte stores, bit-identical output -- ran at 1.60 ms per launch against 0.61 ms: a warp store then touches 32
 // different lines with 16 bytes each, and the L2 request rate, not the instruction count, is what bounds this store stream.)
 // Optional role timeline of the kernel_conv GEMM (-DKC_TIMELINE=1, GPU build): CTA 0 stamps clock64 for its first 32 items --
-// [role 0 TMA producer | 1 MMA issuer | 2 epilogue warp 2][item][8 slots]; fd_debug_read("kc_timeline"), tools/gpu/kc_timeline.py.
+// [role 0 TMA producer | 1 MMA issuer | 2 epilogue warp 2][item][8 slots]; fd_debug_read("kc_timeline"), tests/gpu_scripts/kc_timeline.py.
 #if defined(KC_TIMELINE) && !defined(FD_EMU)
 constexpr int KC_TL_ITEMS = 32;
 __device__ unsigned long long g_kc_timeline[3 * KC_TL_ITEMS * 8];

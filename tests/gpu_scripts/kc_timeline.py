@@ -1,5 +1,5 @@
 """kernel_conv GEMM role timeline on a B200 (NOT collected by pytest).  Needs a build with -DKC_TIMELINE=1:
-    FD_NVCC_EXTRA="-DKC_TIMELINE=1" python -c "import __graft_entry__ as g; g.build_cuda(force=True)"; python tools/gpu/kc_timeline.py
+    FD_NVCC_EXTRA="-DKC_TIMELINE=1" python -c "import __graft_entry__ as g; g.build_cuda(force=True)"; python tests/gpu_scripts/kc_timeline.py
 CTA 0 (leader of cluster 0), config 2: clock64 stamps of the TMA producer, the MMA issuer and one epilogue warp for the first 32 items."""
 import sys
 

@@ -1,5 +1,5 @@
 """k_lvc_p role timeline on a B200 (NOT collected by pytest).  Needs a build with -DLP_TIMELINE=1:
-    FD_NVCC_EXTRA="-DLP_TIMELINE=1" python -c "import __graft_entry__ as g; g.build_cuda(force=True)"; python tools/gpu/lp_timeline.py
+    FD_NVCC_EXTRA="-DLP_TIMELINE=1" python -c "import __graft_entry__ as g; g.build_cuda(force=True)"; python tests/gpu_scripts/lp_timeline.py
 Prints, for CTA 0 of the block-2 layer with dilation 9, the clock64 stamps of every role per tile (cycles since the first stamp)."""
 import sys
 

@@ -1,5 +1,5 @@
 # Multi-GPU check of the time-axis shard mode (run under torchrun, NCCL): long utterances, N = 4, default arithmetic mode.
-#   torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tools/gpu/timeshard_check.py
+#   torchrun --nproc-per-node 2 --master-addr 127.0.0.1 tests/gpu_scripts/timeshard_check.py
 # Per shape: (a) "reference" noise (full-size host draws on every rank) == the single-GPU parity-mode result, bitwise;
 #            (b) "device" noise -- the LATENCY mode: per-rank Philox windows -- == the single-GPU device-noise result, bitwise, and timed
 #                against the single-GPU call with CUDA events (max over ranks).

@@ -251,7 +251,7 @@ def test_full_size_properties(synth, cuda_lib):
 def test_time_shard_sampler_world1_equals_sampler(synth, cuda_lib):
     """SURVEY.md 8f.4 plumbing on one GPU (world 1: no halo, no exchange): per-step fd_sample calls with sliced reference-order
     noise == the single-call sampler bitwise.  The 2-rank halo exchange is covered by tests/test_timeshard_gloo.py (CPU, emulated
-    source) and tools/gpu/timeshard_check.py (2 GPUs, NCCL)."""
+    source) and tests/gpu_scripts/timeshard_check.py (2 GPUs, NCCL)."""
     import fastdiff_b200 as fb
     from fastdiff_b200.synthetic import make_inputs
     from fastdiff_b200.timeshard import TimeShardedSampler

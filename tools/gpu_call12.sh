@@ -3,7 +3,7 @@
 set -u
 OUT=gpurun_out/r2_c12
 mkdir -p "$OUT"; rm -f "$OUT"/*
-timeout 300 python tools/gpu/lvcp_check.py > "$OUT/lvcp_check.log" 2>&1; echo "rc=$?" >> "$OUT/lvcp_check.log"
+timeout 300 python tests/gpu_scripts/lvcp_check.py > "$OUT/lvcp_check.log" 2>&1; echo "rc=$?" >> "$OUT/lvcp_check.log"
 B="python bench.py --steps 10 --warmup 3 --no-cpu"
 timeout 300 $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
 timeout 300 $B --opt final_w=0 > "$OUT/bench_finalw0.json" 2> "$OUT/bench_finalw0.err"

@@ -3,13 +3,13 @@
 set -u
 OUT=gpurun_out/r2_c8
 mkdir -p "$OUT"
-timeout 300 python tools/gpu/lvcp_check.py > "$OUT/lvcp_check.log" 2>&1; echo "rc=$?" >> "$OUT/lvcp_check.log"
+timeout 300 python tests/gpu_scripts/lvcp_check.py > "$OUT/lvcp_check.log" 2>&1; echo "rc=$?" >> "$OUT/lvcp_check.log"
 B="python bench.py --steps 10 --warmup 3"
 timeout 300 $B --no-cpu > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
 FD_NVCC_EXTRA="-DLP_TIMELINE=1 -DKC_TIMELINE=1 -DUT_TIMELINE=1" python -c "import __graft_entry__ as g; g.build_cuda(force=True)" > "$OUT/build.log" 2>&1
-timeout 200 python tools/gpu/lp_timeline.py > "$OUT/lp_timeline.txt" 2>&1
-timeout 200 python tools/gpu/kc_timeline.py 0 > "$OUT/kc_timeline_serial.txt" 2>&1
-timeout 200 python tools/gpu/kc_timeline.py 1 > "$OUT/kc_timeline_overlap.txt" 2>&1
+timeout 200 python tests/gpu_scripts/lp_timeline.py > "$OUT/lp_timeline.txt" 2>&1
+timeout 200 python tests/gpu_scripts/kc_timeline.py 0 > "$OUT/kc_timeline_serial.txt" 2>&1
+timeout 200 python tests/gpu_scripts/kc_timeline.py 1 > "$OUT/kc_timeline_overlap.txt" 2>&1
 python -c "import __graft_entry__ as g; g.build_cuda(force=True)" >> "$OUT/build.log" 2>&1
 for f in "$OUT"/bench_*.json; do
   python - "$f" >> "$OUT/summary.txt" 2>&1 <<'PY'
