@@ -118,3 +118,47 @@ def test_blob_f16_sections_decode_to_the_folded_weights(synth):
             pos = (((ci3 >> 3) ^ (co & 7)) << 3) + (ci3 & 7)
             rec = f16(u[10 + 3 * l + j3, 0, co, pos]) + f16(u[10 + 3 * l + j3, 1, co, pos])
             assert abs(rec / sc[17 + 8 * n + l] - w) <= abs(w) * 2.0 ** -21 + 1e-12
+
+
+def test_merged_n_sections_decode_to_the_folded_weights(synth):
+    """The round-2 merged-N operand images (fd_blob.h: LBn_CONV_F16M, LB2_UP_F16M, FIRST_F16U), decoded with independent index arithmetic:
+    hi and lo pieces are separate ROWS of SWIZZLE_128B tiles whose 128-byte rows hold two taps side by side."""
+    from fastdiff_b200.weights import build_sections
+    sd, W = synth
+    S = build_sections(sd)
+    sc = S["SCALES16"]
+    f16 = lambda u: np.asarray(u, dtype=np.uint16).view(np.float16).astype(np.float64)
+    rng = np.random.default_rng(3)
+
+    def row_val(tile, r, half):   # fp16 value `half` (0..63) of logical row r of a [rows][64 halves] SWIZZLE_128B tile
+        return f16(tile[r, (((half >> 3) ^ (r & 7)) << 3) + (half & 7)])
+
+    for n in (1, 2):   # LBn_CONV_F16M: per layer T01 [64 rows = piece * 32 + co][tap 0 | tap 1], T2 [32 rows co][hi | lo] of tap 2
+        u = S[f"LB{n}_CONV_F16M"].view(np.uint16).reshape(4, 96, 64)
+        for _ in range(300):
+            l, k, co, ci = rng.integers(4), rng.integers(3), rng.integers(32), rng.integers(32)
+            w = float(W[f"lvc_blocks.{n}.convs.{l}.weight"][co, ci, k])
+            if k < 2:
+                rec = row_val(u[l, :64], co, k * 32 + ci) + row_val(u[l, :64], 32 + co, k * 32 + ci)
+            else:
+                rec = row_val(u[l, 64:], co, ci) + row_val(u[l, 64:], co, 32 + ci)
+            assert abs(rec / sc[4 + 4 * n + l] - w) <= abs(w) * 2.0 ** -21 + 1e-12
+    # LB2_UP_F16M: per output phase ph, rows piece * 32 + co = [tap kk1 | tap kk1 + 4], kk1 = (ph + 2) % 4, ConvTranspose1d weight (ci, co, k)
+    u = S["LB2_UP_F16M"].view(np.uint16).reshape(4, 64, 64)
+    up = W["lvc_blocks.2.upsample.weight"]
+    for _ in range(300):
+        ph, tap, co, ci = rng.integers(4), rng.integers(2), rng.integers(32), rng.integers(32)
+        w = float(up[ci, co, (ph + 2) % 4 + 4 * tap])
+        rec = row_val(u[ph], co, tap * 32 + ci) + row_val(u[ph], 32 + co, tap * 32 + ci)
+        assert abs(rec / sc[41] - w) <= abs(w) * 2.0 ** -21 + 1e-12
+    # FIRST_F16U: rows ph * 32 + co of 32 halves: W_ph[i] = first_w[co][i - ph] (0 <= i - ph <= 6), W_ph[10] = first_b[co], else 0; hi 16 | lo 16
+    u = S["FIRST_F16U"].view(np.uint16).reshape(128, 32)
+    fw, fb = W["first_audio_conv.weight"][:, 0, :], W["first_audio_conv.bias"]
+    for ph in range(4):
+        for co in range(32):
+            rec = (f16(u[ph * 32 + co, :16]) + f16(u[ph * 32 + co, 16:])) / sc[41]
+            want = np.zeros(16)
+            want[ph:ph + 7] = fw[co].numpy()
+            want[10] = float(fb[co])
+            assert np.abs(rec - want).max() <= np.abs(want).max() * 2.0 ** -20 + 1e-12
+    assert sc[41] == min(sc[40], sc[41]) and np.log2(sc[41]) == np.round(np.log2(sc[41]))
