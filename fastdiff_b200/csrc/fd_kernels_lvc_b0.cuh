@@ -112,11 +112,6 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
             if (li >= LB0_NSLOT) mbar_wait(&ring_empty[rs], ((li / LB0_NSLOT) - 1) & 1);
             issue_pair(tile, pp, rs);
         }
-        // the other five pairs of the tile go to L2 now: the kernel stream (384 KB per tile, the HBM floor of this kernel) then keeps flowing
-        // while the SIMT phases of this and the next tile run, instead of only during phase 4 through the three ring slots
-        const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
-        for (int f = t0 / 8 + 2 * LB0_NSLOT; f < t0 / 8 + 16 && f < Tm; ++f)
-            bulk_prefetch_l2(kern + ((size_t)b * Tm + f) * KCN, (uint32_t)(KPL * 4));
     };
     int tile = blockIdx.x;
     if (tile < total && gw == 0) { if (elect_one()) issue_tile_head(tile, 0); __syncwarp(); ld_issued = LB0_NSLOT; }
