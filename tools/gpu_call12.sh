@@ -1,15 +1,13 @@
 #!/bin/bash
-# Round-2 call 12 (lean): quick parity of the piece-row path + bench with / without programmatic dependent launch.
+# Round-2 call 12 (lean A/B): quick parity of the piece-row path + bench (+ an optional second bench with the options in $FD_AB_OPT).
 set -u
 OUT=gpurun_out/r2_c12
 mkdir -p "$OUT"; rm -f "$OUT"/*
 timeout 300 python tests/gpu_scripts/lvcp_check.py > "$OUT/lvcp_check.log" 2>&1; echo "rc=$?" >> "$OUT/lvcp_check.log"
 B="python bench.py --steps 10 --warmup 3 --no-cpu"
 timeout 300 $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
-timeout 300 $B --opt final_w=0 > "$OUT/bench_finalw0.json" 2> "$OUT/bench_finalw0.err"
-timeout 200 $B --batch 1 --frames 86 > "$OUT/bench_1x86.json" 2> "$OUT/bench_1x86.err"
-timeout 200 $B --batch 1 --frames 86 --opt final_w=0 > "$OUT/bench_1x86_finalw0.json" 2> "$OUT/bench_1x86_finalw0.err"
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "boundaries or stages or tensor_core_mode or 8x861 or sampler or shard" > "$OUT/gpu_tests.log" 2>&1; echo "rc=$?" >> "$OUT/gpu_tests.log"
+if [ -n "${FD_AB_OPT:-}" ]; then timeout 300 $B --opt $FD_AB_OPT > "$OUT/bench_ab.json" 2> "$OUT/bench_ab.err"; fi
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "boundaries or stages or tensor_core_mode or 8x861" > "$OUT/gpu_tests.log" 2>&1; echo "rc=$?" >> "$OUT/gpu_tests.log"
 for f in "$OUT"/bench_*.json; do
   python - "$f" >> "$OUT/summary.txt" 2>&1 <<'PY'
 import sys, json
