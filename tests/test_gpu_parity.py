@@ -135,6 +135,37 @@ def test_kernel_conv_gemm_utterance_boundaries(synth, cuda_lib, B, Tm):
 
 
 @gpu
+@pytest.mark.parametrize("B,Tm", [(2, 33), (1, 130)])
+def test_round2_kernel_options_agree(synth, cuda_lib, B, Tm):
+    """The alternatives kept behind run-time options against the default path, on the device: `up4` = 0 (k_upsample_tc<4, POUT> instead of
+    k_upsample_p4: same values up to the summation order of up + skip), `final_w` = 1 (k_final_w instead of k_final: other association of
+    the 224-term sums), `pdl` = 1 (programmatic dependent launch: the same kernels, so the same bits) and `lvc_p` = 0 (round-1 row kernels)."""
+    from fastdiff_b200.synthetic import make_inputs
+    from oracle import fastdiff_oracle as O
+    sd, W = synth
+    x, mel = make_inputs(B, Tm, 17)
+    t = torch.tensor([74.99228, 498.0537][:B]).reshape(B, 1)
+    eps_ref = O.denoise(W, x, mel, t)
+    net = _net(sd, "tc_3xf16")
+    eng = net.engine()
+    xd, md, td = x.cuda(), mel.cuda(), t.cuda()
+    base = net((xd, md, td)).cpu()
+    assert (base - eps_ref).abs().max() < EPS_TOL
+    for key, val, bitwise, tol in (("pdl", 1, True, 0.0), ("up4", 0, False, 1e-5), ("final_w", 1, False, 1e-5), ("lvc_p", 0, False, 1e-5)):
+        default = {"pdl": 0, "up4": 1, "final_w": 0, "lvc_p": 1}[key]
+        eng.set_option(key, val)
+        out = net((xd, md, td)).cpu()
+        eng.set_option(key, default)
+        assert (out - eps_ref).abs().max() < EPS_TOL, key
+        if bitwise:
+            assert torch.equal(out, base), key
+        else:
+            assert (out - base).abs().max() < tol, key
+    assert torch.equal(net((xd, md, td)).cpu(), base)
+    assert not eng.check_saturation()
+
+
+@gpu
 def test_f16_mode_options_and_guards(synth, cuda_lib):
     """tc_3xf16 building blocks: the tensor-core kernel-predictor stack against the FFMA one, the side-stream overlap against the
     serial order (bitwise), the cross_check guard, and saturation (finite output, flagged by cross_check) beyond the fp16 range."""
