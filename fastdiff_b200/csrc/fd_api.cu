@@ -1173,6 +1173,23 @@ extern "C" int fd_debug_read(fd_handle* h, const char* name, float* out_dev, siz
         FD_CUDA(h, cudaStreamSynchronize(st));
         return FD_OK;
     }
+#if defined(B0_TIMELINE)
+    if (!strcmp(name, "b0_timeline")) {   // k_lvc_layer_b0h phase timeline
+        constexpr int NW = 4 * 8;
+        *count = NW;
+        if (!out_dev) return FD_OK;
+        static unsigned long long host[NW];
+        static float rel[NW];
+        FD_CUDA(h, cudaStreamSynchronize(st));
+        FD_CUDA(h, cudaMemcpyFromSymbol(host, g_b0_timeline, sizeof host));
+        unsigned long long mn = ~0ull;
+        for (int i = 0; i < NW; ++i) if (host[i] && host[i] < mn) mn = host[i];
+        for (int i = 0; i < NW; ++i) rel[i] = host[i] ? (float)(double)(host[i] - mn + 1) : 0.f;
+        FD_CUDA(h, cudaMemcpyAsync(out_dev, rel, sizeof rel, cudaMemcpyHostToDevice, st));
+        FD_CUDA(h, cudaStreamSynchronize(st));
+        return FD_OK;
+    }
+#endif
 #if defined(UT_TIMELINE)
     if (!strcmp(name, "ut_timeline")) {   // k_upsample_tc<4, POUT> phase timeline
         constexpr int NW = 24 * 8;

@@ -6,6 +6,15 @@
 
 namespace fd {
 
+// Optional phase timeline (-DB0_TIMELINE=1, GPU build): thread 0 of CTA 0 stamps clock64 at the phase boundaries of its tiles (8 slots x 4 tiles; the
+// last launch wins); fd_debug_read("b0_timeline").
+#if defined(B0_TIMELINE) && !defined(FD_EMU)
+__device__ unsigned long long g_b0_timeline[4 * 8];
+#define B0_STAMP(slot) do { if (blockIdx.x == 0 && tid == 0 && tl_n < 4) g_b0_timeline[tl_n * 8 + (slot)] = clock64(); } while (0)
+#else
+#define B0_STAMP(slot) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------
 // One LVC layer of block 0
 // (hop 8) on tensor cores in SWAPPED-operand form.  With 8 samples per frame an M = 128 time-step tile would use 8 rows per
@@ -116,10 +125,13 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
     int tile = blockIdx.x;
     if (tile < total && gw == 0) { if (elect_one()) issue_tile_head(tile, 0); __syncwarp(); ld_issued = LB0_NSLOT; }
     uint32_t parity = 0;
-    for (; tile < total; tile += gridDim.x, parity ^= 1) {
+    [[maybe_unused]] int tl_n = 0;
+    for (; tile < total; tile += gridDim.x, parity ^= 1, ++tl_n) {
+        B0_STAMP(0);
         const int b = tile / ntt, t0 = (tile % ntt) * LT_TT;
         // ---------------- phase 1: raw rows -> fp16 pieces, in place ----------------
         mbar_wait(bar_rows, parity);
+        B0_STAMP(1);
         {
             float4 xv[3], sv[3];
 #pragma unroll
@@ -147,6 +159,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
         }
         fence_async_smem();
         __syncthreads();
+        B0_STAMP(2);
         // ---------------- phase 2: dilated conv (two passes: rows 0..127 and the two extra rows) ----------------
         if (gw == 0) {
             tc_fence_after();
@@ -173,6 +186,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
             __syncwarp();
         }
         mbar_wait(&bars[0], parity);
+        B0_STAMP(3);
         tc_fence_after();
         // ---------------- phase 3: y = lrelu(conv + b) -> pieces, rows of the Y tile (over the A tile) ----------------
         if (gw < 8) {
@@ -211,6 +225,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        B0_STAMP(4);
         // ---------------- phase 4: location-variable conv, one accumulation group per frame pair, kernels through the ring ----------------
         if (gw == 0) {
             tc_fence_after();
@@ -273,6 +288,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
                     }
             }
             mbar_wait(&bars[1], parity);
+            B0_STAMP(5);
             tc_fence_after();
             if (gw == 0 && tile + (int)gridDim.x < total) {   // the A/Y tile and every ring slot are free: request the next tile
                 if (elect_one()) issue_tile_head(tile + gridDim.x, ld_issued);
@@ -321,6 +337,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
         }
         tc_fence_before();
         __syncthreads();
+        B0_STAMP(6);
     }
     tc_fence_before();
     __syncthreads();
