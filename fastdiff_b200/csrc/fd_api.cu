@@ -43,6 +43,9 @@ struct fd_handle {
     uint64_t epoch = 0;          // bumped by everything that changes what a captured graph would do (mode, options, weights, noise window)
     int final_stream = 0;        // option "final_w" = 1: final conv + update as the streaming warp kernel k_final_w.  Measured SLOWER than k_final (0.466 vs 0.335 ms
                                  // per N=4 call at config 2, round 2): kept as a cross-check of k_final's arithmetic, off by default
+    int kc_res = 0;              // kernel_conv GEMM (tc_3xf16), option "kc_res" = 1: frame tile resident in shared memory, weights streamed, contiguous item ranges
+                                 // (measured SLOWER, 0.92 vs 0.57 ms per launch: DESIGN.md 4c.14); 0 = whole-stage ring, items strided over the CTA pairs
+    int kc_clusters = 0;         // test option "kc_clusters": cap on the CTA pairs of the kernel_conv GEMM (0 = one per SM pair); 1 makes one pair walk every frame tile
     int up4 = 1;                 // piece-row path: block 2 upsampling + skip by k_upsample_p4 (option "up4", 0 = k_upsample_tc<4, true>)
     int lvc_p = 1;               // mode tc_3xf16: LVC blocks 1, 2 on the piece-row protocol (k_lvc_p + k_upsample_tc<R, true>; option "lvc_p", 0 = k_lvc_layer_h)
     unsigned int* sat_flag = nullptr;   // device word, sticky: an fp16 piece saturated in a tensor-core kernel (fd_check_saturation)
@@ -350,6 +353,8 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
     if (!strcmp(key, "tc_b0")) { h->tc_b0 = (int)value; return FD_OK; }
     if (!strcmp(key, "lvc_p")) { h->lvc_p = (int)value; return FD_OK; }
     if (!strcmp(key, "up4")) { h->up4 = (int)value; return FD_OK; }
+    if (!strcmp(key, "kc_res")) { h->kc_res = (int)value; return FD_OK; }
+    if (!strcmp(key, "kc_clusters")) { h->kc_clusters = (int)value; return FD_OK; }
     if (!strcmp(key, "final_w")) { h->final_stream = (int)value; return FD_OK; }
 #ifndef FD_EMU
     if (!strcmp(key, "pdl")) { g_fd_pdl = value ? 1 : 0; return FD_OK; }   // programmatic dependent launch of the step's kernels (process-wide)
@@ -532,22 +537,33 @@ static int emu_lvc_layer_h(fd_handle* h, int blk, int layer, const float* x_in, 
 // The CTA-pair kernel_conv GEMM (k_kc_gemm_tc2<true, 16>: 2-SM TMA, cta_group::2 MMA, multicast commit, remote arrives) on the model.
 static int emu_kc_gemm_tc2(fd_handle* h, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st, int b0_pieces, int kimg) {
     KcgMaps maps;
+    const int res = h->kc_res;
+    const uint32_t h_box_rows = res ? KC3_BROWS : 128;
     const uint64_t rows = (uint64_t)B * (Tm + 2);
     float inv[NBLK];
     for (int n = 0; n < NBLK; ++n) {
         const float* w16 = (n == 0 && b0_pieces) ? sec(h, FD_S_LB0_KCT_F16P) : sec(h, FD_S_LB0_KCT_F16 + n);
         emu_make_map_2d(&maps.w_hi[n], w16, KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM);
         emu_make_map_2d(&maps.w_lo[n], w16 + (size_t)KCN * (KCK / 2), KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM);
-        emu_make_map_2d(&maps.h_hi[n], hk_hi + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128);
-        emu_make_map_2d(&maps.h_lo[n], hk_lo + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128);
+        emu_make_map_2d(&maps.h_hi[n], hk_hi + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, h_box_rows);
+        emu_make_map_2d(&maps.h_lo[n], hk_lo + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, h_box_rows);
         inv[n] = 1.f / (emu_scale16(h, n) * S16_HK);
     }
     const int M = B * (Tm + 2) - 2;
     const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
-    const int clusters = items < 8 ? items : 8;
-    if (b0_pieces) {
+    const int cap = h->kc_clusters > 0 ? h->kc_clusters : 8;
+    const int clusters = items < cap ? items : cap;
+    if (b0_pieces && res) {
+        auto k = k_kc_gemm_tc2<true, 16, true, true>;
+        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC3_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], kimg ? 64 : 0);
+    } else if (b0_pieces) {
         auto k = k_kc_gemm_tc2<true, 16, true>;
         FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_BP), sec(h, FD_S_LB1_KC_B),
+                           sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], kimg ? 64 : 0);
+    } else if (res) {
+        auto k = k_kc_gemm_tc2<true, 16, false, true>;
+        FD_LAUNCH_CLUSTER2(k, dim3(2 * clusters), dim3(64 + 32 * 16), KC3_SMEM_BYTES, st, maps, sec(h, FD_S_LB0_KC_B), sec(h, FD_S_LB1_KC_B),
                            sec(h, FD_S_LB2_KC_B), kern, B, Tm, 1, inv[0], inv[1], inv[2], kimg ? 64 : 0);
     } else {
         auto k = k_kc_gemm_tc2<true, 16>;
@@ -801,7 +817,7 @@ static int run_denoiser(fd_handle* h, const float* x_dev, const float* mel_dev, 
     } else {
 #ifndef FD_EMU
         ScopedTimer tm(h, KC_KC_GEMM, st);
-        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0, kimg);
+        int rc = tc_kc_gemm(h->tc_state, h->mode, ws + w.hk_hi, ws + w.hk_lo, kern, B, Tm, st, h->err, &h->launches, b0_gemm_pieces ? 1 : 0, kimg, h->kc_res, h->kc_clusters);
         if (rc) return rc;
 #endif
     }

@@ -412,6 +412,27 @@ constexpr int KC2_A_BYTES = 128 * 128;       // 16 KB: 128 weight rows x one 32-
 constexpr int KC2_B_BYTES = 128 * 128;       // 16 KB: this CTA's 128 of the 256 frame rows
 constexpr int KC2_STAGE_BYTES = 2 * KC2_A_BYTES + 2 * KC2_B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 64 KB
 constexpr int KC2_SMEM_BYTES = KC2_STAGES * KC2_STAGE_BYTES + 1024 + 256;
+// RES form (k_kc_gemm_tc2<true, 16, B0P, true>, option "kc_res" = 1; parity-green on B200 and measured SLOWER than the default, see below):
+// the frame tile stays resident, only the weights stream.
+//   * a CTA pair walks a CONTIGUOUS range of the (block, frame tile, n tile) sequence, so the 256 frames of a tile are loaded once per ~97 items
+//     and not once per item; the three k-atoms of the hidden im2col are the SAME rows shifted by one (taps p, p+1, p+2): one 130-row SWIZZLE_128B
+//     tile per piece serves all three through shifted descriptor starts (absolute-address swizzle, base_offset 0 -- the LVC kernels' trick,
+//     here on a cta_group::2 B operand);
+//   * what streams through the ring is the weight k-atom only (A_hi | A_lo = 32 KB): 4 stages = 1.33 items of prefetch at half the bytes
+//     per item; two frame-tile buffers, so the next tile's load overlaps the last items of the current one;
+//   * the epilogue warps read all 64 accumulator columns before the first store and release the stage at once (KC_EARLY_RELEASE).
+// Result (profiles/r02_kc_gemm_res_ab.txt): 0.92 ms per launch against 0.57 -- the operand side is fine (no `full` waits), the STORES slow down
+// (2,200-6,300 cycles per 32 frames instead of ~2,800).  The likely cause: with the merged-N image the two 64-byte halves of a 128-byte line of the predicted-kernel tensor belong to items 8 n-tile pairs apart; strided
+// over the pairs they are written within microseconds of each other by neighbouring pairs and leave L2 as full lines, in a contiguous range the
+// same pair writes them ~40 us (~140 MB of stores) apart and the half lines go to DRAM one by one.  The early release alone, on the whole-stage
+// ring, was slower too (2.60 vs 2.33 ms per call): the 3-slot ring holds exactly one item, so the wait just moves from `tempty` to `full`.
+constexpr int KC3_ASTAGES = 4;
+constexpr int KC3_A_STAGE = 2 * KC2_A_BYTES;          // 32 KB
+constexpr int KC3_BROWS = 130;                        // 128 frames + 2 rows of im2col halo
+constexpr int KC3_B_PIECE = 17 * 1024;                // 130 x 128 B rounded up to the 1024-byte swizzle period
+constexpr int KC3_B_BUF = 2 * KC3_B_PIECE;            // hi | lo
+constexpr int KC3_RING_BYTES = KC3_ASTAGES * KC3_A_STAGE + 2 * KC3_B_BUF;   // 200,704
+constexpr int KC3_SMEM_BYTES = KC3_RING_BYTES + 1024 + 256;
 
 #ifndef FD_EMU
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -457,6 +478,10 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 #ifndef KC_STORE_CS
 #define KC_STORE_CS 0     // 1: streaming (evict-first) cache hint on the predicted-kernel stores
 #endif
+#ifndef KC_EARLY_RELEASE
+#define KC_EARLY_RELEASE 1   // 1 (RES form only): an epilogue warp reads all of its 64 accumulator columns before its first store and releases the stage
+                             // right away.  With the whole-stage ring this was SLOWER (2.60 vs 2.33 ms per call): the operand fetch of the next item became the wait.
+#endif
 #ifndef KC_STORE_SHFL
 #define KC_STORE_SHFL 0   // 1: adjacent lanes swap one piece and store 32-bit words (one 128-byte line per warp store) instead of two 16-bit stores
 #endif
@@ -475,7 +500,7 @@ __device__ unsigned long long g_kc_timeline[3 * KC_TL_ITEMS * 8];
 #else
 #define KC_STAMP(role, it, slot) do { } while (0)
 #endif
-template <bool F16, int EPW, bool B0P = false>
+template <bool F16, int EPW, bool B0P = false, bool RES = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EPW, 1)
 k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bias0, const float* __restrict__ bias1,
               const float* __restrict__ bias2, float* __restrict__ kern_all, int B, int Tm, int three_pass,
@@ -486,12 +511,16 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
     constexpr int CPW = 256 / (EPW / 4);   // frame columns per epilogue warp
     FD_DYN_SMEM(unsigned char, smem_raw);
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t* bars = (uint64_t*)(smem + KC2_STAGES * KC2_STAGE_BYTES);
+    static_assert(!RES || (F16 && EPW == 16), "the resident-frame-tile form exists for the fp16-piece GEMM only");
+    constexpr int NST = RES ? KC3_ASTAGES : KC2_STAGES;
+    uint64_t* bars = (uint64_t*)(smem + (RES ? KC3_RING_BYTES : KC2_STAGES * KC2_STAGE_BYTES));
     uint64_t* full_bar = bars;                     // [STAGES]  (leader's copy is used) TMA of both CTAs -> leader MMA
-    uint64_t* empty_bar = bars + KC2_STAGES;       // [STAGES]  leader MMA -> TMA producer of each CTA (multicast commit)
-    uint64_t* tfull_bar = bars + 2 * KC2_STAGES;   // [2]       leader MMA -> epilogue of each CTA (multicast commit)
+    uint64_t* empty_bar = bars + NST;              // [STAGES]  leader MMA -> TMA producer of each CTA (multicast commit)
+    uint64_t* tfull_bar = bars + 2 * NST;          // [2]       leader MMA -> epilogue of each CTA (multicast commit)
     uint64_t* tempty_bar = tfull_bar + 2;          // [2]       (leader's copy) epilogue warps of both CTAs -> leader MMA
-    uint32_t* tmem_base_s = (uint32_t*)(tempty_bar + 2);
+    uint64_t* bfull_bar = tempty_bar + 2;          // [2] RES:  frame tile landed (leader's copy)
+    uint64_t* bempty_bar = bfull_bar + 2;          // [2] RES:  leader MMA -> TMA producer of each CTA: the tile's last MMA has completed
+    uint32_t* tmem_base_s = (uint32_t*)(bempty_bar + 2);
 
     // warp index broadcast from lane 0: the role branches below are then provably warp-uniform for ptxas (uniform registers stay usable)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -502,10 +531,14 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
     const int items_per_blk = n_pairs * f_tiles;
     const int total_items = NBLK * items_per_blk;
     const int pair_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    // items of this CTA pair: strided over the pairs (all pairs on the same frame tile at the same time), or -- RES -- one contiguous range
+    const int i_lo = RES ? (int)((long long)total_items * pair_id / n_clusters) : pair_id;
+    const int i_hi = RES ? (int)((long long)total_items * (pair_id + 1) / n_clusters) : total_items;
+    const int i_step = RES ? 1 : n_clusters;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < KC2_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * EPW); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 2 * EPW); mbar_init(&bfull_bar[a], 1); mbar_init(&bempty_bar[a], 1); }
         mbar_init_fence();
     }
     if (warp == 0) {   // collective over the pair: the same warp of both CTAs
@@ -522,12 +555,35 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
             [[maybe_unused]] int it_no = 0;
-            for (int item = pair_id; item < total_items; item += n_clusters, ++it_no) {
+            [[maybe_unused]] int cur_tile = -1;
+            [[maybe_unused]] uint32_t n_tiles_loaded = 0;
+            for (int item = i_lo; item < i_hi; item += i_step, ++it_no) {
                 const int blk = item / items_per_blk, r = item % items_per_blk;
                 const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
                 const CUtensorMap* wh = &maps.w_hi[blk]; const CUtensorMap* wl = &maps.w_lo[blk];
                 KC_STAMP(0, it_no, 0);
                 const CUtensorMap* hh = &maps.h_hi[blk]; const CUtensorMap* hl = &maps.h_lo[blk];
+                if constexpr (RES) {
+                    if (blk * f_tiles + ft != cur_tile) {   // next frame tile: 130 rows per piece into the buffer the MMA issuer has released
+                        cur_tile = blk * f_tiles + ft;
+                        const uint32_t bb = n_tiles_loaded & 1u, bph = (n_tiles_loaded >> 1) & 1u;
+                        mbar_wait(&bempty_bar[bb], bph ^ 1);
+                        unsigned char* bt = smem + KC3_ASTAGES * KC3_A_STAGE + bb * KC3_B_BUF;
+                        if (rank == 0) mbar_expect_tx(&bfull_bar[bb], 2u * 2u * (uint32_t)(KC3_BROWS * 128));
+                        tma_load_2d_2sm(bt, hh, 0, ft * 256 + (int)rank * 128, &bfull_bar[bb]);
+                        tma_load_2d_2sm(bt + KC3_B_PIECE, hl, 0, ft * 256 + (int)rank * 128, &bfull_bar[bb]);
+                        ++n_tiles_loaded;
+                    }
+                    for (int a = 0; a < NATOM; ++a) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        KC_STAMP(0, it_no, 1 + a);
+                        unsigned char* st = smem + stage * KC3_A_STAGE;
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2u * (uint32_t)KC3_A_STAGE);
+                        tma_load_2d_2sm(st, wh, a * 32, nt * 128, &full_bar[stage]);
+                        tma_load_2d_2sm(st + KC2_A_BYTES, wl, a * 32, nt * 128, &full_bar[stage]);
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+                } else
                 for (int a = 0; a < NATOM; ++a) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     KC_STAMP(0, it_no, 1 + a);
@@ -553,12 +609,45 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             constexpr uint32_t idesc = F16 ? umma_idesc_f16(256, 256) : umma_idesc_tf32(256, 256);
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             [[maybe_unused]] int it_no = 0;
-            for (int item = pair_id; item < total_items; item += n_clusters, ++it_no) {
+            [[maybe_unused]] int cur_tile = -1;
+            [[maybe_unused]] uint32_t n_tiles_used = 0, bb = 0;
+            auto tile_of = [&](int item) -> int { return item < i_hi ? (item / items_per_blk) * f_tiles + (item % items_per_blk) / n_pairs : -1; };
+            for (int item = i_lo; item < i_hi; item += i_step, ++it_no) {
                 KC_STAMP(1, it_no, 0);
+                if constexpr (RES) {
+                    if (tile_of(item) != cur_tile) {
+                        cur_tile = tile_of(item);
+                        bb = n_tiles_used & 1u;
+                        mbar_wait(&bfull_bar[bb], (n_tiles_used >> 1) & 1u);
+                        ++n_tiles_used;
+                    }
+                }
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 KC_STAMP(1, it_no, 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
+                if constexpr (RES) {
+                    const uint32_t bt = smem_u32(smem + KC3_ASTAGES * KC3_A_STAGE) + bb * KC3_B_BUF;
+                    for (int a = 0; a < NATOM; ++a) {
+                        mbar_wait(&full_bar[stage], phase);
+                        KC_STAMP(1, it_no, 2 + a);
+                        tc_fence_after();
+                        const uint32_t st = smem_u32(smem + stage * KC3_A_STAGE);
+                        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + KC2_A_BYTES);
+                        // tap a of the im2col = the tile's rows shifted by a: start address + a * 128 B, base_offset 0
+                        const uint64_t b_hi = umma_desc_sw128(bt + a * 128), b_lo = umma_desc_sw128(bt + KC3_B_PIECE + a * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            umma_f16_2sm(d_tmem, a_hi + adv, b_hi + adv, idesc, (a | k) ? 1u : 0u);
+                            umma_f16_2sm(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                            umma_f16_2sm(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+                        }
+                        tc_commit_2sm(&empty_bar[stage]);
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+                    if (tile_of(item + 1) != cur_tile) tc_commit_2sm(&bempty_bar[bb]);   // the tile's last item: its buffer goes back once these MMAs are done
+                } else
                 for (int a = 0; a < NATOM; ++a) {
                     mbar_wait(&full_bar[stage], phase);
                     KC_STAMP(1, it_no, 2 + a);
@@ -600,19 +689,19 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
         // the bias of the NEXT item is loaded one item ahead: a dependent global load at the top of every item (~1,000 of the ~7,000 cycles an
         // item's epilogue took) sat between the accumulator hand-over and the first store (round-2 GEMM timeline)
         auto bias_of = [&](int item) -> float {
-            if (item >= total_items) return 0.f;
+            if (item >= i_hi) return 0.f;
             const int blk = item / items_per_blk, nt = ((item % items_per_blk) % n_pairs) * 2 + (int)rank;
             const float* bias = blk == 0 ? bias0 : (blk == 1 ? bias1 : bias2);
             return bias[nt * 128 + q * 32 + lane];
         };
-        float bv_next = bias_of(pair_id);
-        for (int item = pair_id; item < total_items; item += n_clusters, ++it_no) {
+        float bv_next = bias_of(i_lo);
+        for (int item = i_lo; item < i_hi; item += i_step, ++it_no) {
             const int blk = item / items_per_blk, r = item % items_per_blk;
             const int ft = r / n_pairs, nt = (r % n_pairs) * 2 + (int)rank;
             const int n = nt * 128 + q * 32 + lane;
             if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 0);
             const float bv = bv_next;
-            bv_next = bias_of(item + n_clusters);
+            bv_next = bias_of(item + i_step);
             const float inv = F16 ? (blk == 0 ? inv0 : (blk == 1 ? inv1 : inv2)) : 1.f;
             float* kern = kern_all + (size_t)blk * B * Tm * KCN;
             // F16, blocks 1 and 2 (tensor-core LVC consumers): the predicted kernel w is written as fp16 pieces of w*S16_KERN straight
@@ -730,6 +819,23 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                 if (as_pieces) {
                     uint16_t* ph = reinterpret_cast<uint16_t*>(o) + hw_hi;
                     uint16_t* pl = reinterpret_cast<uint16_t*>(o) + hw_lo;
+                    if constexpr (CPW == 64 && RES && KC_EARLY_RELEASE) {
+                        // both 32-column halves go to registers first: the accumulator stage returns to the MMA issuer ~half an item's store
+                        // time earlier than with load / store / load / store (the hand-over, not the store rate, sets this kernel's pace)
+                        uint32_t v0[32], v1[32];
+                        tmem_ld_32x32b_x32(taddr, v0);
+                        tmem_ld_32x32b_x32(taddr + 32, v1);
+                        tmem_ld_wait();
+                        release_acc();
+                        if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 2);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) put_pieces(ph + (size_t)j * (2 * KCN), pl + (size_t)j * (2 * KCN), __uint_as_float(v0[j]));
+                        if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 3);
+                        ph += (size_t)64 * KCN; pl += (size_t)64 * KCN;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) put_pieces(ph + (size_t)j * (2 * KCN), pl + (size_t)j * (2 * KCN), __uint_as_float(v1[j]));
+                        if (warp == 2 && lane == 0) KC_STAMP(2, it_no, 5);
+                    } else
 #pragma unroll 1
                     for (int c0 = 0; c0 < CPW; c0 += 32) {
                         uint32_t v[32];
@@ -744,6 +850,18 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                     }
                 } else {
                     o += word;
+                    if constexpr (CPW == 64 && RES && KC_EARLY_RELEASE) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld_32x32b_x32(taddr, v0);
+                        tmem_ld_32x32b_x32(taddr + 32, v1);
+                        tmem_ld_wait();
+                        release_acc();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[(size_t)j * KCN] = F16 ? fmaf(__uint_as_float(v0[j]), inv, bv) : __uint_as_float(v0[j]) + bv;
+                        o += (size_t)32 * KCN;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) o[(size_t)j * KCN] = F16 ? fmaf(__uint_as_float(v1[j]), inv, bv) : __uint_as_float(v1[j]) + bv;
+                    } else
 #pragma unroll 1
                     for (int c0 = 0; c0 < CPW; c0 += 32) {
                         uint32_t v[32];
@@ -761,12 +879,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                 // sub-chunk there is one record base, at most one gap (rows j1, j1 + 1 skipped, later rows shifted by two records), possibly a leading
                 // pad row and a row limit -- all warp-uniform.  (The generic per-row walk below cost ~14,000 cycles per item against ~5,000 for the
                 // straight path and set the pace of the whole kernel: round-2 GEMM timeline.)
-#pragma unroll 1
-                for (int c0 = 0; c0 < CPW; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(taddr + c0, v);
-                    tmem_ld_wait();
-                        if (c0 + 32 >= CPW) release_acc();   // the accumulator is in registers: hand it back before the stores
+                auto gap_chunk = [&](const int c0, const uint32_t (&v)[32]) {
                     // (broadcast from lane 0 so that ptxas KNOWS these are warp-uniform: uniform predicates and branches, no per-store R2UR)
                     const int pc = __shfl_sync(0xffffffffu, p + c0, 0), cen = pc + 1, bbc = cen / (Tm + 2), fpc = cen % (Tm + 2);
                     const int j1 = Tm + 1 - fpc, jlo = fpc == 0 ? 1 : 0, jhi = M - pc;   // end pad row; leading pad row; rows past the end
@@ -802,6 +915,24 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                             if (j >= jlo && j < ja) oa[(size_t)j * KCN] = val;
                             else if (j > j1 + 1 && j < jhi) ob[(size_t)j * KCN] = val;
                         }
+                    }
+                };
+                if constexpr (CPW == 64 && RES && KC_EARLY_RELEASE) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld_32x32b_x32(taddr, v0);
+                    tmem_ld_32x32b_x32(taddr + 32, v1);
+                    tmem_ld_wait();
+                    release_acc();
+                    gap_chunk(0, v0);
+                    gap_chunk(32, v1);
+                } else {
+#pragma unroll 1
+                    for (int c0 = 0; c0 < CPW; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x32(taddr + c0, v);
+                        tmem_ld_wait();
+                        if (c0 + 32 >= CPW) release_acc();   // the accumulator is in registers: hand it back before the stores
+                        gap_chunk(c0, v);
                     }
                 }
             } else {   // tiny utterances (several boundaries per sub-chunk): generic per-row walk
@@ -923,7 +1054,7 @@ static inline int tc_init(void** state, int device, const float* blob, const uin
 // hk_hi / hk_lo: (3, B, T'+2, 64) each, written by k_kp_hidden.
 // kimg (mode tc_3xf16): 1 = blocks 1, 2 written in the merged-N image of k_lvc_p (exp_mask bit 64), 0 = the [hi | lo] row image of k_lvc_layer_h
 static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const float* hk_lo, float* kern, int B, int Tm, cudaStream_t st,
-                             std::string& err, uint64_t* launches, int b0_pieces = 0, int kimg = 0) {
+                             std::string& err, uint64_t* launches, int b0_pieces = 0, int kimg = 0, int res = 0, int max_clusters = 0) {
     TcState* s = (TcState*)state;
     if (!s || !s->ok) { err = "tensor-core path not initialised"; return -4; }
     if (b0_pieces && mode == FD_MODE_TC_3XF16 && !s->b0p_ready) {   // experimental path: maps + attribute on first use only
@@ -932,6 +1063,8 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
         if (tc_make_map_2d(s, &s->w16p_lo, w16 + (size_t)KCN * (KCK / 2), KCK / 2, KCN, KCK * 2, KCG_KATOM, KCG_BM, err)) return -3;
         cudaError_t ea = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
         if (ea != cudaSuccess) { err = std::string("k_kc_gemm_tc2<f16, b0 pieces>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
+        ea = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC3_SMEM_BYTES);
+        if (ea != cudaSuccess) { err = std::string("k_kc_gemm_tc2<f16, b0 pieces, resident tile>: shared-memory attribute: ") + cudaGetErrorString(ea); return -3; }
         s->b0p_ready = 1;
     }
     KcgMaps maps;
@@ -943,19 +1076,29 @@ static inline int tc_kc_gemm(void* state, int mode, const float* hk_hi, const fl
     }
     const int M = B * (Tm + 2) - 2;
     if (mode == FD_MODE_TC_3XF16) {   // fp16 pieces: hk rows are 64 fp16 = 32 fp32-sized elements = one 128-byte k-atom
+        const bool res_form = res != 0;
         for (int n = 0; n < NBLK; ++n) {
             maps.w_hi[n] = s->w16_hi[n]; maps.w_lo[n] = s->w16_lo[n];
-            if (tc_make_map_2d(s, &maps.h_hi[n], hk_hi + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128, err)) return -3;
-            if (tc_make_map_2d(s, &maps.h_lo[n], hk_lo + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, 128, err)) return -3;
+            // (resident form: one 130-row box per frame tile and piece -- the three im2col taps are shifted views of it)
+            if (tc_make_map_2d(s, &maps.h_hi[n], hk_hi + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, res_form ? KC3_BROWS : 128, err)) return -3;
+            if (tc_make_map_2d(s, &maps.h_lo[n], hk_lo + (size_t)n * rows * (HID / 2), HID / 2, rows, HID * 2, KCG_KATOM, res_form ? KC3_BROWS : 128, err)) return -3;
         }
         const int items = NBLK * (KCN / 256) * ((M + 255) / 256);
         int clusters = s->sm_count / 2; if (items < clusters) clusters = items;
+        if (max_clusters > 0 && clusters > max_clusters) clusters = max_clusters;
         float inv[NBLK];
         for (int n = 0; n < NBLK; ++n) inv[n] = 1.f / (s->scales16[n] * S16_HK);
-        if (b0_pieces) {
+        if (b0_pieces && res_form) {
+            maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
+            fd_launch_pdl(k_kc_gemm_tc2<true, 16, true, true>, dim3(2 * clusters), dim3(64 + 32 * 16), KC3_SMEM_BYTES, st, maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                                      s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp | (kimg ? 64 : 0));
+        } else if (b0_pieces) {
             maps.w_hi[0] = s->w16p_hi; maps.w_lo[0] = s->w16p_lo;
             fd_launch_pdl(k_kc_gemm_tc2<true, 16, true>, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, s->blob + s->sec_off[FD_S_LB0_KC_BP], s->blob + s->sec_off[FD_S_LB1_KC_B],
                                                                       s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp | (kimg ? 64 : 0));
+        } else if (res_form) {
+            fd_launch_pdl(k_kc_gemm_tc2<true, 16, false, true>, dim3(2 * clusters), dim3(64 + 32 * 16), KC3_SMEM_BYTES, st, maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
+                                                                  s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp | (kimg ? 64 : 0));
         } else
         fd_launch_pdl(k_kc_gemm_tc2<true, 16>, dim3(2 * clusters), dim3(64 + 32 * 16), KC2_SMEM_BYTES, st, maps, s->blob + s->sec_off[FD_S_LB0_KC_B], s->blob + s->sec_off[FD_S_LB1_KC_B],
                                                                   s->blob + s->sec_off[FD_S_LB2_KC_B], kern, B, Tm, 1, inv[0], inv[1], inv[2], s->kc_exp | (kimg ? 64 : 0));
@@ -2878,6 +3021,8 @@ static inline cudaError_t tc_set_lvc_attrs() {
     e0 = cudaFuncSetAttribute(k_kc_gemm_tc2<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC2_SMEM_BYTES);
+    if (e0 != cudaSuccess) return e0;
+    e0 = cudaFuncSetAttribute(k_kc_gemm_tc2<true, 16, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, KC3_SMEM_BYTES);
     if (e0 != cudaSuccess) return e0;
     e0 = cudaFuncSetAttribute(k_upsample_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ut_smem_bytes<4>());
     if (e0 != cudaSuccess) return e0;

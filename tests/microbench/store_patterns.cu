@@ -27,14 +27,18 @@ __global__ void __launch_bounds__(512, 1) k_store(unsigned char* __restrict__ ou
         __syncthreads();
     }
     const int total = NPAIR * FT;
-    for (int item = pair; item < total; item += npairs) {
+    // V9: the same 2 x st.b16 form as V1, but every CTA pair walks a CONTIGUOUS range of the (frame tile, n tile) sequence -- it stays on one 256-frame
+    // tile for ~97 items (the operand tile of those frames could then stay resident in shared memory) instead of the 74 pairs sharing one frame tile
+    const int i_lo = V == 9 ? (int)((long long)total * pair / npairs) : pair, i_hi = V == 9 ? (int)((long long)total * (pair + 1) / npairs) : total;
+    const int i_step = V == 9 ? 1 : npairs;
+    for (int item = i_lo; item < i_hi; item += i_step) {
         const int ft = item / NPAIR, nt = item % NPAIR;
-        if (V == 1 || V == 2) {          // the GEMM's form: a warp owns one 128-byte row of the record (q) for 64 frames (cpart)
+        if (V == 1 || V == 2 || V == 9) {          // the GEMM's form: a warp owns one 128-byte row of the record (q) for 64 frames (cpart)
             unsigned char* base = out + (size_t)(ft * 256 + cpart * 64) * REC + (size_t)nt * 1024 + rank * 512 + q * 128;
 #pragma unroll 8
             for (int j = 0; j < 64; ++j) {
                 unsigned char* r = base + (size_t)j * REC;
-                if (V == 1) {
+                if (V == 1 || V == 9) {
                     *reinterpret_cast<uint16_t*>(r + lane * 2) = (uint16_t)0x3c00;
                     *reinterpret_cast<uint16_t*>(r + 64 + lane * 2) = (uint16_t)0x3c00;
                 } else {
@@ -117,5 +121,7 @@ int main() {
     run<5>("tile-major layout, cp.async.bulk 16 KB (128 KB contiguous per CTA tile)", buf, bytes);
     run<6>("tile-major layout, st.v4 coalesced", buf, bytes);
     run<7>("tile-major layout, 2 x st.b16 per value", buf, bytes);
+    run<9>("record layout, 2 x st.b16 per value, contiguous item range per CTA pair (frame tile resident)", buf, bytes);
+    run<1>("record layout, 2 x st.b16 per value (again)", buf, bytes);
     return 0;
 }

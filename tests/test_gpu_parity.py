@@ -135,6 +135,42 @@ def test_kernel_conv_gemm_utterance_boundaries(synth, cuda_lib, B, Tm):
 
 
 @gpu
+def test_kernel_conv_gemm_forms_agree(synth, cuda_lib):
+    """k_kc_gemm_tc2 on the device: the resident-frame-tile form (option `kc_res` = 1) against the default whole-stage ring (`kc_res` = 0) -- the same
+    MMAs in the same order, so the same bits -- with the CTA-pair count capped (`kc_clusters`) so that one pair walks all 12 frame tiles
+    (both tile buffers reused many times), 5 pairs split tiles unevenly, and the default 74.  Every variant runs at its own diffusion
+    step followed by the reference form at that step, so a skipped item would show."""
+    from fastdiff_b200.synthetic import make_inputs
+    sd, _ = synth
+    net = _net(sd, "tc_3xf16")
+    B, Tm = 4, 200                      # 806 padded rows: four frame tiles per block
+    x, mel = make_inputs(B, Tm, 9)
+    xd, md = x.cuda(), mel.cuda()
+    net((xd, md, torch.full((B, 1), 3.0).cuda()))
+    eng = net.engine()
+
+    def run(res, clusters, t):
+        eng.set_option("kc_res", res)
+        eng.set_option("kc_clusters", clusters)
+        net((xd, md, t.cuda()))
+        return [eng.debug_read(f"kernels{n}", B, Tm).cpu() for n in range(3)] + [eng.debug_read(f"kbias{n}", B, Tm).cpu() for n in range(3)]
+
+    prev = None
+    for i, (res, clusters) in enumerate(((1, 0), (1, 1), (1, 5), (1, 37), (0, 7))):
+        t = torch.tensor([7.413235, 498.0537, 74.99228, 23.46759]).reshape(B, 1) + 13.0 * i
+        got = run(res, clusters, t)
+        want = run(0, 0, t)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), (res, clusters)
+        if prev is not None:
+            assert not torch.equal(got[1], prev[1])
+        prev = got
+    eng.set_option("kc_res", 0)
+    eng.set_option("kc_clusters", 0)
+    assert not eng.check_saturation()
+
+
+@gpu
 @pytest.mark.parametrize("B,Tm", [(2, 33), (1, 130)])
 def test_round2_kernel_options_agree(synth, cuda_lib, B, Tm):
     """The alternatives kept behind run-time options against the default path, on the device: `up4` = 0 (k_upsample_tc<4, POUT> instead of
@@ -151,8 +187,8 @@ def test_round2_kernel_options_agree(synth, cuda_lib, B, Tm):
     xd, md, td = x.cuda(), mel.cuda(), t.cuda()
     base = net((xd, md, td)).cpu()
     assert (base - eps_ref).abs().max() < EPS_TOL
-    for key, val, bitwise, tol in (("pdl", 1, True, 0.0), ("up4", 0, False, 1e-5), ("final_w", 1, False, 1e-5), ("lvc_p", 0, False, 1e-5)):
-        default = {"pdl": 0, "up4": 1, "final_w": 0, "lvc_p": 1}[key]
+    for key, val, bitwise, tol in (("pdl", 1, True, 0.0), ("kc_res", 1, True, 0.0), ("up4", 0, False, 1e-5), ("final_w", 1, False, 1e-5), ("lvc_p", 0, False, 1e-5)):
+        default = {"pdl": 0, "kc_res": 0, "up4": 1, "final_w": 0, "lvc_p": 1}[key]
         eng.set_option(key, val)
         out = net((xd, md, td)).cpu()
         eng.set_option(key, default)
