@@ -368,8 +368,13 @@ extern "C" int fd_set_option(fd_handle* h, const char* key, int64_t value) {
 #ifndef FD_EMU
     if (!strcmp(key, "lvc_swizzle")) { tc_set_lvc_swizzle(h->tc_state, (int)value); return FD_OK; }
     if (!strcmp(key, "kc_2cta")) { tc_set_kc_2cta(h->tc_state, (int)value); return FD_OK; }
-    if (!strcmp(key, "lvc_exp")) { tc_set_lvc_exp(h->tc_state, (int)value); return FD_OK; }
-    if (!strcmp(key, "kc_exp")) { tc_set_kc_exp(h->tc_state, (int)value); return FD_OK; }
+    if (!strcmp(key, "lvc_exp") || !strcmp(key, "kc_exp")) {
+        // masks that switch parts of the arithmetic or of the stores off to time what is left: wrong results by construction
+        if (value != 0 && !getenv("FASTDIFF_B200_TIMING_EXPERIMENTS"))
+            return fail(h, FD_ERR_INVALID, "fd_set_option: %s is a timing-experiment mask (wrong results by construction); set FASTDIFF_B200_TIMING_EXPERIMENTS=1 to allow it", key);
+        if (key[0] == 'l') tc_set_lvc_exp(h->tc_state, (int)value); else tc_set_kc_exp(h->tc_state, (int)value);
+        return FD_OK;
+    }
 #endif
     return fail(h, FD_ERR_INVALID, "fd_set_option: unknown key '%s'", key);
 }

@@ -202,6 +202,20 @@ def test_round2_kernel_options_agree(synth, cuda_lib, B, Tm):
 
 
 @gpu
+def test_timing_experiment_masks_are_refused(synth, cuda_lib, monkeypatch):
+    """`kc_exp` / `lvc_exp` switch parts of the arithmetic off to time the rest (wrong results by construction): the library refuses them
+    unless FASTDIFF_B200_TIMING_EXPERIMENTS is set, and 0 (off) is always accepted."""
+    from fastdiff_b200._lib import FdError
+    sd, _ = synth
+    eng = _net(sd, "tc_3xf16").engine()
+    monkeypatch.delenv("FASTDIFF_B200_TIMING_EXPERIMENTS", raising=False)
+    for key in ("kc_exp", "lvc_exp"):
+        with pytest.raises(FdError):
+            eng.set_option(key, 1)
+        eng.set_option(key, 0)
+
+
+@gpu
 def test_f16_mode_options_and_guards(synth, cuda_lib):
     """tc_3xf16 building blocks: the tensor-core kernel-predictor stack against the FFMA one, the side-stream overlap against the
     serial order (bitwise), the cross_check guard, and saturation (finite output, flagged by cross_check) beyond the fp16 range."""
