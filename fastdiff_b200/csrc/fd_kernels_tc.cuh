@@ -476,14 +476,11 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive 
 // K = 16, and the epilogue undoes the scales: kern = acc * inv[blk] + bias.  Half the MMAs and half the operand bytes of the
 // tf32 variant for the same 22 significant bits per operand.
 #ifndef KC_STORE_CS
-#define KC_STORE_CS 0     // 1: streaming (evict-first) cache hint on the predicted-kernel stores
-#endif
+#define KC_STORE_CS 1     // 1: streaming (evict-first) cache hint on the predicted-kernel piece stores: the 2 GB stream then does not push the operand
+#endif                    //    tiles out of L2 -- GEMM prefix of a reverse step 0.776 -> 0.750 ms in the 2 s power-profile loops, same joules (profiles/r02_energy_ab.txt)
 #ifndef KC_EARLY_RELEASE
 #define KC_EARLY_RELEASE 1   // 1 (RES form only): an epilogue warp reads all of its 64 accumulator columns before its first store and releases the stage
                              // right away.  With the whole-stage ring this was SLOWER (2.60 vs 2.33 ms per call): the operand fetch of the next item became the wait.
-#endif
-#ifndef KC_STORE_SHFL
-#define KC_STORE_SHFL 0   // 1: adjacent lanes swap one piece and store 32-bit words (one 128-byte line per warp store) instead of two 16-bit stores
 #endif
 // EPW = epilogue warps per CTA (8 or 16: EPW/4 per TMEM lane quarter, each taking 256/(EPW/4) of the 256 frame columns).
 // B0P (experimental, option "tc_b0" = 1): block 0's predicted kernels are written as fp16 pieces as well (its weight rows then come
@@ -733,7 +730,7 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
                         hw_lo = base + (((4 + (ci >> 3)) ^ sw) << 3);
                     }
                 } else {
-                const int base = 2 * ((n - rem) + ko * 32) + (KC_STORE_SHFL ? (ci & 6) : (ci & 7));
+                const int base = 2 * ((n - rem) + ko * 32) + (ci & 7);
                 hw_hi = base + (((ci >> 3) ^ (oo & 7)) << 3);
                 hw_lo = base + (((4 + (ci >> 3)) ^ (oo & 7)) << 3);
                 }
@@ -742,28 +739,16 @@ k_kc_gemm_tc2(const __grid_constant__ KcgMaps maps, const float* __restrict__ bi
             // warp-uniform; broadcast from lane 0 so that ptxas KNOWS it (otherwise every store below re-materialises its uniform
             // memory descriptor with two R2UR: 40% of the epilogue's instructions)
             const bool as_pieces = __shfl_sync(0xffffffffu, (int)(pieces && is_w), 0) != 0;
-            [[maybe_unused]] const int odd = lane & 1;
             auto put_pieces = [&](uint16_t* ph, uint16_t* pl, float accv) {
                 const float sv = fmaf(accv, inv_s, bv_s);
-                uint16_t l16;
                 const uint16_t h16 = f16_sat_bits(sv);
-#if KC_STORE_SHFL
-                // even lane (element i) keeps the hi halves of (i, i+1), odd lane the lo halves; ph/pl point at the even element's halfword
-                const float hi_f = f16_bits_to_float(h16), lo_f = sv - hi_f;
-                const float recv = __shfl_xor_sync(0xffffffffu, odd ? hi_f : lo_f, 1);
-                uint32_t packed;
-                packed = pack_f16x2_sat(odd ? lo_f : recv, odd ? recv : hi_f);
-                *reinterpret_cast<uint32_t*>(odd ? pl : ph) = packed;
-                (void)l16;
-#else
-                l16 = f16_sat_bits(sv - f16_bits_to_float(h16));
-#if KC_STORE_CS
+                const uint16_t l16 = f16_sat_bits(sv - f16_bits_to_float(h16));
+#if KC_STORE_CS && !defined(FD_EMU)
                 asm volatile("st.global.cs.b16 [%0], %1;" ::"l"(ph), "h"(h16) : "memory");
                 asm volatile("st.global.cs.b16 [%0], %1;" ::"l"(pl), "h"(l16) : "memory");
 #else
                 *ph = h16;
                 *pl = l16;
-#endif
 #endif
             };
             int p = ft * 256 + cpart * CPW;

@@ -1,5 +1,5 @@
 """Energy per kernel class of one reverse step at config 2 on a B200 (NOT collected by pytest):
-    python tests/gpu_scripts/power_profile.py
+    python tests/gpu_scripts/power_profile.py [prefix ...]
 The denoiser is run as growing prefixes (`stop_after` = 1 .. 99) in a loop of ~2 s each; NVML's total-energy counter and the wall clock give
 joules and milliseconds per iteration, the differences between prefixes the share of each class; SM clocks are sampled while the loop runs."""
 import sys
@@ -39,7 +39,8 @@ names = {1: "embed + kernel predictor + kernel_conv GEMM", 2: "+ DBlocks (+ bloc
          5: "+ upsample 2 + LVC block 2", 99: "+ final conv + update (whole reverse step)"}
 prev_e = prev_t = 0.0
 print("prefix | ms/iter | J/iter | avg W | SM MHz (median while running) | class: ms, J, W")
-for stop in (1, 2, 3, 4, 5, 99):
+stops = tuple(int(a) for a in sys.argv[1:]) or (1, 2, 3, 4, 5, 99)   # optional: the prefixes to run (differences are then between those)
+for stop in stops:
     eng.set_option("stop_after", stop)
     for _ in range(20):
         net(data)
