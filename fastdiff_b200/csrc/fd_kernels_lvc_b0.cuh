@@ -107,7 +107,7 @@ k_lvc_layer_b0h(LvcHParams p, const float* __restrict__ x_in, const float* __res
             if (f0 + h >= Tm) continue;
             const float* src = kern + ((size_t)b * Tm + f0 + h) * KCN;
             for (int k = 0; k < 3; ++k)
-                bulk_g2s(ring + slot * LB0_PAIR_BYTES + k * 16384 + h * 8192, src + k * 2048, 8192, &ring_full[slot]);
+                bulk_g2s_once(ring + slot * LB0_PAIR_BYTES + k * 16384 + h * 8192, src + k * 2048, 8192, &ring_full[slot]);
         }
     };
 

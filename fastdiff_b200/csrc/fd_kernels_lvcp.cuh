@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                         const int ws = wc & 1;
                         mbar_wait(&w_free[ws], (uint32_t)(((wc >> 1) & 1) ^ 1));
                         mbar_expect_tx(&w_full[ws], 24576u);
-                        bulk_g2s(w_t + ws * W_BYTES, p.kern + ((size_t)b * Tm + f0) * KCN, 24576u, &w_full[ws]);
+                        bulk_g2s_once(w_t + ws * W_BYTES, p.kern + ((size_t)b * Tm + f0) * KCN, 24576u, &w_full[ws]);
                         ++wc;
                     }
                     new_frame = !(tt & 1);      // the next tile (b, tt - 1) shares this frame iff tt is odd
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(LP_THREADS, 1) k_lvc_p(const LvcPParams p) {
                             const float* kf = p.kern + ((size_t)b * Tm + f0 + fi) * KCN;
 #pragma unroll
                             for (int part = 0; part < 3; ++part)
-                                bulk_g2s(w_t + ws * W_BYTES + part * 16384 + fi * 8192, kf + part * 2048, 8192u, &w_full[ws]);
+                                bulk_g2s_once(w_t + ws * W_BYTES + part * 16384 + fi * 8192, kf + part * 2048, 8192u, &w_full[ws]);
                         }
                 }
                 if (--tt < 0) { tt = ntt - 1; --b; new_frame = true; }

@@ -1164,6 +1164,21 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// The predicted-kernel tensor is read exactly once per reverse step (2 GB at config 2): an evict-first L2 policy on those loads keeps the stream
+// from displacing the activation rows the next layer re-reads and the weight images (LVC_KERN_EF, measured: profiles/r02_energy_ab.txt).
+#ifndef LVC_KERN_EF
+#define LVC_KERN_EF 1
+#endif
+__device__ __forceinline__ void bulk_g2s_once(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+#if LVC_KERN_EF
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+#else
+    bulk_g2s(smem_dst, gsrc, bytes, bar);
+#endif
+}
 #endif  // !FD_EMU
 // ---- small helpers shared by the kernels that also compile for the emulator ----
 template <int N> __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[N]);

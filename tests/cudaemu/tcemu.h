@@ -79,6 +79,7 @@ inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t*
     emu_mbar_complete_tx(bar, bytes);
 }
 inline void bulk_prefetch_l2(const void*, uint32_t) {}
+inline void bulk_g2s_once(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) { bulk_g2s(smem_dst, gsrc, bytes, bar); }   // (L2 policy hint: no functional effect)
 // shared -> global bulk copy (bulk async-groups).  The model performs the copy as LATE as the program allows -- when the issuing thread
 // executes wait_group(.read) -- so a staging buffer that is overwritten before its copies were waited for delivers the wrong bytes and
 // the parity tests see it (the adversarial schedule for source-reuse hazards).  A kernel must end with bulk_wait_all() in every issuing
