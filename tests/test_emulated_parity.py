@@ -141,17 +141,16 @@ def test_emulated_tensor_core_sampler_vs_oracle(synth, emu_lib):
 def test_emulated_kernel_conv_gemm_forms_agree(synth, emu_lib):
     """k_kc_gemm_tc2, resident-frame-tile form (option `kc_res` = 1: contiguous item range per CTA pair, one 130-row tile per piece serving the
     three im2col taps through shifted descriptor starts, two tile buffers, 4-stage weight ring, early accumulator release) against the
-    default whole-stage ring (`kc_res` = 0): the same MMAs in the same order, so the same bits.  `kc_clusters` = 1 makes ONE pair walk all six frame
-    tiles (both tile buffers reused, barrier parities wrap), 3 splits the range inside tiles."""
+    default whole-stage ring (`kc_res` = 0): the same MMAs in the same order, so the same bits.  `kc_clusters` = 1 makes ONE pair walk all three frame
+    tiles (a tile buffer is reused: the producer waits for the MMA issuer's release), 3 splits the range inside tiles."""
     from fastdiff_b200.synthetic import make_inputs
     sd, _ = synth
     net = _net(sd, emu_lib)
     net.mode = "tc_3xf16"
-    B, Tm = 2, 129                      # 260 padded rows: two frame tiles per block
+    B, Tm = 1, 129                      # one frame tile per block: three tiles in all (the GPU test walks twelve)
     x, mel = make_inputs(B, Tm, 9)
-    net((x, mel, torch.tensor([[1.0], [2.0]])))
     eng = net.engine()
-    eng.set_option("stop_after", 2)     # embedding + kernel predictor: the GEMM's output is what is compared
+    eng.set_option("stop_after", 1)     # embedding + kernel predictor + GEMM: the GEMM's output is what is compared
 
     def run(res, clusters, t):
         eng.set_option("kc_res", res)
@@ -162,7 +161,7 @@ def test_emulated_kernel_conv_gemm_forms_agree(synth, emu_lib):
     # every variant runs at its OWN diffusion step, followed by the whole-stage ring at the same step: an item a variant skipped would
     # keep the previous step's value and differ
     for i, (res, clusters) in enumerate(((1, 1), (1, 3))):
-        t = torch.tensor([[7.413235 + 40.0 * i], [498.0537 - 55.0 * i]])
+        t = torch.tensor([[7.413235 + 40.0 * i]])
         got = run(res, clusters, t)
         want = run(0, 0, t)
         for a, b in zip(got, want):
