@@ -37,6 +37,19 @@ struct Up4Params {
     float inv;               // 1 / (S16_ACT * SCALES16[41])
 };
 
+#ifndef U4_STORE32
+#define U4_STORE32 1   // 1: 256-bit stores of whole 32-byte sectors in the epilogue (thread = 16 channels x 2 phases); 0: 16-byte stores (8 channels x 4 phases)
+#endif
+// 32 bytes (two 16-byte chunks) to a 32-byte aligned global address
+__device__ __forceinline__ void st_global_u8(float* p, const uint4 a, const uint4 b) {
+#if FD_VEC256 && !defined(FD_EMU)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+#else
+    *reinterpret_cast<uint4*>(p) = a;
+    *reinterpret_cast<uint4*>(p + 4) = b;
+#endif
+}
 __global__ void __launch_bounds__(512, 2) k_upsample_p4(const Up4Params p) {
     pdl_trigger();
 
@@ -169,6 +182,43 @@ __global__ void __launch_bounds__(512, 2) k_upsample_p4(const Up4Params p) {
         mbar_wait(&bar[0], parity);
         tc_fence_after();
         if (gw_u == 0 && tile + (int)gridDim.x < total) { if (elect_one()) issue_loads(tile + gridDim.x, parity ^ 1u); __syncwarp(); }   // raw rows are free
+#if U4_STORE32
+        // ---- phase 3: epilogue: thread = (input row m, 16 channels, 2 of the 4 phases).  The two 8-channel chunks of a piece sit in one aligned
+        //      32-byte pair of the swizzled row (chunk c at c ^ (t & 7): the pair base takes bits 1-2 of the XOR, bit 0 swaps the halves), so a
+        //      thread writes whole 32-byte sectors with one 256-bit store per piece instead of half sectors with 16-byte stores ----
+        {
+            const int q = gw & 3, pair = (gw >> 2) & 1, phh = gw >> 3, m = m0 + q * 32 + lane;
+            const float inv16 = p.inv * S16_ACT;
+#pragma unroll
+            for (int pi = 0; pi < 2; ++pi) {
+                const int ph = phh * 2 + pi;
+                uint4 hi[2], lo[2];
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[8], v2[8];
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + ph * 64 + pair * 16 + hf * 8;
+                    tmem_ld_32x32b_x8(ta, v);
+                    tmem_ld_32x32b_x8(ta + 32, v2);
+                    tmem_ld_wait();
+                    float z[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float zz = fmaf(__uint_as_float(v[i]) + __uint_as_float(v2[i]), inv16, b_s[pair * 16 + hf * 8 + i]);   // 16 (up + skip + bias)
+                        z[i] = fmaxf(zz, 0.2f * zz);
+                    }
+                    lp_split8(z, hi[hf], lo[hf], vmax);
+                }
+                if (m < Tin) {
+                    const int t = 4 * m + ph, sw = t & 7, odd = sw & 1;
+                    float* dst = p.p_out + lp_row_of(b, Tout, t) * C;            // 32 fp32-sized words = 128 bytes of pieces
+                    const uint4 h_a = odd ? hi[1] : hi[0], h_b = odd ? hi[0] : hi[1];
+                    const uint4 l_a = odd ? lo[1] : lo[0], l_b = odd ? lo[0] : lo[1];
+                    st_global_u8(dst + (((2 * pair) ^ (sw & 6)) << 2), h_a, h_b);
+                    st_global_u8(dst + (((4 + 2 * pair) ^ (sw & 6)) << 2), l_a, l_b);
+                }
+            }
+        }
+#else
         // ---- phase 3: epilogue: thread = (input row m, 8 channels); its 4 outputs are consecutive rows 4 m + ph ----
         {
             const int q = gw & 3, part = gw >> 2, m = m0 + q * 32 + lane;
@@ -200,6 +250,7 @@ __global__ void __launch_bounds__(512, 2) k_upsample_p4(const Up4Params p) {
                 }
             }
         }
+#endif
         tc_fence_before();
         __syncthreads();
     }
